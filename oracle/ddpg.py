@@ -1,0 +1,262 @@
+"""Oracle: Actor / Critic MLPs and the DDPG off-policy update, NumPy float32.
+
+TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.
+
+Restates with hand-written forward / backward (no autograd):
+  * ``Actor``  src/model.py:7-45,  ``Critic`` src/model.py:48-83
+  * ``DDPG.critic_update`` src/agent.py:1302-1343
+  * ``DDPG.actor_update``  src/agent.py:1288-1300
+  * ``DDPG.update_target_network`` src/agent.py:1255-1271
+  * ``DDPG.update`` src/agent.py:1378-1404 (HER / uniform branch)
+  * ``DDPG.get_gradient_norm`` src/agent.py:1279-1286
+and the torch library semantics those lines rely on (torch 2.11, CPU,
+single-tensor code paths): ``nn.Linear``, ``LeakyReLU(0.01)``, ``Tanh``,
+``mse_loss``, ``clip_grad_norm_``, ``Adam`` / ``AdamW``, ``CosineAnnealingLR``.
+
+Pinned by ``tests/golden/ddpg_*.npz`` produced by the unmodified reference
+``DDPG`` class (see tests/golden/make_golden.py); tolerance rel 1e-5.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+F32 = np.float32
+LEAKY_SLOPE = F32(0.01)
+
+
+# ----------------------------------------------------------------------------
+# parameters
+# ----------------------------------------------------------------------------
+def init_mlp(rng, in_dim, hidden, out_dim, layers):
+    """Xavier-uniform weights, bias 0.01 (src/model.py:39-42). rng: np Generator."""
+    dims = [in_dim] + [hidden] * layers + [out_dim]
+    params = []
+    for i in range(len(dims) - 1):
+        fan_in, fan_out = dims[i], dims[i + 1]
+        bound = math.sqrt(6.0 / (fan_in + fan_out))
+        w = rng.uniform(-bound, bound, size=(fan_out, fan_in)).astype(F32)
+        b = np.full(fan_out, 0.01, dtype=F32)
+        params.append([w, b])
+    return params
+
+
+def clone_params(p):
+    return [[w.copy(), b.copy()] for w, b in p]
+
+
+def zeros_like_params(p):
+    return [[np.zeros_like(w), np.zeros_like(b)] for w, b in p]
+
+
+def state_dict_to_params(sd, prefix):
+    """Reference checkpoint naming: ``base_net.{0,2,..}`` (Actor) / ``net.{..}``
+    (Critic), weight [out,in] row-major fp32 (src/model.py:24-26,64-65)."""
+    idx = sorted({int(k.split(".")[1]) for k in sd if k.startswith(prefix + ".")})
+    return [[np.asarray(sd[f"{prefix}.{i}.weight"], F32).copy(),
+             np.asarray(sd[f"{prefix}.{i}.bias"], F32).copy()] for i in idx]
+
+
+# ----------------------------------------------------------------------------
+# forward / backward
+# ----------------------------------------------------------------------------
+def mlp_forward(params, x, final_tanh):
+    """Returns (output, cache). Hidden layers Linear->LeakyReLU(0.01); last layer
+    Linear (+Tanh for the actor)."""
+    acts = [np.asarray(x, F32)]
+    h = acts[0]
+    n = len(params)
+    for i, (w, b) in enumerate(params):
+        z = (h @ w.T + b).astype(F32)
+        if i < n - 1:
+            h = np.where(z > 0, z, z * LEAKY_SLOPE).astype(F32)
+        else:
+            h = np.tanh(z).astype(F32) if final_tanh else z
+        acts.append(h)
+    return h, acts
+
+
+def mlp_backward(params, acts, d_out, final_tanh, need_input_grad=False):
+    """d_out = dLoss/d(output).  Returns (grads like params, d_input or None)."""
+    n = len(params)
+    grads = zeros_like_params(params)
+    out = acts[-1]
+    dz = (d_out * (F32(1.0) - out * out)).astype(F32) if final_tanh else d_out.astype(F32)
+    d_in = None
+    for i in range(n - 1, -1, -1):
+        w, _ = params[i]
+        x = acts[i]
+        grads[i][0] = (dz.T @ x).astype(F32)
+        grads[i][1] = dz.sum(axis=0).astype(F32)
+        if i > 0 or need_input_grad:
+            dx = (dz @ w).astype(F32)
+            if i > 0:
+                # LeakyReLU backward keyed on the (post-activation) sign: x>0 ? 1 : slope
+                dz = np.where(x > 0, dx, dx * LEAKY_SLOPE).astype(F32)
+            else:
+                d_in = dx
+    return grads, d_in
+
+
+# ----------------------------------------------------------------------------
+# torch optimiser / clip semantics
+# ----------------------------------------------------------------------------
+def grad_norm_python(grads):
+    """src/agent.py:1279-1286: sqrt(sum_p (||g_p||_2 as float)**2) in Python floats."""
+    tot = 0.0
+    for w, b in grads:
+        for g in (w, b):
+            tot += float(np.sqrt(np.sum(np.square(g, dtype=F32), dtype=F32))) ** 2
+    return tot ** 0.5
+
+
+def clip_grad_norm_(grads, max_norm):
+    """torch.nn.utils.clip_grad_norm_ (L2): coef = max_norm/(total+1e-6), clamped
+    to <=1 and ALWAYS multiplied in.  Returns the pre-clip total norm."""
+    norms = np.array([np.sqrt(np.sum(np.square(g, dtype=F32), dtype=F32))
+                      for pair in grads for g in pair], dtype=F32)
+    total = F32(np.sqrt(np.sum(np.square(norms), dtype=F32)))
+    coef = F32(max_norm) / (total + F32(1e-6))
+    coef = F32(min(coef, F32(1.0)))
+    for pair in grads:
+        pair[0] *= coef
+        pair[1] *= coef
+    return float(total)
+
+
+class AdamState:
+    """torch.optim.Adam / AdamW, single-tensor CPU path, betas (0.9, 0.999),
+    eps 1e-8.  weight_decay: 0 for Adam (DDPG, src/agent.py:1201-1202); AdamW
+    default 0.01 decoupled (TD3/SAC/TQC, src/agent.py:46-48)."""
+
+    def __init__(self, params, decoupled_wd=0.0):
+        self.m = zeros_like_params(params)
+        self.v = zeros_like_params(params)
+        self.t = 0
+        self.wd = decoupled_wd
+        self.b1, self.b2, self.eps = 0.9, 0.999, 1e-8
+
+    def step(self, params, grads, lr):
+        self.t += 1
+        bc1 = 1.0 - self.b1 ** self.t
+        bc2 = 1.0 - self.b2 ** self.t
+        step_size = F32(lr / bc1)
+        bc2_sqrt = F32(bc2 ** 0.5)
+        for i in range(len(params)):
+            for j in range(2):
+                p, g = params[i][j], grads[i][j]
+                m, v = self.m[i][j], self.v[i][j]
+                if self.wd:
+                    p *= F32(1.0 - lr * self.wd)
+                m += F32(1.0 - self.b1) * (g - m)                      # lerp_
+                v *= F32(self.b2)
+                v += F32(1.0 - self.b2) * g * g                         # addcmul_
+                denom = np.sqrt(v) / bc2_sqrt + F32(self.eps)
+                p -= step_size * (m / denom)                            # addcdiv_
+
+
+class CosineAnnealingLR:
+    """torch.optim.lr_scheduler.CosineAnnealingLR, recursive (chainable) form as
+    driven by ``scheduler.step()`` once per optimiser step
+    (src/agent.py:1203-1212,1298,1334).  ``lr`` is the rate the NEXT optimiser
+    step will use."""
+
+    def __init__(self, base_lr, T_max, eta_min):
+        self.base_lr, self.T_max, self.eta_min = base_lr, T_max, eta_min
+        self.last_epoch = 0
+        self.lr = base_lr
+
+    def step(self):
+        self.last_epoch += 1
+        e, T = self.last_epoch, self.T_max
+        if (e - 1 - T) % (2 * T) == 0:
+            self.lr = self.lr + (self.base_lr - self.eta_min) * (1 - math.cos(math.pi / T)) / 2
+        else:
+            self.lr = (1 + math.cos(math.pi * e / T)) / (1 + math.cos(math.pi * (e - 1) / T)) \
+                * (self.lr - self.eta_min) + self.eta_min
+        return self.lr
+
+
+# ----------------------------------------------------------------------------
+# DDPG
+# ----------------------------------------------------------------------------
+class DDPGOracle:
+    """State + update rule of ``DDPG`` (src/agent.py:1173-1404) on explicit batches."""
+
+    POLYAK_EVERY = 40  # literal at src/agent.py:1397
+
+    def __init__(self, actor, critic, *, gamma, tau, grad_clip, actor_lr, critic_lr,
+                 actor_lr_min=None, critic_lr_min=None, ac_scheduler_steps=1,
+                 cr_scheduler_steps=1, ac_update_freq=1):
+        self.actor = clone_params(actor)
+        self.critic = clone_params(critic)
+        self.target_actor = clone_params(actor)      # hard sync, :1251-1253
+        self.target_critic = clone_params(critic)
+        self.actor_opt = AdamState(self.actor)
+        self.critic_opt = AdamState(self.critic)
+        self.actor_sched = CosineAnnealingLR(actor_lr, ac_scheduler_steps,
+                                             actor_lr if actor_lr_min is None else actor_lr_min)
+        self.critic_sched = CosineAnnealingLR(critic_lr, cr_scheduler_steps,
+                                              critic_lr if critic_lr_min is None else critic_lr_min)
+        self.gamma, self.tau, self.grad_clip = gamma, tau, grad_clip
+        self.ac_update_freq = ac_update_freq
+
+    # src/agent.py:1302-1343
+    def critic_update(self, s, a, r, ns, d):
+        g = F32(self.gamma)
+        na, _ = mlp_forward(self.target_actor, ns, final_tanh=True)
+        tq, _ = mlp_forward(self.target_critic, np.concatenate([ns, na], -1), final_tanh=False)
+        y = (r + g * (F32(1.0) - d) * tq).astype(F32)
+        y = np.clip(y, F32(-1.0 / (1.0 - self.gamma)), F32(0.0)).astype(F32)
+        q, acts = mlp_forward(self.critic, np.concatenate([s, a], -1), final_tanh=False)
+        B = q.shape[0]
+        diff = (q - y).astype(F32)
+        loss = float(np.mean(diff * diff, dtype=F32))
+        td = float(np.mean(np.abs(y - q), dtype=F32))
+        dq = (F32(2.0) * diff / F32(B)).astype(F32)
+        grads, _ = mlp_backward(self.critic, acts, dq, final_tanh=False)
+        if self.grad_clip is not None:
+            clip_grad_norm_(grads, self.grad_clip)
+        gnorm = grad_norm_python(grads)
+        self.critic_opt.step(self.critic, grads, self.critic_sched.lr)
+        self.critic_sched.step()
+        self.last_critic_grads = grads
+        self.last_y = y
+        return loss, td, float(np.mean(q, dtype=F32)), gnorm
+
+    # src/agent.py:1288-1300
+    def actor_update(self, s):
+        a, a_acts = mlp_forward(self.actor, s, final_tanh=True)
+        q, c_acts = mlp_forward(self.critic, np.concatenate([s, a], -1), final_tanh=False)
+        B = q.shape[0]
+        loss = float(-np.mean(q, dtype=F32))
+        dq = np.full_like(q, F32(-1.0) / F32(B))
+        _, d_in = mlp_backward(self.critic, c_acts, dq, final_tanh=False, need_input_grad=True)
+        d_a = d_in[:, s.shape[1]:]
+        grads, _ = mlp_backward(self.actor, a_acts, d_a, final_tanh=True)
+        if self.grad_clip is not None:
+            clip_grad_norm_(grads, self.grad_clip)
+        self.actor_opt.step(self.actor, grads, self.actor_sched.lr)
+        self.actor_sched.step()
+        self.last_actor_grads = grads
+        return loss, grad_norm_python(grads)
+
+    # src/agent.py:1255-1271
+    def soft_update(self, tau):
+        t = F32(tau)
+        omt = F32(1 - tau)
+        for tgt, src in ((self.target_actor, self.actor), (self.target_critic, self.critic)):
+            for (tw, tb), (w, b) in zip(tgt, src):
+                tw[...] = t * w + omt * tw
+                tb[...] = t * b + omt * tb
+
+    # src/agent.py:1378-1404
+    def update_on_batch(self, step, s, a, r, ns, d):
+        closs, td, qv, cg = self.critic_update(s, a, r, ns, d)
+        if step % self.POLYAK_EVERY == 0:
+            self.soft_update(self.tau)
+        if step % self.ac_update_freq == 0:
+            aloss, agn = self.actor_update(s)
+            return closs, aloss, td, qv, cg, agn
+        return closs, td, qv, cg

@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory from the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference, which does not exist on
+the GPU box):
+
+    python tests/golden/make_golden.py
+
+It imports the reference's own ``src.buffer`` / ``src.agent`` / ``src.utils`` /
+``src.model`` behind a stub ``gymnasium`` module (``src/utils.py:5`` imports it
+at module top; the real package is not installed), drives them with seeded
+synthetic inputs, records every Mersenne-Twister draw the hot path consumes
+(``random.randint`` at src/buffer.py:153, ``random.sample`` at src/buffer.py:124)
+and stores inputs + draws + outputs as small ``.npz`` files.  The parity tests
+replay those inputs/draws through the oracle (CPU) and the CUDA path (GPU).
+
+``compute_reward`` is the one piece that cannot come from the reference tree
+(panda-gym is un-vendored): the generator binds ``panda_reward`` below, the
+published sparse rule written with the same NumPy calls panda-gym uses
+(``np.linalg.norm(a - b, axis=-1)`` then ``-np.array(d > 0.05, float32)``).
+"""
+import os
+import random
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("GCRL_REFERENCE", "/root/reference")
+
+
+def import_reference():
+    g = types.ModuleType("gymnasium")
+
+    class _W:
+        def __init__(self, env=None):
+            self.env = env
+
+    g.Wrapper = _W
+    g.ObservationWrapper = _W
+    g.vector = types.SimpleNamespace(AsyncVectorEnv=object,
+                                     AutoresetMode=types.SimpleNamespace(NEXT_STEP=0))
+    g.spaces = types.SimpleNamespace(Dict=dict, Box=object)
+    sys.modules.setdefault("gymnasium", g)
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import src.agent as agent
+    import src.buffer as buffer
+    import src.model as model
+    import src.utils as utils
+    return agent, buffer, model, utils
+
+
+def panda_reward(achieved_goal, desired_goal, info):
+    d = np.linalg.norm(achieved_goal - desired_goal, axis=-1)
+    return -np.array(d > 0.05, dtype=np.float32)
+
+
+# ----------------------------------------------------------------------------
+# synthetic episodes (SURVEY 8d recipe, small)
+# ----------------------------------------------------------------------------
+def synth_episode(rng, T, O, G, A, terminated_last=False):
+    """Rows exactly as env.py:163-224 hands them to push_her (no normalisation):
+    state = obs_t || dg, next_state = obs_{t+1} || dg, ag = achieved goal of the
+    NEXT observation, reward = sparse reward of the next observation."""
+    obs = rng.standard_normal((T + 1, O)).astype(np.float32)
+    ag = np.empty((T + 1, G), np.float32)
+    ag[0] = rng.uniform(-0.15, 0.15, G)
+    for t in range(T):
+        step = rng.normal(0, 0.02, G) * (rng.random() > 0.3)
+        ag[t + 1] = ag[t] + step.astype(np.float32)
+    dg = rng.uniform(-0.15, 0.15, G).astype(np.float32)
+    act = rng.uniform(-1, 1, (T, A)).astype(np.float32)
+    s = np.concatenate([obs[:-1], np.repeat(dg[None], T, 0)], -1)
+    ns = np.concatenate([obs[1:], np.repeat(dg[None], T, 0)], -1)
+    rew = np.array([panda_reward(ag[t + 1], dg, {}) for t in range(T)], dtype=np.float64)
+    done = np.zeros(T, bool)
+    done[-1] = terminated_last
+    return dict(s=s, a=act, ns=ns, r=rew, d=done, dg=np.repeat(dg[None], T, 0), ag=ag[1:])
+
+
+def her_case(buffer_mod, name, *, O, G, A, k, lens, max_mem_len, nenvs, seed, batches):
+    import torch
+    rng = np.random.default_rng(seed)
+    random.seed(1898 + seed)               # reference default seed, src/main.py:79
+    buf = buffer_mod.HERBuffer(max_mem_len, 50, nenvs, k_future=k)
+    buf.compute_reward = panda_reward
+    draws = []
+    real_randint = random.randint
+
+    def rec_randint(a, b):
+        v = real_randint(a, b)
+        draws.append(v)
+        return v
+
+    out = {}
+    eps = [synth_episode(rng, T, O, G, A, terminated_last=(T < 50)) for T in lens]
+    # interleave the per-env staging like env.py:192: round-robin over envs
+    cursors = [(i, 0) for i in range(min(nenvs, len(eps)))]
+    nxt = len(cursors)
+    slot_of = {i: i for i in range(len(cursors))}   # env slot -> episode id
+    order = []                                      # commit order of episodes
+    buffer_mod.random.randint = rec_randint
+    try:
+        active = dict(slot_of)
+        pos = {e: 0 for e in active.values()}
+        while active:
+            for slot in sorted(active):
+                e = active[slot]
+                ep = eps[e]
+                t = pos[e]
+                n0 = len(draws)
+                buf.push(slot, torch.from_numpy(ep["s"][t]), ep["a"][t],
+                         torch.from_numpy(ep["ns"][t]), ep["r"][t], ep["d"][t],
+                         ep["dg"][t], ep["ag"][t])
+                pos[e] += 1
+                if pos[e] == ep["s"].shape[0]:
+                    T = pos[e]
+                    fut = np.zeros((T, k), np.uint8)
+                    d = draws[n0:]
+                    assert len(d) == (T - 1) * k
+                    if T > 1:
+                        fut[:T - 1] = np.array(d, np.uint8).reshape(T - 1, k)
+                    order.append(e)
+                    out[f"ep{len(order) - 1}_fut"] = fut
+                    for key, val in ep.items():
+                        out[f"ep{len(order) - 1}_{key}"] = val
+                    if nxt < len(eps):
+                        active[slot] = nxt
+                        pos[nxt] = 0
+                        nxt += 1
+                    else:
+                        del active[slot]
+    finally:
+        buffer_mod.random.randint = real_randint
+    out["n_episodes"] = np.int64(len(order))
+    out["len"] = np.int64(len(buf))
+    out["meta"] = np.array([O, G, A, k, max_mem_len, nenvs], np.int64)
+    # full dump of the live deque, entry by entry
+    S, Aa, NS, R, Dn, _, _ = zip(*list(buf.buffer))
+    out["dump_s"] = np.array(S, np.float32)
+    out["dump_a"] = np.array(Aa, np.float32)
+    out["dump_ns"] = np.array(NS, np.float32)
+    out["dump_r"] = np.array([np.float32(x) for x in R], np.float32)
+    out["dump_d"] = np.array([np.float32(bool(x)) for x in Dn], np.float32)
+    # reference sample(): recover the index stream by replaying the MT state
+    for bi, B in enumerate(batches):
+        st = random.getstate()
+        s, a, r, ns, d = buf.sample(B)
+        random.setstate(st)
+        idx = random.sample(range(len(buf)), B)
+        assert np.array_equal(out["dump_s"][idx], s.numpy())
+        out[f"b{bi}_idx"] = np.array(idx, np.int64)
+        out[f"b{bi}_s"] = s.numpy()
+        out[f"b{bi}_a"] = a.numpy()
+        out[f"b{bi}_r"] = r.numpy()
+        out[f"b{bi}_ns"] = ns.numpy()
+        out[f"b{bi}_d"] = d.numpy()
+    out["n_batches"] = np.int64(len(batches))
+    np.savez_compressed(os.path.join(HERE, f"her_{name}.npz"), **out)
+    print(f"her_{name}: {len(order)} episodes, {len(buf)} entries")
+
+
+def reward_case():
+    """Known-answer edge cases + random cases for the restated reward rule."""
+    rng = np.random.default_rng(7)
+    a = rng.uniform(-0.2, 0.2, (4096, 3)).astype(np.float32)
+    b = (a + rng.normal(0, 0.03, (4096, 3))).astype(np.float32)
+    thr = np.float32(0.05)
+    edge = [thr, np.nextafter(thr, np.float32(1)), np.nextafter(thr, np.float32(0)),
+            np.float32(0.0)]
+    ea = np.zeros((len(edge) * 3, 3), np.float32)
+    eb = np.zeros_like(ea)
+    for i, e in enumerate(edge):
+        for ax in range(3):
+            eb[i * 3 + ax, ax] = e
+    a = np.concatenate([a, ea])
+    b = np.concatenate([b, eb])
+    r = panda_reward(a, b, {})
+    np.savez_compressed(os.path.join(HERE, "reward_kat.npz"), a=a, b=b, r=r)
+    print("reward_kat:", r.shape, "success frac", float(np.mean(np.signbit(r) & (r == 0))))
+
+
+def normalizer_case(utils_mod):
+    rng = np.random.default_rng(11)
+    out = {}
+    for tag, dim, dtype in (("obs", 19, np.float64), ("dg", 3, np.float32)):
+        nz = utils_mod.RunningNormalizer(size=dim)
+        for i in range(6):
+            n = int(rng.integers(1, 40))
+            x = (rng.standard_normal((n, dim)) * rng.uniform(0.1, 3) + rng.uniform(-2, 2)).astype(dtype)
+            nz.update(x)
+            out[f"{tag}_x{i}"] = x
+            out[f"{tag}_mean{i}"] = np.array(nz.mean, np.float64)
+            out[f"{tag}_var{i}"] = np.array(nz.var, np.float64)
+            out[f"{tag}_count{i}"] = np.float64(nz.count)
+        q = (rng.standard_normal((33, dim)) * 8).astype(dtype)
+        out[f"{tag}_q"] = q
+        out[f"{tag}_qn"] = nz.normalize(q)
+    np.savez_compressed(os.path.join(HERE, "normalizer.npz"), **out)
+    print("normalizer: ok")
+
+
+def flat_params(module):
+    return {k: v.detach().cpu().numpy().copy() for k, v in module.state_dict().items()}
+
+
+def ddpg_case(agent_mod, utils_mod, name, *, D, A, H, L, B, steps, seed, gamma=0.98,
+              tau=0.05, grad_clip=10.0, actor_lr=1e-3, critic_lr=1e-3, actor_lr_min=None,
+              critic_lr_min=None, ac_T=1, cr_T=1, ac_update_freq=1, store_weights=True):
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import ddpg as O  # only for the seeded weight initialiser
+    torch.set_num_threads(1)
+    cfg = utils_mod.BaseAgentConfig(
+        hidden_dim=H, layer_count=L, actor_lr=actor_lr,
+        actor_lr_min=actor_lr if actor_lr_min is None else actor_lr_min,
+        ac_scheduler_steps=ac_T, critic_lr=critic_lr,
+        critic_lr_min=critic_lr if critic_lr_min is None else critic_lr_min,
+        cr_scheduler_steps=cr_T, buffer_type="HER", max_len=1000, alpha=1.0, batch_size=B,
+        gamma=gamma, ac_update_freq=ac_update_freq, noise_std=0.2, noise_clamp=0.5,
+        policy_noise=0.0, grad_clip=grad_clip, beta=1.0, beta_end=1, k_future=4,
+        max_eps_len=50, tau=tau)
+    ag = agent_mod.DDPG(obs_dim=D, ac_dim=A, config=cfg, weights=None, nenvs=1, gradient_step=40)
+    ag.device = "cpu"
+    rng = np.random.default_rng(seed)
+    actor0 = O.init_mlp(rng, D, H, A, L)
+    critic0 = O.init_mlp(rng, D + A, H, 1, L)
+    with torch.no_grad():
+        for net, pref, params in ((ag.actor, "base_net", actor0), (ag.critic, "net", critic0)):
+            sd = net.state_dict()
+            for i, (w, b) in enumerate(params):
+                sd[f"{pref}.{2 * i}.weight"].copy_(torch.from_numpy(w))
+                sd[f"{pref}.{2 * i}.bias"].copy_(torch.from_numpy(b))
+    ag.update_target_network()
+    out = {"meta": np.array([D, A, H, L, B, seed, ac_T, cr_T, ac_update_freq], np.int64),
+           "hp": np.array([gamma, tau, grad_clip, actor_lr, critic_lr,
+                           actor_lr if actor_lr_min is None else actor_lr_min,
+                           critic_lr if critic_lr_min is None else critic_lr_min], np.float64),
+           "steps": np.array(steps, np.int64)}
+    for si, step in enumerate(steps):
+        s = rng.standard_normal((B, D)).astype(np.float32)
+        ns = (s + 0.1 * rng.standard_normal((B, D))).astype(np.float32)
+        a = rng.uniform(-1, 1, (B, A)).astype(np.float32)
+        r = -(rng.random((B, 1)) > 0.3).astype(np.float32)          # -1.0 / -0.0
+        d = (rng.random((B, 1)) < 0.1).astype(np.float32)
+        batch = tuple(torch.from_numpy(x) for x in (s, a, r, ns, d))
+        ag.buffer.sample = lambda bs, _b=batch: _b                   # feed explicit batch
+        info = ag.update(step)
+        out[f"s{si}_batch_s"], out[f"s{si}_batch_a"], out[f"s{si}_batch_r"] = s, a, r
+        out[f"s{si}_batch_ns"], out[f"s{si}_batch_d"] = ns, d
+        out[f"s{si}_info"] = np.array([float(x) for x in info], np.float64)
+        out[f"s{si}_lr"] = np.array([ag.critic_opt.param_groups[0]["lr"],
+                                     ag.actor_opt.param_groups[0]["lr"]], np.float64)
+        if store_weights or si == len(steps) - 1:
+            for tag, net in (("actor", ag.actor), ("critic", ag.critic),
+                             ("target_actor", ag.target_actor), ("target_critic", ag.target_critic)):
+                for k_, v in flat_params(net).items():
+                    out[f"s{si}_{tag}.{k_}"] = v
+    np.savez_compressed(os.path.join(HERE, f"ddpg_{name}.npz"), **out)
+    print(f"ddpg_{name}: {len(steps)} steps; last info {out[f's{len(steps) - 1}_info']}")
+
+
+def checkpoint_case(model_mod):
+    """Load-compat + forward-differential fixture from the shipped Reach checkpoint
+    (resources/DDPG/reach/{actor,critic}.pth: H=64, D=10, A=3)."""
+    import torch
+    sd_a = torch.load(os.path.join(REF, "resources/DDPG/reach/actor.pth"), map_location="cpu")
+    sd_c = torch.load(os.path.join(REF, "resources/DDPG/reach/critic.pth"), map_location="cpu")
+    D = sd_a["base_net.0.weight"].shape[1]
+    H = sd_a["base_net.0.weight"].shape[0]
+    A = sd_a["base_net.6.weight"].shape[0]
+    actor = model_mod.Actor(D, H, A, 3)
+    critic = model_mod.Critic(D + A, H, 3)
+    actor.load_state_dict(sd_a)
+    critic.load_state_dict(sd_c)
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((37, D)).astype(np.float32)
+    with torch.no_grad():
+        act = actor(torch.from_numpy(x))
+        q = critic(torch.cat([torch.from_numpy(x), act], -1))
+    out = {"x": x, "act": act.numpy(), "q": q.numpy()}
+    for k, v in sd_a.items():
+        out["actor." + k] = v.numpy()
+    for k, v in sd_c.items():
+        out["critic." + k] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, "checkpoint_reach.npz"), **out)
+    print("checkpoint_reach: D,H,A =", D, H, A)
+
+
+def main():
+    agent_mod, buffer_mod, model_mod, utils_mod = import_reference()
+    reward_case()
+    her_case(buffer_mod, "reach_small", O=7, G=3, A=3, k=4,
+             lens=[50, 50, 7, 1, 2, 50, 13, 50], max_mem_len=100000, nenvs=2, seed=0,
+             batches=[32, 256, 1])
+    her_case(buffer_mod, "push_evict", O=19, G=3, A=3, k=4,
+             lens=[50, 50, 50, 3, 50, 50, 21, 50, 50], max_mem_len=777, nenvs=3, seed=1,
+             batches=[64, 512])
+    her_case(buffer_mod, "pickplace_k8", O=20, G=3, A=4, k=8,
+             lens=[50, 50, 50, 50, 9, 50], max_mem_len=100000, nenvs=4, seed=2,
+             batches=[128, 1000])
+    her_case(buffer_mod, "k0", O=6, G=3, A=3, k=0,
+             lens=[50, 5, 50], max_mem_len=1000, nenvs=1, seed=3, batches=[50])
+    normalizer_case(utils_mod)
+    ddpg_case(agent_mod, utils_mod, "reach_h64", D=10, A=3, H=64, L=3, B=64,
+              steps=[38, 39, 40, 41, 42], seed=5)
+    ddpg_case(agent_mod, utils_mod, "push_h256", D=21, A=3, H=256, L=3, B=256,
+              steps=[39, 40, 41], seed=6, store_weights=False)
+    ddpg_case(agent_mod, utils_mod, "pickplace_l2_cosine", D=23, A=4, H=128, L=2, B=96,
+              steps=[1, 2, 3, 4, 5, 6, 7, 8], seed=8, actor_lr=1e-3, actor_lr_min=1e-4, ac_T=3,
+              critic_lr=2e-3, critic_lr_min=5e-4, cr_T=2, ac_update_freq=2, gamma=0.95,
+              grad_clip=0.05, tau=0.005, store_weights=False)
+    checkpoint_case(model_mod)
+
+
+if __name__ == "__main__":
+    main()
