@@ -1,0 +1,706 @@
+// Off-policy learner: DDPG and TD3 update orchestration over the kernels in mlp.cu/optim.cu.
+//
+// Replaces (reference src/agent.py) DDPG.critic_update :1302-1343, actor_update :1288-1300,
+// update_target_network :1255-1271 and update :1378-1404; TD3Agent.critic_update :164-251,
+// actor_update :149-162, update_actor/update_critic :117-132, update :281-317.
+//
+// Device memory per agent: every network is one flat fp32 buffer (weights [out, ld(in)] then
+// bias, per layer, 16 B aligned segments) with matching flat gradient / Adam m / Adam v
+// buffers; activations are [max_batch, ld(hidden)] per layer; the [state | action] operand
+// rows (sa, nsa, spi) fold torch.cat: the actor heads write their tanh output straight into
+// the action columns.  An update is captured once per (batch, flags) into a CUDA graph and
+// replayed; per-step scalars (lr / bias corrections) travel through a small device struct.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <initializer_list>
+#include <map>
+#include <tuple>
+#include <vector>
+
+#include "mlp.cuh"
+
+struct gcrl_her;
+namespace gcrl {
+void her_sample_into(gcrl_her *h, int64_t B, const int64_t *idx_host, float *s, float *a, float *r,
+                     float *ns, float *d, int64_t *idx_out, cudaStream_t st);
+int her_state_dim(const gcrl_her *h);
+int her_act_dim(const gcrl_her *h);
+int her_device(const gcrl_her *h);
+}  // namespace gcrl
+
+using namespace gcrl;
+
+namespace {
+
+inline int pad4(int x) { return (x + 3) & ~3; }
+
+struct Net {
+  int layers = 0;  // number of Linear layers = layer_count + 1
+  int in_dim = 0, hidden = 0, out_dim = 0;
+  std::vector<int> in_d, out_d, ldw, w_off, b_off;
+  int total = 0;
+  float *p = nullptr, *g = nullptr, *m = nullptr, *v = nullptr;
+  int adam_t = 0;
+
+  void init(int in, int hid, int out, int layer_count, bool trainable) {
+    layers = layer_count + 1;
+    in_dim = in; hidden = hid; out_dim = out;
+    int off = 0;
+    for (int l = 0; l < layers; ++l) {
+      in_d.push_back(l == 0 ? in : hid);
+      out_d.push_back(l == layers - 1 ? out : hid);
+      ldw.push_back(pad4(in_d[l]));
+      w_off.push_back(off);
+      off += out_d[l] * ldw[l];
+      b_off.push_back(off);
+      off += pad4(out_d[l]);
+    }
+    total = off;
+    p = dev_alloc<float>(total);
+    GCRL_CUDA(cudaMemset(p, 0, size_t(total) * 4));
+    if (trainable) {
+      g = dev_alloc<float>(total);
+      m = dev_alloc<float>(total);
+      v = dev_alloc<float>(total);
+      GCRL_CUDA(cudaMemset(g, 0, size_t(total) * 4));
+      GCRL_CUDA(cudaMemset(m, 0, size_t(total) * 4));
+      GCRL_CUDA(cudaMemset(v, 0, size_t(total) * 4));
+    }
+  }
+  void destroy() {
+    cudaFree(p);
+    if (g) { cudaFree(g); cudaFree(m); cudaFree(v); }
+  }
+  const float *W(int l) const { return p + w_off[l]; }
+  const float *b(int l) const { return p + b_off[l]; }
+};
+
+struct Acts {  // post-activation outputs of the hidden layers, [max_batch, ldh] each
+  std::vector<float *> h;
+  void init(int hidden_layers, int64_t maxB, int ldh) {
+    for (int l = 0; l < hidden_layers; ++l) h.push_back(dev_alloc<float>(size_t(maxB) * ldh));
+  }
+  void destroy() { for (auto p : h) cudaFree(p); }
+};
+
+enum NetId { ACTOR = 0, CRITIC1 = 1, T_ACTOR = 2, T_CRITIC1 = 3, CRITIC2 = 4, T_CRITIC2 = 5, NUM_NETS = 6 };
+enum Slot { S_CLOSS = 0, S_ALOSS = 1, S_TD = 2, S_Q = 3, S_CGRAD = 4, S_AGRAD = 5, S_C2LOSS = 6, S_C2GRAD = 7 };
+
+constexpr int kMaxSplits = 128;
+
+}  // namespace
+
+struct gcrl_agent {
+  int device = 0;
+  gcrl_agent_config cfg{};
+  int D = 0, A = 0, H = 0, L = 0, ldh = 0, ldc = 0;
+  int64_t maxB = 0;
+  bool td3 = false;
+  Net net[NUM_NETS];
+  bool has[NUM_NETS] = {};
+  Acts acts_actor, acts_c1, acts_c2, acts_tgt;
+  float *dz[2] = {nullptr, nullptr};       // ping-pong grad-wrt-preactivation buffers [maxB, ldh]
+  float *sa = nullptr, *nsa = nullptr, *spi = nullptr;
+  float *q1 = nullptr, *q2 = nullptr, *qt1 = nullptr, *qt2 = nullptr, *yv = nullptr, *dz_act = nullptr;
+  float *br = nullptr, *bd = nullptr;      // reward / done copies
+  float *bs = nullptr, *ba = nullptr, *bns = nullptr, *br0 = nullptr, *bd0 = nullptr;  // sampled batch
+  float *partials = nullptr;               // [kMaxSplits][max net total]
+  int64_t slab = 0;
+  float *metric_partials = nullptr;        // [kMaxSplits][4]
+  float *sumsq = nullptr;                  // [reduce grid]
+  float *metrics = nullptr;                // [8]
+  StepScalars *d_scalars = nullptr;
+  PinnedRing scal_stage;
+  PinnedRing io_stage;
+  float *d_io = nullptr;
+  size_t io_cap = 0;
+  bool use_graphs = true;
+  cudaStream_t cap_stream = nullptr;       // capture-only stream (the caller's may be the legacy one)
+  std::map<std::tuple<int64_t, int, int>, cudaGraphExec_t> graphs;   // (B, flags, phase mask)
+};
+
+namespace {
+
+// ---- forward / backward building blocks ----------------------------------------------------
+// hidden stack: X[B, K0] -> acts.h[0..L-1]
+void forward_hidden(const gcrl_agent *ag, const Net &n, const float *X, int ldx, int K0, const Acts &acts,
+                    int B, cudaStream_t st) {
+  const float *in = X;
+  int ldin = ldx, K = K0;
+  for (int l = 0; l < ag->L; ++l) {
+    launch_linear_fwd(in, ldin, n.W(l), n.ldw[l], n.b(l), acts.h[l], ag->ldh, B, ag->H, K, ACT_LEAKY, st);
+    in = acts.h[l];
+    ldin = ag->ldh;
+    K = ag->H;
+  }
+}
+
+// Backward through the hidden stack given dz[cur] = grad wrt the pre-activation of the last hidden
+// layer.  Writes split partial weight/bias grads; returns per-layer split counts.  When
+// `to_input` the chain continues to dZ of layer 0 (left in dz[*cur_out]).
+void backward_hidden(gcrl_agent *ag, const Net &n, const float *X, int ldx, int K0, const Acts &acts, int B,
+                     int cur, bool want_wgrad, int *splits /*[layers]*/, int *cur_out, cudaStream_t st) {
+  for (int l = ag->L - 1; l >= 0; --l) {
+    const float *xin = l == 0 ? X : acts.h[l - 1];
+    const int ldin = l == 0 ? ldx : ag->ldh;
+    const int K = l == 0 ? K0 : ag->H;
+    if (want_wgrad)
+      splits[l] = launch_linear_wgrad(ag->dz[cur], ag->ldh, xin, ldin, ag->partials + n.w_off[l], n.ldw[l],
+                                      ag->slab, ag->partials + n.b_off[l], ag->slab, B, ag->H, K,
+                                      kMaxSplits, st);
+    if (l > 0) {
+      launch_linear_dgrad(ag->dz[cur], ag->ldh, n.W(l), n.ldw[l], acts.h[l - 1], ag->ldh, ag->dz[cur ^ 1],
+                          ag->ldh, B, ag->H, ag->H, st);
+      cur ^= 1;
+    }
+  }
+  *cur_out = cur;
+}
+
+void reduce_and_step(gcrl_agent *ag, Net &n, const int *splits, int head_splits, int which, float max_norm,
+                     int slot_loss, int slot_td, int slot_q, int slot_norm, int metric_splits, int B,
+                     float *target, bool polyak, cudaStream_t st) {
+  ReduceArgs r{};
+  r.nseg = 0;
+  for (int l = 0; l < n.layers; ++l) {
+    const int sp = l == n.layers - 1 ? head_splits : splits[l];
+    SegDesc w{n.w_off[l], n.out_d[l] * n.ldw[l], ag->partials, sp, ag->slab, n.w_off[l]};
+    SegDesc b{n.b_off[l], n.out_d[l], ag->partials, sp, ag->slab, n.b_off[l]};
+    r.seg[r.nseg++] = w;
+    r.seg[r.nseg++] = b;
+  }
+  r.total = n.total;
+  r.grad = n.g;
+  r.sumsq_partials = ag->sumsq;
+  r.metric_partials = metric_splits > 0 ? ag->metric_partials : nullptr;
+  r.metric_splits = metric_splits;
+  r.metric_scale = 1.0f / float(B);
+  r.metrics = ag->metrics;
+  r.slot_loss = slot_loss; r.slot_td = slot_td; r.slot_q = slot_q;
+  launch_reduce_grads(r, st);
+  AdamArgs a{};
+  a.p = n.p; a.m = n.m; a.v = n.v; a.g = n.g; a.n = n.total;
+  a.sumsq_partials = ag->sumsq; a.nsumsq = reduce_grid(n.total);
+  a.max_norm = max_norm;
+  a.weight_decay = ag->cfg.weight_decay;
+  a.sc = ag->d_scalars; a.which = which;
+  a.target = target; a.tau = ag->cfg.tau; a.one_minus_tau = float(1.0 - double(ag->cfg.tau));
+  a.polyak = polyak ? 1 : 0;
+  a.metrics = ag->metrics; a.slot_norm = slot_norm;
+  launch_adam(a, st);
+}
+
+// ---- phases ------------------------------------------------------------------------------------
+// phase 0/1: critic(s).  Operands sa / nsa / br / bd must be resident.
+void critic_forward_backward(gcrl_agent *ag, int which_critic, int B, int *splits, int *head_splits,
+                             int *metric_splits, cudaStream_t st) {
+  const Net &c = ag->net[which_critic == 0 ? CRITIC1 : CRITIC2];
+  const Acts &acts = which_critic == 0 ? ag->acts_c1 : ag->acts_c2;
+  float *q = which_critic == 0 ? ag->q1 : ag->q2;
+  const int K0 = ag->D + ag->A;
+  HeadBwdArgs h{};
+  h.mode = 0;
+  h.loss_kind = ag->td3 ? 1 : 0;
+  h.clamp_y = ag->td3 ? 0 : 1;                       // DDPG clamps y to [-1/(1-gamma), 0] (:1317)
+  h.nout = 1;
+  h.q = q; h.qt1 = ag->qt1; h.qt2 = ag->td3 ? ag->qt2 : nullptr;
+  h.q_other = (ag->td3 && which_critic == 1) ? ag->q1 : nullptr;
+  h.r = ag->br; h.d = ag->bd;
+  h.gamma = ag->cfg.gamma;
+  h.y_lo = float(-1.0 / (1.0 - double(ag->cfg.gamma)));
+  h.Hact = acts.h[ag->L - 1]; h.ldh = ag->ldh;
+  h.W = c.W(ag->L); h.ldw = c.ldw[ag->L];
+  h.dZprev = ag->dz[0]; h.lddz = ag->ldh;
+  h.pW = ag->partials + c.w_off[ag->L]; h.w_split_stride = ag->slab;
+  h.pB = ag->partials + c.b_off[ag->L]; h.b_split_stride = ag->slab;
+  h.metric_partials = ag->metric_partials;
+  h.y_out = ag->yv;
+  h.M = B; h.K = ag->H;
+  *head_splits = launch_head_bwd(h, kMaxSplits, st);
+  *metric_splits = *head_splits;
+  int cur;
+  backward_hidden(ag, c, ag->sa, ag->ldc, K0, acts, B, 0, true, splits, &cur, st);
+}
+
+void targets_and_critic_forward(gcrl_agent *ag, int B, const float *noise, cudaStream_t st) {
+  const int D = ag->D, A = ag->A, K0 = D + A;
+  // a' = target_actor(s')  -> action columns of nsa                          (:1312 / :179)
+  forward_hidden(ag, ag->net[T_ACTOR], ag->nsa, ag->ldc, D, ag->acts_tgt, B, st);
+  launch_head_fwd(ag->acts_tgt.h[ag->L - 1], ag->ldh, ag->net[T_ACTOR].W(ag->L), ag->net[T_ACTOR].ldw[ag->L],
+                  ag->net[T_ACTOR].b(ag->L), ag->nsa, ag->ldc, D, B, ag->H, A, 1, st);
+  if (ag->td3) {
+    GCRL_REQUIRE(noise != nullptr, "TD3 update needs the [B, A] standard-normal noise tensor");
+    launch_td3_smooth(ag->nsa, ag->ldc, D, noise, A, B, ag->cfg.policy_noise, ag->cfg.noise_clamp, st);
+  }
+  // q' = target_critic([s', a'])                                               (:1313-1315)
+  forward_hidden(ag, ag->net[T_CRITIC1], ag->nsa, ag->ldc, K0, ag->acts_tgt, B, st);
+  launch_head_fwd(ag->acts_tgt.h[ag->L - 1], ag->ldh, ag->net[T_CRITIC1].W(ag->L),
+                  ag->net[T_CRITIC1].ldw[ag->L], ag->net[T_CRITIC1].b(ag->L), ag->qt1, 1, 0, B, ag->H, 1, 0, st);
+  if (ag->td3) {
+    forward_hidden(ag, ag->net[T_CRITIC2], ag->nsa, ag->ldc, K0, ag->acts_tgt, B, st);
+    launch_head_fwd(ag->acts_tgt.h[ag->L - 1], ag->ldh, ag->net[T_CRITIC2].W(ag->L),
+                    ag->net[T_CRITIC2].ldw[ag->L], ag->net[T_CRITIC2].b(ag->L), ag->qt2, 1, 0, B, ag->H, 1, 0,
+                    st);
+  }
+  // q = critic([s, a])                                                          (:1319)
+  forward_hidden(ag, ag->net[CRITIC1], ag->sa, ag->ldc, K0, ag->acts_c1, B, st);
+  launch_head_fwd(ag->acts_c1.h[ag->L - 1], ag->ldh, ag->net[CRITIC1].W(ag->L), ag->net[CRITIC1].ldw[ag->L],
+                  ag->net[CRITIC1].b(ag->L), ag->q1, 1, 0, B, ag->H, 1, 0, st);
+  if (ag->td3) {
+    forward_hidden(ag, ag->net[CRITIC2], ag->sa, ag->ldc, K0, ag->acts_c2, B, st);
+    launch_head_fwd(ag->acts_c2.h[ag->L - 1], ag->ldh, ag->net[CRITIC2].W(ag->L), ag->net[CRITIC2].ldw[ag->L],
+                    ag->net[CRITIC2].b(ag->L), ag->q2, 1, 0, B, ag->H, 1, 0, st);
+  }
+}
+
+struct PhaseState {
+  int splits[8] = {};
+  int head_splits = 0, metric_splits = 0;
+};
+
+void critic_phase_fb(gcrl_agent *ag, int B, const float *noise, PhaseState *ps /*[2]*/, cudaStream_t st) {
+  targets_and_critic_forward(ag, B, noise, st);
+  critic_forward_backward(ag, 0, B, ps[0].splits, &ps[0].head_splits, &ps[0].metric_splits, st);
+}
+
+void critic_phase_step(gcrl_agent *ag, int B, int flags, PhaseState *ps, cudaStream_t st) {
+  const bool polyak = ag->td3 ? true : ((flags & 2) != 0);
+  // DDPG: actor target blends the PRE-step actor, before the actor step (:1397-1401)
+  if (!ag->td3 && polyak)
+    launch_polyak(ag->net[T_ACTOR].p, ag->net[ACTOR].p, ag->net[ACTOR].total, ag->cfg.tau,
+                  float(1.0 - double(ag->cfg.tau)), st);
+  const float clip1 = ag->td3 ? -1.0f : ag->cfg.grad_clip;     // TD3 critic 1 is NOT clipped (:201)
+  reduce_and_step(ag, ag->net[CRITIC1], ps[0].splits, ps[0].head_splits, 0, clip1, S_CLOSS,
+                  ag->td3 ? -1 : S_TD, ag->td3 ? -1 : S_Q, S_CGRAD, ps[0].metric_splits, B,
+                  ag->net[T_CRITIC1].p, polyak, st);
+  if (ag->td3) {
+    // critic 2: its own backward reuses dz / partial buffers after critic 1's optimiser pass
+    critic_forward_backward(ag, 1, B, ps[1].splits, &ps[1].head_splits, &ps[1].metric_splits, st);
+    reduce_and_step(ag, ag->net[CRITIC2], ps[1].splits, ps[1].head_splits, 0, ag->cfg.grad_clip, S_C2LOSS,
+                    S_TD, S_Q, S_C2GRAD, ps[1].metric_splits, B, ag->net[T_CRITIC2].p, polyak, st);
+  }
+}
+
+void actor_phase_fb(gcrl_agent *ag, int B, PhaseState *ps, cudaStream_t st) {
+  const int D = ag->D, A = ag->A, K0 = D + A, L = ag->L;
+  const Net &actor = ag->net[ACTOR];
+  const Net &c = ag->net[CRITIC1];
+  // a = actor(s) -> action columns of spi; q = critic([s, a]) with the stepped critic (:1289-1290)
+  forward_hidden(ag, actor, ag->spi, ag->ldc, D, ag->acts_actor, B, st);
+  launch_head_fwd(ag->acts_actor.h[L - 1], ag->ldh, actor.W(L), actor.ldw[L], actor.b(L), ag->spi, ag->ldc, D,
+                  B, ag->H, A, 1, st);
+  forward_hidden(ag, c, ag->spi, ag->ldc, K0, ag->acts_c1, B, st);
+  launch_head_fwd(ag->acts_c1.h[L - 1], ag->ldh, c.W(L), c.ldw[L], c.b(L), ag->q1, 1, 0, B, ag->H, 1, 0, st);
+  // d(-mean q)/d(critic hidden) ... down to the action columns
+  HeadBwdArgs h{};
+  h.mode = 1; h.nout = 1; h.q = ag->q1;
+  h.Hact = ag->acts_c1.h[L - 1]; h.ldh = ag->ldh;
+  h.W = c.W(L); h.ldw = c.ldw[L];
+  h.dZprev = ag->dz[0]; h.lddz = ag->ldh;
+  h.pW = nullptr; h.pB = nullptr;                     // critic weight grads are discarded (:1293-1294)
+  h.metric_partials = ag->metric_partials;
+  h.M = B; h.K = ag->H;
+  ps->metric_splits = launch_head_bwd(h, kMaxSplits, st);
+  int cur;
+  int dummy[8];
+  backward_hidden(ag, c, ag->spi, ag->ldc, K0, ag->acts_c1, B, 0, false, dummy, &cur, st);
+  launch_action_grad(ag->dz[cur], ag->ldh, c.W(0), c.ldw[0], ag->spi, ag->ldc, D, ag->dz_act, B, ag->H, A, st);
+  // actor head + hidden stack backward
+  HeadBwdArgs ha{};
+  ha.mode = 2; ha.nout = A; ha.dz_in = ag->dz_act;
+  ha.Hact = ag->acts_actor.h[L - 1]; ha.ldh = ag->ldh;
+  ha.W = actor.W(L); ha.ldw = actor.ldw[L];
+  ha.dZprev = ag->dz[0]; ha.lddz = ag->ldh;
+  ha.pW = ag->partials + actor.w_off[L]; ha.w_split_stride = ag->slab;
+  ha.pB = ag->partials + actor.b_off[L]; ha.b_split_stride = ag->slab;
+  ha.M = B; ha.K = ag->H;
+  ps->head_splits = launch_head_bwd(ha, kMaxSplits, st);
+  backward_hidden(ag, actor, ag->spi, ag->ldc, D, ag->acts_actor, B, 0, true, ps->splits, &cur, st);
+}
+
+void actor_phase_step(gcrl_agent *ag, int B, PhaseState *ps, cudaStream_t st) {
+  // the actor-loss metric partials were written before the actor head pass reused nothing of them
+  reduce_and_step(ag, ag->net[ACTOR], ps->splits, ps->head_splits, 1, ag->cfg.grad_clip, S_ALOSS, -1, -1,
+                  S_AGRAD, ps->metric_splits, B, ag->net[T_ACTOR].p, ag->td3, st);
+}
+
+void write_scalars(gcrl_agent *ag, double lr_c, double lr_a, bool actor_steps, cudaStream_t st) {
+  auto fill = [&](int t, double lr, float *out) {
+    const double bc1 = 1.0 - std::pow(0.9, double(t));
+    const double bc2 = 1.0 - std::pow(0.999, double(t));
+    out[0] = float(lr / bc1);
+    out[1] = float(std::sqrt(bc2));
+    out[2] = float(1.0 - lr * double(ag->cfg.weight_decay));
+    out[3] = 0.f;
+  };
+  int slot;
+  auto *sc = reinterpret_cast<StepScalars *>(ag->scal_stage.acquire(sizeof(StepScalars), &slot));
+  ag->net[CRITIC1].adam_t += 1;
+  if (ag->td3) ag->net[CRITIC2].adam_t += 1;
+  fill(ag->net[CRITIC1].adam_t, lr_c, &sc->step_size_c);
+  if (actor_steps) ag->net[ACTOR].adam_t += 1;
+  fill(std::max(1, ag->net[ACTOR].adam_t), lr_a, &sc->step_size_a);
+  GCRL_CUDA(cudaMemcpyAsync(ag->d_scalars, sc, sizeof(StepScalars), cudaMemcpyHostToDevice, st));
+  ag->scal_stage.release(slot, st);
+}
+
+void run_update_body(gcrl_agent *ag, int B, const float *noise, int flags, cudaStream_t st) {
+  PhaseState ps[2], pa;
+  critic_phase_fb(ag, B, noise, ps, st);
+  critic_phase_step(ag, B, flags, ps, st);
+  if (flags & 1) {
+    actor_phase_fb(ag, B, &pa, st);
+    actor_phase_step(ag, B, &pa, st);
+  }
+}
+
+// Replay (or capture on first use) the update graph for (B, flags).  TD3 noise pointers vary per
+// call, so the noise is first copied into an internal buffer by the caller.
+void run_update(gcrl_agent *ag, int B, const float *noise, int flags, cudaStream_t st) {
+  if (!ag->use_graphs) {
+    run_update_body(ag, B, noise, flags, st);
+    return;
+  }
+  const auto key = std::make_tuple(int64_t(B), flags, 0);
+  auto it = ag->graphs.find(key);
+  if (it == ag->graphs.end()) {
+    cudaGraph_t graph = nullptr;
+    GCRL_CUDA(cudaStreamBeginCapture(ag->cap_stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      run_update_body(ag, B, noise, flags, ag->cap_stream);
+    } catch (...) {
+      cudaStreamEndCapture(ag->cap_stream, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    GCRL_CUDA(cudaStreamEndCapture(ag->cap_stream, &graph));
+    cudaGraphExec_t exec = nullptr;
+    GCRL_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    GCRL_CUDA(cudaGraphDestroy(graph));
+    it = ag->graphs.emplace(key, exec).first;
+  }
+  GCRL_CUDA(cudaGraphLaunch(it->second, st));
+}
+
+void check_batch(const gcrl_agent *ag, int64_t B) {
+  GCRL_REQUIRE(ag != nullptr, "agent handle is NULL");
+  GCRL_REQUIRE(B >= 1 && B <= ag->maxB, "batch size outside [1, max_batch]");
+}
+
+float *stage_to_device(gcrl_agent *ag, const float *host, size_t count, size_t offset_floats,
+                       cudaStream_t st) {
+  int slot;
+  char *p = ag->io_stage.acquire(count * 4, &slot);
+  std::memcpy(p, host, count * 4);
+  GCRL_CUDA(cudaMemcpyAsync(ag->d_io + offset_floats, p, count * 4, cudaMemcpyHostToDevice, st));
+  ag->io_stage.release(slot, st);
+  return ag->d_io + offset_floats;
+}
+
+void ensure_io(gcrl_agent *ag, size_t floats, cudaStream_t st) {
+  if (floats > ag->io_cap) {
+    GCRL_CUDA(cudaStreamSynchronize(st));
+    if (ag->d_io) GCRL_CUDA(cudaFree(ag->d_io));
+    ag->io_cap = floats * 2;
+    ag->d_io = dev_alloc<float>(ag->io_cap);
+  }
+}
+
+void finish_metrics(gcrl_agent *ag, float *metrics_host, cudaStream_t st) {
+  if (metrics_host == nullptr) return;
+  GCRL_CUDA(cudaMemcpyAsync(metrics_host, ag->metrics, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  GCRL_CUDA(cudaStreamSynchronize(st));
+}
+
+}  // namespace
+
+extern "C" {
+
+int gcrl_agent_create(gcrl_agent **out, int device, const gcrl_agent_config *cfg) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(out != nullptr && cfg != nullptr, "NULL argument");
+  GCRL_REQUIRE(cfg->algo == GCRL_ALGO_DDPG || cfg->algo == GCRL_ALGO_TD3, "unknown algo");
+  GCRL_REQUIRE(cfg->state_dim >= 1 && cfg->act_dim >= 1 && cfg->act_dim <= 4,
+               "need state_dim >= 1 and 1 <= act_dim <= 4");
+  GCRL_REQUIRE(cfg->hidden_dim >= 1 && cfg->hidden_dim <= 4096, "hidden_dim outside [1, 4096]");
+  GCRL_REQUIRE(cfg->layer_count >= 1 && cfg->layer_count <= 6, "layer_count outside [1, 6]");
+  GCRL_REQUIRE(cfg->max_batch >= 1, "max_batch must be >= 1");
+  GCRL_REQUIRE(cfg->precision == 0, "only precision 0 (fp32) is implemented");
+  GCRL_CUDA(cudaSetDevice(device));
+  auto *ag = new gcrl_agent();
+  try {
+    ag->device = device;
+    ag->cfg = *cfg;
+    ag->D = cfg->state_dim; ag->A = cfg->act_dim; ag->H = cfg->hidden_dim; ag->L = cfg->layer_count;
+    ag->ldh = pad4(ag->H);
+    ag->ldc = pad4(ag->D + ag->A);
+    ag->maxB = cfg->max_batch;
+    ag->td3 = cfg->algo == GCRL_ALGO_TD3;
+    GCRL_REQUIRE(ag->maxB <= int64_t(kMaxSplits) * 512, "max_batch too large for the partial buffers");
+    const int D = ag->D, A = ag->A, H = ag->H, L = ag->L;
+    ag->net[ACTOR].init(D, H, A, L, true);       ag->has[ACTOR] = true;
+    ag->net[CRITIC1].init(D + A, H, 1, L, true); ag->has[CRITIC1] = true;
+    ag->net[T_ACTOR].init(D, H, A, L, false);    ag->has[T_ACTOR] = true;
+    ag->net[T_CRITIC1].init(D + A, H, 1, L, false); ag->has[T_CRITIC1] = true;
+    if (ag->td3) {
+      ag->net[CRITIC2].init(D + A, H, 1, L, true);    ag->has[CRITIC2] = true;
+      ag->net[T_CRITIC2].init(D + A, H, 1, L, false); ag->has[T_CRITIC2] = true;
+    }
+    const int64_t mb = ag->maxB;
+    ag->acts_actor.init(L, mb, ag->ldh);
+    ag->acts_c1.init(L, mb, ag->ldh);
+    if (ag->td3) ag->acts_c2.init(L, mb, ag->ldh);
+    ag->acts_tgt.init(L, mb, ag->ldh);
+    for (auto &p : ag->dz) p = dev_alloc<float>(size_t(mb) * ag->ldh);
+    ag->sa = dev_alloc<float>(size_t(mb) * ag->ldc);
+    ag->nsa = dev_alloc<float>(size_t(mb) * ag->ldc);
+    ag->spi = dev_alloc<float>(size_t(mb) * ag->ldc);
+    for (float **p : {&ag->q1, &ag->q2, &ag->qt1, &ag->qt2, &ag->yv, &ag->br, &ag->bd, &ag->br0, &ag->bd0})
+      *p = dev_alloc<float>(size_t(mb));
+    ag->dz_act = dev_alloc<float>(size_t(mb) * 4);
+    ag->bs = dev_alloc<float>(size_t(mb) * D);
+    ag->bns = dev_alloc<float>(size_t(mb) * D);
+    ag->ba = dev_alloc<float>(size_t(mb) * A);
+    ag->slab = std::max(ag->net[ACTOR].total, ag->net[CRITIC1].total);
+    ag->partials = dev_alloc<float>(size_t(kMaxSplits) * ag->slab);
+    ag->metric_partials = dev_alloc<float>(size_t(kMaxSplits) * 4);
+    ag->sumsq = dev_alloc<float>(size_t(reduce_grid(int(ag->slab))) + 8);
+    ag->metrics = dev_alloc<float>(8);
+    GCRL_CUDA(cudaMemset(ag->metrics, 0, 8 * sizeof(float)));
+    ag->d_scalars = dev_alloc<StepScalars>(1);
+    ag->scal_stage.init(256);
+    GCRL_CUDA(cudaStreamCreateWithFlags(&ag->cap_stream, cudaStreamNonBlocking));
+    const char *ng = getenv("GCRL_B200_NO_GRAPH");
+    ag->use_graphs = !(ng && ng[0] == '1');
+    ag->io_stage.init(size_t(1) << 16);
+  } catch (...) {
+    delete ag;
+    throw;
+  }
+  *out = ag;
+  GCRL_API_END
+}
+
+int gcrl_agent_destroy(gcrl_agent *ag) {
+  GCRL_API_BEGIN
+  if (ag == nullptr) return GCRL_OK;
+  cudaSetDevice(ag->device);
+  cudaDeviceSynchronize();
+  for (auto &kv : ag->graphs) cudaGraphExecDestroy(kv.second);
+  for (int i = 0; i < NUM_NETS; ++i)
+    if (ag->has[i]) ag->net[i].destroy();
+  ag->acts_actor.destroy(); ag->acts_c1.destroy(); ag->acts_c2.destroy(); ag->acts_tgt.destroy();
+  for (float *p : {ag->dz[0], ag->dz[1], ag->sa, ag->nsa, ag->spi, ag->q1, ag->q2, ag->qt1, ag->qt2, ag->yv,
+                   ag->dz_act, ag->br, ag->bd, ag->bs, ag->ba, ag->bns, ag->br0, ag->bd0, ag->partials,
+                   ag->metric_partials, ag->sumsq, ag->metrics, ag->d_io})
+    if (p) cudaFree(p);
+  cudaFree(ag->d_scalars);
+  if (ag->cap_stream) cudaStreamDestroy(ag->cap_stream);
+  ag->scal_stage.destroy();
+  ag->io_stage.destroy();
+  delete ag;
+  GCRL_API_END
+}
+
+int gcrl_agent_num_layers(const gcrl_agent *ag, int net) {
+  if (ag == nullptr || net < 0 || net >= NUM_NETS || !ag->has[net]) return -1;
+  return ag->net[net].layers;
+}
+
+int gcrl_agent_layer_shape(const gcrl_agent *ag, int net, int layer, int *out_dim, int *in_dim) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(ag && net >= 0 && net < NUM_NETS && ag->has[net], "bad network id");
+  GCRL_REQUIRE(layer >= 0 && layer < ag->net[net].layers, "bad layer index");
+  if (out_dim) *out_dim = ag->net[net].out_d[layer];
+  if (in_dim) *in_dim = ag->net[net].in_d[layer];
+  GCRL_API_END
+}
+
+int gcrl_agent_set_layer(gcrl_agent *ag, int net, int layer, const float *weight_host,
+                         const float *bias_host, void *stream) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(ag && net >= 0 && net < NUM_NETS && ag->has[net], "bad network id");
+  Net &n = ag->net[net];
+  GCRL_REQUIRE(layer >= 0 && layer < n.layers && weight_host && bias_host, "bad layer / NULL data");
+  GCRL_CUDA(cudaSetDevice(ag->device));
+  cudaStream_t st = as_stream(stream);
+  const int o = n.out_d[layer], i = n.in_d[layer], ld = n.ldw[layer];
+  std::vector<float> padded(size_t(o) * ld + pad4(o), 0.f);
+  for (int r = 0; r < o; ++r) std::memcpy(&padded[size_t(r) * ld], weight_host + size_t(r) * i, size_t(i) * 4);
+  std::memcpy(&padded[size_t(o) * ld], bias_host, size_t(o) * 4);
+  GCRL_CUDA(cudaMemcpyAsync(n.p + n.w_off[layer], padded.data(), padded.size() * 4, cudaMemcpyHostToDevice, st));
+  GCRL_CUDA(cudaStreamSynchronize(st));
+  GCRL_API_END
+}
+
+int gcrl_agent_get_layer(gcrl_agent *ag, int net, int layer, float *weight_host, float *bias_host,
+                         void *stream) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(ag && net >= 0 && net < NUM_NETS && ag->has[net], "bad network id");
+  Net &n = ag->net[net];
+  GCRL_REQUIRE(layer >= 0 && layer < n.layers, "bad layer index");
+  GCRL_CUDA(cudaSetDevice(ag->device));
+  cudaStream_t st = as_stream(stream);
+  const int o = n.out_d[layer], i = n.in_d[layer], ld = n.ldw[layer];
+  std::vector<float> padded(size_t(o) * ld + pad4(o));
+  GCRL_CUDA(cudaMemcpyAsync(padded.data(), n.p + n.w_off[layer], padded.size() * 4, cudaMemcpyDeviceToHost, st));
+  GCRL_CUDA(cudaStreamSynchronize(st));
+  if (weight_host)
+    for (int r = 0; r < o; ++r) std::memcpy(weight_host + size_t(r) * i, &padded[size_t(r) * ld], size_t(i) * 4);
+  if (bias_host) std::memcpy(bias_host, &padded[size_t(o) * ld], size_t(o) * 4);
+  GCRL_API_END
+}
+
+int gcrl_agent_hard_update(gcrl_agent *ag, void *stream) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(ag != nullptr, "agent handle is NULL");
+  GCRL_CUDA(cudaSetDevice(ag->device));
+  cudaStream_t st = as_stream(stream);
+  const int pairs[3][2] = {{T_ACTOR, ACTOR}, {T_CRITIC1, CRITIC1}, {T_CRITIC2, CRITIC2}};
+  for (auto &pr : pairs)
+    if (ag->has[pr[0]])
+      GCRL_CUDA(cudaMemcpyAsync(ag->net[pr[0]].p, ag->net[pr[1]].p, size_t(ag->net[pr[1]].total) * 4,
+                                cudaMemcpyDeviceToDevice, st));
+  GCRL_API_END
+}
+
+int gcrl_agent_reset_optim(gcrl_agent *ag, void *stream) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(ag != nullptr, "agent handle is NULL");
+  GCRL_CUDA(cudaSetDevice(ag->device));
+  cudaStream_t st = as_stream(stream);
+  for (int i : {ACTOR, CRITIC1, CRITIC2})
+    if (ag->has[i]) {
+      GCRL_CUDA(cudaMemsetAsync(ag->net[i].m, 0, size_t(ag->net[i].total) * 4, st));
+      GCRL_CUDA(cudaMemsetAsync(ag->net[i].v, 0, size_t(ag->net[i].total) * 4, st));
+      ag->net[i].adam_t = 0;
+    }
+  GCRL_API_END
+}
+
+int gcrl_agent_update_batch(gcrl_agent *ag, int64_t B, const float *s_dev, const float *a_dev,
+                            const float *r_dev, const float *ns_dev, const float *d_dev,
+                            const float *noise_dev, double lr_critic, double lr_actor, int flags,
+                            float *metrics_host, void *stream) {
+  GCRL_API_BEGIN
+  check_batch(ag, B);
+  GCRL_REQUIRE(s_dev && a_dev && r_dev && ns_dev && d_dev, "NULL batch pointer");
+  GCRL_REQUIRE(!ag->td3 || noise_dev != nullptr, "TD3 update needs noise");
+  GCRL_CUDA(cudaSetDevice(ag->device));
+  cudaStream_t st = as_stream(stream);
+  launch_ingest_batch(s_dev, a_dev, r_dev, ns_dev, d_dev, ag->D, ag->A, int(B), ag->sa, ag->nsa, ag->spi,
+                      ag->ldc, ag->br, ag->bd, st);
+  const float *noise = nullptr;
+  if (ag->td3) {  // stable address for the captured graph
+    GCRL_CUDA(cudaMemcpyAsync(ag->dz_act, noise_dev, size_t(B) * ag->A * 4, cudaMemcpyDeviceToDevice, st));
+    noise = ag->dz_act;
+  }
+  write_scalars(ag, lr_critic, lr_actor, (flags & 1) != 0, st);
+  run_update(ag, int(B), noise, flags, st);
+  finish_metrics(ag, metrics_host, st);
+  GCRL_API_END
+}
+
+int gcrl_agent_update_from_buffer(gcrl_agent *ag, gcrl_her *buf, int64_t B, const int64_t *idx_host,
+                                  const float *noise_dev, double lr_critic, double lr_actor, int flags,
+                                  float *metrics_host, void *stream) {
+  GCRL_API_BEGIN
+  check_batch(ag, B);
+  GCRL_REQUIRE(buf != nullptr, "buffer handle is NULL");
+  GCRL_REQUIRE(her_state_dim(buf) == ag->D && her_act_dim(buf) == ag->A, "buffer / agent shape mismatch");
+  GCRL_REQUIRE(her_device(buf) == ag->device, "buffer and agent live on different devices");
+  GCRL_REQUIRE(!ag->td3 || noise_dev != nullptr, "TD3 update needs noise");
+  GCRL_CUDA(cudaSetDevice(ag->device));
+  cudaStream_t st = as_stream(stream);
+  her_sample_into(buf, B, idx_host, ag->bs, ag->ba, ag->br0, ag->bns, ag->bd0, nullptr, st);
+  launch_ingest_batch(ag->bs, ag->ba, ag->br0, ag->bns, ag->bd0, ag->D, ag->A, int(B), ag->sa, ag->nsa,
+                      ag->spi, ag->ldc, ag->br, ag->bd, st);
+  const float *noise = nullptr;
+  if (ag->td3) {
+    GCRL_CUDA(cudaMemcpyAsync(ag->dz_act, noise_dev, size_t(B) * ag->A * 4, cudaMemcpyDeviceToDevice, st));
+    noise = ag->dz_act;
+  }
+  write_scalars(ag, lr_critic, lr_actor, (flags & 1) != 0, st);
+  run_update(ag, int(B), noise, flags, st);
+  finish_metrics(ag, metrics_host, st);
+  GCRL_API_END
+}
+
+int gcrl_agent_read_metrics(gcrl_agent *ag, float *metrics_host, void *stream) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(ag != nullptr && metrics_host != nullptr, "NULL argument");
+  GCRL_CUDA(cudaSetDevice(ag->device));
+  finish_metrics(ag, metrics_host, as_stream(stream));
+  GCRL_API_END
+}
+
+int gcrl_agent_act(gcrl_agent *ag, int64_t n, const float *obs_host, float *act_host, void *stream) {
+  GCRL_API_BEGIN
+  check_batch(ag, n);
+  GCRL_REQUIRE(obs_host && act_host, "NULL argument");
+  GCRL_CUDA(cudaSetDevice(ag->device));
+  cudaStream_t st = as_stream(stream);
+  const int D = ag->D, A = ag->A, L = ag->L;
+  ensure_io(ag, size_t(n) * (D + 4), st);
+  float *obs = stage_to_device(ag, obs_host, size_t(n) * D, 0, st);
+  // uses the actor-phase scratch (spi / acts_actor): select_action never overlaps an update
+  launch_pack_rows(obs, D, nullptr, A, ag->spi, ag->ldc, int(n), st);
+  const Net &actor = ag->net[ACTOR];
+  forward_hidden(ag, actor, ag->spi, ag->ldc, D, ag->acts_actor, int(n), st);
+  float *out = ag->d_io + size_t(n) * D;
+  launch_head_fwd(ag->acts_actor.h[L - 1], ag->ldh, actor.W(L), actor.ldw[L], actor.b(L), out, A, 0, int(n),
+                  ag->H, A, 1, st);
+  GCRL_CUDA(cudaMemcpyAsync(act_host, out, size_t(n) * A * 4, cudaMemcpyDeviceToHost, st));
+  GCRL_CUDA(cudaStreamSynchronize(st));
+  GCRL_API_END
+}
+
+int gcrl_agent_q(gcrl_agent *ag, int64_t n, const float *obs_host, const float *act_host, float *q_host,
+                 void *stream) {
+  GCRL_API_BEGIN
+  check_batch(ag, n);
+  GCRL_REQUIRE(obs_host && act_host && q_host, "NULL argument");
+  GCRL_CUDA(cudaSetDevice(ag->device));
+  cudaStream_t st = as_stream(stream);
+  const int D = ag->D, A = ag->A, L = ag->L;
+  ensure_io(ag, size_t(n) * (D + A + 1), st);
+  float *obs = stage_to_device(ag, obs_host, size_t(n) * D, 0, st);
+  float *act = stage_to_device(ag, act_host, size_t(n) * A, size_t(n) * D, st);
+  launch_pack_rows(obs, D, act, A, ag->spi, ag->ldc, int(n), st);
+  const Net &c = ag->net[CRITIC1];
+  forward_hidden(ag, c, ag->spi, ag->ldc, D + A, ag->acts_c1, int(n), st);
+  float *out = ag->d_io + size_t(n) * (D + A);
+  launch_head_fwd(ag->acts_c1.h[L - 1], ag->ldh, c.W(L), c.ldw[L], c.b(L), out, 1, 0, int(n), ag->H, 1, 0, st);
+  GCRL_CUDA(cudaMemcpyAsync(q_host, out, size_t(n) * 4, cudaMemcpyDeviceToHost, st));
+  GCRL_CUDA(cudaStreamSynchronize(st));
+  GCRL_API_END
+}
+
+// ---- data-parallel phase hooks ---------------------------------------------------------------------
+int gcrl_agent_update_phase(gcrl_agent *ag, int phase, int64_t B, const float *s_dev, const float *a_dev,
+                            const float *r_dev, const float *ns_dev, const float *d_dev,
+                            const float *noise_dev, double lr, int flags, void *stream) {
+  GCRL_API_BEGIN
+  (void)ag; (void)phase; (void)B; (void)s_dev; (void)a_dev; (void)r_dev; (void)ns_dev; (void)d_dev;
+  (void)noise_dev; (void)lr; (void)flags; (void)stream;
+  throw Error(GCRL_ERR_INVALID, "gcrl_agent_update_phase: data-parallel phases not built yet");
+  GCRL_API_END
+}
+
+int gcrl_agent_grad_buffer(gcrl_agent *ag, int net, float **grad_dev, int64_t *count) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(ag && net >= 0 && net < NUM_NETS && ag->has[net] && ag->net[net].g, "bad network id");
+  if (grad_dev) *grad_dev = ag->net[net].g;
+  if (count) *count = ag->net[net].total;
+  GCRL_API_END
+}
+
+int gcrl_agent_metrics_buffer(gcrl_agent *ag, float **metrics_dev) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(ag != nullptr && metrics_dev != nullptr, "NULL argument");
+  *metrics_dev = ag->metrics;
+  GCRL_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// Error plumbing, pinned staging ring, misc C-ABI entry points.
+#include "common.cuh"
+
+#include <cstring>
+
+namespace gcrl {
+
+static thread_local std::string g_last_error;
+
+void set_last_error(const std::string &m) { g_last_error = m; }
+
+int sm_count() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0, n = 0;
+    GCRL_CUDA(cudaGetDevice(&dev));
+    GCRL_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    cached = n > 0 ? n : 148;
+  }
+  return cached;
+}
+
+void PinnedRing::init(size_t bytes) {
+  slot_bytes = (bytes + 255) & ~size_t(255);
+  GCRL_CUDA(cudaMallocHost(&base, slot_bytes * kSlots));
+  for (int i = 0; i < kSlots; ++i) {
+    GCRL_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    used[i] = false;
+  }
+  next = 0;
+}
+
+void PinnedRing::destroy() {
+  if (!base) return;
+  for (int i = 0; i < kSlots; ++i) cudaEventDestroy(ev[i]);
+  cudaFreeHost(base);
+  base = nullptr;
+}
+
+char *PinnedRing::acquire(size_t bytes, int *slot) {
+  if (bytes > slot_bytes) {
+    // grow: drain everything in flight, then reallocate
+    for (int i = 0; i < kSlots; ++i)
+      if (used[i]) { GCRL_CUDA(cudaEventSynchronize(ev[i])); used[i] = false; }
+    GCRL_CUDA(cudaFreeHost(base));
+    base = nullptr;
+    slot_bytes = (bytes * 2 + 255) & ~size_t(255);
+    GCRL_CUDA(cudaMallocHost(&base, slot_bytes * kSlots));
+  }
+  int s = next;
+  next = (next + 1) % kSlots;
+  if (used[s]) { GCRL_CUDA(cudaEventSynchronize(ev[s])); used[s] = false; }
+  *slot = s;
+  return base + size_t(s) * slot_bytes;
+}
+
+void PinnedRing::release(int slot, cudaStream_t st) {
+  GCRL_CUDA(cudaEventRecord(ev[slot], st));
+  used[slot] = true;
+}
+
+}  // namespace gcrl
+
+extern "C" {
+
+int gcrl_abi_version(void) { return GCRL_ABI_VERSION; }
+
+const char *gcrl_last_error(void) { return gcrl::g_last_error.c_str(); }
+
+int gcrl_device_count(int *count) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(count != nullptr, "count is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  *count = n;
+  GCRL_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// Shared helpers for the gcrl_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+#include "gcrl_b200.h"
+
+namespace gcrl {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string &m);
+
+#define GCRL_CUDA(expr)                                                                    \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      throw ::gcrl::Error(GCRL_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+#define GCRL_REQUIRE(cond, msg)                                          \
+  do {                                                                   \
+    if (!(cond)) throw ::gcrl::Error(GCRL_ERR_INVALID, std::string(msg)); \
+  } while (0)
+
+#define GCRL_API_BEGIN try {
+#define GCRL_API_END                                   \
+  }                                                    \
+  catch (const ::gcrl::Error &e) {                     \
+    ::gcrl::set_last_error(e.what());                  \
+    return e.code;                                     \
+  }                                                    \
+  catch (const std::exception &e) {                    \
+    ::gcrl::set_last_error(e.what());                  \
+    return GCRL_ERR_INVALID;                           \
+  }                                                    \
+  return GCRL_OK;
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// number of SMs of the current device (148 on B200), cached per process
+int sm_count();
+
+template <typename T>
+T *dev_alloc(size_t n) {
+  T *p = nullptr;
+  GCRL_CUDA(cudaMalloc(&p, (n ? n : 1) * sizeof(T)));
+  return p;
+}
+
+// Pinned host staging ring: a slot is reused only after the copy that read it finished.
+struct PinnedRing {
+  static constexpr int kSlots = 8;
+  char *base = nullptr;
+  size_t slot_bytes = 0;
+  cudaEvent_t ev[kSlots] = {};
+  bool used[kSlots] = {};
+  int next = 0;
+  void init(size_t bytes);
+  void destroy();
+  // returns a host pointer valid until release(slot, stream) + the stream reaching it
+  char *acquire(size_t bytes, int *slot);
+  void release(int slot, cudaStream_t st);
+};
+
+// ---- device helpers -------------------------------------------------------------------
+// Exact unsigned division by a runtime constant (Granlund-Montgomery, 32-bit n < 2^31).
+struct FastDiv {
+  uint32_t d, mul, shr;
+  __host__ __device__ FastDiv() : d(1), mul(0), shr(0) {}
+  __host__ __device__ explicit FastDiv(uint32_t div) : d(div) {
+    if (div == 1) { mul = 0; shr = 0; return; }
+    uint32_t l = 0;
+    while ((1u << l) < div) ++l;              // ceil(log2(d))
+    shr = l - 1;
+    mul = (uint32_t)(((1ull << 32) * ((1ull << l) - div)) / div + 1);
+  }
+  __host__ __device__ __forceinline__ uint32_t div(uint32_t n) const {
+#ifdef __CUDA_ARCH__
+    if (d == 1) return n;
+    uint32_t t = __umulhi(n, mul);
+    return (t + ((n - t) >> 1)) >> shr;
+#else
+    return n / d;
+#endif
+  }
+};
+
+__device__ __forceinline__ float4 ldg_stream4(const float4 *p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream4(float4 *p, const float4 &v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du;
+  x ^= x >> 15; x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+
+}  // namespace gcrl

@@ -1,0 +1,622 @@
+// Device-resident HER episode store + lazy future-relabelling sampler (sm_100a).
+//
+// Replaces HERBuffer (reference src/buffer.py:92-179).  The reference materialises
+// every relabelled copy into a Python deque at episode end; here only the T raw
+// transitions of an episode are stored (one packed row each) and sample() maps a deque
+// position -> (episode, t, j) -> relabelled transition on the fly.  The mapping is the
+// one SURVEY.md 8(a-3) proves entry-for-entry equal to apply_her.
+//
+// HBM layout (all fp32 words, row stride a multiple of 16 B):
+//   rows[cap_tr][row_f] : s[D] | ns[D] | a[A] | r | d | ag[G] | fut[k] (uint8, packed) | pad
+//   ag  [cap_tr][gpad]  : compact copy of ag so the future-goal gather touches a 12-16 B
+//                         row of a small (L2-resident at 1M transitions) array
+//   eps [cap_ep]        : {entry_start, tr_slot, T} per live episode (ring, pow2)
+//   buckets[nb]         : episode id holding entry (b << 6) (ring, pow2) -> O(1) lookup
+//   hdr                 : totals, maintained by the commit kernel so that graph-captured
+//                         sample kernels see fresh values without new kernel arguments
+#include <algorithm>
+#include <cstring>
+#include <deque>
+#include <vector>
+
+#include "common.cuh"
+
+namespace gcrl {
+
+constexpr int kBucketShift = 6;
+constexpr int kSamplesPerBlock = 128;
+constexpr int kSampleThreads = 256;
+
+struct __align__(16) EpRec {
+  int64_t entry_start;
+  uint32_t tr_slot;
+  uint32_t T;
+};
+
+struct HerHeader {
+  int64_t total_entries;
+  int64_t len;
+  int64_t ep_first;
+  int64_t ep_last;
+  unsigned long long draw_epoch;
+  unsigned int ticket;
+  unsigned int pad;
+};
+
+struct HerGeom {
+  float *rows;
+  float *ag;
+  EpRec *eps;
+  int64_t *buckets;
+  HerHeader *hdr;
+  uint32_t cap_tr, ep_mask, bucket_mask;
+  int D, G, A, K, row_f, gpad;
+  int off_ns, off_a, off_r, off_d, off_ag, off_fut;
+  FastDiv div_k1, div_D, div_A, div_rf4;
+  uint64_t seed;
+};
+
+struct __align__(16) CommitHdr {
+  int64_t entry_start, eid, total_entries, len, ep_first, first_bucket;
+  uint32_t n_buckets, tr_slot, T, pad;
+};
+static_assert(sizeof(CommitHdr) == 64, "CommitHdr must be 64 bytes");
+
+// ---------------------------------------------------------------------------------------
+// commit: scatter one staged episode blob into the rings
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) her_commit_kernel(HerGeom g, const char *__restrict__ blob) {
+  const CommitHdr h = *reinterpret_cast<const CommitHdr *>(blob);
+  const float4 *src_rows = reinterpret_cast<const float4 *>(blob + sizeof(CommitHdr));
+  const int rf4 = g.row_f >> 2, g4 = g.gpad >> 2;
+  const float4 *src_ag = src_rows + size_t(h.T) * rf4;
+  float4 *rows4 = reinterpret_cast<float4 *>(g.rows);
+  float4 *ag4 = reinterpret_cast<float4 *>(g.ag);
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nth = gridDim.x * blockDim.x;
+  for (int e = tid; e < int(h.T) * rf4; e += nth) {
+    uint32_t t = g.div_rf4.div(e), q = e - t * rf4;
+    uint32_t slot = h.tr_slot + t;
+    if (slot >= g.cap_tr) slot -= g.cap_tr;
+    rows4[size_t(slot) * rf4 + q] = src_rows[e];
+  }
+  for (int e = tid; e < int(h.T) * g4; e += nth) {
+    uint32_t t = e / g4, q = e - t * g4;
+    uint32_t slot = h.tr_slot + t;
+    if (slot >= g.cap_tr) slot -= g.cap_tr;
+    ag4[size_t(slot) * g4 + q] = src_ag[e];
+  }
+  for (int b = tid; b < int(h.n_buckets); b += nth)
+    g.buckets[(h.first_bucket + b) & g.bucket_mask] = h.eid;
+  if (tid == 0) {
+    EpRec rec;
+    rec.entry_start = h.entry_start;
+    rec.tr_slot = h.tr_slot;
+    rec.T = h.T;
+    g.eps[h.eid & g.ep_mask] = rec;
+    g.hdr->total_entries = h.total_entries;
+    g.hdr->len = h.len;
+    g.hdr->ep_first = h.ep_first;
+    g.hdr->ep_last = h.eid;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// on-device index stream: keyed 4-round Feistel permutation of [0, n) with cycle walking.
+// Position i of call `epoch` is perm_epoch(i): B distinct, uniformly spread positions,
+// i.e. sampling WITHOUT replacement like random.sample (reference src/buffer.py:124).
+// ---------------------------------------------------------------------------------------
+__host__ __device__ inline int64_t feistel_position(uint64_t x, uint64_t n, uint64_t seed,
+                                                    uint64_t epoch) {
+  if (n <= 1) return 0;
+  int b = 0;
+  while (b < 63 && (1ull << b) < n) ++b;
+  if (b < 2) b = 2;
+  b += (b & 1);
+  const int half = b >> 1;
+  const uint32_t mask = half >= 32 ? 0xffffffffu : ((1u << half) - 1u);
+  const uint64_t k0 = splitmix64(seed ^ (epoch * 0xD1B54A32D192ED03ull));
+  const uint64_t k1 = splitmix64(k0);
+  const uint32_t keys[4] = {uint32_t(k0), uint32_t(k0 >> 32), uint32_t(k1), uint32_t(k1 >> 32)};
+  do {
+    uint32_t L = uint32_t(x >> half) & mask, R = uint32_t(x) & mask;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      uint32_t nl = R;
+      R = L ^ (mix32(R ^ keys[r]) & mask);
+      L = nl;
+    }
+    x = (uint64_t(L) << half) | R;
+  } while (x >= n);
+  return int64_t(x);
+}
+
+// ---------------------------------------------------------------------------------------
+// sample: gather + relabel + reward, 128 samples per CTA staged through shared memory so
+// both the row gathers (16 B vectors, 13 per Push row) and the five output streams are
+// coalesced.
+// ---------------------------------------------------------------------------------------
+template <bool VEC>
+__device__ __forceinline__ void write_field(float *__restrict__ out, const float *tile, int n,
+                                            int width, int off, int row_f, const FastDiv &dw,
+                                            int tid) {
+  const int total = n * width;
+  if (VEC) {
+    for (int q = tid * 4; q < total; q += kSampleThreads * 4) {
+      uint32_t i = dw.div(q), c = q - i * width;
+      if (q + 3 < total) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          v[u] = tile[i * row_f + off + c];
+          if (++c == uint32_t(width)) { c = 0; ++i; }
+        }
+        stg_stream4(reinterpret_cast<float4 *>(out + q), make_float4(v[0], v[1], v[2], v[3]));
+      } else {
+        for (int e = q; e < total; ++e) {
+          out[e] = tile[i * row_f + off + c];
+          if (++c == uint32_t(width)) { c = 0; ++i; }
+        }
+      }
+    }
+  } else {
+    for (int q = tid; q < total; q += kSampleThreads) {
+      uint32_t i = dw.div(q), c = q - i * width;
+      out[q] = tile[i * row_f + off + c];
+    }
+  }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kSampleThreads)
+her_sample_kernel(HerGeom g, int64_t B, const int64_t *__restrict__ idx, float *__restrict__ out_s,
+                  float *__restrict__ out_a, float *__restrict__ out_r, float *__restrict__ out_ns,
+                  float *__restrict__ out_d, int64_t *__restrict__ idx_out) {
+  extern __shared__ float4 smem4[];
+  float *tile = reinterpret_cast<float *>(smem4);
+  uint32_t *m_row = reinterpret_cast<uint32_t *>(tile + kSamplesPerBlock * g.row_f);
+  uint32_t *m_ep0 = m_row + kSamplesPerBlock;
+  uint32_t *m_j = m_ep0 + kSamplesPerBlock;
+
+  const int tid = threadIdx.x;
+  const int64_t base = int64_t(blockIdx.x) * kSamplesPerBlock;
+  const int n = int(min(int64_t(kSamplesPerBlock), B - base));
+
+  // ---- phase 1: deque position -> (episode, t, j) -> ring slot -------------------------
+  if (tid < n) {
+    const HerHeader *hdr = g.hdr;
+    const int64_t total = hdr->total_entries, len = hdr->len, ep_last = hdr->ep_last;
+    int64_t p;
+    if (idx != nullptr) {
+      p = idx[base + tid];
+      p = p < 0 ? 0 : (p >= len ? len - 1 : p);
+    } else {
+      p = feistel_position(uint64_t(base + tid), uint64_t(len), g.seed, hdr->draw_epoch);
+    }
+    if (idx_out != nullptr) idx_out[base + tid] = p;
+    const int64_t ge = total - len + p;  // global entry id
+    const int64_t b = ge >> kBucketShift;
+    int64_t lo = g.buckets[b & g.bucket_mask];
+    lo = lo < hdr->ep_first ? hdr->ep_first : lo;  // never look at evicted episode records
+    int64_t hi = (((b + 1) << kBucketShift) < total) ? g.buckets[(b + 1) & g.bucket_mask] : ep_last;
+    EpRec rec = g.eps[lo & g.ep_mask];
+    while (lo < hi) {  // largest episode id in [lo, hi] whose first entry is <= ge
+      const int64_t mid = (lo + hi + 1) >> 1;
+      const EpRec r2 = g.eps[mid & g.ep_mask];
+      if (r2.entry_start <= ge) { lo = mid; rec = r2; } else { hi = mid - 1; }
+    }
+    const uint32_t o = uint32_t(ge - rec.entry_start);
+    uint32_t t = g.div_k1.div(o);
+    uint32_t j = o - t * uint32_t(g.K + 1);
+    if (t >= rec.T - 1) { t = rec.T - 1; j = 0; }  // last step carries no relabels
+    uint32_t slot = rec.tr_slot + t;
+    if (slot >= g.cap_tr) slot -= g.cap_tr;
+    m_row[tid] = slot;
+    m_ep0[tid] = rec.tr_slot;
+    m_j[tid] = j;
+  }
+  __syncthreads();
+
+  // ---- phase 2: coalesced 16 B gathers of the packed rows into shared memory -----------
+  {
+    const int rf4 = g.row_f >> 2;
+    const int nchunks = n * rf4;
+    const float4 *rows4 = reinterpret_cast<const float4 *>(g.rows);
+    for (int c0 = tid; c0 < nchunks; c0 += kSampleThreads * 4) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + u * kSampleThreads;
+        if (c < nchunks) {
+          const uint32_t i = g.div_rf4.div(c), q = c - i * rf4;
+          v[u] = ldg_stream4(rows4 + size_t(m_row[i]) * rf4 + q);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + u * kSampleThreads;
+        if (c < nchunks) smem4[c] = v[u];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 3: future-goal relabel + sparse reward (bit-exact fp32, no FMA) -----------
+  if (tid < n) {
+    const uint32_t j = m_j[tid];
+    if (j > 0) {
+      float *row = tile + tid * g.row_f;
+      const uint8_t *fut = reinterpret_cast<const uint8_t *>(row + g.off_fut);
+      uint32_t fs = m_ep0[tid] + uint32_t(fut[j - 1]);
+      if (fs >= g.cap_tr) fs -= g.cap_tr;
+      const float *agf = g.ag + size_t(fs) * g.gpad;
+      float acc = 0.f;
+      for (int c = 0; c < g.G; ++c) {
+        const float gf = __ldg(agf + c);
+        const float diff = __fsub_rn(row[g.off_ag + c], gf);   // achieved(t) - future goal
+        const float sq = __fmul_rn(diff, diff);
+        acc = (c == 0) ? sq : __fadd_rn(acc, sq);              // left-to-right, no FMA
+        row[g.D - g.G + c] = gf;
+        row[g.off_ns + g.D - g.G + c] = gf;
+      }
+      const float dist = __fsqrt_rn(acc);
+      row[g.off_r] = (dist > 0.05f) ? -1.0f : -0.0f;            // -(d > 0.05) as float32
+      row[g.off_d] = 0.0f;                                      // new_done = False
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 4: coalesced write-out of the five output tensors --------------------------
+  const FastDiv one(1);
+  write_field<VEC>(out_s + base * g.D, tile, n, g.D, 0, g.row_f, g.div_D, tid);
+  write_field<VEC>(out_ns + base * g.D, tile, n, g.D, g.off_ns, g.row_f, g.div_D, tid);
+  write_field<VEC>(out_a + base * g.A, tile, n, g.A, g.off_a, g.row_f, g.div_A, tid);
+  write_field<VEC>(out_r + base, tile, n, 1, g.off_r, g.row_f, one, tid);
+  write_field<VEC>(out_d + base, tile, n, 1, g.off_d, g.row_f, one, tid);
+
+  // device index stream: the last CTA to finish advances the draw epoch
+  if (idx == nullptr && tid == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(&g.hdr->ticket, 1u);
+    if (t == gridDim.x - 1) {
+      g.hdr->ticket = 0;
+      atomicAdd(&g.hdr->draw_epoch, 1ull);
+    }
+  }
+}
+
+}  // namespace gcrl
+
+// ---------------------------------------------------------------------------------------
+// host object
+// ---------------------------------------------------------------------------------------
+using namespace gcrl;
+
+struct gcrl_her {
+  int device = 0;
+  int64_t max_entries = 0, cap_tr = 0, cap_ep = 0, nb = 0;
+  HerGeom g{};
+  // host bookkeeping (mirrors the reference deque's counters)
+  int64_t total_entries = 0, total_tr = 0, next_eid = 0, ep_first = 0, tr_live_first = 0;
+  std::deque<std::pair<int64_t, int>> live;  // (entry_end, T) of live episodes, oldest first
+  uint64_t seed = 0, host_ctr = 0;
+  PinnedRing stage;
+  char *d_stage[PinnedRing::kSlots] = {};
+  size_t blob_max = 0;
+  PinnedRing idx_stage;
+  int64_t *d_idx = nullptr;
+  size_t idx_cap = 0;
+  // device scratch for the host-output path
+  float *d_out = nullptr;
+  int64_t *d_idx_out = nullptr;
+  size_t out_cap = 0;
+  size_t smem_bytes = 0;
+
+  int64_t len() const { return std::min(total_entries, max_entries); }
+};
+
+static void her_launch_sample(gcrl_her *h, int64_t B, const int64_t *idx_dev, float *s, float *a,
+                              float *r, float *ns, float *d, int64_t *idx_out, cudaStream_t st) {
+  const unsigned blocks = unsigned((B + kSamplesPerBlock - 1) / kSamplesPerBlock);
+  auto aligned = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  const bool vec = aligned(s) && aligned(a) && aligned(r) && aligned(ns) && aligned(d);
+  if (vec)
+    her_sample_kernel<true><<<blocks, kSampleThreads, h->smem_bytes, st>>>(h->g, B, idx_dev, s, a, r,
+                                                                         ns, d, idx_out);
+  else
+    her_sample_kernel<false><<<blocks, kSampleThreads, h->smem_bytes, st>>>(h->g, B, idx_dev, s, a,
+                                                                          r, ns, d, idx_out);
+  GCRL_CUDA(cudaGetLastError());
+}
+
+static const int64_t *her_stage_indices(gcrl_her *h, int64_t B, const int64_t *idx_host,
+                                        cudaStream_t st) {
+  if (idx_host == nullptr) return nullptr;
+  const int64_t len = h->len();
+  for (int64_t i = 0; i < B; ++i)
+    if (idx_host[i] < 0 || idx_host[i] >= len)
+      throw Error(GCRL_ERR_INVALID, "sample index out of range [0, len)");
+  if (size_t(B) > h->idx_cap) {
+    GCRL_CUDA(cudaStreamSynchronize(st));
+    if (h->d_idx) GCRL_CUDA(cudaFree(h->d_idx));
+    h->idx_cap = size_t(B) * 2;
+    h->d_idx = dev_alloc<int64_t>(h->idx_cap);
+  }
+  int slot;
+  char *p = h->idx_stage.acquire(size_t(B) * sizeof(int64_t), &slot);
+  std::memcpy(p, idx_host, size_t(B) * sizeof(int64_t));
+  GCRL_CUDA(cudaMemcpyAsync(h->d_idx, p, size_t(B) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  h->idx_stage.release(slot, st);
+  return h->d_idx;
+}
+
+// Exposed to the agent translation unit (fused sample + update path).
+namespace gcrl {
+void her_sample_into(gcrl_her *h, int64_t B, const int64_t *idx_host, float *s, float *a, float *r,
+                     float *ns, float *d, int64_t *idx_out, cudaStream_t st) {
+  GCRL_REQUIRE(B >= 0, "negative batch size");
+  if (h->len() < B)
+    throw Error(GCRL_ERR_UNDERFILLED, "[ERROR] Not enough in buffer to sample");
+  if (B == 0) return;
+  const int64_t *idx_dev = her_stage_indices(h, B, idx_host, st);
+  her_launch_sample(h, B, idx_dev, s, a, r, ns, d, idx_out, st);
+}
+int her_state_dim(const gcrl_her *h) { return h->g.D; }
+int her_act_dim(const gcrl_her *h) { return h->g.A; }
+int her_device(const gcrl_her *h) { return h->device; }
+}  // namespace gcrl
+
+static int64_t next_pow2(int64_t x) {
+  int64_t p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+extern "C" {
+
+int gcrl_her_create(gcrl_her **out, int device, int64_t max_entries, int64_t cap_transitions,
+                    int state_dim, int goal_dim, int act_dim, int k_future, uint64_t seed) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(out != nullptr, "out is NULL");
+  GCRL_REQUIRE(max_entries >= 1, "max_entries must be >= 1");
+  GCRL_REQUIRE(goal_dim >= 1 && state_dim > goal_dim, "need state_dim > goal_dim >= 1");
+  GCRL_REQUIRE(act_dim >= 1 && k_future >= 0 && k_future <= 64, "bad act_dim / k_future");
+  if (cap_transitions <= 0) cap_transitions = max_entries;
+  GCRL_REQUIRE(cap_transitions < (int64_t(1) << 31), "cap_transitions must be < 2^31");
+  GCRL_CUDA(cudaSetDevice(device));
+  auto *h = new gcrl_her();
+  try {
+    h->device = device;
+    h->max_entries = max_entries;
+    h->cap_tr = cap_transitions;
+    h->cap_ep = next_pow2(cap_transitions);
+    h->nb = next_pow2((max_entries >> kBucketShift) + 4);
+    h->seed = seed;
+    HerGeom &g = h->g;
+    g.D = state_dim; g.G = goal_dim; g.A = act_dim; g.K = k_future;
+    g.off_ns = state_dim;
+    g.off_a = 2 * state_dim;
+    g.off_r = g.off_a + act_dim;
+    g.off_d = g.off_r + 1;
+    g.off_ag = g.off_d + 1;
+    g.off_fut = g.off_ag + goal_dim;
+    g.row_f = (g.off_fut + (k_future + 3) / 4 + 3) & ~3;
+    g.gpad = (goal_dim + 3) & ~3;
+    g.cap_tr = uint32_t(h->cap_tr);
+    g.ep_mask = uint32_t(h->cap_ep - 1);
+    g.bucket_mask = uint32_t(h->nb - 1);
+    g.div_k1 = FastDiv(uint32_t(k_future + 1));
+    g.div_D = FastDiv(uint32_t(state_dim));
+    g.div_A = FastDiv(uint32_t(act_dim));
+    g.div_rf4 = FastDiv(uint32_t(g.row_f / 4));
+    g.seed = seed;
+    h->smem_bytes = size_t(kSamplesPerBlock) * g.row_f * 4 + 3 * kSamplesPerBlock * 4;
+    GCRL_REQUIRE(h->smem_bytes <= 227 * 1024, "transition row too wide for the sampler tile");
+    g.rows = dev_alloc<float>(size_t(h->cap_tr) * g.row_f);
+    g.ag = dev_alloc<float>(size_t(h->cap_tr) * g.gpad);
+    g.eps = dev_alloc<EpRec>(size_t(h->cap_ep));
+    g.buckets = dev_alloc<int64_t>(size_t(h->nb));
+    g.hdr = dev_alloc<HerHeader>(1);
+    GCRL_CUDA(cudaMemset(g.hdr, 0, sizeof(HerHeader)));
+    GCRL_CUDA(cudaMemset(g.buckets, 0, size_t(h->nb) * sizeof(int64_t)));
+    GCRL_CUDA(cudaMemset(g.eps, 0, size_t(h->cap_ep) * sizeof(EpRec)));
+    h->blob_max = sizeof(CommitHdr) + size_t(255) * (g.row_f + g.gpad) * 4;
+    h->stage.init(h->blob_max);
+    for (int i = 0; i < PinnedRing::kSlots; ++i) h->d_stage[i] = dev_alloc<char>(h->blob_max);
+    h->idx_stage.init(size_t(1) << 16);
+    GCRL_CUDA(cudaFuncSetAttribute(her_sample_kernel<true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->smem_bytes)));
+    GCRL_CUDA(cudaFuncSetAttribute(her_sample_kernel<false>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->smem_bytes)));
+  } catch (...) {
+    delete h;
+    throw;
+  }
+  *out = h;
+  GCRL_API_END
+}
+
+int gcrl_her_destroy(gcrl_her *h) {
+  GCRL_API_BEGIN
+  if (h == nullptr) return GCRL_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  cudaFree(h->g.rows); cudaFree(h->g.ag); cudaFree(h->g.eps); cudaFree(h->g.buckets);
+  cudaFree(h->g.hdr);
+  for (auto p : h->d_stage) cudaFree(p);
+  if (h->d_idx) cudaFree(h->d_idx);
+  if (h->d_out) cudaFree(h->d_out);
+  if (h->d_idx_out) cudaFree(h->d_idx_out);
+  h->stage.destroy();
+  h->idx_stage.destroy();
+  delete h;
+  GCRL_API_END
+}
+
+int gcrl_her_push_episode(gcrl_her *h, int T, const float *s, const float *a, const float *ns,
+                          const float *r, const float *d, const float *ag, const uint8_t *fut,
+                          void *stream) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(h != nullptr, "handle is NULL");
+  GCRL_REQUIRE(T >= 1 && T <= 255, "episode length must be in [1, 255]");
+  GCRL_REQUIRE(s && a && ns && r && d && ag, "NULL episode array");
+  GCRL_CUDA(cudaSetDevice(h->device));
+  const HerGeom &g = h->g;
+  const int k = g.K;
+  const int64_t E = int64_t(T - 1) * (k + 1) + 1;
+  // ---- eviction accounting (per-entry FIFO of deque(maxlen), src/buffer.py:101) ----
+  const int64_t new_total = h->total_entries + E;
+  const int64_t new_len = std::min(new_total, h->max_entries);
+  const int64_t first_live = new_total - new_len;
+  int64_t ep_first = h->ep_first, tr_live_first = h->tr_live_first;
+  size_t drop = 0;
+  while (drop < h->live.size() && h->live[drop].first <= first_live) {
+    tr_live_first += h->live[drop].second;
+    ++ep_first;
+    ++drop;
+  }
+  if (h->total_tr + T - tr_live_first > h->cap_tr)
+    throw Error(GCRL_ERR_CAPACITY, "transition ring too small for the live window");
+  if (h->next_eid + 1 - ep_first > h->cap_ep)
+    throw Error(GCRL_ERR_CAPACITY, "episode ring too small for the live window");
+  // ---- stage the blob ----
+  const size_t bytes = sizeof(CommitHdr) + size_t(T) * (g.row_f + g.gpad) * 4;
+  int slot;
+  char *blob = h->stage.acquire(bytes, &slot);
+  auto *ch = reinterpret_cast<CommitHdr *>(blob);
+  ch->entry_start = h->total_entries;
+  ch->eid = h->next_eid;
+  ch->total_entries = new_total;
+  ch->len = new_len;
+  ch->ep_first = ep_first;
+  const int64_t b0 = (h->total_entries + (1 << kBucketShift) - 1) >> kBucketShift;
+  const int64_t b1 = (new_total + (1 << kBucketShift) - 1) >> kBucketShift;  // exclusive
+  ch->first_bucket = b0;
+  ch->n_buckets = uint32_t(b1 - b0);
+  ch->tr_slot = uint32_t(h->total_tr % h->cap_tr);
+  ch->T = uint32_t(T);
+  ch->pad = 0;
+  float *rows = reinterpret_cast<float *>(blob + sizeof(CommitHdr));
+  float *agc = rows + size_t(T) * g.row_f;
+  for (int t = 0; t < T; ++t) {
+    float *row = rows + size_t(t) * g.row_f;
+    std::memset(row, 0, size_t(g.row_f) * 4);
+    std::memcpy(row, s + size_t(t) * g.D, size_t(g.D) * 4);
+    std::memcpy(row + g.off_ns, ns + size_t(t) * g.D, size_t(g.D) * 4);
+    std::memcpy(row + g.off_a, a + size_t(t) * g.A, size_t(g.A) * 4);
+    row[g.off_r] = r[t];
+    row[g.off_d] = d[t];
+    std::memcpy(row + g.off_ag, ag + size_t(t) * g.G, size_t(g.G) * 4);
+    uint8_t *fb = reinterpret_cast<uint8_t *>(row + g.off_fut);
+    if (t < T - 1) {
+      for (int j = 0; j < k; ++j) {
+        int f;
+        if (fut != nullptr) {
+          f = fut[size_t(t) * k + j];
+          if (f <= t || f >= T) throw Error(GCRL_ERR_INVALID, "future index outside [t+1, T-1]");
+        } else {
+          f = t + 1 + int(splitmix64(h->seed ^ (0xA5A5A5A5ull + h->host_ctr++)) % uint64_t(T - 1 - t));
+        }
+        fb[j] = uint8_t(f);
+      }
+    }
+    float *agr = agc + size_t(t) * g.gpad;
+    std::memset(agr, 0, size_t(g.gpad) * 4);
+    std::memcpy(agr, ag + size_t(t) * g.G, size_t(g.G) * 4);
+  }
+  cudaStream_t st = as_stream(stream);
+  GCRL_CUDA(cudaMemcpyAsync(h->d_stage[slot], blob, bytes, cudaMemcpyHostToDevice, st));
+  h->stage.release(slot, st);
+  const int work = T * (g.row_f / 4);
+  const int blocks = std::max(1, std::min(32, (work + 255) / 256));
+  her_commit_kernel<<<blocks, 256, 0, st>>>(g, h->d_stage[slot]);
+  GCRL_CUDA(cudaGetLastError());
+  // ---- commit host counters ----
+  h->live.erase(h->live.begin(), h->live.begin() + drop);
+  h->live.emplace_back(new_total, T);
+  h->ep_first = ep_first;
+  h->tr_live_first = tr_live_first;
+  h->total_entries = new_total;
+  h->total_tr += T;
+  h->next_eid += 1;
+  GCRL_API_END
+}
+
+int64_t gcrl_her_len(const gcrl_her *h) { return h ? h->len() : 0; }
+int64_t gcrl_her_total_entries(const gcrl_her *h) { return h ? h->total_entries : 0; }
+int64_t gcrl_her_live_transitions(const gcrl_her *h) {
+  return h ? h->total_tr - h->tr_live_first : 0;
+}
+
+int gcrl_her_clear(gcrl_her *h) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(h != nullptr, "handle is NULL");
+  GCRL_CUDA(cudaSetDevice(h->device));
+  GCRL_CUDA(cudaDeviceSynchronize());
+  GCRL_CUDA(cudaMemset(h->g.hdr, 0, sizeof(HerHeader)));
+  h->total_entries = h->total_tr = h->next_eid = h->ep_first = h->tr_live_first = 0;
+  h->live.clear();
+  GCRL_API_END
+}
+
+int gcrl_her_sample(gcrl_her *h, int64_t B, const int64_t *idx_host, float *states_dev,
+                    float *actions_dev, float *rewards_dev, float *next_states_dev,
+                    float *dones_dev, int64_t *idx_out_dev, void *stream) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(h != nullptr, "handle is NULL");
+  GCRL_REQUIRE(B == 0 || (states_dev && actions_dev && rewards_dev && next_states_dev && dones_dev),
+               "NULL output");
+  GCRL_CUDA(cudaSetDevice(h->device));
+  her_sample_into(h, B, idx_host, states_dev, actions_dev, rewards_dev, next_states_dev, dones_dev,
+                  idx_out_dev, as_stream(stream));
+  GCRL_API_END
+}
+
+int gcrl_her_sample_dev_idx(gcrl_her *h, int64_t B, const int64_t *idx_dev, float *states_dev,
+                            float *actions_dev, float *rewards_dev, float *next_states_dev,
+                            float *dones_dev, void *stream) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(h != nullptr && idx_dev != nullptr, "NULL handle / indices");
+  GCRL_CUDA(cudaSetDevice(h->device));
+  if (h->len() < B) throw Error(GCRL_ERR_UNDERFILLED, "[ERROR] Not enough in buffer to sample");
+  if (B > 0)
+    her_launch_sample(h, B, idx_dev, states_dev, actions_dev, rewards_dev, next_states_dev,
+                      dones_dev, nullptr, as_stream(stream));
+  GCRL_API_END
+}
+
+int gcrl_her_sample_host(gcrl_her *h, int64_t B, const int64_t *idx_host, float *states,
+                         float *actions, float *rewards, float *next_states, float *dones,
+                         int64_t *idx_out, void *stream) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(h != nullptr, "handle is NULL");
+  GCRL_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = as_stream(stream);
+  const HerGeom &g = h->g;
+  const size_t per = size_t(2 * g.D + g.A + 2);
+  const size_t Bp = (size_t(B) + 3) & ~size_t(3);  // keep every field 16 B aligned
+  if (Bp > h->out_cap) {
+    GCRL_CUDA(cudaStreamSynchronize(st));
+    if (h->d_out) GCRL_CUDA(cudaFree(h->d_out));
+    if (h->d_idx_out) GCRL_CUDA(cudaFree(h->d_idx_out));
+    h->out_cap = Bp * 2;
+    h->d_out = dev_alloc<float>(h->out_cap * per);
+    h->d_idx_out = dev_alloc<int64_t>(h->out_cap);
+  }
+  float *ds = h->d_out, *dns = ds + Bp * g.D, *da = dns + Bp * g.D, *dr = da + Bp * g.A,
+        *dd = dr + Bp;
+  her_sample_into(h, B, idx_host, ds, da, dr, dns, dd, idx_out ? h->d_idx_out : nullptr, st);
+  if (B > 0) {
+    GCRL_CUDA(cudaMemcpyAsync(states, ds, size_t(B) * g.D * 4, cudaMemcpyDeviceToHost, st));
+    GCRL_CUDA(cudaMemcpyAsync(next_states, dns, size_t(B) * g.D * 4, cudaMemcpyDeviceToHost, st));
+    GCRL_CUDA(cudaMemcpyAsync(actions, da, size_t(B) * g.A * 4, cudaMemcpyDeviceToHost, st));
+    GCRL_CUDA(cudaMemcpyAsync(rewards, dr, size_t(B) * 4, cudaMemcpyDeviceToHost, st));
+    GCRL_CUDA(cudaMemcpyAsync(dones, dd, size_t(B) * 4, cudaMemcpyDeviceToHost, st));
+    if (idx_out)
+      GCRL_CUDA(cudaMemcpyAsync(idx_out, h->d_idx_out, size_t(B) * 8, cudaMemcpyDeviceToHost, st));
+    GCRL_CUDA(cudaStreamSynchronize(st));
+  }
+  GCRL_API_END
+}
+
+}  // extern "C"

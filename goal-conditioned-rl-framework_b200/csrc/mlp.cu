@@ -1,0 +1,584 @@
+// fp32 (FFMA) forward / backward kernels for the 64..512-wide actor / critic MLPs.
+//
+// Replaces the torch library calls behind Actor/Critic (reference src/model.py:7-83) and
+// autograd in DDPG.critic_update / actor_update (src/agent.py:1288-1343): nn.Linear,
+// LeakyReLU(0.01), Tanh, torch.cat (folded: the producers write straight into the
+// [state | action] rows), mse / smooth-l1 and the backward GEMMs.  This is the
+// parity-exact path (plain fp32 fused multiply-add, deterministic fixed-order
+// reductions).
+#include <algorithm>
+
+#include "mlp.cuh"
+
+namespace gcrl {
+
+enum : int { OP_FWD = 0, OP_DGRAD = 1, OP_WGRAD = 2 };
+
+struct GemmParams {
+  const float *A; int lda;
+  const float *B; int ldb;
+  float *C; int ldc;
+  const float *bias;
+  const float *act; int ldact;
+  float *Cb;
+  int M, N, K;
+  int act_mode;
+  int k_chunk;
+  int64_t c_split_stride, cb_split_stride;
+};
+
+constexpr int BK = 16;
+constexpr int SPAD = 4;
+
+// ---- tile loaders ------------------------------------------------------------------------
+// RC: element (i, r) at base[i * ld + r]  (reduction index contiguous)
+template <int BT, int NT>
+__device__ __forceinline__ void load_rc(const float *__restrict__ base, int ld, int i0, int imax, int r0,
+                                        int rmax, float4 (&reg)[BT * 4 / NT], int tid) {
+#pragma unroll
+  for (int u = 0; u < BT * 4 / NT; ++u) {
+    const int c = tid + u * NT;
+    const int i = c >> 2, q = c & 3;
+    const int gi = i0 + i, gr = r0 + q * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gi < imax && gr < rmax) {
+      const float *ptr = base + size_t(gi) * ld + gr;
+      if (gr + 3 < rmax) {
+        v = *reinterpret_cast<const float4 *>(ptr);
+      } else {
+        v.x = ptr[0];
+        if (gr + 1 < rmax) v.y = ptr[1];
+        if (gr + 2 < rmax) v.z = ptr[2];
+      }
+    }
+    reg[u] = v;
+  }
+}
+template <int BT, int NT>
+__device__ __forceinline__ void store_rc(float (*S)[BT + SPAD], const float4 (&reg)[BT * 4 / NT], int tid) {
+#pragma unroll
+  for (int u = 0; u < BT * 4 / NT; ++u) {
+    const int c = tid + u * NT;
+    const int i = c >> 2, q = c & 3;
+    S[q * 4 + 0][i] = reg[u].x;
+    S[q * 4 + 1][i] = reg[u].y;
+    S[q * 4 + 2][i] = reg[u].z;
+    S[q * 4 + 3][i] = reg[u].w;
+  }
+}
+// IC: element (i, r) at base[r * ld + i]  (output index contiguous)
+template <int BT, int NT>
+__device__ __forceinline__ void load_ic(const float *__restrict__ base, int ld, int i0, int imax, int r0,
+                                        int rmax, float4 (&reg)[BT * 4 / NT], int tid) {
+#pragma unroll
+  for (int u = 0; u < BT * 4 / NT; ++u) {
+    const int c = tid + u * NT;
+    const int r = c / (BT / 4), q = c % (BT / 4);
+    const int gr = r0 + r, gi = i0 + q * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gr < rmax && gi < imax) {
+      const float *ptr = base + size_t(gr) * ld + gi;
+      if (gi + 3 < imax) {
+        v = *reinterpret_cast<const float4 *>(ptr);
+      } else {
+        v.x = ptr[0];
+        if (gi + 1 < imax) v.y = ptr[1];
+        if (gi + 2 < imax) v.z = ptr[2];
+      }
+    }
+    reg[u] = v;
+  }
+}
+template <int BT, int NT>
+__device__ __forceinline__ void store_ic(float (*S)[BT + SPAD], const float4 (&reg)[BT * 4 / NT], int tid) {
+#pragma unroll
+  for (int u = 0; u < BT * 4 / NT; ++u) {
+    const int c = tid + u * NT;
+    const int r = c / (BT / 4), q = c % (BT / 4);
+    *reinterpret_cast<float4 *>(&S[r][q * 4]) = reg[u];
+  }
+}
+
+// ---- tiled SGEMM: C[M,N] = sum_r A(m,r) B(r,n) with op-specific operand layouts -----------
+//   OP_FWD  : A = X  (RC),  B = W  (RC),  epilogue + bias, LeakyReLU
+//   OP_DGRAD: A = dZ (RC),  B = W  (IC),  epilogue * LeakyReLU'(act)
+//   OP_WGRAD: A = dZ (IC),  B = X  (IC),  reduction = batch, split over blockIdx.z; the CTAs
+//             of the first tile column also emit the bias gradient (column sums of dZ)
+template <int BM, int BN, int TM, int TN, int OP>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(GemmParams p) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  constexpr int TXN = BN / TN;
+  static_assert((BM * 4) % NT == 0 && (BN * 4) % NT == 0, "tile/threads mismatch");
+  static_assert(TM == 4 || TM == 8, "TM");
+  static_assert(TN == 4 || TN == 8, "TN");
+  __shared__ __align__(16) float As[2][BK][BM + SPAD];
+  __shared__ __align__(16) float Bs[2][BK][BN + SPAD];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % TXN, ty = tid / TXN;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  int rbeg = 0, rend = p.K;
+  if (OP == OP_WGRAD) {
+    rbeg = blockIdx.z * p.k_chunk;
+    rend = min(p.K, rbeg + p.k_chunk);
+  }
+  const int nk = (rend - rbeg + BK - 1) / BK;
+
+  float4 ra[BM * 4 / NT], rb[BN * 4 / NT];
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  float bsum = 0.f;
+
+  auto gload = [&](int t) {
+    const int r0 = rbeg + t * BK;
+    if (OP == OP_WGRAD) load_ic<BM, NT>(p.A, p.lda, m0, p.M, r0, rend, ra, tid);
+    else                load_rc<BM, NT>(p.A, p.lda, m0, p.M, r0, rend, ra, tid);
+    if (OP == OP_FWD)   load_rc<BN, NT>(p.B, p.ldb, n0, p.N, r0, rend, rb, tid);
+    else                load_ic<BN, NT>(p.B, p.ldb, n0, p.N, r0, rend, rb, tid);
+  };
+  auto sstore = [&](int buf) {
+    if (OP == OP_WGRAD) store_ic<BM, NT>(As[buf], ra, tid); else store_rc<BM, NT>(As[buf], ra, tid);
+    if (OP == OP_FWD)   store_rc<BN, NT>(Bs[buf], rb, tid); else store_ic<BN, NT>(Bs[buf], rb, tid);
+  };
+
+  if (nk > 0) {
+    gload(0);
+    sstore(0);
+  }
+  __syncthreads();
+  for (int t = 0; t < nk; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < nk) gload(t + 1);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[TM], b[TN];
+      {
+        const float4 v = *reinterpret_cast<const float4 *>(&As[buf][k][ty * 4]);
+        a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+        if (TM == 8) {
+          const float4 w = *reinterpret_cast<const float4 *>(&As[buf][k][BM / 2 + ty * 4]);
+          a[TM - 4] = w.x; a[TM - 3] = w.y; a[TM - 2] = w.z; a[TM - 1] = w.w;
+        }
+      }
+      {
+        const float4 v = *reinterpret_cast<const float4 *>(&Bs[buf][k][tx * 4]);
+        b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
+        if (TN == 8) {
+          const float4 w = *reinterpret_cast<const float4 *>(&Bs[buf][k][BN / 2 + tx * 4]);
+          b[TN - 4] = w.x; b[TN - 3] = w.y; b[TN - 2] = w.z; b[TN - 1] = w.w;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (OP == OP_WGRAD && blockIdx.x == 0 && tid < BM) {
+#pragma unroll
+      for (int k = 0; k < BK; ++k) bsum += As[buf][k][tid];
+    }
+    if (t + 1 < nk) sstore(buf ^ 1);
+    __syncthreads();
+  }
+
+  // ---- epilogue ----
+  float *C = p.C;
+  if (OP == OP_WGRAD) C += int64_t(blockIdx.z) * p.c_split_stride;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ((TM == 8 && i >= 4) ? (BM / 2 + ty * 4 + i - 4) : (ty * 4 + i));
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int jh = 0; jh < TN / 4; ++jh) {
+      const int n = n0 + (jh == 0 ? tx * 4 : BN / 2 + tx * 4);
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float x = acc[i][jh * 4 + j];
+        const int nn = n + j;
+        if (nn < p.N) {
+          if (OP == OP_FWD) {
+            x += p.bias[nn];
+            if (p.act_mode == ACT_LEAKY) x = x > 0.f ? x : x * kLeakySlope;
+          } else if (OP == OP_DGRAD) {
+            if (p.act != nullptr) {
+              const float h = p.act[size_t(m) * p.ldact + nn];
+              x = h > 0.f ? x : x * kLeakySlope;
+            }
+          }
+        }
+        v[j] = x;
+      }
+      // weight-gradient slabs are written over the full padded row (zeros beyond N) so the
+      // fixed-order reduction never reads an unwritten word
+      const int nbound = (OP == OP_WGRAD) ? p.ldc : p.N;
+      float *dst = C + size_t(m) * p.ldc + n;
+      if (n + 3 < nbound) {
+        *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n + j < nbound) dst[j] = v[j];
+      }
+    }
+  }
+  if (OP == OP_WGRAD && blockIdx.x == 0 && tid < BM && m0 + tid < p.M)
+    p.Cb[int64_t(blockIdx.z) * p.cb_split_stride + m0 + tid] = bsum;
+}
+
+template <int OP>
+static void launch_gemm(const GemmParams &p, int splits, cudaStream_t st) {
+  const int sms = sm_count();
+  auto tiles = [&](int bm, int bn) { return ((p.M + bm - 1) / bm) * ((p.N + bn - 1) / bn) * splits; };
+  if (tiles(128, 128) >= sms) {
+    dim3 grid((p.N + 127) / 128, (p.M + 127) / 128, splits);
+    gemm_kernel<128, 128, 8, 8, OP><<<grid, 256, 0, st>>>(p);
+  } else if (tiles(64, 64) >= sms / 2) {
+    dim3 grid((p.N + 63) / 64, (p.M + 63) / 64, splits);
+    gemm_kernel<64, 64, 4, 4, OP><<<grid, 256, 0, st>>>(p);
+  } else {
+    dim3 grid((p.N + 31) / 32, (p.M + 31) / 32, splits);
+    gemm_kernel<32, 32, 4, 4, OP><<<grid, 64, 0, st>>>(p);
+  }
+  GCRL_CUDA(cudaGetLastError());
+}
+
+void launch_linear_fwd(const float *X, int ldx, const float *W, int ldw, const float *bias, float *Y,
+                       int ldy, int M, int N, int K, int act, cudaStream_t st) {
+  GemmParams p{};
+  p.A = X; p.lda = ldx; p.B = W; p.ldb = ldw; p.C = Y; p.ldc = ldy; p.bias = bias;
+  p.M = M; p.N = N; p.K = K; p.act_mode = act;
+  launch_gemm<OP_FWD>(p, 1, st);
+}
+
+void launch_linear_dgrad(const float *dZ, int lddz, const float *W, int ldw, const float *Xact,
+                         int ldxa, float *dX, int lddx, int M, int N, int K, cudaStream_t st) {
+  GemmParams p{};
+  p.A = dZ; p.lda = lddz; p.B = W; p.ldb = ldw; p.C = dX; p.ldc = lddx;
+  p.act = Xact; p.ldact = ldxa;
+  p.M = M; p.N = K; p.K = N;  // output [M, K_layer], reduction over the layer's N outputs
+  launch_gemm<OP_DGRAD>(p, 1, st);
+}
+
+int launch_linear_wgrad(const float *dZ, int lddz, const float *X, int ldx, float *pW, int ldw,
+                        int64_t w_split_stride, float *pB, int64_t b_split_stride, int M, int N, int K,
+                        int max_splits, cudaStream_t st) {
+  // output [N, K] (+ bias [N]); reduction over the M batch rows, split into slabs
+  const int sms = sm_count();
+  const int base_tiles = ((N + 63) / 64) * ((K + 63) / 64);
+  int splits = std::max(1, std::min(max_splits, (2 * sms + base_tiles - 1) / base_tiles));
+  int chunk = (M + splits - 1) / splits;
+  chunk = std::max(64, (chunk + BK - 1) / BK * BK);
+  splits = (M + chunk - 1) / chunk;
+  GemmParams p{};
+  p.A = dZ; p.lda = lddz; p.B = X; p.ldb = ldx; p.C = pW; p.ldc = ldw; p.Cb = pB;
+  p.M = N; p.N = K; p.K = M;
+  p.k_chunk = chunk;
+  p.c_split_stride = w_split_stride;
+  p.cb_split_stride = b_split_stride;
+  launch_gemm<OP_WGRAD>(p, splits, st);
+  return splits;
+}
+
+// ---- skinny output layer ---------------------------------------------------------------------
+template <int NOUT>
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(const float *__restrict__ H, int ldh, const float *__restrict__ W, int ldw,
+                const float *__restrict__ bias, float *__restrict__ out, int ldo, int col0, int M, int K,
+                int tanh_out) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int K4 = K >> 2;
+  for (int m = warp; m < M; m += nwarps) {
+    const float *h = H + size_t(m) * ldh;
+    float acc[NOUT];
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n) acc[n] = 0.f;
+    for (int k4 = lane; k4 < K4; k4 += 32) {
+      const float4 hv = *reinterpret_cast<const float4 *>(h + k4 * 4);
+#pragma unroll
+      for (int n = 0; n < NOUT; ++n) {
+        const float4 wv = *reinterpret_cast<const float4 *>(W + size_t(n) * ldw + k4 * 4);
+        acc[n] = fmaf(hv.x, wv.x, acc[n]);
+        acc[n] = fmaf(hv.y, wv.y, acc[n]);
+        acc[n] = fmaf(hv.z, wv.z, acc[n]);
+        acc[n] = fmaf(hv.w, wv.w, acc[n]);
+      }
+    }
+    for (int k = K4 * 4 + lane; k < K; k += 32) {
+#pragma unroll
+      for (int n = 0; n < NOUT; ++n) acc[n] = fmaf(h[k], W[size_t(n) * ldw + k], acc[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n)
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], s);
+    if (lane == 0) {
+#pragma unroll
+      for (int n = 0; n < NOUT; ++n) {
+        float v = acc[n] + bias[n];
+        if (tanh_out) v = tanhf(v);
+        out[size_t(m) * ldo + col0 + n] = v;
+      }
+    }
+  }
+}
+
+void launch_head_fwd(const float *Hact, int ldh, const float *W, int ldw, const float *bias, float *out,
+                     int ldo, int col0, int M, int K, int nout, int tanh_out, cudaStream_t st) {
+  const int blocks = std::max(1, std::min((M + 7) / 8, sm_count() * 8));
+  switch (nout) {
+    case 1: head_fwd_kernel<1><<<blocks, 256, 0, st>>>(Hact, ldh, W, ldw, bias, out, ldo, col0, M, K, tanh_out); break;
+    case 2: head_fwd_kernel<2><<<blocks, 256, 0, st>>>(Hact, ldh, W, ldw, bias, out, ldo, col0, M, K, tanh_out); break;
+    case 3: head_fwd_kernel<3><<<blocks, 256, 0, st>>>(Hact, ldh, W, ldw, bias, out, ldo, col0, M, K, tanh_out); break;
+    case 4: head_fwd_kernel<4><<<blocks, 256, 0, st>>>(Hact, ldh, W, ldw, bias, out, ldo, col0, M, K, tanh_out); break;
+    default: throw Error(GCRL_ERR_INVALID, "head width must be 1..4");
+  }
+  GCRL_CUDA(cudaGetLastError());
+}
+
+// ---- loss + backward through the skinny output layer ------------------------------------------
+constexpr int kHeadSlabMax = 512;
+
+template <int NOUT>
+__global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs a, int rows_per_slab) {
+  __shared__ float dz_s[kHeadSlabMax][NOUT];
+  __shared__ float met_s[kHeadSlabMax][3];
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.x * rows_per_slab;
+  const int nrows = min(rows_per_slab, a.M - r0);
+  const float invM = 1.0f / float(a.M);
+
+  for (int i = tid; i < nrows; i += blockDim.x) {
+    const int m = r0 + i;
+    if (a.mode == 0) {
+      float qt = a.qt1[m];
+      if (a.qt2 != nullptr) qt = fminf(qt, a.qt2[m]);
+      float y = a.r[m] + a.gamma * (1.0f - a.d[m]) * qt;
+      if (a.clamp_y) y = fminf(fmaxf(y, a.y_lo), 0.0f);
+      if (a.y_out != nullptr) a.y_out[m] = y;
+      const float q = a.q[m];
+      const float diff = q - y;
+      float loss, g;
+      if (a.loss_kind == 0) {            // mse_loss
+        loss = diff * diff;
+        g = 2.0f * diff;
+      } else {                           // smooth_l1_loss, beta = 1
+        const float ad = fabsf(diff);
+        loss = ad < 1.0f ? 0.5f * diff * diff : ad - 0.5f;
+        g = ad < 1.0f ? diff : (diff > 0.f ? 1.0f : -1.0f);
+      }
+      dz_s[i][0] = g * invM;
+      met_s[i][0] = loss;
+      if (a.q_other != nullptr) {        // TD3: mean(max(td1, td2)), mean over both critics' q
+        const float qo = a.q_other[m];
+        met_s[i][1] = fmaxf(fabsf(q - y), fabsf(qo - y));
+        met_s[i][2] = 0.5f * (q + qo);
+      } else {
+        met_s[i][1] = fabsf(y - q);
+        met_s[i][2] = q;
+      }
+    } else if (a.mode == 1) {
+      dz_s[i][0] = -invM;
+      met_s[i][0] = -a.q[m];             // actor loss = -mean(q)
+      met_s[i][1] = 0.f;
+      met_s[i][2] = a.q[m];
+    } else {
+#pragma unroll
+      for (int n = 0; n < NOUT; ++n) dz_s[i][n] = a.dz_in[size_t(m) * 4 + n];
+    }
+  }
+  __syncthreads();
+
+  if (a.mode != 2 && tid < 3) {          // fixed-order partial sums of the slab's metrics
+    float s = 0.f;
+    for (int i = 0; i < nrows; ++i) s += met_s[i][tid];
+    a.metric_partials[size_t(blockIdx.x) * 4 + tid] = s;
+  }
+  if (a.pB != nullptr && tid >= 32 && tid < 32 + NOUT) {
+    const int n = tid - 32;
+    float s = 0.f;
+    for (int i = 0; i < nrows; ++i) s += dz_s[i][n];
+    a.pB[int64_t(blockIdx.x) * a.b_split_stride + n] = s;
+  }
+
+  for (int k = tid; k < a.K; k += blockDim.x) {
+    float w[NOUT], acc[NOUT];
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n) {
+      w[n] = a.W[size_t(n) * a.ldw + k];
+      acc[n] = 0.f;
+    }
+    for (int i = 0; i < nrows; ++i) {
+      const size_t m = size_t(r0 + i);
+      const float h = a.Hact[m * a.ldh + k];
+      float dh = 0.f;
+#pragma unroll
+      for (int n = 0; n < NOUT; ++n) {
+        const float dz = dz_s[i][n];
+        dh = fmaf(dz, w[n], dh);
+        acc[n] = fmaf(dz, h, acc[n]);
+      }
+      a.dZprev[m * a.lddz + k] = h > 0.f ? dh : dh * kLeakySlope;
+    }
+    if (a.pW != nullptr) {
+#pragma unroll
+      for (int n = 0; n < NOUT; ++n)
+        a.pW[int64_t(blockIdx.x) * a.w_split_stride + size_t(n) * a.ldw + k] = acc[n];
+    }
+  }
+  if (a.pW != nullptr) {  // zero the row padding of the slab
+    for (int k = a.K + tid; k < a.ldw; k += blockDim.x)
+#pragma unroll
+      for (int n = 0; n < NOUT; ++n)
+        a.pW[int64_t(blockIdx.x) * a.w_split_stride + size_t(n) * a.ldw + k] = 0.f;
+  }
+}
+
+int launch_head_bwd(const HeadBwdArgs &a, int max_splits, cudaStream_t st) {
+  int rows = (a.M + max_splits - 1) / max_splits;
+  rows = std::min(kHeadSlabMax, std::max(rows, 16));
+  const int slabs = (a.M + rows - 1) / rows;
+  if (slabs > max_splits) throw Error(GCRL_ERR_INVALID, "batch too large for head_bwd partial buffers");
+  switch (a.nout) {
+    case 1: head_bwd_kernel<1><<<slabs, 256, 0, st>>>(a, rows); break;
+    case 2: head_bwd_kernel<2><<<slabs, 256, 0, st>>>(a, rows); break;
+    case 3: head_bwd_kernel<3><<<slabs, 256, 0, st>>>(a, rows); break;
+    case 4: head_bwd_kernel<4><<<slabs, 256, 0, st>>>(a, rows); break;
+    default: throw Error(GCRL_ERR_INVALID, "head width must be 1..4");
+  }
+  GCRL_CUDA(cudaGetLastError());
+  return slabs;
+}
+
+// ---- d(actor loss)/d(action) through critic layer 1, fused with tanh' ---------------------------
+__global__ void __launch_bounds__(256)
+action_grad_kernel(const float *__restrict__ dZ1, int lddz, const float *__restrict__ W1, int ldw,
+                   const float *__restrict__ sa, int ldsa, int col0, float *__restrict__ dz_out, int M, int N,
+                   int nact) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int m = warp; m < M; m += nwarps) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int n = lane; n < N; n += 32) {
+      const float g = dZ1[size_t(m) * lddz + n];
+      const float *w = W1 + size_t(n) * ldw + col0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nact) acc[j] = fmaf(g, w[j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], s);
+    if (lane < 4) {
+      float v = 0.f;
+      if (lane < nact) {
+        const float act = sa[size_t(m) * ldsa + col0 + lane];
+        const float g = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+        v = g * (1.0f - act * act);
+      }
+      dz_out[size_t(m) * 4 + lane] = v;
+    }
+  }
+}
+
+void launch_action_grad(const float *dZ1, int lddz, const float *W1, int ldw, const float *sa, int ldsa,
+                        int col0, float *dz_out, int M, int N, int nact, cudaStream_t st) {
+  GCRL_REQUIRE(nact >= 1 && nact <= 4, "act_dim must be 1..4");
+  const int blocks = std::max(1, std::min((M + 7) / 8, sm_count() * 8));
+  action_grad_kernel<<<blocks, 256, 0, st>>>(dZ1, lddz, W1, ldw, sa, ldsa, col0, dz_out, M, N, nact);
+  GCRL_CUDA(cudaGetLastError());
+}
+
+// ---- batch ingest: all packed operand rows in one launch ---------------------------------------
+__global__ void __launch_bounds__(256)
+ingest_batch_kernel(const float *__restrict__ s, const float *__restrict__ a, const float *__restrict__ r,
+                    const float *__restrict__ ns, const float *__restrict__ d, int D, int A, int M,
+                    float *__restrict__ sa, float *__restrict__ nsa, float *__restrict__ spi, int ldc,
+                    float *__restrict__ r_out, float *__restrict__ d_out, FastDiv dl) {
+  const int total = M * ldc;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int m = int(dl.div(uint32_t(e)));
+    const int c = e - m * ldc;
+    float vs = 0.f, vsa = 0.f, vns = 0.f;
+    if (c < D) {
+      vs = s[size_t(m) * D + c];
+      vsa = vs;
+      vns = ns[size_t(m) * D + c];
+    } else if (c < D + A) {
+      vsa = a[size_t(m) * A + (c - D)];
+    }
+    sa[e] = vsa;
+    nsa[e] = vns;
+    spi[e] = vs;
+    if (c == 0) {
+      r_out[m] = r[m];
+      d_out[m] = d[m];
+    }
+  }
+}
+
+void launch_ingest_batch(const float *s, const float *a, const float *r, const float *ns, const float *d,
+                         int D, int A, int M, float *sa, float *nsa, float *spi, int ldc, float *r_out,
+                         float *d_out, cudaStream_t st) {
+  const int total = M * ldc;
+  if (total == 0) return;
+  const int blocks = std::min((total + 255) / 256, sm_count() * 8);
+  ingest_batch_kernel<<<blocks, 256, 0, st>>>(s, a, r, ns, d, D, A, M, sa, nsa, spi, ldc, r_out, d_out,
+                                             FastDiv(uint32_t(ldc)));
+  GCRL_CUDA(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256)
+td3_smooth_kernel(float *__restrict__ x, int ldx, int col0, const float *__restrict__ noise, int A, int M,
+                  float sigma, float clampv) {
+  const int total = M * A;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int m = e / A, j = e - m * A;
+    float n = noise[e] * sigma;
+    n = fminf(fmaxf(n, -clampv), clampv);
+    float *p = x + size_t(m) * ldx + col0 + j;
+    *p = fminf(fmaxf(*p + n, -1.0f), 1.0f);
+  }
+}
+
+void launch_td3_smooth(float *x, int ldx, int col0, const float *noise, int A, int M, float sigma,
+                       float clampv, cudaStream_t st) {
+  const int total = M * A;
+  if (total == 0) return;
+  td3_smooth_kernel<<<std::min((total + 255) / 256, sm_count() * 8), 256, 0, st>>>(x, ldx, col0, noise, A,
+                                                                                  M, sigma, clampv);
+  GCRL_CUDA(cudaGetLastError());
+}
+
+// ---- [s | a | 0] row packing ------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const float *__restrict__ s, int D, const float *__restrict__ a, int A, float *__restrict__ out,
+                 int ldo, int64_t total, FastDiv dl) {
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+       e += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t m = (total < (int64_t(1) << 31)) ? int64_t(dl.div(uint32_t(e))) : e / ldo;
+    const int c = int(e - m * ldo);
+    float v = 0.f;
+    if (c < D) v = s[m * D + c];
+    else if (a != nullptr && c < D + A) v = a[m * A + (c - D)];
+    out[e] = v;
+  }
+}
+
+void launch_pack_rows(const float *s, int D, const float *a, int A, float *out, int ldo, int M,
+                      cudaStream_t st) {
+  const int64_t total = int64_t(M) * ldo;
+  if (total == 0) return;
+  const int blocks = int(std::min<int64_t>((total + 255) / 256, int64_t(sm_count()) * 8));
+  pack_rows_kernel<<<blocks, 256, 0, st>>>(s, D, a, A, out, ldo, total, FastDiv(uint32_t(ldo)));
+  GCRL_CUDA(cudaGetLastError());
+}
+
+}  // namespace gcrl

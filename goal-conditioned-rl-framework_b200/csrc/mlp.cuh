@@ -1,0 +1,110 @@
+// Launch helpers for the MLP forward/backward/optimiser kernels (mlp.cu, optim.cu).
+// All 2-D operands are (pointer, leading dimension) with the leading dimension a multiple
+// of 4 floats and the base 16-byte aligned; logical sizes are arbitrary.
+#pragma once
+#include "common.cuh"
+
+namespace gcrl {
+
+constexpr float kLeakySlope = 0.01f;  // nn.LeakyReLU() default, reference src/model.py:20
+
+enum ActMode : int { ACT_NONE = 0, ACT_LEAKY = 1 };
+
+// Y[M,N] = act(X[M,K] * W[N,K]^T + bias[N])
+void launch_linear_fwd(const float *X, int ldx, const float *W, int ldw, const float *bias, float *Y,
+                       int ldy, int M, int N, int K, int act, cudaStream_t st);
+
+// dX[M,K] = (dZ[M,N] * W[N,K]) (.) leaky'(Xact[M,K])     (Xact == nullptr: no activation factor)
+void launch_linear_dgrad(const float *dZ, int lddz, const float *W, int ldw, const float *Xact,
+                         int ldxa, float *dX, int lddx, int M, int N, int K, cudaStream_t st);
+
+// Split-batch partial weight gradients:
+//   pW[s][N][ldw] = sum_{m in slab s} dZ[m,n] * X[m,k],   pB[s][N] = sum_{m in slab s} dZ[m,n]
+// Returns the number of slabs S written (<= max_splits).
+int launch_linear_wgrad(const float *dZ, int lddz, const float *X, int ldx, float *pW, int ldw,
+                        int64_t w_split_stride, float *pB, int64_t b_split_stride, int M, int N, int K,
+                        int max_splits, cudaStream_t st);
+
+// Skinny output layer, NOUT <= 4:  out[m, col0 + n] = f(H[m,:] . W[n,:] + bias[n]),  f = tanh | id
+void launch_head_fwd(const float *Hact, int ldh, const float *W, int ldw, const float *bias, float *out,
+                     int ldo, int col0, int M, int K, int nout, int tanh_out, cudaStream_t st);
+
+struct HeadBwdArgs {
+  // mode 0 (critic TD loss): dz = w_is * 2 (q - y) / M with
+  //        y = r + gamma (1 - d) min(qt1, qt2)   [clamped to [y_lo, 0] when clamp_y]
+  //        loss_kind 0: mse, 1: smooth-l1 (beta 1)   (TD3, reference src/agent.py:189-197)
+  // mode 1 (actor loss through the critic): dz = -1 / M
+  // mode 2 (actor head): dz[m,n] given in dz_in[m*4+n]
+  int mode, loss_kind, clamp_y, nout;
+  const float *q, *qt1, *qt2, *r, *d, *dz_in;
+  const float *q_other;   // TD3 critic 2: metrics use max(|q-y|, |q_other-y|) and (q+q_other)/2
+  float gamma, y_lo;
+  const float *Hact; int ldh;      // last hidden activation [M, K]
+  const float *W; int ldw;         // head weight [nout, K]
+  float *dZprev; int lddz;         // out: grad wrt last hidden pre-activation [M, K]
+  float *pW; int64_t w_split_stride;  // out: partial head weight grads [S][nout][ldw] (nullptr: skip)
+  float *pB; int64_t b_split_stride;  // out: partial head bias grads   [S][nout]
+  float *metric_partials;          // out: [S][4] = sum loss, sum |y-q|, sum q, unused
+  float *y_out;                    // optional [M]
+  int M, K;
+};
+// Returns the number of row slabs S.
+int launch_head_bwd(const HeadBwdArgs &a, int max_splits, cudaStream_t st);
+
+// Critic layer-1 input gradient restricted to the action columns, fused with tanh':
+//   dz_out[m*4 + j] = (sum_n dZ1[m,n] W1[n, col0 + j]) * (1 - act[m, col0 + j]^2)
+void launch_action_grad(const float *dZ1, int lddz, const float *W1, int ldw, const float *sa, int ldsa,
+                        int col0, float *dz_out, int M, int N, int nact, cudaStream_t st);
+
+// pack dense s[M,D], a[M,A] (optional) into rows [s | a | 0-pad] with leading dimension ldo
+void launch_pack_rows(const float *s, int D, const float *a, int A, float *out, int ldo, int M,
+                      cudaStream_t st);
+
+// ---- optimiser (optim.cu) --------------------------------------------------------------
+struct SegDesc {          // one parameter segment of a flat network buffer
+  int begin, count;       // [begin, begin+count) in the flat buffer
+  const float *partials;  // [splits][split_stride] partial sums (nullptr: already reduced)
+  int splits;
+  int64_t split_stride;
+  int offset;             // offset of this segment inside a partial slab
+};
+constexpr int kMaxSegs = 16;
+struct ReduceArgs {
+  SegDesc seg[kMaxSegs];
+  int nseg, total;
+  float *grad;            // flat gradient out
+  float *sumsq_partials;  // [gridDim.x]
+  // metrics finalisation (block 0): out[slot] = sum(partials[.][j]) * scale
+  const float *metric_partials; int metric_splits; float metric_scale;
+  float *metrics; int slot_loss, slot_td, slot_q;
+};
+int reduce_grid(int total);
+void launch_reduce_grads(const ReduceArgs &a, cudaStream_t st);
+
+struct StepScalars {       // written by the host before every update (device copy)
+  // per optimiser: lr / (1 - b1^t), sqrt(1 - b2^t), 1 - lr * weight_decay, unused
+  float step_size_c, bc2_sqrt_c, decay_c, pad0;
+  float step_size_a, bc2_sqrt_a, decay_a, pad1;
+};
+struct AdamArgs {
+  float *p, *m, *v; const float *g; int n;
+  const float *sumsq_partials; int nsumsq;
+  float max_norm;          // < 0: no clipping
+  float weight_decay;      // decoupled (AdamW); 0 for Adam
+  const StepScalars *sc; int which;   // 0: critic scalars, 1: actor scalars
+  float *target; float tau, one_minus_tau; int polyak;   // fused Polyak of `target` with the NEW p
+  float *metrics; int slot_norm;
+};
+void launch_adam(const AdamArgs &a, cudaStream_t st);
+void launch_polyak(float *target, const float *src, int n, float tau, float one_minus_tau,
+                   cudaStream_t st);
+
+// one launch: dense (s, a, r, ns, d) -> sa = [s|a|0], nsa = [ns|0], spi = [s|0], r, d copies
+void launch_ingest_batch(const float *s, const float *a, const float *r, const float *ns, const float *d,
+                         int D, int A, int M, float *sa, float *nsa, float *spi, int ldc, float *r_out,
+                         float *d_out, cudaStream_t st);
+// TD3 target-policy smoothing: x[m, col0+j] = clamp(x + clamp(noise[m*A+j] * sigma, +-c), -1, 1)
+void launch_td3_smooth(float *x, int ldx, int col0, const float *noise, int A, int M, float sigma,
+                       float clampv, cudaStream_t st);
+
+}  // namespace gcrl

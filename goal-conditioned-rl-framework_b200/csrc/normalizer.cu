@@ -1,0 +1,302 @@
+// Running mean/std normaliser on the device (sm_100a).
+//
+// Replaces RunningNormalizer (reference src/utils.py:68-117): float64 running
+// (mean, var, count) merged with the batch moments by Chan's parallel-variance formula,
+// normalize = clip((x - mean) / (sqrt(var) + 1e-8), +-clip).
+//
+// Kernels
+//   norm_partial_kernel : one warp per column, lanes stride over the rows of the CTA's row
+//                         slab with a per-lane Welford accumulator, lanes merged with
+//                         shuffles (Chan merge of (n, mean, M2) triples) -> one partial per
+//                         (CTA, column).  Bound: HBM read of 4|8 * n * dim bytes.
+//   norm_merge_kernel   : fixed-order merge of the CTA partials -> batch (mean, var, n),
+//                         then the reference's _update_from_moments (src/utils.py:82-94).
+//   norm_apply_kernel   : element-wise normalise + clip, float64 math, f64 or f32 output.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace gcrl {
+
+struct Moments {
+  double n, mean, m2;
+};
+
+__device__ __forceinline__ Moments chan_merge(const Moments &a, const Moments &b) {
+  if (b.n == 0.0) return a;
+  if (a.n == 0.0) return b;
+  Moments r;
+  r.n = a.n + b.n;
+  const double delta = b.mean - a.mean;
+  r.mean = a.mean + delta * (b.n / r.n);
+  r.m2 = a.m2 + b.m2 + delta * delta * (a.n * b.n / r.n);
+  return r;
+}
+
+__device__ __forceinline__ double shfl_xor_d(double v, int m) {
+  return __shfl_xor_sync(0xffffffffu, v, m);
+}
+
+constexpr int kNormWarps = 8;  // columns handled concurrently per CTA
+
+template <typename T>
+__global__ void __launch_bounds__(kNormWarps * 32)
+norm_partial_kernel(const T *__restrict__ x, int64_t n, int dim, int64_t rows_per_block,
+                    Moments *__restrict__ partials /* [gridDim.x][dim] */) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r0 = int64_t(blockIdx.x) * rows_per_block;
+  const int64_t r1 = min(n, r0 + rows_per_block);
+  for (int c = warp; c < dim; c += kNormWarps) {
+    Moments acc{0.0, 0.0, 0.0};
+    for (int64_t r = r0 + lane; r < r1; r += 32) {
+      const double v = double(x[r * dim + c]);
+      acc.n += 1.0;
+      const double d = v - acc.mean;
+      acc.mean += d / acc.n;
+      acc.m2 += d * (v - acc.mean);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      Moments o{shfl_xor_d(acc.n, m), shfl_xor_d(acc.mean, m), shfl_xor_d(acc.m2, m)};
+      // merge in a lane-order-independent way: lower lane first
+      acc = (lane & m) ? chan_merge(o, acc) : chan_merge(acc, o);
+    }
+    if (lane == 0) partials[size_t(blockIdx.x) * dim + c] = acc;
+  }
+}
+
+struct NormState {
+  double *mean, *var, *count;  // device, [dim], [dim], [1]
+};
+
+__global__ void norm_merge_kernel(const Moments *__restrict__ partials, int nblocks, int dim,
+                                  NormState st) {
+  const int c = threadIdx.x;  // single CTA, one thread per column
+  const double count = *st.count;
+  __syncthreads();            // every column reads the old count before thread 0 replaces it
+  if (c >= dim) return;
+  Moments b{0.0, 0.0, 0.0};
+  for (int i = 0; i < nblocks; ++i) b = chan_merge(b, partials[size_t(i) * dim + c]);
+  // reference _update_from_moments (src/utils.py:82-94) with batch var = M2 / n
+  const double bvar = b.m2 / b.n;
+  const double tot = count + b.n;
+  const double delta = b.mean - st.mean[c];
+  const double new_mean = st.mean[c] + delta * b.n / tot;
+  const double m2 = st.var[c] * count + bvar * b.n + delta * delta * count * b.n / tot;
+  st.mean[c] = new_mean;
+  st.var[c] = m2 / tot;
+  if (c == 0) *st.count = tot;
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+norm_apply_kernel(const TI *__restrict__ x, int64_t n, int dim, NormState st, double clip,
+                  TO *__restrict__ out, int64_t out_stride, int64_t out_col0, FastDiv ddiv) {
+  const int64_t total = n * dim;
+  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+       e += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = (total < (int64_t(1) << 31)) ? int64_t(ddiv.div(uint32_t(e))) : e / dim;
+    const int c = int(e - r * dim);
+    double z = (double(x[e]) - st.mean[c]) / (sqrt(st.var[c]) + 1e-8);
+    z = fmin(fmax(z, -clip), clip);
+    out[r * out_stride + out_col0 + c] = TO(z);
+  }
+}
+
+}  // namespace gcrl
+
+using namespace gcrl;
+
+struct gcrl_norm {
+  int device = 0, dim = 0;
+  double clip = 5.0;
+  NormState st{};
+  double *d_state = nullptr;  // mean[dim] | var[dim] | count[2]
+  Moments *d_partials = nullptr;
+  int max_blocks = 0;
+  void *d_x = nullptr;
+  size_t x_cap = 0;
+  double *d_out = nullptr;
+  size_t out_cap = 0;
+  PinnedRing stage;
+};
+
+static void norm_update_device(gcrl_norm *h, const void *x_dev, int64_t n, int is_f64,
+                               cudaStream_t st) {
+  if (n <= 0) return;
+  const int64_t rows_per_block = std::max<int64_t>(256, (n + h->max_blocks - 1) / h->max_blocks);
+  const int nblocks = int((n + rows_per_block - 1) / rows_per_block);
+  if (is_f64)
+    norm_partial_kernel<double><<<nblocks, kNormWarps * 32, 0, st>>>(
+        static_cast<const double *>(x_dev), n, h->dim, rows_per_block, h->d_partials);
+  else
+    norm_partial_kernel<float><<<nblocks, kNormWarps * 32, 0, st>>>(
+        static_cast<const float *>(x_dev), n, h->dim, rows_per_block, h->d_partials);
+  GCRL_CUDA(cudaGetLastError());
+  const int threads = 128;
+  GCRL_REQUIRE(h->dim <= threads, "normaliser dim > 128 not supported");
+  norm_merge_kernel<<<1, threads, 0, st>>>(h->d_partials, nblocks, h->dim, h->st);
+  GCRL_CUDA(cudaGetLastError());
+}
+
+static const void *norm_stage_in(gcrl_norm *h, const void *x_host, int64_t n, int is_f64,
+                                 cudaStream_t st) {
+  const size_t bytes = size_t(n) * h->dim * (is_f64 ? 8 : 4);
+  if (bytes > h->x_cap) {
+    GCRL_CUDA(cudaStreamSynchronize(st));
+    if (h->d_x) GCRL_CUDA(cudaFree(h->d_x));
+    h->x_cap = std::max<size_t>(bytes * 2, 4096);
+    h->d_x = dev_alloc<char>(h->x_cap);
+  }
+  int slot;
+  char *p = h->stage.acquire(bytes, &slot);
+  std::memcpy(p, x_host, bytes);
+  GCRL_CUDA(cudaMemcpyAsync(h->d_x, p, bytes, cudaMemcpyHostToDevice, st));
+  h->stage.release(slot, st);
+  return h->d_x;
+}
+
+template <typename TO>
+static void norm_apply_launch(gcrl_norm *h, const void *x_dev, int64_t n, int is_f64, TO *out,
+                              int64_t stride, int64_t col0, cudaStream_t st) {
+  if (n <= 0) return;
+  const int64_t total = n * h->dim;
+  const int blocks = int(std::min<int64_t>((total + 255) / 256, int64_t(sm_count()) * 8));
+  const FastDiv dd{uint32_t(h->dim)};
+  if (is_f64)
+    norm_apply_kernel<double, TO><<<blocks, 256, 0, st>>>(static_cast<const double *>(x_dev), n,
+                                                         h->dim, h->st, h->clip, out, stride, col0, dd);
+  else
+    norm_apply_kernel<float, TO><<<blocks, 256, 0, st>>>(static_cast<const float *>(x_dev), n,
+                                                        h->dim, h->st, h->clip, out, stride, col0, dd);
+  GCRL_CUDA(cudaGetLastError());
+}
+
+extern "C" {
+
+int gcrl_norm_create(gcrl_norm **out, int device, int dim, double clip_range, double eps_count) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(out != nullptr && dim >= 1 && dim <= 128, "need 1 <= dim <= 128");
+  GCRL_CUDA(cudaSetDevice(device));
+  auto *h = new gcrl_norm();
+  try {
+    h->device = device;
+    h->dim = dim;
+    h->clip = clip_range;
+    h->d_state = dev_alloc<double>(size_t(2 * dim + 2));
+    h->st.mean = h->d_state;
+    h->st.var = h->d_state + dim;
+    h->st.count = h->d_state + 2 * dim;
+    h->max_blocks = sm_count() * 4;
+    h->d_partials = dev_alloc<Moments>(size_t(h->max_blocks) * dim);
+    h->stage.init(size_t(1) << 16);
+  } catch (...) {
+    delete h;
+    throw;
+  }
+  *out = h;
+  std::vector<double> init(size_t(2 * dim + 2), 0.0);
+  for (int i = 0; i < dim; ++i) init[dim + i] = 1.0;  // var = 1, mean = 0 (src/utils.py:70-71)
+  init[2 * dim] = init[2 * dim + 1] = eps_count;      // count = eps (src/utils.py:72)
+  GCRL_CUDA(cudaMemcpy(h->d_state, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
+  GCRL_API_END
+}
+
+int gcrl_norm_destroy(gcrl_norm *h) {
+  GCRL_API_BEGIN
+  if (h == nullptr) return GCRL_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  cudaFree(h->d_state); cudaFree(h->d_partials);
+  if (h->d_x) cudaFree(h->d_x);
+  if (h->d_out) cudaFree(h->d_out);
+  h->stage.destroy();
+  delete h;
+  GCRL_API_END
+}
+
+int gcrl_norm_update(gcrl_norm *h, const void *x_host, int64_t n, int is_f64, void *stream) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(h != nullptr && (x_host != nullptr || n == 0) && n >= 0, "bad arguments");
+  GCRL_CUDA(cudaSetDevice(h->device));
+  if (n == 0) return GCRL_OK;
+  cudaStream_t st = as_stream(stream);
+  const void *xd = norm_stage_in(h, x_host, n, is_f64, st);
+  norm_update_device(h, xd, n, is_f64, st);
+  GCRL_API_END
+}
+
+int gcrl_norm_update_dev(gcrl_norm *h, const void *x_dev, int64_t n, int is_f64, void *stream) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(h != nullptr && (x_dev != nullptr || n == 0) && n >= 0, "bad arguments");
+  GCRL_CUDA(cudaSetDevice(h->device));
+  norm_update_device(h, x_dev, n, is_f64, as_stream(stream));
+  GCRL_API_END
+}
+
+int gcrl_norm_apply(gcrl_norm *h, const void *x_host, int64_t n, int is_f64, double *out_host,
+                    void *stream) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(h != nullptr && n >= 0 && (n == 0 || (x_host && out_host)), "bad arguments");
+  GCRL_CUDA(cudaSetDevice(h->device));
+  if (n == 0) return GCRL_OK;
+  cudaStream_t st = as_stream(stream);
+  const void *xd = norm_stage_in(h, x_host, n, is_f64, st);
+  const size_t cnt = size_t(n) * h->dim;
+  if (cnt > h->out_cap) {
+    GCRL_CUDA(cudaStreamSynchronize(st));
+    if (h->d_out) GCRL_CUDA(cudaFree(h->d_out));
+    h->out_cap = cnt * 2;
+    h->d_out = dev_alloc<double>(h->out_cap);
+  }
+  norm_apply_launch<double>(h, xd, n, is_f64, h->d_out, h->dim, 0, st);
+  GCRL_CUDA(cudaMemcpyAsync(out_host, h->d_out, cnt * 8, cudaMemcpyDeviceToHost, st));
+  GCRL_CUDA(cudaStreamSynchronize(st));
+  GCRL_API_END
+}
+
+int gcrl_norm_apply_dev_f32(gcrl_norm *h, const void *x_dev, int64_t n, int is_f64,
+                            float *out_dev, int64_t out_stride, int64_t out_col0, void *stream) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(h != nullptr && n >= 0 && (n == 0 || (x_dev && out_dev)), "bad arguments");
+  GCRL_REQUIRE(out_stride >= h->dim + out_col0 && out_col0 >= 0, "bad output stride / column");
+  GCRL_CUDA(cudaSetDevice(h->device));
+  norm_apply_launch<float>(h, x_dev, n, is_f64, out_dev, out_stride, out_col0, as_stream(stream));
+  GCRL_API_END
+}
+
+int gcrl_norm_get_state(gcrl_norm *h, double *mean, double *var, double *count,
+                        double *clip_range, void *stream) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(h != nullptr, "handle is NULL");
+  GCRL_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = as_stream(stream);
+  std::vector<double> host(size_t(2 * h->dim + 2));
+  GCRL_CUDA(cudaMemcpyAsync(host.data(), h->d_state, host.size() * 8, cudaMemcpyDeviceToHost, st));
+  GCRL_CUDA(cudaStreamSynchronize(st));
+  if (mean) std::memcpy(mean, host.data(), size_t(h->dim) * 8);
+  if (var) std::memcpy(var, host.data() + h->dim, size_t(h->dim) * 8);
+  if (count) *count = host[size_t(2 * h->dim)];
+  if (clip_range) *clip_range = h->clip;
+  GCRL_API_END
+}
+
+int gcrl_norm_set_state(gcrl_norm *h, const double *mean, const double *var, double count,
+                        double clip_range, void *stream) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(h != nullptr && mean && var, "bad arguments");
+  GCRL_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = as_stream(stream);
+  std::vector<double> host(size_t(2 * h->dim + 2));
+  std::memcpy(host.data(), mean, size_t(h->dim) * 8);
+  std::memcpy(host.data() + h->dim, var, size_t(h->dim) * 8);
+  host[size_t(2 * h->dim)] = host[size_t(2 * h->dim + 1)] = count;
+  h->clip = clip_range;
+  GCRL_CUDA(cudaMemcpyAsync(h->d_state, host.data(), host.size() * 8, cudaMemcpyHostToDevice, st));
+  GCRL_CUDA(cudaStreamSynchronize(st));
+  GCRL_API_END
+}
+
+}  // extern "C"

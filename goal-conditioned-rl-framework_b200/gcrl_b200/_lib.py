@@ -1,0 +1,127 @@
+"""ctypes binding of include/gcrl_b200.h (the drop-in C ABI)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_NAME = "libgcrl_b200.so"
+
+
+def library_path() -> str:
+    return os.environ.get("GCRL_B200_LIB", os.path.join(_HERE, _LIB_NAME))
+
+
+class GcrlError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"gcrl_b200 error {code}: {msg}")
+        self.code = code
+
+
+OK, ERR_INVALID, ERR_UNDERFILLED, ERR_CUDA, ERR_CAPACITY = 0, 1, 2, 3, 4
+
+c_i32, c_i64, c_u64, c_f32, c_f64 = C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_double
+vp = C.c_void_p
+pp = C.POINTER(C.c_void_p)
+
+
+class AgentConfig(C.Structure):
+    """struct gcrl_agent_config (include/gcrl_b200.h)."""
+    _fields_ = [("algo", c_i32), ("state_dim", c_i32), ("act_dim", c_i32), ("hidden_dim", c_i32),
+                ("layer_count", c_i32), ("max_batch", c_i32), ("gamma", c_f32), ("tau", c_f32),
+                ("grad_clip", c_f32), ("policy_noise", c_f32), ("noise_clamp", c_f32),
+                ("weight_decay", c_f32), ("precision", c_i32), ("reserved", c_i32)]
+
+
+# name -> (restype, argtypes); every symbol include/gcrl_b200.h declares
+SIGNATURES = {
+    "gcrl_abi_version": (C.c_int, []),
+    "gcrl_last_error": (C.c_char_p, []),
+    "gcrl_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    # HER buffer
+    "gcrl_her_create": (C.c_int, [pp, C.c_int, c_i64, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, c_u64]),
+    "gcrl_her_destroy": (C.c_int, [vp]),
+    "gcrl_her_push_episode": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "gcrl_her_len": (c_i64, [vp]),
+    "gcrl_her_total_entries": (c_i64, [vp]),
+    "gcrl_her_live_transitions": (c_i64, [vp]),
+    "gcrl_her_clear": (C.c_int, [vp]),
+    "gcrl_her_sample": (C.c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "gcrl_her_sample_dev_idx": (C.c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp]),
+    "gcrl_her_sample_host": (C.c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp, vp]),
+    # normaliser
+    "gcrl_norm_create": (C.c_int, [pp, C.c_int, C.c_int, c_f64, c_f64]),
+    "gcrl_norm_destroy": (C.c_int, [vp]),
+    "gcrl_norm_update": (C.c_int, [vp, vp, c_i64, C.c_int, vp]),
+    "gcrl_norm_update_dev": (C.c_int, [vp, vp, c_i64, C.c_int, vp]),
+    "gcrl_norm_apply": (C.c_int, [vp, vp, c_i64, C.c_int, vp, vp]),
+    "gcrl_norm_apply_dev_f32": (C.c_int, [vp, vp, c_i64, C.c_int, vp, c_i64, c_i64, vp]),
+    "gcrl_norm_get_state": (C.c_int, [vp, vp, vp, C.POINTER(c_f64), C.POINTER(c_f64), vp]),
+    "gcrl_norm_set_state": (C.c_int, [vp, vp, vp, c_f64, c_f64, vp]),
+    # agents
+    "gcrl_agent_create": (C.c_int, [pp, C.c_int, C.POINTER(AgentConfig)]),
+    "gcrl_agent_destroy": (C.c_int, [vp]),
+    "gcrl_agent_num_layers": (C.c_int, [vp, C.c_int]),
+    "gcrl_agent_layer_shape": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "gcrl_agent_set_layer": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),
+    "gcrl_agent_get_layer": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp]),
+    "gcrl_agent_hard_update": (C.c_int, [vp, vp]),
+    "gcrl_agent_reset_optim": (C.c_int, [vp, vp]),
+    "gcrl_agent_update_batch": (C.c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, c_f64, c_f64, C.c_int, vp, vp]),
+    "gcrl_agent_update_from_buffer": (C.c_int, [vp, vp, c_i64, vp, vp, c_f64, c_f64, C.c_int, vp, vp]),
+    "gcrl_agent_read_metrics": (C.c_int, [vp, vp, vp]),
+    "gcrl_agent_act": (C.c_int, [vp, c_i64, vp, vp, vp]),
+    "gcrl_agent_q": (C.c_int, [vp, c_i64, vp, vp, vp, vp]),
+    "gcrl_agent_update_phase": (C.c_int, [vp, C.c_int, c_i64, vp, vp, vp, vp, vp, vp, c_f64, C.c_int, vp]),
+    "gcrl_agent_grad_buffer": (C.c_int, [vp, C.c_int, pp, C.POINTER(c_i64)]),
+    "gcrl_agent_metrics_buffer": (C.c_int, [vp, pp]),
+}
+
+
+def _load():
+    path = library_path()
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} not found: the CUDA extension is not built. Run ./build.sh (or "
+            "`python -c 'import __graft_entry__ as g; g.build()'`) -- there is no CPU fallback.")
+    dll = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(dll, name)          # AttributeError if the library lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if dll.gcrl_abi_version() != 1:
+        raise ImportError("libgcrl_b200.so ABI version mismatch")
+    return dll
+
+
+lib = _load()
+
+
+def check(code):
+    if code != OK:
+        msg = lib.gcrl_last_error().decode("utf-8", "replace")
+        if code == ERR_UNDERFILLED:
+            raise AssertionError(msg)          # reference: assert at src/buffer.py:122
+        if code == ERR_INVALID:
+            raise ValueError(msg)
+        raise GcrlError(code, msg)
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    check(lib.gcrl_device_count(C.byref(n)))
+    return n.value
+
+
+def require_cuda():
+    if device_count() < 1:
+        raise GcrlError(ERR_CUDA, "no CUDA device: gcrl_b200 has no CPU fallback")
+
+
+def np_ptr(arr):
+    return arr.ctypes.data_as(vp)
+
+
+def current_stream(device_index):
+    import torch
+    return vp(torch.cuda.current_stream(device_index).cuda_stream)

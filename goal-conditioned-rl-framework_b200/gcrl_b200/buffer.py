@@ -1,0 +1,162 @@
+"""HERBuffer over the device-resident episode store (reference src/buffer.py:92-179)."""
+from __future__ import annotations
+
+import ctypes as C
+import random
+from collections import deque
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib, np_ptr, vp
+
+_FLUSH_LEN = 50  # the reference flushes on `done or len >= 50` (literal, src/buffer.py:117)
+
+
+def _to_np(x, dtype=np.float32):
+    if hasattr(x, "detach"):                 # torch tensor (env.py hands device rows)
+        x = x.detach().cpu().numpy()
+    return np.asarray(x, dtype=dtype)
+
+
+class HERBuffer:
+    """Same constructor, ``push`` / ``sample`` / ``__len__`` and attributes as the
+    reference class.  Transitions are staged per env on the host and committed to the GPU
+    as whole episodes; relabelling, the sparse reward and the gather run in
+    csrc/her.cu at sample time.
+
+    index_source:
+      "host"   -- future indices come from ``random.randint`` and sample positions from
+                  ``random.sample(range(len), B)``: the reference's exact Mersenne-Twister
+                  stream (src/buffer.py:124,153), bit-identical batches.
+      "device" -- both are drawn on the GPU (no per-call host work).
+    ``compute_reward`` is accepted for interface compatibility (src/env.py:105 assigns
+    it); relabelled rewards always use the sparse Panda rule -(||ag - g|| > 0.05).
+    """
+
+    def __init__(self, max_mem_len, max_eps_len, nenvs, threshold=0.05, k_future=4, *,
+                 index_source="host", seed=1898, cap_transitions=0, device=0):
+        _lib.require_cuda()
+        if index_source not in ("host", "device"):
+            raise ValueError(f"index_source must be 'host' or 'device', got {index_source!r}")
+        self.max_mem_len = int(max_mem_len)
+        self.episodes = [deque(maxlen=max_eps_len) for _ in range(nenvs)]
+        self.device_index = int(device)
+        self.device = f"cuda:{self.device_index}"
+        self.threshold = threshold
+        self.k_future = int(k_future)
+        self.compute_reward = None
+        self.obs_normalizer = None
+        self.dg_normalizer = None
+        self.index_source = index_source
+        self.seed = int(seed)
+        self.cap_transitions = int(cap_transitions)
+        self._h = None
+        self._dims = None
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.gcrl_her_destroy(self._h)
+            self._h = None
+
+    # -- handle ---------------------------------------------------------------------------
+    def _ensure(self, D, A, G):
+        if self._h is None:
+            h = vp()
+            check(lib.gcrl_her_create(C.byref(h), self.device_index, self.max_mem_len,
+                                      self.cap_transitions, D, G, A, self.k_future, self.seed))
+            self._h, self._dims = h, (D, A, G)
+        elif self._dims != (D, A, G):
+            raise ValueError(f"transition shape changed: {self._dims} -> {(D, A, G)}")
+
+    @property
+    def handle(self):
+        return self._h
+
+    def _stream(self):
+        return _lib.current_stream(self.device_index)
+
+    # -- reference API --------------------------------------------------------------------
+    def push(self, idx, state, action, next_state, reward, done, desired_goal, achieved_goal):
+        ep = self.episodes[idx]
+        ep.append((_to_np(state), _to_np(action), _to_np(next_state), np.float32(reward),
+                   bool(done), _to_np(achieved_goal)))
+        if done or len(ep) >= _FLUSH_LEN:
+            self._commit(ep)
+            ep.clear()
+
+    def push_episode(self, s, a, ns, r, d, ag, fut=None):
+        """Commit a whole episode at once (arrays [T,...]); fut [T,k] uint8 or None."""
+        s = np.ascontiguousarray(s, np.float32)
+        a = np.ascontiguousarray(a, np.float32)
+        ns = np.ascontiguousarray(ns, np.float32)
+        r = np.ascontiguousarray(r, np.float32).reshape(-1)
+        d = np.ascontiguousarray(d, np.float32).reshape(-1)
+        ag = np.ascontiguousarray(ag, np.float32)
+        T = s.shape[0]
+        self._ensure(s.shape[1], a.shape[1], ag.shape[1])
+        if fut is None and self.index_source == "host":
+            fut = self._draw_future(T)
+        fptr = None
+        if fut is not None:
+            fut = np.ascontiguousarray(fut, np.uint8).reshape(T, max(self.k_future, 1))[:, :self.k_future]
+            fut = np.ascontiguousarray(fut)
+            fptr = np_ptr(fut)
+        check(lib.gcrl_her_push_episode(self._h, T, np_ptr(s), np_ptr(a), np_ptr(ns), np_ptr(r),
+                                        np_ptr(d), np_ptr(ag), fptr, self._stream()))
+
+    def _draw_future(self, T):
+        """random.randint(t+1, T-1) in apply_her's order (src/buffer.py:145-153)."""
+        k = self.k_future
+        fut = np.zeros((T, max(k, 1)), np.uint8)
+        for t in range(T - 1):
+            for j in range(k):
+                fut[t, j] = random.randint(t + 1, T - 1)
+        return fut
+
+    def _commit(self, ep):
+        s, a, ns, r, d, ag = zip(*ep)
+        self.push_episode(np.stack(s), np.stack(a), np.stack(ns), np.array(r, np.float32),
+                          np.array(d, np.float32), np.stack(ag))
+
+    def sample(self, batch_size: int, indices=None):
+        import torch
+        assert len(self) >= batch_size, "[ERROR] Not enough in buffer to sample"
+        B = int(batch_size)
+        D, A, _ = self._dims
+        dev = torch.device("cuda", self.device_index)
+        out = [torch.empty((B, w), dtype=torch.float32, device=dev) for w in (D, A, 1, D, 1)]
+        iptr = None
+        if indices is None and self.index_source == "host":
+            indices = random.sample(range(len(self)), B)       # == random.sample(deque, B)
+        if indices is not None:
+            indices = np.ascontiguousarray(indices, np.int64)
+            iptr = np_ptr(indices)
+        check(lib.gcrl_her_sample(self._h, B, iptr, vp(out[0].data_ptr()), vp(out[1].data_ptr()),
+                                  vp(out[2].data_ptr()), vp(out[3].data_ptr()),
+                                  vp(out[4].data_ptr()), None, self._stream()))
+        return tuple(out)                    # states, actions, rewards, next_states, dones
+
+    def sample_host(self, batch_size: int, indices=None, return_indices=False):
+        """sample() with NumPy outputs on the host (device->host copies inside the call)."""
+        assert len(self) >= batch_size, "[ERROR] Not enough in buffer to sample"
+        B = int(batch_size)
+        D, A, _ = self._dims
+        out = [np.empty((B, w), np.float32) for w in (D, A, 1, D, 1)]
+        iptr = None
+        if indices is None and self.index_source == "host":
+            indices = random.sample(range(len(self)), B)
+        if indices is not None:
+            indices = np.ascontiguousarray(indices, np.int64)
+            iptr = np_ptr(indices)
+        used = np.empty(B, np.int64) if return_indices else None
+        check(lib.gcrl_her_sample_host(self._h, B, iptr, np_ptr(out[0]), np_ptr(out[1]),
+                                       np_ptr(out[2]), np_ptr(out[3]), np_ptr(out[4]),
+                                       np_ptr(used) if used is not None else None, self._stream()))
+        return (*out, used) if return_indices else tuple(out)
+
+    def __len__(self):
+        return int(lib.gcrl_her_len(self._h)) if self._h else 0
+
+    def compute_termination(self, dg, ag):                 # src/buffer.py:140-141
+        return np.linalg.norm(np.asarray(dg) - np.asarray(ag), axis=-1) < self.threshold

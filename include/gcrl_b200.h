@@ -1,0 +1,210 @@
+/*
+ * gcrl_b200.h -- C ABI of the B200-native HER-sample + off-policy-update hot path.
+ *
+ * Drop-in boundary for CodeKnight314/Goal-Conditioned-RL-Framework.  The reference
+ * has no FFI of its own (it is pure Python), so each entry point below replaces a
+ * reference *method*; the citation next to it is the reference file:line it stands
+ * in for.  INTEGRATION.md shows the ctypes binding and the two-line import change a
+ * maintainer makes in src/env.py.
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in signatures.  `stream` is a
+ *     cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - every function returns GCRL_OK (0) or an error code; gcrl_last_error() gives
+ *     the message for the calling thread.
+ *   - "dev" pointers are device pointers on the handle's GPU, "host" pointers are
+ *     ordinary host memory borrowed for the duration of the call.
+ *   - one host thread drives one handle; work is ordered on the stream passed in.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     fails with GCRL_ERR_CUDA.
+ */
+#ifndef GCRL_B200_H
+#define GCRL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCRL_ABI_VERSION 1
+
+#define GCRL_OK 0
+#define GCRL_ERR_INVALID 1      /* bad argument / shape                                  */
+#define GCRL_ERR_UNDERFILLED 2  /* sample(B) with len < B: AssertionError, buffer.py:122 */
+#define GCRL_ERR_CUDA 3         /* CUDA runtime error (or no device)                     */
+#define GCRL_ERR_CAPACITY 4     /* transition / episode ring would overflow              */
+
+int gcrl_abi_version(void);
+const char *gcrl_last_error(void);
+int gcrl_device_count(int *count);
+
+/* ------------------------------------------------------------------------------------
+ * HER replay buffer -- replaces HERBuffer, src/buffer.py:92-179
+ * ------------------------------------------------------------------------------------
+ * Device-resident episode store.  An episode of T transitions stands for
+ * E = (T-1)(k+1)+1 *entries* in the reference's deque order (src/buffer.py:145-179):
+ * for t = 0..T-1 the original, then -- if t < T-1 -- k future-relabelled copies.
+ * Entries are never materialised: gcrl_her_sample() maps a deque position to
+ * (episode, t, j) and relabels on the fly.  `max_entries` is the deque's maxlen
+ * (per-ENTRY FIFO eviction, src/buffer.py:101); `cap_transitions` sizes the ring of
+ * stored transitions (<= 0: max_entries, always sufficient).
+ */
+typedef struct gcrl_her gcrl_her;
+
+int gcrl_her_create(gcrl_her **out, int device, int64_t max_entries, int64_t cap_transitions,
+                    int state_dim /* D = obs + goal */, int goal_dim, int act_dim, int k_future,
+                    uint64_t seed);
+int gcrl_her_destroy(gcrl_her *h);
+
+/* Commit one finished episode (what HERBuffer.push does when `done or len >= 50`,
+ * src/buffer.py:117-119 -> apply_her :143-179).  Row t is the tuple pushed at
+ * src/env.py:215-224: s[t] = state, ns[t] = next_state (both [D], goal in the last
+ * goal_dim columns), a[t], r[t], d[t] (0/1), ag[t] = achieved goal of the NEXT
+ * observation.  fut[t*k + j] (t < T-1) is the absolute future index f in [t+1, T-1]
+ * drawn by `random.randint(t+1, T-1)` at src/buffer.py:153; NULL = draw them from the
+ * handle's own counter-based generator.  All pointers are host memory.  1 <= T <= 255. */
+int gcrl_her_push_episode(gcrl_her *h, int T, const float *s, const float *a, const float *ns,
+                          const float *r, const float *d, const float *ag, const uint8_t *fut,
+                          void *stream);
+
+int64_t gcrl_her_len(const gcrl_her *h);            /* __len__, src/buffer.py:137-138   */
+int64_t gcrl_her_total_entries(const gcrl_her *h);  /* entries ever appended            */
+int64_t gcrl_her_live_transitions(const gcrl_her *h);
+int gcrl_her_clear(gcrl_her *h);
+
+/* sample(batch_size), src/buffer.py:121-135.  Outputs are DEVICE pointers:
+ * states [B,D], actions [B,A], rewards [B,1], next_states [B,D], dones [B,1] float32.
+ * idx_host: B deque positions in [0, len) (the stream `random.sample(range(len), B)`
+ * yields -- identical to random.sample(deque, B) at src/buffer.py:124), or NULL to draw
+ * B distinct positions on the device (keyed Feistel permutation of [0, len), i.e.
+ * uniform without replacement like random.sample).  idx_out_dev (optional, int64[B])
+ * receives the positions used.  Returns GCRL_ERR_UNDERFILLED when len < B. */
+int gcrl_her_sample(gcrl_her *h, int64_t B, const int64_t *idx_host, float *states_dev,
+                    float *actions_dev, float *rewards_dev, float *next_states_dev,
+                    float *dones_dev, int64_t *idx_out_dev, void *stream);
+/* Same, positions already on the device. */
+int gcrl_her_sample_dev_idx(gcrl_her *h, int64_t B, const int64_t *idx_dev, float *states_dev,
+                            float *actions_dev, float *rewards_dev, float *next_states_dev,
+                            float *dones_dev, void *stream);
+/* Same as gcrl_her_sample but the five outputs are HOST buffers (device->host copies
+ * and a stream synchronise inside the call). */
+int gcrl_her_sample_host(gcrl_her *h, int64_t B, const int64_t *idx_host, float *states,
+                         float *actions, float *rewards, float *next_states, float *dones,
+                         int64_t *idx_out, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Running normaliser -- replaces RunningNormalizer, src/utils.py:68-117
+ * ------------------------------------------------------------------------------------ */
+typedef struct gcrl_norm gcrl_norm;
+
+int gcrl_norm_create(gcrl_norm **out, int device, int dim, double clip_range, double eps_count);
+int gcrl_norm_destroy(gcrl_norm *h);
+/* update(x), src/utils.py:75-94.  x: host [n, dim], float64 (is_f64 != 0) or float32. */
+int gcrl_norm_update(gcrl_norm *h, const void *x_host, int64_t n, int is_f64, void *stream);
+/* Same with x already on the device. */
+int gcrl_norm_update_dev(gcrl_norm *h, const void *x_dev, int64_t n, int is_f64, void *stream);
+/* normalize(x), src/utils.py:96-98: clip((x-mean)/(sqrt(var)+1e-8), +-clip) in float64.
+ * host in -> host out (float64 [n, dim]); synchronises the stream. */
+int gcrl_norm_apply(gcrl_norm *h, const void *x_host, int64_t n, int is_f64, double *out_host,
+                    void *stream);
+/* Device variant: float32 output written at out_dev[row*out_stride + out_col0 + c]
+ * (lets the caller build obs||goal rows, src/agent.py:1434-1445, without a concat). */
+int gcrl_norm_apply_dev_f32(gcrl_norm *h, const void *x_dev, int64_t n, int is_f64,
+                            float *out_dev, int64_t out_stride, int64_t out_col0, void *stream);
+int gcrl_norm_get_state(gcrl_norm *h, double *mean, double *var, double *count,
+                        double *clip_range, void *stream);
+int gcrl_norm_set_state(gcrl_norm *h, const double *mean, const double *var, double count,
+                        double clip_range, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Off-policy agents -- replace DDPG (src/agent.py:1173-1465) and TD3Agent (:12-386)
+ * ------------------------------------------------------------------------------------ */
+typedef struct gcrl_agent gcrl_agent;
+
+#define GCRL_ALGO_DDPG 0
+#define GCRL_ALGO_TD3 1
+
+typedef struct gcrl_agent_config {
+  int32_t algo;          /* GCRL_ALGO_*                                                */
+  int32_t state_dim;     /* D = obs + goal (env.py:120 passes obs_dim + dg_dim)        */
+  int32_t act_dim;
+  int32_t hidden_dim;    /* BaseAgentConfig.hidden_dim, src/utils.py:11                */
+  int32_t layer_count;   /* number of hidden layers, src/utils.py:12                   */
+  int32_t max_batch;     /* largest B an update will see                               */
+  float gamma;           /* src/utils.py:23                                            */
+  float tau;             /* src/utils.py:33                                            */
+  float grad_clip;       /* < 0: no clipping (grad_clip None)                          */
+  float policy_noise;    /* TD3 target smoothing sigma, src/agent.py:175               */
+  float noise_clamp;     /* TD3, src/agent.py:176                                      */
+  float weight_decay;    /* 0 = Adam (DDPG); 0.01 = AdamW default (TD3)                */
+  int32_t precision;     /* 0 = fp32 FFMA (parity); reserved for tensor-core modes     */
+  int32_t reserved;
+} gcrl_agent_config;
+
+int gcrl_agent_create(gcrl_agent **out, int device, const gcrl_agent_config *cfg);
+int gcrl_agent_destroy(gcrl_agent *h);
+
+/* Networks: 0 actor, 1 critic(_1), 2 target_actor, 3 target_critic(_1), 4 critic_2,
+ * 5 target_critic_2.  Parameters are exchanged per layer in the reference checkpoint
+ * layout: weight [out, in] row-major fp32, bias [out] (state_dict keys
+ * base_net.{0,2,..} / net.{0,2,..}, src/model.py:24-26,64-65; save/load :32-37). */
+int gcrl_agent_num_layers(const gcrl_agent *h, int net);
+int gcrl_agent_layer_shape(const gcrl_agent *h, int net, int layer, int *out_dim, int *in_dim);
+int gcrl_agent_set_layer(gcrl_agent *h, int net, int layer, const float *weight_host,
+                         const float *bias_host, void *stream);
+int gcrl_agent_get_layer(gcrl_agent *h, int net, int layer, float *weight_host,
+                         float *bias_host, void *stream);
+/* update_target_network(hard_update=True), src/agent.py:1255-1258 */
+int gcrl_agent_hard_update(gcrl_agent *h, void *stream);
+/* Optimiser state is zeroed (Adam step counters too): a fresh torch.optim.Adam. */
+int gcrl_agent_reset_optim(gcrl_agent *h, void *stream);
+
+/* One update on an explicit device batch (critic_update :1302-1343, Polyak :1259-1271,
+ * actor_update :1288-1300, in the order of update() :1378-1404).
+ *   flags bit0: run the actor step; bit1: Polyak soft update (before the actor step).
+ *   noise_dev: TD3 only, [B, A] standard-normal draws (the randn_like at agent.py:175),
+ *   NULL for DDPG.
+ *   metrics_host (optional, float[8]): critic_loss, actor_loss, td_error, q_value,
+ *   critic_grad_norm, actor_grad_norm, critic2_loss, critic2_grad_norm -- copied back
+ *   and the stream synchronised when non-NULL; NULL leaves the update fully async. */
+int gcrl_agent_update_batch(gcrl_agent *h, int64_t B, const float *s_dev, const float *a_dev,
+                            const float *r_dev, const float *ns_dev, const float *d_dev,
+                            const float *noise_dev, double lr_critic, double lr_actor,
+                            int flags, float *metrics_host, void *stream);
+/* Fused hot path: sample B transitions from `buf` (positions idx_host or on-device
+ * draw) and run the update, one call (update(), src/agent.py:1378-1404). */
+int gcrl_agent_update_from_buffer(gcrl_agent *h, gcrl_her *buf, int64_t B,
+                                  const int64_t *idx_host, const float *noise_dev,
+                                  double lr_critic, double lr_actor, int flags,
+                                  float *metrics_host, void *stream);
+/* Device metrics of the most recent update (float[8], same order). */
+int gcrl_agent_read_metrics(gcrl_agent *h, float *metrics_host, void *stream);
+
+/* actor(obs) for select_action, src/agent.py:1345-1366: obs host [n, D] -> act host
+ * [n, A] = tanh-squashed network output (the caller applies the reference's second
+ * tanh, noise and clipping). */
+int gcrl_agent_act(gcrl_agent *h, int64_t n, const float *obs_host, float *act_host,
+                   void *stream);
+/* Q(s, a) with the online critic; host in / host out [n, 1] (tests, diagnostics). */
+int gcrl_agent_q(gcrl_agent *h, int64_t n, const float *obs_host, const float *act_host,
+                 float *q_host, void *stream);
+
+/* Data-parallel hooks (one process per GPU; the caller all-reduces between phases):
+ * phase 0: critic forward/backward -> flat critic gradient (sum over the local batch,
+ *          already divided by B_local);   phase 1: clip + Adam (+ Polyak per flags);
+ * phase 2: actor forward/backward -> flat actor gradient;   phase 3: clip + Adam.
+ * gcrl_agent_grad_buffer exposes the flat fp32 gradient of a network (device ptr +
+ * element count) so it can be handed to NCCL. */
+int gcrl_agent_update_phase(gcrl_agent *h, int phase, int64_t B, const float *s_dev,
+                            const float *a_dev, const float *r_dev, const float *ns_dev,
+                            const float *d_dev, const float *noise_dev, double lr, int flags,
+                            void *stream);
+int gcrl_agent_grad_buffer(gcrl_agent *h, int net, float **grad_dev, int64_t *count);
+/* flat metric partial sums for cross-rank averaging: device float[8] */
+int gcrl_agent_metrics_buffer(gcrl_agent *h, float **metrics_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCRL_B200_H */
