@@ -1,0 +1,474 @@
+#!/usr/bin/env python
+"""bench.py -- HER sample + DDPG update hot path on B200, next to the CPU port of the reference.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one pass of the hot path over one batch: draw B positions of the HER buffer,
+gather + future-relabel + sparse reward, then one DDPG update (target forward, Bellman target,
+critic backward, clip, Adam, Polyak every 40th step, actor backward, clip, Adam) -- what
+``DDPG.update(step)`` does in the reference (src/agent.py:1378-1404).
+
+Workload at N=1 (BASELINE.json configs[1]): PandaPush shape (obs 18, goal 3, action 3), T=50,
+k_future=4, 1M stored transitions per GPU (20 000 episodes = 4.92M deque entries), batch 256,
+hidden 256 x 3 layers, synthetic data (SURVEY 8d recipe).  N>1: every rank owns its own
+1M-transition episode shard and samples its local batch of 256 (weak scaling); critic and actor
+gradients are averaged with NCCL between backward and optimiser phases.
+
+One JSON line on stdout (rank 0); progress on stderr.
+"""
+import argparse
+import json
+import os
+import random
+import sys
+import threading
+import time
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "goal-conditioned-rl-framework_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "her_relabelled_transitions_per_s"   # sampled+relabelled transitions consumed by DDPG updates
+UNIT = "transitions/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--hidden", type=int, default=256)
+    ap.add_argument("--layers", type=int, default=3)
+    ap.add_argument("--obs", type=int, default=18)
+    ap.add_argument("--goal", type=int, default=3)
+    ap.add_argument("--act", type=int, default=3)
+    ap.add_argument("--k-future", type=int, default=4)
+    ap.add_argument("--transitions", type=int, default=1_000_000, help="stored raw transitions per GPU")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the batch sweep / kernel rooflines")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic data: obs ~ N(0,1); achieved goal = random walk, 30 % rest steps;
+# desired goal ~ U(-0.15, 0.15)^3 constant per episode; actions ~ U(-1, 1); done = 0
+# ------------------------------------------------------------------------------------------
+def sparse_reward(ag, dg):
+    d = ag - dg
+    sq = d * d
+    acc = sq[..., 0]
+    for i in range(1, sq.shape[-1]):
+        acc = acc + sq[..., i]
+    return -(np.sqrt(acc) > np.float32(0.05)).astype(np.float32)
+
+
+def synth(rng, E, T, O, G, A, k):
+    obs = rng.standard_normal((E, T + 1, O), dtype=np.float32)
+    steps = rng.normal(0, 0.02, (E, T, G)).astype(np.float32) * (rng.random((E, T, 1)) > 0.3)
+    ag0 = rng.uniform(-0.15, 0.15, (E, 1, G)).astype(np.float32)
+    ag = np.concatenate([ag0, ag0 + np.cumsum(steps, 1, dtype=np.float32)], 1)
+    dg = np.repeat(rng.uniform(-0.15, 0.15, (E, 1, G)).astype(np.float32), T, 1)
+    s = np.concatenate([obs[:, :-1], dg], -1)
+    ns = np.concatenate([obs[:, 1:], dg], -1)
+    a = rng.uniform(-1, 1, (E, T, A)).astype(np.float32)
+    r = sparse_reward(ag[:, 1:], dg)
+    d = np.zeros((E, T), np.float32)
+    fut = np.zeros((E, T, max(k, 1)), np.uint8)
+    for t in range(T - 1):
+        fut[:, t] = rng.integers(t + 1, T, (E, max(k, 1)))
+    return dict(s=s, a=a, ns=ns, r=r, d=d, ag=np.ascontiguousarray(ag[:, 1:]), fut=fut[:, :, :k] if k else fut)
+
+
+def agent_config(args, max_len):
+    return types.SimpleNamespace(
+        hidden_dim=args.hidden, layer_count=args.layers, actor_lr=1e-3, actor_lr_min=1e-3,
+        ac_scheduler_steps=1, critic_lr=1e-3, critic_lr_min=1e-3, cr_scheduler_steps=1, buffer_type="HER",
+        max_len=max_len, alpha=1.0, batch_size=args.batch, gamma=0.98, ac_update_freq=1, noise_std=0.2,
+        noise_clamp=0.5, policy_noise=0.0, grad_clip=10.0, beta=1.0, beta_end=1, k_future=args.k_future,
+        max_eps_len=50, tau=0.05)
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the NumPy port of the reference (oracle/), eager deque buffer + DDPG update
+# ------------------------------------------------------------------------------------------
+def cpu_arm(args, steps, warmup, seconds=None):
+    """Times sample(B) + update on the host.  The eager deque design is run at the reference's
+    own cap, max_len = 1M entries (src/config/DDPG/config_ddpg_push.yaml:28); beyond that it needs
+    >5 GB of Python objects."""
+    from collections import deque
+    from oracle import ddpg as OD
+    from oracle import her as OH
+    try:
+        from threadpoolctl import threadpool_info
+        cores = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        cores = os.cpu_count() or 1
+    rng = np.random.default_rng(0)
+    T, k, O, G, A = 50, args.k_future, args.obs, args.goal, args.act
+    D = O + G
+    max_len = 1_000_000
+    E = max_len // ((T - 1) * (k + 1) + 1) + 1
+    t0 = time.time()
+    data = synth(rng, E, T, O, G, A, k)
+    buf = OH.HERBufferOracle(max_len, 50, 1, k_future=k)
+    for e in range(E):   # vectorised materialisation of apply_her's entries, then the same deque
+        S, Aa, R, NS, Dn = OH.materialise_episode(data["s"][e], data["a"][e], data["ns"][e], data["r"][e],
+                                                  data["d"][e], data["ag"][e], data["fut"][e], k)
+        buf.buffer.extend(zip(S, Aa, NS, R[:, 0], Dn[:, 0] > 0, S[:, -G:], S[:, -G:]))
+    log(f"[cpu] deque of {len(buf)} entries built in {time.time() - t0:.1f}s; BLAS threads {cores}")
+    actor0, critic0 = OD.init_mlp(rng, D, args.hidden, A, args.layers), OD.init_mlp(rng, D + A, args.hidden, 1, args.layers)
+    agent = OD.DDPGOracle(actor0, critic0, gamma=0.98, tau=0.05, grad_clip=10.0, actor_lr=1e-3, critic_lr=1e-3)
+    random.seed(1898)
+    B = args.batch
+
+    def one(step):
+        s, a, r, ns, d = buf.sample(B)
+        agent.update_on_batch(step, s, a, r, ns, d)
+
+    for i in range(warmup):
+        one(i + 1)
+    n, t0 = 0, time.perf_counter()
+    while n < steps:
+        one(warmup + n + 1)
+        n += 1
+        if seconds is not None and time.perf_counter() - t0 > seconds:
+            break
+    dt = time.perf_counter() - t0
+    return dict(value=n * B / dt, unit=UNIT, cores=cores, kind="port",
+                sample=f"{n} steps of sample({B}) + DDPG update (H={args.hidden}, L={args.layers}) on a "
+                       f"{len(buf)}-entry eager deque (the reference's own max_len), NumPy/BLAS port of the "
+                       f"reference (oracle/her.py, oracle/ddpg.py), {dt:.1f}s",
+                updates_per_s=n / dt, ms_per_step=dt / n * 1e3, steps=n)
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_arm(args, args.steps, args.warmup, seconds=120.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": res["steps"], "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.gpus), "updates_per_s": res["updates_per_s"],
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"DDPG sample+update, PandaPush shape (obs {args.obs}, goal {args.goal}, act {args.act}), "
+                        f"T=50, k_future={args.k_future}, {args.transitions} stored transitions per GPU, "
+                        f"batch {args.batch} per GPU, hidden {args.hidden} x {args.layers}",
+            "batch_per_gpu": args.batch, "global_batch": args.batch * world, "hidden": args.hidden,
+            "layers": args.layers, "buffer_transitions_per_gpu": args.transitions,
+            "parallelism": f"dp{world} (episode-sharded buffer, NCCL gradient all-reduce)" if world > 1 else "single GPU",
+            "index_stream": "on-device (value) / host Mersenne-Twister random.sample (e2e)",
+            "l2": "flushed between timed steps (256 MiB write); buffer (224 MB) larger than L2"}
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+    NOTE = {"sw_power_cap": 0x4}
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.stop_flag = [], set(), False
+        self.max_mhz, self.ok = None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:   # noqa: BLE001
+            log(f"[clocks] NVML unavailable: {e}")
+
+    def sample(self):
+        nv = self.nv
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:   # noqa: BLE001
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in {**self.BAD, **self.NOTE}.items():
+            if mask & bit:
+                self.reasons.add(name)
+
+    def run(self):
+        while self.ok and not self.stop_flag:
+            try:
+                self.sample()
+            except Exception:   # noqa: BLE001
+                break
+            time.sleep(self.period)
+
+    def result(self):
+        self.stop_flag = True
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml_unavailable"]}
+        if not self.samples:
+            self.sample()
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": float(self.max_mhz),
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def gpu_main(args):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    import gcrl_b200
+    from gcrl_b200 import DDPG, _lib
+    from gcrl_b200._lib import check, lib, vp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:   # noqa: BLE001
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+
+    T, k, O, G, A, B = 50, args.k_future, args.obs, args.goal, args.act, args.batch
+    D = O + G
+    E = args.transitions // T
+    per_ep = (T - 1) * (k + 1) + 1
+    max_len = E * per_ep
+    rng = np.random.default_rng(1000 + rank)            # every rank owns a different episode shard
+    t0 = time.time()
+    data = synth(rng, E, T, O, G, A, k)
+    launches0 = int(lib.gcrl_kernel_launches())
+
+    def make_agent(index_source, max_batch):
+        torch.manual_seed(1898)                          # identical initial weights on every rank
+        ag = DDPG(D, A, agent_config(args, max_len), None, 1, 40, index_source=index_source, device=local,
+                  max_batch=max_batch, seed=1898 + rank)
+        for e in range(E):
+            ag.buffer.push_episode(data["s"][e], data["a"][e], data["ns"][e], data["r"][e], data["d"][e],
+                                   data["ag"][e], data["fut"][e])
+        return ag
+
+    sweep_batches = [] if (args.no_sweep or world > 1) else [1024, 4096, 16384, 65536]
+    agent = make_agent("device", max(B, max(sweep_batches + [B])))
+    torch.cuda.synchronize()
+    log(f"[rank {rank}] {E} episodes / {len(agent.buffer)} entries committed in {time.time() - t0:.1f}s")
+    if world > 1:
+        agent.enable_data_parallel()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    sp = vp(stream.cuda_stream)
+
+    def device_step(step, batch=B):
+        """Async step on the device index stream, no host read-back (what `value` times)."""
+        agent.batch_size = batch
+        agent._run_update(step, sync=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_steps(n, first_step, batch=B, do_flush=True):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for i, (e0, e1) in enumerate(evs):
+            if do_flush:
+                flush.fill_(i & 0xFF)
+            e0.record(stream)
+            device_step(first_step + i, batch)
+            e1.record(stream)
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)    # ms
+
+    # ---- warm-up (graph capture for both flag sets, clocks ramp), then the timed region ----
+    step = 1
+    for _ in range(max(args.warmup, 3) + 80):
+        device_step(step)
+        step += 1
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = int(lib.gcrl_kernel_launches())
+    ms = timed_steps(args.steps, step)
+    step += args.steps
+    launches = int(lib.gcrl_kernel_launches()) - l0
+    barrier()
+    # keep the sampler alive over a short loaded stretch so that short runs still record clocks
+    t_end = time.time() + 0.3
+    while time.time() < t_end:
+        device_step(step)
+        step += 1
+    torch.cuda.synchronize()
+    clk = clocks.result()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # back-to-back (no flush, graph replays pipelined): the production regime, reported beside `value`
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        device_step(step + i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    step += args.steps
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_b2b = float(t.item())
+
+    # ---- e2e: the public API call a user makes -- agent.update(step) with the reference's host
+    # Mersenne-Twister index stream (H2D of the positions from pinned memory), the 8-float metric
+    # read-back every step (D2H), and the ingest of 16 fresh episodes every 40 updates
+    # (max_episode / gradient_step of config_ddpg_push.yaml) ----
+    agent.index_source = "host"
+    agent.buffer.index_source = "host"
+    agent.batch_size = B
+    random.seed(1898 + rank)
+    row_bytes = 4 * (2 * D + A + 2 + G) + k
+    ep_bytes = 64 + T * (row_bytes + 16)
+    h2d = B * 8 + 32 + 16 * ep_bytes / 40.0
+    d2h = 32
+
+    def e2e_step(i):
+        if i % 40 == 0:
+            for e in range(16):
+                j = (i // 40 * 16 + e) % E
+                agent.buffer.push_episode(data["s"][j], data["a"][j], data["ns"][j], data["r"][j], data["d"][j],
+                                          data["ag"][j], None)     # future offsets drawn by random.randint
+        return agent.update(step + i)
+
+    for i in range(max(args.warmup, 3)):
+        e2e_step(i)
+    n_e2e = max(40, min(args.steps, 400))
+    barrier()
+    e0.record(stream)
+    w0 = time.perf_counter()
+    for i in range(n_e2e):
+        info = e2e_step(i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - w0) * 1e3
+    step += n_e2e
+    t = torch.tensor([max(e0.elapsed_time(e1), wall)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+    e2e_value = world * B * n_e2e / (ms_e2e * 1e-3)
+    assert all(np.isfinite(float(x)) for x in info), info
+
+    # ---- kernel rooflines (rank 0, N=1): the HER sampler alone, CUDA events on its stream ----
+    agent.index_source = "device"
+    agent.buffer.index_source = "device"
+    alg_bytes = 4 * (2 * O + A + 2 * G) + 5 + 4 * (2 * D + A + 2)      # 373 B for Push
+    rooflines = {}
+
+    def time_sampler(batch, iters):
+        outs = [torch.empty((batch, w), dtype=torch.float32, device=dev) for w in (D, A, 1, D, 1)]
+        ptrs = [vp(o.data_ptr()) for o in outs]
+        for _ in range(5):
+            check(lib.gcrl_her_sample(agent.buffer.handle, batch, None, *ptrs, None, sp))
+        tot = 0.0
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        for i, (a0, a1) in enumerate(evs):
+            flush.fill_(i & 0xFF)
+            a0.record(stream)
+            check(lib.gcrl_her_sample(agent.buffer.handle, batch, None, *ptrs, None, sp))
+            a1.record(stream)
+        torch.cuda.synchronize()
+        tot = sum(a.elapsed_time(b) for a, b in evs) / iters
+        return tot
+
+    if rank == 0:
+        for batch in [B] + sweep_batches:
+            ms_k = time_sampler(batch, 50)
+            ach = batch * alg_bytes / (ms_k * 1e-3) / 1e9
+            rooflines[f"her_sample_kernel_B{batch}"] = {
+                "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "traffic": None, "ms_per_launch": ms_k, "algorithmic_bytes_per_transition": alg_bytes,
+                "transitions_per_s": batch / (ms_k * 1e-3)}
+    sweep = {}
+    for batch in sweep_batches:
+        for _ in range(45):
+            device_step(step, batch)
+            step += 1
+        n = max(20, min(200, args.steps))
+        ms_s = timed_steps(n, step, batch)
+        step += n
+        flops = 2.0 * (4 * (D * args.hidden + (args.layers - 1) * args.hidden ** 2 + args.hidden * A)
+                       + 6 * ((D + A) * args.hidden + (args.layers - 1) * args.hidden ** 2 + args.hidden)) * batch
+        sweep[f"B{batch}"] = {"ms_per_step": ms_s / n, "transitions_per_s": batch * n / (ms_s * 1e-3),
+                              "updates_per_s": n / (ms_s * 1e-3), "update_tflops": flops / (ms_s / n * 1e-3) / 1e12}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_arm(args, 10 ** 9, 2, seconds=args.cpu_seconds)
+    if rank == 0:
+        key = f"her_sample_kernel_B{B}"
+        roof = dict(rooflines.get(key, {}))
+        roof["kernel"] = "her_sample_kernel"
+        roof["peak_source"] = peak_src
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "updates_per_s": world * args.steps / (ms * 1e-3) / world,
+            "back_to_back": {"ms_per_step": ms_b2b / args.steps, "value": world * B * args.steps / (ms_b2b * 1e-3),
+                             "note": "same steps without the L2 flush, graph replays pipelined"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / n_e2e, "steps": n_e2e,
+                    "api": "DDPG.update(step) with host random.sample index stream + metric read-back; "
+                           "16 episodes ingested every 40 updates"},
+            "gpu_launches": launches, "clocks": clk, "roofline": roof, "rooflines": rooflines, "sweep": sweep,
+            "cpu_baseline": None if cpu is None else {k_: cpu[k_] for k_ in ("value", "unit", "cores", "kind", "sample")},
+            "library": os.path.relpath(gcrl_b200.library_path(), ROOT),
+            "kernel_launches_total": int(lib.gcrl_kernel_launches()) - launches0,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_main(args)
+    else:
+        gpu_main(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -115,9 +115,12 @@ struct gcrl_agent {
   PinnedRing io_stage;
   float *d_io = nullptr;
   size_t io_cap = 0;
+  float *noise = nullptr;                  // TD3 smoothing noise copy [maxB, A]
+  int dp_B = -1, dp_flags = -1;            // the update the data-parallel phases belong to
   bool use_graphs = true;
   cudaStream_t cap_stream = nullptr;       // capture-only stream (the caller's may be the legacy one)
-  std::map<std::tuple<int64_t, int, int>, cudaGraphExec_t> graphs;   // (B, flags, phase mask)
+  struct GraphRec { cudaGraphExec_t exec; uint64_t kernels; };
+  std::map<std::tuple<int64_t, int, int>, GraphRec> graphs;   // (B, flags, phase mask)
 };
 
 namespace {
@@ -158,15 +161,18 @@ void backward_hidden(gcrl_agent *ag, const Net &n, const float *X, int ldx, int 
   *cur_out = cur;
 }
 
-void reduce_and_step(gcrl_agent *ag, Net &n, const int *splits, int head_splits, int which, float max_norm,
-                     int slot_loss, int slot_td, int slot_q, int slot_norm, int metric_splits, int B,
-                     float *target, bool polyak, cudaStream_t st) {
+// partial slabs -> flat gradient of `n` (+ per-CTA sums of squares, + batch-mean metrics).
+// rereduce: the gradient is already in n.g (it was averaged across ranks); only the sums of
+// squares for the global-norm clip are recomputed.
+void reduce_grads(gcrl_agent *ag, Net &n, const int *splits, int head_splits, bool rereduce, int slot_loss,
+                  int slot_td, int slot_q, int metric_splits, int B, cudaStream_t st) {
   ReduceArgs r{};
   r.nseg = 0;
   for (int l = 0; l < n.layers; ++l) {
-    const int sp = l == n.layers - 1 ? head_splits : splits[l];
-    SegDesc w{n.w_off[l], n.out_d[l] * n.ldw[l], ag->partials, sp, ag->slab, n.w_off[l]};
-    SegDesc b{n.b_off[l], n.out_d[l], ag->partials, sp, ag->slab, n.b_off[l]};
+    const int sp = rereduce ? 0 : (l == n.layers - 1 ? head_splits : splits[l]);
+    const float *src = rereduce ? nullptr : ag->partials;
+    SegDesc w{n.w_off[l], n.out_d[l] * n.ldw[l], src, sp, ag->slab, n.w_off[l]};
+    SegDesc b{n.b_off[l], n.out_d[l], src, sp, ag->slab, n.b_off[l]};
     r.seg[r.nseg++] = w;
     r.seg[r.nseg++] = b;
   }
@@ -179,6 +185,11 @@ void reduce_and_step(gcrl_agent *ag, Net &n, const int *splits, int head_splits,
   r.metrics = ag->metrics;
   r.slot_loss = slot_loss; r.slot_td = slot_td; r.slot_q = slot_q;
   launch_reduce_grads(r, st);
+}
+
+// global-norm clip + Adam(W) (+ fused Polyak of `target` with the stepped parameters)
+void adam_step(gcrl_agent *ag, Net &n, int which, float max_norm, int slot_norm, float *target, bool polyak,
+               cudaStream_t st) {
   AdamArgs a{};
   a.p = n.p; a.m = n.m; a.v = n.v; a.g = n.g; a.n = n.total;
   a.sumsq_partials = ag->sumsq; a.nsumsq = reduce_grid(n.total);
@@ -259,30 +270,42 @@ struct PhaseState {
   int head_splits = 0, metric_splits = 0;
 };
 
-void critic_phase_fb(gcrl_agent *ag, int B, const float *noise, PhaseState *ps /*[2]*/, cudaStream_t st) {
+// critic(s): forward, loss, backward, partials -> flat local-mean gradient(s) + metrics
+void critic_phase_grads(gcrl_agent *ag, int B, const float *noise, cudaStream_t st) {
+  PhaseState ps;
   targets_and_critic_forward(ag, B, noise, st);
-  critic_forward_backward(ag, 0, B, ps[0].splits, &ps[0].head_splits, &ps[0].metric_splits, st);
+  critic_forward_backward(ag, 0, B, ps.splits, &ps.head_splits, &ps.metric_splits, st);
+  reduce_grads(ag, ag->net[CRITIC1], ps.splits, ps.head_splits, false, S_CLOSS, ag->td3 ? -1 : S_TD,
+               ag->td3 ? -1 : S_Q, ps.metric_splits, B, st);
+}
+void critic2_phase_grads(gcrl_agent *ag, int B, cudaStream_t st) {   // TD3 only; reuses dz / partials
+  PhaseState ps;
+  critic_forward_backward(ag, 1, B, ps.splits, &ps.head_splits, &ps.metric_splits, st);
+  reduce_grads(ag, ag->net[CRITIC2], ps.splits, ps.head_splits, false, S_C2LOSS, S_TD, S_Q, ps.metric_splits,
+               B, st);
 }
 
-void critic_phase_step(gcrl_agent *ag, int B, int flags, PhaseState *ps, cudaStream_t st) {
+// clip + Adam (+ Polyak) of critic `which`; rereduce: gradients were replaced by the cross-rank
+// average, so the sums of squares are recomputed first.
+void critic_phase_step(gcrl_agent *ag, int which, int flags, bool rereduce, cudaStream_t st) {
   const bool polyak = ag->td3 ? true : ((flags & 2) != 0);
-  // DDPG: actor target blends the PRE-step actor, before the actor step (:1397-1401)
-  if (!ag->td3 && polyak)
+  Net &c = ag->net[which == 0 ? CRITIC1 : CRITIC2];
+  if (rereduce) reduce_grads(ag, c, nullptr, 0, true, -1, -1, -1, 0, 1, st);
+  // TD3 critic 1 is NOT clipped (:201 is commented out), critic 2 is
+  const float clip = (ag->td3 && which == 0) ? -1.0f : ag->cfg.grad_clip;
+  adam_step(ag, c, 0, clip, which == 0 ? S_CGRAD : S_C2GRAD, ag->net[which == 0 ? T_CRITIC1 : T_CRITIC2].p,
+            polyak, st);
+}
+
+// DDPG: the actor target blends the PRE-step actor, before the actor step (:1397-1401)
+void ddpg_actor_target_polyak(gcrl_agent *ag, int flags, cudaStream_t st) {
+  if (!ag->td3 && (flags & 2))
     launch_polyak(ag->net[T_ACTOR].p, ag->net[ACTOR].p, ag->net[ACTOR].total, ag->cfg.tau,
                   float(1.0 - double(ag->cfg.tau)), st);
-  const float clip1 = ag->td3 ? -1.0f : ag->cfg.grad_clip;     // TD3 critic 1 is NOT clipped (:201)
-  reduce_and_step(ag, ag->net[CRITIC1], ps[0].splits, ps[0].head_splits, 0, clip1, S_CLOSS,
-                  ag->td3 ? -1 : S_TD, ag->td3 ? -1 : S_Q, S_CGRAD, ps[0].metric_splits, B,
-                  ag->net[T_CRITIC1].p, polyak, st);
-  if (ag->td3) {
-    // critic 2: its own backward reuses dz / partial buffers after critic 1's optimiser pass
-    critic_forward_backward(ag, 1, B, ps[1].splits, &ps[1].head_splits, &ps[1].metric_splits, st);
-    reduce_and_step(ag, ag->net[CRITIC2], ps[1].splits, ps[1].head_splits, 0, ag->cfg.grad_clip, S_C2LOSS,
-                    S_TD, S_Q, S_C2GRAD, ps[1].metric_splits, B, ag->net[T_CRITIC2].p, polyak, st);
-  }
 }
 
-void actor_phase_fb(gcrl_agent *ag, int B, PhaseState *ps, cudaStream_t st) {
+void actor_phase_grads(gcrl_agent *ag, int B, cudaStream_t st) {
+  PhaseState pstate, *ps = &pstate;
   const int D = ag->D, A = ag->A, K0 = D + A, L = ag->L;
   const Net &actor = ag->net[ACTOR];
   const Net &c = ag->net[CRITIC1];
@@ -301,7 +324,7 @@ void actor_phase_fb(gcrl_agent *ag, int B, PhaseState *ps, cudaStream_t st) {
   h.pW = nullptr; h.pB = nullptr;                     // critic weight grads are discarded (:1293-1294)
   h.metric_partials = ag->metric_partials;
   h.M = B; h.K = ag->H;
-  ps->metric_splits = launch_head_bwd(h, kMaxSplits, st);
+  const int actor_metric_splits = launch_head_bwd(h, kMaxSplits, st);
   int cur;
   int dummy[8];
   backward_hidden(ag, c, ag->spi, ag->ldc, K0, ag->acts_c1, B, 0, false, dummy, &cur, st);
@@ -317,12 +340,15 @@ void actor_phase_fb(gcrl_agent *ag, int B, PhaseState *ps, cudaStream_t st) {
   ha.M = B; ha.K = ag->H;
   ps->head_splits = launch_head_bwd(ha, kMaxSplits, st);
   backward_hidden(ag, actor, ag->spi, ag->ldc, D, ag->acts_actor, B, 0, true, ps->splits, &cur, st);
+  // the actor-loss metric partials (critic head pass) are still intact: the actor head pass has mode 2
+  reduce_grads(ag, ag->net[ACTOR], ps->splits, ps->head_splits, false, S_ALOSS, -1, -1, actor_metric_splits, B,
+               st);
 }
 
-void actor_phase_step(gcrl_agent *ag, int B, PhaseState *ps, cudaStream_t st) {
-  // the actor-loss metric partials were written before the actor head pass reused nothing of them
-  reduce_and_step(ag, ag->net[ACTOR], ps->splits, ps->head_splits, 1, ag->cfg.grad_clip, S_ALOSS, -1, -1,
-                  S_AGRAD, ps->metric_splits, B, ag->net[T_ACTOR].p, ag->td3, st);
+void actor_phase_step(gcrl_agent *ag, bool rereduce, cudaStream_t st) {
+  Net &a = ag->net[ACTOR];
+  if (rereduce) reduce_grads(ag, a, nullptr, 0, true, -1, -1, -1, 0, 1, st);
+  adam_step(ag, a, 1, ag->cfg.grad_clip, S_AGRAD, ag->net[T_ACTOR].p, ag->td3, st);
 }
 
 void write_scalars(gcrl_agent *ag, double lr_c, double lr_a, bool actor_steps, cudaStream_t st) {
@@ -345,42 +371,80 @@ void write_scalars(gcrl_agent *ag, double lr_c, double lr_a, bool actor_steps, c
   ag->scal_stage.release(slot, st);
 }
 
-void run_update_body(gcrl_agent *ag, int B, const float *noise, int flags, cudaStream_t st) {
-  PhaseState ps[2], pa;
-  critic_phase_fb(ag, B, noise, ps, st);
-  critic_phase_step(ag, B, flags, ps, st);
-  if (flags & 1) {
-    actor_phase_fb(ag, B, &pa, st);
-    actor_phase_step(ag, B, &pa, st);
+// phase masks: bit0 critic grads, bit1 critic step, bit2 actor grads, bit3 actor step.
+// A single-GPU update runs all four back to back (mask 15); the data-parallel path runs them one
+// at a time with the caller's gradient all-reduce in between (steps then re-reduce).
+enum : int { PH_CGRAD = 1, PH_CSTEP = 2, PH_AGRAD = 4, PH_ASTEP = 8, PH_ALL = 15 };
+
+void run_update_body(gcrl_agent *ag, int B, const float *noise, int flags, int mask, cudaStream_t st) {
+  const bool dp = mask != PH_ALL;
+  if (mask & PH_CGRAD) {
+    critic_phase_grads(ag, B, noise, st);
+    if (ag->td3 && dp) critic2_phase_grads(ag, B, st);
   }
+  if (mask & PH_CSTEP) {
+    ddpg_actor_target_polyak(ag, flags, st);
+    critic_phase_step(ag, 0, flags, dp, st);
+    if (ag->td3) {
+      if (!dp) critic2_phase_grads(ag, B, st);
+      critic_phase_step(ag, 1, flags, dp, st);
+    }
+  }
+  if ((mask & PH_AGRAD) && (flags & 1)) actor_phase_grads(ag, B, st);
+  if ((mask & PH_ASTEP) && (flags & 1)) actor_phase_step(ag, dp, st);
 }
 
-// Replay (or capture on first use) the update graph for (B, flags).  TD3 noise pointers vary per
-// call, so the noise is first copied into an internal buffer by the caller.
-void run_update(gcrl_agent *ag, int B, const float *noise, int flags, cudaStream_t st) {
+// Replay (or capture on first use) the graph of (B, flags, phase mask).  TD3 noise pointers vary
+// per call, so the noise is first copied into an internal buffer by the caller.
+void run_update(gcrl_agent *ag, int B, const float *noise, int flags, int mask, cudaStream_t st) {
   if (!ag->use_graphs) {
-    run_update_body(ag, B, noise, flags, st);
+    run_update_body(ag, B, noise, flags, mask, st);
     return;
   }
-  const auto key = std::make_tuple(int64_t(B), flags, 0);
+  const auto key = std::make_tuple(int64_t(B), flags, mask);
   auto it = ag->graphs.find(key);
   if (it == ag->graphs.end()) {
     cudaGraph_t graph = nullptr;
+    const uint64_t before = launch_counter();
     GCRL_CUDA(cudaStreamBeginCapture(ag->cap_stream, cudaStreamCaptureModeThreadLocal));
     try {
-      run_update_body(ag, B, noise, flags, ag->cap_stream);
+      run_update_body(ag, B, noise, flags, mask, ag->cap_stream);
     } catch (...) {
       cudaStreamEndCapture(ag->cap_stream, &graph);
       if (graph) cudaGraphDestroy(graph);
       throw;
     }
     GCRL_CUDA(cudaStreamEndCapture(ag->cap_stream, &graph));
+    const uint64_t kernels = launch_counter() - before;   // recorded, not executed, by the capture
+    count_launch(uint64_t(0) - kernels);
     cudaGraphExec_t exec = nullptr;
     GCRL_CUDA(cudaGraphInstantiate(&exec, graph, 0));
     GCRL_CUDA(cudaGraphDestroy(graph));
-    it = ag->graphs.emplace(key, exec).first;
+    it = ag->graphs.emplace(key, gcrl_agent::GraphRec{exec, kernels}).first;
   }
-  GCRL_CUDA(cudaGraphLaunch(it->second, st));
+  GCRL_CUDA(cudaGraphLaunch(it->second.exec, st));
+  count_launch(it->second.kernels);
+}
+
+// Stage one batch (sampled from `buf`, or the caller's dense device batch) into the operand rows.
+void ingest(gcrl_agent *ag, gcrl_her *buf, int64_t B, const int64_t *idx_host, const float *s, const float *a,
+            const float *r, const float *ns, const float *d, const float *noise_dev, const float **noise_out,
+            cudaStream_t st) {
+  if (buf != nullptr) {
+    GCRL_REQUIRE(her_state_dim(buf) == ag->D && her_act_dim(buf) == ag->A, "buffer / agent shape mismatch");
+    GCRL_REQUIRE(her_device(buf) == ag->device, "buffer and agent live on different devices");
+    her_sample_into(buf, B, idx_host, ag->bs, ag->ba, ag->br0, ag->bns, ag->bd0, nullptr, st);
+    s = ag->bs; a = ag->ba; r = ag->br0; ns = ag->bns; d = ag->bd0;
+  } else {
+    GCRL_REQUIRE(s && a && r && ns && d, "NULL batch pointer");
+  }
+  GCRL_REQUIRE(!ag->td3 || noise_dev != nullptr, "TD3 update needs the [B, A] standard-normal noise tensor");
+  launch_ingest_batch(s, a, r, ns, d, ag->D, ag->A, int(B), ag->sa, ag->nsa, ag->spi, ag->ldc, ag->br, ag->bd, st);
+  *noise_out = nullptr;
+  if (ag->td3) {  // stable address for the captured graph
+    GCRL_CUDA(cudaMemcpyAsync(ag->noise, noise_dev, size_t(B) * ag->A * 4, cudaMemcpyDeviceToDevice, st));
+    *noise_out = ag->noise;
+  }
 }
 
 void check_batch(const gcrl_agent *ag, int64_t B) {
@@ -459,6 +523,7 @@ int gcrl_agent_create(gcrl_agent **out, int device, const gcrl_agent_config *cfg
     for (float **p : {&ag->q1, &ag->q2, &ag->qt1, &ag->qt2, &ag->yv, &ag->br, &ag->bd, &ag->br0, &ag->bd0})
       *p = dev_alloc<float>(size_t(mb));
     ag->dz_act = dev_alloc<float>(size_t(mb) * 4);
+    ag->noise = dev_alloc<float>(size_t(mb) * 4);
     ag->bs = dev_alloc<float>(size_t(mb) * D);
     ag->bns = dev_alloc<float>(size_t(mb) * D);
     ag->ba = dev_alloc<float>(size_t(mb) * A);
@@ -487,13 +552,13 @@ int gcrl_agent_destroy(gcrl_agent *ag) {
   if (ag == nullptr) return GCRL_OK;
   cudaSetDevice(ag->device);
   cudaDeviceSynchronize();
-  for (auto &kv : ag->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto &kv : ag->graphs) cudaGraphExecDestroy(kv.second.exec);
   for (int i = 0; i < NUM_NETS; ++i)
     if (ag->has[i]) ag->net[i].destroy();
   ag->acts_actor.destroy(); ag->acts_c1.destroy(); ag->acts_c2.destroy(); ag->acts_tgt.destroy();
   for (float *p : {ag->dz[0], ag->dz[1], ag->sa, ag->nsa, ag->spi, ag->q1, ag->q2, ag->qt1, ag->qt2, ag->yv,
                    ag->dz_act, ag->br, ag->bd, ag->bs, ag->ba, ag->bns, ag->br0, ag->bd0, ag->partials,
-                   ag->metric_partials, ag->sumsq, ag->metrics, ag->d_io})
+                   ag->metric_partials, ag->sumsq, ag->metrics, ag->d_io, ag->noise})
     if (p) cudaFree(p);
   cudaFree(ag->d_scalars);
   if (ag->cap_stream) cudaStreamDestroy(ag->cap_stream);
@@ -585,19 +650,12 @@ int gcrl_agent_update_batch(gcrl_agent *ag, int64_t B, const float *s_dev, const
                             float *metrics_host, void *stream) {
   GCRL_API_BEGIN
   check_batch(ag, B);
-  GCRL_REQUIRE(s_dev && a_dev && r_dev && ns_dev && d_dev, "NULL batch pointer");
-  GCRL_REQUIRE(!ag->td3 || noise_dev != nullptr, "TD3 update needs noise");
   GCRL_CUDA(cudaSetDevice(ag->device));
   cudaStream_t st = as_stream(stream);
-  launch_ingest_batch(s_dev, a_dev, r_dev, ns_dev, d_dev, ag->D, ag->A, int(B), ag->sa, ag->nsa, ag->spi,
-                      ag->ldc, ag->br, ag->bd, st);
   const float *noise = nullptr;
-  if (ag->td3) {  // stable address for the captured graph
-    GCRL_CUDA(cudaMemcpyAsync(ag->dz_act, noise_dev, size_t(B) * ag->A * 4, cudaMemcpyDeviceToDevice, st));
-    noise = ag->dz_act;
-  }
+  ingest(ag, nullptr, B, nullptr, s_dev, a_dev, r_dev, ns_dev, d_dev, noise_dev, &noise, st);
   write_scalars(ag, lr_critic, lr_actor, (flags & 1) != 0, st);
-  run_update(ag, int(B), noise, flags, st);
+  run_update(ag, int(B), noise, flags, PH_ALL, st);
   finish_metrics(ag, metrics_host, st);
   GCRL_API_END
 }
@@ -608,21 +666,12 @@ int gcrl_agent_update_from_buffer(gcrl_agent *ag, gcrl_her *buf, int64_t B, cons
   GCRL_API_BEGIN
   check_batch(ag, B);
   GCRL_REQUIRE(buf != nullptr, "buffer handle is NULL");
-  GCRL_REQUIRE(her_state_dim(buf) == ag->D && her_act_dim(buf) == ag->A, "buffer / agent shape mismatch");
-  GCRL_REQUIRE(her_device(buf) == ag->device, "buffer and agent live on different devices");
-  GCRL_REQUIRE(!ag->td3 || noise_dev != nullptr, "TD3 update needs noise");
   GCRL_CUDA(cudaSetDevice(ag->device));
   cudaStream_t st = as_stream(stream);
-  her_sample_into(buf, B, idx_host, ag->bs, ag->ba, ag->br0, ag->bns, ag->bd0, nullptr, st);
-  launch_ingest_batch(ag->bs, ag->ba, ag->br0, ag->bns, ag->bd0, ag->D, ag->A, int(B), ag->sa, ag->nsa,
-                      ag->spi, ag->ldc, ag->br, ag->bd, st);
   const float *noise = nullptr;
-  if (ag->td3) {
-    GCRL_CUDA(cudaMemcpyAsync(ag->dz_act, noise_dev, size_t(B) * ag->A * 4, cudaMemcpyDeviceToDevice, st));
-    noise = ag->dz_act;
-  }
+  ingest(ag, buf, B, idx_host, nullptr, nullptr, nullptr, nullptr, nullptr, noise_dev, &noise, st);
   write_scalars(ag, lr_critic, lr_actor, (flags & 1) != 0, st);
-  run_update(ag, int(B), noise, flags, st);
+  run_update(ag, int(B), noise, flags, PH_ALL, st);
   finish_metrics(ag, metrics_host, st);
   GCRL_API_END
 }
@@ -678,13 +727,26 @@ int gcrl_agent_q(gcrl_agent *ag, int64_t n, const float *obs_host, const float *
 }
 
 // ---- data-parallel phase hooks ---------------------------------------------------------------------
-int gcrl_agent_update_phase(gcrl_agent *ag, int phase, int64_t B, const float *s_dev, const float *a_dev,
-                            const float *r_dev, const float *ns_dev, const float *d_dev,
-                            const float *noise_dev, double lr, int flags, void *stream) {
+int gcrl_agent_update_phase(gcrl_agent *ag, int phase, gcrl_her *buf, int64_t B, const int64_t *idx_host,
+                            const float *s_dev, const float *a_dev, const float *r_dev, const float *ns_dev,
+                            const float *d_dev, const float *noise_dev, double lr_critic, double lr_actor,
+                            int flags, void *stream) {
   GCRL_API_BEGIN
-  (void)ag; (void)phase; (void)B; (void)s_dev; (void)a_dev; (void)r_dev; (void)ns_dev; (void)d_dev;
-  (void)noise_dev; (void)lr; (void)flags; (void)stream;
-  throw Error(GCRL_ERR_INVALID, "gcrl_agent_update_phase: data-parallel phases not built yet");
+  check_batch(ag, B);
+  GCRL_REQUIRE(phase >= 0 && phase <= 3, "phase must be 0..3");
+  GCRL_CUDA(cudaSetDevice(ag->device));
+  cudaStream_t st = as_stream(stream);
+  if (phase == 0) {
+    const float *noise = nullptr;
+    ingest(ag, buf, B, idx_host, s_dev, a_dev, r_dev, ns_dev, d_dev, noise_dev, &noise, st);
+    write_scalars(ag, lr_critic, lr_actor, (flags & 1) != 0, st);
+    ag->dp_B = int(B);
+    ag->dp_flags = flags;
+    run_update(ag, int(B), noise, flags, PH_CGRAD, st);
+  } else {
+    GCRL_REQUIRE(ag->dp_B == int(B) && ag->dp_flags == flags, "phase 1..3 must follow phase 0 of the same update");
+    run_update(ag, int(B), ag->td3 ? ag->noise : nullptr, flags, phase == 1 ? PH_CSTEP : (phase == 2 ? PH_AGRAD : PH_ASTEP), st);
+  }
   GCRL_API_END
 }
 

@@ -1,6 +1,7 @@
 // Error plumbing, pinned staging ring, misc C-ABI entry points.
 #include "common.cuh"
 
+#include <atomic>
 #include <cstring>
 
 namespace gcrl {
@@ -19,6 +20,10 @@ int sm_count() {
   }
   return cached;
 }
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+uint64_t launch_counter() { return g_launches.load(std::memory_order_relaxed); }
 
 void PinnedRing::init(size_t bytes) {
   slot_bytes = (bytes + 255) & ~size_t(255);
@@ -66,6 +71,8 @@ extern "C" {
 int gcrl_abi_version(void) { return GCRL_ABI_VERSION; }
 
 const char *gcrl_last_error(void) { return gcrl::g_last_error.c_str(); }
+
+uint64_t gcrl_kernel_launches(void) { return gcrl::launch_counter(); }
 
 int gcrl_device_count(int *count) {
   GCRL_API_BEGIN

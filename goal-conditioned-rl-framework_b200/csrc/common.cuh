@@ -24,6 +24,13 @@ void set_last_error(const std::string &m);
       throw ::gcrl::Error(GCRL_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
   } while (0)
 
+// after every kernel launch: account for it and surface launch-configuration errors
+#define GCRL_LAUNCHED()                   \
+  do {                                    \
+    ::gcrl::count_launch();               \
+    GCRL_CUDA(cudaGetLastError());        \
+  } while (0)
+
 #define GCRL_REQUIRE(cond, msg)                                          \
   do {                                                                   \
     if (!(cond)) throw ::gcrl::Error(GCRL_ERR_INVALID, std::string(msg)); \
@@ -46,6 +53,11 @@ inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s
 
 // number of SMs of the current device (148 on B200), cached per process
 int sm_count();
+
+// Kernel-launch accounting (gcrl_kernel_launches): every launch site calls count_launch();
+// while a stream capture is recording, launches are tallied per graph and credited on replay.
+void count_launch(uint64_t n = 1);
+uint64_t launch_counter();
 
 template <typename T>
 T *dev_alloc(size_t n) {

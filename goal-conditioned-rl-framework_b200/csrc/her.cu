@@ -326,7 +326,7 @@ static void her_launch_sample(gcrl_her *h, int64_t B, const int64_t *idx_dev, fl
   else
     her_sample_kernel<false><<<blocks, kSampleThreads, h->smem_bytes, st>>>(h->g, B, idx_dev, s, a,
                                                                           r, ns, d, idx_out);
-  GCRL_CUDA(cudaGetLastError());
+  GCRL_LAUNCHED();
 }
 
 static const int64_t *her_stage_indices(gcrl_her *h, int64_t B, const int64_t *idx_host,
@@ -530,7 +530,7 @@ int gcrl_her_push_episode(gcrl_her *h, int T, const float *s, const float *a, co
   const int work = T * (g.row_f / 4);
   const int blocks = std::max(1, std::min(32, (work + 255) / 256));
   her_commit_kernel<<<blocks, 256, 0, st>>>(g, h->d_stage[slot]);
-  GCRL_CUDA(cudaGetLastError());
+  GCRL_LAUNCHED();
   // ---- commit host counters ----
   h->live.erase(h->live.begin(), h->live.begin() + drop);
   h->live.emplace_back(new_total, T);

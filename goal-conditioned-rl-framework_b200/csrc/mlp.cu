@@ -243,7 +243,7 @@ static void launch_gemm(const GemmParams &p, int splits, cudaStream_t st) {
     dim3 grid((p.N + 31) / 32, (p.M + 31) / 32, splits);
     gemm_kernel<32, 32, 4, 4, OP><<<grid, 64, 0, st>>>(p);
   }
-  GCRL_CUDA(cudaGetLastError());
+  GCRL_LAUNCHED();
 }
 
 void launch_linear_fwd(const float *X, int ldx, const float *W, int ldw, const float *bias, float *Y,
@@ -338,7 +338,7 @@ void launch_head_fwd(const float *Hact, int ldh, const float *W, int ldw, const 
     case 4: head_fwd_kernel<4><<<blocks, 256, 0, st>>>(Hact, ldh, W, ldw, bias, out, ldo, col0, M, K, tanh_out); break;
     default: throw Error(GCRL_ERR_INVALID, "head width must be 1..4");
   }
-  GCRL_CUDA(cudaGetLastError());
+  GCRL_LAUNCHED();
 }
 
 // ---- loss + backward through the skinny output layer ------------------------------------------
@@ -451,7 +451,7 @@ int launch_head_bwd(const HeadBwdArgs &a, int max_splits, cudaStream_t st) {
     case 4: head_bwd_kernel<4><<<slabs, 256, 0, st>>>(a, rows); break;
     default: throw Error(GCRL_ERR_INVALID, "head width must be 1..4");
   }
-  GCRL_CUDA(cudaGetLastError());
+  GCRL_LAUNCHED();
   return slabs;
 }
 
@@ -493,7 +493,7 @@ void launch_action_grad(const float *dZ1, int lddz, const float *W1, int ldw, co
   GCRL_REQUIRE(nact >= 1 && nact <= 4, "act_dim must be 1..4");
   const int blocks = std::max(1, std::min((M + 7) / 8, sm_count() * 8));
   action_grad_kernel<<<blocks, 256, 0, st>>>(dZ1, lddz, W1, ldw, sa, ldsa, col0, dz_out, M, N, nact);
-  GCRL_CUDA(cudaGetLastError());
+  GCRL_LAUNCHED();
 }
 
 // ---- batch ingest: all packed operand rows in one launch ---------------------------------------
@@ -532,7 +532,7 @@ void launch_ingest_batch(const float *s, const float *a, const float *r, const f
   const int blocks = std::min((total + 255) / 256, sm_count() * 8);
   ingest_batch_kernel<<<blocks, 256, 0, st>>>(s, a, r, ns, d, D, A, M, sa, nsa, spi, ldc, r_out, d_out,
                                              FastDiv(uint32_t(ldc)));
-  GCRL_CUDA(cudaGetLastError());
+  GCRL_LAUNCHED();
 }
 
 __global__ void __launch_bounds__(256)
@@ -554,7 +554,7 @@ void launch_td3_smooth(float *x, int ldx, int col0, const float *noise, int A, i
   if (total == 0) return;
   td3_smooth_kernel<<<std::min((total + 255) / 256, sm_count() * 8), 256, 0, st>>>(x, ldx, col0, noise, A,
                                                                                   M, sigma, clampv);
-  GCRL_CUDA(cudaGetLastError());
+  GCRL_LAUNCHED();
 }
 
 // ---- [s | a | 0] row packing ------------------------------------------------------------------
@@ -578,7 +578,7 @@ void launch_pack_rows(const float *s, int D, const float *a, int A, float *out, 
   if (total == 0) return;
   const int blocks = int(std::min<int64_t>((total + 255) / 256, int64_t(sm_count()) * 8));
   pack_rows_kernel<<<blocks, 256, 0, st>>>(s, D, a, A, out, ldo, total, FastDiv(uint32_t(ldo)));
-  GCRL_CUDA(cudaGetLastError());
+  GCRL_LAUNCHED();
 }
 
 }  // namespace gcrl

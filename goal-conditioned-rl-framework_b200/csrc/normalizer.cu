@@ -134,11 +134,11 @@ static void norm_update_device(gcrl_norm *h, const void *x_dev, int64_t n, int i
   else
     norm_partial_kernel<float><<<nblocks, kNormWarps * 32, 0, st>>>(
         static_cast<const float *>(x_dev), n, h->dim, rows_per_block, h->d_partials);
-  GCRL_CUDA(cudaGetLastError());
+  GCRL_LAUNCHED();
   const int threads = 128;
   GCRL_REQUIRE(h->dim <= threads, "normaliser dim > 128 not supported");
   norm_merge_kernel<<<1, threads, 0, st>>>(h->d_partials, nblocks, h->dim, h->st);
-  GCRL_CUDA(cudaGetLastError());
+  GCRL_LAUNCHED();
 }
 
 static const void *norm_stage_in(gcrl_norm *h, const void *x_host, int64_t n, int is_f64,
@@ -171,7 +171,7 @@ static void norm_apply_launch(gcrl_norm *h, const void *x_dev, int64_t n, int is
   else
     norm_apply_kernel<float, TO><<<blocks, 256, 0, st>>>(static_cast<const float *>(x_dev), n,
                                                         h->dim, h->st, h->clip, out, stride, col0, dd);
-  GCRL_CUDA(cudaGetLastError());
+  GCRL_LAUNCHED();
 }
 
 extern "C" {

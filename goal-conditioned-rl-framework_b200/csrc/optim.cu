@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kOptThreads) reduce_grads_kernel(ReduceArgs a)
 
 void launch_reduce_grads(const ReduceArgs &a, cudaStream_t st) {
   reduce_grads_kernel<<<reduce_grid(a.total), kOptThreads, 0, st>>>(a);
-  GCRL_CUDA(cudaGetLastError());
+  GCRL_LAUNCHED();
 }
 
 // torch.optim.Adam(W) single-tensor semantics (betas 0.9/0.999, eps 1e-8):
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kOptThreads) adam_kernel(AdamArgs a) {
 
 void launch_adam(const AdamArgs &a, cudaStream_t st) {
   adam_kernel<<<reduce_grid(a.n), kOptThreads, 0, st>>>(a);
-  GCRL_CUDA(cudaGetLastError());
+  GCRL_LAUNCHED();
 }
 
 __global__ void __launch_bounds__(kOptThreads)
@@ -130,7 +130,7 @@ polyak_kernel(float *__restrict__ target, const float *__restrict__ src, int n, 
 void launch_polyak(float *target, const float *src, int n, float tau, float one_minus_tau,
                    cudaStream_t st) {
   polyak_kernel<<<reduce_grid(n), kOptThreads, 0, st>>>(target, src, n, tau, one_minus_tau);
-  GCRL_CUDA(cudaGetLastError());
+  GCRL_LAUNCHED();
 }
 
 }  // namespace gcrl

@@ -38,6 +38,7 @@ SIGNATURES = {
     "gcrl_abi_version": (C.c_int, []),
     "gcrl_last_error": (C.c_char_p, []),
     "gcrl_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "gcrl_kernel_launches": (c_u64, []),
     # HER buffer
     "gcrl_her_create": (C.c_int, [pp, C.c_int, c_i64, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, c_u64]),
     "gcrl_her_destroy": (C.c_int, [vp]),
@@ -72,7 +73,8 @@ SIGNATURES = {
     "gcrl_agent_read_metrics": (C.c_int, [vp, vp, vp]),
     "gcrl_agent_act": (C.c_int, [vp, c_i64, vp, vp, vp]),
     "gcrl_agent_q": (C.c_int, [vp, c_i64, vp, vp, vp, vp]),
-    "gcrl_agent_update_phase": (C.c_int, [vp, C.c_int, c_i64, vp, vp, vp, vp, vp, vp, c_f64, C.c_int, vp]),
+    "gcrl_agent_update_phase": (C.c_int, [vp, C.c_int, vp, c_i64, vp, vp, vp, vp, vp, vp, vp, c_f64, c_f64,
+                                         C.c_int, vp]),
     "gcrl_agent_grad_buffer": (C.c_int, [vp, C.c_int, pp, C.POINTER(c_i64)]),
     "gcrl_agent_metrics_buffer": (C.c_int, [vp, pp]),
 }

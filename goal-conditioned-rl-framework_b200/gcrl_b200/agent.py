@@ -255,6 +255,35 @@ class _AgentBase:
     def _flags(self, step):
         raise NotImplementedError
 
+    # -- data parallel (one process per GPU) -------------------------------------
+    _dp = None
+
+    def enable_data_parallel(self, process_group=None, allreduce_mean=None):
+        """Average gradients over the ranks of ``process_group`` (torch.distributed, NCCL over
+        NVLink) between the backward and the optimiser phases of every update.  Each rank keeps
+        its own episode shard of the buffer and samples its local minibatch; weights, optimiser
+        state and targets stay replicated because every rank applies the same averaged
+        gradient.  ``allreduce_mean(tensor)`` overrides the collective (tests)."""
+        from .parallel import GradAverager
+        self._dp = GradAverager(self, process_group, allreduce_mean)
+        return self._dp
+
+    def grad_tensor(self, net):
+        """The flat fp32 gradient buffer of a trainable network as a torch tensor (zero copy)."""
+        from .parallel import device_tensor
+        ptr, n = vp(), C.c_int64()
+        check(lib.gcrl_agent_grad_buffer(self._h, net, C.byref(ptr), C.byref(n)))
+        return device_tensor(ptr.value, n.value, self.device_index)
+
+    def metrics_tensor(self):
+        from .parallel import device_tensor
+        ptr = vp()
+        check(lib.gcrl_agent_metrics_buffer(self._h, C.byref(ptr)))
+        return device_tensor(ptr.value, 8, self.device_index)
+
+    def _trainable_critics(self):
+        return (NET_CRITIC,)
+
     def _run_update(self, step, batch=None, indices=None, noise=None, sync=True):
         """One update; ``batch`` = 5 device tensors (explicit batch) or None (sample from the
         buffer; ``indices`` optional host positions).  Returns the raw 8-float metric vector
@@ -263,22 +292,37 @@ class _AgentBase:
         lr_c, lr_a = self.critic_scheduler.lr, self.actor_scheduler.lr
         mptr = C.cast(self._metrics, vp) if sync else None
         nptr = vp(noise.data_ptr()) if noise is not None else None
+        iptr = None
         if batch is None:
             B = self.batch_size
             assert len(self.buffer) >= B, "[ERROR] Not enough in buffer to sample"
-            iptr = None
             if indices is None and self.index_source == "host":
                 indices = random.sample(range(len(self.buffer)), B)
             if indices is not None:
                 indices = np.ascontiguousarray(indices, np.int64)
                 iptr = np_ptr(indices)
-            check(lib.gcrl_agent_update_from_buffer(self._h, self.buffer.handle, B, iptr, nptr,
-                                                    lr_c, lr_a, flags, mptr, self._stream()))
+            bufh, ptrs = self.buffer.handle, (None,) * 5
         else:
-            s, a, r, ns, d = batch
-            check(lib.gcrl_agent_update_batch(self._h, s.shape[0], vp(s.data_ptr()), vp(a.data_ptr()),
-                                              vp(r.data_ptr()), vp(ns.data_ptr()), vp(d.data_ptr()),
-                                              nptr, lr_c, lr_a, flags, mptr, self._stream()))
+            B = batch[0].shape[0]
+            bufh, ptrs = None, tuple(vp(t.data_ptr()) for t in batch)      # s, a, r, ns, d
+        if self._dp is not None:
+            st = self._stream()
+            for phase in range(4):
+                check(lib.gcrl_agent_update_phase(self._h, phase, bufh, B, iptr, *ptrs, nptr, lr_c, lr_a,
+                                                  flags, st))
+                if phase == 0:
+                    self._dp.average(self._trainable_critics())
+                elif phase == 2 and (flags & 1):
+                    self._dp.average((NET_ACTOR,))
+            if sync:
+                self._dp.average_metrics()
+                check(lib.gcrl_agent_read_metrics(self._h, mptr, st))
+        elif batch is None:
+            check(lib.gcrl_agent_update_from_buffer(self._h, bufh, B, iptr, nptr, lr_c, lr_a, flags, mptr,
+                                                    self._stream()))
+        else:
+            check(lib.gcrl_agent_update_batch(self._h, B, *ptrs, nptr, lr_c, lr_a, flags, mptr,
+                                              self._stream()))
         self.critic_scheduler.step()
         if flags & 1:
             self.actor_scheduler.step()
@@ -384,6 +428,9 @@ class TD3Agent(_AgentBase):
 
     def update_target_network(self):
         self.hard_update()
+
+    def _trainable_critics(self):
+        return (NET_CRITIC, NET_CRITIC2)
 
     def _flags(self, step):
         return 1 if step % self.ac_update_freq == 0 else 0

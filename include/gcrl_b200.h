@@ -38,6 +38,9 @@ extern "C" {
 int gcrl_abi_version(void);
 const char *gcrl_last_error(void);
 int gcrl_device_count(int *count);
+/* Number of CUDA kernels this library has launched in the calling process so far (graph
+ * replays count their kernel nodes).  Diagnostics / bench.py's "gpu_launches". */
+uint64_t gcrl_kernel_launches(void);
 
 /* ------------------------------------------------------------------------------------
  * HER replay buffer -- replaces HERBuffer, src/buffer.py:92-179
@@ -190,18 +193,27 @@ int gcrl_agent_act(gcrl_agent *h, int64_t n, const float *obs_host, float *act_h
 int gcrl_agent_q(gcrl_agent *h, int64_t n, const float *obs_host, const float *act_host,
                  float *q_host, void *stream);
 
-/* Data-parallel hooks (one process per GPU; the caller all-reduces between phases):
- * phase 0: critic forward/backward -> flat critic gradient (sum over the local batch,
- *          already divided by B_local);   phase 1: clip + Adam (+ Polyak per flags);
- * phase 2: actor forward/backward -> flat actor gradient;   phase 3: clip + Adam.
- * gcrl_agent_grad_buffer exposes the flat fp32 gradient of a network (device ptr +
- * element count) so it can be handed to NCCL. */
-int gcrl_agent_update_phase(gcrl_agent *h, int phase, int64_t B, const float *s_dev,
-                            const float *a_dev, const float *r_dev, const float *ns_dev,
-                            const float *d_dev, const float *noise_dev, double lr, int flags,
+/* Data-parallel hooks (one process per GPU, buffer sharded by episode, weights replicated).
+ * The update above is cut at the two points where gradients are averaged across ranks:
+ *   phase 0: ingest the local batch (sampled from `buf` at idx_host / on-device draw when buf is
+ *            non-NULL, else the dense device batch) -> target + critic forward, loss, backward ->
+ *            flat critic gradient(s) = mean over the LOCAL batch, local metrics;
+ *   [caller: all-reduce AVG of gcrl_agent_grad_buffer(critic) (and critic_2 for TD3)]
+ *   phase 1: global-norm clip on the averaged gradient + Adam (+ Polyak per flags);
+ *   phase 2: actor forward through the stepped critic, backward -> flat actor gradient;
+ *   [caller: all-reduce AVG of gcrl_agent_grad_buffer(actor)]
+ *   phase 3: clip + Adam (actor).
+ * Phases 2/3 are no-ops when flags bit0 is clear.  With world size 1 and no all-reduce the four
+ * phases reproduce gcrl_agent_update_* bit for bit. */
+int gcrl_agent_update_phase(gcrl_agent *h, int phase, gcrl_her *buf, int64_t B,
+                            const int64_t *idx_host, const float *s_dev, const float *a_dev,
+                            const float *r_dev, const float *ns_dev, const float *d_dev,
+                            const float *noise_dev, double lr_critic, double lr_actor, int flags,
                             void *stream);
+/* flat fp32 gradient of a trainable network: device pointer + element count (for NCCL) */
 int gcrl_agent_grad_buffer(gcrl_agent *h, int net, float **grad_dev, int64_t *count);
-/* flat metric partial sums for cross-rank averaging: device float[8] */
+/* device float[8] holding the metrics of the most recent update (averaged across ranks by the
+ * caller when a data-parallel run wants global losses) */
 int gcrl_agent_metrics_buffer(gcrl_agent *h, float **metrics_dev);
 
 #ifdef __cplusplus

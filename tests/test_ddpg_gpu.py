@@ -1,0 +1,186 @@
+"""GPU parity: the DDPG update (csrc/agent.cu, mlp.cu, optim.cu) through the C ABI versus
+fixtures dumped from the unmodified reference ``DDPG.update`` (src/agent.py:1378-1404) and
+versus the NumPy oracle.
+
+Tolerance (north_star: "within a stated fp32 tolerance (e.g. rel 1e-5)"):
+  metrics (losses, td, q, grad norms)   rel 2e-5 + abs 1e-6
+  Bellman targets y, Q                  rel 1e-5 (norm-wise) per tensor
+  post-update weights                   tests.helpers.weights_close (rel 1e-5 norm-wise + Adam
+                                        eps-regime allowance, documented there)
+"""
+import types
+
+import numpy as np
+import pytest
+
+from oracle import ddpg as OD
+from tests.helpers import DDPG_CASES, ddpg_params_from_golden, load, rel_err, weights_close
+
+pytestmark = pytest.mark.gpu
+
+
+def make_config(g=None, **over):
+    base = dict(hidden_dim=64, layer_count=3, actor_lr=1e-3, actor_lr_min=1e-3, ac_scheduler_steps=1,
+                critic_lr=1e-3, critic_lr_min=1e-3, cr_scheduler_steps=1, buffer_type="HER",
+                max_len=100000, alpha=1.0, batch_size=64, gamma=0.98, ac_update_freq=1, noise_std=0.2,
+                noise_clamp=0.5, policy_noise=0.2, grad_clip=10.0, beta=1.0, beta_end=1, k_future=4,
+                max_eps_len=50, tau=0.05)
+    if g is not None:
+        D, A, H, L, B, seed, ac_T, cr_T, freq = (int(x) for x in g["meta"])
+        gamma, tau, clip, alr, clr, alr_min, clr_min = (float(x) for x in g["hp"])
+        base.update(hidden_dim=H, layer_count=L, batch_size=B, gamma=gamma, tau=tau, grad_clip=clip,
+                    actor_lr=alr, critic_lr=clr, actor_lr_min=alr_min, critic_lr_min=clr_min,
+                    ac_scheduler_steps=ac_T, cr_scheduler_steps=cr_T, ac_update_freq=freq)
+    base.update(over)
+    return types.SimpleNamespace(**base)
+
+
+def make_agent_from_golden(g):
+    from gcrl_b200 import DDPG
+    from gcrl_b200.agent import NET_ACTOR, NET_CRITIC
+    D, A, H, L, B, seed = (int(x) for x in g["meta"][:6])
+    ag = DDPG(D, A, make_config(g), None, 1, 40)
+    rng = np.random.default_rng(seed)
+    actor0 = OD.init_mlp(rng, D, H, A, L)
+    critic0 = OD.init_mlp(rng, D + A, H, 1, L)
+    ag._set_layers(NET_ACTOR, actor0)
+    ag._set_layers(NET_CRITIC, critic0)
+    ag.update_target_network()
+    return ag, rng
+
+
+def batch_to_device(g, si):
+    import torch
+    return tuple(torch.from_numpy(g[f"s{si}_batch_{k}"]).cuda() for k in ("s", "a", "r", "ns", "d"))
+
+
+@pytest.mark.parametrize("case", DDPG_CASES)
+def test_update_matches_reference_fixture(case):
+    g = load("ddpg_" + case)
+    ag, _ = make_agent_from_golden(g)
+    lr = max(float(g["hp"][3]), float(g["hp"][4]))
+    for si, step in enumerate(g["steps"]):
+        info = ag.update(int(step), batch=batch_to_device(g, si))
+        ref = g[f"s{si}_info"]
+        assert len(info) == len(ref), "tuple arity (6 with the actor step, else 4)"
+        np.testing.assert_allclose(np.array([float(x) for x in info]), ref, rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose([ag.critic_scheduler.lr, ag.actor_scheduler.lr], g[f"s{si}_lr"],
+                                   rtol=1e-12)
+        if f"s{si}_actor.base_net.0.weight" in g.files:
+            for tag, net in (("actor", ag.actor), ("critic", ag.critic),
+                             ("target_actor", ag.target_actor), ("target_critic", ag.target_critic)):
+                for (w, b), (rw, rb) in zip(net.layers(), ddpg_params_from_golden(g, si, tag)):
+                    assert weights_close(w, rw, lr, si + 1), (case, si, tag, rel_err(w, rw))
+                    assert weights_close(b, rb, lr, si + 1), (case, si, tag, rel_err(b, rb))
+
+
+@pytest.mark.parametrize("B,H,L,D,A", [(1, 64, 3, 10, 3), (33, 100, 2, 22, 3), (1000, 256, 3, 23, 4),
+                                       (4096, 512, 3, 22, 3), (777, 64, 1, 7, 1)])
+def test_update_matches_oracle_odd_shapes(B, H, L, D, A):
+    """Ragged shapes (B not a tile multiple, H not a multiple of 16, A in 1..4), 4 updates
+    spanning a Polyak step, versus the NumPy oracle on identical weights and batches."""
+    import torch
+    from gcrl_b200 import DDPG
+    from gcrl_b200.agent import NET_ACTOR, NET_CRITIC
+    rng = np.random.default_rng(B * 7 + H)
+    cfg = make_config(hidden_dim=H, layer_count=L, batch_size=B, grad_clip=0.5, tau=0.05)
+    ag = DDPG(D, A, cfg, None, 1, 40)
+    actor0, critic0 = OD.init_mlp(rng, D, H, A, L), OD.init_mlp(rng, D + A, H, 1, L)
+    ag._set_layers(NET_ACTOR, actor0)
+    ag._set_layers(NET_CRITIC, critic0)
+    ag.update_target_network()
+    orc = OD.DDPGOracle(actor0, critic0, gamma=cfg.gamma, tau=cfg.tau, grad_clip=cfg.grad_clip,
+                        actor_lr=cfg.actor_lr, critic_lr=cfg.critic_lr)
+    for si, step in enumerate((39, 40, 41, 42)):
+        s = rng.standard_normal((B, D)).astype(np.float32)
+        ns = (s + 0.1 * rng.standard_normal((B, D))).astype(np.float32)
+        a = rng.uniform(-1, 1, (B, A)).astype(np.float32)
+        r = -(rng.random((B, 1)) > 0.3).astype(np.float32)
+        d = (rng.random((B, 1)) < 0.1).astype(np.float32)
+        want = orc.update_on_batch(step, s, a, r, ns, d)
+        got = ag.update(step, batch=tuple(torch.from_numpy(x).cuda() for x in (s, a, r, ns, d)))
+        np.testing.assert_allclose(np.array([float(x) for x in got]), np.array(want), rtol=5e-5, atol=2e-6)
+    for net, ref in ((ag.actor, orc.actor), (ag.critic, orc.critic),
+                     (ag.target_actor, orc.target_actor), (ag.target_critic, orc.target_critic)):
+        for (w, b), (rw, rb) in zip(net.layers(), ref):
+            assert weights_close(w, rw, 1e-3, 4) and weights_close(b, rb, 1e-3, 4)
+
+
+def test_checkpoint_load_and_forward_matches_reference():
+    """state_dict key names / layout of the shipped Reach checkpoint (src/model.py:32-37) and
+    actor / critic forward versus the reference's own outputs."""
+    import torch
+    from gcrl_b200 import DDPG
+    g = load("checkpoint_reach")
+    ag = DDPG(10, 3, make_config(hidden_dim=64, layer_count=3, batch_size=64), None, 1, 40)
+    ag.actor.load_state_dict({k[6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("actor.")})
+    ag.critic.load_state_dict({k[7:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("critic.")})
+    act = ag._actor_forward(g["x"])
+    np.testing.assert_allclose(act, g["act"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(ag.q_values(g["x"], act), g["q"], rtol=1e-5, atol=1e-6)
+    sd = ag.actor.state_dict()
+    assert sorted(sd) == sorted(k[6:] for k in g.files if k.startswith("actor."))
+    for k, v in sd.items():
+        assert np.array_equal(v.numpy(), g["actor." + k])
+    # eval-mode select_action applies the reference's second tanh (src/agent.py:1364-1366)
+    np.testing.assert_allclose(ag.select_action(g["x"], eval_action=True), np.tanh(g["act"]), rtol=1e-5,
+                               atol=1e-6)
+
+
+def test_save_weights_round_trip(tmp_path):
+    import torch
+    from gcrl_b200 import DDPG
+    ag = DDPG(10, 3, make_config(), None, 1, 40)
+    ag.save_weights(str(tmp_path / "w"))
+    sd = torch.load(str(tmp_path / "w" / "actor.pth"))
+    assert list(sd) == [f"base_net.{i}.{p}" for i in (0, 2, 4, 6) for p in ("weight", "bias")]
+    sc = torch.load(str(tmp_path / "w" / "critic.pth"))
+    assert list(sc) == [f"net.{i}.{p}" for i in (0, 2, 4, 6) for p in ("weight", "bias")]
+    ag2 = DDPG(10, 3, make_config(), str(tmp_path / "w"), 1, 40)
+    for (w, b), (w2, b2) in zip(ag.actor.layers() + ag.critic.layers(), ag2.actor.layers() + ag2.critic.layers()):
+        assert np.array_equal(w, w2) and np.array_equal(b, b2)
+    for (w, b), (w2, b2) in zip(ag2.actor.layers(), ag2.target_actor.layers()):
+        assert np.array_equal(w, w2) and np.array_equal(b, b2)         # hard sync at init (:1251-1253)
+
+
+def test_update_from_buffer_equals_sample_then_update():
+    """The fused sample+update call == sample() followed by update(batch) on the same indices,
+    bit for bit (same kernels, same order)."""
+    from gcrl_b200 import DDPG
+    from gcrl_b200.agent import NET_ACTOR, NET_CRITIC
+    from tests.helpers import her_episodes
+    g = load("her_push_evict")
+    D, A = 22, 3
+    agents = []
+    for _ in range(2):
+        ag = DDPG(D, A, make_config(hidden_dim=64, batch_size=128, max_len=777), None, 1, 40)
+        rng = np.random.default_rng(1)
+        ag._set_layers(NET_ACTOR, OD.init_mlp(rng, D, 64, A, 3))
+        ag._set_layers(NET_CRITIC, OD.init_mlp(rng, D + A, 64, 1, 3))
+        ag.update_target_network()
+        for ep in her_episodes(g):
+            ag.buffer.push_episode(ep["s"], ep["a"], ep["ns"], ep["r"], ep["d"], ep["ag"], ep["fut"])
+        agents.append(ag)
+    rng = np.random.default_rng(2)
+    for step in (39, 40, 41):
+        idx = rng.permutation(len(agents[0].buffer))[:128]
+        i1 = agents[0].update(step, indices=idx)
+        i2 = agents[1].update(step, batch=agents[1].buffer.sample(128, indices=idx))
+        assert [float(x) for x in i1] == [float(x) for x in i2]
+    for n1, n2 in ((agents[0].actor, agents[1].actor), (agents[0].critic, agents[1].critic)):
+        for (w, b), (w2, b2) in zip(n1.layers(), n2.layers()):
+            assert np.array_equal(w, w2) and np.array_equal(b, b2)
+
+
+def test_update_is_deterministic_run_to_run():
+    import torch
+    g = load("ddpg_push_h256")
+    outs = []
+    for _ in range(2):
+        ag, _ = make_agent_from_golden(g)
+        infos = [ag.update(int(step), batch=batch_to_device(g, si)) for si, step in enumerate(g["steps"])]
+        outs.append((infos, [w.copy() for w, _ in ag.critic.layers() + ag.actor.layers()]))
+    assert [[float(x) for x in i] for i in outs[0][0]] == [[float(x) for x in i] for i in outs[1][0]]
+    for w1, w2 in zip(outs[0][1], outs[1][1]):
+        assert np.array_equal(w1, w2)
+    torch.cuda.synchronize()
