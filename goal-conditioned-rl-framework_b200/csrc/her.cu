@@ -260,7 +260,10 @@ her_sample_kernel(HerGeom g, int64_t B, const int64_t *__restrict__ idx, float *
         row[g.off_ns + g.D - g.G + c] = gf;
       }
       const float dist = __fsqrt_rn(acc);
-      row[g.off_r] = (dist > 0.05f) ? -1.0f : -0.0f;            // -(d > 0.05) as float32
+      // -(d > 0.05) as float32: -1.0f, or -0.0f with the SIGN BIT SET on success
+      // (-np.array(False, float32)).  Written as an INTEGER word: with a float-typed select
+      // nvcc 12.9 rewrites {-1.0f, -0.0f} into int->float(-(int)pred), which yields +0.0f.
+      reinterpret_cast<uint32_t *>(row)[g.off_r] = 0x80000000u | ((dist > 0.05f) ? 0x3F800000u : 0u);
       row[g.off_d] = 0.0f;                                      // new_done = False
     }
   }

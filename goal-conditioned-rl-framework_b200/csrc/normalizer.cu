@@ -5,6 +5,12 @@
 // normalize = clip((x - mean) / (sqrt(var) + 1e-8), +-clip).
 //
 // Kernels
+//   norm_update_seq_kernel : batches of <= 8192 rows (the reference's regime: 2-4 rows per env
+//                         per step, src/env.py:165-172).  One thread per column walks the rows in
+//                         order, accumulating in the INPUT dtype with unfused IEEE operations --
+//                         exactly what numpy's axis-0 np.mean / np.var do for dim >= 2 -- then
+//                         applies _update_from_moments in float64 without FMA contraction, so the
+//                         running statistics are bit-identical to the reference's.
 //   norm_partial_kernel : one warp per column, lanes stride over the rows of the CTA's row
 //                         slab with a per-lane Welford accumulator, lanes merged with
 //                         shuffles (Chan merge of (n, mean, M2) triples) -> one partial per
@@ -71,6 +77,56 @@ struct NormState {
   double *mean, *var, *count;  // device, [dim], [dim], [1]
 };
 
+// unfused IEEE arithmetic in the input dtype (numpy never contracts a*b+c)
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+
+// RunningNormalizer._update_from_moments (src/utils.py:82-94), float64, operation for operation:
+//   total = count + n;  delta = bmean - mean;  mean += delta * n / total
+//   m2 = var * count + m_b + delta^2 * count * n / total;  var = m2 / total
+// m_b = batch_var * n is formed by the CALLER: numpy evaluates it in the batch dtype (a float32
+// batch variance times a Python int stays float32, src/utils.py:88).
+__device__ __forceinline__ void update_from_moments(NormState st, int c, double count, double bmean,
+                                                    double m_b, double n) {
+  const double tot = __dadd_rn(count, n);
+  const double mean = st.mean[c];
+  const double delta = __dsub_rn(bmean, mean);
+  const double new_mean = __dadd_rn(mean, __ddiv_rn(__dmul_rn(delta, n), tot));
+  const double m2 = __dadd_rn(__dadd_rn(__dmul_rn(st.var[c], count), m_b),
+                              __ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(delta, delta), count), n), tot));
+  st.mean[c] = new_mean;
+  st.var[c] = __ddiv_rn(m2, tot);
+  if (c == 0) *st.count = tot;
+}
+
+constexpr int64_t kSeqMaxRows = 8192;
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+norm_update_seq_kernel(const T *__restrict__ x, int n, int dim, NormState st) {
+  const int c = threadIdx.x;  // single CTA, one thread per column (coalesced across the row)
+  const double count = *st.count;
+  __syncthreads();            // every column reads the old count before thread 0 replaces it
+  if (c >= dim) return;
+  T s = x[c];
+  for (int r = 1; r < n; ++r) s = add_rn(s, x[size_t(r) * dim + c]);
+  const T mean = div_rn(s, T(n));
+  T d = sub_rn(x[c], mean);
+  T v = mul_rn(d, d);
+  for (int r = 1; r < n; ++r) {
+    d = sub_rn(x[size_t(r) * dim + c], mean);
+    v = add_rn(v, mul_rn(d, d));
+  }
+  const T var = div_rn(v, T(n));
+  update_from_moments(st, c, count, double(mean), double(mul_rn(var, T(n))), double(n));
+}
+
 __global__ void norm_merge_kernel(const Moments *__restrict__ partials, int nblocks, int dim,
                                   NormState st) {
   const int c = threadIdx.x;  // single CTA, one thread per column
@@ -79,15 +135,7 @@ __global__ void norm_merge_kernel(const Moments *__restrict__ partials, int nblo
   if (c >= dim) return;
   Moments b{0.0, 0.0, 0.0};
   for (int i = 0; i < nblocks; ++i) b = chan_merge(b, partials[size_t(i) * dim + c]);
-  // reference _update_from_moments (src/utils.py:82-94) with batch var = M2 / n
-  const double bvar = b.m2 / b.n;
-  const double tot = count + b.n;
-  const double delta = b.mean - st.mean[c];
-  const double new_mean = st.mean[c] + delta * b.n / tot;
-  const double m2 = st.var[c] * count + bvar * b.n + delta * delta * count * b.n / tot;
-  st.mean[c] = new_mean;
-  st.var[c] = m2 / tot;
-  if (c == 0) *st.count = tot;
+  update_from_moments(st, c, count, b.mean, b.m2, b.n);
 }
 
 template <typename TI, typename TO>
@@ -126,6 +174,15 @@ struct gcrl_norm {
 static void norm_update_device(gcrl_norm *h, const void *x_dev, int64_t n, int is_f64,
                                cudaStream_t st) {
   if (n <= 0) return;
+  GCRL_REQUIRE(h->dim <= 128, "normaliser dim > 128 not supported");
+  if (n <= kSeqMaxRows && h->dim >= 2) {   // reference-scale batch: bit-exact numpy order
+    if (is_f64)
+      norm_update_seq_kernel<double><<<1, 128, 0, st>>>(static_cast<const double *>(x_dev), int(n), h->dim, h->st);
+    else
+      norm_update_seq_kernel<float><<<1, 128, 0, st>>>(static_cast<const float *>(x_dev), int(n), h->dim, h->st);
+    GCRL_LAUNCHED();
+    return;
+  }
   const int64_t rows_per_block = std::max<int64_t>(256, (n + h->max_blocks - 1) / h->max_blocks);
   const int nblocks = int((n + rows_per_block - 1) / rows_per_block);
   if (is_f64)

@@ -95,11 +95,11 @@ class HERBuffer:
         ag = np.ascontiguousarray(ag, np.float32)
         T = s.shape[0]
         self._ensure(s.shape[1], a.shape[1], ag.shape[1])
-        if fut is None and self.index_source == "host":
+        if fut is None and self.index_source == "host" and self.k_future > 0:
             fut = self._draw_future(T)
         fptr = None
-        if fut is not None:
-            fut = np.ascontiguousarray(fut, np.uint8).reshape(T, max(self.k_future, 1))[:, :self.k_future]
+        if fut is not None and self.k_future > 0:
+            fut = np.ascontiguousarray(fut, np.uint8).reshape(T, -1)[:, :self.k_future]
             fut = np.ascontiguousarray(fut)
             fptr = np_ptr(fut)
         check(lib.gcrl_her_push_episode(self._h, T, np_ptr(s), np_ptr(a), np_ptr(ns), np_ptr(r),
