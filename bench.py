@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--no-sweep", action="store_true", help="skip the batch sweep / kernel rooflines")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--spinup", type=int, default=80, help="extra untimed steps before the W warm-up steps")
     return ap.parse_args()
 
 
@@ -312,7 +313,7 @@ def gpu_main(args):
 
     # ---- warm-up (graph capture for both flag sets, clocks ramp), then the timed region ----
     step = 1
-    for _ in range(max(args.warmup, 3) + 80):
+    for _ in range(max(args.warmup, 3) + args.spinup):
         device_step(step)
         step += 1
     barrier()
