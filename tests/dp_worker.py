@@ -1,0 +1,67 @@
+"""torchrun worker for tests/test_dp_gpu.py::test_two_gpu_nccl_run_matches_single_rank: every rank
+updates on its own batch with NCCL-averaged gradients; rank 0 also runs a single-rank agent on the
+concatenated batch and compares."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "goal-conditioned-rl-framework_b200"))
+from tests.helpers import weights_close  # noqa: E402
+from tests.test_dp_gpu import rand_batch  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    D, A, H, L, B = 21, 3, 256, 3, 256
+    ag = make_agent_on(local, D, A, H, L, B)
+    ag.enable_data_parallel()
+    single = make_agent_on(local, D, A, H, L, world * B) if rank == 0 else None
+    rng = np.random.default_rng(5)
+    for step in (39, 40, 41, 42):
+        batches = [rand_batch_on(rng, B, D, A, local) for _ in range(world)]   # same stream on every rank
+        info = ag.update(step, batch=batches[rank])
+        if rank == 0:
+            want = single.update(step, batch=tuple(torch.cat(parts) for parts in zip(*batches)))
+            np.testing.assert_allclose(np.array([float(x) for x in info]), np.array([float(x) for x in want]),
+                                       rtol=5e-5, atol=2e-6)
+    # replicas identical across ranks, and equal to the single-rank run within tolerance
+    flat = torch.cat([torch.from_numpy(w).reshape(-1) for w, _ in ag.actor.layers() + ag.critic.layers()]).cuda()
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    for g in gathered[1:]:
+        assert torch.equal(g, gathered[0])
+    if rank == 0:
+        for (w, b), (ws, bs) in zip(ag.actor.layers() + ag.critic.layers() + ag.target_critic.layers(),
+                                    single.actor.layers() + single.critic.layers() + single.target_critic.layers()):
+            assert weights_close(w, ws, 1e-3, 4) and weights_close(b, bs, 1e-3, 4)
+        print("DP_OK", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def make_agent_on(dev, D, A, H, L, B):
+    from gcrl_b200 import DDPG
+    from gcrl_b200.agent import NET_ACTOR, NET_CRITIC
+    from oracle import ddpg as OD
+    from tests.test_ddpg_gpu import make_config
+    ag = DDPG(D, A, make_config(hidden_dim=H, layer_count=L, batch_size=B, grad_clip=0.5), None, 1, 40, device=dev)
+    rng = np.random.default_rng(3)
+    ag._set_layers(NET_ACTOR, OD.init_mlp(rng, D, H, A, L))
+    ag._set_layers(NET_CRITIC, OD.init_mlp(rng, D + A, H, 1, L))
+    ag.update_target_network()
+    return ag
+
+
+def rand_batch_on(rng, B, D, A, dev):
+    return tuple(t.to(torch.device("cuda", dev)) for t in (x.cpu() for x in rand_batch(rng, B, D, A)))
+
+
+if __name__ == "__main__":
+    main()

@@ -262,6 +262,70 @@ def ddpg_case(agent_mod, utils_mod, name, *, D, A, H, L, B, steps, seed, gamma=0
     print(f"ddpg_{name}: {len(steps)} steps; last info {out[f's{len(steps) - 1}_info']}")
 
 
+def td3_case(agent_mod, utils_mod, name, *, D, A, H, L, B, steps, seed, gamma=0.98, tau=0.05,
+             grad_clip=1.0, lr=1e-3, policy_noise=0.2, noise_clamp=0.5, ac_update_freq=2):
+    """Unmodified reference TD3Agent.update on explicit batches; every torch.randn_like draw of
+    the target-policy smoothing (src/agent.py:175) is recorded."""
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import ddpg as O
+    torch.set_num_threads(1)
+    cfg = utils_mod.BaseAgentConfig(
+        hidden_dim=H, layer_count=L, actor_lr=lr, actor_lr_min=lr, ac_scheduler_steps=1, critic_lr=lr,
+        critic_lr_min=lr, cr_scheduler_steps=1, buffer_type="HER", max_len=1000, alpha=1.0, batch_size=B,
+        gamma=gamma, ac_update_freq=ac_update_freq, noise_std=0.2, noise_clamp=noise_clamp,
+        policy_noise=policy_noise, grad_clip=grad_clip, beta=1.0, beta_end=1, k_future=4, max_eps_len=50,
+        tau=tau)
+    ag = agent_mod.TD3Agent(obs_dim=D, ac_dim=A, config=cfg, weights=None, nenvs=1, gradient_step=40)
+    ag.device = "cpu"
+    rng = np.random.default_rng(seed)
+    nets0 = {"actor": O.init_mlp(rng, D, H, A, L), "critic_1": O.init_mlp(rng, D + A, H, 1, L),
+             "critic_2": O.init_mlp(rng, D + A, H, 1, L)}
+    with torch.no_grad():
+        for tag, pref in (("actor", "base_net"), ("critic_1", "net"), ("critic_2", "net")):
+            sd = getattr(ag, tag).state_dict()
+            for i, (w, b) in enumerate(nets0[tag]):
+                sd[f"{pref}.{2 * i}.weight"].copy_(torch.from_numpy(w))
+                sd[f"{pref}.{2 * i}.bias"].copy_(torch.from_numpy(b))
+    ag.update_target_network()
+    out = {"meta": np.array([D, A, H, L, B, seed, ac_update_freq], np.int64),
+           "hp": np.array([gamma, tau, grad_clip, lr, policy_noise, noise_clamp], np.float64),
+           "steps": np.array(steps, np.int64)}
+    torch.manual_seed(seed)
+    real_randn_like = torch.randn_like
+    for si, step in enumerate(steps):
+        s = rng.standard_normal((B, D)).astype(np.float32)
+        ns = (s + 0.1 * rng.standard_normal((B, D))).astype(np.float32)
+        a = rng.uniform(-1, 1, (B, A)).astype(np.float32)
+        r = -(rng.random((B, 1)) > 0.3).astype(np.float32)
+        d = (rng.random((B, 1)) < 0.1).astype(np.float32)
+        batch = tuple(torch.from_numpy(x) for x in (s, a, r, ns, d))
+        ag.buffer.sample = lambda bs, _b=batch: _b
+        drawn = []
+
+        def rec(t, *a_, **k_):
+            v = real_randn_like(t, *a_, **k_)
+            drawn.append(v.numpy().copy())
+            return v
+
+        agent_mod.torch.randn_like = rec
+        try:
+            info = ag.update(step)
+        finally:
+            agent_mod.torch.randn_like = real_randn_like
+        assert len(drawn) == 1
+        for key, val in zip(("s", "a", "r", "ns", "d"), (s, a, r, ns, d)):
+            out[f"s{si}_batch_{key}"] = val
+        out[f"s{si}_noise"] = drawn[0]
+        out[f"s{si}_info"] = np.array([float(x) for x in info], np.float64)
+        if si == len(steps) - 1:
+            for tag in ("actor", "critic_1", "critic_2", "target_actor", "target_critic_1", "target_critic_2"):
+                for k_, v in flat_params(getattr(ag, tag)).items():
+                    out[f"s{si}_{tag}.{k_}"] = v
+    np.savez_compressed(os.path.join(HERE, f"td3_{name}.npz"), **out)
+    print(f"td3_{name}: {len(steps)} steps; last info {out[f's{len(steps) - 1}_info']}")
+
+
 def checkpoint_case(model_mod):
     """Load-compat + forward-differential fixture from the shipped Reach checkpoint
     (resources/DDPG/reach/{actor,critic}.pth: H=64, D=10, A=3)."""
@@ -291,6 +355,11 @@ def checkpoint_case(model_mod):
 
 def main():
     agent_mod, buffer_mod, model_mod, utils_mod = import_reference()
+    td3_case(agent_mod, utils_mod, "push_h64", D=22, A=3, H=64, L=3, B=128, steps=[1, 2, 3, 4, 5], seed=21)
+    td3_case(agent_mod, utils_mod, "pickplace_h256", D=23, A=4, H=256, L=2, B=200, steps=[7, 8, 9], seed=22,
+             grad_clip=0.1, ac_update_freq=1, tau=0.005, policy_noise=0.3, noise_clamp=0.25)
+    if len(sys.argv) > 1 and sys.argv[1] == "td3":
+        return
     reward_case()
     her_case(buffer_mod, "reach_small", O=7, G=3, A=3, k=4,
              lens=[50, 50, 7, 1, 2, 50, 13, 50], max_mem_len=100000, nenvs=2, seed=0,

@@ -99,7 +99,10 @@ def test_update_matches_oracle_odd_shapes(B, H, L, D, A):
         d = (rng.random((B, 1)) < 0.1).astype(np.float32)
         want = orc.update_on_batch(step, s, a, r, ns, d)
         got = ag.update(step, batch=tuple(torch.from_numpy(x).cuda() for x in (s, a, r, ns, d)))
-        np.testing.assert_allclose(np.array([float(x) for x in got]), np.array(want), rtol=5e-5, atol=2e-6)
+        # batch means / gradient norms are fp32 sums over B terms evaluated in a different order than
+        # BLAS: the summation-order noise grows like sqrt(B) (rel 5e-5 at B <= 256)
+        rtol = 5e-5 * max(1.0, (B / 256.0) ** 0.5)
+        np.testing.assert_allclose(np.array([float(x) for x in got]), np.array(want), rtol=rtol, atol=2e-6)
     for net, ref in ((ag.actor, orc.actor), (ag.critic, orc.critic),
                      (ag.target_actor, orc.target_actor), (ag.target_critic, orc.target_critic)):
         for (w, b), (rw, rb) in zip(net.layers(), ref):

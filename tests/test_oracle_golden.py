@@ -144,3 +144,33 @@ def test_checkpoint_forward_matches_reference():
     q, _ = OD.mlp_forward(critic, np.concatenate([g["x"], act], -1), final_tanh=False)
     np.testing.assert_allclose(act, g["act"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(q, g["q"], rtol=1e-5, atol=1e-6)
+
+
+# ---- TD3 ------------------------------------------------------------------------------------
+TD3_CASES = ["push_h64", "pickplace_h256"]
+
+
+def make_td3_oracle(g):
+    from oracle import td3 as OT
+    D, A, H, L, B, seed, freq = (int(x) for x in g["meta"])
+    gamma, tau, clip, lr, pn, nc = (float(x) for x in g["hp"])
+    rng = np.random.default_rng(seed)
+    nets = [OD.init_mlp(rng, D, H, A, L), OD.init_mlp(rng, D + A, H, 1, L), OD.init_mlp(rng, D + A, H, 1, L)]
+    return OT.TD3Oracle(*nets, gamma=gamma, tau=tau, grad_clip=clip, actor_lr=lr, critic_lr=lr,
+                        policy_noise=pn, noise_clamp=nc, ac_update_freq=freq), nets
+
+
+@pytest.mark.parametrize("case", TD3_CASES)
+def test_td3_oracle_matches_reference(case):
+    g = load("td3_" + case)
+    orc, _ = make_td3_oracle(g)
+    lr = float(g["hp"][3])
+    n = len(g["steps"])
+    for si, step in enumerate(g["steps"]):
+        info = orc.update_on_batch(int(step), *ddpg_batch(g, si), g[f"s{si}_noise"])
+        ref = g[f"s{si}_info"]
+        assert len(info) == len(ref)
+        np.testing.assert_allclose(np.array(info), ref, rtol=2e-5, atol=1e-6)
+    for tag in ("actor", "critic_1", "critic_2", "target_actor", "target_critic_1", "target_critic_2"):
+        for (w, b), (rw, rb) in zip(getattr(orc, tag), ddpg_params_from_golden(g, n - 1, tag)):
+            assert weights_close(w, rw, lr, n) and weights_close(b, rb, lr, n), tag
