@@ -39,8 +39,11 @@ struct Net {
   int layers = 0;  // number of Linear layers = layer_count + 1
   int in_dim = 0, hidden = 0, out_dim = 0;
   std::vector<int> in_d, out_d, ldw, w_off, b_off;
-  int total = 0;
+  std::vector<int> ldt, t_off;   // transposed copy Wt[in][ldt] per layer (forward operand of fused.cu)
+  int total = 0, total_t = 0;
   float *p = nullptr, *g = nullptr, *m = nullptr, *v = nullptr;
+  float *pT = nullptr;
+  int *tmap = nullptr;           // [total] -> index into pT, -1 for bias / padding
   int adam_t = 0;
 
   void init(int in, int hid, int out, int layer_count, bool trainable) {
@@ -57,6 +60,21 @@ struct Net {
       off += pad4(out_d[l]);
     }
     total = off;
+    int toff = 0;
+    for (int l = 0; l < layers; ++l) {
+      ldt.push_back(pad4(out_d[l]));
+      t_off.push_back(toff);
+      toff += in_d[l] * ldt[l];
+    }
+    total_t = toff;
+    std::vector<int> map(size_t(total), -1);
+    for (int l = 0; l < layers; ++l)
+      for (int o = 0; o < out_d[l]; ++o)
+        for (int i = 0; i < in_d[l]; ++i) map[size_t(w_off[l]) + size_t(o) * ldw[l] + i] = t_off[l] + i * ldt[l] + o;
+    tmap = dev_alloc<int>(total);
+    GCRL_CUDA(cudaMemcpy(tmap, map.data(), size_t(total) * sizeof(int), cudaMemcpyHostToDevice));
+    pT = dev_alloc<float>(total_t);
+    GCRL_CUDA(cudaMemset(pT, 0, size_t(total_t) * 4));
     p = dev_alloc<float>(total);
     GCRL_CUDA(cudaMemset(p, 0, size_t(total) * 4));
     if (trainable) {
@@ -70,6 +88,8 @@ struct Net {
   }
   void destroy() {
     cudaFree(p);
+    cudaFree(pT);
+    cudaFree(tmap);
     if (g) { cudaFree(g); cudaFree(m); cudaFree(v); }
   }
   const float *W(int l) const { return p + w_off[l]; }
@@ -116,6 +136,9 @@ struct gcrl_agent {
   float *d_io = nullptr;
   size_t io_cap = 0;
   float *noise = nullptr;                  // TD3 smoothing noise copy [maxB, A]
+  std::vector<float *> dzl;                // fused path: per-layer pre-activation gradients [maxB, ldh]
+  float *dzh = nullptr;                    // fused path: critic head dL/dq [maxB]
+  bool use_fused = true;
   int dp_B = -1, dp_flags = -1;            // the update the data-parallel phases belong to
   bool use_graphs = true;
   cudaStream_t cap_stream = nullptr;       // capture-only stream (the caller's may be the legacy one)
@@ -188,7 +211,7 @@ void reduce_grads(gcrl_agent *ag, Net &n, const int *splits, int head_splits, bo
 }
 
 // global-norm clip + Adam(W) (+ fused Polyak of `target` with the stepped parameters)
-void adam_step(gcrl_agent *ag, Net &n, int which, float max_norm, int slot_norm, float *target, bool polyak,
+void adam_step(gcrl_agent *ag, Net &n, int which, float max_norm, int slot_norm, Net *target, bool polyak,
                cudaStream_t st) {
   AdamArgs a{};
   a.p = n.p; a.m = n.m; a.v = n.v; a.g = n.g; a.n = n.total;
@@ -196,9 +219,10 @@ void adam_step(gcrl_agent *ag, Net &n, int which, float max_norm, int slot_norm,
   a.max_norm = max_norm;
   a.weight_decay = ag->cfg.weight_decay;
   a.sc = ag->d_scalars; a.which = which;
-  a.target = target; a.tau = ag->cfg.tau; a.one_minus_tau = float(1.0 - double(ag->cfg.tau));
-  a.polyak = polyak ? 1 : 0;
+  a.target = target ? target->p : nullptr; a.tau = ag->cfg.tau; a.one_minus_tau = float(1.0 - double(ag->cfg.tau));
+  a.polyak = (polyak && target) ? 1 : 0;
   a.metrics = ag->metrics; a.slot_norm = slot_norm;
+  a.tmap = n.tmap; a.pT = n.pT; a.targetT = target ? target->pT : nullptr;
   launch_adam(a, st);
 }
 
@@ -270,8 +294,79 @@ struct PhaseState {
   int head_splits = 0, metric_splits = 0;
 };
 
+// ---- row-slab fused path (fused.cu): DDPG, B <= 1024 ---------------------------------------------
+bool fused_ok(const gcrl_agent *ag, int B) {
+  return ag->use_fused && !ag->td3 && fused_supported(B, ag->D, ag->A, ag->H, ag->L);
+}
+
+FusedNet fused_net(const gcrl_agent *ag, const Net &n) {
+  FusedNet f{};
+  for (int l = 0; l < ag->L; ++l) {
+    f.Wt[l] = n.pT + n.t_off[l]; f.ldt[l] = n.ldt[l];
+    f.W[l] = n.p + n.w_off[l];   f.ldw[l] = n.ldw[l];
+    f.b[l] = n.p + n.b_off[l];
+  }
+  f.Wh = n.p + n.w_off[ag->L]; f.ldwh = n.ldw[ag->L]; f.bh = n.p + n.b_off[ag->L];
+  return f;
+}
+
+// weight gradients of all layers of `n` in one launch; hidden-layer operands: dzl[l] and
+// (l == 0 ? sa : acts.h[l-1]); head operand: dz_head [B][ld_head] and acts.h[L-1]
+int fused_wgrads(gcrl_agent *ag, const Net &n, const Acts &acts, int K0, const float *dz_head, int ld_head,
+                 int B, cudaStream_t st) {
+  WgradProblem pr[kMaxWgradProblems];
+  const int L = ag->L;
+  for (int l = 0; l < L; ++l) {
+    pr[l] = WgradProblem{ag->dzl[l], ag->ldh, l == 0 ? ag->sa : acts.h[l - 1], l == 0 ? ag->ldc : ag->ldh,
+                         ag->partials + n.w_off[l], n.ldw[l], ag->partials + n.b_off[l], ag->H,
+                         l == 0 ? K0 : ag->H};
+  }
+  pr[L] = WgradProblem{dz_head, ld_head, acts.h[L - 1], ag->ldh, ag->partials + n.w_off[L], n.ldw[L],
+                       ag->partials + n.b_off[L], n.out_d[L], ag->H};
+  return launch_multi_wgrad(pr, L + 1, B, ag->slab, kMaxSplits, st);
+}
+
+void fused_critic_phase_grads(gcrl_agent *ag, int B, cudaStream_t st) {
+  FusedCriticArgs a{};
+  a.ta = fused_net(ag, ag->net[T_ACTOR]);
+  a.tc = fused_net(ag, ag->net[T_CRITIC1]);
+  a.c = fused_net(ag, ag->net[CRITIC1]);
+  a.s = ag->bs; a.a = ag->ba; a.r = ag->br0; a.ns = ag->bns; a.d = ag->bd0;
+  a.B = B; a.D = ag->D; a.A = ag->A; a.H = ag->H; a.L = ag->L; a.ldh = ag->ldh; a.ldc = ag->ldc;
+  a.gamma = ag->cfg.gamma;
+  a.y_lo = float(-1.0 / (1.0 - double(ag->cfg.gamma)));
+  a.clamp_y = 1;                                       // DDPG clamps y to [-1/(1-gamma), 0] (:1317)
+  a.sa_out = ag->sa;
+  for (int l = 0; l < ag->L; ++l) { a.h_out[l] = ag->acts_c1.h[l]; a.dz_out[l] = ag->dzl[l]; }
+  a.dzh_out = ag->dzh; a.y_out = ag->yv; a.q_out = ag->q1;
+  a.metric_partials = ag->metric_partials;
+  const int slabs = launch_fused_critic(a, st);
+  const Net &c = ag->net[CRITIC1];
+  const int S = fused_wgrads(ag, c, ag->acts_c1, ag->D + ag->A, ag->dzh, 1, B, st);
+  int splits[8];
+  for (int l = 0; l < 8; ++l) splits[l] = S;
+  reduce_grads(ag, ag->net[CRITIC1], splits, S, false, S_CLOSS, S_TD, S_Q, slabs, B, st);
+}
+
+void fused_actor_phase_grads(gcrl_agent *ag, int B, cudaStream_t st) {
+  FusedActorArgs a{};
+  a.actor = fused_net(ag, ag->net[ACTOR]);
+  a.c = fused_net(ag, ag->net[CRITIC1]);
+  a.s = ag->bs;
+  a.B = B; a.D = ag->D; a.A = ag->A; a.H = ag->H; a.L = ag->L; a.ldh = ag->ldh;
+  for (int l = 0; l < ag->L; ++l) { a.h_out[l] = ag->acts_actor.h[l]; a.dz_out[l] = ag->dzl[l]; }
+  a.da_out = ag->dz_act;
+  a.metric_partials = ag->metric_partials;
+  const int slabs = launch_fused_actor(a, st);
+  const int S = fused_wgrads(ag, ag->net[ACTOR], ag->acts_actor, ag->D, ag->dz_act, 4, B, st);
+  int splits[8];
+  for (int l = 0; l < 8; ++l) splits[l] = S;
+  reduce_grads(ag, ag->net[ACTOR], splits, S, false, S_ALOSS, -1, -1, slabs, B, st);
+}
+
 // critic(s): forward, loss, backward, partials -> flat local-mean gradient(s) + metrics
 void critic_phase_grads(gcrl_agent *ag, int B, const float *noise, cudaStream_t st) {
+  if (fused_ok(ag, B)) { fused_critic_phase_grads(ag, B, st); return; }
   PhaseState ps;
   targets_and_critic_forward(ag, B, noise, st);
   critic_forward_backward(ag, 0, B, ps.splits, &ps.head_splits, &ps.metric_splits, st);
@@ -293,7 +388,7 @@ void critic_phase_step(gcrl_agent *ag, int which, int flags, bool rereduce, cuda
   if (rereduce) reduce_grads(ag, c, nullptr, 0, true, -1, -1, -1, 0, 1, st);
   // TD3 critic 1 is NOT clipped (:201 is commented out), critic 2 is
   const float clip = (ag->td3 && which == 0) ? -1.0f : ag->cfg.grad_clip;
-  adam_step(ag, c, 0, clip, which == 0 ? S_CGRAD : S_C2GRAD, ag->net[which == 0 ? T_CRITIC1 : T_CRITIC2].p,
+  adam_step(ag, c, 0, clip, which == 0 ? S_CGRAD : S_C2GRAD, &ag->net[which == 0 ? T_CRITIC1 : T_CRITIC2],
             polyak, st);
 }
 
@@ -301,10 +396,11 @@ void critic_phase_step(gcrl_agent *ag, int which, int flags, bool rereduce, cuda
 void ddpg_actor_target_polyak(gcrl_agent *ag, int flags, cudaStream_t st) {
   if (!ag->td3 && (flags & 2))
     launch_polyak(ag->net[T_ACTOR].p, ag->net[ACTOR].p, ag->net[ACTOR].total, ag->cfg.tau,
-                  float(1.0 - double(ag->cfg.tau)), st);
+                  float(1.0 - double(ag->cfg.tau)), ag->net[ACTOR].tmap, ag->net[T_ACTOR].pT, st);
 }
 
 void actor_phase_grads(gcrl_agent *ag, int B, cudaStream_t st) {
+  if (fused_ok(ag, B)) { fused_actor_phase_grads(ag, B, st); return; }
   PhaseState pstate, *ps = &pstate;
   const int D = ag->D, A = ag->A, K0 = D + A, L = ag->L;
   const Net &actor = ag->net[ACTOR];
@@ -348,7 +444,7 @@ void actor_phase_grads(gcrl_agent *ag, int B, cudaStream_t st) {
 void actor_phase_step(gcrl_agent *ag, bool rereduce, cudaStream_t st) {
   Net &a = ag->net[ACTOR];
   if (rereduce) reduce_grads(ag, a, nullptr, 0, true, -1, -1, -1, 0, 1, st);
-  adam_step(ag, a, 1, ag->cfg.grad_clip, S_AGRAD, ag->net[T_ACTOR].p, ag->td3, st);
+  adam_step(ag, a, 1, ag->cfg.grad_clip, S_AGRAD, &ag->net[T_ACTOR], ag->td3, st);
 }
 
 void write_scalars(gcrl_agent *ag, double lr_c, double lr_a, bool actor_steps, cudaStream_t st) {
@@ -439,7 +535,19 @@ void ingest(gcrl_agent *ag, gcrl_her *buf, int64_t B, const int64_t *idx_host, c
     GCRL_REQUIRE(s && a && r && ns && d, "NULL batch pointer");
   }
   GCRL_REQUIRE(!ag->td3 || noise_dev != nullptr, "TD3 update needs the [B, A] standard-normal noise tensor");
-  launch_ingest_batch(s, a, r, ns, d, ag->D, ag->A, int(B), ag->sa, ag->nsa, ag->spi, ag->ldc, ag->br, ag->bd, st);
+  if (fused_ok(ag, int(B))) {
+    // the fused kernels read the dense batch in place (stable addresses for the captured graph)
+    if (buf == nullptr) {
+      const size_t n = size_t(B) * 4;
+      GCRL_CUDA(cudaMemcpyAsync(ag->bs, s, n * ag->D, cudaMemcpyDeviceToDevice, st));
+      GCRL_CUDA(cudaMemcpyAsync(ag->ba, a, n * ag->A, cudaMemcpyDeviceToDevice, st));
+      GCRL_CUDA(cudaMemcpyAsync(ag->br0, r, n, cudaMemcpyDeviceToDevice, st));
+      GCRL_CUDA(cudaMemcpyAsync(ag->bns, ns, n * ag->D, cudaMemcpyDeviceToDevice, st));
+      GCRL_CUDA(cudaMemcpyAsync(ag->bd0, d, n, cudaMemcpyDeviceToDevice, st));
+    }
+  } else {
+    launch_ingest_batch(s, a, r, ns, d, ag->D, ag->A, int(B), ag->sa, ag->nsa, ag->spi, ag->ldc, ag->br, ag->bd, st);
+  }
   *noise_out = nullptr;
   if (ag->td3) {  // stable address for the captured graph
     GCRL_CUDA(cudaMemcpyAsync(ag->noise, noise_dev, size_t(B) * ag->A * 4, cudaMemcpyDeviceToDevice, st));
@@ -524,12 +632,16 @@ int gcrl_agent_create(gcrl_agent **out, int device, const gcrl_agent_config *cfg
       *p = dev_alloc<float>(size_t(mb));
     ag->dz_act = dev_alloc<float>(size_t(mb) * 4);
     ag->noise = dev_alloc<float>(size_t(mb) * 4);
+    for (int l = 0; l < L; ++l) ag->dzl.push_back(dev_alloc<float>(size_t(mb) * ag->ldh));
+    ag->dzh = dev_alloc<float>(size_t(mb));
+    const char *nf = getenv("GCRL_B200_NO_FUSED");
+    ag->use_fused = !(nf && nf[0] == '1');
     ag->bs = dev_alloc<float>(size_t(mb) * D);
     ag->bns = dev_alloc<float>(size_t(mb) * D);
     ag->ba = dev_alloc<float>(size_t(mb) * A);
     ag->slab = std::max(ag->net[ACTOR].total, ag->net[CRITIC1].total);
     ag->partials = dev_alloc<float>(size_t(kMaxSplits) * ag->slab);
-    ag->metric_partials = dev_alloc<float>(size_t(kMaxSplits) * 4);
+    ag->metric_partials = dev_alloc<float>(size_t(256) * 4);
     ag->sumsq = dev_alloc<float>(size_t(reduce_grid(int(ag->slab))) + 8);
     ag->metrics = dev_alloc<float>(8);
     GCRL_CUDA(cudaMemset(ag->metrics, 0, 8 * sizeof(float)));
@@ -558,8 +670,9 @@ int gcrl_agent_destroy(gcrl_agent *ag) {
   ag->acts_actor.destroy(); ag->acts_c1.destroy(); ag->acts_c2.destroy(); ag->acts_tgt.destroy();
   for (float *p : {ag->dz[0], ag->dz[1], ag->sa, ag->nsa, ag->spi, ag->q1, ag->q2, ag->qt1, ag->qt2, ag->yv,
                    ag->dz_act, ag->br, ag->bd, ag->bs, ag->ba, ag->bns, ag->br0, ag->bd0, ag->partials,
-                   ag->metric_partials, ag->sumsq, ag->metrics, ag->d_io, ag->noise})
+                   ag->metric_partials, ag->sumsq, ag->metrics, ag->d_io, ag->noise, ag->dzh})
     if (p) cudaFree(p);
+  for (float *p : ag->dzl) cudaFree(p);
   cudaFree(ag->d_scalars);
   if (ag->cap_stream) cudaStreamDestroy(ag->cap_stream);
   ag->scal_stage.destroy();
@@ -595,6 +708,7 @@ int gcrl_agent_set_layer(gcrl_agent *ag, int net, int layer, const float *weight
   for (int r = 0; r < o; ++r) std::memcpy(&padded[size_t(r) * ld], weight_host + size_t(r) * i, size_t(i) * 4);
   std::memcpy(&padded[size_t(o) * ld], bias_host, size_t(o) * 4);
   GCRL_CUDA(cudaMemcpyAsync(n.p + n.w_off[layer], padded.data(), padded.size() * 4, cudaMemcpyHostToDevice, st));
+  launch_sync_transposed(n.p, n.pT, n.tmap, n.total, st);
   GCRL_CUDA(cudaStreamSynchronize(st));
   GCRL_API_END
 }
@@ -624,9 +738,12 @@ int gcrl_agent_hard_update(gcrl_agent *ag, void *stream) {
   cudaStream_t st = as_stream(stream);
   const int pairs[3][2] = {{T_ACTOR, ACTOR}, {T_CRITIC1, CRITIC1}, {T_CRITIC2, CRITIC2}};
   for (auto &pr : pairs)
-    if (ag->has[pr[0]])
+    if (ag->has[pr[0]]) {
       GCRL_CUDA(cudaMemcpyAsync(ag->net[pr[0]].p, ag->net[pr[1]].p, size_t(ag->net[pr[1]].total) * 4,
                                 cudaMemcpyDeviceToDevice, st));
+      GCRL_CUDA(cudaMemcpyAsync(ag->net[pr[0]].pT, ag->net[pr[1]].pT, size_t(ag->net[pr[1]].total_t) * 4,
+                                cudaMemcpyDeviceToDevice, st));
+    }
   GCRL_API_END
 }
 

@@ -1,0 +1,409 @@
+// Row-slab fused DDPG update kernels (small / medium batch regime).
+//
+// Every network pass of the update is independent per batch row; only the weight gradients
+// reduce over rows.  So one CTA takes a slab of R batch rows and carries it through ALL layers:
+//   critic phase (reference src/agent.py:1302-1329):
+//     a' = target_actor(s')  ->  q' = target_critic(s', a')  ->  y = clamp(r + gamma (1-d) q')
+//     q = critic(s, a)       ->  dL/dq = 2 (q - y) / B       ->  backward through the critic
+//   actor phase (src/agent.py:1288-1294):
+//     a = actor(s) -> q = critic(s, a) (stepped critic) -> d(-mean q)/da -> backward through the actor
+// with activations in shared memory ([feature][row] layout, so a thread's R row values are one
+// 16/32-byte broadcast load) and weights streamed from L2 with coalesced 16-byte loads.  The
+// forward uses a transposed copy Wt[in][out] of every weight (maintained by the Adam / Polyak
+// kernels), the input-gradient pass uses W[out][in] as stored: in both the reduction index is the
+// row index of the matrix, so one routine serves both.  Warps split the reduction range
+// (K-split) and combine in shared memory in a fixed order -> deterministic.
+// The kernels leave the per-layer activations and pre-activation gradients in global memory; the
+// weight-gradient GEMMs of all layers then run as ONE multi-problem launch (mlp.cu).
+// Launches per update: 57 -> 9.
+#include <algorithm>
+
+#include "mlp.cuh"
+
+namespace gcrl {
+
+constexpr int kFusedThreads = 512;
+constexpr int kFusedWarps = kFusedThreads / 32;
+
+enum : int { EPI_BIAS_LEAKY = 0, EPI_DLEAKY = 1 };
+
+template <int R>
+struct RowVec {
+  float v[R];
+};
+
+template <int R>
+__device__ __forceinline__ void load_rows(const float *p, float (&x)[R]) {
+  const float4 *q = reinterpret_cast<const float4 *>(p);
+#pragma unroll
+  for (int i = 0; i < R / 4; ++i) {
+    const float4 t = q[i];
+    x[4 * i] = t.x; x[4 * i + 1] = t.y; x[4 * i + 2] = t.z; x[4 * i + 3] = t.w;
+  }
+}
+
+// yT[j][r] = epi( sum_i xT[i][r] * M[i * ldm + j] ),  i in [0, K), j in [0, N)
+//   EPI_BIAS_LEAKY: leaky(acc + bias[j])          (forward layer; M = Wt)
+//   EPI_DLEAKY    : acc * leaky'(refT[j][r])      (input gradient;  M = W)
+// xT, refT, yT: shared memory [feature][R]; red: shared scratch of 2048 * R floats.
+// All threads of the CTA must call; ends with a __syncthreads().
+template <int R, int EPI>
+__device__ __forceinline__ void slab_matmul(const float *xT, int K, const float *__restrict__ M, int ldm, int N,
+                                            const float *__restrict__ bias, const float *refT, float *yT,
+                                            float *red) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ngroups = (N + 3) >> 2;              // 4 adjacent output columns per thread
+  const int ncw = (ngroups + 31) >> 5;           // warps needed to cover the columns
+  const int ks_total = kFusedWarps / ncw;        // K-split factor
+  const int Np = ncw * 128;
+  const int cw = warp % ncw, ks = warp / ncw;
+  const int j0 = (cw * 32 + lane) * 4;
+  if (ks < ks_total) {
+    const int kc = (K + ks_total - 1) / ks_total;
+    const int kbeg = ks * kc, kend = min(K, kbeg + kc);
+    float acc[4][R];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[c][r] = 0.f;
+    if (j0 < N) {
+      const float *mp = M + size_t(kbeg) * ldm + j0;
+#pragma unroll 8
+      for (int i = kbeg; i < kend; ++i, mp += ldm) {
+        const float4 w = __ldg(reinterpret_cast<const float4 *>(mp));
+        float x[R];
+        load_rows<R>(xT + i * R, x);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          acc[0][r] = fmaf(w.x, x[r], acc[0][r]);
+          acc[1][r] = fmaf(w.y, x[r], acc[1][r]);
+          acc[2][r] = fmaf(w.z, x[r], acc[2][r]);
+          acc[3][r] = fmaf(w.w, x[r], acc[3][r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float4 *dst = reinterpret_cast<float4 *>(red + (size_t(ks) * Np + j0 + c) * R);
+#pragma unroll
+      for (int q = 0; q < R / 4; ++q)
+        dst[q] = make_float4(acc[c][4 * q], acc[c][4 * q + 1], acc[c][4 * q + 2], acc[c][4 * q + 3]);
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < N * R; e += kFusedThreads) {
+    const int j = e / R, r = e - j * R;
+    float s = red[size_t(j) * R + r];
+    for (int k2 = 1; k2 < ks_total; ++k2) s += red[(size_t(k2) * Np + j) * R + r];
+    if (EPI == EPI_BIAS_LEAKY) {
+      s += bias[j];
+      s = s > 0.f ? s : s * kLeakySlope;
+    } else {
+      s = refT[e] > 0.f ? s : s * kLeakySlope;
+    }
+    yT[e] = s;
+  }
+  __syncthreads();
+}
+
+// out[j][r] = f( sum_k hT[k][r] * Wh[j * ldw + k] + bh[j] ), j < nout <= 4: one warp per (j, r)
+template <int R>
+__device__ __forceinline__ void slab_head(const float *hT, int K, const float *__restrict__ Wh, int ldw,
+                                          const float *__restrict__ bh, int nout, bool tanh_out, float *out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int p = warp; p < nout * R; p += kFusedWarps) {
+    const int j = p / R, r = p - j * R;
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc = fmaf(hT[k * R + r], __ldg(Wh + size_t(j) * ldw + k), acc);
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) {
+      float v = acc + bh[j];
+      out[p] = tanh_out ? tanhf(v) : v;
+    }
+  }
+  __syncthreads();
+}
+
+// smem [feature][R] -> global [row0 + r][ld] (rows >= B skipped)
+template <int R>
+__device__ __forceinline__ void store_rows(const float *yT, int N, float *__restrict__ out, int ld, int row0,
+                                           int B) {
+  for (int e = threadIdx.x; e < N * R; e += kFusedThreads) {
+    const int r = e / N, j = e - r * N;
+    if (row0 + r < B) out[size_t(row0 + r) * ld + j] = yT[j * R + r];
+  }
+}
+
+// hidden stack of one network: in (K0 features) -> L layers; layer outputs go to hs[l] when
+// keep (all kept) else ping-pong between tmp0/tmp1.  Returns the last layer's buffer.
+template <int R>
+__device__ __forceinline__ const float *slab_forward(const FusedNet &n, int L, int H, const float *in, int K0,
+                                                     float *const *keep, float *tmp0, float *tmp1, float *red,
+                                                     float *const *gout, int ldh, int row0, int B) {
+  const float *x = in;
+  int K = K0;
+  for (int l = 0; l < L; ++l) {
+    float *y = keep ? keep[l] : ((l & 1) ? tmp1 : tmp0);
+    slab_matmul<R, EPI_BIAS_LEAKY>(x, K, n.Wt[l], n.ldt[l], H, n.b[l], nullptr, y, red);
+    if (gout) store_rows<R>(y, H, gout[l], ldh, row0, B);
+    x = y;
+    K = H;
+  }
+  return x;
+}
+
+struct SmemPlan {
+  float *xa, *xb, *t0, *t1, *red, *small;
+  float *keep1[kFusedMaxL], *keep2[kFusedMaxL];
+};
+
+template <int R>
+__device__ __forceinline__ SmemPlan carve(float *base, int KinP, int H, int L, bool two_keeps) {
+  SmemPlan p;
+  p.xa = base; base += KinP * R;
+  p.xb = base; base += KinP * R;
+  p.t0 = base; base += H * R;
+  p.t1 = base; base += H * R;
+  for (int l = 0; l < L; ++l) { p.keep1[l] = base; base += H * R; }
+  for (int l = 0; l < L; ++l) { p.keep2[l] = two_keeps ? base : nullptr; if (two_keeps) base += H * R; }
+  p.red = base; base += 2048 * R;
+  p.small = base;
+  return p;
+}
+
+size_t fused_smem_bytes(int R, int D, int A, int H, int L, bool two_keeps) {
+  const int KinP = (D + A + 3) & ~3;
+  size_t f = size_t(2) * KinP * R + size_t(2) * H * R + size_t(L) * H * R * (two_keeps ? 2 : 1) +
+             size_t(2048) * R + 16 * R;
+  return f * sizeof(float);
+}
+
+// ---------------------------------------------------------------------------------------------
+// critic phase
+// ---------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(kFusedThreads, 1) fused_critic_kernel(FusedCriticArgs a) {
+  extern __shared__ float4 fsm4[];
+  const int D = a.D, A = a.A, H = a.H, L = a.L, B = a.B;
+  const int KinP = (D + A + 3) & ~3;
+  SmemPlan sp = carve<R>(reinterpret_cast<float *>(fsm4), KinP, H, L, false);
+  float *x_ns = sp.xa, *x_sa = sp.xb;
+  float *qn = sp.small, *q = qn + R, *yv = q + R, *dzh = yv + R, *rr = dzh + R, *dd = rr + R;
+  float *anext = dd + R;                          // [A][R], A <= 4
+  const int row0 = blockIdx.x * R, tid = threadIdx.x;
+
+  // ---- 0. stage the slab's rows: x_ns = [s' | (a')], x_sa = [s | a]; also emit [s | a | 0] rows ----
+  for (int e = tid; e < KinP * R; e += kFusedThreads) {
+    const int k = e / R, r = e - k * R, row = row0 + r;
+    float vns = 0.f, vsa = 0.f;
+    if (row < B) {
+      if (k < D) { vns = a.ns[size_t(row) * D + k]; vsa = a.s[size_t(row) * D + k]; }
+      else if (k < D + A) vsa = a.a[size_t(row) * A + (k - D)];
+    }
+    x_ns[e] = vns;
+    x_sa[e] = vsa;
+  }
+  if (tid < R) {
+    const int row = row0 + tid;
+    rr[tid] = row < B ? a.r[row] : 0.f;
+    dd[tid] = row < B ? a.d[row] : 0.f;
+  }
+  __syncthreads();
+  if (a.sa_out != nullptr) {
+    for (int e = tid; e < a.ldc * R; e += kFusedThreads) {
+      const int r = e / a.ldc, k = e - r * a.ldc;
+      if (row0 + r < B) a.sa_out[size_t(row0 + r) * a.ldc + k] = k < KinP ? x_sa[k * R + r] : 0.f;
+    }
+  }
+
+  // ---- 1. a' = target_actor(s') (:1312) ----
+  const float *h = slab_forward<R>(a.ta, L, H, x_ns, D, nullptr, sp.t0, sp.t1, sp.red, nullptr, 0, row0, B);
+  slab_head<R>(h, H, a.ta.Wh, a.ta.ldwh, a.ta.bh, A, true, anext);
+  for (int e = tid; e < A * R; e += kFusedThreads) x_ns[D * R + e] = anext[e];
+  __syncthreads();
+  // ---- 2. q' = target_critic([s', a']) (:1313-1315) ----
+  h = slab_forward<R>(a.tc, L, H, x_ns, D + A, nullptr, sp.t0, sp.t1, sp.red, nullptr, 0, row0, B);
+  slab_head<R>(h, H, a.tc.Wh, a.tc.ldwh, a.tc.bh, 1, false, qn);
+  // ---- 3. q = critic([s, a]) (:1319), activations kept for the backward pass ----
+  h = slab_forward<R>(a.c, L, H, x_sa, D + A, sp.keep1, nullptr, nullptr, sp.red, a.h_out, a.ldh, row0, B);
+  slab_head<R>(h, H, a.c.Wh, a.c.ldwh, a.c.bh, 1, false, q);
+  // ---- 4. Bellman target, loss, dL/dq (:1316-1326) ----
+  if (tid == 0) {
+    float ls = 0.f, ts = 0.f, qs = 0.f;
+    const float invB = 1.0f / float(B);
+    for (int r = 0; r < R; ++r) {
+      const int row = row0 + r;
+      float g = 0.f;
+      if (row < B) {
+        float y = rr[r] + a.gamma * (1.0f - dd[r]) * qn[r];
+        if (a.clamp_y) y = fminf(fmaxf(y, a.y_lo), 0.0f);
+        const float diff = q[r] - y;
+        ls += diff * diff;
+        ts += fabsf(y - q[r]);
+        qs += q[r];
+        g = 2.0f * diff * invB;
+        a.dzh_out[row] = g;
+        if (a.y_out) a.y_out[row] = y;
+        if (a.q_out) a.q_out[row] = q[r];
+      }
+      dzh[r] = g;
+    }
+    float *mp = a.metric_partials + size_t(blockIdx.x) * 4;
+    mp[0] = ls; mp[1] = ts; mp[2] = qs; mp[3] = 0.f;
+  }
+  __syncthreads();
+  // ---- 5. backward through the critic: pre-activation gradients of every hidden layer ----
+  float *dz = sp.t0, *dzn = sp.t1;
+  for (int e = tid; e < H * R; e += kFusedThreads) {
+    const int k = e / R, r = e - k * R;
+    const float g = dzh[r] * __ldg(a.c.Wh + k);
+    dz[e] = sp.keep1[L - 1][e] > 0.f ? g : g * kLeakySlope;
+  }
+  __syncthreads();
+  store_rows<R>(dz, H, a.dz_out[L - 1], a.ldh, row0, B);
+  for (int l = L - 1; l >= 1; --l) {
+    slab_matmul<R, EPI_DLEAKY>(dz, H, a.c.W[l], a.c.ldw[l], H, nullptr, sp.keep1[l - 1], dzn, sp.red);
+    store_rows<R>(dzn, H, a.dz_out[l - 1], a.ldh, row0, B);
+    float *t = dz; dz = dzn; dzn = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// actor phase
+// ---------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(kFusedThreads, 1) fused_actor_kernel(FusedActorArgs a) {
+  extern __shared__ float4 fsm4[];
+  const int D = a.D, A = a.A, H = a.H, L = a.L, B = a.B;
+  const int KinP = (D + A + 3) & ~3;
+  SmemPlan sp = carve<R>(reinterpret_cast<float *>(fsm4), KinP, H, L, true);
+  float *x_sa = sp.xa;
+  float *q = sp.small, *act = q + R, *da = act + 4 * R;   // act, da: [A][R]
+  const int row0 = blockIdx.x * R, tid = threadIdx.x;
+
+  for (int e = tid; e < KinP * R; e += kFusedThreads) {
+    const int k = e / R, r = e - k * R, row = row0 + r;
+    x_sa[e] = (row < B && k < D) ? a.s[size_t(row) * D + k] : 0.f;
+  }
+  __syncthreads();
+  // ---- a = actor(s) (:1289); hidden activations kept (smem) and emitted (global, for wgrad) ----
+  const float *h = slab_forward<R>(a.actor, L, H, x_sa, D, sp.keep1, nullptr, nullptr, sp.red, a.h_out, a.ldh,
+                                   row0, B);
+  slab_head<R>(h, H, a.actor.Wh, a.actor.ldwh, a.actor.bh, A, true, act);
+  for (int e = tid; e < A * R; e += kFusedThreads) x_sa[D * R + e] = act[e];
+  __syncthreads();
+  // ---- q = critic([s, a]) with the stepped critic (:1290) ----
+  h = slab_forward<R>(a.c, L, H, x_sa, D + A, sp.keep2, nullptr, nullptr, sp.red, nullptr, 0, row0, B);
+  slab_head<R>(h, H, a.c.Wh, a.c.ldwh, a.c.bh, 1, false, q);
+  if (tid == 0) {
+    float qs = 0.f;
+    for (int r = 0; r < R; ++r)
+      if (row0 + r < B) qs += q[r];
+    float *mp = a.metric_partials + size_t(blockIdx.x) * 4;
+    mp[0] = -qs; mp[1] = 0.f; mp[2] = qs; mp[3] = 0.f;     // actor loss = -mean(q) (:1291)
+  }
+  // ---- d(-mean q) / d(critic hidden), down to the critic's first layer ----
+  const float invB = 1.0f / float(B);
+  float *dz = sp.t0, *dzn = sp.t1;
+  for (int e = tid; e < H * R; e += kFusedThreads) {
+    const int k = e / R, r = e - k * R;
+    const float g = (row0 + r < B) ? -invB * __ldg(a.c.Wh + k) : 0.f;
+    dz[e] = sp.keep2[L - 1][e] > 0.f ? g : g * kLeakySlope;
+  }
+  __syncthreads();
+  for (int l = L - 1; l >= 1; --l) {
+    slab_matmul<R, EPI_DLEAKY>(dz, H, a.c.W[l], a.c.ldw[l], H, nullptr, sp.keep2[l - 1], dzn, sp.red);
+    float *t = dz; dz = dzn; dzn = t;
+  }
+  // ---- dq/da through the critic's first layer (action columns), times tanh' ----
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int p = warp; p < A * R; p += kFusedWarps) {
+      const int j = p / R, r = p - j * R;
+      float acc = 0.f;
+      for (int n = lane; n < H; n += 32) acc = fmaf(dz[n * R + r], __ldg(a.c.W[0] + size_t(n) * a.c.ldw[0] + D + j), acc);
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+      if (lane == 0) {
+        const float t = act[p];
+        const float v = acc * (1.0f - t * t);
+        da[p] = v;
+        if (row0 + r < B) a.da_out[size_t(row0 + r) * 4 + j] = v;
+      }
+    }
+    for (int p = tid; p < R; p += kFusedThreads)               // zero the unused head columns
+      for (int j = A; j < 4; ++j)
+        if (row0 + p < B) a.da_out[size_t(row0 + p) * 4 + j] = 0.f;
+  }
+  __syncthreads();
+  // ---- backward through the actor head and hidden stack ----
+  for (int e = tid; e < H * R; e += kFusedThreads) {
+    const int k = e / R, r = e - k * R;
+    float g = 0.f;
+    for (int j = 0; j < A; ++j) g = fmaf(da[j * R + r], __ldg(a.actor.Wh + size_t(j) * a.actor.ldwh + k), g);
+    dzn[e] = sp.keep1[L - 1][e] > 0.f ? g : g * kLeakySlope;
+  }
+  __syncthreads();
+  { float *t = dz; dz = dzn; dzn = t; }
+  store_rows<R>(dz, H, a.dz_out[L - 1], a.ldh, row0, B);
+  for (int l = L - 1; l >= 1; --l) {
+    slab_matmul<R, EPI_DLEAKY>(dz, H, a.actor.W[l], a.actor.ldw[l], H, nullptr, sp.keep1[l - 1], dzn, sp.red);
+    store_rows<R>(dzn, H, a.dz_out[l - 1], a.ldh, row0, B);
+    float *t = dz; dz = dzn; dzn = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+static int g_fused_smem_set[2][2] = {{0, 0}, {0, 0}};
+
+template <typename K>
+static void ensure_smem(K kernel, size_t bytes, int *flag) {
+  if (*flag < int(bytes)) {
+    GCRL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
+    *flag = int(bytes);
+  }
+}
+
+int fused_rows_per_cta(int B) { return B <= 512 ? 4 : 8; }
+
+bool fused_supported(int B, int D, int A, int H, int L) {
+  if (B < 1 || B > 1024 || L < 1 || L > kFusedMaxL || A > 4 || H < 4 || H > 2048) return false;
+  const int R = fused_rows_per_cta(B);
+  if ((B + R - 1) / R > 256) return false;
+  return fused_smem_bytes(R, D, A, H, L, true) <= size_t(200) * 1024;
+}
+
+int launch_fused_critic(const FusedCriticArgs &a, cudaStream_t st) {
+  const int R = fused_rows_per_cta(a.B);
+  const int grid = (a.B + R - 1) / R;
+  const size_t smem = fused_smem_bytes(R, a.D, a.A, a.H, a.L, false);
+  if (R == 4) {
+    ensure_smem(fused_critic_kernel<4>, smem, &g_fused_smem_set[0][0]);
+    fused_critic_kernel<4><<<grid, kFusedThreads, smem, st>>>(a);
+  } else {
+    ensure_smem(fused_critic_kernel<8>, smem, &g_fused_smem_set[0][1]);
+    fused_critic_kernel<8><<<grid, kFusedThreads, smem, st>>>(a);
+  }
+  GCRL_LAUNCHED();
+  return grid;
+}
+
+int launch_fused_actor(const FusedActorArgs &a, cudaStream_t st) {
+  const int R = fused_rows_per_cta(a.B);
+  const int grid = (a.B + R - 1) / R;
+  const size_t smem = fused_smem_bytes(R, a.D, a.A, a.H, a.L, true);
+  if (R == 4) {
+    ensure_smem(fused_actor_kernel<4>, smem, &g_fused_smem_set[1][0]);
+    fused_actor_kernel<4><<<grid, kFusedThreads, smem, st>>>(a);
+  } else {
+    ensure_smem(fused_actor_kernel<8>, smem, &g_fused_smem_set[1][1]);
+    fused_actor_kernel<8><<<grid, kFusedThreads, smem, st>>>(a);
+  }
+  GCRL_LAUNCHED();
+  return grid;
+}
+
+}  // namespace gcrl

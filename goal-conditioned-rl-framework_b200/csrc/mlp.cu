@@ -105,7 +105,7 @@ __device__ __forceinline__ void store_ic(float (*S)[BT + SPAD], const float4 (&r
 //   OP_WGRAD: A = dZ (IC),  B = X  (IC),  reduction = batch, split over blockIdx.z; the CTAs
 //             of the first tile column also emit the bias gradient (column sums of dZ)
 template <int BM, int BN, int TM, int TN, int OP>
-__global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(GemmParams p) {
+__device__ __forceinline__ void gemm_body(const GemmParams &p, const int bx, const int by, const int bz) {
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int TXN = BN / TN;
   static_assert((BM * 4) % NT == 0 && (BN * 4) % NT == 0, "tile/threads mismatch");
@@ -116,10 +116,10 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(GemmParams 
 
   const int tid = threadIdx.x;
   const int tx = tid % TXN, ty = tid / TXN;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int m0 = by * BM, n0 = bx * BN;
   int rbeg = 0, rend = p.K;
   if (OP == OP_WGRAD) {
-    rbeg = blockIdx.z * p.k_chunk;
+    rbeg = bz * p.k_chunk;
     rend = min(p.K, rbeg + p.k_chunk);
   }
   const int nk = (rend - rbeg + BK - 1) / BK;
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(GemmParams 
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
-    if (OP == OP_WGRAD && blockIdx.x == 0 && tid < BM) {
+    if (OP == OP_WGRAD && bx == 0 && tid < BM) {
 #pragma unroll
       for (int k = 0; k < BK; ++k) bsum += As[buf][k][tid];
     }
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(GemmParams 
 
   // ---- epilogue ----
   float *C = p.C;
-  if (OP == OP_WGRAD) C += int64_t(blockIdx.z) * p.c_split_stride;
+  if (OP == OP_WGRAD) C += int64_t(bz) * p.c_split_stride;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int m = m0 + ((TM == 8 && i >= 4) ? (BM / 2 + ty * 4 + i - 4) : (ty * 4 + i));
@@ -225,8 +225,60 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(GemmParams 
       }
     }
   }
-  if (OP == OP_WGRAD && blockIdx.x == 0 && tid < BM && m0 + tid < p.M)
-    p.Cb[int64_t(blockIdx.z) * p.cb_split_stride + m0 + tid] = bsum;
+  if (OP == OP_WGRAD && bx == 0 && tid < BM && m0 + tid < p.M)
+    p.Cb[int64_t(bz) * p.cb_split_stride + m0 + tid] = bsum;
+}
+
+template <int BM, int BN, int TM, int TN, int OP>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(GemmParams p) {
+  gemm_body<BM, BN, TM, TN, OP>(p, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// Multi-problem weight-gradient launch: blockIdx.x enumerates the output tiles of all problems,
+// blockIdx.z the batch slabs.
+struct MultiGemm {
+  GemmParams p[kMaxWgradProblems];
+  int tile_begin[kMaxWgradProblems + 1];
+  int tiles_x[kMaxWgradProblems];
+  int nprob;
+};
+
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) multi_wgrad_kernel(MultiGemm mg) {
+  int i = 0;
+  while (i + 1 < mg.nprob && int(blockIdx.x) >= mg.tile_begin[i + 1]) ++i;
+  const int local = blockIdx.x - mg.tile_begin[i];
+  const int bx = local % mg.tiles_x[i], by = local / mg.tiles_x[i];
+  gemm_body<BM, BN, TM, TN, OP_WGRAD>(mg.p[i], bx, by, blockIdx.z);
+}
+
+int launch_multi_wgrad(const WgradProblem *probs, int nprob, int M, int64_t split_stride, int max_splits,
+                       cudaStream_t st) {
+  GCRL_REQUIRE(nprob >= 1 && nprob <= kMaxWgradProblems, "too many wgrad problems");
+  int splits = std::max(1, std::min(max_splits, M / 64));
+  int chunk = (M + splits - 1) / splits;
+  chunk = (chunk + BK - 1) / BK * BK;
+  splits = (M + chunk - 1) / chunk;
+  MultiGemm mg{};
+  mg.nprob = nprob;
+  int tiles = 0;
+  for (int i = 0; i < nprob; ++i) {
+    GemmParams &p = mg.p[i];
+    p.A = probs[i].dZ; p.lda = probs[i].lddz; p.B = probs[i].X; p.ldb = probs[i].ldx;
+    p.C = probs[i].pW; p.ldc = probs[i].ldw; p.Cb = probs[i].pB;
+    p.M = probs[i].N; p.N = probs[i].K; p.K = M;
+    p.k_chunk = chunk;
+    p.c_split_stride = split_stride;
+    p.cb_split_stride = split_stride;
+    mg.tile_begin[i] = tiles;
+    mg.tiles_x[i] = (p.N + 31) / 32;
+    tiles += mg.tiles_x[i] * ((p.M + 31) / 32);
+  }
+  mg.tile_begin[nprob] = tiles;
+  dim3 grid(tiles, 1, splits);
+  multi_wgrad_kernel<32, 32, 4, 4><<<grid, 64, 0, st>>>(mg);
+  GCRL_LAUNCHED();
+  return splits;
 }
 
 template <int OP>

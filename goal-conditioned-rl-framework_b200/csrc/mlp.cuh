@@ -60,6 +60,54 @@ void launch_action_grad(const float *dZ1, int lddz, const float *W1, int ldw, co
 void launch_pack_rows(const float *s, int D, const float *a, int A, float *out, int ldo, int M,
                       cudaStream_t st);
 
+// All weight gradients of one network in ONE launch (multi-problem split-batch GEMM):
+//   problem i: pW_i[s][N_i][ldw_i] = sum_{m in slab s} dZ_i[m,n] * X_i[m,k]  (+ bias partials)
+struct WgradProblem {
+  const float *dZ; int lddz;
+  const float *X; int ldx;
+  float *pW; int ldw;
+  float *pB;
+  int N, K;          // layer output / input widths
+};
+constexpr int kMaxWgradProblems = 8;
+// Returns the number of batch slabs S (same for every problem).
+int launch_multi_wgrad(const WgradProblem *probs, int nprob, int M, int64_t split_stride, int max_splits,
+                       cudaStream_t st);
+
+// ---- row-slab fused update kernels (fused.cu) -----------------------------------------------
+constexpr int kFusedMaxL = 6;
+struct FusedNet {               // hidden layers 0..L-1 and the output head of one MLP
+  const float *Wt[kFusedMaxL];  // transposed weights [in][ldt]   (forward)
+  const float *W[kFusedMaxL];   // weights as stored  [out][ldw]  (input gradient)
+  const float *b[kFusedMaxL];
+  int ldt[kFusedMaxL], ldw[kFusedMaxL];
+  const float *Wh, *bh;         // head [nout][ldwh]
+  int ldwh;
+};
+struct FusedCriticArgs {
+  FusedNet ta, tc, c;           // target actor, target critic, critic
+  const float *s, *a, *r, *ns, *d;   // dense batch
+  int B, D, A, H, L, ldh, ldc;
+  float gamma, y_lo; int clamp_y;
+  float *sa_out;                // [B][ldc]  = [s | a | 0] rows (layer-1 wgrad operand)
+  float *h_out[kFusedMaxL];     // critic hidden activations [B][ldh]
+  float *dz_out[kFusedMaxL];    // critic pre-activation gradients [B][ldh]
+  float *dzh_out, *y_out, *q_out;   // [B]
+  float *metric_partials;       // [grid][4]
+};
+struct FusedActorArgs {
+  FusedNet actor, c;
+  const float *s;
+  int B, D, A, H, L, ldh;
+  float *h_out[kFusedMaxL];     // actor hidden activations
+  float *dz_out[kFusedMaxL];    // actor pre-activation gradients
+  float *da_out;                // [B][4] gradient at the actor head's pre-activation
+  float *metric_partials;
+};
+bool fused_supported(int B, int D, int A, int H, int L);
+int launch_fused_critic(const FusedCriticArgs &a, cudaStream_t st);   // returns the grid (metric slabs)
+int launch_fused_actor(const FusedActorArgs &a, cudaStream_t st);
+
 // ---- optimiser (optim.cu) --------------------------------------------------------------
 struct SegDesc {          // one parameter segment of a flat network buffer
   int begin, count;       // [begin, begin+count) in the flat buffer
@@ -94,10 +142,15 @@ struct AdamArgs {
   const StepScalars *sc; int which;   // 0: critic scalars, 1: actor scalars
   float *target; float tau, one_minus_tau; int polyak;   // fused Polyak of `target` with the NEW p
   float *metrics; int slot_norm;
+  // transposed weight copies kept in step with p / target (fused.cu's forward operand)
+  const int *tmap;         // [n] index into pT, or -1 (bias / padding)
+  float *pT, *targetT;
 };
 void launch_adam(const AdamArgs &a, cudaStream_t st);
 void launch_polyak(float *target, const float *src, int n, float tau, float one_minus_tau,
-                   cudaStream_t st);
+                   const int *tmap, float *targetT, cudaStream_t st);
+// pT[tmap[e]] = p[e] for every weight element
+void launch_sync_transposed(const float *p, float *pT, const int *tmap, int n, cudaStream_t st);
 
 // one launch: dense (s, a, r, ns, d) -> sa = [s|a|0], nsa = [ns|0], spi = [s|0], r, d copies
 void launch_ingest_batch(const float *s, const float *a, const float *r, const float *ns, const float *d,

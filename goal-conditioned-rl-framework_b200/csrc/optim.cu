@@ -110,7 +110,13 @@ __global__ void __launch_bounds__(kOptThreads) adam_kernel(AdamArgs a) {
     a.m[e] = m;
     a.v[e] = v;
     a.p[e] = p;
-    if (a.polyak) a.target[e] = a.tau * p + a.one_minus_tau * a.target[e];
+    const int tm = a.tmap != nullptr ? a.tmap[e] : -1;
+    if (tm >= 0) a.pT[tm] = p;
+    if (a.polyak) {
+      const float t = a.tau * p + a.one_minus_tau * a.target[e];
+      a.target[e] = t;
+      if (tm >= 0) a.targetT[tm] = t;
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && a.metrics != nullptr && a.slot_norm >= 0)
     a.metrics[a.slot_norm] = s_norm * coef;  // norm after clipping (src/agent.py:1332,:1300)
@@ -122,14 +128,34 @@ void launch_adam(const AdamArgs &a, cudaStream_t st) {
 }
 
 __global__ void __launch_bounds__(kOptThreads)
-polyak_kernel(float *__restrict__ target, const float *__restrict__ src, int n, float tau, float omt) {
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
-    target[e] = tau * src[e] + omt * target[e];
+polyak_kernel(float *__restrict__ target, const float *__restrict__ src, int n, float tau, float omt,
+              const int *__restrict__ tmap, float *__restrict__ targetT) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const float t = tau * src[e] + omt * target[e];
+    target[e] = t;
+    if (tmap != nullptr) {
+      const int tm = tmap[e];
+      if (tm >= 0) targetT[tm] = t;
+    }
+  }
 }
 
 void launch_polyak(float *target, const float *src, int n, float tau, float one_minus_tau,
-                   cudaStream_t st) {
-  polyak_kernel<<<reduce_grid(n), kOptThreads, 0, st>>>(target, src, n, tau, one_minus_tau);
+                   const int *tmap, float *targetT, cudaStream_t st) {
+  polyak_kernel<<<reduce_grid(n), kOptThreads, 0, st>>>(target, src, n, tau, one_minus_tau, tmap, targetT);
+  GCRL_LAUNCHED();
+}
+
+__global__ void __launch_bounds__(kOptThreads)
+sync_transposed_kernel(const float *__restrict__ p, float *__restrict__ pT, const int *__restrict__ tmap, int n) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int tm = tmap[e];
+    if (tm >= 0) pT[tm] = p[e];
+  }
+}
+
+void launch_sync_transposed(const float *p, float *pT, const int *tmap, int n, cudaStream_t st) {
+  sync_transposed_kernel<<<reduce_grid(n), kOptThreads, 0, st>>>(p, pT, tmap, n);
   GCRL_LAUNCHED();
 }
 

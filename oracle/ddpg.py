@@ -201,6 +201,8 @@ class DDPGOracle:
                                               critic_lr if critic_lr_min is None else critic_lr_min)
         self.gamma, self.tau, self.grad_clip = gamma, tau, grad_clip
         self.ac_update_freq = ac_update_freq
+        self.flip_delta = 0.0            # > 0: actor_update also evaluates _actor_flip_slack
+        self.last_actor_flip_slack = 0.0
 
     # src/agent.py:1302-1343
     def critic_update(self, s, a, r, ns, d):
@@ -235,12 +237,50 @@ class DDPGOracle:
         _, d_in = mlp_backward(self.critic, c_acts, dq, final_tanh=False, need_input_grad=True)
         d_a = d_in[:, s.shape[1]:]
         grads, _ = mlp_backward(self.actor, a_acts, d_a, final_tanh=True)
+        if self.flip_delta:
+            self.last_actor_flip_slack = self._actor_flip_slack(s, a_acts, c_acts, dq, grads)
         if self.grad_clip is not None:
             clip_grad_norm_(grads, self.grad_clip)
         self.actor_opt.step(self.actor, grads, self.actor_sched.lr)
         self.actor_sched.step()
         self.last_actor_grads = grads
         return loss, grad_norm_python(grads)
+
+    def _actor_flip_slack(self, s, a_acts, c_acts, dq, grads):
+        """Conditioning of the actor gradient norm (test tolerance, not reference behaviour).
+
+        LeakyReLU' is discontinuous at 0: a hidden pre-activation that is zero to within fp32
+        rounding (|z| < flip_delta, a few ulps of the O(1) terms summed) takes slope 1 or 0.01 depending on summation order, and the
+        gradient jumps by a finite amount.  For every such unit of the actor-phase forward
+        passes, recompute the (pre-clip) gradient norm with that unit's sign flipped; the sum of
+        the absolute changes bounds what any correctly rounded fp32 implementation may deviate
+        by on this batch.  Returns that bound relative to the norm (0.0 when no unit is
+        near zero)."""
+        base = grad_norm_python(grads)
+        slack = 0.0
+        D = s.shape[1]
+
+        def row_grads(a_row, c_row, r_):
+            _, d_in = mlp_backward(self.critic, c_row, dq[r_:r_ + 1], final_tanh=False, need_input_grad=True)
+            g, _ = mlp_backward(self.actor, a_row, d_in[:, D:], final_tanh=True)
+            return g
+
+        for which, acts in (("actor", a_acts), ("critic", c_acts)):
+            for li in range(1, len(acts) - 1):
+                h = acts[li]      # post-activation: z for z > 0, 0.01 z otherwise
+                rows, units = np.nonzero(np.abs(np.where(h > 0, h, h / LEAKY_SLOPE)) < self.flip_delta)
+                for r_, u_ in zip(rows, units):
+                    # only row r_'s contribution to the batch-summed gradient changes
+                    a_row = [x[r_:r_ + 1].copy() for x in a_acts]
+                    c_row = [x[r_:r_ + 1].copy() for x in c_acts]
+                    g_old = row_grads(a_row, c_row, r_)
+                    tgt = a_row if which == "actor" else c_row
+                    tgt[li][0, u_] = F32(-1e-30) if tgt[li][0, u_] > 0 else F32(1e-30)
+                    g_new = row_grads(a_row, c_row, r_)
+                    g2 = [[w + (nw - ow), b + (nb - ob)]
+                          for (w, b), (nw, nb), (ow, ob) in zip(grads, g_new, g_old)]
+                    slack += abs(grad_norm_python(g2) - base)
+        return slack / max(base, 1e-30)
 
     # src/agent.py:1255-1271
     def soft_update(self, tau):

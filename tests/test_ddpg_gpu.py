@@ -91,6 +91,8 @@ def test_update_matches_oracle_odd_shapes(B, H, L, D, A):
     ag.update_target_network()
     orc = OD.DDPGOracle(actor0, critic0, gamma=cfg.gamma, tau=cfg.tau, grad_clip=cfg.grad_clip,
                         actor_lr=cfg.actor_lr, critic_lr=cfg.critic_lr)
+    orc.flip_delta = 5e-6
+    slack_total = 0.0
     for si, step in enumerate((39, 40, 41, 42)):
         s = rng.standard_normal((B, D)).astype(np.float32)
         ns = (s + 0.1 * rng.standard_normal((B, D))).astype(np.float32)
@@ -101,12 +103,24 @@ def test_update_matches_oracle_odd_shapes(B, H, L, D, A):
         got = ag.update(step, batch=tuple(torch.from_numpy(x).cuda() for x in (s, a, r, ns, d)))
         # batch means / gradient norms are fp32 sums over B terms evaluated in a different order than
         # BLAS: the summation-order noise grows like sqrt(B) (rel 5e-5 at B <= 256)
-        rtol = 5e-5 * max(1.0, (B / 256.0) ** 0.5)
-        np.testing.assert_allclose(np.array([float(x) for x in got]), np.array(want), rtol=rtol, atol=2e-6)
-    for net, ref in ((ag.actor, orc.actor), (ag.critic, orc.critic),
-                     (ag.target_actor, orc.target_actor), (ag.target_critic, orc.target_critic)):
+        rtol = np.full(6, 5e-5 * max(1.0, (B / 256.0) ** 0.5))
+        # actor gradient norm: plus the oracle's own bound for hidden units whose pre-activation
+        # is zero to fp32 rounding (LeakyReLU' jumps there; oracle/ddpg.py::_actor_flip_slack)
+        rtol[5] += orc.last_actor_flip_slack
+        slack_total += orc.last_actor_flip_slack
+        got, want = np.array([float(x) for x in got]), np.array(want)
+        assert np.all(np.abs(got - want) <= rtol * np.abs(want) + 2e-6), (step, got, want, rtol)
+    # A LeakyReLU sign flip changes one batch row's whole gradient contribution, i.e. a dense
+    # low-rank perturbation (~1e-3 relative) that Adam's per-element normalisation amplifies for the
+    # small-gradient elements: when the oracle saw such units the bulk criterion is applied to 95 %
+    # of the actor's elements instead of 99.98 %; the hard bound 2 lr nsteps always holds.
+    frac = {True: 0.05, False: 2e-4}
+    for net, ref, flipped in ((ag.actor, orc.actor, slack_total > 0), (ag.critic, orc.critic, False),
+                              (ag.target_actor, orc.target_actor, slack_total > 0),
+                              (ag.target_critic, orc.target_critic, False)):
         for (w, b), (rw, rb) in zip(net.layers(), ref):
-            assert weights_close(w, rw, 1e-3, 4) and weights_close(b, rb, 1e-3, 4)
+            assert weights_close(w, rw, 1e-3, 4, outlier_frac=frac[flipped])
+            assert weights_close(b, rb, 1e-3, 4, outlier_frac=frac[flipped])
 
 
 def test_checkpoint_load_and_forward_matches_reference():
