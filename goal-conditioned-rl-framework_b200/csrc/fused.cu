@@ -17,6 +17,7 @@
 // weight-gradient GEMMs of all layers then run as ONE multi-problem launch (mlp.cu).
 // Launches per update: 57 -> 9.
 #include <algorithm>
+#include <cstdlib>
 
 #include "mlp.cuh"
 
@@ -367,7 +368,10 @@ static void ensure_smem(K kernel, size_t bytes, int *flag) {
   }
 }
 
-int fused_rows_per_cta(int B) { return B <= 512 ? 4 : 8; }
+int fused_rows_per_cta(int B) {
+  if (const char *e = getenv("GCRL_FUSED_R")) return atoi(e);
+  return B <= 512 ? 4 : 8;
+}
 
 bool fused_supported(int B, int D, int A, int H, int L) {
   if (B < 1 || B > 1024 || L < 1 || L > kFusedMaxL || A > 4 || H < 4 || H > 2048) return false;
