@@ -326,6 +326,98 @@ def td3_case(agent_mod, utils_mod, name, *, D, A, H, L, B, steps, seed, gamma=0.
     print(f"td3_{name}: {len(steps)} steps; last info {out[f's{len(steps) - 1}_info']}")
 
 
+def sac_case(agent_mod, utils_mod, algo, name, *, D, A, H, L, B, steps, seed, gamma=0.98, tau=0.05,
+             grad_clip=1.0, lr=1e-3, alpha_lr=3e-4, alpha_min_steps=2, gradient_step=2, ac_update_freq=1):
+    """Unmodified reference SACAgent / TQCAgent.update on explicit batches; every standard-normal
+    draw behind ``Normal.rsample`` (src/model.py:134) is recorded: one for the next-state sample in
+    critic_update, one for the state sample in actor_update."""
+    import torch
+    import torch.distributions.normal as tdn
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import ddpg as O
+    from oracle import sac as OS
+    torch.set_num_threads(1)
+    cfg = utils_mod.SACAgentConfig(
+        hidden_dim=H, layer_count=L, actor_lr=lr, actor_lr_min=lr, ac_scheduler_steps=1, critic_lr=lr,
+        critic_lr_min=lr, cr_scheduler_steps=1, buffer_type="HER", max_len=1000, alpha=1.0, batch_size=B,
+        gamma=gamma, ac_update_freq=ac_update_freq, noise_std=0.2, noise_clamp=0.5, policy_noise=0.2,
+        grad_clip=grad_clip, beta=1.0, beta_end=1, k_future=4, max_eps_len=50, tau=tau, alpha_lr=alpha_lr,
+        alpha_min_steps=alpha_min_steps)
+    cls = agent_mod.SACAgent if algo == "sac" else agent_mod.TQCAgent
+    ag = cls(obs_dim=D, ac_dim=A, config=cfg, weights=None, nenvs=1, gradient_step=gradient_step)
+    ag.device = "cpu"
+    rng = np.random.default_rng(seed)
+    n = 2 if algo == "sac" else 5
+    actor0, _ = OS.init_sac_actor(rng, D, H, A, L, head_scale=0.1, log_std_bias=-1.0)
+    critics0 = [O.init_mlp(rng, D + A, H, 1, L) for _ in range(n)]
+    critics = [ag.critic_1, ag.critic_2] if algo == "sac" else list(ag.critics)
+    with torch.no_grad():
+        sd = ag.actor.state_dict()
+        for l in range(L):
+            sd[f"base_net.{3 * l}.weight"].copy_(torch.from_numpy(actor0[2 * l][0]))
+            sd[f"base_net.{3 * l}.bias"].copy_(torch.from_numpy(actor0[2 * l][1]))
+        sd["mean_head.weight"].copy_(torch.from_numpy(actor0[2 * L][0]))
+        sd["mean_head.bias"].copy_(torch.from_numpy(actor0[2 * L][1]))
+        sd["log_std_head.weight"].copy_(torch.from_numpy(actor0[2 * L + 1][0]))
+        sd["log_std_head.bias"].copy_(torch.from_numpy(actor0[2 * L + 1][1]))
+        for c, p0 in zip(critics, critics0):
+            sd = c.state_dict()
+            for i, (w, b) in enumerate(p0):
+                sd[f"net.{2 * i}.weight"].copy_(torch.from_numpy(w))
+                sd[f"net.{2 * i}.bias"].copy_(torch.from_numpy(b))
+    ag.update_target_network()
+    out = {"meta": np.array([D, A, H, L, B, seed, ac_update_freq, gradient_step, alpha_min_steps], np.int64),
+           "hp": np.array([gamma, tau, grad_clip, lr, alpha_lr], np.float64),
+           "steps": np.array(steps, np.int64)}
+    torch.manual_seed(seed)
+    real = tdn._standard_normal
+    for si, step in enumerate(steps):
+        s = rng.standard_normal((B, D)).astype(np.float32)
+        ns = (s + 0.1 * rng.standard_normal((B, D))).astype(np.float32)
+        a = rng.uniform(-1, 1, (B, A)).astype(np.float32)
+        r = -(rng.random((B, 1)) > 0.3).astype(np.float32)
+        d = (rng.random((B, 1)) < 0.1).astype(np.float32)
+        batch = tuple(torch.from_numpy(x) for x in (s, a, r, ns, d))
+        ag.buffer.sample = lambda bs, _b=batch: _b
+        drawn = []
+
+        def rec(*a_, **k_):
+            v = real(*a_, **k_)
+            drawn.append(v.numpy().copy())
+            return v
+
+        tdn._standard_normal = rec
+        try:
+            info = ag.update(step)
+        finally:
+            tdn._standard_normal = real
+        assert len(drawn) == (2 if step % ac_update_freq == 0 else 1), len(drawn)
+        for key, val in zip(("s", "a", "r", "ns", "d"), (s, a, r, ns, d)):
+            out[f"s{si}_batch_{key}"] = val
+        out[f"s{si}_eps_next"] = drawn[0]
+        out[f"s{si}_eps_cur"] = drawn[1] if len(drawn) > 1 else np.zeros_like(drawn[0])
+        out[f"s{si}_info"] = np.array([float(x) for x in info], np.float64)
+        out[f"s{si}_log_alpha"] = ag.log_alpha.detach().numpy().copy()
+        if si == len(steps) - 1:
+            tags = [("actor", ag.actor)]
+            if algo == "sac":
+                tags += [("critic_1", ag.critic_1), ("critic_2", ag.critic_2),
+                         ("target_critic_1", ag.target_critic_1), ("target_critic_2", ag.target_critic_2)]
+            else:
+                keep = (0, len(ag.critics) - 1)      # first and last critic keep the fixture small
+                tags += [(f"critic_{i}", c) for i, c in enumerate(ag.critics) if i in keep]
+                tags += [(f"target_critic_{i}", c) for i, c in enumerate(ag.target_critics) if i in keep]
+            for tag, net in tags:
+                for k_, v in flat_params(net).items():
+                    out[f"s{si}_{tag}.{k_}"] = v
+    # deterministic / eval-mode action (select_action(eval_action=True), running statistics)
+    x = rng.standard_normal((7, D)).astype(np.float32)
+    out["eval_x"] = x
+    out["eval_act"] = ag.select_action(x, eval_action=True)
+    np.savez_compressed(os.path.join(HERE, f"{algo}_{name}.npz"), **out)
+    print(f"{algo}_{name}: {len(steps)} steps; last info {out[f's{len(steps) - 1}_info']}")
+
+
 def checkpoint_case(model_mod):
     """Load-compat + forward-differential fixture from the shipped Reach checkpoint
     (resources/DDPG/reach/{actor,critic}.pth: H=64, D=10, A=3)."""
@@ -353,8 +445,21 @@ def checkpoint_case(model_mod):
     print("checkpoint_reach: D,H,A =", D, H, A)
 
 
+def sac_cases(agent_mod, utils_mod):
+    sac_case(agent_mod, utils_mod, "sac", "push_h64", D=22, A=3, H=64, L=3, B=128, steps=[1, 2, 3, 4, 5],
+             seed=31)
+    sac_case(agent_mod, utils_mod, "sac", "pickplace_h256", D=23, A=4, H=256, L=2, B=200, steps=[4, 5, 6],
+             seed=32, grad_clip=0.1, tau=0.005, ac_update_freq=2, gradient_step=3, alpha_min_steps=0)
+    sac_case(agent_mod, utils_mod, "tqc", "slide_h64", D=22, A=3, H=64, L=3, B=128, steps=[1, 2, 3, 4, 5],
+             seed=33)
+    sac_case(agent_mod, utils_mod, "tqc", "push_h256", D=22, A=3, H=256, L=3, B=256, steps=[9, 10, 11],
+             seed=34, grad_clip=0.5, tau=0.005, alpha_min_steps=0, alpha_lr=1e-2)
+
+
 def main():
     agent_mod, buffer_mod, model_mod, utils_mod = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "sac":
+        return sac_cases(agent_mod, utils_mod)
     td3_case(agent_mod, utils_mod, "push_h64", D=22, A=3, H=64, L=3, B=128, steps=[1, 2, 3, 4, 5], seed=21)
     td3_case(agent_mod, utils_mod, "pickplace_h256", D=23, A=4, H=256, L=2, B=200, steps=[7, 8, 9], seed=22,
              grad_clip=0.1, ac_update_freq=1, tau=0.005, policy_noise=0.3, noise_clamp=0.25)
@@ -382,6 +487,7 @@ def main():
               critic_lr=2e-3, critic_lr_min=5e-4, cr_T=2, ac_update_freq=2, gamma=0.95,
               grad_clip=0.05, tau=0.005, store_weights=False)
     checkpoint_case(model_mod)
+    sac_cases(agent_mod, utils_mod)
 
 
 if __name__ == "__main__":

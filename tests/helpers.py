@@ -7,6 +7,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 HER_CASES = ["reach_small", "push_evict", "pickplace_k8", "k0"]
 DDPG_CASES = ["reach_h64", "push_h256", "pickplace_l2_cosine"]
+SAC_CASES = [("sac", "push_h64"), ("sac", "pickplace_h256"), ("tqc", "slide_h64"), ("tqc", "push_h256")]
 
 
 def load(name):
@@ -60,3 +61,55 @@ def weights_close(w, ref, lr, nsteps, rtol=1e-5, outlier_frac=2e-4):
     if float(np.max(err)) > 2.0 * lr * nsteps + rtol * np.max(np.abs(ref)):
         return False
     return bool(np.count_nonzero(err > tol) <= outlier_frac * err.size)
+
+
+def sac_params_from_golden(g, si, tag):
+    """SACActorModel state_dict (src/model.py:100-116: base_net.{3l} Linear, base_net.{3l+1}
+    BatchNorm1d, mean_head, log_std_head) -> oracle layout; Critic -> list of [W, b]."""
+    pref = f"s{si}_{tag}."
+    if tag != "actor":
+        return ddpg_params_from_golden(g, si, tag)
+    L = len([k for k in g.files if k.startswith(pref + "base_net.") and k.endswith("running_mean")])
+    params, stats = [], []
+    for l in range(L):
+        params.append([g[f"{pref}base_net.{3 * l}.weight"], g[f"{pref}base_net.{3 * l}.bias"]])
+        params.append([g[f"{pref}base_net.{3 * l + 1}.weight"], g[f"{pref}base_net.{3 * l + 1}.bias"]])
+        stats.append([g[f"{pref}base_net.{3 * l + 1}.running_mean"], g[f"{pref}base_net.{3 * l + 1}.running_var"]])
+    params.append([g[pref + "mean_head.weight"], g[pref + "mean_head.bias"]])
+    params.append([g[pref + "log_std_head.weight"], g[pref + "log_std_head.bias"]])
+    return {"params": params, "stats": stats}
+
+
+def sac_initial_nets(algo, g):
+    """Seeded initial parameters exactly as tests/golden/make_golden.py::sac_case drew them."""
+    from oracle import ddpg as OD
+    from oracle import sac as OS
+    D, A, H, L, B, seed = (int(x) for x in g["meta"][:6])
+    rng = np.random.default_rng(seed)
+    actor0, stats0 = OS.init_sac_actor(rng, D, H, A, L, head_scale=0.1, log_std_bias=-1.0)
+    critics0 = [OD.init_mlp(rng, D + A, H, 1, L) for _ in range(2 if algo == "sac" else 5)]
+    return actor0, stats0, critics0
+
+
+def sac_oracle_from_golden(algo, g):
+    from oracle import sac as OS
+    D, A, H, L, B, seed, freq, gstep, amin = (int(x) for x in g["meta"])
+    gamma, tau, clip, lr, alpha_lr = (float(x) for x in g["hp"])
+    actor0, stats0, critics0 = sac_initial_nets(algo, g)
+    return OS.SACOracle(algo, actor0, stats0, critics0, act_dim=A, gamma=gamma, tau=tau, grad_clip=clip,
+                        actor_lr=lr, critic_lr=lr, alpha_lr=alpha_lr, alpha_min_steps=amin,
+                        gradient_step=gstep, ac_update_freq=freq)
+
+
+def assert_sac_actor_close(params, ref_params, lr, nsteps):
+    """SAC actor parameters in oracle layout.  The bias of a Linear that feeds BatchNorm has an
+    exactly-zero true gradient (the batch mean is subtracted again), so what reaches AdamW is pure
+    fp32 rounding noise, which Adam normalises to +-lr steps in a random direction: those biases
+    (which cannot change the network's output) are only held to Adam's hard bound."""
+    L = (len(params) - 2) // 2
+    for i, ((w, b), (rw, rb)) in enumerate(zip(params, ref_params)):
+        assert weights_close(w, rw, lr, nsteps), ("actor", i, rel_err(w, rw))
+        if i < 2 * L and i % 2 == 0:
+            assert float(np.max(np.abs(np.asarray(b, np.float64) - rb))) <= 2.0 * lr * nsteps + 1e-6, ("actor bias", i)
+        else:
+            assert weights_close(b, rb, lr, nsteps), ("actor", i, rel_err(b, rb))
