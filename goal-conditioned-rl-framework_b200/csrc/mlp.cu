@@ -408,10 +408,15 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs a, int rows_p
   for (int i = tid; i < nrows; i += blockDim.x) {
     const int m = r0 + i;
     if (a.mode == 0) {
-      float qt = a.qt1[m];
-      if (a.qt2 != nullptr) qt = fminf(qt, a.qt2[m]);
-      float y = a.r[m] + a.gamma * (1.0f - a.d[m]) * qt;
-      if (a.clamp_y) y = fminf(fmaxf(y, a.y_lo), 0.0f);
+      float y;
+      if (a.y_in != nullptr) {
+        y = a.y_in[m];
+      } else {
+        float qt = a.qt1[m];
+        if (a.qt2 != nullptr) qt = fminf(qt, a.qt2[m]);
+        y = a.r[m] + a.gamma * (1.0f - a.d[m]) * qt;
+        if (a.clamp_y) y = fminf(fmaxf(y, a.y_lo), 0.0f);
+      }
       if (a.y_out != nullptr) a.y_out[m] = y;
       const float q = a.q[m];
       const float diff = q - y;

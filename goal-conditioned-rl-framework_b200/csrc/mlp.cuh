@@ -37,6 +37,7 @@ struct HeadBwdArgs {
   // mode 2 (actor head): dz[m,n] given in dz_in[m*4+n]
   int mode, loss_kind, clamp_y, nout;
   const float *q, *qt1, *qt2, *r, *d, *dz_in;
+  const float *y_in;      // mode 0: Bellman target given per row (SAC / TQC) instead of built from qt1/qt2
   const float *q_other;   // TD3 critic 2: metrics use max(|q-y|, |q_other-y|) and (q+q_other)/2
   float gamma, y_lo;
   const float *Hact; int ldh;      // last hidden activation [M, K]
@@ -116,7 +117,7 @@ struct SegDesc {          // one parameter segment of a flat network buffer
   int64_t split_stride;
   int offset;             // offset of this segment inside a partial slab
 };
-constexpr int kMaxSegs = 16;
+constexpr int kMaxSegs = 32;
 struct ReduceArgs {
   SegDesc seg[kMaxSegs];
   int nseg, total;

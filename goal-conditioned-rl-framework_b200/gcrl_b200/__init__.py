@@ -10,6 +10,7 @@ from ._lib import GcrlError, lib, library_path  # noqa: F401
 from .buffer import HERBuffer  # noqa: F401
 from .normalizer import RunningNormalizer  # noqa: F401
 from .agent import DDPG, TD3Agent, CosineAnnealingLR  # noqa: F401
+from .sac import SACAgent, TQCAgent  # noqa: F401
 
-__all__ = ["HERBuffer", "RunningNormalizer", "DDPG", "TD3Agent", "GcrlError", "lib",
+__all__ = ["HERBuffer", "RunningNormalizer", "DDPG", "TD3Agent", "SACAgent", "TQCAgent", "GcrlError", "lib",
            "library_path", "CosineAnnealingLR"]

@@ -33,6 +33,14 @@ class AgentConfig(C.Structure):
                 ("weight_decay", c_f32), ("precision", c_i32), ("reserved", c_i32)]
 
 
+class SacConfig(C.Structure):
+    """struct gcrl_sac_config (include/gcrl_b200.h)."""
+    _fields_ = [("algo", c_i32), ("state_dim", c_i32), ("act_dim", c_i32), ("hidden_dim", c_i32),
+                ("layer_count", c_i32), ("max_batch", c_i32), ("n_critics", c_i32), ("drop_top", c_i32),
+                ("gamma", c_f32), ("tau", c_f32), ("grad_clip", c_f32), ("weight_decay", c_f32),
+                ("entropy_coef", c_f32), ("target_entropy", c_f32), ("alpha_lr", c_f32), ("reserved", c_i32)]
+
+
 # name -> (restype, argtypes); every symbol include/gcrl_b200.h declares
 SIGNATURES = {
     "gcrl_abi_version": (C.c_int, []),
@@ -77,6 +85,21 @@ SIGNATURES = {
                                          C.c_int, vp]),
     "gcrl_agent_grad_buffer": (C.c_int, [vp, C.c_int, pp, C.POINTER(c_i64)]),
     "gcrl_agent_metrics_buffer": (C.c_int, [vp, pp]),
+    # SAC / TQC
+    "gcrl_sac_create": (C.c_int, [pp, C.c_int, C.POINTER(SacConfig)]),
+    "gcrl_sac_destroy": (C.c_int, [vp]),
+    "gcrl_sac_set_actor_linear": (C.c_int, [vp, C.c_int, vp, vp, vp]),
+    "gcrl_sac_get_actor_linear": (C.c_int, [vp, C.c_int, vp, vp, vp]),
+    "gcrl_sac_set_actor_bn": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp]),
+    "gcrl_sac_get_actor_bn": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp]),
+    "gcrl_sac_set_critic_layer": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    "gcrl_sac_get_critic_layer": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    "gcrl_sac_hard_update": (C.c_int, [vp, vp]),
+    "gcrl_sac_set_log_alpha": (C.c_int, [vp, c_f32, vp]),
+    "gcrl_sac_get_log_alpha": (C.c_int, [vp, C.POINTER(c_f32), vp]),
+    "gcrl_sac_update_batch": (C.c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp, c_f64, c_f64, C.c_int, vp, vp]),
+    "gcrl_sac_update_from_buffer": (C.c_int, [vp, vp, c_i64, vp, vp, vp, c_f64, c_f64, C.c_int, vp, vp]),
+    "gcrl_sac_act": (C.c_int, [vp, c_i64, vp, vp, vp, vp]),
 }
 
 
@@ -91,7 +114,7 @@ def _load():
         fn = getattr(dll, name)          # AttributeError if the library lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if dll.gcrl_abi_version() != 1:
+    if dll.gcrl_abi_version() != 2:
         raise ImportError("libgcrl_b200.so ABI version mismatch")
     return dll
 

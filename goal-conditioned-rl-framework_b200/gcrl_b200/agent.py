@@ -116,6 +116,20 @@ class _AgentBase:
 
     def __init__(self, obs_dim, ac_dim, config, weights, nenvs, gradient_step, *,
                  index_source="host", device=0, max_batch=None, seed=1898):
+        self._init_common(obs_dim, ac_dim, config, nenvs, gradient_step, index_source, device, seed)
+        cfg = AgentConfig(algo=self.ALGO, state_dim=self.obs_dim, act_dim=self.ac_dim,
+                          hidden_dim=config.hidden_dim, layer_count=config.layer_count,
+                          max_batch=int(max_batch or config.batch_size), gamma=config.gamma,
+                          tau=config.tau,
+                          grad_clip=-1.0 if config.grad_clip is None else config.grad_clip,
+                          policy_noise=config.policy_noise, noise_clamp=config.noise_clamp,
+                          weight_decay=self.WEIGHT_DECAY, precision=0, reserved=0)
+        h = vp()
+        check(lib.gcrl_agent_create(C.byref(h), self.device_index, C.byref(cfg)))
+        self._h = h
+        self._metrics = (C.c_float * 8)()
+
+    def _init_common(self, obs_dim, ac_dim, config, nenvs, gradient_step, index_source, device, seed):
         _lib.require_cuda()
         self.device_index = int(device)
         self.device = f"cuda:{self.device_index}"
@@ -146,18 +160,6 @@ class _AgentBase:
         self.beta = self.beta_start = config.beta
         self.beta_max = 1.0
         self.beta_end = config.beta_end
-
-        cfg = AgentConfig(algo=self.ALGO, state_dim=self.obs_dim, act_dim=self.ac_dim,
-                          hidden_dim=config.hidden_dim, layer_count=config.layer_count,
-                          max_batch=int(max_batch or config.batch_size), gamma=config.gamma,
-                          tau=config.tau,
-                          grad_clip=-1.0 if config.grad_clip is None else config.grad_clip,
-                          policy_noise=config.policy_noise, noise_clamp=config.noise_clamp,
-                          weight_decay=self.WEIGHT_DECAY, precision=0, reserved=0)
-        h = vp()
-        check(lib.gcrl_agent_create(C.byref(h), self.device_index, C.byref(cfg)))
-        self._h = h
-        self._metrics = (C.c_float * 8)()
 
         self.actor_scheduler = CosineAnnealingLR(config.actor_lr, config.ac_scheduler_steps,
                                                  config.actor_lr_min)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GCRL_ABI_VERSION 1
+#define GCRL_ABI_VERSION 2
 
 #define GCRL_OK 0
 #define GCRL_ERR_INVALID 1      /* bad argument / shape                                  */
@@ -215,6 +215,85 @@ int gcrl_agent_grad_buffer(gcrl_agent *h, int net, float **grad_dev, int64_t *co
 /* device float[8] holding the metrics of the most recent update (averaged across ranks by the
  * caller when a data-parallel run wants global losses) */
 int gcrl_agent_metrics_buffer(gcrl_agent *h, float **metrics_dev);
+
+/* ------------------------------------------------------------------------------------
+ * Stochastic-actor agents -- replace SACAgent (src/agent.py:388-770) and TQCAgent (:773-1171)
+ * ------------------------------------------------------------------------------------
+ * Actor = SACActorModel (src/model.py:86-141): L x (Linear -> BatchNorm1d -> ReLU), mean_head,
+ * log_std_head.  Critics = an ensemble of n scalar Critic MLPs with n target copies; the value
+ * used in the Bellman target and in the actor loss is the mean of the (n - drop_top) smallest
+ * critic outputs per sample: SAC n = 2, drop_top = 1 (torch.min, :566,:519); "TQC" n = 5,
+ * drop_top = 2 (sort / slice / mean, :971-976, :919-921).  BatchNorm runs in train mode (batch
+ * statistics, running statistics updated) for both policy samples of an update, exactly as the
+ * reference does under set_train() (:701-706), including inside torch.no_grad (:556-557). */
+typedef struct gcrl_sac gcrl_sac;
+
+#define GCRL_ALGO_SAC 2
+#define GCRL_ALGO_TQC 3
+
+typedef struct gcrl_sac_config {
+  int32_t algo;            /* GCRL_ALGO_SAC | GCRL_ALGO_TQC                                   */
+  int32_t state_dim;       /* D = obs + goal                                                   */
+  int32_t act_dim;         /* 1..4                                                             */
+  int32_t hidden_dim;
+  int32_t layer_count;
+  int32_t max_batch;
+  int32_t n_critics;       /* SAC 2; TQC 5 (getattr default, src/agent.py:789)                 */
+  int32_t drop_top;        /* SAC 1 (= min); TQC 2 (src/agent.py:790)                          */
+  float gamma, tau, grad_clip;
+  float weight_decay;      /* AdamW default 0.01 (:420-425)                                    */
+  float entropy_coef;      /* >= 0: literal coefficient (SAC: 0.2, :521,:569); < 0: use the
+                              learned alpha = exp(log_alpha) (TQC, :928,:978)                  */
+  float target_entropy;    /* SAC -A/2 (:423); TQC -A (:815)                                   */
+  float alpha_lr;          /* SACAgentConfig.alpha_lr, src/utils.py:37                         */
+  int32_t reserved;
+} gcrl_sac_config;
+
+int gcrl_sac_create(gcrl_sac **out, int device, const gcrl_sac_config *cfg);
+int gcrl_sac_destroy(gcrl_sac *h);
+
+/* Parameter exchange in the reference's state_dict layout (fp32, weight [out, in] row-major).
+ * Actor Linear layers: 0..L-1 = base_net.{3l}; L = mean_head; L+1 = log_std_head.
+ * Actor BatchNorm l = base_net.{3l+1}: weight, bias, running_mean, running_var [H].
+ * Critics: critic 0..n-1 (critic_1/critic_2 or critics.{i}), target != 0 for the target copy;
+ * layer = net.{2 layer}. */
+int gcrl_sac_set_actor_linear(gcrl_sac *h, int layer, const float *weight_host, const float *bias_host,
+                              void *stream);
+int gcrl_sac_get_actor_linear(gcrl_sac *h, int layer, float *weight_host, float *bias_host, void *stream);
+int gcrl_sac_set_actor_bn(gcrl_sac *h, int layer, const float *weight, const float *bias,
+                          const float *running_mean, const float *running_var, void *stream);
+int gcrl_sac_get_actor_bn(gcrl_sac *h, int layer, float *weight, float *bias, float *running_mean,
+                          float *running_var, void *stream);
+int gcrl_sac_set_critic_layer(gcrl_sac *h, int critic, int target, int layer, const float *weight_host,
+                              const float *bias_host, void *stream);
+int gcrl_sac_get_critic_layer(gcrl_sac *h, int critic, int target, int layer, float *weight_host,
+                              float *bias_host, void *stream);
+int gcrl_sac_hard_update(gcrl_sac *h, void *stream);          /* update_target_network, :483-485 */
+int gcrl_sac_set_log_alpha(gcrl_sac *h, float log_alpha, void *stream);
+int gcrl_sac_get_log_alpha(gcrl_sac *h, float *log_alpha, void *stream);
+
+/* One update (update(), src/agent.py:659-699 / :1062-1100) on an explicit device batch.
+ *   eps_next_dev / eps_cur_dev: [B, A] standard-normal draws behind Normal.rsample
+ *   (src/model.py:134) for the next-state sample (critic_update) and the state sample
+ *   (actor_update; may be NULL when flags bit0 is clear).
+ *   flags bit0: actor step (+ alpha bookkeeping); bit1: Polyak of the target critics
+ *   (SAC: step % gradient_step == 0, :681; TQC: always, :1086); bit2: alpha update
+ *   (step > alpha_min_steps, :533).
+ *   metrics_host (optional, float[12]): q1_loss, q2_loss, actor_loss, td_error, q_value,
+ *   critic_1_grad, critic_2_grad, actor_grad, alpha_loss, alpha, log_alpha, unused -- the
+ *   reference's return tuple (:684-698); for TQC slots 0/1 and 5/6 carry the ensemble means
+ *   (:1013-1014). */
+int gcrl_sac_update_batch(gcrl_sac *h, int64_t B, const float *s_dev, const float *a_dev,
+                          const float *r_dev, const float *ns_dev, const float *d_dev,
+                          const float *eps_next_dev, const float *eps_cur_dev, double lr_critic,
+                          double lr_actor, int flags, float *metrics_host, void *stream);
+int gcrl_sac_update_from_buffer(gcrl_sac *h, gcrl_her *buf, int64_t B, const int64_t *idx_host,
+                                const float *eps_next_dev, const float *eps_cur_dev, double lr_critic,
+                                double lr_actor, int flags, float *metrics_host, void *stream);
+/* select_action, :641-647: eval-mode actor (running statistics).  eps_host NULL = deterministic
+ * tanh(mean); otherwise tanh(mean + std * eps).  obs host [n, D] -> act host [n, A]. */
+int gcrl_sac_act(gcrl_sac *h, int64_t n, const float *obs_host, const float *eps_host, float *act_host,
+                 void *stream);
 
 #ifdef __cplusplus
 }
