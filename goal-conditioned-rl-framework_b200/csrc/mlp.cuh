@@ -109,6 +109,12 @@ bool fused_supported(int B, int D, int A, int H, int L);
 int launch_fused_critic(const FusedCriticArgs &a, cudaStream_t st);   // returns the grid (metric slabs)
 int launch_fused_actor(const FusedActorArgs &a, cudaStream_t st);
 
+// ---- tensor-core dense layers (tc_gemm.cu): tcgen05 / TMEM / TMA, 3xTF32 split for fp32 accuracy ----
+bool tc_dense_supported(int M, int N, int K);
+// out[M, N] = epilogue(X[M, K] * W[N, K]^T); mode 0: leaky(. + bias), 1: . * leaky'(act), 2: . + bias
+void launch_tc_dense(const float *X, int ldx, const float *W, int ldw, const float *bias, const float *act,
+                     int ldact, float *out, int ldo, int M, int N, int K, int mode, cudaStream_t st);
+
 // ---- optimiser (optim.cu) --------------------------------------------------------------
 struct SegDesc {          // one parameter segment of a flat network buffer
   int begin, count;       // [begin, begin+count) in the flat buffer

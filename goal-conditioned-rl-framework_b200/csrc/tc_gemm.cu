@@ -1,0 +1,432 @@
+// Dense hidden layers on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), large-batch regime.
+//
+//   FWD  : Y[M,N]  = leaky(X[M,K] W[N,K]^T + b)          (nn.Linear + LeakyReLU, src/model.py:17-30)
+//   DGRAD: dX[M,N] = (dZ[M,K] Wt[N,K]^T) (.) leaky'(act)  (autograd of the same; Wt = transposed copy)
+//
+// fp32 accuracy on TF32 tensor cores ("3xTF32"): every operand is split in shared memory into
+//   hi = rna_tf32(x),  lo = rna_tf32(x - hi)   (x - hi is exact in fp32)
+// and the product is accumulated in fp32 TMEM as  hi*hi + hi*lo + lo*hi  (the lo*lo term is
+// 2^-22 relative).  Both halves are already valid TF32 bit patterns, so the result does not depend on
+// how the tensor core would round raw fp32 inputs.
+//
+// One persistent CTA per SM, 10 warps:
+//   warp 0      TMA producer    (cp.async.bulk.tensor, 64-byte swizzle, 4-stage ring of 16-wide K tiles)
+//   warp 1      MMA issuer      (one elected thread: 6 x tcgen05.mma.kind::tf32 per K tile)
+//   warps 2-5   epilogue        (tcgen05.ld 32 lanes x 32 columns, bias / activation, 16-byte stores)
+//   warps 6-13  hi / lo splitter (generic-proxy pass over the landed stage, fence.proxy.async)
+// Pipelines: full (TMA -> splitter), ready (splitter -> MMA), empty (MMA commit -> TMA),
+// tmem_full / tmem_empty (MMA <-> epilogue; two accumulator stages of N columns, so the epilogue of
+// tile i overlaps the MMAs of tile i+1).
+#include <cuda.h>
+
+#include <cstdlib>
+#include <map>
+#include <tuple>
+
+#include "mlp.cuh"
+
+namespace gcrl {
+namespace {
+
+constexpr int BM = 128;            // rows per tile = TMEM lanes = UMMA M
+constexpr int BKF = 16;            // fp32 elements per K tile = one 64-byte swizzle row
+constexpr int ROWB = BKF * 4;      // bytes per operand row in a stage
+constexpr int STAGES = 4;
+constexpr int kSplitWarps = 8;
+constexpr int kSplitThreads = kSplitWarps * 32;
+constexpr int kTcThreads = (6 + kSplitWarps) * 32;
+constexpr int kStgLd = 36;         // epilogue staging row stride in floats (16-byte aligned, conflict-free)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 64-byte-swizzled operand tile: rows of 64 bytes, 8-row groups 512 bytes apart.
+// Descriptor (cute::UMMA::SmemDescriptor): start >> 4 [0,14), LBO >> 4 [16,30) (unused for swizzled
+// K-major), SBO >> 4 [32,46), version 1 [46,48), layout [61,64): SWIZZLE_64B = 4 (SWIZZLE_128B = 2).
+__device__ __forceinline__ uint64_t umma_desc_sw(uint32_t saddr) {
+  constexpr uint64_t layout = ROWB == 128 ? 2 : 4;
+  return uint64_t((saddr >> 4) & 0x3FFF) | (uint64_t(1) << 16) | (uint64_t((8 * ROWB) >> 4) << 32) |
+         (uint64_t(1) << 46) | (layout << 61);
+}
+
+__device__ __forceinline__ uint32_t rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+struct TcArgs {
+  float *out; int ldo;
+  const float *bias;             // mode 0
+  const float *act; int ldact;   // mode 1
+  int M, N, K;                   // N <= BN * n_tiles
+  int mode;                      // 0: leaky(acc + bias); 1: acc * leaky'(act); 2: acc + bias
+  int n_tiles, m_tiles;
+  int dbg;                       // timing experiments only (GCRL_TC_DBG): 1 skip split, 2 skip stores, 4 one MMA per k step
+};
+
+template <int BN>
+struct TcSmem {
+  static constexpr int kA = BM * ROWB, kB = BN * ROWB;
+  static constexpr int kStage = 2 * kA + 2 * kB;            // A_hi | A_lo | B_hi | B_lo
+  static constexpr int kBytes = STAGES * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/ + 4 * 32 * kStgLd * 4;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  using S = TcSmem<BN>;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + STAGES * S::kStage;
+  // barrier layout (8 bytes each): full[S], ready[S], empty[S], tmem_full[2], tmem_empty[2], then tmem ptr
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto ready = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+  auto tfull = [&](int s) { return bars + 8u * (3 * STAGES + s); };
+  auto tempty = [&](int s) { return bars + 8u * (3 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 4);
+  const uint32_t stage_base = bars + 256;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(ready(s), kSplitThreads);
+      mbar_init(empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull(s), 1);
+      mbar_init(tempty(s), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2 * BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int nk = (a.K + BKF - 1) / BKF;
+  const int total_tiles = a.m_tiles * a.n_tiles;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m0 = (t / a.n_tiles) * BM, n0 = (t % a.n_tiles) * BN;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(empty(s), ((it / STAGES) & 1) ^ 1);
+          mbar_expect_tx(full(s), S::kA + S::kB);
+          const uint32_t st = base + s * S::kStage;
+          tma_load_2d(st, &tmA, full(s), kb * BKF, m0);
+          tma_load_2d(st + 2 * S::kA, &tmB, full(s), kb * BKF, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6) = 1, A/B = TF32 [7,10),[10,13) = 2,
+      // K-major both, N >> 3 at [17,23), M >> 4 at [24,29)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+      uint32_t it = 0, tile_it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
+        const int as = tile_it & 1;
+        mbar_wait(tempty(as), ((tile_it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + uint32_t(as * BN);
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(ready(s), (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t st = base + s * S::kStage;
+          const uint64_t a_hi = umma_desc_sw(st), a_lo = umma_desc_sw(st + S::kA);
+          const uint64_t b_hi = umma_desc_sw(st + 2 * S::kA), b_lo = umma_desc_sw(st + 2 * S::kA + S::kB);
+#pragma unroll
+          for (int k = 0; k < BKF / 8; ++k) {          // UMMA K = 8 for tf32 (32 bytes): +2 in the >>4 address
+            const uint64_t ko = uint64_t(k * 2);
+            umma_tf32(d, a_lo + ko, b_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (!(a.dbg & 4)) {
+              umma_tf32(d, a_hi + ko, b_lo + ko, idesc, 1u);
+              umma_tf32(d, a_hi + ko, b_hi + ko, idesc, 1u);
+            }
+          }
+          umma_commit(empty(s));                        // smem stage reusable once these MMAs retire
+        }
+        umma_commit(tfull(as));                         // accumulator complete
+      }
+    }
+  } else if (warp < 6) {
+    // ===== epilogue: TMEM lanes (warp % 4) * 32 .. + 31 =====
+    const int q = warp & 3;
+    uint32_t tile_it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
+      const int m0 = (t / a.n_tiles) * BM, n0 = (t % a.n_tiles) * BN;
+      const int as = tile_it & 1;
+      mbar_wait(tfull(as), (tile_it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN);
+      // 32 accumulator columns at a time: TMEM -> registers (lane = row) -> padded smem tile ->
+      // (lane = 4 columns of one of 4 rows) so that every global access is a full 128-byte row segment
+      const uint32_t stg = stage_base + uint32_t(q) * (32 * kStgLd * 4);
+      const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + uint32_t(c), v);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + uint32_t(lane * kStgLd + j) * 4), "r"(v[j]),
+                       "r"(v[j + 1]), "r"(v[j + 2]), "r"(v[j + 3])
+                       : "memory");
+        __syncwarp();
+        const int col = n0 + c + sub_c;
+        if (col < a.N && !(a.dbg & 2)) {                // N is a multiple of 4 (padded leading dims)
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.mode != 1) bv = __ldg(reinterpret_cast<const float4 *>(a.bias + col));
+#pragma unroll
+          for (int r8 = 0; r8 < 8; ++r8) {
+            const int lr = r8 * 4 + sub_r;
+            const int row = m0 + q * 32 + lr;
+            float4 x;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                         : "r"(stg + uint32_t(lr * kStgLd + sub_c) * 4));
+            if (row < a.M) {
+              if (a.mode == 1) {
+                const float4 h = *reinterpret_cast<const float4 *>(a.act + size_t(row) * a.ldact + col);
+                x.x = h.x > 0.f ? x.x : x.x * kLeakySlope;
+                x.y = h.y > 0.f ? x.y : x.y * kLeakySlope;
+                x.z = h.z > 0.f ? x.z : x.z * kLeakySlope;
+                x.w = h.w > 0.f ? x.w : x.w * kLeakySlope;
+              } else {
+                x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
+                if (a.mode == 0) {
+                  x.x = x.x > 0.f ? x.x : x.x * kLeakySlope;
+                  x.y = x.y > 0.f ? x.y : x.y * kLeakySlope;
+                  x.z = x.z > 0.f ? x.z : x.z * kLeakySlope;
+                  x.w = x.w > 0.f ? x.w : x.w * kLeakySlope;
+                }
+              }
+              *reinterpret_cast<float4 *>(a.out + size_t(row) * a.ldo + col) = x;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(as));
+    }
+  } else {
+    // ===== hi / lo splitter =====
+    const int tid = threadIdx.x - 6 * 32;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int kb = 0; kb < nk; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(full(s), (it / STAGES) & 1);
+        const uint32_t st = base + s * S::kStage;
+        // chunk c (16 bytes) of the stage: A chunks first (hi at st, lo at st + kA), then B chunks
+        // (hi at st + 2 kA, lo at + kB).  All loads of a thread are issued before the first store.
+        constexpr int kChunksA = S::kA / 16, kChunks = (S::kA + S::kB) / 16;
+        constexpr int kPer = (kChunks + kSplitThreads - 1) / kSplitThreads;
+        if (!(a.dbg & 1)) {
+          float x[kPer][4];
+          uint32_t hi_addr[kPer], lo_addr[kPer];
+#pragma unroll
+          for (int u = 0; u < kPer; ++u) {
+            const int c = tid + u * kSplitThreads;
+            const bool isA = c < kChunksA;
+            hi_addr[u] = isA ? st + 16u * c : st + 2 * S::kA + 16u * (c - kChunksA);
+            lo_addr[u] = hi_addr[u] + (isA ? S::kA : S::kB);
+            if (c < kChunks)
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(x[u][0]), "=f"(x[u][1]), "=f"(x[u][2]), "=f"(x[u][3])
+                           : "r"(hi_addr[u]));
+          }
+#pragma unroll
+          for (int u = 0; u < kPer; ++u) {
+            const int c = tid + u * kSplitThreads;
+            if (c < kChunks) {
+              uint32_t h[4], l[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                h[e] = rna_tf32(x[u][e]);
+                l[e] = rna_tf32(x[u][e] - __uint_as_float(h[e]));
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr[u]), "r"(h[0]), "r"(h[1]), "r"(h[2]),
+                           "r"(h[3])
+                           : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lo_addr[u]), "r"(l[0]), "r"(l[1]), "r"(l[2]),
+                           "r"(l[3])
+                           : "memory");
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
+        mbar_arrive(ready(s));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    GCRL_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (p == nullptr || qres != cudaDriverEntryPointSuccess)
+      throw Error(GCRL_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// fp32 row-major [rows, cols] with leading dimension ld -> box of (box_rows x 32 floats), 128-byte swizzle,
+// out-of-bounds elements read as zero (ragged M / K tails).
+CUtensorMap make_map(const float *ptr, int64_t rows, int cols, int ld, int box_rows) {
+  CUtensorMap m;
+  const cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  const cuuint64_t strides[1] = {cuuint64_t(ld) * 4};
+  const cuuint32_t box[2] = {cuuint32_t(BKF), cuuint32_t(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box,
+                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, ROWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(GCRL_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string(int(r)) + ")");
+  return m;
+}
+
+template <int BN>
+void launch_bn(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcArgs &a, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    GCRL_CUDA(cudaFuncSetAttribute(tc_dense_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   TcSmem<BN>::kBytes));
+    attr_set = true;
+  }
+  const int grid = std::min(a.m_tiles * a.n_tiles, sm_count());
+  tc_dense_kernel<BN><<<grid, kTcThreads, TcSmem<BN>::kBytes, st>>>(tmA, tmB, a);
+  GCRL_LAUNCHED();
+}
+
+}  // namespace
+
+bool tc_dense_supported(int M, int N, int K) {
+  return M >= 1 && N >= 16 && (N % 16) == 0 && K >= 4 && (K % 4) == 0 && (N <= 256 || N % 256 == 0);
+}
+
+// out[M, N] = epilogue( X[M, K] * W[N, K]^T )
+//   mode 0: leaky(. + bias)   mode 1: . * leaky'(act)   mode 2: . + bias
+void launch_tc_dense(const float *X, int ldx, const float *W, int ldw, const float *bias, const float *act,
+                     int ldact, float *out, int ldo, int M, int N, int K, int mode, cudaStream_t st) {
+  GCRL_REQUIRE(tc_dense_supported(M, N, K), "shape not supported by the tensor-core dense kernel");
+  GCRL_REQUIRE((ldx % 4) == 0 && (ldw % 4) == 0 && (ldo % 4) == 0, "leading dimensions must be multiples of 4");
+  const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  TcArgs a{};
+  a.out = out; a.ldo = ldo; a.bias = bias; a.act = act; a.ldact = ldact;
+  a.M = M; a.N = N; a.K = K; a.mode = mode;
+  a.m_tiles = (M + BM - 1) / BM;
+  a.n_tiles = (N + BN - 1) / BN;
+  if (const char *e = getenv("GCRL_TC_DBG")) a.dbg = atoi(e);
+  const CUtensorMap tmA = make_map(X, M, K, ldx, BM);
+  const CUtensorMap tmB = make_map(W, N, K, ldw, BN);
+  if (BN == 64) launch_bn<64>(tmA, tmB, a, st);
+  else if (BN == 128) launch_bn<128>(tmA, tmB, a, st);
+  else launch_bn<256>(tmA, tmB, a, st);
+}
+
+}  // namespace gcrl
+
+extern "C" int gcrl_dense_layer(int device, int engine, int mode, int64_t M, int N, int K, const float *x_dev,
+                                int ldx, const float *w_dev, int ldw, const float *bias_dev, const float *act_dev,
+                                int ldact, float *y_dev, int ldy, void *stream) {
+  GCRL_API_BEGIN
+  using namespace gcrl;
+  GCRL_REQUIRE(x_dev && w_dev && y_dev && M >= 1 && M < (int64_t(1) << 31), "bad argument");
+  GCRL_REQUIRE(mode >= 0 && mode <= 2 && (mode == 1 ? act_dev != nullptr : bias_dev != nullptr), "bad mode / operands");
+  GCRL_CUDA(cudaSetDevice(device));
+  cudaStream_t st = as_stream(stream);
+  if (engine == 1) {
+    launch_tc_dense(x_dev, ldx, w_dev, ldw, bias_dev, act_dev, ldact, y_dev, ldy, int(M), N, K, mode, st);
+  } else {
+    GCRL_REQUIRE(engine == 0 && mode != 1, "engine 0 (fp32 FFMA) implements modes 0 and 2");
+    launch_linear_fwd(x_dev, ldx, w_dev, ldw, bias_dev, y_dev, ldy, int(M), N, K, mode == 0 ? ACT_LEAKY : ACT_NONE, st);
+  }
+  GCRL_API_END
+}

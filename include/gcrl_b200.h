@@ -295,6 +295,19 @@ int gcrl_sac_update_from_buffer(gcrl_sac *h, gcrl_her *buf, int64_t B, const int
 int gcrl_sac_act(gcrl_sac *h, int64_t n, const float *obs_host, const float *eps_host, float *act_host,
                  void *stream);
 
+/* ------------------------------------------------------------------------------------
+ * Diagnostics / micro-benchmarks
+ * ------------------------------------------------------------------------------------
+ * One dense layer on device buffers (what nn.Linear + LeakyReLU, src/model.py:17-30, and its
+ * autograd input-gradient compute), with a selectable engine:
+ *   engine 0: fp32 FFMA tiles (mlp.cu);  engine 1: tcgen05 tensor cores, 3xTF32 split (tc_gemm.cu).
+ *   mode 0: y = leaky(x w^T + bias);  mode 1: y = (x w^T) * leaky'(act) (engine 1 only);
+ *   mode 2: y = x w^T + bias.
+ * x [M, K] (ldx), w [N, K] (ldw), y [M, N] (ldy); leading dimensions multiples of 4 floats. */
+int gcrl_dense_layer(int device, int engine, int mode, int64_t M, int N, int K, const float *x_dev,
+                     int ldx, const float *w_dev, int ldw, const float *bias_dev, const float *act_dev,
+                     int ldact, float *y_dev, int ldy, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,15 @@
+import sys, os
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, os.path.join(ROOT, "goal-conditioned-rl-framework_b200"))
+import torch
+from gcrl_b200._lib import lib, check, vp
+M, N, K = 65536, 256, 256
+x = torch.randn(M, K, device="cuda"); w = torch.randn(N, K, device="cuda") / 16; b = torch.randn(N, device="cuda")
+y = torch.empty(M, N, device="cuda"); st = vp(torch.cuda.current_stream().cuda_stream)
+def go(engine, n):
+    for _ in range(n):
+        check(lib.gcrl_dense_layer(0, engine, 0, M, N, K, vp(x.data_ptr()), K, vp(w.data_ptr()), K, vp(b.data_ptr()), None, 0, vp(y.data_ptr()), N, st))
+go(1, 3)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); go(1, 20); e1.record(); torch.cuda.synchronize()
+print(os.environ.get("GCRL_TC_DBG", "0"), f"{e0.elapsed_time(e1)/20*1000:.1f} us")
