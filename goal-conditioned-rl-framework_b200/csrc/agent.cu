@@ -148,6 +148,14 @@ struct gcrl_agent {
 
 namespace {
 
+// Tensor-core (tcgen05, 3xTF32) dense layers: large batches only -- below ~1k rows a 128-row tile
+// grid cannot fill the 148 SMs and the fp32 tiles / row-slab kernels win.
+constexpr int kTcMinBatch = 8192;     // 64 row tiles of 128: enough CTAs in flight to beat the fp32 tiles
+bool use_tc(const gcrl_agent *ag, int B, int N, int K) {
+  if (!tc_dense_supported(B, N, K)) return false;
+  return ag->cfg.precision == 2 ? B >= 128 : (ag->cfg.precision == 1 && B >= kTcMinBatch);
+}
+
 // ---- forward / backward building blocks ----------------------------------------------------
 // hidden stack: X[B, K0] -> acts.h[0..L-1]
 void forward_hidden(const gcrl_agent *ag, const Net &n, const float *X, int ldx, int K0, const Acts &acts,
@@ -155,7 +163,12 @@ void forward_hidden(const gcrl_agent *ag, const Net &n, const float *X, int ldx,
   const float *in = X;
   int ldin = ldx, K = K0;
   for (int l = 0; l < ag->L; ++l) {
-    launch_linear_fwd(in, ldin, n.W(l), n.ldw[l], n.b(l), acts.h[l], ag->ldh, B, ag->H, K, ACT_LEAKY, st);
+    // layer 0: the operand rows and the weight rows are zero-padded to ld, so the padded K is exact
+    const int Kp = (K + 3) & ~3;
+    if (use_tc(ag, B, ag->H, Kp))
+      launch_tc_dense(in, ldin, n.W(l), n.ldw[l], n.b(l), nullptr, 0, acts.h[l], ag->ldh, B, ag->H, Kp, 0, st);
+    else
+      launch_linear_fwd(in, ldin, n.W(l), n.ldw[l], n.b(l), acts.h[l], ag->ldh, B, ag->H, K, ACT_LEAKY, st);
     in = acts.h[l];
     ldin = ag->ldh;
     K = ag->H;
@@ -176,8 +189,12 @@ void backward_hidden(gcrl_agent *ag, const Net &n, const float *X, int ldx, int 
                                       ag->slab, ag->partials + n.b_off[l], ag->slab, B, ag->H, K,
                                       kMaxSplits, st);
     if (l > 0) {
-      launch_linear_dgrad(ag->dz[cur], ag->ldh, n.W(l), n.ldw[l], acts.h[l - 1], ag->ldh, ag->dz[cur ^ 1],
-                          ag->ldh, B, ag->H, ag->H, st);
+      if (use_tc(ag, B, ag->H, ag->H))   // dX = dZ Wt^T with the transposed weight copy as the K-major operand
+        launch_tc_dense(ag->dz[cur], ag->ldh, n.pT + n.t_off[l], n.ldt[l], nullptr, acts.h[l - 1], ag->ldh,
+                        ag->dz[cur ^ 1], ag->ldh, B, ag->H, ag->H, 1, st);
+      else
+        launch_linear_dgrad(ag->dz[cur], ag->ldh, n.W(l), n.ldw[l], acts.h[l - 1], ag->ldh, ag->dz[cur ^ 1],
+                            ag->ldh, B, ag->H, ag->H, st);
       cur ^= 1;
     }
   }
@@ -598,7 +615,7 @@ int gcrl_agent_create(gcrl_agent **out, int device, const gcrl_agent_config *cfg
   GCRL_REQUIRE(cfg->hidden_dim >= 1 && cfg->hidden_dim <= 4096, "hidden_dim outside [1, 4096]");
   GCRL_REQUIRE(cfg->layer_count >= 1 && cfg->layer_count <= 6, "layer_count outside [1, 6]");
   GCRL_REQUIRE(cfg->max_batch >= 1, "max_batch must be >= 1");
-  GCRL_REQUIRE(cfg->precision == 0, "only precision 0 (fp32) is implemented");
+  GCRL_REQUIRE(cfg->precision >= 0 && cfg->precision <= 2, "precision must be 0 (fp32 FFMA), 1 (tensor cores for large batches) or 2 (tensor cores whenever supported)");
   GCRL_CUDA(cudaSetDevice(device));
   auto *ag = new gcrl_agent();
   try {
@@ -651,6 +668,7 @@ int gcrl_agent_create(gcrl_agent **out, int device, const gcrl_agent_config *cfg
     const char *ng = getenv("GCRL_B200_NO_GRAPH");
     ag->use_graphs = !(ng && ng[0] == '1');
     ag->io_stage.init(size_t(1) << 16);
+    if (ag->cfg.precision >= 1) tc_dense_init();
   } catch (...) {
     delete ag;
     throw;

@@ -111,6 +111,7 @@ int launch_fused_actor(const FusedActorArgs &a, cudaStream_t st);
 
 // ---- tensor-core dense layers (tc_gemm.cu): tcgen05 / TMEM / TMA, 3xTF32 split for fp32 accuracy ----
 bool tc_dense_supported(int M, int N, int K);
+void tc_dense_init();
 // out[M, N] = epilogue(X[M, K] * W[N, K]^T); mode 0: leaky(. + bias), 1: . * leaky'(act), 2: . + bias
 void launch_tc_dense(const float *X, int ldx, const float *W, int ldw, const float *bias, const float *act,
                      int ldact, float *out, int ldo, int M, int N, int K, int mode, cudaStream_t st);

@@ -373,19 +373,32 @@ CUtensorMap make_map(const float *ptr, int64_t rows, int cols, int ld, int box_r
 }
 
 template <int BN>
-void launch_bn(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcArgs &a, cudaStream_t st) {
+void set_attr() {
   static bool attr_set = false;
   if (!attr_set) {
     GCRL_CUDA(cudaFuncSetAttribute(tc_dense_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    TcSmem<BN>::kBytes));
     attr_set = true;
   }
+}
+
+template <int BN>
+void launch_bn(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcArgs &a, cudaStream_t st) {
+  set_attr<BN>();
   const int grid = std::min(a.m_tiles * a.n_tiles, sm_count());
   tc_dense_kernel<BN><<<grid, kTcThreads, TcSmem<BN>::kBytes, st>>>(tmA, tmB, a);
   GCRL_LAUNCHED();
 }
 
 }  // namespace
+
+// one-time host setup (driver entry point, shared-memory opt-in): call outside stream capture
+void tc_dense_init() {
+  encode_fn();
+  set_attr<64>();
+  set_attr<128>();
+  set_attr<256>();
+}
 
 bool tc_dense_supported(int M, int N, int K) {
   return M >= 1 && N >= 16 && (N % 16) == 0 && K >= 4 && (K % 4) == 0 && (N <= 256 || N % 256 == 0);

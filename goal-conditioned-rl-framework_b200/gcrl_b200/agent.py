@@ -115,7 +115,10 @@ class _AgentBase:
     WEIGHT_DECAY = 0.0
 
     def __init__(self, obs_dim, ac_dim, config, weights, nenvs, gradient_step, *,
-                 index_source="host", device=0, max_batch=None, seed=1898):
+                 index_source="host", device=0, max_batch=None, seed=1898, precision=1):
+        """precision: 1 (default) runs the hidden-layer GEMMs of batches >= 8192 on the tcgen05 tensor
+        cores with the 3xTF32 split (fp32-level accuracy, rel ~2e-6 per layer); 2 does so for every
+        batch >= 128; 0 keeps every GEMM on the fp32 FFMA tiles."""
         self._init_common(obs_dim, ac_dim, config, nenvs, gradient_step, index_source, device, seed)
         cfg = AgentConfig(algo=self.ALGO, state_dim=self.obs_dim, act_dim=self.ac_dim,
                           hidden_dim=config.hidden_dim, layer_count=config.layer_count,
@@ -123,7 +126,7 @@ class _AgentBase:
                           tau=config.tau,
                           grad_clip=-1.0 if config.grad_clip is None else config.grad_clip,
                           policy_noise=config.policy_noise, noise_clamp=config.noise_clamp,
-                          weight_decay=self.WEIGHT_DECAY, precision=0, reserved=0)
+                          weight_decay=self.WEIGHT_DECAY, precision=int(precision), reserved=0)
         h = vp()
         check(lib.gcrl_agent_create(C.byref(h), self.device_index, C.byref(cfg)))
         self._h = h

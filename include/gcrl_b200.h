@@ -141,7 +141,10 @@ typedef struct gcrl_agent_config {
   float policy_noise;    /* TD3 target smoothing sigma, src/agent.py:175               */
   float noise_clamp;     /* TD3, src/agent.py:176                                      */
   float weight_decay;    /* 0 = Adam (DDPG); 0.01 = AdamW default (TD3)                */
-  int32_t precision;     /* 0 = fp32 FFMA (parity); reserved for tensor-core modes     */
+  int32_t precision;     /* 0 = fp32 FFMA everywhere; 1 = hidden-layer forward / input-gradient
+                            GEMMs on tcgen05 tensor cores (3xTF32 split, fp32-level accuracy)
+                            once the batch reaches 8192 rows; 2 = the same for every batch
+                            >= 128 rows (tests)                                           */
   int32_t reserved;
 } gcrl_agent_config;
 

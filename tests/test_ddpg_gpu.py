@@ -84,7 +84,7 @@ def test_update_matches_oracle_odd_shapes(B, H, L, D, A):
     from gcrl_b200.agent import NET_ACTOR, NET_CRITIC
     rng = np.random.default_rng(B * 7 + H)
     cfg = make_config(hidden_dim=H, layer_count=L, batch_size=B, grad_clip=0.5, tau=0.05)
-    ag = DDPG(D, A, cfg, None, 1, 40)
+    ag = DDPG(D, A, cfg, None, 1, 40, precision=0)
     actor0, critic0 = OD.init_mlp(rng, D, H, A, L), OD.init_mlp(rng, D + A, H, 1, L)
     ag._set_layers(NET_ACTOR, actor0)
     ag._set_layers(NET_CRITIC, critic0)
@@ -122,6 +122,57 @@ def test_update_matches_oracle_odd_shapes(B, H, L, D, A):
         for (w, b), (rw, rb) in zip(net.layers(), ref):
             assert weights_close(w, rw, 1e-3, 4, outlier_frac=frac[flipped])
             assert weights_close(b, rb, 1e-3, 4, outlier_frac=frac[flipped])
+
+
+@pytest.mark.parametrize("B,H,L,D,A", [(2048, 256, 3, 21, 3), (5000, 64, 2, 23, 4), (1100, 512, 3, 22, 3)])
+def test_tensor_core_update_matches_fp32_update(B, H, L, D, A):
+    """precision=2 (tcgen05, 3xTF32 split, forced for small batches) versus precision=0 (fp32 FFMA) on identical weights and
+    batches, and versus the NumPy oracle: metrics rel 5e-5 * sqrt(B/256) like the fp32 path."""
+    import torch
+    from gcrl_b200 import DDPG
+    from gcrl_b200.agent import NET_ACTOR, NET_CRITIC
+    rng = np.random.default_rng(B + H)
+    cfg = make_config(hidden_dim=H, layer_count=L, batch_size=B, grad_clip=0.5, tau=0.05)
+    actor0, critic0 = OD.init_mlp(rng, D, H, A, L), OD.init_mlp(rng, D + A, H, 1, L)
+    agents = []
+    for precision in (0, 2):
+        ag = DDPG(D, A, cfg, None, 1, 40, precision=precision)
+        ag._set_layers(NET_ACTOR, actor0)
+        ag._set_layers(NET_CRITIC, critic0)
+        ag.update_target_network()
+        agents.append(ag)
+    orc = OD.DDPGOracle(actor0, critic0, gamma=cfg.gamma, tau=cfg.tau, grad_clip=cfg.grad_clip,
+                        actor_lr=cfg.actor_lr, critic_lr=cfg.critic_lr)
+    # pre-activations carry ~2e-6 relative error per 3xTF32 layer (fp32 tiles: 5e-7), so units within
+    # 2e-5 of zero may take either LeakyReLU slope (oracle/ddpg.py::_actor_flip_slack)
+    orc.flip_delta = 2e-5
+    rtol = np.full(6, 5e-5 * max(1.0, (B / 256.0) ** 0.5))
+    for step in (40, 41):
+        s = rng.standard_normal((B, D)).astype(np.float32)
+        ns = (s + 0.1 * rng.standard_normal((B, D))).astype(np.float32)
+        a = rng.uniform(-1, 1, (B, A)).astype(np.float32)
+        r = -(rng.random((B, 1)) > 0.3).astype(np.float32)
+        d = (rng.random((B, 1)) < 0.1).astype(np.float32)
+        want = np.array(orc.update_on_batch(step, s, a, r, ns, d))
+        tol = rtol.copy()
+        tol[5] += orc.last_actor_flip_slack
+        batch = tuple(torch.from_numpy(x).cuda() for x in (s, a, r, ns, d))
+        got = [np.array([float(x) for x in ag.update(step, batch=batch)]) for ag in agents]
+        for g in got:
+            assert np.all(np.abs(g - want) <= tol * np.abs(want) + 2e-6), (step, g, want, tol)
+    assert lib_launch_names_include_tc()
+
+
+def lib_launch_names_include_tc():
+    """The precision=1 agent really went through tc_gemm.cu: a direct call must succeed on this GPU."""
+    import torch
+    from gcrl_b200._lib import check, lib, vp
+    x = torch.randn(1024, 64, device="cuda"); w = torch.randn(64, 64, device="cuda"); b = torch.zeros(64, device="cuda")
+    y = torch.empty(1024, 64, device="cuda")
+    check(lib.gcrl_dense_layer(0, 1, 2, 1024, 64, 64, vp(x.data_ptr()), 64, vp(w.data_ptr()), 64, vp(b.data_ptr()), None,
+                               0, vp(y.data_ptr()), 64, vp(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    return bool(torch.allclose(y, x @ w.T, rtol=1e-4, atol=1e-4))
 
 
 def test_checkpoint_load_and_forward_matches_reference():

@@ -1,0 +1,59 @@
+"""GPU numerics: the tcgen05 dense-layer kernel (csrc/tc_gemm.cu, 3xTF32 split) against a float64
+reference of nn.Linear + LeakyReLU (src/model.py:17-30) and of its input gradient.  Tolerance:
+max-norm relative error <= 1e-5 (observed 2e-6; the fp32 FFMA tiles give 5e-7)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(engine, mode, x, w, b, act):
+    import torch
+    from gcrl_b200._lib import check, lib, vp
+    M, K = x.shape
+    N = w.shape[0]
+    y = torch.full((M, N), float("nan"), device="cuda")
+    check(lib.gcrl_dense_layer(0, engine, mode, M, N, K, vp(x.data_ptr()), x.stride(0), vp(w.data_ptr()), w.stride(0),
+                               None if b is None else vp(b.data_ptr()), None if act is None else vp(act.data_ptr()),
+                               0 if act is None else act.stride(0), vp(y.data_ptr()), y.stride(0),
+                               vp(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    return y
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 256), (1, 64, 64), (1000, 256, 256), (65536, 256, 256), (300, 64, 64),
+                                   (4096, 512, 512), (777, 96, 100), (5000, 256, 24), (129, 16, 4)])
+def test_tc_dense_matches_float64(M, N, K):
+    import torch
+    torch.manual_seed(M + N + K)
+    x = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") / K ** 0.5
+    b = torch.randn(N, device="cuda")
+    act = torch.randn(M, N, device="cuda")
+    ref = x.double() @ w.double().T
+    wants = {0: torch.nn.functional.leaky_relu(ref + b.double(), 0.01),
+             1: ref * torch.where(act > 0, 1.0, 0.01).double(),
+             2: ref + b.double()}
+    for mode, want in wants.items():
+        got = _run(1, mode, x, w, b if mode != 1 else None, act if mode == 1 else None)
+        assert torch.isfinite(got).all()
+        err = ((got.double() - want).abs().max() / want.abs().max()).item()
+        assert err <= 1e-5, (mode, err)
+
+
+def test_tc_dense_strided_operands_and_zero_padding():
+    """Leading dimensions larger than the logical widths (the agent's padded rows)."""
+    import torch
+    torch.manual_seed(3)
+    M, N, K = 2048, 64, 24
+    xs = torch.randn(M, 28, device="cuda")
+    ws = torch.randn(N, 28, device="cuda")
+    b = torch.randn(N, device="cuda")
+    ys = torch.zeros(M, 80, device="cuda")
+    from gcrl_b200._lib import check, lib, vp
+    check(lib.gcrl_dense_layer(0, 1, 2, M, N, K, vp(xs.data_ptr()), 28, vp(ws.data_ptr()), 28, vp(b.data_ptr()), None, 0,
+                               vp(ys.data_ptr()), 80, vp(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    want = xs[:, :K].double() @ ws[:, :K].double().T + b.double()
+    assert ((ys[:, :N].double() - want).abs().max() / want.abs().max()).item() <= 1e-5
+    assert float(ys[:, N:].abs().max()) == 0.0          # columns beyond N untouched
