@@ -138,7 +138,7 @@ struct gcrl_agent {
   float *noise = nullptr;                  // TD3 smoothing noise copy [maxB, A]
   std::vector<float *> dzl;                // fused path: per-layer pre-activation gradients [maxB, ldh]
   float *dzh = nullptr;                    // fused path: critic head dL/dq [maxB]
-  bool use_fused = true;
+  bool use_fused = true, use_cluster = false;
   int dp_B = -1, dp_flags = -1;            // the update the data-parallel phases belong to
   bool use_graphs = true;
   cudaStream_t cap_stream = nullptr;       // capture-only stream (the caller's may be the legacy one)
@@ -312,8 +312,13 @@ struct PhaseState {
 };
 
 // ---- row-slab fused path (fused.cu): DDPG, B <= 1024 ---------------------------------------------
+constexpr int kClusterMaxBatch = 2048;
+bool cluster_ok(const gcrl_agent *ag, int B) {
+  return ag->use_fused && ag->use_cluster && !ag->td3 && B <= kClusterMaxBatch &&
+         cluster_supported(B, ag->D, ag->A, ag->H, ag->L);
+}
 bool fused_ok(const gcrl_agent *ag, int B) {
-  return ag->use_fused && !ag->td3 && fused_supported(B, ag->D, ag->A, ag->H, ag->L);
+  return cluster_ok(ag, B) || (ag->use_fused && !ag->td3 && fused_supported(B, ag->D, ag->A, ag->H, ag->L));
 }
 
 FusedNet fused_net(const gcrl_agent *ag, const Net &n) {
@@ -357,7 +362,7 @@ void fused_critic_phase_grads(gcrl_agent *ag, int B, cudaStream_t st) {
   for (int l = 0; l < ag->L; ++l) { a.h_out[l] = ag->acts_c1.h[l]; a.dz_out[l] = ag->dzl[l]; }
   a.dzh_out = ag->dzh; a.y_out = ag->yv; a.q_out = ag->q1;
   a.metric_partials = ag->metric_partials;
-  const int slabs = launch_fused_critic(a, st);
+  const int slabs = cluster_ok(ag, B) ? launch_cluster_critic(a, st) : launch_fused_critic(a, st);
   const Net &c = ag->net[CRITIC1];
   const int S = fused_wgrads(ag, c, ag->acts_c1, ag->D + ag->A, ag->dzh, 1, B, st);
   int splits[8];
@@ -374,7 +379,7 @@ void fused_actor_phase_grads(gcrl_agent *ag, int B, cudaStream_t st) {
   for (int l = 0; l < ag->L; ++l) { a.h_out[l] = ag->acts_actor.h[l]; a.dz_out[l] = ag->dzl[l]; }
   a.da_out = ag->dz_act;
   a.metric_partials = ag->metric_partials;
-  const int slabs = launch_fused_actor(a, st);
+  const int slabs = cluster_ok(ag, B) ? launch_cluster_actor(a, st) : launch_fused_actor(a, st);
   const int S = fused_wgrads(ag, ag->net[ACTOR], ag->acts_actor, ag->D, ag->dz_act, 4, B, st);
   int splits[8];
   for (int l = 0; l < 8; ++l) splits[l] = S;
@@ -653,6 +658,11 @@ int gcrl_agent_create(gcrl_agent **out, int device, const gcrl_agent_config *cfg
     ag->dzh = dev_alloc<float>(size_t(mb));
     const char *nf = getenv("GCRL_B200_NO_FUSED");
     ag->use_fused = !(nf && nf[0] == '1');
+    // cluster.cu (layers split over an 8-CTA cluster through DSMEM) is parity-green but measured slower
+    // than the row-slab kernels at B = 256 (0.275 vs 0.160 ms per update, profiles/README.md): opt-in
+    const char *nc = getenv("GCRL_B200_CLUSTER");
+    ag->use_cluster = nc && nc[0] == '1';
+    if (ag->use_fused && ag->use_cluster && cluster_supported(1, D, A, H, L)) cluster_init(D, A, H, L);
     ag->bs = dev_alloc<float>(size_t(mb) * D);
     ag->bns = dev_alloc<float>(size_t(mb) * D);
     ag->ba = dev_alloc<float>(size_t(mb) * A);

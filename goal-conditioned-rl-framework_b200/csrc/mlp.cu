@@ -395,6 +395,7 @@ void launch_head_fwd(const float *Hact, int ldh, const float *W, int ldw, const 
 
 // ---- loss + backward through the skinny output layer ------------------------------------------
 constexpr int kHeadSlabMax = 512;
+constexpr int kHeadColBlock = 64;
 
 template <int NOUT>
 __global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs a, int rows_per_slab) {
@@ -451,48 +452,73 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs a, int rows_p
   }
   __syncthreads();
 
-  if (a.mode != 2 && tid < 3) {          // fixed-order partial sums of the slab's metrics
-    float s = 0.f;
-    for (int i = 0; i < nrows; ++i) s += met_s[i][tid];
-    a.metric_partials[size_t(blockIdx.x) * 4 + tid] = s;
-  }
-  if (a.pB != nullptr && tid >= 32 && tid < 32 + NOUT) {
-    const int n = tid - 32;
-    float s = 0.f;
-    for (int i = 0; i < nrows; ++i) s += dz_s[i][n];
-    a.pB[int64_t(blockIdx.x) * a.b_split_stride + n] = s;
+  if (blockIdx.y == 0) {
+    if (a.mode != 2 && tid < 3) {          // fixed-order partial sums of the slab's metrics
+      float s = 0.f;
+      for (int i = 0; i < nrows; ++i) s += met_s[i][tid];
+      a.metric_partials[size_t(blockIdx.x) * 4 + tid] = s;
+    }
+    if (a.pB != nullptr && tid >= 32 && tid < 32 + NOUT) {
+      const int n = tid - 32;
+      float s = 0.f;
+      for (int i = 0; i < nrows; ++i) s += dz_s[i][n];
+      a.pB[int64_t(blockIdx.x) * a.b_split_stride + n] = s;
+    }
   }
 
-  for (int k = tid; k < a.K; k += blockDim.x) {
-    float w[NOUT], acc[NOUT];
+  // column block blockIdx.y (64 columns): 16 column groups of 4 x 16 row groups; every access is a
+  // 16-byte vector; the per-row-group weight-gradient partials are combined in a fixed order
+  __shared__ float red_s[16][NOUT][kHeadColBlock];
+  const int cgp = tid & 15, rg = tid >> 4;
+  const int k0 = blockIdx.y * kHeadColBlock + cgp * 4;
+  float w[NOUT][4], acc[NOUT][4];
+  bool valid[4];
 #pragma unroll
-    for (int n = 0; n < NOUT; ++n) {
-      w[n] = a.W[size_t(n) * a.ldw + k];
-      acc[n] = 0.f;
+  for (int u = 0; u < 4; ++u) valid[u] = k0 + u < a.K;
+#pragma unroll
+  for (int n = 0; n < NOUT; ++n)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      w[n][u] = valid[u] ? a.W[size_t(n) * a.ldw + k0 + u] : 0.f;
+      acc[n][u] = 0.f;
     }
-    for (int i = 0; i < nrows; ++i) {
+  if (valid[0]) {
+#pragma unroll 4
+    for (int i = rg; i < nrows; i += 16) {
       const size_t m = size_t(r0 + i);
-      const float h = a.Hact[m * a.ldh + k];
-      float dh = 0.f;
+      const float4 hv = *reinterpret_cast<const float4 *>(a.Hact + m * a.ldh + k0);
+      const float h[4] = {valid[0] ? hv.x : 0.f, valid[1] ? hv.y : 0.f, valid[2] ? hv.z : 0.f, valid[3] ? hv.w : 0.f};
+      float dh[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int n = 0; n < NOUT; ++n) {
         const float dz = dz_s[i][n];
-        dh = fmaf(dz, w[n], dh);
-        acc[n] = fmaf(dz, h, acc[n]);
-      }
-      a.dZprev[m * a.lddz + k] = h > 0.f ? dh : dh * kLeakySlope;
-    }
-    if (a.pW != nullptr) {
 #pragma unroll
-      for (int n = 0; n < NOUT; ++n)
-        a.pW[int64_t(blockIdx.x) * a.w_split_stride + size_t(n) * a.ldw + k] = acc[n];
+        for (int u = 0; u < 4; ++u) {
+          dh[u] = fmaf(dz, w[n][u], dh[u]);
+          acc[n][u] = fmaf(dz, h[u], acc[n][u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) dh[u] = h[u] > 0.f ? dh[u] : dh[u] * kLeakySlope;
+      *reinterpret_cast<float4 *>(a.dZprev + m * a.lddz + k0) = make_float4(dh[0], dh[1], dh[2], dh[3]);
     }
   }
-  if (a.pW != nullptr) {  // zero the row padding of the slab
-    for (int k = a.K + tid; k < a.ldw; k += blockDim.x)
+  if (a.pW != nullptr) {
 #pragma unroll
-      for (int n = 0; n < NOUT; ++n)
-        a.pW[int64_t(blockIdx.x) * a.w_split_stride + size_t(n) * a.ldw + k] = 0.f;
+    for (int n = 0; n < NOUT; ++n)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) red_s[rg][n][cgp * 4 + u] = acc[n][u];
+    __syncthreads();
+    for (int idx = tid; idx < NOUT * kHeadColBlock; idx += blockDim.x) {
+      const int n = idx / kHeadColBlock, c = idx - n * kHeadColBlock;
+      const int k = blockIdx.y * kHeadColBlock + c;
+      if (k < a.ldw) {                    // columns K .. ldw-1 (row padding of the slab) receive exact zeros
+        float s = 0.f;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) s += red_s[g][n][c];
+        a.pW[int64_t(blockIdx.x) * a.w_split_stride + size_t(n) * a.ldw + k] = s;
+      }
+    }
   }
 }
 
@@ -501,11 +527,12 @@ int launch_head_bwd(const HeadBwdArgs &a, int max_splits, cudaStream_t st) {
   rows = std::min(kHeadSlabMax, std::max(rows, 16));
   const int slabs = (a.M + rows - 1) / rows;
   if (slabs > max_splits) throw Error(GCRL_ERR_INVALID, "batch too large for head_bwd partial buffers");
+  const dim3 grid(slabs, (a.K + kHeadColBlock - 1) / kHeadColBlock);
   switch (a.nout) {
-    case 1: head_bwd_kernel<1><<<slabs, 256, 0, st>>>(a, rows); break;
-    case 2: head_bwd_kernel<2><<<slabs, 256, 0, st>>>(a, rows); break;
-    case 3: head_bwd_kernel<3><<<slabs, 256, 0, st>>>(a, rows); break;
-    case 4: head_bwd_kernel<4><<<slabs, 256, 0, st>>>(a, rows); break;
+    case 1: head_bwd_kernel<1><<<grid, 256, 0, st>>>(a, rows); break;
+    case 2: head_bwd_kernel<2><<<grid, 256, 0, st>>>(a, rows); break;
+    case 3: head_bwd_kernel<3><<<grid, 256, 0, st>>>(a, rows); break;
+    case 4: head_bwd_kernel<4><<<grid, 256, 0, st>>>(a, rows); break;
     default: throw Error(GCRL_ERR_INVALID, "head width must be 1..4");
   }
   GCRL_LAUNCHED();

@@ -108,6 +108,11 @@ struct FusedActorArgs {
 bool fused_supported(int B, int D, int A, int H, int L);
 int launch_fused_critic(const FusedCriticArgs &a, cudaStream_t st);   // returns the grid (metric slabs)
 int launch_fused_actor(const FusedActorArgs &a, cudaStream_t st);
+// cluster-fused variants (cluster.cu): 8-CTA clusters, layers split by output column over DSMEM
+bool cluster_supported(int B, int D, int A, int H, int L);
+void cluster_init(int D, int A, int H, int L);
+int launch_cluster_critic(const FusedCriticArgs &a, cudaStream_t st);   // returns the number of clusters
+int launch_cluster_actor(const FusedActorArgs &a, cudaStream_t st);
 
 // ---- tensor-core dense layers (tc_gemm.cu): tcgen05 / TMEM / TMA, 3xTF32 split for fp32 accuracy ----
 bool tc_dense_supported(int M, int N, int K);
