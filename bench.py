@@ -178,6 +178,7 @@ def workload_config(args, world):
             "layers": args.layers, "buffer_transitions_per_gpu": args.transitions,
             "parallelism": f"dp{world} (episode-sharded buffer, NCCL gradient all-reduce)" if world > 1 else "single GPU",
             "index_stream": "on-device (value) / host Mersenne-Twister random.sample (e2e)",
+            "engines": "batch <= 1024: row-slab fused fp32 kernels; >= 8192: tcgen05 3xTF32 hidden layers (sweep)",
             "l2": "flushed between timed steps (256 MiB write); buffer (224 MB) larger than L2"}
 
 
@@ -421,6 +422,61 @@ def gpu_main(args):
                 "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                 "traffic": None, "ms_per_launch": ms_k, "algorithmic_bytes_per_transition": alg_bytes,
                 "transitions_per_s": batch / (ms_k * 1e-3)}
+    # the dominant kernel of the step at the headline batch: the critic-phase row-slab kernel
+    # (fp32 FFMA by design below 8192 rows; tensor cores take the hidden layers above that)
+    Hh, Ll = args.hidden, args.layers
+    amac = D * Hh + (Ll - 1) * Hh * Hh + Hh * A
+    cmac = (D + A) * Hh + (Ll - 1) * Hh * Hh + Hh
+    bf16_peak = float(peaks.get("bf16_tflops", 2250.0))
+    if rank == 0:
+        try:
+            msk = C.c_float()
+            check(lib.gcrl_agent_time_critic_kernel(agent._h, B, 200, C.byref(msk), sp))
+            # algorithmic flops per launch: target actor + target critic + critic forward, critic input
+            # gradients through the (L - 1) hidden layers
+            fl = 2.0 * B * (amac + 2 * cmac + (Ll - 1) * Hh * Hh + Hh)
+            ach = fl / (msk.value * 1e-3) / 1e12
+            rooflines[f"fused_critic_kernel_B{B}"] = {
+                "bound": "tensor", "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
+                "traffic": None, "ms_per_launch": msk.value, "algorithmic_flops_per_launch": fl,
+                "note": "fp32 FFMA row-slab kernel (weights streamed from L2 once per 4-row slab); latency-bound "
+                        "at this batch -- the tensor-core path serves batches >= 8192"}
+        except Exception as e:   # noqa: BLE001
+            log(f"[roofline] critic kernel timing skipped: {e}")
+        if sweep_batches:
+            Mt = 65536
+            xt = torch.randn(Mt, Hh, device=dev)
+            wt = torch.randn(Hh, Hh, device=dev) / Hh ** 0.5
+            bt = torch.zeros(Hh, device=dev)
+            yt = torch.empty(Mt, Hh, device=dev)
+
+            def dense(engine):
+                check(lib.gcrl_dense_layer(local, engine, 0, Mt, Hh, Hh, vp(xt.data_ptr()), Hh, vp(wt.data_ptr()), Hh,
+                                           vp(bt.data_ptr()), None, 0, vp(yt.data_ptr()), Hh, sp))
+            for engine, name in ((1, "tc_dense_kernel"), (0, "gemm_kernel_fp32")):
+                try:
+                    for _ in range(3):
+                        dense(engine)
+                    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+                    for i, (a0, a1) in enumerate(evs):
+                        flush.fill_(i & 0xFF)
+                        a0.record(stream)
+                        dense(engine)
+                        a1.record(stream)
+                    torch.cuda.synchronize()
+                    ms_k = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+                    fl = 2.0 * Mt * Hh * Hh
+                    ach = fl / (ms_k * 1e-3) / 1e12
+                    rooflines[f"{name}_M{Mt}_H{Hh}"] = {
+                        "bound": "tensor", "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
+                        "traffic": None, "ms_per_launch": ms_k, "algorithmic_flops_per_launch": fl,
+                        "note": ("tcgen05 kind::tf32, 3 MMAs per product (hi/lo split) for fp32 accuracy: tensor-pipe "
+                                 "work is 3x the algorithmic flops" if engine == 1 else
+                                 "fp32 FFMA tiles (the precision-0 path), for comparison")}
+                except Exception as e:   # noqa: BLE001
+                    log(f"[roofline] dense layer engine {engine} skipped: {e}")
+            del xt, wt, bt, yt
+
     sweep = {}
     for batch in sweep_batches:
         for _ in range(45):
@@ -437,10 +493,14 @@ def gpu_main(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_arm(args, 10 ** 9, 2, seconds=args.cpu_seconds)
+    variants = {}
+    if rank == 0 and world == 1 and not args.no_sweep:
+        variants = time_variants(args, data, E, max_len, dev, local)
     if rank == 0:
-        key = f"her_sample_kernel_B{B}"
+        key = f"fused_critic_kernel_B{B}" if f"fused_critic_kernel_B{B}" in rooflines else f"her_sample_kernel_B{B}"
         roof = dict(rooflines.get(key, {}))
-        roof["kernel"] = "her_sample_kernel"
+        roof["kernel"] = key.rsplit("_B", 1)[0]
+        roof["share_of_step"] = (roof.get("ms_per_launch", 0.0) / (ms / args.steps)) if roof else None
         roof["peak_source"] = peak_src
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -454,6 +514,7 @@ def gpu_main(args):
                     "api": "DDPG.update(step) with host random.sample index stream + metric read-back; "
                            "16 episodes ingested every 40 updates"},
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "rooflines": rooflines, "sweep": sweep,
+            "variants": variants,
             "cpu_baseline": None if cpu is None else {k_: cpu[k_] for k_ in ("value", "unit", "cores", "kind", "sample")},
             "library": os.path.relpath(gcrl_b200.library_path(), ROOT),
             "kernel_launches_total": int(lib.gcrl_kernel_launches()) - launches0,
@@ -461,6 +522,41 @@ def gpu_main(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_variants(args, data, E, max_len, dev, local, steps=60):
+    """updates/s of the other agents behind the same interface (TD3, SAC, TQC) on the same buffer
+    contents and shapes, device index stream, metric read-back every step (their update() is synchronous)."""
+    import torch
+    from gcrl_b200 import SACAgent, TD3Agent, TQCAgent
+    out = {}
+    T = 50
+    for name, cls in (("td3", TD3Agent), ("sac", SACAgent), ("tqc", TQCAgent)):
+        try:
+            cfg = agent_config(args, max_len)
+            cfg.alpha_lr, cfg.alpha_min, cfg.alpha_min_steps = 3e-4, 0.05, 0
+            cfg.ac_update_freq = 2 if name == "td3" else 1
+            cfg.grad_clip = 1.0
+            torch.manual_seed(1898)
+            ag = cls(args.obs + args.goal, args.act, cfg, None, 1, 40, index_source="device", device=local)
+            for e in range(min(E, 2000)):
+                ag.buffer.push_episode(data["s"][e], data["a"][e], data["ns"][e], data["r"][e], data["d"][e],
+                                       data["ag"][e], data["fut"][e])
+            for i in range(5):
+                ag.update(i + 1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(steps):
+                info = ag.update(6 + i)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            assert all(np.isfinite(float(x)) for x in info)
+            out[name] = {"updates_per_s": steps / dt, "ms_per_update": dt / steps * 1e3, "batch": args.batch,
+                         "hidden": args.hidden, "layers": args.layers}
+            del ag
+        except Exception as e:   # noqa: BLE001
+            out[name] = {"error": str(e)}
+    return out
 
 
 def main():

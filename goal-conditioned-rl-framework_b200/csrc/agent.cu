@@ -348,7 +348,7 @@ int fused_wgrads(gcrl_agent *ag, const Net &n, const Acts &acts, int K0, const f
   return launch_multi_wgrad(pr, L + 1, B, ag->slab, kMaxSplits, st);
 }
 
-void fused_critic_phase_grads(gcrl_agent *ag, int B, cudaStream_t st) {
+FusedCriticArgs fused_critic_args(gcrl_agent *ag, int B) {
   FusedCriticArgs a{};
   a.ta = fused_net(ag, ag->net[T_ACTOR]);
   a.tc = fused_net(ag, ag->net[T_CRITIC1]);
@@ -362,6 +362,11 @@ void fused_critic_phase_grads(gcrl_agent *ag, int B, cudaStream_t st) {
   for (int l = 0; l < ag->L; ++l) { a.h_out[l] = ag->acts_c1.h[l]; a.dz_out[l] = ag->dzl[l]; }
   a.dzh_out = ag->dzh; a.y_out = ag->yv; a.q_out = ag->q1;
   a.metric_partials = ag->metric_partials;
+  return a;
+}
+
+void fused_critic_phase_grads(gcrl_agent *ag, int B, cudaStream_t st) {
+  const FusedCriticArgs a = fused_critic_args(ag, B);
   const int slabs = cluster_ok(ag, B) ? launch_cluster_critic(a, st) : launch_fused_critic(a, st);
   const Net &c = ag->net[CRITIC1];
   const int S = fused_wgrads(ag, c, ag->acts_c1, ag->D + ag->A, ag->dzh, 1, B, st);
@@ -892,6 +897,31 @@ int gcrl_agent_update_phase(gcrl_agent *ag, int phase, gcrl_her *buf, int64_t B,
     GCRL_REQUIRE(ag->dp_B == int(B) && ag->dp_flags == flags, "phase 1..3 must follow phase 0 of the same update");
     run_update(ag, int(B), ag->td3 ? ag->noise : nullptr, flags, phase == 1 ? PH_CSTEP : (phase == 2 ? PH_AGRAD : PH_ASTEP), st);
   }
+  GCRL_API_END
+}
+
+int gcrl_agent_time_critic_kernel(gcrl_agent *ag, int64_t B, int iters, float *ms_per_launch, void *stream) {
+  GCRL_API_BEGIN
+  check_batch(ag, B);
+  GCRL_REQUIRE(iters >= 1 && ms_per_launch != nullptr, "bad argument");
+  GCRL_REQUIRE(fused_ok(ag, int(B)), "the fused critic-phase kernel does not serve this batch / shape");
+  GCRL_CUDA(cudaSetDevice(ag->device));
+  cudaStream_t st = as_stream(stream);
+  const FusedCriticArgs a = fused_critic_args(ag, int(B));
+  cudaEvent_t e0, e1;
+  GCRL_CUDA(cudaEventCreate(&e0));
+  GCRL_CUDA(cudaEventCreate(&e1));
+  const bool cl = cluster_ok(ag, int(B));
+  for (int i = 0; i < 3; ++i) cl ? launch_cluster_critic(a, st) : launch_fused_critic(a, st);
+  GCRL_CUDA(cudaEventRecord(e0, st));
+  for (int i = 0; i < iters; ++i) cl ? launch_cluster_critic(a, st) : launch_fused_critic(a, st);
+  GCRL_CUDA(cudaEventRecord(e1, st));
+  GCRL_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  GCRL_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_launch = ms / float(iters);
   GCRL_API_END
 }
 

@@ -307,6 +307,12 @@ int gcrl_sac_act(gcrl_sac *h, int64_t n, const float *obs_host, const float *eps
  *   mode 0: y = leaky(x w^T + bias);  mode 1: y = (x w^T) * leaky'(act) (engine 1 only);
  *   mode 2: y = x w^T + bias.
  * x [M, K] (ldx), w [N, K] (ldw), y [M, N] (ldy); leading dimensions multiples of 4 floats. */
+/* Average duration (CUDA events on `stream`, back to back, warm) of the critic-phase kernel of the
+ * small-batch path (fused.cu / cluster.cu: target actor + target critic + critic forward, Bellman
+ * target, loss, critic input gradients) on the batch left resident by the last update of size B.
+ * Feeds bench.py's roofline object; it recomputes the same activations, no state changes. */
+int gcrl_agent_time_critic_kernel(gcrl_agent *h, int64_t B, int iters, float *ms_per_launch, void *stream);
+
 int gcrl_dense_layer(int device, int engine, int mode, int64_t M, int N, int K, const float *x_dev,
                      int ldx, const float *w_dev, int ldw, const float *bias_dev, const float *act_dev,
                      int ldact, float *y_dev, int ldy, void *stream);
