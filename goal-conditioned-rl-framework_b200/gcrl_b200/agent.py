@@ -298,11 +298,13 @@ class _AgentBase:
         mptr = C.cast(self._metrics, vp) if sync else None
         nptr = vp(noise.data_ptr()) if noise is not None else None
         iptr = None
+        predraw = False
         if batch is None:
             B = self.batch_size
             assert len(self.buffer) >= B, "[ERROR] Not enough in buffer to sample"
             if indices is None and self.index_source == "host":
-                indices = random.sample(range(len(self.buffer)), B)
+                indices = self._take_predrawn(B)
+                predraw = sync and self._dp is None
             if indices is not None:
                 indices = np.ascontiguousarray(indices, np.int64)
                 iptr = np_ptr(indices)
@@ -323,8 +325,15 @@ class _AgentBase:
                 self._dp.average_metrics()
                 check(lib.gcrl_agent_read_metrics(self._h, mptr, st))
         elif batch is None:
-            check(lib.gcrl_agent_update_from_buffer(self._h, bufh, B, iptr, nptr, lr_c, lr_a, flags, mptr,
-                                                    self._stream()))
+            if predraw:
+                # launch asynchronously, draw the NEXT call's positions while the GPU works, then read back
+                check(lib.gcrl_agent_update_from_buffer(self._h, bufh, B, iptr, nptr, lr_c, lr_a, flags, None,
+                                                        self._stream()))
+                self._predraw(B)
+                check(lib.gcrl_agent_read_metrics(self._h, mptr, self._stream()))
+            else:
+                check(lib.gcrl_agent_update_from_buffer(self._h, bufh, B, iptr, nptr, lr_c, lr_a, flags, mptr,
+                                                        self._stream()))
         else:
             check(lib.gcrl_agent_update_batch(self._h, B, *ptrs, nptr, lr_c, lr_a, flags, mptr,
                                               self._stream()))
@@ -332,6 +341,32 @@ class _AgentBase:
         if flags & 1:
             self.actor_scheduler.step()
         return [float(x) for x in self._metrics] if sync else None
+
+    # -- host index stream: latency hiding without changing the Mersenne-Twister stream ---------------
+    # ``random.sample(range(len), B)`` costs ~0.1 ms of host time per update.  The draw for the next
+    # update is made while the GPU executes the current one, and the global ``random`` state is put
+    # back right away; the next update uses the pre-drawn positions only if the state it finds is
+    # exactly the one that was put back (nobody consumed the stream in between, same buffer length and
+    # batch), and then advances the state to where its own draw would have left it.  Any other
+    # consumer (apply_her's randint, select_action's random.random, a reseed) therefore sees precisely
+    # the reference's interleaving.
+    _pre = None
+
+    def _predraw(self, B):
+        n = len(self.buffer)
+        before = random.getstate()
+        idx = random.sample(range(n), B)
+        after = random.getstate()
+        random.setstate(before)
+        self._pre = (before, after, idx, n, B)
+
+    def _take_predrawn(self, B):
+        pre, self._pre = self._pre, None
+        n = len(self.buffer)
+        if pre is not None and pre[3] == n and pre[4] == B and random.getstate() == pre[0]:
+            random.setstate(pre[1])
+            return pre[2]
+        return random.sample(range(n), B)
 
     def read_metrics(self):
         check(lib.gcrl_agent_read_metrics(self._h, C.cast(self._metrics, vp), self._stream()))

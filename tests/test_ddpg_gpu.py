@@ -253,3 +253,36 @@ def test_update_is_deterministic_run_to_run():
     for w1, w2 in zip(outs[0][1], outs[1][1]):
         assert np.array_equal(w1, w2)
     torch.cuda.synchronize()
+
+
+def test_predrawn_host_indices_keep_the_reference_random_stream():
+    """update() pre-draws the next call's positions while the GPU works; every consumer of the global
+    ``random`` stream must still see exactly the reference's interleaving of sample / randint / random."""
+    import random
+    from gcrl_b200 import DDPG
+    from tests.helpers import her_episodes
+    g = load("her_reach_small")
+    ag = DDPG(10, 3, make_config(batch_size=32, max_len=100000), None, 2, 40)
+    eps = her_episodes(g)
+    for ep in eps[:6]:
+        ag.buffer.push_episode(ep["s"], ep["a"], ep["ns"], ep["r"], ep["d"], ep["ag"], ep["fut"])
+    random.seed(7)
+    expect_rng = random.Random(7)
+    n = len(ag.buffer)
+    seen = []
+    real_take = ag._take_predrawn
+    ag._take_predrawn = lambda B: seen.append(list(real_take(B))) or seen[-1]
+    script = ["u", "u", "r", "u", "p", "u", "u", "r", "r", "u"]
+    step = 1
+    for op in script:
+        if op == "u":
+            ag.update(step)
+            step += 1
+            assert seen[-1] == expect_rng.sample(range(n), 32)
+        elif op == "r":                      # another consumer (select_action's random.random, :1348)
+            assert random.random() == expect_rng.random()
+        else:                                # an episode commit changes len(buffer): the pre-draw is void
+            ep = eps[6]
+            ag.buffer.push_episode(ep["s"], ep["a"], ep["ns"], ep["r"], ep["d"], ep["ag"], ep["fut"])
+            n = len(ag.buffer)
+    assert random.random() == expect_rng.random()
