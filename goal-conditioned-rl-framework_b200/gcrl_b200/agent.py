@@ -304,7 +304,7 @@ class _AgentBase:
             assert len(self.buffer) >= B, "[ERROR] Not enough in buffer to sample"
             if indices is None and self.index_source == "host":
                 indices = self._take_predrawn(B)
-                predraw = sync and self._dp is None
+                predraw = sync
             if indices is not None:
                 indices = np.ascontiguousarray(indices, np.int64)
                 iptr = np_ptr(indices)
@@ -322,6 +322,8 @@ class _AgentBase:
                 elif phase == 2 and (flags & 1):
                     self._dp.average((NET_ACTOR,))
             if sync:
+                if predraw:
+                    self._predraw(B)       # host work hidden behind the queued phases and all-reduces
                 self._dp.average_metrics()
                 check(lib.gcrl_agent_read_metrics(self._h, mptr, st))
         elif batch is None:
