@@ -184,10 +184,16 @@ void backward_hidden(gcrl_agent *ag, const Net &n, const float *X, int ldx, int 
     const float *xin = l == 0 ? X : acts.h[l - 1];
     const int ldin = l == 0 ? ldx : ag->ldh;
     const int K = l == 0 ? K0 : ag->H;
-    if (want_wgrad)
-      splits[l] = launch_linear_wgrad(ag->dz[cur], ag->ldh, xin, ldin, ag->partials + n.w_off[l], n.ldw[l],
-                                      ag->slab, ag->partials + n.b_off[l], ag->slab, B, ag->H, K,
-                                      kMaxSplits, st);
+    if (want_wgrad) {
+      const int Kp = (K + 3) & ~3;     // operand rows are zero-padded to ld (layer 0)
+      if (use_tc(ag, B, ag->H, Kp) && tc_wgrad_supported(B, ag->H, Kp))
+        splits[l] = launch_tc_wgrad(ag->dz[cur], ag->ldh, xin, ldin, ag->partials + n.w_off[l], n.ldw[l], ag->slab,
+                                    ag->partials + n.b_off[l], ag->slab, B, ag->H, Kp, kMaxSplits, st);
+      else
+        splits[l] = launch_linear_wgrad(ag->dz[cur], ag->ldh, xin, ldin, ag->partials + n.w_off[l], n.ldw[l],
+                                        ag->slab, ag->partials + n.b_off[l], ag->slab, B, ag->H, K,
+                                        kMaxSplits, st);
+    }
     if (l > 0) {
       if (use_tc(ag, B, ag->H, ag->H))   // dX = dZ Wt^T with the transposed weight copy as the K-major operand
         launch_tc_dense(ag->dz[cur], ag->ldh, n.pT + n.t_off[l], n.ldt[l], nullptr, acts.h[l - 1], ag->ldh,

@@ -117,6 +117,10 @@ int launch_cluster_actor(const FusedActorArgs &a, cudaStream_t st);
 // ---- tensor-core dense layers (tc_gemm.cu): tcgen05 / TMEM / TMA, 3xTF32 split for fp32 accuracy ----
 bool tc_dense_supported(int M, int N, int K);
 void tc_dense_init();
+bool tc_wgrad_supported(int M, int N, int K);
+// tensor-core version of launch_linear_wgrad (same partial-slab contract); returns the number of slabs
+int launch_tc_wgrad(const float *dZ, int lddz, const float *X, int ldx, float *pW, int ldw, int64_t w_split_stride,
+                    float *pB, int64_t b_split_stride, int M, int N, int K, int max_splits, cudaStream_t st);
 // out[M, N] = epilogue(X[M, K] * W[N, K]^T); mode 0: leaky(. + bias), 1: . * leaky'(act), 2: . + bias
 void launch_tc_dense(const float *X, int ldx, const float *W, int ldw, const float *bias, const float *act,
                      int ldact, float *out, int ldo, int M, int N, int K, int mode, cudaStream_t st);

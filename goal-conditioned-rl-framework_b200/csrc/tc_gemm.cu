@@ -103,6 +103,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw(uint32_t saddr) {
          (uint64_t(1) << 46) | (layout << 61);
 }
 
+// MN-major operand (weight gradient): boxes of [16 batch rows][32 features] = 2048 bytes.  For 32-bit
+// MN-major operands the only layout the tensor core accepts is the 128-byte swizzle with 32-byte atoms
+// (cute::UMMA::Layout_MN_SW128_32B_Atom = Swizzle<2,5,2>, layout type 1; TMA: SWIZZLE_128B_ATOM_32B): the
+// swizzle atom is 4 batch rows x 128 bytes, so the K groups inside a box are 512 bytes apart (SBO) and
+// consecutive 32-feature MN blocks are one box apart (LBO).
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
+  return uint64_t((saddr >> 4) & 0x3FFF) | (uint64_t(2048 >> 4) << 16) | (uint64_t(512 >> 4) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(1) << 61);
+}
+
 __device__ __forceinline__ uint32_t rna_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -116,6 +126,10 @@ struct TcArgs {
   int M, N, K;                   // N <= BN * n_tiles
   int mode;                      // 0: leaky(acc + bias); 1: acc * leaky'(act); 2: acc + bias
   int n_tiles, m_tiles;
+  // kind 1 (weight gradient): out[slab][n][k] = sum_{m in slab} A[m][n] B[m][k]; both operands MN-major,
+  // the batch is the reduction; n_tiles = ceil(N / 128), k_tiles = ceil(K / BN); M rows in nslabs slabs
+  int kind, rows_per_slab, nslabs, k_tiles;
+  long long split_stride;
   int dbg;                       // timing experiments only (GCRL_TC_DBG): 1 skip split, 2 skip stores, 4 one MMA per k step
 };
 
@@ -165,22 +179,49 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int nk = (a.K + BKF - 1) / BKF;
-  const int total_tiles = a.m_tiles * a.n_tiles;
+  const bool wg = a.kind == 1;
+  const int total_tiles = wg ? a.nslabs * a.n_tiles * a.k_tiles : a.m_tiles * a.n_tiles;
+  // tile decode.  dense: (m block, n block), K tiles of BKF columns.  wgrad: (slab, n block, k block),
+  // "K tiles" = 16 batch rows each.
+  struct Tile { int m0, n0, nk, slab; };
+  auto decode = [&](int t) {
+    Tile ti;
+    if (!wg) {
+      ti.m0 = (t / a.n_tiles) * BM; ti.n0 = (t % a.n_tiles) * BN; ti.nk = (a.K + BKF - 1) / BKF; ti.slab = 0;
+    } else {
+      const int per = a.n_tiles * a.k_tiles;
+      ti.slab = t / per;
+      const int rem = t - ti.slab * per;
+      ti.m0 = (rem / a.k_tiles) * BM;            // first output row (n index) of the tile
+      ti.n0 = (rem % a.k_tiles) * BN;            // first output column (k index)
+      const int r0 = ti.slab * a.rows_per_slab;
+      ti.nk = (min(a.rows_per_slab, a.M - r0) + 15) / 16;
+    }
+    return ti;
+  };
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int m0 = (t / a.n_tiles) * BM, n0 = (t % a.n_tiles) * BN;
-        for (int kb = 0; kb < nk; ++kb, ++it) {
+        const Tile ti = decode(t);
+        for (int kb = 0; kb < ti.nk; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(empty(s), ((it / STAGES) & 1) ^ 1);
           mbar_expect_tx(full(s), S::kA + S::kB);
           const uint32_t st = base + s * S::kStage;
-          tma_load_2d(st, &tmA, full(s), kb * BKF, m0);
-          tma_load_2d(st + 2 * S::kA, &tmB, full(s), kb * BKF, n0);
+          if (!wg) {
+            tma_load_2d(st, &tmA, full(s), kb * BKF, ti.m0);
+            tma_load_2d(st + 2 * S::kA, &tmB, full(s), kb * BKF, ti.n0);
+          } else {
+            // boxes of 16 batch rows x 32 features (128-byte swizzle, 32-byte atoms), one per 32-feature MN block
+            const int r = ti.slab * a.rows_per_slab + kb * 16;
+#pragma unroll 1
+            for (int b = 0; b < BM / 32; ++b) tma_load_2d(st + b * 2048, &tmA, full(s), ti.m0 + 32 * b, r);
+#pragma unroll 1
+            for (int b = 0; b < BN / 32; ++b) tma_load_2d(st + 2 * S::kA + b * 2048, &tmB, full(s), ti.n0 + 32 * b, r);
+          }
         }
       }
     }
@@ -189,9 +230,12 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (lane == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6) = 1, A/B = TF32 [7,10),[10,13) = 2,
       // K-major both, N >> 3 at [17,23), M >> 4 at [24,29)
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+      // kind 1: A and B MN-major (bits 15, 16)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24) |
+                             (wg ? (3u << 15) : 0u);
       uint32_t it = 0, tile_it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
+        const int nk = decode(t).nk;
         const int as = tile_it & 1;
         mbar_wait(tempty(as), ((tile_it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -201,11 +245,15 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mbar_wait(ready(s), (it / STAGES) & 1);
           tc_fence_after();
           const uint32_t st = base + s * S::kStage;
-          const uint64_t a_hi = umma_desc_sw(st), a_lo = umma_desc_sw(st + S::kA);
-          const uint64_t b_hi = umma_desc_sw(st + 2 * S::kA), b_lo = umma_desc_sw(st + 2 * S::kA + S::kB);
+          const uint64_t a_hi = wg ? umma_desc_mn(st) : umma_desc_sw(st);
+          const uint64_t a_lo = wg ? umma_desc_mn(st + S::kA) : umma_desc_sw(st + S::kA);
+          const uint64_t b_hi = wg ? umma_desc_mn(st + 2 * S::kA) : umma_desc_sw(st + 2 * S::kA);
+          const uint64_t b_lo = wg ? umma_desc_mn(st + 2 * S::kA + S::kB) : umma_desc_sw(st + 2 * S::kA + S::kB);
 #pragma unroll
-          for (int k = 0; k < BKF / 8; ++k) {          // UMMA K = 8 for tf32 (32 bytes): +2 in the >>4 address
-            const uint64_t ko = uint64_t(k * 2);
+          for (int k = 0; k < BKF / 8; ++k) {
+            // UMMA K = 8 for tf32.  K-major: 32 bytes along the swizzled row (+2 in the >>4 address);
+            // MN-major: the next 8-row group of every box (+1024 bytes)
+            const uint64_t ko = wg ? uint64_t(k * (1024 >> 4)) : uint64_t(k * 2);
             umma_tf32(d, a_lo + ko, b_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
             if (!(a.dbg & 4)) {
               umma_tf32(d, a_hi + ko, b_lo + ko, idesc, 1u);
@@ -222,7 +270,10 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int q = warp & 3;
     uint32_t tile_it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
-      const int m0 = (t / a.n_tiles) * BM, n0 = (t % a.n_tiles) * BN;
+      const Tile ti = decode(t);
+      const int m0 = ti.m0, n0 = ti.n0;
+      const int rows_valid = wg ? a.N : a.M, cols_valid = wg ? a.ldo : a.N;
+      float *const obase = a.out + (wg ? size_t(ti.slab) * size_t(a.split_stride) : size_t(0));
       const int as = tile_it & 1;
       mbar_wait(tfull(as), (tile_it >> 1) & 1);
       tc_fence_after();
@@ -243,9 +294,9 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                        : "memory");
         __syncwarp();
         const int col = n0 + c + sub_c;
-        if (col < a.N && !(a.dbg & 2)) {                // N is a multiple of 4 (padded leading dims)
+        if (col < cols_valid && !(a.dbg & 2)) {         // widths are multiples of 4 (padded leading dims)
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (a.mode != 1) bv = __ldg(reinterpret_cast<const float4 *>(a.bias + col));
+          if (a.mode == 0 || a.mode == 2) bv = __ldg(reinterpret_cast<const float4 *>(a.bias + col));
 #pragma unroll
           for (int r8 = 0; r8 < 8; ++r8) {
             const int lr = r8 * 4 + sub_r;
@@ -254,8 +305,10 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
                          : "r"(stg + uint32_t(lr * kStgLd + sub_c) * 4));
-            if (row < a.M) {
-              if (a.mode == 1) {
+            if (row < rows_valid) {
+              if (a.mode == 3) {
+                // plain store (weight-gradient partial slab)
+              } else if (a.mode == 1) {
                 const float4 h = *reinterpret_cast<const float4 *>(a.act + size_t(row) * a.ldact + col);
                 x.x = h.x > 0.f ? x.x : x.x * kLeakySlope;
                 x.y = h.y > 0.f ? x.y : x.y * kLeakySlope;
@@ -270,7 +323,7 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                   x.w = x.w > 0.f ? x.w : x.w * kLeakySlope;
                 }
               }
-              *reinterpret_cast<float4 *>(a.out + size_t(row) * a.ldo + col) = x;
+              *reinterpret_cast<float4 *>(obase + size_t(row) * a.ldo + col) = x;
             }
           }
         }
@@ -284,6 +337,7 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int tid = threadIdx.x - 6 * 32;
     uint32_t it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int nk = decode(t).nk;
       for (int kb = 0; kb < nk; ++kb, ++it) {
         const int s = it % STAGES;
         mbar_wait(full(s), (it / STAGES) & 1);
@@ -357,19 +411,41 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// fp32 row-major [rows, cols] with leading dimension ld -> box of (box_rows x 32 floats), 128-byte swizzle,
-// out-of-bounds elements read as zero (ragged M / K tails).
-CUtensorMap make_map(const float *ptr, int64_t rows, int cols, int ld, int box_rows) {
+// fp32 row-major [rows, cols] with leading dimension ld -> box of (box_rows x box_cols floats), swizzle span =
+// the box row (64 or 128 bytes); out-of-bounds elements read as zero (ragged M / N / K tails).
+CUtensorMap make_map(const float *ptr, int64_t rows, int cols, int ld, int box_rows, int box_cols = BKF,
+                     bool atom32 = false) {
   CUtensorMap m;
   const cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
   const cuuint64_t strides[1] = {cuuint64_t(ld) * 4};
-  const cuuint32_t box[2] = {cuuint32_t(BKF), cuuint32_t(box_rows)};
+  const cuuint32_t box[2] = {cuuint32_t(box_cols), cuuint32_t(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box,
-                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, ROWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                        : (box_cols * 4 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B),
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw Error(GCRL_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string(int(r)) + ")");
   return m;
+}
+
+// pB[slab][n] = sum over the slab's rows of dZ[m][n]   (bias gradient partials; fixed order)
+__global__ void __launch_bounds__(128)
+colsum_partials_kernel(const float *__restrict__ dZ, int lddz, int M, int N, int rows_per_slab, float *__restrict__ pB,
+                       long long split_stride) {
+  const int n = blockIdx.y * 128 + threadIdx.x;
+  if (n >= N) return;
+  const int r0 = blockIdx.x * rows_per_slab, r1 = min(M, r0 + rows_per_slab);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int m = r0;
+  for (; m + 3 < r1; m += 4) {
+    s0 += dZ[size_t(m) * lddz + n];
+    s1 += dZ[size_t(m + 1) * lddz + n];
+    s2 += dZ[size_t(m + 2) * lddz + n];
+    s3 += dZ[size_t(m + 3) * lddz + n];
+  }
+  for (; m < r1; ++m) s0 += dZ[size_t(m) * lddz + n];
+  pB[(long long)blockIdx.x * split_stride + n] = (s0 + s1) + (s2 + s3);
 }
 
 template <int BN>
@@ -385,7 +461,8 @@ void set_attr() {
 template <int BN>
 void launch_bn(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcArgs &a, cudaStream_t st) {
   set_attr<BN>();
-  const int grid = std::min(a.m_tiles * a.n_tiles, sm_count());
+  const int tiles = a.kind == 1 ? a.nslabs * a.n_tiles * a.k_tiles : a.m_tiles * a.n_tiles;
+  const int grid = std::min(tiles, sm_count());
   tc_dense_kernel<BN><<<grid, kTcThreads, TcSmem<BN>::kBytes, st>>>(tmA, tmB, a);
   GCRL_LAUNCHED();
 }
@@ -424,6 +501,45 @@ void launch_tc_dense(const float *X, int ldx, const float *W, int ldw, const flo
   else launch_bn<256>(tmA, tmB, a, st);
 }
 
+bool tc_wgrad_supported(int M, int N, int K) {
+  return M >= 16 && N >= 4 && (N % 4) == 0 && K >= 4 && (K % 4) == 0;
+}
+
+// Split-batch partial weight gradients on the tensor cores (same contract as launch_linear_wgrad):
+//   pW[s][N][ldw] = sum_{m in slab s} dZ[m,n] X[m,k],   pB[s][N] = sum_{m in slab s} dZ[m,n]
+int launch_tc_wgrad(const float *dZ, int lddz, const float *X, int ldx, float *pW, int ldw, int64_t w_split_stride,
+                    float *pB, int64_t b_split_stride, int M, int N, int K, int max_splits, cudaStream_t st) {
+  GCRL_REQUIRE(tc_wgrad_supported(M, N, K), "shape not supported by the tensor-core weight-gradient kernel");
+  GCRL_REQUIRE((lddz % 4) == 0 && (ldx % 4) == 0 && (ldw % 4) == 0, "leading dimensions must be multiples of 4");
+  const int BN = K <= 64 ? 64 : (K <= 128 ? 128 : 256);
+  TcArgs a{};
+  a.kind = 1; a.mode = 3;
+  a.out = pW; a.ldo = ldw;
+  a.M = M; a.N = N; a.K = K;
+  a.n_tiles = (N + BM - 1) / BM;
+  a.k_tiles = (std::max(K, ldw) + BN - 1) / BN;      // every column of the padded slab rows is written
+  a.m_tiles = 0;
+  const int per = a.n_tiles * a.k_tiles;
+  // slabs: fill the SMs, and keep the rows accumulated per TMEM tile <= 512 (the tensor core's fp32
+  // accumulation error grows linearly with the number of MMAs chained into one accumulator; the slab
+  // partials are summed in plain fp32 afterwards)
+  int slabs = std::max(1, std::min(max_splits, std::max(sm_count() / per, (M + 511) / 512)));
+  int rows = ((M + slabs - 1) / slabs + 15) & ~15;
+  slabs = (M + rows - 1) / rows;
+  a.rows_per_slab = rows; a.nslabs = slabs; a.split_stride = w_split_stride;
+  if (const char *e = getenv("GCRL_TC_DBG")) a.dbg = atoi(e);
+  const CUtensorMap tmA = make_map(dZ, M, N, lddz, 16, 32, true);
+  const CUtensorMap tmB = make_map(X, M, K, ldx, 16, 32, true);
+  if (BN == 64) launch_bn<64>(tmA, tmB, a, st);
+  else if (BN == 128) launch_bn<128>(tmA, tmB, a, st);
+  else launch_bn<256>(tmA, tmB, a, st);
+  if (pB != nullptr) {
+    colsum_partials_kernel<<<dim3(slabs, (N + 127) / 128), 128, 0, st>>>(dZ, lddz, M, N, rows, pB, b_split_stride);
+    GCRL_LAUNCHED();
+  }
+  return slabs;
+}
+
 }  // namespace gcrl
 
 extern "C" int gcrl_dense_layer(int device, int engine, int mode, int64_t M, int N, int K, const float *x_dev,
@@ -441,5 +557,22 @@ extern "C" int gcrl_dense_layer(int device, int engine, int mode, int64_t M, int
     GCRL_REQUIRE(engine == 0 && mode != 1, "engine 0 (fp32 FFMA) implements modes 0 and 2");
     launch_linear_fwd(x_dev, ldx, w_dev, ldw, bias_dev, y_dev, ldy, int(M), N, K, mode == 0 ? ACT_LEAKY : ACT_NONE, st);
   }
+  GCRL_API_END
+}
+
+extern "C" int gcrl_dense_wgrad(int device, int engine, int64_t M, int N, int K, const float *dz_dev, int lddz,
+                                const float *x_dev, int ldx, float *pw_dev, int ldw, int64_t w_split_stride,
+                                float *pb_dev, int64_t b_split_stride, int max_splits, int *splits_out, void *stream) {
+  GCRL_API_BEGIN
+  using namespace gcrl;
+  GCRL_REQUIRE(dz_dev && x_dev && pw_dev && splits_out && M >= 1 && M < (int64_t(1) << 31), "bad argument");
+  GCRL_REQUIRE(engine == 0 || engine == 1, "engine must be 0 (fp32 FFMA) or 1 (tensor cores)");
+  GCRL_CUDA(cudaSetDevice(device));
+  cudaStream_t st = as_stream(stream);
+  *splits_out = engine == 1
+                    ? launch_tc_wgrad(dz_dev, lddz, x_dev, ldx, pw_dev, ldw, w_split_stride, pb_dev, b_split_stride, int(M),
+                                      N, K, max_splits, st)
+                    : launch_linear_wgrad(dz_dev, lddz, x_dev, ldx, pw_dev, ldw, w_split_stride, pb_dev, b_split_stride,
+                                          int(M), N, K, max_splits, st);
   GCRL_API_END
 }

@@ -102,6 +102,8 @@ SIGNATURES = {
     "gcrl_sac_act": (C.c_int, [vp, c_i64, vp, vp, vp, vp]),
     # diagnostics
     "gcrl_agent_time_critic_kernel": (C.c_int, [vp, c_i64, C.c_int, C.POINTER(c_f32), vp]),
+    "gcrl_dense_wgrad": (C.c_int, [C.c_int, C.c_int, c_i64, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, c_i64,
+                                   vp, c_i64, C.c_int, C.POINTER(C.c_int), vp]),
     "gcrl_dense_layer": (C.c_int, [C.c_int, C.c_int, C.c_int, c_i64, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp,
                                    vp, C.c_int, vp, C.c_int, vp]),
 }

@@ -317,6 +317,14 @@ int gcrl_dense_layer(int device, int engine, int mode, int64_t M, int N, int K, 
                      int ldx, const float *w_dev, int ldw, const float *bias_dev, const float *act_dev,
                      int ldact, float *y_dev, int ldy, void *stream);
 
+/* Split-batch weight gradient of one dense layer (autograd of nn.Linear over the batch):
+ *   pw[s][n][k] = sum_{m in slab s} dz[m, n] x[m, k],  pb[s][n] = sum_{m in slab s} dz[m, n]
+ * for s < *splits_out <= max_splits slabs of batch rows (the caller sums the slabs in order).
+ * engine 0: fp32 FFMA tiles; engine 1: tcgen05, MN-major operands, 3xTF32 split. */
+int gcrl_dense_wgrad(int device, int engine, int64_t M, int N, int K, const float *dz_dev, int lddz,
+                     const float *x_dev, int ldx, float *pw_dev, int ldw, int64_t w_split_stride,
+                     float *pb_dev, int64_t b_split_stride, int max_splits, int *splits_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,3 +57,33 @@ def test_tc_dense_strided_operands_and_zero_padding():
     want = xs[:, :K].double() @ ws[:, :K].double().T + b.double()
     assert ((ys[:, :N].double() - want).abs().max() / want.abs().max()).item() <= 1e-5
     assert float(ys[:, N:].abs().max()) == 0.0          # columns beyond N untouched
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 128, 32), (4096, 256, 256), (5000, 64, 64), (3000, 256, 24), (8192, 512, 512),
+                                   (777, 96, 100), (2048, 4, 64), (16, 256, 256), (65536, 256, 256)])
+def test_tc_wgrad_matches_float64(M, N, K):
+    """Tensor-core weight gradient (MN-major operands, 32-byte-atom swizzle, split batch): the summed
+    partial slabs against dZ^T X in float64; row padding of every slab exactly zero.  Tolerance 1e-5
+    max-norm relative (observed 1e-7 .. 7e-6, growing with the rows accumulated per TMEM tile)."""
+    import ctypes as C
+    import torch
+    from gcrl_b200._lib import check, lib, vp
+    torch.manual_seed(M + N + K)
+    dz = torch.randn(M, N, device="cuda") / M ** 0.5
+    x = torch.randn(M, K, device="cuda")
+    ldw = (K + 3) // 4 * 4 + 4
+    stride = N * ldw + 8
+    pw = torch.full((128, stride), float("nan"), device="cuda")
+    pb = torch.full((128, N + 4), float("nan"), device="cuda")
+    sp = C.c_int()
+    check(lib.gcrl_dense_wgrad(0, 1, M, N, K, vp(dz.data_ptr()), N, vp(x.data_ptr()), K, vp(pw.data_ptr()), ldw, stride,
+                               vp(pb.data_ptr()), N + 4, 128, C.byref(sp), vp(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    S = sp.value
+    assert 1 <= S <= 128
+    W = pw[:S, :N * ldw].double().sum(0).reshape(N, ldw)
+    want = dz.double().T @ x.double()
+    assert ((W[:, :K] - want).abs().max() / want.abs().max()).item() <= 1e-5
+    assert float(W[:, K:].abs().max()) == 0.0
+    wb = dz.double().sum(0)
+    assert ((pb[:S, :N].double().sum(0) - wb).abs().max() / wb.abs().max()).item() <= 1e-5
