@@ -178,7 +178,7 @@ def workload_config(args, world):
             "layers": args.layers, "buffer_transitions_per_gpu": args.transitions,
             "parallelism": f"dp{world} (episode-sharded buffer, NCCL gradient all-reduce)" if world > 1 else "single GPU",
             "index_stream": "on-device (value) / host Mersenne-Twister random.sample (e2e)",
-            "engines": "batch <= 1024: row-slab fused fp32 kernels; >= 8192: tcgen05 3xTF32 hidden layers (sweep)",
+            "engines": "batch <= 1024: row-slab fused fp32 kernels; >= 2048: tcgen05 3xTF32 hidden layers (sweep)",
             "l2": "flushed between timed steps (256 MiB write); buffer (224 MB) larger than L2"}
 
 
@@ -423,7 +423,7 @@ def gpu_main(args):
                 "traffic": None, "ms_per_launch": ms_k, "algorithmic_bytes_per_transition": alg_bytes,
                 "transitions_per_s": batch / (ms_k * 1e-3)}
     # the dominant kernel of the step at the headline batch: the critic-phase row-slab kernel
-    # (fp32 FFMA by design below 8192 rows; tensor cores take the hidden layers above that)
+    # (fp32 FFMA by design below 2048 rows; tensor cores take the hidden layers above that)
     Hh, Ll = args.hidden, args.layers
     amac = D * Hh + (Ll - 1) * Hh * Hh + Hh * A
     cmac = (D + A) * Hh + (Ll - 1) * Hh * Hh + Hh
@@ -440,7 +440,7 @@ def gpu_main(args):
                 "bound": "tensor", "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
                 "traffic": None, "ms_per_launch": msk.value, "algorithmic_flops_per_launch": fl,
                 "note": "fp32 FFMA row-slab kernel (weights streamed from L2 once per 4-row slab); latency-bound "
-                        "at this batch -- the tensor-core path serves batches >= 8192"}
+                        "at this batch -- the tensor-core path serves batches >= 2048"}
         except Exception as e:   # noqa: BLE001
             log(f"[roofline] critic kernel timing skipped: {e}")
         if sweep_batches:

@@ -150,7 +150,7 @@ namespace {
 
 // Tensor-core (tcgen05, 3xTF32) dense layers: large batches only -- below ~1k rows a 128-row tile
 // grid cannot fill the 148 SMs and the fp32 tiles / row-slab kernels win.
-constexpr int kTcMinBatch = 8192;     // 64 row tiles of 128: enough CTAs in flight to beat the fp32 tiles
+constexpr int kTcMinBatch = 2048;     // measured break-even with the fp32 tiles (the column tile narrows to fill the SMs)
 bool use_tc(const gcrl_agent *ag, int B, int N, int K) {
   if (!tc_dense_supported(B, N, K)) return false;
   return ag->cfg.precision == 2 ? B >= 128 : (ag->cfg.precision == 1 && B >= kTcMinBatch);

@@ -487,7 +487,12 @@ void launch_tc_dense(const float *X, int ldx, const float *W, int ldw, const flo
                      int ldact, float *out, int ldo, int M, int N, int K, int mode, cudaStream_t st) {
   GCRL_REQUIRE(tc_dense_supported(M, N, K), "shape not supported by the tensor-core dense kernel");
   GCRL_REQUIRE((ldx % 4) == 0 && (ldw % 4) == 0 && (ldo % 4) == 0, "leading dimensions must be multiples of 4");
-  const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  // column tile: as wide as the layer when the row tiles alone fill the SMs (the activation tile is then
+  // loaded and split once), narrower when the batch is small so that more CTAs share the work
+  int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  const int m_tiles_ = (M + BM - 1) / BM;
+  while (BN > 64 && m_tiles_ * ((N + BN - 1) / BN) < (sm_count() * 3) / 4) BN >>= 1;
+  if (const char *e = getenv("GCRL_TC_BN")) BN = atoi(e);
   TcArgs a{};
   a.out = out; a.ldo = ldo; a.bias = bias; a.act = act; a.ldact = ldact;
   a.M = M; a.N = N; a.K = K; a.mode = mode;

@@ -116,7 +116,7 @@ class _AgentBase:
 
     def __init__(self, obs_dim, ac_dim, config, weights, nenvs, gradient_step, *,
                  index_source="host", device=0, max_batch=None, seed=1898, precision=1):
-        """precision: 1 (default) runs the hidden-layer GEMMs of batches >= 8192 on the tcgen05 tensor
+        """precision: 1 (default) runs the hidden-layer GEMMs of batches >= 2048 on the tcgen05 tensor
         cores with the 3xTF32 split (fp32-level accuracy, rel ~2e-6 per layer); 2 does so for every
         batch >= 128; 0 keeps every GEMM on the fp32 FFMA tiles."""
         self._init_common(obs_dim, ac_dim, config, nenvs, gradient_step, index_source, device, seed)

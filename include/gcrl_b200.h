@@ -143,7 +143,7 @@ typedef struct gcrl_agent_config {
   float weight_decay;    /* 0 = Adam (DDPG); 0.01 = AdamW default (TD3)                */
   int32_t precision;     /* 0 = fp32 FFMA everywhere; 1 = hidden-layer forward / input-gradient
                             GEMMs on tcgen05 tensor cores (3xTF32 split, fp32-level accuracy)
-                            once the batch reaches 8192 rows; 2 = the same for every batch
+                            once the batch reaches 2048 rows; 2 = the same for every batch
                             >= 128 rows (tests)                                           */
   int32_t reserved;
 } gcrl_agent_config;
