@@ -770,6 +770,59 @@ int gcrl_agent_get_layer(gcrl_agent *ag, int net, int layer, float *weight_host,
   GCRL_API_END
 }
 
+// Adam state of one layer of a trainable network, in the layout of set_layer / get_layer
+// (exp_avg = m, exp_avg_sq = v of torch.optim.Adam); `set` != 0 uploads, else downloads.
+static int adam_layer_io(gcrl_agent *ag, int net, int layer, float *m_w, float *m_b, float *v_w, float *v_b, int set,
+                         void *stream) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(ag && net >= 0 && net < NUM_NETS && ag->has[net] && ag->net[net].m, "bad (or non-trainable) network id");
+  Net &n = ag->net[net];
+  GCRL_REQUIRE(layer >= 0 && layer < n.layers && m_w && m_b && v_w && v_b, "bad layer / NULL data");
+  GCRL_CUDA(cudaSetDevice(ag->device));
+  cudaStream_t st = as_stream(stream);
+  const int o = n.out_d[layer], i = n.in_d[layer], ld = n.ldw[layer];
+  std::vector<float> padded(size_t(o) * ld + pad4(o), 0.f);
+  float *dev[2] = {n.m, n.v};
+  float *hw[2] = {m_w, v_w}, *hb[2] = {m_b, v_b};
+  for (int k = 0; k < 2; ++k) {
+    if (set) {
+      std::fill(padded.begin(), padded.end(), 0.f);
+      for (int r = 0; r < o; ++r) std::memcpy(&padded[size_t(r) * ld], hw[k] + size_t(r) * i, size_t(i) * 4);
+      std::memcpy(&padded[size_t(o) * ld], hb[k], size_t(o) * 4);
+      GCRL_CUDA(cudaMemcpyAsync(dev[k] + n.w_off[layer], padded.data(), padded.size() * 4, cudaMemcpyHostToDevice, st));
+      GCRL_CUDA(cudaStreamSynchronize(st));
+    } else {
+      GCRL_CUDA(cudaMemcpyAsync(padded.data(), dev[k] + n.w_off[layer], padded.size() * 4, cudaMemcpyDeviceToHost, st));
+      GCRL_CUDA(cudaStreamSynchronize(st));
+      for (int r = 0; r < o; ++r) std::memcpy(hw[k] + size_t(r) * i, &padded[size_t(r) * ld], size_t(i) * 4);
+      std::memcpy(hb[k], &padded[size_t(o) * ld], size_t(o) * 4);
+    }
+  }
+  GCRL_API_END
+}
+
+int gcrl_agent_get_adam_layer(gcrl_agent *ag, int net, int layer, float *m_w, float *m_b, float *v_w, float *v_b,
+                              void *stream) {
+  return adam_layer_io(ag, net, layer, m_w, m_b, v_w, v_b, 0, stream);
+}
+int gcrl_agent_set_adam_layer(gcrl_agent *ag, int net, int layer, const float *m_w, const float *m_b, const float *v_w,
+                              const float *v_b, void *stream) {
+  return adam_layer_io(ag, net, layer, const_cast<float *>(m_w), const_cast<float *>(m_b), const_cast<float *>(v_w),
+                       const_cast<float *>(v_b), 1, stream);
+}
+int gcrl_agent_get_adam_step(gcrl_agent *ag, int net, int *step) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(ag && step && net >= 0 && net < NUM_NETS && ag->has[net] && ag->net[net].m, "bad network id");
+  *step = ag->net[net].adam_t;
+  GCRL_API_END
+}
+int gcrl_agent_set_adam_step(gcrl_agent *ag, int net, int step) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(ag && step >= 0 && net >= 0 && net < NUM_NETS && ag->has[net] && ag->net[net].m, "bad network id");
+  ag->net[net].adam_t = step;
+  GCRL_API_END
+}
+
 int gcrl_agent_hard_update(gcrl_agent *ag, void *stream) {
   GCRL_API_BEGIN
   GCRL_REQUIRE(ag != nullptr, "agent handle is NULL");

@@ -344,6 +344,62 @@ class _AgentBase:
             self.actor_scheduler.step()
         return [float(x) for x in self._metrics] if sync else None
 
+    # -- true resume: everything update() depends on, beyond the reference's weight files ----
+    def _all_nets(self):
+        return [n for n in range(6) if self._num_layers(n) > 0]
+
+    def _trainable_nets(self):
+        return (NET_ACTOR,) + tuple(self._trainable_critics())
+
+    def state_dict(self):
+        """Weights of every network (targets included), Adam moments and step counts, both learning-rate
+        schedules and the PER beta schedule: restoring it makes the next update() bit-identical to the
+        one an uninterrupted run would have made on the same batch."""
+        import torch
+        out = {"algo": self.ALGO, "nets": {}, "adam": {}, "beta": self.beta}
+        for net in self._all_nets():
+            out["nets"][net] = [(torch.from_numpy(w), torch.from_numpy(b)) for w, b in self._get_layers(net)]
+        for net in self._trainable_nets():
+            layers = []
+            for layer, (w, b) in enumerate(self._get_layers(net)):
+                mw, vw = np.empty_like(w), np.empty_like(w)
+                mb, vb = np.empty_like(b), np.empty_like(b)
+                check(lib.gcrl_agent_get_adam_layer(self._h, net, layer, np_ptr(mw), np_ptr(mb), np_ptr(vw), np_ptr(vb),
+                                                    self._stream()))
+                layers.append(tuple(torch.from_numpy(x) for x in (mw, mb, vw, vb)))
+            step = C.c_int()
+            check(lib.gcrl_agent_get_adam_step(self._h, net, C.byref(step)))
+            out["adam"][net] = {"step": int(step.value), "layers": layers}
+        for name, sch in (("actor_scheduler", self.actor_scheduler), ("critic_scheduler", self.critic_scheduler)):
+            out[name] = {"last_epoch": sch.last_epoch, "lr": sch.lr}
+        return out
+
+    def load_state_dict(self, sd):
+        if sd["algo"] != self.ALGO:
+            raise ValueError("checkpoint belongs to a different agent type")
+        for net, layers in sd["nets"].items():
+            self._set_layers(int(net), [(w.numpy(), b.numpy()) for w, b in layers])
+        for net, st in sd["adam"].items():
+            for layer, arrs in enumerate(st["layers"]):
+                mw, mb, vw, vb = (np.ascontiguousarray(x.numpy(), np.float32) for x in arrs)
+                check(lib.gcrl_agent_set_adam_layer(self._h, int(net), layer, np_ptr(mw), np_ptr(mb), np_ptr(vw),
+                                                    np_ptr(vb), self._stream()))
+            check(lib.gcrl_agent_set_adam_step(self._h, int(net), int(st["step"])))
+        for name in ("actor_scheduler", "critic_scheduler"):
+            sch = getattr(self, name)
+            sch.last_epoch, sch.lr = int(sd[name]["last_epoch"]), float(sd[name]["lr"])
+        self.beta = sd["beta"]
+
+    def save_checkpoint(self, path: str):
+        """save_weights(path) (the reference's files) plus ``trainer_state.pt`` for a true resume."""
+        import torch
+        self.save_weights(path)
+        torch.save(self.state_dict(), os.path.join(path, "trainer_state.pt"))
+
+    def load_checkpoint(self, path: str):
+        import torch
+        self.load_state_dict(torch.load(os.path.join(path, "trainer_state.pt"), map_location="cpu", weights_only=False))
+
     # -- host index stream: latency hiding without changing the Mersenne-Twister stream ---------------
     # ``random.sample(range(len), B)`` costs ~0.1 ms of host time per update.  The draw for the next
     # update is made while the GPU executes the current one, and the global ``random`` state is put

@@ -161,6 +161,15 @@ int gcrl_agent_set_layer(gcrl_agent *h, int net, int layer, const float *weight_
                          const float *bias_host, void *stream);
 int gcrl_agent_get_layer(gcrl_agent *h, int net, int layer, float *weight_host,
                          float *bias_host, void *stream);
+/* Optimiser state for a true resume (the reference checkpoints weights only, src/env.py:430-440,
+ * so its "resume" restarts Adam from zero): exp_avg / exp_avg_sq of torch.optim.Adam for one layer of
+ * a trainable network (0 actor, 1 critic, 4 critic_2), same layout as get_layer, and the step count. */
+int gcrl_agent_get_adam_layer(gcrl_agent *h, int net, int layer, float *m_weight, float *m_bias,
+                              float *v_weight, float *v_bias, void *stream);
+int gcrl_agent_set_adam_layer(gcrl_agent *h, int net, int layer, const float *m_weight, const float *m_bias,
+                              const float *v_weight, const float *v_bias, void *stream);
+int gcrl_agent_get_adam_step(gcrl_agent *h, int net, int *step);
+int gcrl_agent_set_adam_step(gcrl_agent *h, int net, int step);
 /* update_target_network(hard_update=True), src/agent.py:1255-1258 */
 int gcrl_agent_hard_update(gcrl_agent *h, void *stream);
 /* Optimiser state is zeroed (Adam step counters too): a fresh torch.optim.Adam. */

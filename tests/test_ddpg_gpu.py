@@ -286,3 +286,39 @@ def test_predrawn_host_indices_keep_the_reference_random_stream():
             ag.buffer.push_episode(ep["s"], ep["a"], ep["ns"], ep["r"], ep["d"], ep["ag"], ep["fut"])
             n = len(ag.buffer)
     assert random.random() == expect_rng.random()
+
+
+@pytest.mark.parametrize("algo", ["ddpg", "td3"])
+def test_true_resume_is_bit_identical(tmp_path, algo):
+    """save_checkpoint / load_checkpoint (weights, targets, Adam moments + step counts, schedulers): a
+    resumed agent makes bit-identical updates; the reference's own checkpoint (weights only) cannot."""
+    import torch
+    from gcrl_b200 import DDPG, TD3Agent
+    cls = DDPG if algo == "ddpg" else TD3Agent
+    D, A, B = 22, 3, 128
+    cfg = make_config(hidden_dim=64, batch_size=B, actor_lr=1e-3, actor_lr_min=1e-4, ac_scheduler_steps=5,
+                      critic_lr=2e-3, critic_lr_min=5e-4, cr_scheduler_steps=3, ac_update_freq=2)
+    rng = np.random.default_rng(11)
+
+    def batch():
+        s = rng.standard_normal((B, D)).astype(np.float32)
+        return tuple(torch.from_numpy(x).cuda() for x in (
+            s, rng.uniform(-1, 1, (B, A)).astype(np.float32), -(rng.random((B, 1)) > 0.3).astype(np.float32),
+            (s + 0.1 * rng.standard_normal((B, D))).astype(np.float32), (rng.random((B, 1)) < 0.1).astype(np.float32)))
+    batches = [batch() for _ in range(8)]
+    noises = [torch.randn((B, A), device="cuda") for _ in range(8)]
+    kw = (lambda i: {"noise": noises[i]}) if algo == "td3" else (lambda i: {})
+    torch.manual_seed(5)
+    a1 = cls(D, A, cfg, None, 1, 40)
+    for i in range(4):
+        a1.update(37 + i, batch=batches[i], **kw(i))
+    a1.save_checkpoint(str(tmp_path / "ck"))
+    ref = [a1.update(41 + i, batch=batches[4 + i], **kw(4 + i)) for i in range(4)]
+    torch.manual_seed(99)                                   # different initial weights: everything must come from the file
+    a2 = cls(D, A, cfg, None, 1, 40)
+    a2.load_checkpoint(str(tmp_path / "ck"))
+    got = [a2.update(41 + i, batch=batches[4 + i], **kw(4 + i)) for i in range(4)]
+    assert [[float(x) for x in r] for r in ref] == [[float(x) for x in g] for g in got]
+    for n1, n2 in zip((a1.actor, a1.target_actor), (a2.actor, a2.target_actor)):
+        for (w, b), (w2, b2) in zip(n1.layers(), n2.layers()):
+            assert np.array_equal(w, w2) and np.array_equal(b, b2)
