@@ -427,31 +427,34 @@ policy_head_bwd_kernel(const float *__restrict__ dzh, const float *__restrict__ 
 }
 
 // alpha_update (src/agent.py:532-546): AdamW (wd 0.01, betas 0.9/0.999, eps 1e-8) on the scalar
-// log_alpha with gradient -mean(log pi + target_entropy); alpha = exp(log_alpha).
-// st: [0] log_alpha, [1] alpha, [2] m, [3] v
+// log_alpha with gradient -mean(log pi + target_entropy); alpha = exp(log_alpha).  Two kernels so that the
+// batch mean can be averaged across data-parallel ranks in between (it sits right behind the actor's
+// flat gradient).  st: [0] log_alpha, [1] alpha, [2] m, [3] v
 __global__ void __launch_bounds__(1024)
-alpha_update_kernel(const float *__restrict__ logp, int M, float target_entropy, float step_size, float bc2_sqrt,
-                    float decay, float *__restrict__ st, float *__restrict__ loss_out) {
+alpha_mean_kernel(const float *__restrict__ logp, int M, float target_entropy, float *__restrict__ mean_out) {
   __shared__ float sm[1024];
   float s = 0.f;
   for (int m = threadIdx.x; m < M; m += 1024) s += logp[m] + target_entropy;
   const float tot = cta_sum_1024(s, sm);
-  if (threadIdx.x == 0) {
-    const float mean = tot / float(M);
-    float la = st[0];
-    *loss_out = -(la * mean);
-    const float g = -mean;
-    la *= decay;
-    float m1 = st[2], v = st[3];
-    m1 = m1 + float(1.0 - 0.9) * (g - m1);
-    v = v * float(0.999) + float(1.0 - 0.999) * g * g;
-    const float denom = sqrtf(v) / bc2_sqrt + 1e-8f;
-    la = la - step_size * (m1 / denom);
-    st[0] = la;
-    st[1] = expf(la);
-    st[2] = m1;
-    st[3] = v;
-  }
+  if (threadIdx.x == 0) *mean_out = tot / float(M);
+}
+
+__global__ void alpha_step_kernel(const float *__restrict__ mean_in, float step_size, float bc2_sqrt, float decay,
+                                  float *__restrict__ st, float *__restrict__ loss_out) {
+  const float mean = *mean_in;
+  float la = st[0];
+  *loss_out = -(la * mean);
+  const float g = -mean;
+  la *= decay;
+  float m1 = st[2], v = st[3];
+  m1 = m1 + float(1.0 - 0.9) * (g - m1);
+  v = v * float(0.999) + float(1.0 - 0.999) * g * g;
+  const float denom = sqrtf(v) / bc2_sqrt + 1e-8f;
+  la = la - step_size * (m1 / denom);
+  st[0] = la;
+  st[1] = expf(la);
+  st[2] = m1;
+  st[3] = v;
 }
 
 __global__ void polyak_plain_kernel(float *__restrict__ t, const float *__restrict__ s, int n, float tau, float omt) {
@@ -465,7 +468,7 @@ struct CriticNet {
   std::vector<int> in_d, out_d, ldw, w_off, b_off;
   int total = 0;
   float *p = nullptr, *g = nullptr, *m = nullptr, *v = nullptr;
-  void init(int in, int hid, int L, bool trainable) {
+  void init(int in, int hid, int L, bool trainable, float *grad_store = nullptr) {
     layers = L + 1;
     int off = 0;
     for (int l = 0; l < layers; ++l) {
@@ -479,10 +482,19 @@ struct CriticNet {
     p = dev_alloc<float>(total);
     GCRL_CUDA(cudaMemset(p, 0, size_t(total) * 4));
     if (trainable) {
-      for (float **q : {&g, &m, &v}) { *q = dev_alloc<float>(total); GCRL_CUDA(cudaMemset(*q, 0, size_t(total) * 4)); }
+      for (float **q : {&m, &v}) { *q = dev_alloc<float>(total); GCRL_CUDA(cudaMemset(*q, 0, size_t(total) * 4)); }
+      g = grad_store;          // slice of gcrl_sac::critic_grads (one all-reduce covers the ensemble)
     }
   }
-  void destroy() { for (float *q : {p, g, m, v}) if (q) cudaFree(q); }
+  static int layout_total(int in, int hid, int L) {
+    int off = 0;
+    for (int l = 0; l <= L; ++l) {
+      const int i = l == 0 ? in : hid, o = l == L ? 1 : hid;
+      off += o * pad4(i) + pad4(o);
+    }
+    return off;
+  }
+  void destroy() { for (float *q : {p, m, v}) if (q) cudaFree(q); }
   const float *W(int l) const { return p + w_off[l]; }
   const float *b(int l) const { return p + b_off[l]; }
 };
@@ -509,16 +521,19 @@ struct ActorNet {
     ws_off = off; off += A * ldh;
     bs_off = off; off += 4;
     total = off;
-    for (float **q : {&p, &g, &m, &v}) { *q = dev_alloc<float>(total); GCRL_CUDA(cudaMemset(*q, 0, size_t(total) * 4)); }
-    rmean = dev_alloc<float>(size_t(L) * ldh);
-    rvar = dev_alloc<float>(size_t(L) * ldh);
+    for (float **q : {&p, &g, &m, &v}) {      // g[total] holds mean(log pi + target_entropy) for alpha_update
+      *q = dev_alloc<float>(total + 4);
+      GCRL_CUDA(cudaMemset(*q, 0, size_t(total + 4) * 4));
+    }
+    rmean = dev_alloc<float>(size_t(2) * L * ldh);   // running mean | running var, one buffer (data-parallel average)
+    rvar = rmean + size_t(L) * ldh;
     std::vector<float> ones(size_t(L) * ldh, 1.0f);
     GCRL_CUDA(cudaMemset(rmean, 0, ones.size() * 4));
     GCRL_CUDA(cudaMemcpy(rvar, ones.data(), ones.size() * 4, cudaMemcpyHostToDevice));
     for (int l = 0; l < L; ++l)   // BatchNorm weight = 1 (torch default)
       GCRL_CUDA(cudaMemcpy(p + gam_off[l], ones.data(), size_t(H) * 4, cudaMemcpyHostToDevice));
   }
-  void destroy() { for (float *q : {p, g, m, v, rmean, rvar}) if (q) cudaFree(q); }
+  void destroy() { for (float *q : {p, g, m, v, rmean}) if (q) cudaFree(q); }
 };
 
 }  // namespace
@@ -531,6 +546,10 @@ struct gcrl_sac {
   ActorNet actor;
   CriticNet critic[kMaxCritics], target[kMaxCritics];
   int adam_t_c = 0, adam_t_a = 0, adam_t_alpha = 0;
+  int dp_B = -1, dp_flags = -1;                  // the update the data-parallel phases belong to
+  float dp_alpha[3] = {0.f, 1.f, 1.f};
+  float *critic_grads = nullptr;                 // [n][critic_stride]: the ensemble's flat gradients, contiguous
+  int critic_stride = 0;
   // activations
   std::vector<float *> xhat, ah;                 // actor: [L] x [maxB, ldh]
   float *invstd = nullptr;                       // [L][ldh]
@@ -634,11 +653,27 @@ void adam(gcrl_sac *ag, float *p, float *m, float *v, const float *g, int total,
   launch_adam(a, st);
 }
 
-// critic_update (SAC :548-639, TQC :951-1042)
-void critic_update(gcrl_sac *ag, int B, int flags, cudaStream_t st) {
+// sums of squares of an (averaged) flat gradient that is already in place
+void rereduce(gcrl_sac *ag, float *g, int total, cudaStream_t st) {
+  ReduceArgs r{};
+  r.nseg = 1;
+  r.seg[0] = SegDesc{0, total, nullptr, 0, 0, 0};
+  r.total = total; r.grad = g; r.sumsq_partials = ag->sumsq;
+  r.metrics = ag->mdev; r.slot_loss = r.slot_td = r.slot_q = -1;
+  launch_reduce_grads(r, st);
+}
+
+enum : int { PH_CGRAD = 1, PH_CSTEP = 2, PH_AGRAD = 4, PH_ASTEP = 8, PH_ALL = 15 };
+
+// critic_update (SAC :548-639, TQC :951-1042).  mask PH_ALL: every critic is stepped right after its own
+// backward; data-parallel: PH_CGRAD leaves the n flat gradients in critic_grads (all-reduced by the
+// caller), PH_CSTEP clips and steps on the averaged gradients.
+void critic_update(gcrl_sac *ag, int B, int flags, int mask, cudaStream_t st) {
   const int n = ag->n, L = ag->L, K0 = ag->D + ag->A;
   const bool tqc = ag->cfg.algo == GCRL_ALGO_TQC;
-  // a', log pi' = actor.sample(s') in train mode (batch statistics; running statistics move)
+  const bool dp = mask != PH_ALL;
+  if (mask & PH_CGRAD) {
+  // next action and log-probability = actor.sample(next_state) in train mode (batch statistics; running statistics move)
   actor_fwd(ag, ag->nsa, ag->eps_next, B, true, false, nullptr, st);
   for (int i = 0; i < n; ++i) critic_fwd(ag, ag->target[i], ag->nsa, ag->th, ag->qt + int64_t(i) * ag->maxB, B, st);
   sac_target_kernel<<<blocks_for(B, 256), 256, 0, st>>>(ag->qt, ag->maxB, n, ag->keep, ag->logp, ag->br, ag->bd,
@@ -676,9 +711,17 @@ void critic_update(gcrl_sac *ag, int B, int flags, cudaStream_t st) {
       }
     }
     reduce_critic(ag, c, splits, head_splits, st);
-    adam(ag, c.p, c.m, c.v, c.g, c.total, 0, ag->target[i].p, (flags & 2) != 0, M_CGN + i, st);
+    if (!dp) adam(ag, c.p, c.m, c.v, c.g, c.total, 0, ag->target[i].p, (flags & 2) != 0, M_CGN + i, st);
   }
-  if (tqc) {   // logged Q = mean over the STEPPED critics (:1016-1019)
+  }
+  if (dp && (mask & PH_CSTEP)) {
+    for (int i = 0; i < n; ++i) {
+      CriticNet &c = ag->critic[i];
+      rereduce(ag, c.g, c.total, st);
+      adam(ag, c.p, c.m, c.v, c.g, c.total, 0, ag->target[i].p, (flags & 2) != 0, M_CGN + i, st);
+    }
+  }
+  if (tqc && (mask & PH_CSTEP)) {   // logged Q = mean over the STEPPED critics (:1016-1019)
     for (int i = 0; i < n; ++i) critic_fwd(ag, ag->critic[i], ag->sa, ag->th, ag->qt + int64_t(i) * ag->maxB, B, st);
     critic_metrics_kernel<<<1, 1024, 0, st>>>(ag->qt, ag->maxB, n, nullptr, B, ag->mdev + M_CLOSS, 1);
     GCRL_LAUNCHED();
@@ -686,10 +729,12 @@ void critic_update(gcrl_sac *ag, int B, int flags, cudaStream_t st) {
 }
 
 // actor_update (SAC :513-530, TQC :912-934) + alpha_update (:532-546 / :936-949)
-void actor_update(gcrl_sac *ag, int B, int flags, float alpha_step, float alpha_bc2, float alpha_decay,
+void actor_update(gcrl_sac *ag, int B, int flags, int mask, float alpha_step, float alpha_bc2, float alpha_decay,
                   cudaStream_t st) {
   const int n = ag->n, L = ag->L, D = ag->D, A = ag->A;
   ActorNet &a = ag->actor;
+  const bool dp = mask != PH_ALL;
+  if (mask & PH_AGRAD) {
   actor_fwd(ag, ag->spi, ag->eps_cur, B, true, true, nullptr, st);
   for (int i = 0; i < n; ++i) critic_fwd(ag, ag->critic[i], ag->spi, ag->ch[i], ag->q + int64_t(i) * ag->maxB, B, st);
   actor_trunc_kernel<<<1, 1024, 0, st>>>(ag->q, ag->maxB, n, ag->keep, ag->logp, ag->cfg.entropy_coef,
@@ -760,23 +805,42 @@ void actor_update(gcrl_sac *ag, int B, int flags, float alpha_step, float alpha_
   r.total = a.total; r.grad = a.g; r.sumsq_partials = ag->sumsq;
   r.metrics = ag->mdev; r.slot_loss = r.slot_td = r.slot_q = -1;
   launch_reduce_grads(r, st);
-  adam(ag, a.p, a.m, a.v, a.g, a.total, 1, nullptr, false, M_AGN, st);
   if (flags & 4) {
-    alpha_update_kernel<<<1, 1024, 0, st>>>(ag->logp, B, ag->cfg.target_entropy, alpha_step, alpha_bc2, alpha_decay,
-                                           ag->alpha_state, ag->mdev + M_ALPHA_LOSS);
+    alpha_mean_kernel<<<1, 1024, 0, st>>>(ag->logp, B, ag->cfg.target_entropy, a.g + a.total);
     GCRL_LAUNCHED();
-  } else {
-    GCRL_CUDA(cudaMemsetAsync(ag->mdev + M_ALPHA_LOSS, 0, 4, st));
+  }
+  }
+  if (mask & PH_ASTEP) {
+    if (dp) rereduce(ag, a.g, a.total, st);
+    adam(ag, a.p, a.m, a.v, a.g, a.total, 1, nullptr, false, M_AGN, st);
+    if (flags & 4) {
+      alpha_step_kernel<<<1, 1, 0, st>>>(a.g + a.total, alpha_step, alpha_bc2, alpha_decay, ag->alpha_state,
+                                        ag->mdev + M_ALPHA_LOSS);
+      GCRL_LAUNCHED();
+    } else {
+      GCRL_CUDA(cudaMemsetAsync(ag->mdev + M_ALPHA_LOSS, 0, 4, st));
+    }
   }
 }
 
-void sac_update(gcrl_sac *ag, gcrl_her *buf, int64_t B64, const int64_t *idx_host, const float *s, const float *a,
-                const float *r, const float *ns, const float *d, const float *eps_next, const float *eps_cur,
-                double lr_c, double lr_a, int flags, float *metrics_host, cudaStream_t st) {
+void read_metrics(gcrl_sac *ag, int flags, float *metrics_host, cudaStream_t st);
+
+// phase < 0: the whole update.  phase 0..3: the data-parallel cut (critic grads | critic steps | actor grads |
+// actor step), the caller averaging critic_grads / the actor gradient across ranks in between.
+void sac_update(gcrl_sac *ag, int phase, gcrl_her *buf, int64_t B64, const int64_t *idx_host, const float *s,
+                const float *a, const float *r, const float *ns, const float *d, const float *eps_next,
+                const float *eps_cur, double lr_c, double lr_a, int flags, float *metrics_host, cudaStream_t st) {
   GCRL_REQUIRE(ag != nullptr, "agent handle is NULL");
   GCRL_REQUIRE(B64 >= 2 && B64 <= ag->maxB, "batch size outside [2, max_batch] (BatchNorm needs > 1 row)");
-  GCRL_REQUIRE(eps_next != nullptr && (eps_cur != nullptr || !(flags & 1)), "NULL rsample noise tensor");
   const int B = int(B64);
+  if (phase > 0) {
+    GCRL_REQUIRE(ag->dp_B == B && ag->dp_flags == flags, "phase 1..3 must follow phase 0 of the same update");
+    if (phase == 1) critic_update(ag, B, flags, PH_CSTEP, st);
+    else if (flags & 1) actor_update(ag, B, flags, phase == 2 ? PH_AGRAD : PH_ASTEP, ag->dp_alpha[0], ag->dp_alpha[1],
+                                     ag->dp_alpha[2], st);
+    return;
+  }
+  GCRL_REQUIRE(eps_next != nullptr && (eps_cur != nullptr || !(flags & 1)), "NULL rsample noise tensor");
   if (buf != nullptr) {
     GCRL_REQUIRE(her_state_dim(buf) == ag->D && her_act_dim(buf) == ag->A, "buffer / agent shape mismatch");
     GCRL_REQUIRE(her_device(buf) == ag->device, "buffer and agent live on different devices");
@@ -805,15 +869,23 @@ void sac_update(gcrl_sac *ag, gcrl_her *buf, int64_t B64, const int64_t *idx_hos
   GCRL_CUDA(cudaMemcpyAsync(ag->d_scalars, sc, sizeof(StepScalars), cudaMemcpyHostToDevice, st));
   ag->scal_stage.release(slot, st);
 
-  critic_update(ag, B, flags, st);
-  if (flags & 1) {
-    float al[4] = {0.f, 1.f, 1.f, 0.f};
-    if (flags & 4) {
-      ag->adam_t_alpha += 1;
-      fill(ag->adam_t_alpha, double(ag->cfg.alpha_lr), al);
-    }
-    actor_update(ag, B, flags, al[0], al[1], al[2], st);
+  float al[4] = {0.f, 1.f, 1.f, 0.f};
+  if ((flags & 1) && (flags & 4)) {
+    ag->adam_t_alpha += 1;
+    fill(ag->adam_t_alpha, double(ag->cfg.alpha_lr), al);
   }
+  if (phase == 0) {
+    ag->dp_B = B; ag->dp_flags = flags;
+    for (int i = 0; i < 3; ++i) ag->dp_alpha[i] = al[i];
+    critic_update(ag, B, flags, PH_CGRAD, st);
+    return;
+  }
+  critic_update(ag, B, flags, PH_ALL, st);
+  if (flags & 1) actor_update(ag, B, flags, PH_ALL, al[0], al[1], al[2], st);
+  read_metrics(ag, flags, metrics_host, st);
+}
+
+void read_metrics(gcrl_sac *ag, int flags, float *metrics_host, cudaStream_t st) {
   if (metrics_host != nullptr) {
     float hm[32], hs[4];
     GCRL_CUDA(cudaMemcpyAsync(hm, ag->mdev, sizeof(hm), cudaMemcpyDeviceToHost, st));
@@ -891,7 +963,13 @@ int gcrl_sac_create(gcrl_sac **out, int device, const gcrl_sac_config *cfg) {
     const int D = ag->D, A = ag->A, H = ag->H, L = ag->L, n = ag->n;
     const size_t mb = size_t(ag->maxB), act = mb * ag->ldh;
     ag->actor.init(D, H, A, L);
-    for (int i = 0; i < n; ++i) { ag->critic[i].init(D + A, H, L, true); ag->target[i].init(D + A, H, L, false); }
+    ag->critic_stride = CriticNet::layout_total(D + A, H, L);
+    ag->critic_grads = dev_alloc<float>(size_t(n) * ag->critic_stride);
+    GCRL_CUDA(cudaMemset(ag->critic_grads, 0, size_t(n) * ag->critic_stride * 4));
+    for (int i = 0; i < n; ++i) {
+      ag->critic[i].init(D + A, H, L, true, ag->critic_grads + size_t(i) * ag->critic_stride);
+      ag->target[i].init(D + A, H, L, false);
+    }
     for (int l = 0; l < L; ++l) { ag->xhat.push_back(dev_alloc<float>(act)); ag->ah.push_back(dev_alloc<float>(act)); }
     ag->invstd = dev_alloc<float>(size_t(L) * ag->ldh);
     ag->ch.resize(n);
@@ -935,7 +1013,8 @@ int gcrl_sac_destroy(gcrl_sac *ag) {
   for (auto &v : ag->ch) for (float *p : v) cudaFree(p);
   for (float *p : {ag->invstd, ag->dz[0], ag->dz[1], ag->sa, ag->nsa, ag->spi, ag->br, ag->bd, ag->bs, ag->ba, ag->bns,
                    ag->br0, ag->bd0, ag->q, ag->qt, ag->y, ag->dq, ag->logp, ag->act4, ag->std4, ag->gate4, ag->dact,
-                   ag->dzh, ag->eps_next, ag->eps_cur, ag->partials, ag->sumsq, ag->mdev, ag->alpha_state, ag->d_io})
+                   ag->dzh, ag->eps_next, ag->eps_cur, ag->partials, ag->sumsq, ag->mdev, ag->alpha_state, ag->d_io,
+                   ag->critic_grads})
     if (p) cudaFree(p);
   cudaFree(ag->d_scalars);
   ag->scal_stage.destroy();
@@ -1052,7 +1131,7 @@ int gcrl_sac_update_batch(gcrl_sac *ag, int64_t B, const float *s, const float *
   GCRL_API_BEGIN
   GCRL_REQUIRE(ag != nullptr, "agent handle is NULL");
   GCRL_CUDA(cudaSetDevice(ag->device));
-  sac_update(ag, nullptr, B, nullptr, s, a, r, ns, d, eps_next, eps_cur, lr_c, lr_a, flags, metrics_host,
+  sac_update(ag, -1, nullptr, B, nullptr, s, a, r, ns, d, eps_next, eps_cur, lr_c, lr_a, flags, metrics_host,
              as_stream(stream));
   GCRL_API_END
 }
@@ -1063,8 +1142,40 @@ int gcrl_sac_update_from_buffer(gcrl_sac *ag, gcrl_her *buf, int64_t B, const in
   GCRL_API_BEGIN
   GCRL_REQUIRE(ag != nullptr && buf != nullptr, "NULL handle");
   GCRL_CUDA(cudaSetDevice(ag->device));
-  sac_update(ag, buf, B, idx_host, nullptr, nullptr, nullptr, nullptr, nullptr, eps_next, eps_cur, lr_c, lr_a, flags,
-             metrics_host, as_stream(stream));
+  sac_update(ag, -1, buf, B, idx_host, nullptr, nullptr, nullptr, nullptr, nullptr, eps_next, eps_cur, lr_c, lr_a,
+             flags, metrics_host, as_stream(stream));
+  GCRL_API_END
+}
+
+int gcrl_sac_update_phase(gcrl_sac *ag, int phase, gcrl_her *buf, int64_t B, const int64_t *idx_host, const float *s,
+                          const float *a, const float *r, const float *ns, const float *d, const float *eps_next,
+                          const float *eps_cur, double lr_c, double lr_a, int flags, void *stream) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(ag != nullptr && phase >= 0 && phase <= 3, "NULL handle / phase outside 0..3");
+  GCRL_CUDA(cudaSetDevice(ag->device));
+  sac_update(ag, phase, buf, B, idx_host, s, a, r, ns, d, eps_next, eps_cur, lr_c, lr_a, flags, nullptr,
+             as_stream(stream));
+  GCRL_API_END
+}
+
+int gcrl_sac_dp_buffer(gcrl_sac *ag, int which, float **dev, int64_t *count) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(ag != nullptr && dev != nullptr && count != nullptr, "NULL argument");
+  switch (which) {
+    case 0: *dev = ag->actor.g; *count = ag->actor.total + 4; break;                       // + alpha's batch mean
+    case 1: *dev = ag->critic_grads; *count = int64_t(ag->n) * ag->critic_stride; break;
+    case 2: *dev = ag->actor.rmean; *count = int64_t(2) * ag->L * ag->ldh; break;          // BatchNorm running stats
+    case 3: *dev = ag->mdev; *count = 32; break;
+    default: throw Error(GCRL_ERR_INVALID, "which must be 0 (actor grad), 1 (critic grads), 2 (BN stats), 3 (metrics)");
+  }
+  GCRL_API_END
+}
+
+int gcrl_sac_read_metrics(gcrl_sac *ag, int flags, float *metrics_host, void *stream) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(ag != nullptr && metrics_host != nullptr, "NULL argument");
+  GCRL_CUDA(cudaSetDevice(ag->device));
+  read_metrics(ag, flags, metrics_host, as_stream(stream));
   GCRL_API_END
 }
 

@@ -104,6 +104,10 @@ SIGNATURES = {
     "gcrl_sac_update_batch": (C.c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp, c_f64, c_f64, C.c_int, vp, vp]),
     "gcrl_sac_update_from_buffer": (C.c_int, [vp, vp, c_i64, vp, vp, vp, c_f64, c_f64, C.c_int, vp, vp]),
     "gcrl_sac_act": (C.c_int, [vp, c_i64, vp, vp, vp, vp]),
+    "gcrl_sac_update_phase": (C.c_int, [vp, C.c_int, vp, c_i64, vp, vp, vp, vp, vp, vp, vp, vp, c_f64, c_f64, C.c_int,
+                                        vp]),
+    "gcrl_sac_dp_buffer": (C.c_int, [vp, C.c_int, pp, C.POINTER(c_i64)]),
+    "gcrl_sac_read_metrics": (C.c_int, [vp, C.c_int, vp, vp]),
     # diagnostics
     "gcrl_agent_time_critic_kernel": (C.c_int, [vp, c_i64, C.c_int, C.POINTER(c_f32), vp]),
     "gcrl_dense_wgrad": (C.c_int, [C.c_int, C.c_int, c_i64, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, c_i64,

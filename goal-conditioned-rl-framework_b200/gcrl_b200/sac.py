@@ -261,6 +261,16 @@ class _SacBase(_AgentBase):
     def _polyak_now(self, step):
         raise NotImplementedError
 
+    # -- data parallel: same GradAverager as DDPG / TD3 over the buffers of gcrl_sac_dp_buffer -------
+    def grad_tensor(self, which):
+        from .parallel import device_tensor
+        ptr, n = vp(), C.c_int64()
+        check(lib.gcrl_sac_dp_buffer(self._h, int(which), C.byref(ptr), C.byref(n)))
+        return device_tensor(ptr.value, n.value, self.device_index)
+
+    def metrics_tensor(self):
+        return self.grad_tensor(3)
+
     def update(self, step: int, batch=None, indices=None, eps_next=None, eps_cur=None):
         import torch
         B = self.batch_size if batch is None else batch[0].shape[0]
@@ -275,18 +285,32 @@ class _SacBase(_AgentBase):
         mptr = C.cast(self._metrics, vp)
         en = vp(eps_next.data_ptr())
         ec = vp(eps_cur.data_ptr()) if eps_cur is not None else None
+        iptr, bufh, ptrs = None, None, (None,) * 5
         if batch is None:
             assert len(self.buffer) >= B, "[ERROR] Not enough in buffer to sample"
-            iptr = None
             if indices is None and self.index_source == "host":
                 indices = random.sample(range(len(self.buffer)), B)
             if indices is not None:
                 indices = np.ascontiguousarray(indices, np.int64)
                 iptr = np_ptr(indices)
-            check(lib.gcrl_sac_update_from_buffer(self._h, self.buffer.handle, B, iptr, en, ec, lr_c, lr_a, flags,
-                                                  mptr, self._stream()))
+            bufh = self.buffer.handle
         else:
             ptrs = tuple(vp(t.data_ptr()) for t in batch)
+        if self._dp is not None:
+            st = self._stream()
+            for phase in range(4):
+                check(lib.gcrl_sac_update_phase(self._h, phase, bufh, B, iptr, *ptrs, en, ec, lr_c, lr_a, flags, st))
+                if phase == 0:
+                    self._dp.average((1,))                 # the critic ensemble's gradients, one buffer
+                elif phase == 2 and (flags & 1):
+                    self._dp.average((0,))                 # actor gradient + alpha's batch mean
+            self._dp.average((2,))                         # BatchNorm running statistics
+            self._dp.average_metrics()
+            check(lib.gcrl_sac_read_metrics(self._h, flags, mptr, st))
+        elif batch is None:
+            check(lib.gcrl_sac_update_from_buffer(self._h, bufh, B, iptr, en, ec, lr_c, lr_a, flags, mptr,
+                                                  self._stream()))
+        else:
             check(lib.gcrl_sac_update_batch(self._h, B, *ptrs, en, ec, lr_c, lr_a, flags, mptr, self._stream()))
         self.critic_scheduler.step()
         self._bn_batches += 1

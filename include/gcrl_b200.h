@@ -302,6 +302,28 @@ int gcrl_sac_update_batch(gcrl_sac *h, int64_t B, const float *s_dev, const floa
 int gcrl_sac_update_from_buffer(gcrl_sac *h, gcrl_her *buf, int64_t B, const int64_t *idx_host,
                                 const float *eps_next_dev, const float *eps_cur_dev, double lr_critic,
                                 double lr_actor, int flags, float *metrics_host, void *stream);
+/* Data-parallel hooks (one process per GPU, episode-sharded buffer, replicated weights): the update cut
+ * at the points where gradients are averaged across ranks --
+ *   phase 0: ingest the local batch, policy sample, targets, all critic forwards / backwards
+ *            -> the ensemble's flat gradients (gcrl_sac_dp_buffer which = 1), local metrics;
+ *   phase 1: clip + AdamW (+ Polyak per flags) of every critic on the averaged gradients;
+ *   phase 2: actor forward / backward through the stepped critics -> actor gradient, followed in the same
+ *            buffer by alpha's batch mean (which = 0);
+ *   phase 3: clip + AdamW of the actor, alpha step.
+ * BatchNorm uses the LOCAL batch statistics on every rank (torch DistributedDataParallel's default
+ * without SyncBatchNorm); the caller averages the running statistics (which = 2) after phase 3 so that
+ * the replicas' eval-mode policies stay identical.  With world size 1 the four phases reproduce
+ * gcrl_sac_update_* bit for bit. */
+int gcrl_sac_update_phase(gcrl_sac *h, int phase, gcrl_her *buf, int64_t B, const int64_t *idx_host,
+                          const float *s_dev, const float *a_dev, const float *r_dev, const float *ns_dev,
+                          const float *d_dev, const float *eps_next_dev, const float *eps_cur_dev,
+                          double lr_critic, double lr_actor, int flags, void *stream);
+/* which: 0 actor gradient (+ 4 trailing floats: alpha's batch mean), 1 all critic gradients (contiguous),
+ * 2 BatchNorm running mean | var of every layer, 3 the 32-float device metrics block. */
+int gcrl_sac_dp_buffer(gcrl_sac *h, int which, float **dev, int64_t *count);
+/* The metrics tuple of the most recent update (float[12], same order as gcrl_sac_update_batch). */
+int gcrl_sac_read_metrics(gcrl_sac *h, int flags, float *metrics_host, void *stream);
+
 /* select_action, :641-647: eval-mode actor (running statistics).  eps_host NULL = deterministic
  * tanh(mean); otherwise tanh(mean + std * eps).  obs host [n, D] -> act host [n, A]. */
 int gcrl_sac_act(gcrl_sac *h, int64_t n, const float *obs_host, const float *eps_host, float *act_host,

@@ -41,9 +41,47 @@ def main():
         for (w, b), (ws, bs) in zip(ag.actor.layers() + ag.critic.layers() + ag.target_critic.layers(),
                                     single.actor.layers() + single.critic.layers() + single.target_critic.layers()):
             assert weights_close(w, ws, 1e-3, 4) and weights_close(b, bs, 1e-3, 4)
+    tqc_section(rank, world, local)
+    if rank == 0:
         print("DP_OK", flush=True)
     dist.barrier()
     dist.destroy_process_group()
+
+
+def tqc_section(rank, world, local):
+    """TQC over NCCL: every rank on its own batch and noise; replicas (weights, log_alpha, BatchNorm running
+    statistics) must stay bit-identical across ranks."""
+    from oracle import ddpg as OD
+    from oracle import sac as OS
+    from gcrl_b200 import TQCAgent
+    from tests.test_sac_gpu import load_initial, sac_config
+    D, A, H, L, B = 22, 3, 64, 3, 128
+    rng = np.random.default_rng(7)
+    cfg = sac_config(hidden_dim=H, layer_count=L, batch_size=B, grad_clip=0.5, tau=0.05, alpha_min_steps=0, alpha_lr=1e-2)
+    actor0, stats0 = OS.init_sac_actor(rng, D, H, A, L, head_scale=0.1, log_std_bias=-1.0)
+    critics0 = [OD.init_mlp(rng, D + A, H, 1, L) for _ in range(5)]
+    ag = TQCAgent(D, A, cfg, None, 1, 2, device=local)
+    load_initial(ag, actor0, stats0, critics0)
+    ag.enable_data_parallel()
+    dev = torch.device("cuda", local)
+    for step in (1, 2, 3):
+        per_rank = []
+        for _ in range(world):
+            b = rand_batch_on(rng, B, D, A, local)
+            e = [torch.from_numpy(rng.standard_normal((B, A)).astype(np.float32)).to(dev) for _ in range(2)]
+            per_rank.append((b, e))
+        b, e = per_rank[rank]
+        info = ag.update(step, batch=b, eps_next=e[0], eps_cur=e[1])
+        assert len(info) == 9 and all(np.isfinite(float(x)) for x in info)
+    parts = [torch.from_numpy(w).reshape(-1) for v in ag._critic_views + ag._target_views for w, _ in v.layers()]
+    parts += [torch.from_numpy(np.concatenate([x.reshape(-1) for x in ag.actor.bn(l)])) for l in range(L)]
+    parts += [torch.from_numpy(ag.actor.linear(l)[0]).reshape(-1) for l in range(L + 2)]
+    parts.append(torch.tensor([ag.get_log_alpha()]))
+    flat = torch.cat(parts).to(dev)
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    for g in gathered[1:]:
+        assert torch.equal(g, gathered[0]), "TQC replicas diverged"
 
 
 def make_agent_on(dev, D, A, H, L, B):

@@ -5,6 +5,7 @@ with the recorded ``Normal.rsample`` noise, and versus the NumPy oracle on ragge
 Tolerance: metrics rel 2e-5 + abs 1e-6; weights tests.helpers.weights_close /
 assert_sac_actor_close (pre-BatchNorm Linear biases only to Adam's hard bound -- their true
 gradient is zero, see the helper); BatchNorm running variance rel 1e-5."""
+import ctypes as C
 import os
 
 import numpy as np
@@ -151,3 +152,99 @@ def test_sac_from_buffer_own_noise_and_checkpoint_files(tmp_path):
         import torch
         sd = torch.load(str(out / "actor.pth"))
         assert "base_net.1.running_mean" in sd and "mean_head.weight" in sd and "log_std_head.bias" in sd
+
+
+def _rand_batch(rng, B, D, A):
+    import torch
+    s = rng.standard_normal((B, D)).astype(np.float32)
+    arrs = (s, rng.uniform(-1, 1, (B, A)).astype(np.float32), -(rng.random((B, 1)) > 0.3).astype(np.float32),
+            (s + 0.1 * rng.standard_normal((B, D))).astype(np.float32), (rng.random((B, 1)) < 0.1).astype(np.float32),
+            rng.standard_normal((B, A)).astype(np.float32), rng.standard_normal((B, A)).astype(np.float32))
+    return tuple(torch.from_numpy(x).cuda() for x in arrs)
+
+
+def _make(algo, D, A, H, L, B, seed=5):
+    from gcrl_b200 import SACAgent, TQCAgent
+    from oracle import ddpg as OD
+    from oracle import sac as OS
+    rng = np.random.default_rng(seed)
+    cfg = sac_config(hidden_dim=H, layer_count=L, batch_size=B, grad_clip=0.5, tau=0.05, alpha_min_steps=0, alpha_lr=1e-2)
+    actor0, stats0 = OS.init_sac_actor(rng, D, H, A, L, head_scale=0.1, log_std_bias=-1.0)
+    critics0 = [OD.init_mlp(rng, D + A, H, 1, L) for _ in range(2 if algo == "sac" else 5)]
+    ag = (SACAgent if algo == "sac" else TQCAgent)(D, A, cfg, None, 1, 2)
+    load_initial(ag, actor0, stats0, critics0)
+    return ag
+
+
+@pytest.mark.parametrize("algo", ["sac", "tqc"])
+def test_world1_phases_equal_whole_update_bitwise(algo):
+    D, A, H, L, B = 22, 3, 64, 3, 128
+    whole, phased = _make(algo, D, A, H, L, B), _make(algo, D, A, H, L, B)
+    phased.enable_data_parallel(allreduce_mean=lambda t: t)            # world of one: identity
+    rng = np.random.default_rng(0)
+    for step in (1, 2, 3):
+        *batch, e1, e2 = _rand_batch(rng, B, D, A)
+        i1 = whole.update(step, batch=tuple(batch), eps_next=e1, eps_cur=e2)
+        i2 = phased.update(step, batch=tuple(batch), eps_next=e1, eps_cur=e2)
+        assert [float(x) for x in i1] == [float(x) for x in i2]
+    p1, s1 = actor_params(whole)
+    p2, s2 = actor_params(phased)
+    for (w, b), (w2, b2) in zip(p1 + s1, p2 + s2):
+        assert np.array_equal(w, w2) and np.array_equal(b, b2)
+    for v1, v2 in zip(whole._critic_views + whole._target_views, phased._critic_views + phased._target_views):
+        for (w, b), (w2, b2) in zip(v1.layers(), v2.layers()):
+            assert np.array_equal(w, w2) and np.array_equal(b, b2)
+    assert whole.get_log_alpha() == phased.get_log_alpha()
+
+
+def test_tqc_two_emulated_ranks_stay_replicated_and_track_the_averaged_gradient():
+    """Two agents on one GPU play ranks 0/1: phases in lock step, the buffers of gcrl_sac_dp_buffer averaged
+    between them exactly as the NCCL all-reduce does.  Replicas must stay bit-identical (weights, Adam
+    trajectories, log_alpha, BatchNorm running statistics); BatchNorm normalises with LOCAL batch statistics
+    (DDP's default), so the result is close to, not equal to, one rank on the concatenated batch."""
+    import torch
+    from gcrl_b200._lib import check, lib, vp
+    D, A, H, L, B = 22, 3, 64, 2, 256
+    ranks = [_make("tqc", D, A, H, L, B), _make("tqc", D, A, H, L, B)]
+    single = _make("tqc", D, A, H, L, 2 * B)
+    rng = np.random.default_rng(1)
+    st = vp(torch.cuda.current_stream().cuda_stream)
+
+    def average(which):
+        g = [ag.grad_tensor(which) for ag in ranks]
+        mean = (g[0] + g[1]) / 2
+        g[0].copy_(mean)
+        g[1].copy_(mean)
+    for step in (1, 2, 3):
+        data = [_rand_batch(rng, B, D, A) for _ in ranks]
+        flags = 1 | 2 | 4
+        for phase in range(4):
+            for ag, b in zip(ranks, data):
+                check(lib.gcrl_sac_update_phase(ag._h, phase, None, B, None, *(vp(t.data_ptr()) for t in b[:5]),
+                                                vp(b[5].data_ptr()), vp(b[6].data_ptr()), 1e-3, 1e-3, flags, st))
+            if phase == 0:
+                average(1)
+            elif phase == 2:
+                average(0)
+        average(2)
+        cat = [torch.cat([x, y]) for x, y in zip(*data)]
+        info = single.update(step, batch=tuple(cat[:5]), eps_next=cat[5], eps_cur=cat[6])
+        m = []
+        for ag in ranks:
+            buf = (C.c_float * 12)()
+            check(lib.gcrl_sac_read_metrics(ag._h, flags, C.cast(buf, vp), st))
+            m.append(np.array(list(buf)))
+        got = (m[0] + m[1]) / 2
+        want = np.array([float(x) for x in info])
+        np.testing.assert_allclose(got[[0, 3, 4]], want[[0, 3, 4]], rtol=2e-2)       # losses / td / q: means of means
+        assert m[0][9] == m[1][9] and m[0][10] == m[1][10]                           # alpha, log_alpha replicated
+    p0, s0 = actor_params(ranks[0])
+    p1, s1 = actor_params(ranks[1])
+    ps, _ = actor_params(single)
+    for (w, b), (w2, b2) in zip(p0 + s0, p1 + s1):
+        assert np.array_equal(w, w2) and np.array_equal(b, b2)
+    for v0, v1 in zip(ranks[0]._critic_views + ranks[0]._target_views, ranks[1]._critic_views + ranks[1]._target_views):
+        for (w, b), (w2, b2) in zip(v0.layers(), v1.layers()):
+            assert np.array_equal(w, w2) and np.array_equal(b, b2)
+    for (w, _), (ws, _) in zip(ranks[0]._critic_views[0].layers(), single._critic_views[0].layers()):
+        assert np.max(np.abs(w - ws)) <= 2.0 * 1e-3 * 3                              # Adam's hard bound
