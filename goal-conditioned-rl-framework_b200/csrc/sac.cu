@@ -12,7 +12,10 @@
 // its log-probability and analytic backward, the sort-truncate-mean over the critic axis (an
 // insertion sort in registers), the scalar AdamW on log_alpha and the orchestration.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <map>
+#include <tuple>
 #include <vector>
 
 #include "mlp.cuh"
@@ -439,8 +442,10 @@ alpha_mean_kernel(const float *__restrict__ logp, int M, float target_entropy, f
   if (threadIdx.x == 0) *mean_out = tot / float(M);
 }
 
-__global__ void alpha_step_kernel(const float *__restrict__ mean_in, float step_size, float bc2_sqrt, float decay,
+// sc: [0] lr / (1 - b1^t), [1] sqrt(1 - b2^t), [2] 1 - lr * wd  (device scalars, so the update can be a graph)
+__global__ void alpha_step_kernel(const float *__restrict__ mean_in, const float *__restrict__ sc,
                                   float *__restrict__ st, float *__restrict__ loss_out) {
+  const float step_size = sc[0], bc2_sqrt = sc[1], decay = sc[2];
   const float mean = *mean_in;
   float la = st[0];
   *loss_out = -(la * mean);
@@ -547,7 +552,10 @@ struct gcrl_sac {
   CriticNet critic[kMaxCritics], target[kMaxCritics];
   int adam_t_c = 0, adam_t_a = 0, adam_t_alpha = 0;
   int dp_B = -1, dp_flags = -1;                  // the update the data-parallel phases belong to
-  float dp_alpha[3] = {0.f, 1.f, 1.f};
+  bool use_graphs = true;
+  cudaStream_t cap_stream = nullptr;             // capture-only stream (the caller's may be the legacy one)
+  struct GraphRec { cudaGraphExec_t exec; uint64_t kernels; };
+  std::map<std::tuple<int, int, int>, GraphRec> graphs;   // (B, flags, phase mask)
   float *critic_grads = nullptr;                 // [n][critic_stride]: the ensemble's flat gradients, contiguous
   int critic_stride = 0;
   // activations
@@ -729,8 +737,7 @@ void critic_update(gcrl_sac *ag, int B, int flags, int mask, cudaStream_t st) {
 }
 
 // actor_update (SAC :513-530, TQC :912-934) + alpha_update (:532-546 / :936-949)
-void actor_update(gcrl_sac *ag, int B, int flags, int mask, float alpha_step, float alpha_bc2, float alpha_decay,
-                  cudaStream_t st) {
+void actor_update(gcrl_sac *ag, int B, int flags, int mask, cudaStream_t st) {
   const int n = ag->n, L = ag->L, D = ag->D, A = ag->A;
   ActorNet &a = ag->actor;
   const bool dp = mask != PH_ALL;
@@ -814,8 +821,8 @@ void actor_update(gcrl_sac *ag, int B, int flags, int mask, float alpha_step, fl
     if (dp) rereduce(ag, a.g, a.total, st);
     adam(ag, a.p, a.m, a.v, a.g, a.total, 1, nullptr, false, M_AGN, st);
     if (flags & 4) {
-      alpha_step_kernel<<<1, 1, 0, st>>>(a.g + a.total, alpha_step, alpha_bc2, alpha_decay, ag->alpha_state,
-                                        ag->mdev + M_ALPHA_LOSS);
+      alpha_step_kernel<<<1, 1, 0, st>>>(a.g + a.total, reinterpret_cast<const float *>(ag->d_scalars + 1),
+                                        ag->alpha_state, ag->mdev + M_ALPHA_LOSS);
       GCRL_LAUNCHED();
     } else {
       GCRL_CUDA(cudaMemsetAsync(ag->mdev + M_ALPHA_LOSS, 0, 4, st));
@@ -824,6 +831,44 @@ void actor_update(gcrl_sac *ag, int B, int flags, int mask, float alpha_step, fl
 }
 
 void read_metrics(gcrl_sac *ag, int flags, float *metrics_host, cudaStream_t st);
+
+void run_body(gcrl_sac *ag, int B, int flags, int mask, cudaStream_t st) {
+  if (mask & (PH_CGRAD | PH_CSTEP)) critic_update(ag, B, flags, mask == PH_ALL ? PH_ALL : (mask & (PH_CGRAD | PH_CSTEP)), st);
+  if ((mask & (PH_AGRAD | PH_ASTEP)) && (flags & 1))
+    actor_update(ag, B, flags, mask == PH_ALL ? PH_ALL : (mask & (PH_AGRAD | PH_ASTEP)), st);
+}
+
+// Replay (or capture on first use) the CUDA graph of (B, flags, phase mask): ~170 launches per TQC update
+// become one graph launch; everything that varies per step travels through device scalars.
+void run_phases(gcrl_sac *ag, int B, int flags, int mask, cudaStream_t st) {
+  if (!ag->use_graphs) {
+    run_body(ag, B, flags, mask, st);
+    return;
+  }
+  const auto key = std::make_tuple(B, flags, mask);
+  auto it = ag->graphs.find(key);
+  if (it == ag->graphs.end()) {
+    cudaGraph_t graph = nullptr;
+    const uint64_t before = launch_counter();
+    GCRL_CUDA(cudaStreamBeginCapture(ag->cap_stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      run_body(ag, B, flags, mask, ag->cap_stream);
+    } catch (...) {
+      cudaStreamEndCapture(ag->cap_stream, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    GCRL_CUDA(cudaStreamEndCapture(ag->cap_stream, &graph));
+    const uint64_t kernels = launch_counter() - before;   // recorded, not executed, by the capture
+    count_launch(uint64_t(0) - kernels);
+    cudaGraphExec_t exec = nullptr;
+    GCRL_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    GCRL_CUDA(cudaGraphDestroy(graph));
+    it = ag->graphs.emplace(key, gcrl_sac::GraphRec{exec, kernels}).first;
+  }
+  GCRL_CUDA(cudaGraphLaunch(it->second.exec, st));
+  count_launch(it->second.kernels);
+}
 
 // phase < 0: the whole update.  phase 0..3: the data-parallel cut (critic grads | critic steps | actor grads |
 // actor step), the caller averaging critic_grads / the actor gradient across ranks in between.
@@ -835,9 +880,7 @@ void sac_update(gcrl_sac *ag, int phase, gcrl_her *buf, int64_t B64, const int64
   const int B = int(B64);
   if (phase > 0) {
     GCRL_REQUIRE(ag->dp_B == B && ag->dp_flags == flags, "phase 1..3 must follow phase 0 of the same update");
-    if (phase == 1) critic_update(ag, B, flags, PH_CSTEP, st);
-    else if (flags & 1) actor_update(ag, B, flags, phase == 2 ? PH_AGRAD : PH_ASTEP, ag->dp_alpha[0], ag->dp_alpha[1],
-                                     ag->dp_alpha[2], st);
+    run_phases(ag, B, flags, phase == 1 ? PH_CSTEP : (phase == 2 ? PH_AGRAD : PH_ASTEP), st);
     return;
   }
   GCRL_REQUIRE(eps_next != nullptr && (eps_cur != nullptr || !(flags & 1)), "NULL rsample noise tensor");
@@ -860,28 +903,26 @@ void sac_update(gcrl_sac *ag, int phase, gcrl_her *buf, int64_t B64, const int64
     out[2] = float(1.0 - lr * double(ag->cfg.weight_decay));
     out[3] = 0.f;
   };
-  int slot;
-  auto *sc = reinterpret_cast<StepScalars *>(ag->scal_stage.acquire(sizeof(StepScalars), &slot));
+  int slot;   // d_scalars[0] = critic / actor AdamW scalars, d_scalars[1] (first 3 floats) = alpha's
+  auto *sc = reinterpret_cast<StepScalars *>(ag->scal_stage.acquire(2 * sizeof(StepScalars), &slot));
   ag->adam_t_c += 1;
   fill(ag->adam_t_c, lr_c, &sc->step_size_c);
   if (flags & 1) ag->adam_t_a += 1;
   fill(std::max(1, ag->adam_t_a), lr_a, &sc->step_size_a);
-  GCRL_CUDA(cudaMemcpyAsync(ag->d_scalars, sc, sizeof(StepScalars), cudaMemcpyHostToDevice, st));
-  ag->scal_stage.release(slot, st);
-
-  float al[4] = {0.f, 1.f, 1.f, 0.f};
+  float *al = reinterpret_cast<float *>(sc + 1);
+  al[0] = 0.f; al[1] = 1.f; al[2] = 1.f; al[3] = 0.f;
   if ((flags & 1) && (flags & 4)) {
     ag->adam_t_alpha += 1;
     fill(ag->adam_t_alpha, double(ag->cfg.alpha_lr), al);
   }
+  GCRL_CUDA(cudaMemcpyAsync(ag->d_scalars, sc, sizeof(StepScalars) + 16, cudaMemcpyHostToDevice, st));
+  ag->scal_stage.release(slot, st);
   if (phase == 0) {
     ag->dp_B = B; ag->dp_flags = flags;
-    for (int i = 0; i < 3; ++i) ag->dp_alpha[i] = al[i];
-    critic_update(ag, B, flags, PH_CGRAD, st);
+    run_phases(ag, B, flags, PH_CGRAD, st);
     return;
   }
-  critic_update(ag, B, flags, PH_ALL, st);
-  if (flags & 1) actor_update(ag, B, flags, PH_ALL, al[0], al[1], al[2], st);
+  run_phases(ag, B, flags, PH_ALL, st);
   read_metrics(ag, flags, metrics_host, st);
 }
 
@@ -991,7 +1032,10 @@ int gcrl_sac_create(gcrl_sac **out, int device, const gcrl_sac_config *cfg) {
     ag->alpha_state = dev_alloc<float>(4);
     const float init_alpha[4] = {0.f, 1.f, 0.f, 0.f};       // log_alpha = 0 (:424)
     GCRL_CUDA(cudaMemcpy(ag->alpha_state, init_alpha, sizeof(init_alpha), cudaMemcpyHostToDevice));
-    ag->d_scalars = dev_alloc<StepScalars>(1);
+    ag->d_scalars = dev_alloc<StepScalars>(2);
+    GCRL_CUDA(cudaStreamCreateWithFlags(&ag->cap_stream, cudaStreamNonBlocking));
+    const char *ng = getenv("GCRL_B200_NO_GRAPH");
+    ag->use_graphs = !(ng && ng[0] == '1');
     ag->scal_stage.init(256);
     ag->io_stage.init(size_t(1) << 16);
   } catch (...) {
@@ -1016,6 +1060,8 @@ int gcrl_sac_destroy(gcrl_sac *ag) {
                    ag->dzh, ag->eps_next, ag->eps_cur, ag->partials, ag->sumsq, ag->mdev, ag->alpha_state, ag->d_io,
                    ag->critic_grads})
     if (p) cudaFree(p);
+  for (auto &kv : ag->graphs) cudaGraphExecDestroy(kv.second.exec);
+  if (ag->cap_stream) cudaStreamDestroy(ag->cap_stream);
   cudaFree(ag->d_scalars);
   ag->scal_stage.destroy();
   ag->io_stage.destroy();
