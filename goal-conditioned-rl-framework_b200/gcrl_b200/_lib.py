@@ -58,6 +58,8 @@ SIGNATURES = {
     "gcrl_her_sample": (C.c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp, vp]),
     "gcrl_her_sample_dev_idx": (C.c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp]),
     "gcrl_her_sample_host": (C.c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "gcrl_pyrandom_randint": (C.c_int, [vp, C.POINTER(C.c_int), c_i64, vp, vp, vp]),
+    "gcrl_pyrandom_sample_range": (C.c_int, [vp, C.POINTER(C.c_int), c_i64, c_i64, vp]),
     # normaliser
     "gcrl_norm_create": (C.c_int, [pp, C.c_int, C.c_int, c_f64, c_f64]),
     "gcrl_norm_destroy": (C.c_int, [vp]),
@@ -164,3 +166,52 @@ def np_ptr(arr):
 def current_stream(device_index):
     import torch
     return vp(torch.cuda.current_stream(device_index).cuda_stream)
+
+
+# -- CPython `random` mirror (csrc/pyrandom.cu): exact draws from the interpreter's global stream ------------
+def _mt_load():
+    import random
+
+    import numpy as np
+    version, internal, gauss = random.getstate()
+    if version != 3 or len(internal) != 625:
+        raise RuntimeError("unexpected random.getstate() layout")
+    return np.array(internal[:-1], dtype=np.uint32), C.c_int(internal[-1]), gauss
+
+
+def _mt_store(mt, pos, gauss):
+    import random
+    random.setstate((3, tuple(mt.tolist()) + (pos.value,), gauss))
+
+
+def py_randint_seq(lo, hi):
+    """[random.randint(lo[i], hi[i]) for i in range(len(lo))], consuming the global stream identically."""
+    import numpy as np
+    lo = np.ascontiguousarray(lo, np.int32)
+    hi = np.ascontiguousarray(hi, np.int32)
+    out = np.empty(lo.shape, np.int32)
+    mt, pos, gauss = _mt_load()
+    check(lib.gcrl_pyrandom_randint(np_ptr(mt), C.byref(pos), lo.size, np_ptr(lo), np_ptr(hi), np_ptr(out)))
+    _mt_store(mt, pos, gauss)
+    return out
+
+
+def py_sample_range_from(state, n, k):
+    """(positions, state_after) of random.sample(range(n), k) started from ``state`` (a random.getstate()
+    tuple); the interpreter's global generator is not touched."""
+    import numpy as np
+    version, internal, gauss = state
+    if version != 3 or len(internal) != 625:
+        raise RuntimeError("unexpected random.getstate() layout")
+    mt, pos = np.array(internal[:-1], dtype=np.uint32), C.c_int(internal[-1])
+    out = np.empty(int(k), np.int64)
+    check(lib.gcrl_pyrandom_sample_range(np_ptr(mt), C.byref(pos), int(n), int(k), np_ptr(out)))
+    return out, (3, tuple(mt.tolist()) + (pos.value,), gauss)
+
+
+def py_sample_range(n, k):
+    """np.array(random.sample(range(n), k), int64), consuming the global stream identically."""
+    import random
+    out, after = py_sample_range_from(random.getstate(), n, k)
+    random.setstate(after)
+    return out

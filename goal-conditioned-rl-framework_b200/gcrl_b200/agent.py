@@ -413,9 +413,7 @@ class _AgentBase:
     def _predraw(self, B):
         n = len(self.buffer)
         before = random.getstate()
-        idx = random.sample(range(n), B)
-        after = random.getstate()
-        random.setstate(before)
+        idx, after = _lib.py_sample_range_from(before, n, B)     # C mirror of random.sample; global state untouched
         self._pre = (before, after, idx, n, B)
 
     def _take_predrawn(self, B):
@@ -424,7 +422,7 @@ class _AgentBase:
         if pre is not None and pre[3] == n and pre[4] == B and random.getstate() == pre[0]:
             random.setstate(pre[1])
             return pre[2]
-        return random.sample(range(n), B)
+        return _lib.py_sample_range(n, B)
 
     def read_metrics(self):
         check(lib.gcrl_agent_read_metrics(self._h, C.cast(self._metrics, vp), self._stream()))

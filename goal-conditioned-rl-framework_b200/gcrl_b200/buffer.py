@@ -109,9 +109,9 @@ class HERBuffer:
         """random.randint(t+1, T-1) in apply_her's order (src/buffer.py:145-153)."""
         k = self.k_future
         fut = np.zeros((T, max(k, 1)), np.uint8)
-        for t in range(T - 1):
-            for j in range(k):
-                fut[t, j] = random.randint(t + 1, T - 1)
+        if T > 1 and k > 0:   # the same (T - 1) * k draws, in the same order, through the C mirror of CPython's MT
+            lo = np.repeat(np.arange(1, T, dtype=np.int32), k)
+            fut[:T - 1, :k] = _lib.py_randint_seq(lo, np.full(lo.shape, T - 1, np.int32)).reshape(T - 1, k)
         return fut
 
     def _commit(self, ep):
@@ -128,7 +128,7 @@ class HERBuffer:
         out = [torch.empty((B, w), dtype=torch.float32, device=dev) for w in (D, A, 1, D, 1)]
         iptr = None
         if indices is None and self.index_source == "host":
-            indices = random.sample(range(len(self)), B)       # == random.sample(deque, B)
+            indices = _lib.py_sample_range(len(self), B)       # == random.sample(deque, B), same MT stream
         if indices is not None:
             indices = np.ascontiguousarray(indices, np.int64)
             iptr = np_ptr(indices)
@@ -145,7 +145,7 @@ class HERBuffer:
         out = [np.empty((B, w), np.float32) for w in (D, A, 1, D, 1)]
         iptr = None
         if indices is None and self.index_source == "host":
-            indices = random.sample(range(len(self)), B)
+            indices = _lib.py_sample_range(len(self), B)
         if indices is not None:
             indices = np.ascontiguousarray(indices, np.int64)
             iptr = np_ptr(indices)

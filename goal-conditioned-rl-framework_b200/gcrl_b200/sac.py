@@ -289,7 +289,7 @@ class _SacBase(_AgentBase):
         if batch is None:
             assert len(self.buffer) >= B, "[ERROR] Not enough in buffer to sample"
             if indices is None and self.index_source == "host":
-                indices = random.sample(range(len(self.buffer)), B)
+                indices = _lib.py_sample_range(len(self.buffer), B)
             if indices is not None:
                 indices = np.ascontiguousarray(indices, np.int64)
                 iptr = np_ptr(indices)

@@ -96,6 +96,15 @@ int gcrl_her_sample_host(gcrl_her *h, int64_t B, const int64_t *idx_host, float 
                          float *actions, float *rewards, float *next_states, float *dones,
                          int64_t *idx_out, void *stream);
 
+/* Host-side mirror of CPython's `random` draws on this path (no GPU involved): advance a copy of the
+ * interpreter's MT19937 state (the 624 words and position of random.getstate()) exactly as
+ * random.randint(lo[i], hi[i]) (src/buffer.py:153) / random.sample(range(n), k) (== random.sample(deque, k),
+ * src/buffer.py:124) would, CPython 3.12 algorithms.  The caller writes the state back with
+ * random.setstate(), so every other consumer of the global stream sees the reference's interleaving. */
+int gcrl_pyrandom_randint(uint32_t *mt624, int *pos, int64_t count, const int32_t *lo, const int32_t *hi,
+                          int32_t *out);
+int gcrl_pyrandom_sample_range(uint32_t *mt624, int *pos, int64_t n, int64_t k, int64_t *out);
+
 /* ------------------------------------------------------------------------------------
  * Running normaliser -- replaces RunningNormalizer, src/utils.py:68-117
  * ------------------------------------------------------------------------------------ */

@@ -14,6 +14,8 @@ from tests.helpers import HER_CASES, bits, her_episodes, load
 
 pytestmark = pytest.mark.gpu
 
+HER_SEEDS = {"reach_small": 0, "push_evict": 1, "pickplace_k8": 2, "k0": 3}   # make_golden.py::main
+
 FIELDS = ("s", "a", "r", "ns", "d")
 
 
@@ -63,30 +65,29 @@ def test_sample_matches_reference_batches(case):
 
 @pytest.mark.parametrize("case", ["reach_small", "push_evict"])
 def test_push_api_consumes_reference_mt_stream(case):
-    """push() per transition + random.randint in apply_her's order + random.sample: with the
-    generator's seed the product consumes the identical Mersenne-Twister stream."""
+    """push() per transition, then sample(): seeded like the fixture generator (random.seed(1898 + seed),
+    tests/golden/make_golden.py::her_case) the product must consume the interpreter's Mersenne-Twister exactly
+    as the reference does -- every random.randint of apply_her (src/buffer.py:153) and every random.sample of
+    sample() (:124), now drawn by the C mirror of CPython's generator -- so the deque dump AND the sampled
+    batches are reproduced bit for bit without being told a single index."""
     g = load("her_" + case)
     eps = her_episodes(g)
     buf, k = make_buffer(g)
-    draws = []
-    for ep in eps:
-        T = ep["s"].shape[0]
-        draws.extend(int(v) for v in ep["fut"][:T - 1].reshape(-1))
-    it = iter(draws)
-    real = random.randint
-    random.randint = lambda a, b: next(it)
-    try:
-        for ep in eps:                                         # commit order == golden order
-            for t in range(ep["s"].shape[0]):
-                buf.push(0, ep["s"][t], ep["a"][t], ep["ns"][t], ep["r"][t], bool(ep["d"][t]),
-                         ep["dg"][t], ep["ag"][t])
-    finally:
-        random.randint = real
-    assert next(it, None) is None
+    random.seed(1898 + HER_SEEDS[case])
+    for ep in eps:                                             # commit order == golden order
+        for t in range(ep["s"].shape[0]):
+            buf.push(0, ep["s"][t], ep["a"][t], ep["ns"][t], ep["r"][t], bool(ep["d"][t]),
+                     ep["dg"][t], ep["ag"][t])
     n = int(g["len"])
     out = buf.sample_host(n, indices=np.arange(n))
     for got, key in zip(out, ("dump_s", "dump_a", "dump_r", "dump_ns", "dump_d")):
         assert_bits(got, g[key], (case, key))
+    for bi in range(int(g["n_batches"])):                      # the reference's sample() calls, in order
+        B = g[f"b{bi}_idx"].shape[0]
+        *batch, used = buf.sample_host(B, return_indices=True)
+        assert np.array_equal(used, g[f"b{bi}_idx"]), (case, bi)
+        for got, key in zip(batch, ("s", "a", "r", "ns", "d")):
+            assert_bits(got, g[f"b{bi}_{key}"], (case, bi, key))
 
 
 def test_reward_known_answers_through_the_kernel():

@@ -1,0 +1,54 @@
+"""The C mirror of CPython's `random` draws (csrc/pyrandom.cu) against the interpreter itself: same values AND
+the same generator state afterwards, so the streams stay interleavable with any other consumer."""
+import random
+
+import numpy as np
+import pytest
+
+from gcrl_b200 import _lib
+
+
+@pytest.mark.parametrize("seed", [0, 1898, 12345])
+def test_randint_sequence_matches_python(seed):
+    rng = np.random.default_rng(seed)
+    lo = rng.integers(0, 50, 5000).astype(np.int32)
+    hi = (lo + rng.integers(0, 300, 5000)).astype(np.int32)
+    random.seed(seed)
+    random.random()                                   # arbitrary position inside the 624-word block
+    want = [random.randint(int(a), int(b)) for a, b in zip(lo, hi)]
+    after = random.getstate()
+    random.seed(seed)
+    random.random()
+    got = _lib.py_randint_seq(lo, hi)
+    assert got.tolist() == want
+    assert random.getstate() == after
+    assert random.random() == random.Random().random() or True
+
+
+@pytest.mark.parametrize("n,k", [(10, 10), (21, 5), (100, 30), (117, 64), (4_920_000, 256), (1_000_000, 65536),
+                                 (4096, 4096), (5, 0), (2 ** 20, 1000), (2 ** 31 + 5, 300)])
+def test_sample_range_matches_python(n, k):
+    random.seed(n + k)
+    want = random.sample(range(n), k)
+    after = random.getstate()
+    random.seed(n + k)
+    got = _lib.py_sample_range(n, k)
+    assert got.tolist() == want
+    assert random.getstate() == after
+
+
+def test_future_draws_of_the_buffer_use_the_same_stream():
+    """HERBuffer._draw_future == the reference's nested randint loop (src/buffer.py:145-153)."""
+    from gcrl_b200.buffer import HERBuffer
+    buf = HERBuffer.__new__(HERBuffer)
+    buf.k_future = 4
+    for T in (1, 2, 7, 50):
+        random.seed(T)
+        want = np.zeros((T, 4), np.uint8)
+        for t in range(T - 1):
+            for j in range(4):
+                want[t, j] = random.randint(t + 1, T - 1)
+        after = random.getstate()
+        random.seed(T)
+        got = buf._draw_future(T)
+        assert np.array_equal(got, want) and random.getstate() == after
