@@ -551,6 +551,45 @@ int64_t gcrl_her_live_transitions(const gcrl_her *h) {
   return h ? h->total_tr - h->tr_live_first : 0;
 }
 
+// ---- export of the live window (true resume): episodes oldest first, exactly as committed ----------
+int64_t gcrl_her_live_episodes(const gcrl_her *h) { return h ? int64_t(h->live.size()) : 0; }
+
+int gcrl_her_get_episode(gcrl_her *h, int64_t i, int *T_out, float *s, float *a, float *ns, float *r, float *d,
+                         float *ag, uint8_t *fut, void *stream) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(h != nullptr && T_out != nullptr, "NULL argument");
+  GCRL_REQUIRE(i >= 0 && i < int64_t(h->live.size()), "episode index outside the live window");
+  const HerGeom &g = h->g;
+  int64_t first = h->tr_live_first;
+  for (int64_t e = 0; e < i; ++e) first += h->live[size_t(e)].second;
+  const int T = h->live[size_t(i)].second;
+  *T_out = T;
+  if (s == nullptr) return GCRL_OK;                      // length query only
+  GCRL_REQUIRE(a && ns && r && d && ag && (fut || g.K == 0), "NULL episode array");
+  GCRL_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = as_stream(stream);
+  std::vector<float> rows(size_t(T) * g.row_f);
+  const int64_t slot0 = first % h->cap_tr;
+  const int64_t n0 = std::min<int64_t>(T, h->cap_tr - slot0);       // the ring may wrap inside the episode
+  GCRL_CUDA(cudaMemcpyAsync(rows.data(), g.rows + size_t(slot0) * g.row_f, size_t(n0) * g.row_f * 4,
+                            cudaMemcpyDeviceToHost, st));
+  if (n0 < T)
+    GCRL_CUDA(cudaMemcpyAsync(rows.data() + size_t(n0) * g.row_f, g.rows, size_t(T - n0) * g.row_f * 4,
+                              cudaMemcpyDeviceToHost, st));
+  GCRL_CUDA(cudaStreamSynchronize(st));
+  for (int t = 0; t < T; ++t) {
+    const float *row = rows.data() + size_t(t) * g.row_f;
+    std::memcpy(s + size_t(t) * g.D, row, size_t(g.D) * 4);
+    std::memcpy(ns + size_t(t) * g.D, row + g.off_ns, size_t(g.D) * 4);
+    std::memcpy(a + size_t(t) * g.A, row + g.off_a, size_t(g.A) * 4);
+    r[t] = row[g.off_r];
+    d[t] = row[g.off_d];
+    std::memcpy(ag + size_t(t) * g.G, row + g.off_ag, size_t(g.G) * 4);
+    if (g.K > 0) std::memcpy(fut + size_t(t) * g.K, row + g.off_fut, size_t(g.K));
+  }
+  GCRL_API_END
+}
+
 int gcrl_her_clear(gcrl_her *h) {
   GCRL_API_BEGIN
   GCRL_REQUIRE(h != nullptr, "handle is NULL");

@@ -55,6 +55,8 @@ SIGNATURES = {
     "gcrl_her_total_entries": (c_i64, [vp]),
     "gcrl_her_live_transitions": (c_i64, [vp]),
     "gcrl_her_clear": (C.c_int, [vp]),
+    "gcrl_her_live_episodes": (c_i64, [vp]),
+    "gcrl_her_get_episode": (C.c_int, [vp, c_i64, C.POINTER(C.c_int), vp, vp, vp, vp, vp, vp, vp, vp]),
     "gcrl_her_sample": (C.c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp, vp]),
     "gcrl_her_sample_dev_idx": (C.c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp]),
     "gcrl_her_sample_host": (C.c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp, vp]),

@@ -390,15 +390,28 @@ class _AgentBase:
             sch.last_epoch, sch.lr = int(sd[name]["last_epoch"]), float(sd[name]["lr"])
         self.beta = sd["beta"]
 
-    def save_checkpoint(self, path: str):
-        """save_weights(path) (the reference's files) plus ``trainer_state.pt`` for a true resume."""
+    def save_checkpoint(self, path: str, with_buffer: bool = True):
+        """save_weights(path) (the reference's files) plus ``trainer_state.pt`` (targets, Adam, schedulers,
+        the interpreter's ``random`` state) and ``buffer_state.pt`` (the replay buffer's live window) for a
+        true resume."""
         import torch
         self.save_weights(path)
-        torch.save(self.state_dict(), os.path.join(path, "trainer_state.pt"))
+        st = self.state_dict()
+        st["python_random"] = random.getstate()
+        torch.save(st, os.path.join(path, "trainer_state.pt"))
+        if with_buffer:
+            torch.save(self.buffer.state_dict(), os.path.join(path, "buffer_state.pt"))
 
     def load_checkpoint(self, path: str):
         import torch
-        self.load_state_dict(torch.load(os.path.join(path, "trainer_state.pt"), map_location="cpu", weights_only=False))
+        st = torch.load(os.path.join(path, "trainer_state.pt"), map_location="cpu", weights_only=False)
+        self.load_state_dict(st)
+        bpath = os.path.join(path, "buffer_state.pt")
+        if os.path.exists(bpath):
+            self.buffer.load_state_dict(torch.load(bpath, map_location="cpu", weights_only=False))
+        if "python_random" in st:
+            random.setstate(st["python_random"])
+        self._pre = None
 
     # -- host index stream: latency hiding without changing the Mersenne-Twister stream ---------------
     # ``random.sample(range(len), B)`` costs ~0.1 ms of host time per update.  The draw for the next

@@ -158,5 +158,43 @@ class HERBuffer:
     def __len__(self):
         return int(lib.gcrl_her_len(self._h)) if self._h else 0
 
+    # -- true resume: the live window + the per-env staging deques ---------------------------
+    def state_dict(self):
+        """Every episode that still holds a live entry (oldest first, with the future indices that were
+        drawn) and the transitions staged per env.  ``load_state_dict`` on a fresh buffer with the same
+        ``max_mem_len`` / ``k_future`` reproduces every deque position, so a resumed run samples the same
+        batches from the same ``random`` stream."""
+        eps = []
+        if self._h:
+            D, A, G = self._dims
+            k = self.k_future
+            for i in range(int(lib.gcrl_her_live_episodes(self._h))):
+                T = C.c_int()
+                check(lib.gcrl_her_get_episode(self._h, i, C.byref(T), *([None] * 7), self._stream()))
+                n = T.value
+                arrs = dict(s=np.empty((n, D), np.float32), a=np.empty((n, A), np.float32),
+                            ns=np.empty((n, D), np.float32), r=np.empty(n, np.float32), d=np.empty(n, np.float32),
+                            ag=np.empty((n, G), np.float32), fut=np.zeros((n, max(k, 1)), np.uint8))
+                fut = np.empty((n, k), np.uint8) if k else None
+                check(lib.gcrl_her_get_episode(self._h, i, C.byref(T), np_ptr(arrs["s"]), np_ptr(arrs["a"]),
+                                               np_ptr(arrs["ns"]), np_ptr(arrs["r"]), np_ptr(arrs["d"]),
+                                               np_ptr(arrs["ag"]), np_ptr(fut) if k else None, self._stream()))
+                if k:
+                    arrs["fut"] = fut
+                eps.append(arrs)
+        return {"max_mem_len": self.max_mem_len, "k_future": self.k_future, "dims": self._dims, "episodes": eps,
+                "staging": [list(ep) for ep in self.episodes]}
+
+    def load_state_dict(self, sd):
+        if sd["max_mem_len"] != self.max_mem_len or sd["k_future"] != self.k_future:
+            raise ValueError("buffer checkpoint was written with a different max_mem_len / k_future")
+        if self._h:
+            check(lib.gcrl_her_clear(self._h))
+        for ep in sd["episodes"]:
+            self.push_episode(ep["s"], ep["a"], ep["ns"], ep["r"], ep["d"], ep["ag"], ep["fut"])
+        for dq, items in zip(self.episodes, sd["staging"]):
+            dq.clear()
+            dq.extend(items)
+
     def compute_termination(self, dg, ag):                 # src/buffer.py:140-141
         return np.linalg.norm(np.asarray(dg) - np.asarray(ag), axis=-1) < self.threshold

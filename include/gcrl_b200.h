@@ -75,6 +75,13 @@ int64_t gcrl_her_len(const gcrl_her *h);            /* __len__, src/buffer.py:13
 int64_t gcrl_her_total_entries(const gcrl_her *h);  /* entries ever appended            */
 int64_t gcrl_her_live_transitions(const gcrl_her *h);
 int gcrl_her_clear(gcrl_her *h);
+/* Export of the live window for a true resume (the reference never checkpoints its replay buffer,
+ * src/env.py:430-440): the episodes that still hold a live entry, oldest first, exactly as committed
+ * (rows as pushed, the future indices that were drawn).  Re-pushing them in order into a fresh buffer
+ * with the same max_entries reproduces every deque position.  s == NULL: query T only. */
+int64_t gcrl_her_live_episodes(const gcrl_her *h);
+int gcrl_her_get_episode(gcrl_her *h, int64_t i, int *T, float *s, float *a, float *ns, float *r, float *d,
+                         float *ag, uint8_t *fut, void *stream);
 
 /* sample(batch_size), src/buffer.py:121-135.  Outputs are DEVICE pointers:
  * states [B,D], actions [B,A], rewards [B,1], next_states [B,D], dones [B,1] float32.

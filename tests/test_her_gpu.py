@@ -236,3 +236,50 @@ def test_full_size_properties_1m_buffer():
     again = buf.sample_host(B, indices=used)
     for x, y in zip(out, again):
         assert np.array_equal(bits(x), bits(y))
+
+
+def test_buffer_and_agent_resume_from_checkpoint_sample_the_same_batches(tmp_path):
+    """A partly evicted buffer + per-env staging + the interpreter's random state + the agent survive
+    save_checkpoint / load_checkpoint: the resumed run draws the same positions, gathers the same bits and
+    makes bit-identical updates, including the episodes committed after the resume."""
+    import torch
+    from gcrl_b200 import DDPG
+    from tests.test_ddpg_gpu import make_config
+    g = load("her_push_evict")
+    eps = her_episodes(g)
+    D, A = 22, 3
+    cfg = make_config(hidden_dim=64, batch_size=64, max_len=777)        # 777 entries: the oldest episodes are evicted
+
+    def feed(ag, ep, upto=None):
+        T = ep["s"].shape[0] if upto is None else upto
+        for t in range(T):
+            ag.push_her(0, ep["s"][t], ep["a"][t], ep["ns"][t], ep["r"][t], bool(ep["d"][t]), ep["dg"][t], ep["ag"][t])
+    torch.manual_seed(1)
+    random.seed(77)
+    a1 = DDPG(D, A, cfg, None, 1, 40)
+    for ep in eps[:6]:
+        feed(a1, ep)
+    feed(a1, eps[6], upto=9)                                            # 9 transitions left in the staging deque
+    for step in (1, 2, 3):
+        a1.update(step)
+    a1.save_checkpoint(str(tmp_path / "ck"))
+
+    def rest(ag):
+        out = []
+        ep = eps[6]
+        for t in range(9, ep["s"].shape[0]):
+            ag.push_her(0, ep["s"][t], ep["a"][t], ep["ns"][t], ep["r"][t], bool(ep["d"][t]), ep["dg"][t], ep["ag"][t])
+        feed(ag, eps[7])
+        for step in (4, 5, 6):
+            out.append([float(x) for x in ag.update(step)])
+        n = len(ag.buffer)
+        return out, n, [x.copy() for x in ag.buffer.sample_host(n, indices=np.arange(n))]
+    ref = rest(a1)
+    torch.manual_seed(2)
+    random.seed(5)
+    a2 = DDPG(D, A, cfg, None, 1, 40)
+    a2.load_checkpoint(str(tmp_path / "ck"))
+    got = rest(a2)
+    assert ref[0] == got[0] and ref[1] == got[1]
+    for x, y in zip(ref[2], got[2]):
+        assert_bits(x, y, "resumed buffer dump")
