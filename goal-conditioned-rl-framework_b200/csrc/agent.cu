@@ -320,11 +320,11 @@ struct PhaseState {
 // ---- row-slab fused path (fused.cu): DDPG, B <= 1024 ---------------------------------------------
 constexpr int kClusterMaxBatch = 2048;
 bool cluster_ok(const gcrl_agent *ag, int B) {
-  return ag->use_fused && ag->use_cluster && !ag->td3 && B <= kClusterMaxBatch &&
+  return ag->use_fused && ag->use_cluster && !ag->td3 && B <= kClusterMaxBatch &&  // (cluster.cu: DDPG only)
          cluster_supported(B, ag->D, ag->A, ag->H, ag->L);
 }
 bool fused_ok(const gcrl_agent *ag, int B) {
-  return cluster_ok(ag, B) || (ag->use_fused && !ag->td3 && fused_supported(B, ag->D, ag->A, ag->H, ag->L));
+  return cluster_ok(ag, B) || (ag->use_fused && fused_supported(B, ag->D, ag->A, ag->H, ag->L));
 }
 
 FusedNet fused_net(const gcrl_agent *ag, const Net &n) {
@@ -354,31 +354,43 @@ int fused_wgrads(gcrl_agent *ag, const Net &n, const Acts &acts, int K0, const f
   return launch_multi_wgrad(pr, L + 1, B, ag->slab, kMaxSplits, st);
 }
 
-FusedCriticArgs fused_critic_args(gcrl_agent *ag, int B) {
+FusedCriticArgs fused_critic_args(gcrl_agent *ag, int B, int which = 0) {
   FusedCriticArgs a{};
   a.ta = fused_net(ag, ag->net[T_ACTOR]);
   a.tc = fused_net(ag, ag->net[T_CRITIC1]);
-  a.c = fused_net(ag, ag->net[CRITIC1]);
+  a.c = fused_net(ag, ag->net[which == 0 ? CRITIC1 : CRITIC2]);
+  if (ag->td3) {
+    a.tc2 = fused_net(ag, ag->net[T_CRITIC2]);
+    a.has_tc2 = 1;
+    a.noise = ag->noise;
+    a.policy_noise = ag->cfg.policy_noise; a.noise_clamp = ag->cfg.noise_clamp;
+    a.loss_kind = 1;
+    if (which == 1) { a.y_in = ag->yv; a.q_other = ag->q1; }     // target and Q1 left by the critic-1 launch
+  }
   a.s = ag->bs; a.a = ag->ba; a.r = ag->br0; a.ns = ag->bns; a.d = ag->bd0;
   a.B = B; a.D = ag->D; a.A = ag->A; a.H = ag->H; a.L = ag->L; a.ldh = ag->ldh; a.ldc = ag->ldc;
   a.gamma = ag->cfg.gamma;
   a.y_lo = float(-1.0 / (1.0 - double(ag->cfg.gamma)));
-  a.clamp_y = 1;                                       // DDPG clamps y to [-1/(1-gamma), 0] (:1317)
-  a.sa_out = ag->sa;
-  for (int l = 0; l < ag->L; ++l) { a.h_out[l] = ag->acts_c1.h[l]; a.dz_out[l] = ag->dzl[l]; }
-  a.dzh_out = ag->dzh; a.y_out = ag->yv; a.q_out = ag->q1;
+  a.clamp_y = ag->td3 ? 0 : 1;                         // DDPG clamps y to [-1/(1-gamma), 0] (:1317); TD3 does not
+  a.sa_out = which == 0 ? ag->sa : nullptr;
+  const Acts &acts = which == 0 ? ag->acts_c1 : ag->acts_c2;
+  for (int l = 0; l < ag->L; ++l) { a.h_out[l] = acts.h[l]; a.dz_out[l] = ag->dzl[l]; }
+  a.dzh_out = ag->dzh; a.y_out = ag->yv; a.q_out = which == 0 ? ag->q1 : ag->q2;
   a.metric_partials = ag->metric_partials;
   return a;
 }
 
-void fused_critic_phase_grads(gcrl_agent *ag, int B, cudaStream_t st) {
-  const FusedCriticArgs a = fused_critic_args(ag, B);
+void fused_critic_phase_grads(gcrl_agent *ag, int B, int which, cudaStream_t st) {
+  const FusedCriticArgs a = fused_critic_args(ag, B, which);
   const int slabs = cluster_ok(ag, B) ? launch_cluster_critic(a, st) : launch_fused_critic(a, st);
-  const Net &c = ag->net[CRITIC1];
-  const int S = fused_wgrads(ag, c, ag->acts_c1, ag->D + ag->A, ag->dzh, 1, B, st);
+  Net &c = ag->net[which == 0 ? CRITIC1 : CRITIC2];
+  const int S = fused_wgrads(ag, c, which == 0 ? ag->acts_c1 : ag->acts_c2, ag->D + ag->A, ag->dzh, 1, B, st);
   int splits[8];
   for (int l = 0; l < 8; ++l) splits[l] = S;
-  reduce_grads(ag, ag->net[CRITIC1], splits, S, false, S_CLOSS, S_TD, S_Q, slabs, B, st);
+  // TD3: td error / Q metrics come from the critic-2 launch (they need both critics' Q)
+  const bool metrics_here = !ag->td3 || which == 1;
+  reduce_grads(ag, c, splits, S, false, which == 0 ? S_CLOSS : S_C2LOSS, metrics_here ? S_TD : -1,
+               metrics_here ? S_Q : -1, slabs, B, st);
 }
 
 void fused_actor_phase_grads(gcrl_agent *ag, int B, cudaStream_t st) {
@@ -399,7 +411,7 @@ void fused_actor_phase_grads(gcrl_agent *ag, int B, cudaStream_t st) {
 
 // critic(s): forward, loss, backward, partials -> flat local-mean gradient(s) + metrics
 void critic_phase_grads(gcrl_agent *ag, int B, const float *noise, cudaStream_t st) {
-  if (fused_ok(ag, B)) { fused_critic_phase_grads(ag, B, st); return; }
+  if (fused_ok(ag, B)) { fused_critic_phase_grads(ag, B, 0, st); return; }
   PhaseState ps;
   targets_and_critic_forward(ag, B, noise, st);
   critic_forward_backward(ag, 0, B, ps.splits, &ps.head_splits, &ps.metric_splits, st);
@@ -407,6 +419,7 @@ void critic_phase_grads(gcrl_agent *ag, int B, const float *noise, cudaStream_t 
                ag->td3 ? -1 : S_Q, ps.metric_splits, B, st);
 }
 void critic2_phase_grads(gcrl_agent *ag, int B, cudaStream_t st) {   // TD3 only; reuses dz / partials
+  if (fused_ok(ag, B)) { fused_critic_phase_grads(ag, B, 1, st); return; }
   PhaseState ps;
   critic_forward_backward(ag, 1, B, ps.splits, &ps.head_splits, &ps.metric_splits, st);
   reduce_grads(ag, ag->net[CRITIC2], ps.splits, ps.head_splits, false, S_C2LOSS, S_TD, S_Q, ps.metric_splits,

@@ -218,14 +218,33 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_critic_kernel(FusedCri
     }
   }
 
-  // ---- 1. a' = target_actor(s') (:1312) ----
-  const float *h = slab_forward<R>(a.ta, L, H, x_ns, D, nullptr, sp.t0, sp.t1, sp.red, nullptr, 0, row0, B);
-  slab_head<R>(h, H, a.ta.Wh, a.ta.ldwh, a.ta.bh, A, true, anext);
-  for (int e = tid; e < A * R; e += kFusedThreads) x_ns[D * R + e] = anext[e];
-  __syncthreads();
-  // ---- 2. q' = target_critic([s', a']) (:1313-1315) ----
-  h = slab_forward<R>(a.tc, L, H, x_ns, D + A, nullptr, sp.t0, sp.t1, sp.red, nullptr, 0, row0, B);
-  slab_head<R>(h, H, a.tc.Wh, a.tc.ldwh, a.tc.bh, 1, false, qn);
+  const float *h;
+  if (a.y_in == nullptr) {
+    // ---- 1. a' = target_actor(s') (:1312); TD3: + clamp(noise * sigma, +-c), clamped to [-1, 1] (:174-179) ----
+    h = slab_forward<R>(a.ta, L, H, x_ns, D, nullptr, sp.t0, sp.t1, sp.red, nullptr, 0, row0, B);
+    slab_head<R>(h, H, a.ta.Wh, a.ta.ldwh, a.ta.bh, A, true, anext);
+    for (int e = tid; e < A * R; e += kFusedThreads) {
+      float v = anext[e];
+      if (a.noise != nullptr) {
+        const int j = e / R, row = row0 + (e - j * R);
+        float n = row < B ? a.noise[size_t(row) * A + j] * a.policy_noise : 0.f;
+        n = fminf(fmaxf(n, -a.noise_clamp), a.noise_clamp);
+        v = fminf(fmaxf(v + n, -1.0f), 1.0f);
+      }
+      x_ns[D * R + e] = v;
+    }
+    __syncthreads();
+    // ---- 2. q' = target_critic([s', a']) (:1313-1315); TD3: min over the two target critics (:181-183) ----
+    h = slab_forward<R>(a.tc, L, H, x_ns, D + A, nullptr, sp.t0, sp.t1, sp.red, nullptr, 0, row0, B);
+    slab_head<R>(h, H, a.tc.Wh, a.tc.ldwh, a.tc.bh, 1, false, qn);
+    if (a.has_tc2) {
+      float *qn2 = anext;          // a' already sits in x_ns
+      h = slab_forward<R>(a.tc2, L, H, x_ns, D + A, nullptr, sp.t0, sp.t1, sp.red, nullptr, 0, row0, B);
+      slab_head<R>(h, H, a.tc2.Wh, a.tc2.ldwh, a.tc2.bh, 1, false, qn2);
+      if (tid < R) qn[tid] = fminf(qn[tid], qn2[tid]);
+      __syncthreads();
+    }
+  }
   // ---- 3. q = critic([s, a]) (:1319), activations kept for the backward pass ----
   h = slab_forward<R>(a.c, L, H, x_sa, D + A, sp.keep1, nullptr, nullptr, sp.red, a.h_out, a.ldh, row0, B);
   slab_head<R>(h, H, a.c.Wh, a.c.ldwh, a.c.bh, 1, false, q);
@@ -237,15 +256,32 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_critic_kernel(FusedCri
       const int row = row0 + r;
       float g = 0.f;
       if (row < B) {
-        float y = rr[r] + a.gamma * (1.0f - dd[r]) * qn[r];
-        if (a.clamp_y) y = fminf(fmaxf(y, a.y_lo), 0.0f);
+        float y;
+        if (a.y_in != nullptr) {
+          y = a.y_in[row];
+        } else {
+          y = rr[r] + a.gamma * (1.0f - dd[r]) * qn[r];
+          if (a.clamp_y) y = fminf(fmaxf(y, a.y_lo), 0.0f);
+        }
         const float diff = q[r] - y;
-        ls += diff * diff;
-        ts += fabsf(y - q[r]);
-        qs += q[r];
-        g = 2.0f * diff * invB;
+        if (a.loss_kind == 0) {                       // mse_loss
+          ls += diff * diff;
+          g = 2.0f * diff * invB;
+        } else {                                      // smooth_l1_loss, beta = 1 (TD3, :189-197)
+          const float ad = fabsf(diff);
+          ls += ad < 1.0f ? 0.5f * diff * diff : ad - 0.5f;
+          g = (ad < 1.0f ? diff : (diff > 0.f ? 1.0f : -1.0f)) * invB;
+        }
+        if (a.q_other != nullptr) {                   // TD3 critic 2: max of both TD errors, mean of both Q
+          const float qo = a.q_other[row];
+          ts += fmaxf(fabsf(q[r] - y), fabsf(qo - y));
+          qs += 0.5f * (q[r] + qo);
+        } else {
+          ts += fabsf(y - q[r]);
+          qs += q[r];
+        }
         a.dzh_out[row] = g;
-        if (a.y_out) a.y_out[row] = y;
+        if (a.y_out && a.y_in == nullptr) a.y_out[row] = y;
         if (a.q_out) a.q_out[row] = q[r];
       }
       dzh[r] = g;

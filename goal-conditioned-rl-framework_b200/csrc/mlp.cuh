@@ -87,6 +87,12 @@ struct FusedNet {               // hidden layers 0..L-1 and the output head of o
 };
 struct FusedCriticArgs {
   FusedNet ta, tc, c;           // target actor, target critic, critic
+  FusedNet tc2; int has_tc2;    // TD3: second target critic (y uses the minimum)
+  const float *noise;           // TD3: [B, A] standard-normal draws of the target-policy smoothing, or nullptr
+  float policy_noise, noise_clamp;
+  int loss_kind;                // 0 mse, 1 smooth-l1 (beta 1)
+  const float *y_in;            // non-null: the Bellman target is given (TD3 critic 2); the target nets are skipped
+  const float *q_other;         // non-null: metrics use max(|q-y|, |q_other-y|) and (q + q_other) / 2
   const float *s, *a, *r, *ns, *d;   // dense batch
   int B, D, A, H, L, ldh, ldc;
   float gamma, y_lo; int clamp_y;
