@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--transitions", type=int, default=1_000_000, help="stored raw transitions per GPU")
     ap.add_argument("--no-sweep", action="store_true", help="skip the batch sweep / kernel rooflines")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-big-buffer", action="store_true", help="skip the 10M-transition sampler point")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--spinup", type=int, default=80, help="extra untimed steps before the W warm-up steps")
     return ap.parse_args()
@@ -422,6 +423,42 @@ def gpu_main(args):
                 "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                 "traffic": None, "ms_per_launch": ms_k, "algorithmic_bytes_per_transition": alg_bytes,
                 "transitions_per_s": batch / (ms_k * 1e-3)}
+    # BASELINE configs[4]: the sampler on a 10x larger buffer (10M stored transitions = 49.2M deque entries,
+    # 2.2 GB of packed rows, far beyond the 126 MB L2): the same 20 000 synthetic episodes committed 10 times
+    if rank == 0 and sweep_batches and not args.no_big_buffer:
+        try:
+            from gcrl_b200 import HERBuffer
+            big = HERBuffer(10 * max_len, 50, 1, k_future=k, index_source="device", seed=7, device=local)
+            t0 = time.time()
+            for rep in range(10):
+                for e in range(E):
+                    big.push_episode(data["s"][e], data["a"][e], data["ns"][e], data["r"][e], data["d"][e],
+                                     data["ag"][e], data["fut"][e])
+            torch.cuda.synchronize()
+            log(f"[big buffer] {len(big)} entries committed in {time.time() - t0:.1f}s")
+            for batch in (256, 65536):
+                outs = [torch.empty((batch, w), dtype=torch.float32, device=dev) for w in (D, A, 1, D, 1)]
+                ptrs = [vp(o.data_ptr()) for o in outs]
+                for _ in range(5):
+                    check(lib.gcrl_her_sample(big.handle, batch, None, *ptrs, None, sp))
+                evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(50)]
+                for i, (a0, a1) in enumerate(evs):
+                    flush.fill_(i & 0xFF)
+                    a0.record(stream)
+                    check(lib.gcrl_her_sample(big.handle, batch, None, *ptrs, None, sp))
+                    a1.record(stream)
+                torch.cuda.synchronize()
+                ms_k = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+                ach = batch * alg_bytes / (ms_k * 1e-3) / 1e9
+                rooflines[f"her_sample_kernel_B{batch}_buffer10M"] = {
+                    "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                    "traffic": None, "ms_per_launch": ms_k, "algorithmic_bytes_per_transition": alg_bytes,
+                    "transitions_per_s": batch / (ms_k * 1e-3), "buffer_transitions": 10 * args.transitions}
+            del big, outs
+            torch.cuda.empty_cache()
+        except Exception as e:   # noqa: BLE001
+            log(f"[big buffer] skipped: {e}")
+
     # the dominant kernel of the step at the headline batch: the critic-phase row-slab kernel
     # (fp32 FFMA by design below 2048 rows; tensor cores take the hidden layers above that)
     Hh, Ll = args.hidden, args.layers
@@ -436,9 +473,12 @@ def gpu_main(args):
             # gradients through the (L - 1) hidden layers
             fl = 2.0 * B * (amac + 2 * cmac + (Ll - 1) * Hh * Hh + Hh)
             ach = fl / (msk.value * 1e-3) / 1e12
+            # DRAM bytes per launch from the one `ncu --set full` capture of this kernel at the bench shape
+            # (profiles/r01b_ncu_full_fused_B256_raw.csv: dram__bytes_read.sum 3.89 MB + write 0.51 MB)
+            traffic = 4.40e6 if (B, Hh, Ll, D, A) == (256, 256, 3, 21, 3) else None
             rooflines[f"fused_critic_kernel_B{B}"] = {
                 "bound": "tensor", "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
-                "traffic": None, "ms_per_launch": msk.value, "algorithmic_flops_per_launch": fl,
+                "traffic": traffic, "ms_per_launch": msk.value, "algorithmic_flops_per_launch": fl,
                 "note": "fp32 FFMA row-slab kernel (weights streamed from L2 once per 4-row slab); latency-bound "
                         "at this batch -- the tensor-core path serves batches >= 2048"}
         except Exception as e:   # noqa: BLE001
@@ -469,7 +509,8 @@ def gpu_main(args):
                     ach = fl / (ms_k * 1e-3) / 1e12
                     rooflines[f"{name}_M{Mt}_H{Hh}"] = {
                         "bound": "tensor", "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
-                        "traffic": None, "ms_per_launch": ms_k, "algorithmic_flops_per_launch": fl,
+                        "traffic": (83.8e6 if (engine == 1 and Hh == 256) else None),   # ncu: 67.4 MB read + 16.4 MB written
+                        "ms_per_launch": ms_k, "algorithmic_flops_per_launch": fl,
                         "note": ("tcgen05 kind::tf32, 3 MMAs per product (hi/lo split) for fp32 accuracy: tensor-pipe "
                                  "work is 3x the algorithmic flops" if engine == 1 else
                                  "fp32 FFMA tiles (the precision-0 path), for comparison")}
