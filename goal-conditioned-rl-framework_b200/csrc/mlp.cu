@@ -543,7 +543,17 @@ int launch_head_bwd(const HeadBwdArgs &a, int max_splits, cudaStream_t st) {
 __global__ void __launch_bounds__(256)
 action_grad_kernel(const float *__restrict__ dZ1, int lddz, const float *__restrict__ W1, int ldw,
                    const float *__restrict__ sa, int ldsa, int col0, float *__restrict__ dz_out, int M, int N,
-                   int nact) {
+                   int nact, int staged) {
+  // the [N][4] action-column block of W1 is staged once per CTA (a strided gather otherwise: every lane
+  // would touch a different row of W1 for every element of dZ1); very wide layers read it in place
+  extern __shared__ float4 w_s[];
+  if (staged) {
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      const float *w = W1 + size_t(n) * ldw + col0;
+      w_s[n] = make_float4(w[0], nact > 1 ? w[1] : 0.f, nact > 2 ? w[2] : 0.f, nact > 3 ? w[3] : 0.f);
+    }
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -551,10 +561,17 @@ action_grad_kernel(const float *__restrict__ dZ1, int lddz, const float *__restr
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int n = lane; n < N; n += 32) {
       const float g = dZ1[size_t(m) * lddz + n];
-      const float *w = W1 + size_t(n) * ldw + col0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (j < nact) acc[j] = fmaf(g, w[j], acc[j]);
+      float4 w;
+      if (staged) {
+        w = w_s[n];
+      } else {
+        const float *wp = W1 + size_t(n) * ldw + col0;
+        w = make_float4(wp[0], nact > 1 ? wp[1] : 0.f, nact > 2 ? wp[2] : 0.f, nact > 3 ? wp[3] : 0.f);
+      }
+      acc[0] = fmaf(g, w.x, acc[0]);
+      acc[1] = fmaf(g, w.y, acc[1]);
+      acc[2] = fmaf(g, w.z, acc[2]);
+      acc[3] = fmaf(g, w.w, acc[3]);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
@@ -576,7 +593,9 @@ void launch_action_grad(const float *dZ1, int lddz, const float *W1, int ldw, co
                         int col0, float *dz_out, int M, int N, int nact, cudaStream_t st) {
   GCRL_REQUIRE(nact >= 1 && nact <= 4, "act_dim must be 1..4");
   const int blocks = std::max(1, std::min((M + 7) / 8, sm_count() * 8));
-  action_grad_kernel<<<blocks, 256, 0, st>>>(dZ1, lddz, W1, ldw, sa, ldsa, col0, dz_out, M, N, nact);
+  const int staged = size_t(N) * 16 <= 48 * 1024 ? 1 : 0;
+  action_grad_kernel<<<blocks, 256, staged ? size_t(N) * 16 : 0, st>>>(dZ1, lddz, W1, ldw, sa, ldsa, col0, dz_out, M,
+                                                                        N, nact, staged);
   GCRL_LAUNCHED();
 }
 
