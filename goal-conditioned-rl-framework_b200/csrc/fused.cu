@@ -183,7 +183,8 @@ size_t fused_smem_bytes(int R, int D, int A, int H, int L, bool two_keeps) {
 // ---------------------------------------------------------------------------------------------
 // critic phase
 // ---------------------------------------------------------------------------------------------
-template <int R>
+// TD3 = false compiles the smoothing noise / second target critic / given-target / smooth-L1 branches out
+template <int R, bool TD3>
 __global__ void __launch_bounds__(kFusedThreads, 1) fused_critic_kernel(FusedCriticArgs a) {
   extern __shared__ float4 fsm4[];
   const int D = a.D, A = a.A, H = a.H, L = a.L, B = a.B;
@@ -219,13 +220,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_critic_kernel(FusedCri
   }
 
   const float *h;
-  if (a.y_in == nullptr) {
+  if (!TD3 || a.y_in == nullptr) {
     // ---- 1. a' = target_actor(s') (:1312); TD3: + clamp(noise * sigma, +-c), clamped to [-1, 1] (:174-179) ----
     h = slab_forward<R>(a.ta, L, H, x_ns, D, nullptr, sp.t0, sp.t1, sp.red, nullptr, 0, row0, B);
     slab_head<R>(h, H, a.ta.Wh, a.ta.ldwh, a.ta.bh, A, true, anext);
     for (int e = tid; e < A * R; e += kFusedThreads) {
       float v = anext[e];
-      if (a.noise != nullptr) {
+      if (TD3 && a.noise != nullptr) {
         const int j = e / R, row = row0 + (e - j * R);
         float n = row < B ? a.noise[size_t(row) * A + j] * a.policy_noise : 0.f;
         n = fminf(fmaxf(n, -a.noise_clamp), a.noise_clamp);
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_critic_kernel(FusedCri
     // ---- 2. q' = target_critic([s', a']) (:1313-1315); TD3: min over the two target critics (:181-183) ----
     h = slab_forward<R>(a.tc, L, H, x_ns, D + A, nullptr, sp.t0, sp.t1, sp.red, nullptr, 0, row0, B);
     slab_head<R>(h, H, a.tc.Wh, a.tc.ldwh, a.tc.bh, 1, false, qn);
-    if (a.has_tc2) {
+    if (TD3 && a.has_tc2) {
       float *qn2 = anext;          // a' already sits in x_ns
       h = slab_forward<R>(a.tc2, L, H, x_ns, D + A, nullptr, sp.t0, sp.t1, sp.red, nullptr, 0, row0, B);
       slab_head<R>(h, H, a.tc2.Wh, a.tc2.ldwh, a.tc2.bh, 1, false, qn2);
@@ -257,14 +258,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_critic_kernel(FusedCri
       float g = 0.f;
       if (row < B) {
         float y;
-        if (a.y_in != nullptr) {
+        if (TD3 && a.y_in != nullptr) {
           y = a.y_in[row];
         } else {
           y = rr[r] + a.gamma * (1.0f - dd[r]) * qn[r];
           if (a.clamp_y) y = fminf(fmaxf(y, a.y_lo), 0.0f);
         }
         const float diff = q[r] - y;
-        if (a.loss_kind == 0) {                       // mse_loss
+        if (!TD3 || a.loss_kind == 0) {               // mse_loss
           ls += diff * diff;
           g = 2.0f * diff * invB;
         } else {                                      // smooth_l1_loss, beta = 1 (TD3, :189-197)
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_critic_kernel(FusedCri
           ls += ad < 1.0f ? 0.5f * diff * diff : ad - 0.5f;
           g = (ad < 1.0f ? diff : (diff > 0.f ? 1.0f : -1.0f)) * invB;
         }
-        if (a.q_other != nullptr) {                   // TD3 critic 2: max of both TD errors, mean of both Q
+        if (TD3 && a.q_other != nullptr) {            // TD3 critic 2: max of both TD errors, mean of both Q
           const float qo = a.q_other[row];
           ts += fmaxf(fabsf(q[r] - y), fabsf(qo - y));
           qs += 0.5f * (q[r] + qo);
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_critic_kernel(FusedCri
           qs += q[r];
         }
         a.dzh_out[row] = g;
-        if (a.y_out && a.y_in == nullptr) a.y_out[row] = y;
+        if (a.y_out && (!TD3 || a.y_in == nullptr)) a.y_out[row] = y;
         if (a.q_out) a.q_out[row] = q[r];
       }
       dzh[r] = g;
@@ -394,7 +395,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_actor_kernel(FusedActo
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
-static int g_fused_smem_set[2][2] = {{0, 0}, {0, 0}};
+static int g_fused_smem_set[3][2] = {{0, 0}, {0, 0}, {0, 0}};
 
 template <typename K>
 static void ensure_smem(K kernel, size_t bytes, int *flag) {
@@ -420,12 +421,17 @@ int launch_fused_critic(const FusedCriticArgs &a, cudaStream_t st) {
   const int R = fused_rows_per_cta(a.B);
   const int grid = (a.B + R - 1) / R;
   const size_t smem = fused_smem_bytes(R, a.D, a.A, a.H, a.L, false);
+  const bool td3 = a.has_tc2 || a.noise != nullptr || a.y_in != nullptr || a.loss_kind != 0 || a.q_other != nullptr;
+  auto go = [&](auto kernel, int *flag) {
+    ensure_smem(kernel, smem, flag);
+    kernel<<<grid, kFusedThreads, smem, st>>>(a);
+  };
   if (R == 4) {
-    ensure_smem(fused_critic_kernel<4>, smem, &g_fused_smem_set[0][0]);
-    fused_critic_kernel<4><<<grid, kFusedThreads, smem, st>>>(a);
+    if (td3) go(fused_critic_kernel<4, true>, &g_fused_smem_set[2][0]);
+    else go(fused_critic_kernel<4, false>, &g_fused_smem_set[0][0]);
   } else {
-    ensure_smem(fused_critic_kernel<8>, smem, &g_fused_smem_set[0][1]);
-    fused_critic_kernel<8><<<grid, kFusedThreads, smem, st>>>(a);
+    if (td3) go(fused_critic_kernel<8, true>, &g_fused_smem_set[2][1]);
+    else go(fused_critic_kernel<8, false>, &g_fused_smem_set[0][1]);
   }
   GCRL_LAUNCHED();
   return grid;
