@@ -56,6 +56,9 @@ def parse():
     ap.add_argument("--transitions", type=int, default=1_000_000, help="stored raw transitions per GPU")
     ap.add_argument("--no-sweep", action="store_true", help="skip the batch sweep / kernel rooflines")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--dp", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: average gradients over NVLink peer memory inside the captured graph (p2p) or with "
+                         "NCCL all-reduce between the update phases (nccl)")
     ap.add_argument("--no-big-buffer", action="store_true", help="skip the 10M-transition sampler point")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--spinup", type=int, default=80, help="extra untimed steps before the W warm-up steps")
@@ -177,7 +180,9 @@ def workload_config(args, world):
                         f"batch {args.batch} per GPU, hidden {args.hidden} x {args.layers}",
             "batch_per_gpu": args.batch, "global_batch": args.batch * world, "hidden": args.hidden,
             "layers": args.layers, "buffer_transitions_per_gpu": args.transitions,
-            "parallelism": f"dp{world} (episode-sharded buffer, NCCL gradient all-reduce)" if world > 1 else "single GPU",
+            "parallelism": (f"dp{world} (episode-sharded buffer, gradients averaged over NVLink peer memory inside the "
+                            f"captured graph)" if args.dp == "p2p" else
+                            f"dp{world} (episode-sharded buffer, NCCL gradient all-reduce)") if world > 1 else "single GPU",
             "index_stream": "on-device (value) / host Mersenne-Twister random.sample (e2e)",
             "engines": "batch <= 1024: row-slab fused fp32 kernels; >= 2048: tcgen05 3xTF32 hidden layers (sweep)",
             "l2": "flushed between timed steps (256 MiB write); buffer (224 MB) larger than L2"}
@@ -287,7 +292,10 @@ def gpu_main(args):
     torch.cuda.synchronize()
     log(f"[rank {rank}] {E} episodes / {len(agent.buffer)} entries committed in {time.time() - t0:.1f}s")
     if world > 1:
-        agent.enable_data_parallel()
+        if args.dp == "p2p":
+            agent.enable_peer_data_parallel()
+        else:
+            agent.enable_data_parallel()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
     sp = vp(stream.cuda_stream)

@@ -140,6 +140,19 @@ struct gcrl_agent {
   float *dzh = nullptr;                    // fused path: critic head dL/dq [maxB]
   bool use_fused = true, use_cluster = false;
   int dp_B = -1, dp_flags = -1;            // the update the data-parallel phases belong to
+  // data-parallel averaging over NVLink peer memory (gcrl_agent_dp_connect)
+  struct P2P {
+    bool on = false;
+    int rank = 0, world = 1;
+    unsigned int *flags = nullptr, *epoch = nullptr;     // [8] arrival counters written by the peers; my barrier count
+    int *err = nullptr;
+    float *outbox = nullptr, *metrics_avg = nullptr;     // [8] metrics published to / averaged over the ranks
+    float *gavg[NUM_NETS] = {};                          // averaged gradient of every trainable network
+    unsigned int **d_peer_flags = nullptr;               // device arrays of `world` peer pointers
+    float **d_peer_outbox = nullptr;
+    float **d_peer_g[NUM_NETS] = {};
+    std::vector<void *> opened;                          // cudaIpcOpenMemHandle results
+  } p2p;
   bool use_graphs = true;
   cudaStream_t cap_stream = nullptr;       // capture-only stream (the caller's may be the legacy one)
   struct GraphRec { cudaGraphExec_t exec; uint64_t kernels; };
@@ -235,9 +248,9 @@ void reduce_grads(gcrl_agent *ag, Net &n, const int *splits, int head_splits, bo
 
 // global-norm clip + Adam(W) (+ fused Polyak of `target` with the stepped parameters)
 void adam_step(gcrl_agent *ag, Net &n, int which, float max_norm, int slot_norm, Net *target, bool polyak,
-               cudaStream_t st) {
+               cudaStream_t st, const float *grad = nullptr) {
   AdamArgs a{};
-  a.p = n.p; a.m = n.m; a.v = n.v; a.g = n.g; a.n = n.total;
+  a.p = n.p; a.m = n.m; a.v = n.v; a.g = grad ? grad : n.g; a.n = n.total;
   a.sumsq_partials = ag->sumsq; a.nsumsq = reduce_grid(n.total);
   a.max_norm = max_norm;
   a.weight_decay = ag->cfg.weight_decay;
@@ -428,14 +441,27 @@ void critic2_phase_grads(gcrl_agent *ag, int B, cudaStream_t st) {   // TD3 only
 
 // clip + Adam (+ Polyak) of critic `which`; rereduce: gradients were replaced by the cross-rank
 // average, so the sums of squares are recomputed first.
+// p2p mode: barrier (every rank's local gradient of `net` is complete), then average the peers' buffers
+// into p2p.gavg[net] (+ the sums of squares the clip needs).  The next barrier in stream order also
+// guarantees that every rank finished reading before anybody overwrites its local gradient again.
+const float *p2p_average(gcrl_agent *ag, int net, cudaStream_t st) {
+  auto &pp = ag->p2p;
+  launch_p2p_barrier(pp.d_peer_flags, pp.epoch, pp.rank, pp.world, pp.err, st);
+  launch_p2p_reduce(pp.d_peer_g[net], pp.world, pp.gavg[net], ag->net[net].total, ag->sumsq, st);
+  return pp.gavg[net];
+}
+
 void critic_phase_step(gcrl_agent *ag, int which, int flags, bool rereduce, cudaStream_t st) {
   const bool polyak = ag->td3 ? true : ((flags & 2) != 0);
-  Net &c = ag->net[which == 0 ? CRITIC1 : CRITIC2];
-  if (rereduce) reduce_grads(ag, c, nullptr, 0, true, -1, -1, -1, 0, 1, st);
+  const int id = which == 0 ? CRITIC1 : CRITIC2;
+  Net &c = ag->net[id];
+  const float *grad = nullptr;
+  if (ag->p2p.on) grad = p2p_average(ag, id, st);
+  else if (rereduce) reduce_grads(ag, c, nullptr, 0, true, -1, -1, -1, 0, 1, st);
   // TD3 critic 1 is NOT clipped (:201 is commented out), critic 2 is
   const float clip = (ag->td3 && which == 0) ? -1.0f : ag->cfg.grad_clip;
   adam_step(ag, c, 0, clip, which == 0 ? S_CGRAD : S_C2GRAD, &ag->net[which == 0 ? T_CRITIC1 : T_CRITIC2],
-            polyak, st);
+            polyak, st, grad);
 }
 
 // DDPG: the actor target blends the PRE-step actor, before the actor step (:1397-1401)
@@ -489,8 +515,10 @@ void actor_phase_grads(gcrl_agent *ag, int B, cudaStream_t st) {
 
 void actor_phase_step(gcrl_agent *ag, bool rereduce, cudaStream_t st) {
   Net &a = ag->net[ACTOR];
-  if (rereduce) reduce_grads(ag, a, nullptr, 0, true, -1, -1, -1, 0, 1, st);
-  adam_step(ag, a, 1, ag->cfg.grad_clip, S_AGRAD, &ag->net[T_ACTOR], ag->td3, st);
+  const float *grad = nullptr;
+  if (ag->p2p.on) grad = p2p_average(ag, ACTOR, st);
+  else if (rereduce) reduce_grads(ag, a, nullptr, 0, true, -1, -1, -1, 0, 1, st);
+  adam_step(ag, a, 1, ag->cfg.grad_clip, S_AGRAD, &ag->net[T_ACTOR], ag->td3, st, grad);
 }
 
 void write_scalars(gcrl_agent *ag, double lr_c, double lr_a, bool actor_steps, cudaStream_t st) {
@@ -534,6 +562,12 @@ void run_update_body(gcrl_agent *ag, int B, const float *noise, int flags, int m
   }
   if ((mask & PH_AGRAD) && (flags & 1)) actor_phase_grads(ag, B, st);
   if ((mask & PH_ASTEP) && (flags & 1)) actor_phase_step(ag, dp, st);
+  if (ag->p2p.on && mask == PH_ALL) {          // batch-mean metrics averaged over the ranks (losses, td, q)
+    auto &pp = ag->p2p;
+    launch_copy8(ag->metrics, pp.outbox, st);
+    launch_p2p_barrier(pp.d_peer_flags, pp.epoch, pp.rank, pp.world, pp.err, st);
+    launch_p2p_metrics(pp.d_peer_outbox, pp.world, pp.metrics_avg, st);
+  }
 }
 
 // Replay (or capture on first use) the graph of (B, flags, phase mask).  TD3 noise pointers vary
@@ -627,8 +661,14 @@ void ensure_io(gcrl_agent *ag, size_t floats, cudaStream_t st) {
 
 void finish_metrics(gcrl_agent *ag, float *metrics_host, cudaStream_t st) {
   if (metrics_host == nullptr) return;
-  GCRL_CUDA(cudaMemcpyAsync(metrics_host, ag->metrics, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  GCRL_CUDA(cudaMemcpyAsync(metrics_host, ag->p2p.on ? ag->p2p.metrics_avg : ag->metrics, 8 * sizeof(float),
+                            cudaMemcpyDeviceToHost, st));
   GCRL_CUDA(cudaStreamSynchronize(st));
+  if (ag->p2p.on) {
+    int err = 0;
+    GCRL_CUDA(cudaMemcpy(&err, ag->p2p.err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) throw Error(GCRL_ERR_CUDA, "data-parallel barrier timed out: a peer rank stopped responding");
+  }
 }
 
 }  // namespace
@@ -717,6 +757,14 @@ int gcrl_agent_destroy(gcrl_agent *ag) {
   cudaSetDevice(ag->device);
   cudaDeviceSynchronize();
   for (auto &kv : ag->graphs) cudaGraphExecDestroy(kv.second.exec);
+  for (void *p : ag->p2p.opened) cudaIpcCloseMemHandle(p);
+  for (void *p : {(void *)ag->p2p.flags, (void *)ag->p2p.epoch, (void *)ag->p2p.err, (void *)ag->p2p.outbox,
+                  (void *)ag->p2p.metrics_avg, (void *)ag->p2p.d_peer_flags, (void *)ag->p2p.d_peer_outbox})
+    if (p) cudaFree(p);
+  for (int i = 0; i < NUM_NETS; ++i) {
+    if (ag->p2p.gavg[i]) cudaFree(ag->p2p.gavg[i]);
+    if (ag->p2p.d_peer_g[i]) cudaFree(ag->p2p.d_peer_g[i]);
+  }
   for (int i = 0; i < NUM_NETS; ++i)
     if (ag->has[i]) ag->net[i].destroy();
   ag->acts_actor.destroy(); ag->acts_c1.destroy(); ag->acts_c2.destroy(); ag->acts_tgt.destroy();
@@ -994,6 +1042,89 @@ int gcrl_agent_time_critic_kernel(gcrl_agent *ag, int64_t B, int iters, float *m
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   *ms_per_launch = ms / float(iters);
+  GCRL_API_END
+}
+
+// ---- data-parallel averaging over NVLink peer memory ---------------------------------------------------
+// Buffers a rank shares with its peers, in this order: flags, metrics outbox, then the flat gradient of every
+// trainable network (actor, critic, critic_2 for TD3).
+static int dp_items(gcrl_agent *ag, void **ptrs) {
+  int n = 0;
+  ptrs[n++] = ag->p2p.flags;
+  ptrs[n++] = ag->p2p.outbox;
+  for (int id : {int(ACTOR), int(CRITIC1), int(CRITIC2)})
+    if (ag->has[id]) ptrs[n++] = ag->net[id].g;
+  return n;
+}
+
+int gcrl_agent_dp_export(gcrl_agent *ag, unsigned char *handles /*[n_items][64]*/, int *n_items) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(ag != nullptr && n_items != nullptr, "NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  GCRL_CUDA(cudaSetDevice(ag->device));
+  auto &pp = ag->p2p;
+  if (pp.flags == nullptr) {
+    pp.flags = dev_alloc<unsigned int>(8);
+    pp.epoch = dev_alloc<unsigned int>(1);
+    pp.err = dev_alloc<int>(1);
+    pp.outbox = dev_alloc<float>(8);
+    pp.metrics_avg = dev_alloc<float>(8);
+    GCRL_CUDA(cudaMemset(pp.flags, 0, 8 * sizeof(unsigned int)));
+    GCRL_CUDA(cudaMemset(pp.epoch, 0, sizeof(unsigned int)));
+    GCRL_CUDA(cudaMemset(pp.err, 0, sizeof(int)));
+    GCRL_CUDA(cudaMemset(pp.outbox, 0, 8 * sizeof(float)));
+    GCRL_CUDA(cudaMemset(pp.metrics_avg, 0, 8 * sizeof(float)));
+    GCRL_CUDA(cudaDeviceSynchronize());
+  }
+  void *ptrs[8];
+  const int n = dp_items(ag, ptrs);
+  *n_items = n;
+  if (handles != nullptr)
+    for (int i = 0; i < n; ++i)
+      GCRL_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(handles + size_t(i) * 64), ptrs[i]));
+  GCRL_API_END
+}
+
+int gcrl_agent_dp_connect(gcrl_agent *ag, int rank, int world, const unsigned char *all_handles /*[world][n_items][64]*/) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(ag != nullptr && all_handles != nullptr, "NULL argument");
+  GCRL_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "need 1 <= world <= 8 and 0 <= rank < world");
+  GCRL_REQUIRE(ag->p2p.flags != nullptr, "call gcrl_agent_dp_export first");
+  GCRL_CUDA(cudaSetDevice(ag->device));
+  auto &pp = ag->p2p;
+  void *mine[8];
+  const int n = dp_items(ag, mine);
+  std::vector<std::vector<void *>> peer(static_cast<size_t>(world), std::vector<void *>(static_cast<size_t>(n), nullptr));
+  for (int r = 0; r < world; ++r)
+    for (int i = 0; i < n; ++i) {
+      if (r == rank) { peer[r][i] = mine[i]; continue; }
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, all_handles + (size_t(r) * n + i) * 64, 64);
+      void *p = nullptr;
+      GCRL_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      pp.opened.push_back(p);
+      peer[r][i] = p;
+    }
+  auto upload = [&](int item) {
+    std::vector<void *> v(static_cast<size_t>(world), nullptr);
+    for (int r = 0; r < world; ++r) v[size_t(r)] = peer[size_t(r)][size_t(item)];
+    void **d = dev_alloc<void *>(size_t(world));
+    GCRL_CUDA(cudaMemcpy(d, v.data(), size_t(world) * sizeof(void *), cudaMemcpyHostToDevice));
+    return d;
+  };
+  pp.d_peer_flags = reinterpret_cast<unsigned int **>(upload(0));
+  pp.d_peer_outbox = reinterpret_cast<float **>(upload(1));
+  int item = 2;
+  for (int id : {int(ACTOR), int(CRITIC1), int(CRITIC2)})
+    if (ag->has[id]) {
+      pp.d_peer_g[id] = reinterpret_cast<float **>(upload(item++));
+      pp.gavg[id] = dev_alloc<float>(size_t(ag->net[id].total));
+      GCRL_CUDA(cudaMemset(pp.gavg[id], 0, size_t(ag->net[id].total) * 4));
+    }
+  pp.rank = rank; pp.world = world; pp.on = true;
+  for (auto &kv : ag->graphs) cudaGraphExecDestroy(kv.second.exec);      // graphs captured without the averaging
+  ag->graphs.clear();
+  GCRL_CUDA(cudaDeviceSynchronize());
   GCRL_API_END
 }
 

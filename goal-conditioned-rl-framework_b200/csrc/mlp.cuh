@@ -170,6 +170,13 @@ struct AdamArgs {
   float *pT, *targetT;
 };
 void launch_adam(const AdamArgs &a, cudaStream_t st);
+// data-parallel averaging over NVLink peer memory (optim.cu)
+void launch_p2p_barrier(unsigned int *const *peer_flags, unsigned int *epoch, int rank, int world, int *err,
+                        cudaStream_t st);
+void launch_p2p_reduce(const float *const *peers, int world, float *out, int n, float *sumsq_partials,
+                       cudaStream_t st);
+void launch_copy8(const float *src, float *dst, cudaStream_t st);
+void launch_p2p_metrics(const float *const *peer_outbox, int world, float *avg, cudaStream_t st);
 void launch_polyak(float *target, const float *src, int n, float tau, float one_minus_tau,
                    const int *tmap, float *targetT, cudaStream_t st);
 // pT[tmap[e]] = p[e] for every weight element

@@ -91,6 +91,8 @@ SIGNATURES = {
     "gcrl_agent_q": (C.c_int, [vp, c_i64, vp, vp, vp, vp]),
     "gcrl_agent_update_phase": (C.c_int, [vp, C.c_int, vp, c_i64, vp, vp, vp, vp, vp, vp, vp, c_f64, c_f64,
                                          C.c_int, vp]),
+    "gcrl_agent_dp_export": (C.c_int, [vp, vp, C.POINTER(C.c_int)]),
+    "gcrl_agent_dp_connect": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "gcrl_agent_grad_buffer": (C.c_int, [vp, C.c_int, pp, C.POINTER(c_i64)]),
     "gcrl_agent_metrics_buffer": (C.c_int, [vp, pp]),
     # SAC / TQC

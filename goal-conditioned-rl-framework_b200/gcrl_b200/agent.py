@@ -263,6 +263,27 @@ class _AgentBase:
     # -- data parallel (one process per GPU) -------------------------------------
     _dp = None
 
+    def enable_peer_data_parallel(self, process_group=None):
+        """Data parallelism without a collective library on the critical path: the ranks exchange CUDA-IPC
+        handles of their flat gradient buffers once (through ``torch.distributed.all_gather_object``), and from
+        then on every ``update()`` averages the critic / actor gradients and the batch-mean metrics over NVLink
+        peer memory inside the one captured CUDA graph (flag barrier + every rank summing all ranks' buffers in
+        rank order).  Same contract as ``enable_data_parallel``: every rank owns its episode shard, samples its
+        local batch, and all ranks issue the same sequence of updates; replicas stay bit-identical."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(process_group), dist.get_world_size(process_group)
+        n = C.c_int()
+        check(lib.gcrl_agent_dp_export(self._h, None, C.byref(n)))
+        buf = (C.c_ubyte * (64 * n.value))()
+        check(lib.gcrl_agent_dp_export(self._h, C.cast(buf, vp), C.byref(n)))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, bytes(buf), group=process_group)
+        blob = b"".join(gathered)
+        check(lib.gcrl_agent_dp_connect(self._h, rank, world, C.cast(C.c_char_p(blob), vp)))
+        dist.barrier(group=process_group)
+        self._dp = None
+        self._peer_dp = (rank, world)
+
     def enable_data_parallel(self, process_group=None, allreduce_mean=None):
         """Average gradients over the ranks of ``process_group`` (torch.distributed, NCCL over
         NVLink) between the backward and the optimiser phases of every update.  Each rank keeps

@@ -238,6 +238,16 @@ int gcrl_agent_update_phase(gcrl_agent *h, int phase, gcrl_her *buf, int64_t B,
                             const float *r_dev, const float *ns_dev, const float *d_dev,
                             const float *noise_dev, double lr_critic, double lr_actor, int flags,
                             void *stream);
+/* Data-parallel averaging over NVLink peer memory instead of a collective library: every rank exports
+ * CUDA-IPC handles of its flag array, metrics outbox and flat gradient buffers (gcrl_agent_dp_export:
+ * handles may be NULL to query n_items; 64 bytes each), the caller all-gathers them (any transport), and
+ * gcrl_agent_dp_connect maps the peers' buffers.  From then on gcrl_agent_update_batch / _from_buffer
+ * average the critic and actor gradients (and the batch-mean metrics) across the ranks inside the one
+ * captured graph: flag barrier over peer memory, every rank sums all ranks' buffers in rank order
+ * (bit-identical replicas), clip + Adam on the average.  All ranks must issue the same sequence of updates
+ * (same batch size and flags).  world <= 8 (one NVSwitch domain). */
+int gcrl_agent_dp_export(gcrl_agent *h, unsigned char *handles, int *n_items);
+int gcrl_agent_dp_connect(gcrl_agent *h, int rank, int world, const unsigned char *all_handles);
 /* flat fp32 gradient of a trainable network: device pointer + element count (for NCCL) */
 int gcrl_agent_grad_buffer(gcrl_agent *h, int net, float **grad_dev, int64_t *count);
 /* device float[8] holding the metrics of the most recent update (averaged across ranks by the

@@ -42,10 +42,64 @@ def main():
                                     single.actor.layers() + single.critic.layers() + single.target_critic.layers()):
             assert weights_close(w, ws, 1e-3, 4) and weights_close(b, bs, 1e-3, 4)
     tqc_section(rank, world, local)
+    p2p_section(rank, world, local)
     if rank == 0:
         print("DP_OK", flush=True)
     dist.barrier()
     dist.destroy_process_group()
+
+
+def p2p_section(rank, world, local):
+    """The same parity rule with the gradients averaged over NVLink peer memory (enable_peer_data_parallel):
+    N ranks on per-rank batches == one rank on the concatenated batch within the fp32 tolerance, replicas
+    bit-identical, for DDPG and TD3."""
+    from gcrl_b200 import TD3Agent
+    from gcrl_b200.agent import NET_ACTOR, NET_CRITIC, NET_CRITIC2
+    from oracle import ddpg as OD
+    from tests.test_ddpg_gpu import make_config
+    D, A, H, L, B = 21, 3, 256, 3, 256
+    dev = torch.device("cuda", local)
+    for algo in ("ddpg", "td3"):
+        def build(batch):
+            if algo == "ddpg":
+                return make_agent_on(local, D, A, H, L, batch)
+            ag = TD3Agent(D, A, make_config(hidden_dim=H, layer_count=L, batch_size=batch, grad_clip=0.5, ac_update_freq=2),
+                          None, 1, 40, device=local)
+            r = np.random.default_rng(3)
+            ag._set_layers(NET_ACTOR, OD.init_mlp(r, D, H, A, L))
+            ag._set_layers(NET_CRITIC, OD.init_mlp(r, D + A, H, 1, L))
+            ag._set_layers(NET_CRITIC2, OD.init_mlp(r, D + A, H, 1, L))
+            ag.update_target_network()
+            return ag
+        ag = build(B)
+        ag.enable_peer_data_parallel()
+        single = build(world * B) if rank == 0 else None
+        rng = np.random.default_rng(9)
+        for step in (39, 40, 41, 42):
+            batches = [rand_batch_on(rng, B, D, A, local) for _ in range(world)]
+            noises = [torch.from_numpy(rng.standard_normal((B, A)).astype(np.float32)).to(dev) for _ in range(world)]
+            kw = {"noise": noises[rank]} if algo == "td3" else {}
+            info = ag.update(step, batch=batches[rank], **kw)
+            if rank == 0:
+                kw1 = {"noise": torch.cat(noises)} if algo == "td3" else {}
+                want = single.update(step, batch=tuple(torch.cat(parts) for parts in zip(*batches)), **kw1)
+                np.testing.assert_allclose(np.array([float(x) for x in info]), np.array([float(x) for x in want]),
+                                           rtol=5e-5, atol=2e-6)
+        nets = [ag.actor, ag.target_actor] + ([ag.critic, ag.target_critic] if algo == "ddpg" else
+                                              [ag.critic_1, ag.critic_2, ag.target_critic_1, ag.target_critic_2])
+        flat = torch.cat([torch.from_numpy(w).reshape(-1) for n in nets for w, _ in n.layers()]).to(dev)
+        gathered = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        for g in gathered[1:]:
+            assert torch.equal(g, gathered[0]), f"{algo}: peer-averaged replicas diverged"
+        if rank == 0:
+            snets = [single.actor] + ([single.critic] if algo == "ddpg" else [single.critic_1, single.critic_2])
+            pnets = [ag.actor] + ([ag.critic] if algo == "ddpg" else [ag.critic_1, ag.critic_2])
+            for pn, sn in zip(pnets, snets):
+                for (w, b), (ws, bs) in zip(pn.layers(), sn.layers()):
+                    assert weights_close(w, ws, 1e-3, 4) and weights_close(b, bs, 1e-3, 4), algo
+        dist.barrier()
+        del ag
 
 
 def tqc_section(rank, world, local):
