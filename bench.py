@@ -293,7 +293,14 @@ def gpu_main(args):
     log(f"[rank {rank}] {E} episodes / {len(agent.buffer)} entries committed in {time.time() - t0:.1f}s")
     if world > 1:
         if args.dp == "p2p":
-            agent.enable_peer_data_parallel()
+            try:
+                agent.enable_peer_data_parallel()
+            except Exception as e:   # noqa: BLE001  (every rank raises together, see enable_peer_data_parallel)
+                log(f"[rank {rank}] peer-memory averaging unavailable ({e}); falling back to NCCL all-reduce")
+                agent2 = make_agent("device", max(B, max(sweep_batches + [B])))   # fresh handle without the mapping
+                agent = agent2
+                args.dp = "nccl"
+                agent.enable_data_parallel()
         else:
             agent.enable_data_parallel()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

@@ -279,7 +279,17 @@ class _AgentBase:
         gathered = [None] * world
         dist.all_gather_object(gathered, bytes(buf), group=process_group)
         blob = b"".join(gathered)
-        check(lib.gcrl_agent_dp_connect(self._h, rank, world, C.cast(C.c_char_p(blob), vp)))
+        err = None
+        try:
+            check(lib.gcrl_agent_dp_connect(self._h, rank, world, C.cast(C.c_char_p(blob), vp)))
+        except Exception as e:   # noqa: BLE001  (e.g. CUDA IPC not permitted in this container)
+            err = e
+        oks = [None] * world                    # all ranks take the same path
+        dist.all_gather_object(oks, err is None, group=process_group)
+        if not all(oks):
+            if err is None:
+                raise RuntimeError("a peer rank could not map the gradient buffers (CUDA IPC)")
+            raise err
         dist.barrier(group=process_group)
         self._dp = None
         self._peer_dp = (rank, world)
