@@ -564,9 +564,8 @@ void run_update_body(gcrl_agent *ag, int B, const float *noise, int flags, int m
   if ((mask & PH_ASTEP) && (flags & 1)) actor_phase_step(ag, dp, st);
   if (ag->p2p.on && mask == PH_ALL) {          // batch-mean metrics averaged over the ranks (losses, td, q)
     auto &pp = ag->p2p;
-    launch_copy8(ag->metrics, pp.outbox, st);
-    launch_p2p_barrier(pp.d_peer_flags, pp.epoch, pp.rank, pp.world, pp.err, st);
-    launch_p2p_metrics(pp.d_peer_outbox, pp.world, pp.metrics_avg, st);
+    launch_p2p_metrics(pp.d_peer_flags, pp.epoch, pp.rank, pp.world, pp.err, ag->metrics, pp.outbox, pp.d_peer_outbox,
+                       pp.metrics_avg, st);
   }
 }
 

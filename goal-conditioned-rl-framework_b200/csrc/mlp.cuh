@@ -175,8 +175,9 @@ void launch_p2p_barrier(unsigned int *const *peer_flags, unsigned int *epoch, in
                         cudaStream_t st);
 void launch_p2p_reduce(const float *const *peers, int world, float *out, int n, float *sumsq_partials,
                        cudaStream_t st);
-void launch_copy8(const float *src, float *dst, cudaStream_t st);
-void launch_p2p_metrics(const float *const *peer_outbox, int world, float *avg, cudaStream_t st);
+void launch_p2p_metrics(unsigned int *const *peer_flags, unsigned int *epoch, int rank, int world, int *err,
+                        const float *local, float *outbox, const float *const *peer_outbox, float *avg,
+                        cudaStream_t st);
 void launch_polyak(float *target, const float *src, int n, float tau, float one_minus_tau,
                    const int *tmap, float *targetT, cudaStream_t st);
 // pT[tmap[e]] = p[e] for every weight element

@@ -129,23 +129,43 @@ void launch_p2p_reduce(const float *const *peers, int world, float *out, int n, 
   GCRL_LAUNCHED();
 }
 
-// metrics: outbox <- local metrics (before the barrier); avg[j] = mean over ranks of outbox[j] (after it)
-__global__ void copy8_kernel(const float *__restrict__ src, float *__restrict__ dst) {
-  if (threadIdx.x < 8) dst[threadIdx.x] = src[threadIdx.x];
-}
-__global__ void p2p_metrics_kernel(const float *const *peer_outbox, int world, float *__restrict__ avg) {
+// metrics in ONE single-block launch: publish the local 8 floats, flag barrier, average the ranks' copies
+// (losses, td error and q are batch means; the gradient norms are already global)
+__global__ void __launch_bounds__(32)
+p2p_metrics_kernel(unsigned int *const *peer_flags, unsigned int *epoch, int rank, int world, int *err,
+                   const float *__restrict__ local, float *__restrict__ outbox, const float *const *peer_outbox,
+                   float *__restrict__ avg) {
+  __shared__ unsigned int e_s;
+  if (threadIdx.x < 8) outbox[threadIdx.x] = local[threadIdx.x];
+  if (threadIdx.x == 0) e_s = *epoch + 1u;
+  __syncwarp();
+  const unsigned int e = e_s;
+  if (int(threadIdx.x) < world) {
+    __threadfence_system();
+    volatile unsigned int *dst = peer_flags[threadIdx.x] + rank;
+    *dst = e;
+    volatile unsigned int *src = peer_flags[rank] + threadIdx.x;
+    const long long t0 = clock64();
+    while (*src < e) {
+      if (clock64() - t0 > 120000000000ll) {
+        *err = 1;
+        break;
+      }
+    }
+    __threadfence_system();
+  }
+  __syncwarp();
   if (threadIdx.x < 8) {
     float s = 0.f;
     for (int r = 0; r < world; ++r) s += __ldcv(peer_outbox[r] + threadIdx.x);
     avg[threadIdx.x] = s / float(world);
   }
+  if (threadIdx.x == 0) *epoch = e;
 }
-void launch_copy8(const float *src, float *dst, cudaStream_t st) {
-  copy8_kernel<<<1, 32, 0, st>>>(src, dst);
-  GCRL_LAUNCHED();
-}
-void launch_p2p_metrics(const float *const *peer_outbox, int world, float *avg, cudaStream_t st) {
-  p2p_metrics_kernel<<<1, 32, 0, st>>>(peer_outbox, world, avg);
+void launch_p2p_metrics(unsigned int *const *peer_flags, unsigned int *epoch, int rank, int world, int *err,
+                        const float *local, float *outbox, const float *const *peer_outbox, float *avg,
+                        cudaStream_t st) {
+  p2p_metrics_kernel<<<1, 32, 0, st>>>(peer_flags, epoch, rank, world, err, local, outbox, peer_outbox, avg);
   GCRL_LAUNCHED();
 }
 
