@@ -431,8 +431,10 @@ def gpu_main(args):
         return tot
 
     if rank == 0:
-        for batch in [B] + sweep_batches:
-            ms_k = time_sampler(batch, 50)
+        # 1 048 576 is beyond BASELINE's sweep: it shows the sampler's bandwidth once launch + dependent-gather
+        # latency (~16 us) is amortised
+        for batch in [B] + sweep_batches + ([1 << 20] if sweep_batches else []):
+            ms_k = time_sampler(batch, 50 if batch <= 65536 else 20)
             ach = batch * alg_bytes / (ms_k * 1e-3) / 1e9
             rooflines[f"her_sample_kernel_B{batch}"] = {
                 "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
@@ -526,8 +528,10 @@ def gpu_main(args):
                         "bound": "tensor", "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
                         "traffic": (83.8e6 if (engine == 1 and Hh == 256) else None),   # ncu: 67.4 MB read + 16.4 MB written
                         "ms_per_launch": ms_k, "algorithmic_flops_per_launch": fl,
+                        "tensor_pipe_tflops": (3.0 * ach if engine == 1 else None),
+                        "tensor_pipe_frac_of_tf32_rate": (3.0 * ach / (0.5 * bf16_peak) if engine == 1 else None),
                         "note": ("tcgen05 kind::tf32, 3 MMAs per product (hi/lo split) for fp32 accuracy: tensor-pipe "
-                                 "work is 3x the algorithmic flops" if engine == 1 else
+                                 "work is 3x the algorithmic flops; the TF32 rate is half the measured bf16 peak" if engine == 1 else
                                  "fp32 FFMA tiles (the precision-0 path), for comparison")}
                 except Exception as e:   # noqa: BLE001
                     log(f"[roofline] dense layer engine {engine} skipped: {e}")
