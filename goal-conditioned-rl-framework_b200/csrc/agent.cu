@@ -138,6 +138,8 @@ struct gcrl_agent {
   float *noise = nullptr;                  // TD3 smoothing noise copy [maxB, A]
   std::vector<float *> dzl;                // fused path: per-layer pre-activation gradients [maxB, ldh]
   float *dzh = nullptr;                    // fused path: critic head dL/dq [maxB]
+  float *per_w = nullptr, *per_td = nullptr;   // prioritised replay: importance weights in, TD errors out [maxB]
+  bool per_on = false;                     // flags bit3 of the update being issued
   bool use_fused = true, use_cluster = false;
   int dp_B = -1, dp_flags = -1;            // the update the data-parallel phases belong to
   // data-parallel averaging over NVLink peer memory (gcrl_agent_dp_connect)
@@ -277,6 +279,7 @@ void critic_forward_backward(gcrl_agent *ag, int which_critic, int B, int *split
   h.nout = 1;
   h.q = q; h.qt1 = ag->qt1; h.qt2 = ag->td3 ? ag->qt2 : nullptr;
   h.q_other = (ag->td3 && which_critic == 1) ? ag->q1 : nullptr;
+  if (ag->per_on) { h.is_w = ag->per_w; h.td_out = ag->per_td; }
   h.r = ag->br; h.d = ag->bd;
   h.gamma = ag->cfg.gamma;
   h.y_lo = float(-1.0 / (1.0 - double(ag->cfg.gamma)));
@@ -333,7 +336,7 @@ struct PhaseState {
 // ---- row-slab fused path (fused.cu): DDPG, B <= 1024 ---------------------------------------------
 constexpr int kClusterMaxBatch = 2048;
 bool cluster_ok(const gcrl_agent *ag, int B) {
-  return ag->use_fused && ag->use_cluster && !ag->td3 && B <= kClusterMaxBatch &&  // (cluster.cu: DDPG only)
+  return ag->use_fused && ag->use_cluster && !ag->td3 && !ag->per_on && B <= kClusterMaxBatch &&  // (cluster.cu: DDPG only)
          cluster_supported(B, ag->D, ag->A, ag->H, ag->L);
 }
 bool fused_ok(const gcrl_agent *ag, int B) {
@@ -380,6 +383,7 @@ FusedCriticArgs fused_critic_args(gcrl_agent *ag, int B, int which = 0) {
     a.loss_kind = 1;
     if (which == 1) { a.y_in = ag->yv; a.q_other = ag->q1; }     // target and Q1 left by the critic-1 launch
   }
+  if (ag->per_on) { a.is_w = ag->per_w; a.td_out = ag->per_td; }
   a.s = ag->bs; a.a = ag->ba; a.r = ag->br0; a.ns = ag->bns; a.d = ag->bd0;
   a.B = B; a.D = ag->D; a.A = ag->A; a.H = ag->H; a.L = ag->L; a.ldh = ag->ldh; a.ldc = ag->ldc;
   a.gamma = ag->cfg.gamma;
@@ -719,6 +723,8 @@ int gcrl_agent_create(gcrl_agent **out, int device, const gcrl_agent_config *cfg
     ag->noise = dev_alloc<float>(size_t(mb) * 4);
     for (int l = 0; l < L; ++l) ag->dzl.push_back(dev_alloc<float>(size_t(mb) * ag->ldh));
     ag->dzh = dev_alloc<float>(size_t(mb));
+    ag->per_w = dev_alloc<float>(size_t(mb));
+    ag->per_td = dev_alloc<float>(size_t(mb));
     const char *nf = getenv("GCRL_B200_NO_FUSED");
     ag->use_fused = !(nf && nf[0] == '1');
     // cluster.cu (layers split over an 8-CTA cluster through DSMEM) is parity-green but measured slower
@@ -769,7 +775,7 @@ int gcrl_agent_destroy(gcrl_agent *ag) {
   ag->acts_actor.destroy(); ag->acts_c1.destroy(); ag->acts_c2.destroy(); ag->acts_tgt.destroy();
   for (float *p : {ag->dz[0], ag->dz[1], ag->sa, ag->nsa, ag->spi, ag->q1, ag->q2, ag->qt1, ag->qt2, ag->yv,
                    ag->dz_act, ag->br, ag->bd, ag->bs, ag->ba, ag->bns, ag->br0, ag->bd0, ag->partials,
-                   ag->metric_partials, ag->sumsq, ag->metrics, ag->d_io, ag->noise, ag->dzh})
+                   ag->metric_partials, ag->sumsq, ag->metrics, ag->d_io, ag->noise, ag->dzh, ag->per_w, ag->per_td})
     if (p) cudaFree(p);
   for (float *p : ag->dzl) cudaFree(p);
   cudaFree(ag->d_scalars);
@@ -922,6 +928,7 @@ int gcrl_agent_update_batch(gcrl_agent *ag, int64_t B, const float *s_dev, const
   GCRL_CUDA(cudaSetDevice(ag->device));
   cudaStream_t st = as_stream(stream);
   const float *noise = nullptr;
+  ag->per_on = (flags & 8) != 0;
   ingest(ag, nullptr, B, nullptr, s_dev, a_dev, r_dev, ns_dev, d_dev, noise_dev, &noise, st);
   write_scalars(ag, lr_critic, lr_actor, (flags & 1) != 0, st);
   run_update(ag, int(B), noise, flags, PH_ALL, st);
@@ -938,6 +945,7 @@ int gcrl_agent_update_from_buffer(gcrl_agent *ag, gcrl_her *buf, int64_t B, cons
   GCRL_CUDA(cudaSetDevice(ag->device));
   cudaStream_t st = as_stream(stream);
   const float *noise = nullptr;
+  ag->per_on = (flags & 8) != 0;
   ingest(ag, buf, B, idx_host, nullptr, nullptr, nullptr, nullptr, nullptr, noise_dev, &noise, st);
   write_scalars(ag, lr_critic, lr_actor, (flags & 1) != 0, st);
   run_update(ag, int(B), noise, flags, PH_ALL, st);
@@ -995,6 +1003,14 @@ int gcrl_agent_q(gcrl_agent *ag, int64_t n, const float *obs_host, const float *
   GCRL_API_END
 }
 
+int gcrl_agent_per_buffers(gcrl_agent *ag, float **weights_dev, float **td_dev) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(ag != nullptr && weights_dev != nullptr && td_dev != nullptr, "NULL argument");
+  *weights_dev = ag->per_w;
+  *td_dev = ag->per_td;
+  GCRL_API_END
+}
+
 // ---- data-parallel phase hooks ---------------------------------------------------------------------
 int gcrl_agent_update_phase(gcrl_agent *ag, int phase, gcrl_her *buf, int64_t B, const int64_t *idx_host,
                             const float *s_dev, const float *a_dev, const float *r_dev, const float *ns_dev,
@@ -1005,6 +1021,7 @@ int gcrl_agent_update_phase(gcrl_agent *ag, int phase, gcrl_her *buf, int64_t B,
   GCRL_REQUIRE(phase >= 0 && phase <= 3, "phase must be 0..3");
   GCRL_CUDA(cudaSetDevice(ag->device));
   cudaStream_t st = as_stream(stream);
+  ag->per_on = (flags & 8) != 0;
   if (phase == 0) {
     const float *noise = nullptr;
     ingest(ag, buf, B, idx_host, s_dev, a_dev, r_dev, ns_dev, d_dev, noise_dev, &noise, st);

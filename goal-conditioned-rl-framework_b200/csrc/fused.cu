@@ -265,22 +265,26 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_critic_kernel(FusedCri
           if (a.clamp_y) y = fminf(fmaxf(y, a.y_lo), 0.0f);
         }
         const float diff = q[r] - y;
+        const float w = a.is_w != nullptr ? a.is_w[row] : 1.0f;     // (weights * loss).mean(), :1322-1324
         if (!TD3 || a.loss_kind == 0) {               // mse_loss
-          ls += diff * diff;
-          g = 2.0f * diff * invB;
+          ls += w * (diff * diff);
+          g = 2.0f * diff * invB * w;
         } else {                                      // smooth_l1_loss, beta = 1 (TD3, :189-197)
           const float ad = fabsf(diff);
-          ls += ad < 1.0f ? 0.5f * diff * diff : ad - 0.5f;
-          g = (ad < 1.0f ? diff : (diff > 0.f ? 1.0f : -1.0f)) * invB;
+          ls += w * (ad < 1.0f ? 0.5f * diff * diff : ad - 0.5f);
+          g = (ad < 1.0f ? diff : (diff > 0.f ? 1.0f : -1.0f)) * invB * w;
         }
+        float td;
         if (TD3 && a.q_other != nullptr) {            // TD3 critic 2: max of both TD errors, mean of both Q
           const float qo = a.q_other[row];
-          ts += fmaxf(fabsf(q[r] - y), fabsf(qo - y));
+          td = fmaxf(fabsf(q[r] - y), fabsf(qo - y));
           qs += 0.5f * (q[r] + qo);
         } else {
-          ts += fabsf(y - q[r]);
+          td = fabsf(y - q[r]);
           qs += q[r];
         }
+        ts += td;
+        if (a.td_out != nullptr) a.td_out[row] = td;
         a.dzh_out[row] = g;
         if (a.y_out && (!TD3 || a.y_in == nullptr)) a.y_out[row] = y;
         if (a.q_out) a.q_out[row] = q[r];

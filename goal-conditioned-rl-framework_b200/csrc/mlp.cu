@@ -430,8 +430,9 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs a, int rows_p
         loss = ad < 1.0f ? 0.5f * diff * diff : ad - 0.5f;
         g = ad < 1.0f ? diff : (diff > 0.f ? 1.0f : -1.0f);
       }
-      dz_s[i][0] = g * invM;
-      met_s[i][0] = loss;
+      const float w = a.is_w != nullptr ? a.is_w[m] : 1.0f;   // (weights * loss).mean(), src/agent.py:1322-1324
+      dz_s[i][0] = g * invM * w;
+      met_s[i][0] = loss * w;
       if (a.q_other != nullptr) {        // TD3: mean(max(td1, td2)), mean over both critics' q
         const float qo = a.q_other[m];
         met_s[i][1] = fmaxf(fabsf(q - y), fabsf(qo - y));
@@ -440,6 +441,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs a, int rows_p
         met_s[i][1] = fabsf(y - q);
         met_s[i][2] = q;
       }
+      if (a.td_out != nullptr && blockIdx.y == 0) a.td_out[m] = met_s[i][1];
     } else if (a.mode == 1) {
       dz_s[i][0] = -invM;
       met_s[i][0] = -a.q[m];             // actor loss = -mean(q)

@@ -39,6 +39,8 @@ struct HeadBwdArgs {
   const float *q, *qt1, *qt2, *r, *d, *dz_in;
   const float *y_in;      // mode 0: Bellman target given per row (SAC / TQC) instead of built from qt1/qt2
   const float *q_other;   // TD3 critic 2: metrics use max(|q-y|, |q_other-y|) and (q+q_other)/2
+  const float *is_w;      // mode 0, prioritised replay: per-sample importance weight of the loss (nullptr: 1)
+  float *td_out;          // mode 0, prioritised replay: per-sample TD error (max with q_other's), or nullptr
   float gamma, y_lo;
   const float *Hact; int ldh;      // last hidden activation [M, K]
   const float *W; int ldw;         // head weight [nout, K]
@@ -93,6 +95,8 @@ struct FusedCriticArgs {
   int loss_kind;                // 0 mse, 1 smooth-l1 (beta 1)
   const float *y_in;            // non-null: the Bellman target is given (TD3 critic 2); the target nets are skipped
   const float *q_other;         // non-null: metrics use max(|q-y|, |q_other-y|) and (q + q_other) / 2
+  const float *is_w;            // prioritised replay: per-sample importance weight of the loss (nullptr: 1)
+  float *td_out;                // prioritised replay: per-sample TD error [B] (max with q_other's), or nullptr
   const float *s, *a, *r, *ns, *d;   // dense batch
   int B, D, A, H, L, ldh, ldc;
   float gamma, y_lo; int clamp_y;

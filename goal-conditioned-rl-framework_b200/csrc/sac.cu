@@ -248,7 +248,7 @@ __device__ __forceinline__ float cta_sum_1024(float v, float *sm) {
 // out[0..n) = mean (q_i - y)^2; out[8] = mean max_i |q_i - y|; out[9] = mean over i, m of q_i
 __global__ void __launch_bounds__(1024)
 critic_metrics_kernel(const float *__restrict__ q, int64_t ldq, int n, const float *__restrict__ y, int M,
-                      float *__restrict__ out, int q_only) {
+                      float *__restrict__ out, int q_only, const float *__restrict__ is_w, float *__restrict__ td_out) {
   __shared__ float sm[1024];
   float loss[kMaxCritics], td = 0.f, qs = 0.f;
 #pragma unroll
@@ -256,16 +256,18 @@ critic_metrics_kernel(const float *__restrict__ q, int64_t ldq, int n, const flo
   for (int m = threadIdx.x; m < M; m += 1024) {
     float mx = 0.f;
     const float yy = q_only ? 0.f : y[m];
+    const float w = is_w != nullptr ? is_w[m] : 1.0f;      // prioritised replay: (weights * loss).mean() (:577-581)
 #pragma unroll
     for (int i = 0; i < kMaxCritics; ++i)
       if (i < n) {
         const float qq = q[int64_t(i) * ldq + m];
         const float df = qq - yy;
-        loss[i] = fmaf(df, df, loss[i]);
+        loss[i] = fmaf(w * df, df, loss[i]);
         mx = fmaxf(mx, fabsf(df));
         qs += qq;
       }
     td += mx;
+    if (td_out != nullptr) td_out[m] = mx;                 // max over the critics of |q_i - y| (:620-621, :1021-1024)
   }
   const float inv = 1.0f / float(M);
   if (!q_only) {
@@ -569,6 +571,8 @@ struct gcrl_sac {
   float *q = nullptr, *qt = nullptr, *y = nullptr, *dq = nullptr;     // [n][maxB], [n][maxB], [maxB], [n][maxB*4]
   float *logp = nullptr, *act4 = nullptr, *std4 = nullptr, *gate4 = nullptr, *dact = nullptr, *dzh = nullptr;
   float *eps_next = nullptr, *eps_cur = nullptr;
+  float *per_w = nullptr, *per_td = nullptr;     // prioritised replay: importance weights in, TD errors out [maxB]
+  bool per_on = false;                           // flags bit3 of the update being issued
   float *partials = nullptr;
   int64_t slab = 0;
   float *sumsq = nullptr;
@@ -689,13 +693,15 @@ void critic_update(gcrl_sac *ag, int B, int flags, int mask, cudaStream_t st) {
                                                        ag->y, B);
   GCRL_LAUNCHED();
   for (int i = 0; i < n; ++i) critic_fwd(ag, ag->critic[i], ag->sa, ag->ch[i], ag->q + int64_t(i) * ag->maxB, B, st);
-  critic_metrics_kernel<<<1, 1024, 0, st>>>(ag->q, ag->maxB, n, ag->y, B, ag->mdev + M_CLOSS, 0);
+  critic_metrics_kernel<<<1, 1024, 0, st>>>(ag->q, ag->maxB, n, ag->y, B, ag->mdev + M_CLOSS, 0,
+                                            ag->per_on ? ag->per_w : nullptr, ag->per_on ? ag->per_td : nullptr);
   GCRL_LAUNCHED();
   for (int i = 0; i < n; ++i) {
     CriticNet &c = ag->critic[i];
     HeadBwdArgs h{};
     h.mode = 0; h.loss_kind = 0; h.clamp_y = 0; h.nout = 1;
     h.q = ag->q + int64_t(i) * ag->maxB; h.y_in = ag->y;
+    if (ag->per_on) h.is_w = ag->per_w;
     h.Hact = ag->ch[i][L - 1]; h.ldh = ag->ldh;
     h.W = c.W(L); h.ldw = c.ldw[L];
     h.dZprev = ag->dz[0]; h.lddz = ag->ldh;
@@ -731,7 +737,7 @@ void critic_update(gcrl_sac *ag, int B, int flags, int mask, cudaStream_t st) {
   }
   if (tqc && (mask & PH_CSTEP)) {   // logged Q = mean over the STEPPED critics (:1016-1019)
     for (int i = 0; i < n; ++i) critic_fwd(ag, ag->critic[i], ag->sa, ag->th, ag->qt + int64_t(i) * ag->maxB, B, st);
-    critic_metrics_kernel<<<1, 1024, 0, st>>>(ag->qt, ag->maxB, n, nullptr, B, ag->mdev + M_CLOSS, 1);
+    critic_metrics_kernel<<<1, 1024, 0, st>>>(ag->qt, ag->maxB, n, nullptr, B, ag->mdev + M_CLOSS, 1, nullptr, nullptr);
     GCRL_LAUNCHED();
   }
 }
@@ -841,6 +847,7 @@ void run_body(gcrl_sac *ag, int B, int flags, int mask, cudaStream_t st) {
 // Replay (or capture on first use) the CUDA graph of (B, flags, phase mask): ~170 launches per TQC update
 // become one graph launch; everything that varies per step travels through device scalars.
 void run_phases(gcrl_sac *ag, int B, int flags, int mask, cudaStream_t st) {
+  ag->per_on = (flags & 8) != 0;
   if (!ag->use_graphs) {
     run_body(ag, B, flags, mask, st);
     return;
@@ -1019,7 +1026,7 @@ int gcrl_sac_create(gcrl_sac **out, int device, const gcrl_sac_config *cfg) {
     for (int l = 0; l < L; ++l) ag->th.push_back(dev_alloc<float>(act));
     for (auto &p : ag->dz) p = dev_alloc<float>(act);
     for (float **p : {&ag->sa, &ag->nsa, &ag->spi}) *p = dev_alloc<float>(mb * ag->ldc);
-    for (float **p : {&ag->br, &ag->bd, &ag->br0, &ag->bd0, &ag->y, &ag->logp}) *p = dev_alloc<float>(mb);
+    for (float **p : {&ag->br, &ag->bd, &ag->br0, &ag->bd0, &ag->y, &ag->logp, &ag->per_w, &ag->per_td}) *p = dev_alloc<float>(mb);
     ag->bs = dev_alloc<float>(mb * D); ag->bns = dev_alloc<float>(mb * D); ag->ba = dev_alloc<float>(mb * A);
     ag->q = dev_alloc<float>(mb * n); ag->qt = dev_alloc<float>(mb * n); ag->dq = dev_alloc<float>(mb * n * 4);
     for (float **p : {&ag->act4, &ag->std4, &ag->gate4, &ag->dact, &ag->eps_next, &ag->eps_cur}) *p = dev_alloc<float>(mb * 4);
@@ -1058,7 +1065,7 @@ int gcrl_sac_destroy(gcrl_sac *ag) {
   for (float *p : {ag->invstd, ag->dz[0], ag->dz[1], ag->sa, ag->nsa, ag->spi, ag->br, ag->bd, ag->bs, ag->ba, ag->bns,
                    ag->br0, ag->bd0, ag->q, ag->qt, ag->y, ag->dq, ag->logp, ag->act4, ag->std4, ag->gate4, ag->dact,
                    ag->dzh, ag->eps_next, ag->eps_cur, ag->partials, ag->sumsq, ag->mdev, ag->alpha_state, ag->d_io,
-                   ag->critic_grads})
+                   ag->critic_grads, ag->per_w, ag->per_td})
     if (p) cudaFree(p);
   for (auto &kv : ag->graphs) cudaGraphExecDestroy(kv.second.exec);
   if (ag->cap_stream) cudaStreamDestroy(ag->cap_stream);
@@ -1201,6 +1208,14 @@ int gcrl_sac_update_phase(gcrl_sac *ag, int phase, gcrl_her *buf, int64_t B, con
   GCRL_CUDA(cudaSetDevice(ag->device));
   sac_update(ag, phase, buf, B, idx_host, s, a, r, ns, d, eps_next, eps_cur, lr_c, lr_a, flags, nullptr,
              as_stream(stream));
+  GCRL_API_END
+}
+
+int gcrl_sac_per_buffers(gcrl_sac *ag, float **weights_dev, float **td_dev) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(ag != nullptr && weights_dev != nullptr && td_dev != nullptr, "NULL argument");
+  *weights_dev = ag->per_w;
+  *td_dev = ag->per_td;
   GCRL_API_END
 }
 

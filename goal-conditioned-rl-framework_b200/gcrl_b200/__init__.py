@@ -8,9 +8,10 @@ raises, and every compute call needs a CUDA device.
 """
 from ._lib import GcrlError, lib, library_path  # noqa: F401
 from .buffer import HERBuffer  # noqa: F401
+from .replay import PERBuffer, ReplayBuffer  # noqa: F401
 from .normalizer import RunningNormalizer  # noqa: F401
 from .agent import DDPG, TD3Agent, CosineAnnealingLR  # noqa: F401
 from .sac import SACAgent, TQCAgent  # noqa: F401
 
-__all__ = ["HERBuffer", "RunningNormalizer", "DDPG", "TD3Agent", "SACAgent", "TQCAgent", "GcrlError", "lib",
+__all__ = ["HERBuffer", "PERBuffer", "ReplayBuffer", "RunningNormalizer", "DDPG", "TD3Agent", "SACAgent", "TQCAgent", "GcrlError", "lib",
            "library_path", "CosineAnnealingLR"]

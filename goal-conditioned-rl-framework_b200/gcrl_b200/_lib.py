@@ -114,6 +114,23 @@ SIGNATURES = {
                                         vp]),
     "gcrl_sac_dp_buffer": (C.c_int, [vp, C.c_int, pp, C.POINTER(c_i64)]),
     "gcrl_sac_read_metrics": (C.c_int, [vp, C.c_int, vp, vp]),
+    # uniform / prioritised replay
+    "gcrl_replay_create": (C.c_int, [pp, C.c_int, c_i64, C.c_int, C.c_int, C.c_int, c_f64]),
+    "gcrl_replay_destroy": (C.c_int, [vp]),
+    "gcrl_replay_push": (C.c_int, [vp, c_i64, vp, vp]),
+    "gcrl_replay_len": (c_i64, [vp]),
+    "gcrl_replay_total": (c_i64, [vp]),
+    "gcrl_replay_sample": (C.c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, vp]),
+    "gcrl_replay_sample_prioritized": (C.c_int, [vp, c_i64, vp, c_f64, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "gcrl_replay_update_priorities": (C.c_int, [vp, c_i64, vp, vp, vp]),
+    "gcrl_replay_get_priorities": (C.c_int, [vp, vp, vp]),
+    "gcrl_replay_set_priorities": (C.c_int, [vp, vp, c_i64, vp]),
+    "gcrl_replay_get_rows": (C.c_int, [vp, c_i64, c_i64, vp, vp]),
+    "gcrl_replay_last_sample_info": (C.c_int, [vp, C.POINTER(c_f32), C.POINTER(C.c_int), vp]),
+    "gcrl_replay_last_positions": (C.c_int, [vp, c_i64, vp, vp]),
+    "gcrl_replay_last_tables": (C.c_int, [vp, vp, vp, vp]),
+    "gcrl_agent_per_buffers": (C.c_int, [vp, pp, pp]),
+    "gcrl_sac_per_buffers": (C.c_int, [vp, pp, pp]),
     # diagnostics
     "gcrl_agent_time_critic_kernel": (C.c_int, [vp, c_i64, C.c_int, C.POINTER(c_f32), vp]),
     "gcrl_dense_wgrad": (C.c_int, [C.c_int, C.c_int, c_i64, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, c_i64,
@@ -134,7 +151,7 @@ def _load():
         fn = getattr(dll, name)          # AttributeError if the library lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if dll.gcrl_abi_version() != 2:
+    if dll.gcrl_abi_version() != 3:
         raise ImportError("libgcrl_b200.so ABI version mismatch")
     return dll
 

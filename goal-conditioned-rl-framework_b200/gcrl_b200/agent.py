@@ -19,6 +19,7 @@ import numpy as np
 from . import _lib
 from ._lib import AgentConfig, check, lib, np_ptr, vp
 from .buffer import HERBuffer
+from .replay import PERBuffer, ReplayBuffer
 
 ALGO_DDPG, ALGO_TD3 = 0, 1
 NET_ACTOR, NET_CRITIC, NET_T_ACTOR, NET_T_CRITIC, NET_CRITIC2, NET_T_CRITIC2 = range(6)
@@ -145,10 +146,10 @@ class _AgentBase:
             self.buffer = HERBuffer(config.max_len, config.max_eps_len, nenvs,
                                     k_future=config.k_future, index_source=index_source,
                                     seed=seed, device=device)
-        elif config.buffer_type in ("PER", "REPLAY"):
-            raise NotImplementedError(
-                f"buffer_type {config.buffer_type!r}: only the HER buffer is on the accelerated "
-                "hot path (every shipped YAML uses 'HER')")
+        elif config.buffer_type == "PER":                                  # src/agent.py:67-68
+            self.buffer = PERBuffer(config.max_len, config.alpha, device=device)
+        elif config.buffer_type == "REPLAY":                               # :69-70
+            self.buffer = ReplayBuffer(config.max_len, device=device)
         else:
             raise ValueError(f"[ERROR] Invalid Buffer type. Received {config.buffer_type}.")
 
@@ -207,7 +208,7 @@ class _AgentBase:
 
     # -- reference API shared by all agents (src/agent.py:1368-1376, 1410-1465) -------------
     def push(self, state, action, reward, next_state, done):
-        raise NotImplementedError("uniform replay push: only the HER path is accelerated")
+        self.buffer.push(state, action, reward, next_state, done)
 
     def push_her(self, idx, state, action, next_state, reward, done, desired_goal, achieved_goal):
         self.buffer.push(idx, state, action, next_state, reward, done, desired_goal, achieved_goal)
@@ -320,6 +321,40 @@ class _AgentBase:
     def _trainable_critics(self):
         return (NET_CRITIC,)
 
+    # -- uniform / prioritised replay behind update() (src/agent.py:1380-1394 and the twins in TD3 / SAC / TQC) --
+    _per = None
+    _replay_out = None
+    _last_td = None
+
+    def _per_ptrs(self):
+        if self._per is None:
+            w, td = vp(), vp()
+            check(lib.gcrl_agent_per_buffers(self._h, C.byref(w), C.byref(td)))
+            self._per = (w, td)
+        return self._per
+
+    def _replay_batch(self, B):
+        """Draw the batch of a non-HER buffer into device tensors.  Returns (batch, prioritised?); for a
+        PERBuffer the importance weights land in the agent's weight array (read by the critic loss when flags
+        bit3 is set) and nothing comes back to the host."""
+        buf = self.buffer
+        assert len(buf) >= B, "Not enough in buffer to sample"
+        if isinstance(buf, PERBuffer):
+            buf._flush()
+            if self._replay_out is None or self._replay_out[0].shape[0] != B:
+                self._replay_out = buf._outputs(B)
+            buf.sample_into(B, self.beta, self._replay_out, self._per_ptrs()[0])
+            return tuple(self._replay_out), True
+        return buf.sample(B), False
+
+    def _replay_finish(self, B):
+        """buffer.update_priorities(indices, td_error) (:1387) on the device, then the per-sample TD errors the
+        reference returns in place of their mean (:1338-1340)."""
+        from .parallel import device_tensor
+        td_ptr = self._per_ptrs()[1]
+        self.buffer.update_priorities_last(B, td_ptr)
+        return device_tensor(td_ptr.value, B, self.device_index).cpu().numpy().reshape(B, 1)
+
     def _run_update(self, step, batch=None, indices=None, noise=None, sync=True):
         """One update; ``batch`` = 5 device tensors (explicit batch) or None (sample from the
         buffer; ``indices`` optional host positions).  Returns the raw 8-float metric vector
@@ -330,6 +365,11 @@ class _AgentBase:
         nptr = vp(noise.data_ptr()) if noise is not None else None
         iptr = None
         predraw = False
+        per = False
+        if batch is None and not isinstance(self.buffer, HERBuffer):
+            batch, per = self._replay_batch(self.batch_size)
+            if per:
+                flags |= 8
         if batch is None:
             B = self.batch_size
             assert len(self.buffer) >= B, "[ERROR] Not enough in buffer to sample"
@@ -370,6 +410,7 @@ class _AgentBase:
         else:
             check(lib.gcrl_agent_update_batch(self._h, B, *ptrs, nptr, lr_c, lr_a, flags, mptr,
                                               self._stream()))
+        self._last_td = self._replay_finish(B) if per else None
         self.critic_scheduler.step()
         if flags & 1:
             self.actor_scheduler.step()
@@ -521,6 +562,8 @@ class DDPG(_AgentBase):
         m = self._run_update(step, batch=batch, indices=indices)
         self.beta_scheduler(step)
         critic_loss, ac_loss, td, q, cg, agn = m[0], m[1], np.float32(m[2]), m[3], m[4], m[5]
+        if self._last_td is not None:          # prioritised replay: the per-sample array (:1338-1340)
+            td = self._last_td
         if step % self.ac_update_freq == 0:
             return critic_loss, ac_loss, td, q, cg, agn
         return critic_loss, td, q, cg
@@ -590,7 +633,7 @@ class TD3Agent(_AgentBase):
         m = self._run_update(step, batch=batch, indices=indices, noise=noise)
         self.beta_scheduler(step)
         q1l, acl, td, q, c1g, acg, q2l, c2g = m
-        td = np.float32(td)
+        td = np.float32(td) if self._last_td is None else self._last_td
         if step % self.ac_update_freq == 0:
             return q1l, q2l, acl, td, q, c1g, c2g, acg
         return q1l, q2l, td, q, c1g, c2g

@@ -18,6 +18,7 @@ import numpy as np
 from . import _lib
 from ._lib import SacConfig, check, lib, np_ptr, vp
 from .agent import CosineAnnealingLR, _AgentBase
+from .buffer import HERBuffer
 
 ALGO_SAC, ALGO_TQC = 2, 3
 
@@ -261,6 +262,13 @@ class _SacBase(_AgentBase):
     def _polyak_now(self, step):
         raise NotImplementedError
 
+    def _per_ptrs(self):
+        if self._per is None:
+            w, td = vp(), vp()
+            check(lib.gcrl_sac_per_buffers(self._h, C.byref(w), C.byref(td)))
+            self._per = (w, td)
+        return self._per
+
     # -- data parallel: same GradAverager as DDPG / TD3 over the buffers of gcrl_sac_dp_buffer -------
     def grad_tensor(self, which):
         from .parallel import device_tensor
@@ -286,6 +294,11 @@ class _SacBase(_AgentBase):
         en = vp(eps_next.data_ptr())
         ec = vp(eps_cur.data_ptr()) if eps_cur is not None else None
         iptr, bufh, ptrs = None, None, (None,) * 5
+        per = False
+        if batch is None and not isinstance(self.buffer, HERBuffer):
+            batch, per = self._replay_batch(B)           # src/agent.py:661-673 / :1064-1076
+            if per:
+                flags |= 8
         if batch is None:
             assert len(self.buffer) >= B, "[ERROR] Not enough in buffer to sample"
             if indices is None and self.index_source == "host":
@@ -312,6 +325,7 @@ class _SacBase(_AgentBase):
                                                   self._stream()))
         else:
             check(lib.gcrl_sac_update_batch(self._h, B, *ptrs, en, ec, lr_c, lr_a, flags, mptr, self._stream()))
+        self._last_td = self._replay_finish(B) if per else None
         self.critic_scheduler.step()
         self._bn_batches += 1
         if actor_step:
@@ -320,7 +334,7 @@ class _SacBase(_AgentBase):
         self.beta_scheduler(step)
         m = [float(x) for x in self._metrics]
         q1l, q2l, acl, td, qv, c1g, c2g, acg, all_ = m[:9]
-        td = np.float32(td)
+        td = np.float32(td) if self._last_td is None else self._last_td
         if actor_step:
             return q1l, q2l, acl, td, qv, c1g, c2g, acg, (all_ if flags & 4 else 0.0)
         return q1l, q2l, td, qv, c1g, c2g

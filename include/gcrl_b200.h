@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GCRL_ABI_VERSION 2
+#define GCRL_ABI_VERSION 3
 
 #define GCRL_OK 0
 #define GCRL_ERR_INVALID 1      /* bad argument / shape                                  */
@@ -354,6 +354,61 @@ int gcrl_sac_read_metrics(gcrl_sac *h, int flags, float *metrics_host, void *str
  * tanh(mean); otherwise tanh(mean + std * eps).  obs host [n, D] -> act host [n, A]. */
 int gcrl_sac_act(gcrl_sac *h, int64_t n, const float *obs_host, const float *eps_host, float *act_host,
                  void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Uniform and prioritised replay -- replace ReplayBuffer (src/buffer.py:8-35) and PERBuffer
+ * (src/buffer.py:38-89), the buffers behind agent.update() when buffer_type is not "HER"
+ * ------------------------------------------------------------------------------------
+ * A bounded FIFO of transitions on the device (deque(maxlen=capacity) semantics: position 0 is the
+ * oldest live entry).  Packed host row: s[D] | a[A] | r | ns[D] | d  (2D + A + 2 floats). */
+typedef struct gcrl_replay gcrl_replay;
+
+/* PERBuffer(max_len, alpha) when prioritized != 0 (:39-44), else ReplayBuffer(max_len) (:9-11). */
+int gcrl_replay_create(gcrl_replay **out, int device, int64_t capacity, int state_dim, int act_dim,
+                       int prioritized, double alpha);
+int gcrl_replay_destroy(gcrl_replay *h);
+/* push() x n (:13-14, :46-48): rows host [n, 2D + A + 2]; new entries get priority 1.0. */
+int gcrl_replay_push(gcrl_replay *h, int64_t n, const float *rows_host, void *stream);
+int64_t gcrl_replay_len(gcrl_replay *h);          /* __len__, :34-35 / :83-84 */
+int64_t gcrl_replay_total(gcrl_replay *h);        /* entries ever appended    */
+/* ReplayBuffer.sample (:16-32) at the positions the caller drew (random.sample(range(len), B) --
+ * the same Mersenne-Twister stream as random.sample(deque, B)); device outputs s [B, D], a [B, A],
+ * r [B], ns [B, D], d [B].  GCRL_ERR_INVALID "Not enough in buffer to sample" mirrors the assert. */
+int gcrl_replay_sample(gcrl_replay *h, int64_t B, const int64_t *idx_host, float *s_dev, float *a_dev,
+                       float *r_dev, float *ns_dev, float *d_dev, void *stream);
+/* PERBuffer.sample(batch_size, beta) (:50-81).  u_host[B] = the uniforms np.random.choice consumes
+ * (RandomState.random_sample(B)); positions = searchsorted(cumsum(P) / cumsum(P)[-1], u, "right") with
+ * P = priorities / priorities.sum() in float32, bit-exact (see per.cu); weights_dev[B] =
+ * (N P[i])^-beta / max.  idx_host_out (optional): the drawn deque positions, copied back with a stream
+ * synchronise; NULL keeps the call asynchronous. */
+int gcrl_replay_sample_prioritized(gcrl_replay *h, int64_t B, const double *u_host, double beta,
+                                   float *s_dev, float *a_dev, float *r_dev, float *ns_dev, float *d_dev,
+                                   float *weights_dev, int64_t *idx_host_out, void *stream);
+/* update_priorities(indices, td) (:86-89): priority = (|td| + 1e-6)^alpha in float32, applied in list
+ * order (the last duplicate wins).  idx_host[B] = deque positions, or NULL = the positions drawn by the
+ * preceding sample_prioritized (kept on the device; no host round trip). */
+int gcrl_replay_update_priorities(gcrl_replay *h, int64_t B, const int64_t *idx_host, const float *td_dev,
+                                  void *stream);
+/* priorities in deque order, host float[len] (tests, checkpoints) */
+int gcrl_replay_get_priorities(gcrl_replay *h, float *prio_host, void *stream);
+int gcrl_replay_set_priorities(gcrl_replay *h, const float *prio_host, int64_t n, void *stream);
+/* stored rows [first, first + n) in deque order, packed host rows (tests, checkpoints) */
+int gcrl_replay_get_rows(gcrl_replay *h, int64_t first, int64_t n, float *rows_host, void *stream);
+/* Of the last sample_prioritized: the float32 priority sum, and whether the float64 cumsum took the
+ * sequential fallback (1) or the order-independent fixed-point scan (0). */
+int gcrl_replay_last_sample_info(gcrl_replay *h, float *priority_sum, int *sequential_cumsum, void *stream);
+/* The deque positions drawn by the last sample_prioritized (what the reference returns as `indices`). */
+int gcrl_replay_last_positions(gcrl_replay *h, int64_t B, int64_t *idx_host, void *stream);
+/* Of the last sample_prioritized: P (float32 [len]) and the searched table (float64 [len]). */
+int gcrl_replay_last_tables(gcrl_replay *h, float *p_host, double *cdf_host, void *stream);
+
+/* The prioritised branch of critic_update (src/agent.py:1322-1324,1338-1340; TD3 :193-197,:232-233;
+ * SAC :577-596,:620-621; TQC :993-997,:1021-1024): with flags bit3 set, gcrl_agent_update_* /
+ * gcrl_sac_update_* weight every sample's critic loss with weights_dev[b] (mean(w * loss)) and write the
+ * per-sample TD error |y - q| (max over the critics) to td_dev[b].  The two device arrays (max_batch
+ * floats each) belong to the agent. */
+int gcrl_agent_per_buffers(gcrl_agent *h, float **weights_dev, float **td_dev);
+int gcrl_sac_per_buffers(gcrl_sac *h, float **weights_dev, float **td_dev);
 
 /* ------------------------------------------------------------------------------------
  * Diagnostics / micro-benchmarks

@@ -205,7 +205,9 @@ class DDPGOracle:
         self.last_actor_flip_slack = 0.0
 
     # src/agent.py:1302-1343
-    def critic_update(self, s, a, r, ns, d):
+    def critic_update(self, s, a, r, ns, d, weights=None):
+        """``weights`` [B, 1]: the prioritised-replay branch (:1322-1324, :1338-1340) -- loss = mean(w * (q - y)^2)
+        and the TD errors come back per sample instead of as their mean."""
         g = F32(self.gamma)
         na, _ = mlp_forward(self.target_actor, ns, final_tanh=True)
         tq, _ = mlp_forward(self.target_critic, np.concatenate([ns, na], -1), final_tanh=False)
@@ -214,9 +216,15 @@ class DDPGOracle:
         q, acts = mlp_forward(self.critic, np.concatenate([s, a], -1), final_tanh=False)
         B = q.shape[0]
         diff = (q - y).astype(F32)
-        loss = float(np.mean(diff * diff, dtype=F32))
-        td = float(np.mean(np.abs(y - q), dtype=F32))
-        dq = (F32(2.0) * diff / F32(B)).astype(F32)
+        if weights is None:
+            loss = float(np.mean(diff * diff, dtype=F32))
+            td = float(np.mean(np.abs(y - q), dtype=F32))
+            dq = (F32(2.0) * diff / F32(B)).astype(F32)
+        else:
+            w = np.asarray(weights, F32).reshape(B, 1)
+            loss = float(np.mean(w * (diff * diff), dtype=F32))
+            td = np.abs(y - q).astype(F32)
+            dq = (F32(2.0) * diff * w / F32(B)).astype(F32)
         grads, _ = mlp_backward(self.critic, acts, dq, final_tanh=False)
         if self.grad_clip is not None:
             clip_grad_norm_(grads, self.grad_clip)
@@ -292,8 +300,8 @@ class DDPGOracle:
                 tb[...] = t * b + omt * tb
 
     # src/agent.py:1378-1404
-    def update_on_batch(self, step, s, a, r, ns, d):
-        closs, td, qv, cg = self.critic_update(s, a, r, ns, d)
+    def update_on_batch(self, step, s, a, r, ns, d, weights=None):
+        closs, td, qv, cg = self.critic_update(s, a, r, ns, d, weights)
         if step % self.POLYAK_EVERY == 0:
             self.soft_update(self.tau)
         if step % self.ac_update_freq == 0:

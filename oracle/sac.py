@@ -205,7 +205,8 @@ class SACOracle:
     def _coef(self):
         return F32(0.2) if self.algo == "sac" else self.alpha
 
-    def critic_update(self, s, a, r, ns, d, eps):
+    def critic_update(self, s, a, r, ns, d, eps, weights=None):
+        w = None if weights is None else np.asarray(weights, F32).reshape(-1, 1)   # prioritised replay (:577-596)
         na, nlogp, _ = actor_sample(self.actor, self.actor_stats, ns, eps, train=True)
         tin = np.concatenate([ns, na], -1)
         tq = np.stack([mlp_forward(tc, tin, False)[0] for tc in self.target_critics])
@@ -219,8 +220,13 @@ class SACOracle:
         for i, c in enumerate(self.critics):
             q, acts = fwd[i] if self.algo == "sac" else mlp_forward(c, cin, False)
             diff = (q - y).astype(F32)
-            losses.append(float(np.mean(diff * diff, dtype=F32)))
-            g, _ = mlp_backward(c, acts, (F32(2) * diff / F32(B)).astype(F32), False)
+            if w is None:
+                losses.append(float(np.mean(diff * diff, dtype=F32)))
+                dq = (F32(2) * diff / F32(B)).astype(F32)
+            else:
+                losses.append(float(np.mean(w * (diff * diff), dtype=F32)))
+                dq = (F32(2) * diff * w / F32(B)).astype(F32)
+            g, _ = mlp_backward(c, acts, dq, False)
             clip_grad_norm_(g, self.grad_clip)
             gns.append(grad_norm_python(g))
             self.critic_opts[i].step(c, g, self.critic_scheds[i].lr)
@@ -231,7 +237,9 @@ class SACOracle:
         if self.algo == "sac":
             for sch in self.critic_scheds:
                 sch.step()
-        td = float(np.mean(np.max(np.stack(tds), axis=0), dtype=F32))
+        td = np.max(np.stack(tds), axis=0).astype(F32)                      # per sample when prioritised (:620-621)
+        if w is None:
+            td = float(np.mean(td, dtype=F32))
         self.last_y = y
         if self.algo == "sac":
             qv = float(np.mean(np.concatenate(qs, -1), dtype=F32))
@@ -280,8 +288,8 @@ class SACOracle:
                 tw[...] = t * w + omt * tw
                 tb[...] = t * b + omt * tb
 
-    def update_on_batch(self, step, s, a, r, ns, d, eps_next, eps_cur):
-        l1, l2, td, qv, g1, g2 = self.critic_update(s, a, r, ns, d, eps_next)
+    def update_on_batch(self, step, s, a, r, ns, d, eps_next, eps_cur, weights=None):
+        l1, l2, td, qv, g1, g2 = self.critic_update(s, a, r, ns, d, eps_next, weights)
         if self.algo == "tqc" or step % self.gradient_step == 0:
             self._polyak()
         if step % self.ac_update_freq == 0:

@@ -21,12 +21,16 @@ from .ddpg import (AdamState, CosineAnnealingLR, F32, clip_grad_norm_, clone_par
 ADAMW_WD = 0.01  # torch.optim.AdamW default, src/agent.py:46-48
 
 
-def smooth_l1(q, y):
-    """torch.nn.functional.smooth_l1_loss(q, y), beta = 1, mean reduction -> (loss, dloss/dq)."""
+def smooth_l1(q, y, weights=None):
+    """torch.nn.functional.smooth_l1_loss(q, y), beta = 1, mean reduction -> (loss, dloss/dq); with ``weights``
+    the prioritised form ``(weights * smooth_l1_loss(q, y, reduction="none")).mean()`` (:193-197)."""
     diff = (q - y).astype(F32)
     ad = np.abs(diff)
     elem = np.where(ad < 1, F32(0.5) * diff * diff, ad - F32(0.5)).astype(F32)
     grad = np.where(ad < 1, diff, np.sign(diff)).astype(F32) / F32(q.shape[0])
+    if weights is not None:
+        w = np.asarray(weights, F32).reshape(q.shape)
+        elem, grad = (w * elem).astype(F32), (w * grad).astype(F32)
     return float(np.mean(elem, dtype=F32)), grad.astype(F32)
 
 
@@ -46,7 +50,7 @@ class TD3Oracle:
         self.gamma, self.tau, self.grad_clip = gamma, tau, grad_clip
         self.policy_noise, self.noise_clamp, self.ac_update_freq = policy_noise, noise_clamp, ac_update_freq
 
-    def critic_update(self, s, a, r, ns, d, randn):                       # :164-251
+    def critic_update(self, s, a, r, ns, d, randn, weights=None):         # :164-251
         noise = np.clip((randn * F32(self.policy_noise)).astype(F32), F32(-self.noise_clamp), F32(self.noise_clamp))
         na, _ = mlp_forward(self.target_actor, ns, final_tanh=True)
         na = np.clip((na + noise).astype(F32), F32(-1), F32(1))
@@ -56,17 +60,19 @@ class TD3Oracle:
         cin = np.concatenate([s, a], -1)
         q1, acts1 = mlp_forward(self.critic_1, cin, False)
         q2, acts2 = mlp_forward(self.critic_2, cin, False)
-        loss1, dq1 = smooth_l1(q1, y)
+        loss1, dq1 = smooth_l1(q1, y, weights)
         g1, _ = mlp_backward(self.critic_1, acts1, dq1, False)
         gn1 = grad_norm_python(g1)                                        # unclipped (:201)
         self.c1_opt.step(self.critic_1, g1, self.critic_sched.lr)
-        loss2, dq2 = smooth_l1(q2, y)
+        loss2, dq2 = smooth_l1(q2, y, weights)
         g2, _ = mlp_backward(self.critic_2, acts2, dq2, False)
         clip_grad_norm_(g2, self.grad_clip)
         gn2 = grad_norm_python(g2)
         self.c2_opt.step(self.critic_2, g2, self.critic_sched.lr)
         self.critic_sched.step()
-        td = float(np.mean(np.maximum(np.abs(q1 - y), np.abs(q2 - y)), dtype=F32))
+        td = np.maximum(np.abs(q1 - y), np.abs(q2 - y)).astype(F32)       # per sample when prioritised (:232-233)
+        if weights is None:
+            td = float(np.mean(td, dtype=F32))
         qv = float(np.mean(np.concatenate([q1, q2], -1), dtype=F32))
         return loss1, loss2, td, qv, gn1, gn2
 
@@ -89,8 +95,8 @@ class TD3Oracle:
             tw[...] = t * w + omt * tw
             tb[...] = t * b + omt * tb
 
-    def update_on_batch(self, step, s, a, r, ns, d, randn):                # :281-317
-        l1, l2, td, qv, g1, g2 = self.critic_update(s, a, r, ns, d, randn)
+    def update_on_batch(self, step, s, a, r, ns, d, randn, weights=None):  # :281-317
+        l1, l2, td, qv, g1, g2 = self.critic_update(s, a, r, ns, d, randn, weights)
         self._polyak(self.target_critic_1, self.critic_1, self.tau)
         self._polyak(self.target_critic_2, self.critic_2, self.tau)
         if step % self.ac_update_freq == 0:

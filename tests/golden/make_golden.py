@@ -418,6 +418,183 @@ def sac_case(agent_mod, utils_mod, algo, name, *, D, A, H, L, B, steps, seed, ga
     print(f"{algo}_{name}: {len(steps)} steps; last info {out[f's{len(steps) - 1}_info']}")
 
 
+def per_case(agent_mod, utils_mod, algo, name, *, D, A, H, L, B, max_len, n0, push_per_step, steps, seed,
+             per_alpha=0.6, beta=0.4, beta_end=4, gamma=0.98, tau=0.05, grad_clip=1.0, lr=1e-3, ac_update_freq=1,
+             gradient_step=2, store_final=True):
+    """The prioritised-replay branch of update() (src/agent.py:1380-1387 and its twins), end to end through the
+    UNMODIFIED reference: PERBuffer.push / sample / update_priorities (src/buffer.py:38-89) behind
+    DDPG / TD3Agent / SACAgent / TQCAgent.update.  Recorded per step: the priorities before the draw, the
+    uniforms np.random.choice consumed, the drawn positions, importance weights and batch, every torch normal
+    draw, the returned tuple (per-sample TD errors separately) and the priorities afterwards."""
+    import torch
+    import torch.distributions.normal as tdn
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import ddpg as O
+    from oracle import sac as OS
+    torch.set_num_threads(1)
+    common = dict(hidden_dim=H, layer_count=L, actor_lr=lr, actor_lr_min=lr, ac_scheduler_steps=1, critic_lr=lr,
+                  critic_lr_min=lr, cr_scheduler_steps=1, buffer_type="PER", max_len=max_len, alpha=per_alpha,
+                  batch_size=B, gamma=gamma, ac_update_freq=ac_update_freq, noise_std=0.2, noise_clamp=0.5,
+                  policy_noise=0.2, grad_clip=grad_clip, beta=beta, beta_end=beta_end, k_future=4, max_eps_len=50,
+                  tau=tau)
+    rng = np.random.default_rng(seed)
+    if algo in ("ddpg", "td3"):
+        cfg = utils_mod.BaseAgentConfig(**common)
+        cls = agent_mod.DDPG if algo == "ddpg" else agent_mod.TD3Agent
+        ag = cls(obs_dim=D, ac_dim=A, config=cfg, weights=None, nenvs=1, gradient_step=40)
+        nets = {"actor": ("base_net", O.init_mlp(rng, D, H, A, L))}
+        for tag in (("critic",) if algo == "ddpg" else ("critic_1", "critic_2")):
+            nets[tag] = ("net", O.init_mlp(rng, D + A, H, 1, L))
+        with torch.no_grad():
+            for tag, (pref, params) in nets.items():
+                sd = getattr(ag, tag).state_dict()
+                for i, (w, b) in enumerate(params):
+                    sd[f"{pref}.{2 * i}.weight"].copy_(torch.from_numpy(w))
+                    sd[f"{pref}.{2 * i}.bias"].copy_(torch.from_numpy(b))
+        final_tags = list(nets) + ["target_" + t for t in nets]
+    else:
+        cfg = utils_mod.SACAgentConfig(**common, alpha_lr=1e-2, alpha_min_steps=0)
+        cls = agent_mod.SACAgent if algo == "sac" else agent_mod.TQCAgent
+        ag = cls(obs_dim=D, ac_dim=A, config=cfg, weights=None, nenvs=1, gradient_step=gradient_step)
+        n = 2 if algo == "sac" else 5
+        actor0, _ = OS.init_sac_actor(rng, D, H, A, L, head_scale=0.1, log_std_bias=-1.0)
+        critics0 = [O.init_mlp(rng, D + A, H, 1, L) for _ in range(n)]
+        critics = [ag.critic_1, ag.critic_2] if algo == "sac" else list(ag.critics)
+        with torch.no_grad():
+            sd = ag.actor.state_dict()
+            for l in range(L):
+                sd[f"base_net.{3 * l}.weight"].copy_(torch.from_numpy(actor0[2 * l][0]))
+                sd[f"base_net.{3 * l}.bias"].copy_(torch.from_numpy(actor0[2 * l][1]))
+            sd["mean_head.weight"].copy_(torch.from_numpy(actor0[2 * L][0]))
+            sd["mean_head.bias"].copy_(torch.from_numpy(actor0[2 * L][1]))
+            sd["log_std_head.weight"].copy_(torch.from_numpy(actor0[2 * L + 1][0]))
+            sd["log_std_head.bias"].copy_(torch.from_numpy(actor0[2 * L + 1][1]))
+            for c, p0 in zip(critics, critics0):
+                sd = c.state_dict()
+                for i, (w, b) in enumerate(p0):
+                    sd[f"net.{2 * i}.weight"].copy_(torch.from_numpy(w))
+                    sd[f"net.{2 * i}.bias"].copy_(torch.from_numpy(b))
+        final_tags = None
+    ag.device = "cpu"
+    ag.buffer.device = "cpu"
+    ag.update_target_network()
+    assert type(ag.buffer).__name__ == "PERBuffer"
+
+    pushed = {k: [] for k in ("s", "a", "r", "ns", "d")}
+
+    def push(count):
+        for _ in range(count):
+            s = rng.standard_normal(D).astype(np.float32)
+            ns = (s + 0.1 * rng.standard_normal(D)).astype(np.float32)
+            a = rng.uniform(-1, 1, A).astype(np.float32)
+            r = np.float64(-float(rng.random() > 0.3))
+            d = np.bool_(rng.random() < 0.1)
+            ag.push(torch.from_numpy(s), a, r, torch.from_numpy(ns), d)       # the types src/env.py:226 hands over
+            for k, v in zip(("s", "a", "r", "ns", "d"), (s, a, np.float32(r), ns, np.float32(d))):
+                pushed[k].append(v)
+
+    out = {"meta": np.array([D, A, H, L, B, seed, ac_update_freq, gradient_step, max_len, n0, push_per_step, beta_end],
+                            np.int64),
+           "hp": np.array([gamma, tau, grad_clip, lr, per_alpha, beta], np.float64),
+           "steps": np.array(steps, np.int64)}
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    real_choice, real_normal, real_randn_like = np.random.choice, tdn._standard_normal, torch.randn_like
+    real_sample = ag.buffer.sample
+    push(n0)
+    for si, step in enumerate(steps):
+        if si:
+            push(push_per_step)
+        out[f"s{si}_prio_before"] = np.array(ag.buffer.priorities, dtype=np.float32)
+        out[f"s{si}_beta"] = np.float64(ag.beta)
+        rec = {"normal": []}
+
+        def choice(N, size, p=None):
+            st = np.random.get_state()
+            idx = real_choice(N, size, p=p)
+            after = np.random.get_state()
+            np.random.set_state(st)
+            rec["u"] = np.random.random_sample(size)
+            assert all(np.array_equal(x, y) for x, y in zip(np.random.get_state(), after)), "choice drew more"
+            rec["P"] = np.array(p, copy=True)
+            return idx
+
+        def sample(bs, b):
+            res = real_sample(bs, b)
+            rec["batch"] = [t.numpy().copy() for t in res[:5]]
+            rec["w"], rec["idx"] = res[5].numpy().copy(), np.asarray(res[6]).copy()
+            return res
+
+        def normal(*a_, **k_):
+            v = real_normal(*a_, **k_)
+            rec["normal"].append(v.numpy().copy())
+            return v
+
+        def randn_like(t, *a_, **k_):
+            v = real_randn_like(t, *a_, **k_)
+            rec["normal"].append(v.numpy().copy())
+            return v
+
+        np.random.choice, ag.buffer.sample = choice, sample
+        tdn._standard_normal, agent_mod.torch.randn_like = normal, randn_like
+        try:
+            info = ag.update(step)
+        finally:
+            np.random.choice, tdn._standard_normal, agent_mod.torch.randn_like = real_choice, real_normal, real_randn_like
+            ag.buffer.sample = real_sample
+        td_pos = {"ddpg": 2 if len(info) == 6 else 1, "td3": 3 if len(info) == 8 else 2}.get(algo, 3 if len(info) == 9 else 2)
+        td = np.asarray(info[td_pos], np.float32).reshape(B, 1)
+        flat = [float(np.mean(x)) if i == td_pos else float(x) for i, x in enumerate(info)]
+        out[f"s{si}_info"] = np.array(flat, np.float64)
+        out[f"s{si}_td"] = td
+        out[f"s{si}_u"], out[f"s{si}_P"] = rec["u"], rec["P"].astype(np.float32)
+        out[f"s{si}_idx"], out[f"s{si}_w"] = rec["idx"].astype(np.int64), rec["w"].astype(np.float32)
+        for key, val in zip(("s", "a", "r", "ns", "d"), rec["batch"]):
+            out[f"s{si}_batch_{key}"] = val
+        for j, v in enumerate(rec["normal"]):
+            out[f"s{si}_normal{j}"] = v
+        out[f"s{si}_n_normal"] = np.int64(len(rec["normal"]))
+        out[f"s{si}_prio_after"] = np.array(ag.buffer.priorities, dtype=np.float32)
+        if algo in ("sac", "tqc"):
+            out[f"s{si}_log_alpha"] = ag.log_alpha.detach().numpy().copy()
+    for k in pushed:
+        out["push_" + k] = np.stack(pushed[k]).astype(np.float32)
+    si = len(steps) - 1
+    if not store_final:
+        pass
+    elif final_tags is not None:
+        for tag in final_tags:
+            for k_, v in flat_params(getattr(ag, tag)).items():
+                out[f"s{si}_{tag}.{k_}"] = v
+    else:
+        tags = [("actor", ag.actor)]
+        if algo == "sac":
+            tags += [("critic_1", ag.critic_1), ("critic_2", ag.critic_2), ("target_critic_1", ag.target_critic_1),
+                     ("target_critic_2", ag.target_critic_2)]
+        else:
+            keep = (0, len(ag.critics) - 1)
+            tags += [(f"critic_{i}", c) for i, c in enumerate(ag.critics) if i in keep]
+            tags += [(f"target_critic_{i}", c) for i, c in enumerate(ag.target_critics) if i in keep]
+        for tag, net in tags:
+            for k_, v in flat_params(net).items():
+                out[f"s{si}_{tag}.{k_}"] = v
+    np.savez_compressed(os.path.join(HERE, f"per_{algo}_{name}.npz"), **out)
+    print(f"per_{algo}_{name}: {len(steps)} steps; len {len(ag.buffer)}; last info {out[f's{si}_info']}")
+
+
+def per_cases(agent_mod, utils_mod):
+    per_case(agent_mod, utils_mod, "ddpg", "reach_h64", D=10, A=3, H=64, L=3, B=64, max_len=500, n0=300,
+             push_per_step=90, steps=[38, 39, 40, 41, 42], seed=41, grad_clip=10.0)
+    per_case(agent_mod, utils_mod, "ddpg", "push_h256", D=21, A=3, H=256, L=3, B=256, max_len=3000, n0=3000,
+             push_per_step=7, steps=[39, 40, 41], seed=42, beta_end=41, ac_update_freq=2, store_final=False)
+    per_case(agent_mod, utils_mod, "td3", "push_h64", D=22, A=3, H=64, L=3, B=128, max_len=700, n0=400,
+             push_per_step=200, steps=[1, 2, 3, 4], seed=43, ac_update_freq=2)
+    per_case(agent_mod, utils_mod, "sac", "push_h64", D=22, A=3, H=64, L=3, B=128, max_len=700, n0=700,
+             push_per_step=50, steps=[1, 2, 3, 4], seed=44)
+    per_case(agent_mod, utils_mod, "tqc", "slide_h64", D=22, A=3, H=64, L=3, B=128, max_len=600, n0=200,
+             push_per_step=150, steps=[1, 2, 3], seed=45)
+
+
 def checkpoint_case(model_mod):
     """Load-compat + forward-differential fixture from the shipped Reach checkpoint
     (resources/DDPG/reach/{actor,critic}.pth: H=64, D=10, A=3)."""
@@ -460,6 +637,8 @@ def main():
     agent_mod, buffer_mod, model_mod, utils_mod = import_reference()
     if len(sys.argv) > 1 and sys.argv[1] == "sac":
         return sac_cases(agent_mod, utils_mod)
+    if len(sys.argv) > 1 and sys.argv[1] == "per":
+        return per_cases(agent_mod, utils_mod)
     td3_case(agent_mod, utils_mod, "push_h64", D=22, A=3, H=64, L=3, B=128, steps=[1, 2, 3, 4, 5], seed=21)
     td3_case(agent_mod, utils_mod, "pickplace_h256", D=23, A=4, H=256, L=2, B=200, steps=[7, 8, 9], seed=22,
              grad_clip=0.1, ac_update_freq=1, tau=0.005, policy_noise=0.3, noise_clamp=0.25)
@@ -488,6 +667,7 @@ def main():
               grad_clip=0.05, tau=0.005, store_weights=False)
     checkpoint_case(model_mod)
     sac_cases(agent_mod, utils_mod)
+    per_cases(agent_mod, utils_mod)
 
 
 if __name__ == "__main__":

@@ -113,3 +113,69 @@ def assert_sac_actor_close(params, ref_params, lr, nsteps):
             assert float(np.max(np.abs(np.asarray(b, np.float64) - rb))) <= 2.0 * lr * nsteps + 1e-6, ("actor bias", i)
         else:
             assert weights_close(b, rb, lr, nsteps), ("actor", i, rel_err(b, rb))
+
+
+# ---- prioritised replay fixtures (tests/golden/make_golden.py::per_case) --------------------------------
+PER_CASES = [("ddpg", "reach_h64"), ("ddpg", "push_h256"), ("td3", "push_h64"), ("sac", "push_h64"),
+             ("tqc", "slide_h64")]
+
+
+def per_meta(g):
+    keys = ("D", "A", "H", "L", "B", "seed", "freq", "gstep", "max_len", "n0", "push_per_step", "beta_end")
+    m = {k: int(v) for k, v in zip(keys, g["meta"])}
+    m.update({k: float(v) for k, v in zip(("gamma", "tau", "clip", "lr", "alpha", "beta"), g["hp"])})
+    return m
+
+
+def per_pushes(g, si):
+    """Row range [lo, hi) of the recorded push stream that the generator appended before step si."""
+    m = per_meta(g)
+    lo = 0 if si == 0 else m["n0"] + (si - 1) * m["push_per_step"]
+    return lo, m["n0"] + si * m["push_per_step"]
+
+
+def per_initial_nets(algo, g):
+    """Seeded initial parameters exactly as per_case drew them (before the push stream)."""
+    from oracle import ddpg as OD
+    from oracle import sac as OS
+    m = per_meta(g)
+    rng = np.random.default_rng(m["seed"])
+    D, A, H, L = m["D"], m["A"], m["H"], m["L"]
+    if algo in ("ddpg", "td3"):
+        nets = [OD.init_mlp(rng, D, H, A, L)]
+        nets += [OD.init_mlp(rng, D + A, H, 1, L) for _ in range(1 if algo == "ddpg" else 2)]
+        return nets
+    actor0, stats0 = OS.init_sac_actor(rng, D, H, A, L, head_scale=0.1, log_std_bias=-1.0)
+    critics0 = [OD.init_mlp(rng, D + A, H, 1, L) for _ in range(2 if algo == "sac" else 5)]
+    return actor0, stats0, critics0
+
+
+def per_oracle(algo, g):
+    """The update oracle of a PER fixture; ``step(step, batch, weights, normals)`` -> info tuple."""
+    from oracle import ddpg as OD
+    from oracle import sac as OS
+    from oracle import td3 as OT
+    m = per_meta(g)
+    kw = dict(gamma=m["gamma"], tau=m["tau"], grad_clip=m["clip"], actor_lr=m["lr"], critic_lr=m["lr"],
+              ac_update_freq=m["freq"])
+    nets = per_initial_nets(algo, g)
+    if algo == "ddpg":
+        orc = OD.DDPGOracle(*nets, **kw)
+        return orc, lambda step, b, w, nrm: orc.update_on_batch(step, *b, weights=w)
+    if algo == "td3":
+        orc = OT.TD3Oracle(*nets, policy_noise=0.2, noise_clamp=0.5, **kw)
+        return orc, lambda step, b, w, nrm: orc.update_on_batch(step, *b, nrm[0], weights=w)
+    orc = OS.SACOracle(algo, *nets, act_dim=m["A"], alpha_lr=1e-2, alpha_min_steps=0, gradient_step=m["gstep"], **kw)
+    return orc, lambda step, b, w, nrm: orc.update_on_batch(step, *b, nrm[0], nrm[1] if len(nrm) > 1 else None,
+                                                            weights=w)
+
+
+def per_td_position(algo, info_len):
+    return {"ddpg": 2 if info_len == 6 else 1, "td3": 3 if info_len == 8 else 2}.get(algo, 3 if info_len == 9 else 2)
+
+
+def ulp_diff_f32(a, b):
+    """Distance in float32 units in the last place (same-sign finite values)."""
+    a = np.ascontiguousarray(a, np.float32).view(np.int32).astype(np.int64)
+    b = np.ascontiguousarray(b, np.float32).view(np.int32).astype(np.int64)
+    return np.abs(a - b)

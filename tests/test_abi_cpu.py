@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_string():
     from gcrl_b200 import _lib
-    assert _lib.lib.gcrl_abi_version() == 2
+    assert _lib.lib.gcrl_abi_version() == 3
     assert isinstance(_lib.lib.gcrl_last_error(), bytes)
 
 
