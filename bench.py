@@ -616,6 +616,47 @@ def time_variants(args, data, E, max_len, dev, local, steps=60):
             del ag
         except Exception as e:   # noqa: BLE001
             out[name] = {"error": str(e)}
+    out.update(time_replay_variants(args, data, E, max_len, local))
+    return out
+
+
+def time_replay_variants(args, data, E, max_len, local, steps=100):
+    """DDPG.update(step) behind the two non-HER buffers (buffer_type "PER" / "REPLAY", src/agent.py:67-70) on the
+    raw transitions of the same synthetic episodes: prioritised draw through numpy.random.choice's exact
+    arithmetic + importance-weighted critic loss + priority write-back, and the uniform random.sample draw.
+    Wall clock per synchronous update, metric read-back included."""
+    import torch
+    from gcrl_b200 import DDPG
+    out = {}
+    for name, btype in (("ddpg_per", "PER"), ("ddpg_replay", "REPLAY")):
+        try:
+            cfg = agent_config(args, max_len)
+            cfg.buffer_type, cfg.alpha, cfg.beta, cfg.beta_end = btype, 0.6, 0.4, 10000
+            torch.manual_seed(1898)
+            np.random.seed(1898)
+            ag = DDPG(args.obs + args.goal, args.act, cfg, None, 1, 40, device=local)
+            n_ep = min(E, max_len // 50)
+            for lo in range(0, n_ep, 256):
+                hi = min(n_ep, lo + 256)
+                cat = lambda k: np.concatenate([data[k][e] for e in range(lo, hi)])     # noqa: E731
+                ag.buffer.push_rows(cat("s"), cat("a"), cat("r"), cat("ns"), cat("d"))
+            for i in range(40):          # the priorities move away from 1.0: the cumsum starts to round
+                ag.update(i + 1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(steps):
+                info = ag.update(41 + i)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            assert np.isfinite(float(info[0]))
+            rec = {"updates_per_s": steps / dt, "ms_per_update": dt / steps * 1e3, "batch": args.batch,
+                   "entries": len(ag.buffer)}
+            if btype == "PER":
+                rec["cumsum_additions_round"] = bool(ag.buffer.last_sample_info()[1])
+            out[name] = rec
+            del ag
+        except Exception as e:   # noqa: BLE001
+            out[name] = {"error": str(e)}
     return out
 
 

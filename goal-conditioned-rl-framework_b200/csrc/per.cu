@@ -23,8 +23,8 @@
 //     when all of them are integer multiples of 2^-52 (true whenever P[i] >= 2^-29, i.e. for all but extreme
 //     priority ratios) and the total is below 2, every partial sum in ANY order is exactly representable: the
 //     kernels then scan the values as int64 fixed point (units of 2^-52) and the result provably equals the
-//     sequential one.  If one element fails the test, a flag routes the call to a single-thread sequential
-//     float64 chain (slow -- about 4 ns per entry -- but exact);
+//     sequential one.  If one element fails the test, a flag routes the call to the general path further down
+//     (the rounding of every addition tracked exactly, still in parallel);
 //   * cdf /= cdf[-1]: IEEE float64 division; searchsorted(side="right"): count of entries <= u.
 // float32 power (importance weights, new priorities) is computed as float(pow(double)) -- within an ulp of
 // any libm / SIMD powf the reference may run on (prioritised replay).
@@ -215,27 +215,227 @@ cdf_from_fixed_kernel(int64_t *__restrict__ fixed, const int64_t *__restrict__ t
   }
 }
 
-// fallback: the reference's left-to-right float64 chain, one thread (loads run ahead of the chain)
-__global__ void seq_cumsum_kernel(const float *__restrict__ pnorm, double *__restrict__ cdf, int64_t n,
-                                  double *__restrict__ last, const int *__restrict__ flags) {
-  if (!(*flags & 1) || threadIdx.x != 0) return;
-  double c = 0.0;
-  int64_t i = 0;
-  for (; i + 8 <= n; i += 8) {
-    float p[8];
+// ---- inexact case: the reference's left-to-right float64 chain, reproduced in parallel ---------------
+// c_i = RN(c_{i-1} + p_i).  While c stays inside one binade [2^k, 2^(k+1)) it is an integer multiple of
+// u = 2^(k-52), and adding p = (a + f) u  (a integer, 0 <= f < 1) rounds to c + a u (f < 1/2), c + (a + 1) u
+// (f > 1/2) or, on a tie (f == 1/2 -- by far the most common inexact case for float32 inputs), to whichever of
+// the two is an even multiple of u.  So one element is a function {parity of c / u} -> (increment in units of
+// u, new parity), these functions compose associatively, and a chunk of elements collapses to two integer
+// increments and two outgoing parities.  Phase A summarises every 512-element chunk for the binade its
+// incoming value is expected in (from the truncated fixed-point scan); phase B walks the chunk summaries in
+// order with the true running value -- one exact addition per chunk -- and processes the few chunks the
+// summary does not cover (binade crossings, about one per power of two) element by element; phase C expands
+// the summarised chunks in parallel.  Every value written is exactly the sequential one.
+constexpr int kChunk = 512;
+constexpr int kChunkPerLane = kChunk / 32;
+
+struct __align__(8) ChunkSum {
+  int64_t d0, d1;      // increment in units of u for incoming parity 0 / 1
+  int k;               // binade of the incoming value the summary was built for
+  int bits;            // bit0 / bit1: outgoing parity for incoming parity 0 / 1; bit2: summary valid
+};
+
+struct ParityFn {
+  int64_t d0, d1;
+  int o;               // bit0: outgoing parity for incoming parity 0, bit1: for incoming parity 1
+};
+
+__device__ __forceinline__ ParityFn fn_compose(const ParityFn &A, const ParityFn &B) {   // A first, then B
+  ParityFn r;
+  const bool a0 = A.o & 1, a1 = (A.o >> 1) & 1;
+  r.d0 = A.d0 + (a0 ? B.d1 : B.d0);
+  r.d1 = A.d1 + (a1 ? B.d1 : B.d0);
+  const int o0 = a0 ? (B.o >> 1) & 1 : B.o & 1;
+  const int o1 = a1 ? (B.o >> 1) & 1 : B.o & 1;
+  r.o = o0 | (o1 << 1);
+  return r;
+}
+
+// p = q u with q = p * scale (scale = 1 / u, a power of two: exact); q has at most 24 significant bits
+__device__ __forceinline__ ParityFn fn_element(float p, double scale, bool &bad) {
+  const double q = double(p) * scale;
+  ParityFn r;
+  if (!(q < kTwo53)) { bad = true; r.d0 = r.d1 = 0; r.o = 2; return r; }
+  const double a = floor(q), f = q - a;
+  const int64_t ai = int64_t(a);
+  if (f == 0.5) {                    // tie: the even neighbour, whatever it takes
+    r.d0 = ai + (ai & 1);
+    r.d1 = ai + ((ai + 1) & 1);
+    r.o = 0;
+  } else {
+    const int64_t d = ai + (f > 0.5 ? 1 : 0);
+    r.d0 = r.d1 = d;
+    r.o = int(d & 1) | (int((d + 1) & 1) << 1);
+  }
+  return r;
+}
+
+__device__ __forceinline__ int64_t shfl_i64(int64_t v, int src) {
+  int lo = int(uint32_t(uint64_t(v))), hi = int(uint32_t(uint64_t(v) >> 32));
+  lo = __shfl_sync(0xffffffffu, lo, src);
+  hi = __shfl_sync(0xffffffffu, hi, src);
+  return int64_t((uint64_t(uint32_t(hi)) << 32) | uint32_t(lo));
+}
+
+__device__ __forceinline__ double pow2(int e) { return __longlong_as_double(int64_t(1023 + e) << 52); }
+__device__ __forceinline__ int binade_of(double c) { return int((__double_as_longlong(c) >> 52) & 0x7ff) - 1023; }
+
+// lane-local fold of the lane's 16 elements + inclusive scan over the warp; returns the lane's inclusive
+// function, *excl = the function of everything before the lane's first element
+__device__ __forceinline__ ParityFn chunk_scan(const float (&p)[kChunkPerLane], double scale, int lane, ParityFn *excl,
+                                               bool *bad_out) {
+  bool bad = false;
+  ParityFn acc = fn_element(p[0], scale, bad);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) p[j] = pnorm[i + j];
+  for (int j = 1; j < kChunkPerLane; ++j) acc = fn_compose(acc, fn_element(p[j], scale, bad));
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      c = __dadd_rn(c, double(p[j]));
-      cdf[i + j] = c;
+  for (int d = 1; d < 32; d <<= 1) {
+    ParityFn o;
+    o.d0 = shfl_up_i64(acc.d0, d);
+    o.d1 = shfl_up_i64(acc.d1, d);
+    o.o = __shfl_up_sync(0xffffffffu, acc.o, d);
+    if (lane >= d) acc = fn_compose(o, acc);
+  }
+  ParityFn e;
+  e.d0 = shfl_up_i64(acc.d0, 1);
+  e.d1 = shfl_up_i64(acc.d1, 1);
+  e.o = __shfl_up_sync(0xffffffffu, acc.o, 1);
+  if (lane == 0) { e.d0 = e.d1 = 0; e.o = 2; }
+  *excl = e;
+  *bad_out = __any_sync(0xffffffffu, bad);
+  return acc;
+}
+
+__device__ __forceinline__ void load_chunk(const float *__restrict__ pnorm, int64_t i0, int64_t n, int lane,
+                                           float (&p)[kChunkPerLane]) {
+  const int64_t base = i0 + lane * kChunkPerLane;
+#pragma unroll
+  for (int j = 0; j < kChunkPerLane; ++j) p[j] = base + j < n ? pnorm[base + j] : 0.0f;
+}
+
+__global__ void __launch_bounds__(256)
+chunk_summary_kernel(const float *__restrict__ pnorm, const int64_t *__restrict__ fixed,
+                     const int64_t *__restrict__ tile_off, int64_t n, int n_chunks, ChunkSum *__restrict__ sums,
+                     const int *__restrict__ flags) {
+  if (!(*flags & 1)) return;
+  const int lane = threadIdx.x & 31;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (j >= n_chunks) return;
+  const int64_t i0 = int64_t(j) * kChunk;
+  double approx = 0.0;                               // truncated fixed-point prefix: the binade guess only
+  if (i0 > 0) approx = double(fixed[i0 - 1] + tile_off[(i0 - 1) / kScanTile]) / kTwo52;
+  ChunkSum s;
+  s.d0 = s.d1 = 0; s.k = 0; s.bits = 0;
+  const int k = approx > 0.0 ? binade_of(approx) : -2000;
+  if (k > -900 && k < 900) {
+    float p[kChunkPerLane];
+    load_chunk(pnorm, i0, n, lane, p);
+    ParityFn excl;
+    bool bad;
+    const ParityFn incl = chunk_scan(p, pow2(52 - k), lane, &excl, &bad);
+    s.d0 = shfl_i64(incl.d0, 31);
+    s.d1 = shfl_i64(incl.d1, 31);
+    s.k = k;
+    s.bits = __shfl_sync(0xffffffffu, incl.o, 31) | (bad ? 0 : 4);
+  }
+  if (lane == 0) sums[j] = s;
+}
+
+constexpr int kWalkBatch = 512;       // chunk summaries staged in shared memory per refill
+
+__global__ void __launch_bounds__(32)
+chunk_walk_kernel(const float *__restrict__ pnorm, double *__restrict__ cdf, int64_t n, int n_chunks,
+                  const ChunkSum *__restrict__ sums, double *__restrict__ cin, unsigned char *__restrict__ expand,
+                  double *__restrict__ last, const int *__restrict__ flags) {
+  if (!(*flags & 1)) return;
+  __shared__ double sbuf[kChunk];
+  __shared__ ChunkSum ssum[kWalkBatch];
+  __shared__ double scin[kWalkBatch];
+  __shared__ unsigned char sexp[kWalkBatch];
+  const int lane = threadIdx.x;
+  double c = 0.0;                                    // every lane carries the same running value
+  for (int j0 = 0; j0 < n_chunks; j0 += kWalkBatch) {
+    const int nb = min(kWalkBatch, n_chunks - j0);
+    for (int t = lane; t < nb; t += 32) ssum[t] = sums[j0 + t];
+    __syncwarp();
+    // per chunk, prepared off the dependent chain: the binade [lo, hi) the summary holds for (empty when the
+    // summary is invalid) and the two increments as doubles; the chain itself is compare, select, add, compare
+    struct Step { double lo, hi, inc0, inc1; };
+    auto prepare = [&](int jj) {
+      const ChunkSum q = ssum[min(jj, nb - 1)];
+      Step st;
+      const bool valid = (q.bits & 4) != 0;
+      st.lo = valid ? pow2(q.k) : 1.0;
+      st.hi = valid ? pow2(q.k + 1) : 0.0;
+      const double u = valid ? pow2(q.k - 52) : 0.0;
+      st.inc0 = double(q.d0) * u;
+      st.inc1 = double(q.d1) * u;
+      return st;
+    };
+    Step s = prepare(0);
+    for (int jj = 0; jj < nb; ++jj) {
+      const Step nxt = prepare(jj + 1);
+      const double inc = (__double_as_longlong(c) & 1) ? s.inc1 : s.inc0;   // parity of c / u
+      const double c_new = __dadd_rn(c, inc);                               // exact while it stays in the binade
+      const bool ok = c >= s.lo && c < s.hi && c_new < s.hi;
+      if (lane == 0) { scin[jj] = c; sexp[jj] = ok ? 1 : 0; }
+      if (ok) {
+        c = c_new;
+      } else {                                       // binade crossing (or the very first chunk): the plain chain
+        const int64_t i0 = int64_t(j0 + jj) * kChunk;
+        for (int t = lane; t < kChunk; t += 32) sbuf[t] = i0 + t < n ? double(pnorm[i0 + t]) : 0.0;
+        __syncwarp();
+        if (lane == 0) {
+          double cc = c;
+#pragma unroll 8
+          for (int t = 0; t < kChunk; ++t) {
+            cc = __dadd_rn(cc, sbuf[t]);
+            sbuf[t] = cc;
+          }
+        }
+        __syncwarp();
+        c = sbuf[kChunk - 1];
+        for (int t = lane; t < kChunk; t += 32)
+          if (i0 + t < n) cdf[i0 + t] = sbuf[t];
+        __syncwarp();
+      }
+      s = nxt;
     }
+    __syncwarp();
+    for (int t = lane; t < nb; t += 32) { cin[j0 + t] = scin[t]; expand[j0 + t] = sexp[t]; }
+    __syncwarp();
   }
-  for (; i < n; ++i) {
-    c = __dadd_rn(c, double(pnorm[i]));
-    cdf[i] = c;
+  if (lane == 0) *last = c;
+}
+
+__global__ void __launch_bounds__(256)
+chunk_expand_kernel(const float *__restrict__ pnorm, double *__restrict__ cdf, int64_t n, int n_chunks,
+                    const ChunkSum *__restrict__ sums, const double *__restrict__ cin,
+                    const unsigned char *__restrict__ expand, const int *__restrict__ flags) {
+  if (!(*flags & 1)) return;
+  const int lane = threadIdx.x & 31;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (j >= n_chunks || !expand[j]) return;
+  const int64_t i0 = int64_t(j) * kChunk;
+  const int k = sums[j].k;
+  const double c0 = cin[j], scale = pow2(52 - k), u = pow2(k - 52);
+  float p[kChunkPerLane];
+  load_chunk(pnorm, i0, n, lane, p);
+  ParityFn excl;
+  bool bad;
+  chunk_scan(p, scale, lane, &excl, &bad);
+  const bool odd_in = __double_as_longlong(c0) & 1;
+  int64_t off = odd_in ? excl.d1 : excl.d0;                          // units of u before the lane's first element
+  int par = odd_in ? (excl.o >> 1) & 1 : excl.o & 1;
+  const int64_t base = i0 + lane * kChunkPerLane;
+#pragma unroll
+  for (int t = 0; t < kChunkPerLane; ++t) {
+    bool b2 = false;
+    const ParityFn f = fn_element(p[t], scale, b2);
+    off += par ? f.d1 : f.d0;
+    par = par ? (f.o >> 1) & 1 : f.o & 1;
+    if (base + t < n) cdf[base + t] = __dadd_rn(c0, double(off) * u);
   }
-  *last = c;
 }
 
 __global__ void cdf_divide_kernel(double *__restrict__ cdf, int64_t n, const double *__restrict__ last,
@@ -357,6 +557,9 @@ struct gcrl_replay {
   int64_t *fixed = nullptr;          // int64 fixed point, then the float64 table in place
   int64_t *tile_sum = nullptr, *d_total = nullptr;
   double *d_last = nullptr;
+  void *d_chunk_sums = nullptr;      // ChunkSum[n_chunks]
+  double *d_chunk_in = nullptr;
+  unsigned char *d_chunk_expand = nullptr;
   float *d_psum = nullptr;
   int *d_flags = nullptr, *winner = nullptr;
   // pairwise-sum tree of the current N
@@ -480,6 +683,12 @@ int gcrl_replay_create(gcrl_replay **out, int device, int64_t capacity, int stat
       h->tile_sum = dev_alloc<int64_t>(size_t(capacity / kScanTile + 2));
       h->d_total = dev_alloc<int64_t>(1);
       h->d_last = dev_alloc<double>(1);
+      {
+        const size_t nc = size_t(capacity / kChunk + 2);
+        h->d_chunk_sums = dev_alloc<ChunkSum>(nc);
+        h->d_chunk_in = dev_alloc<double>(nc);
+        h->d_chunk_expand = dev_alloc<unsigned char>(nc);
+      }
       h->d_psum = dev_alloc<float>(1);
       h->d_flags = dev_alloc<int>(1);
       h->winner = dev_alloc<int>(size_t(capacity));
@@ -503,7 +712,7 @@ int gcrl_replay_destroy(gcrl_replay *h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   for (void *p : {(void *)h->g.rows, (void *)h->g.prio, (void *)h->pnorm, (void *)h->fixed, (void *)h->tile_sum,
-                  (void *)h->d_total, (void *)h->d_last, (void *)h->d_psum, (void *)h->d_flags, (void *)h->winner,
+                  (void *)h->d_total, (void *)h->d_last, h->d_chunk_sums, (void *)h->d_chunk_in, (void *)h->d_chunk_expand, (void *)h->d_psum, (void *)h->d_flags, (void *)h->winner,
                   (void *)h->d_leaf_off, (void *)h->d_node_l, (void *)h->d_node_r, (void *)h->d_group_off,
                   (void *)h->d_vals, (void *)h->d_u, (void *)h->d_wraw, (void *)h->d_pos, (void *)h->d_slot})
     if (p) cudaFree(p);
@@ -599,8 +808,19 @@ int gcrl_replay_sample_prioritized(gcrl_replay *h, int64_t B, const double *u_ho
   cdf_from_fixed_kernel<<<tiles, kScanThreads, 0, st>>>(h->fixed, h->tile_sum, h->d_total, n, h->d_flags);
   GCRL_LAUNCHED();
   double *cdf = reinterpret_cast<double *>(h->fixed);
-  seq_cumsum_kernel<<<1, 32, 0, st>>>(h->pnorm, cdf, n, h->d_last, h->d_flags);
-  GCRL_LAUNCHED();
+  {   // inexact additions: summarise the chunks, walk them in order, expand (all three return at once otherwise)
+    const int n_chunks = blocks_for(n, kChunk);
+    ChunkSum *sums = static_cast<ChunkSum *>(h->d_chunk_sums);
+    chunk_summary_kernel<<<blocks_for(int64_t(n_chunks) * 32, 256), 256, 0, st>>>(h->pnorm, h->fixed, h->tile_sum, n, n_chunks,
+                                                                               sums, h->d_flags);
+    GCRL_LAUNCHED();
+    chunk_walk_kernel<<<1, 32, 0, st>>>(h->pnorm, cdf, n, n_chunks, sums, h->d_chunk_in, h->d_chunk_expand, h->d_last,
+                                        h->d_flags);
+    GCRL_LAUNCHED();
+    chunk_expand_kernel<<<blocks_for(int64_t(n_chunks) * 32, 256), 256, 0, st>>>(h->pnorm, cdf, n, n_chunks, sums,
+                                                                              h->d_chunk_in, h->d_chunk_expand, h->d_flags);
+    GCRL_LAUNCHED();
+  }
   cdf_divide_kernel<<<std::min(tiles, sm_count() * 8), 256, 0, st>>>(cdf, n, h->d_last, h->d_flags);
   GCRL_LAUNCHED();
   per_draw_kernel<<<blocks_for(B * 32, 256), 256, 0, st>>>(h->g, start, n, cdf, h->pnorm, h->d_u, int(B), float(-beta),

@@ -394,8 +394,8 @@ int gcrl_replay_get_priorities(gcrl_replay *h, float *prio_host, void *stream);
 int gcrl_replay_set_priorities(gcrl_replay *h, const float *prio_host, int64_t n, void *stream);
 /* stored rows [first, first + n) in deque order, packed host rows (tests, checkpoints) */
 int gcrl_replay_get_rows(gcrl_replay *h, int64_t first, int64_t n, float *rows_host, void *stream);
-/* Of the last sample_prioritized: the float32 priority sum, and whether the float64 cumsum took the
- * sequential fallback (1) or the order-independent fixed-point scan (0). */
+/* Of the last sample_prioritized: the float32 priority sum, and whether the float64 cumsum had additions that
+ * round (1: every rounding tracked, per.cu) or none (0: order-independent fixed-point scan). */
 int gcrl_replay_last_sample_info(gcrl_replay *h, float *priority_sum, int *sequential_cumsum, void *stream);
 /* The deque positions drawn by the last sample_prioritized (what the reference returns as `indices`). */
 int gcrl_replay_last_positions(gcrl_replay *h, int64_t B, int64_t *idx_host, void *stream);

@@ -2,7 +2,9 @@
 and the fixtures dumped from the unmodified reference (tests/golden/make_golden.py::per_case).
 
 Bit-exact: the float32 priority sum, P, the float64 table, the drawn positions, the gathered rows, FIFO eviction.
-2 ulp of float32: importance weights and new priorities (platform powf, see oracle/per.py).
+float32 power goes through the platform's powf in the reference (libm or a SIMD library, depending on the host
+CPU; see oracle/per.py), so: new priorities 2 ulp of float32; importance weights 4 ulp (a quotient of two powers,
+each within an ulp of the correctly rounded value).
 fp32 tolerance (rel 2e-5 + 1e-6 on metrics, tests.helpers.weights_close on weights): the weighted updates."""
 import random
 import types
@@ -67,37 +69,60 @@ def test_prioritised_draw_is_bit_exact(n, cap, B):
         want_sum, want_P, want_cdf, want_idx, want_w = numpy_reference_draw(prio, u, beta)
         got_sum, sequential = buf.last_sample_info()
         assert bits(got_sum) == bits(want_sum)
-        assert not sequential
+        # order-independent scan whenever every P[i] is a multiple of 2^-52 (always, if min P >= 2^-29)
+        assert sequential == bool(np.any(np.mod(want_P.astype(np.float64) * 2.0 ** 52, 1.0) != 0))
+        assert not sequential or N >= 100000
         got_P, got_cdf = buf.last_tables()
         assert np.array_equal(bits(got_P), bits(want_P))
         assert np.array_equal(got_cdf.view(np.uint64), want_cdf.view(np.uint64))
         assert np.array_equal(idx, want_idx)
         got = packed(s.cpu().numpy(), a.cpu().numpy(), r.cpu().numpy()[:, 0], ns.cpu().numpy(), d.cpu().numpy()[:, 0])
         assert np.array_equal(bits(got), bits(live[want_idx]))
-        assert ulp_diff_f32(w.cpu().numpy()[:, 0], want_w).max() <= 2
+        assert ulp_diff_f32(w.cpu().numpy()[:, 0], want_w).max() <= 4
     if N <= 5000:                                        # the restated rules agree too (pure-Python loops)
         assert np.array_equal(OP.choice_indices(OP.normalised_priorities(prio), u), want_idx)
 
 
-@pytest.mark.parametrize("n", [700, 40000])
-def test_extreme_priority_ratios_take_the_sequential_chain_and_stay_exact(n):
-    """P[i] below 2^-29 with a full mantissa is not a multiple of 2^-52: the float64 additions of the reference's
-    cumsum round, a reordered scan would differ, and the library must fall back to the left-to-right chain."""
+def _priorities(kind, n, rng):
+    if kind == "loguniform":                 # 15 decades: most additions of the float64 cumsum round
+        return (10.0 ** rng.uniform(-14, 1, n)).astype(np.float32)
+    if kind == "ties":                       # few mantissa bits, wide exponents: exact half-ulp ties everywhere
+        return (rng.integers(1, 8, n) * 2.0 ** rng.integers(-40, 3, n)).astype(np.float32)
+    if kind == "spikes":                     # single elements that jump several binades at once
+        p = np.full(n, 1e-9, np.float32) * rng.uniform(0.5, 1.5, n).astype(np.float32)
+        p[rng.integers(0, n, max(3, n // 5000))] = rng.uniform(0.5, 2.0, max(3, n // 5000))
+        return p
+    if kind == "zeros":                      # empty entries: repeated table values
+        p = (10.0 ** rng.uniform(-12, 0, n)).astype(np.float32)
+        p[rng.random(n) < 0.3] = 0.0
+        p[0] = 0.0
+        return p
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["loguniform", "ties", "spikes", "zeros"])
+@pytest.mark.parametrize("n", [700, 40000, 300001])
+def test_rounding_cumsum_is_reproduced_exactly(kind, n):
+    """P[i] that is not a multiple of 2^-52 (below 2^-29 with a full mantissa): the float64 additions of the
+    reference's left-to-right cumsum round -- mostly as exact ties -- and a reordered scan would differ.  The
+    library must notice and track every rounding (per.cu: parity functions per 512-entry chunk)."""
     from gcrl_b200 import PERBuffer
     rng = np.random.default_rng(n)
     buf = PERBuffer(n, 0.6)
     buf.push_rows(*rand_rows(rng, n, 4, 2))
-    prio = (10.0 ** rng.uniform(-14, 1, n)).astype(np.float32)
+    prio = _priorities(kind, n, rng)
     buf.set_priorities(prio)
     u = rng.random(512)
     *_, idx = buf.sample(512, 0.5, uniforms=u)
     want_sum, want_P, want_cdf, want_idx, _ = numpy_reference_draw(prio, u, 0.5)
-    got_sum, sequential = buf.last_sample_info()
-    assert sequential
+    got_sum, inexact = buf.last_sample_info()
+    assert inexact == bool(np.any(np.mod(want_P.astype(np.float64) * 2.0 ** 52, 1.0) != 0))
+    assert inexact or kind == "spikes"
     assert bits(got_sum) == bits(want_sum)
     got_P, got_cdf = buf.last_tables()
     assert np.array_equal(bits(got_P), bits(want_P))
-    assert np.array_equal(got_cdf.view(np.uint64), want_cdf.view(np.uint64))
+    bad = np.nonzero(got_cdf.view(np.uint64) != want_cdf.view(np.uint64))[0]
+    assert bad.size == 0, (bad[:5], got_cdf[bad[:5]], want_cdf[bad[:5]])
     assert np.array_equal(idx, want_idx)
 
 
@@ -206,7 +231,7 @@ def test_per_buffer_matches_reference_fixture(algo, case):
         assert np.array_equal(bits(buf.last_tables()[0]), bits(g[f"s{si}_P"]))
         for got, key in zip((s, a, r, ns, d), ("s", "a", "r", "ns", "d")):
             assert np.array_equal(bits(got.cpu().numpy()), bits(g[f"s{si}_batch_{key}"])), key
-        assert ulp_diff_f32(w.cpu().numpy(), g[f"s{si}_w"]).max() <= 2
+        assert ulp_diff_f32(w.cpu().numpy(), g[f"s{si}_w"]).max() <= 4
         buf.update_priorities(idx, g[f"s{si}_td"])
         assert ulp_diff_f32(buf.priorities, g[f"s{si}_prio_after"]).max() <= 2
 
