@@ -343,6 +343,10 @@ chunk_summary_kernel(const float *__restrict__ pnorm, const int64_t *__restrict_
 
 constexpr int kWalkBatch = 512;       // chunk summaries staged in shared memory per refill
 
+// One warp.  Up to 32 chunk summaries at a time: a warp scan of the composed parity functions gives every chunk's
+// incoming value in one step, and the longest prefix that keeps the running value inside its binade is
+// accepted; the chunk in which the value crosses a power of two (about one per binade) is chained element by
+// element from shared memory.
 __global__ void __launch_bounds__(32)
 chunk_walk_kernel(const float *__restrict__ pnorm, double *__restrict__ cdf, int64_t n, int n_chunks,
                   const ChunkSum *__restrict__ sums, double *__restrict__ cin, unsigned char *__restrict__ expand,
@@ -358,30 +362,43 @@ chunk_walk_kernel(const float *__restrict__ pnorm, double *__restrict__ cdf, int
     const int nb = min(kWalkBatch, n_chunks - j0);
     for (int t = lane; t < nb; t += 32) ssum[t] = sums[j0 + t];
     __syncwarp();
-    // per chunk, prepared off the dependent chain: the binade [lo, hi) the summary holds for (empty when the
-    // summary is invalid) and the two increments as doubles; the chain itself is compare, select, add, compare
-    struct Step { double lo, hi, inc0, inc1; };
-    auto prepare = [&](int jj) {
-      const ChunkSum q = ssum[min(jj, nb - 1)];
-      Step st;
-      const bool valid = (q.bits & 4) != 0;
-      st.lo = valid ? pow2(q.k) : 1.0;
-      st.hi = valid ? pow2(q.k + 1) : 0.0;
-      const double u = valid ? pow2(q.k - 52) : 0.0;
-      st.inc0 = double(q.d0) * u;
-      st.inc1 = double(q.d1) * u;
-      return st;
-    };
-    Step s = prepare(0);
-    for (int jj = 0; jj < nb; ++jj) {
-      const Step nxt = prepare(jj + 1);
-      const double inc = (__double_as_longlong(c) & 1) ? s.inc1 : s.inc0;   // parity of c / u
-      const double c_new = __dadd_rn(c, inc);                               // exact while it stays in the binade
-      const bool ok = c >= s.lo && c < s.hi && c_new < s.hi;
-      if (lane == 0) { scin[jj] = c; sexp[jj] = ok ? 1 : 0; }
-      if (ok) {
-        c = c_new;
-      } else {                                       // binade crossing (or the very first chunk): the plain chain
+    for (int g0 = 0; g0 < nb;) {
+      // ---- fast: the longest run of chunks (up to 32) that keeps c inside its current binade ----
+      const bool live = g0 + lane < nb;
+      const ChunkSum q = ssum[min(g0 + lane, nb - 1)];
+      const int k0 = __shfl_sync(0xffffffffu, q.k, 0);
+      const double lo = pow2(k0), hi = pow2(k0 + 1), u = pow2(k0 - 52);
+      const unsigned same = __ballot_sync(0xffffffffu, live && (q.bits & 4) && q.k == k0);
+      int m = 0;
+      ParityFn acc;
+      acc.d0 = q.d0; acc.d1 = q.d1; acc.o = q.bits & 3;
+      if (!((same >> lane) & 1)) { acc.d0 = acc.d1 = 0; acc.o = 2; }   // never accepted; keeps the scan defined
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        ParityFn o;
+        o.d0 = shfl_up_i64(acc.d0, d);
+        o.d1 = shfl_up_i64(acc.d1, d);
+        o.o = __shfl_up_sync(0xffffffffu, acc.o, d);
+        if (lane >= d) acc = fn_compose(o, acc);
+      }
+      const bool odd = __double_as_longlong(c) & 1;                    // parity of c / u
+      const int64_t d_incl = odd ? acc.d1 : acc.d0;
+      int64_t d_excl = shfl_up_i64(d_incl, 1);
+      if (lane == 0) d_excl = 0;
+      const double c_out = __dadd_rn(c, double(d_incl) * u);          // exact while below hi (increments >= 0)
+      const unsigned inside = __ballot_sync(0xffffffffu, c_out < hi);
+      if ((same & 1) && k0 > -900 && c >= lo && c < hi) m = __ffs(~(same & inside)) - 1;   // leading ones
+      if (m < 0) m = 32;
+      if (m > 0) {
+        if (lane < m) { scin[g0 + lane] = __dadd_rn(c, double(d_excl) * u); sexp[g0 + lane] = 1; }
+        c = __shfl_sync(0xffffffffu, c_out, m - 1);
+        g0 += m;
+        continue;
+      }
+      // ---- the chunk in which c leaves its binade (or the very first one): the plain chain ----
+      {
+        const int jj = g0;
+        if (lane == 0) { scin[jj] = c; sexp[jj] = 0; }
         const int64_t i0 = int64_t(j0 + jj) * kChunk;
         for (int t = lane; t < kChunk; t += 32) sbuf[t] = i0 + t < n ? double(pnorm[i0 + t]) : 0.0;
         __syncwarp();
@@ -398,8 +415,8 @@ chunk_walk_kernel(const float *__restrict__ pnorm, double *__restrict__ cdf, int
         for (int t = lane; t < kChunk; t += 32)
           if (i0 + t < n) cdf[i0 + t] = sbuf[t];
         __syncwarp();
+        g0 += 1;
       }
-      s = nxt;
     }
     __syncwarp();
     for (int t = lane; t < nb; t += 32) { cin[j0 + t] = scin[t]; expand[j0 + t] = sexp[t]; }
