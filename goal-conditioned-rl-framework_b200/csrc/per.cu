@@ -346,13 +346,12 @@ constexpr int kWalkBatch = 512;       // chunk summaries staged in shared memory
 // One warp.  Up to 32 chunk summaries at a time: a warp scan of the composed parity functions gives every chunk's
 // incoming value in one step, and the longest prefix that keeps the running value inside its binade is
 // accepted; the chunk in which the value crosses a power of two (about one per binade) is chained element by
-// element from shared memory.
+// element through the lanes' registers.
 __global__ void __launch_bounds__(32)
 chunk_walk_kernel(const float *__restrict__ pnorm, double *__restrict__ cdf, int64_t n, int n_chunks,
                   const ChunkSum *__restrict__ sums, double *__restrict__ cin, unsigned char *__restrict__ expand,
                   double *__restrict__ last, const int *__restrict__ flags) {
   if (!(*flags & 1)) return;
-  __shared__ double sbuf[kChunk];
   __shared__ ChunkSum ssum[kWalkBatch];
   __shared__ double scin[kWalkBatch];
   __shared__ unsigned char sexp[kWalkBatch];
@@ -396,25 +395,29 @@ chunk_walk_kernel(const float *__restrict__ pnorm, double *__restrict__ cdf, int
         continue;
       }
       // ---- the chunk in which c leaves its binade (or the very first one): the plain chain ----
+      // lane l holds elements [16 l, 16 l + 16) in registers; the running value visits the lanes in order
+      // (one shuffle per lane), so the dependent chain is 512 register-to-register additions
       {
         const int jj = g0;
         if (lane == 0) { scin[jj] = c; sexp[jj] = 0; }
         const int64_t i0 = int64_t(j0 + jj) * kChunk;
-        for (int t = lane; t < kChunk; t += 32) sbuf[t] = i0 + t < n ? double(pnorm[i0 + t]) : 0.0;
-        __syncwarp();
-        if (lane == 0) {
-          double cc = c;
-#pragma unroll 8
-          for (int t = 0; t < kChunk; ++t) {
-            cc = __dadd_rn(cc, sbuf[t]);
-            sbuf[t] = cc;
+        float p[kChunkPerLane];
+        load_chunk(pnorm, i0, n, lane, p);
+        double v[kChunkPerLane];
+#pragma unroll 1
+        for (int l = 0; l < 32; ++l) {
+          double t = c;
+#pragma unroll
+          for (int e = 0; e < kChunkPerLane; ++e) {
+            t = __dadd_rn(t, double(p[e]));
+            if (lane == l) v[e] = t;
           }
+          c = __shfl_sync(0xffffffffu, t, l);
         }
-        __syncwarp();
-        c = sbuf[kChunk - 1];
-        for (int t = lane; t < kChunk; t += 32)
-          if (i0 + t < n) cdf[i0 + t] = sbuf[t];
-        __syncwarp();
+        const int64_t base = i0 + lane * kChunkPerLane;
+#pragma unroll
+        for (int e = 0; e < kChunkPerLane; ++e)
+          if (base + e < n) cdf[base + e] = v[e];
         g0 += 1;
       }
     }

@@ -339,13 +339,14 @@ class _AgentBase:
         bit3 is set) and nothing comes back to the host."""
         buf = self.buffer
         assert len(buf) >= B, "Not enough in buffer to sample"
+        buf._flush()
+        if self._replay_out is None or self._replay_out[0].shape[0] != B:
+            self._replay_out = buf._outputs(B)          # reused: the update copies the batch before it returns
         if isinstance(buf, PERBuffer):
-            buf._flush()
-            if self._replay_out is None or self._replay_out[0].shape[0] != B:
-                self._replay_out = buf._outputs(B)
             buf.sample_into(B, self.beta, self._replay_out, self._per_ptrs()[0])
             return tuple(self._replay_out), True
-        return buf.sample(B), False
+        buf.sample_into(B, self._replay_out)
+        return tuple(self._replay_out), False
 
     def _replay_finish(self, B):
         """buffer.update_priorities(indices, td_error) (:1387) on the device, then the per-sample TD errors the
@@ -470,6 +471,7 @@ class _AgentBase:
         self.save_weights(path)
         st = self.state_dict()
         st["python_random"] = random.getstate()
+        st["numpy_random"] = np.random.get_state()        # PERBuffer.sample draws from NumPy's global stream
         torch.save(st, os.path.join(path, "trainer_state.pt"))
         if with_buffer:
             torch.save(self.buffer.state_dict(), os.path.join(path, "buffer_state.pt"))
@@ -483,6 +485,8 @@ class _AgentBase:
             self.buffer.load_state_dict(torch.load(bpath, map_location="cpu", weights_only=False))
         if "python_random" in st:
             random.setstate(st["python_random"])
+        if "numpy_random" in st:
+            np.random.set_state(st["numpy_random"])
         self._pre = None
 
     # -- host index stream: latency hiding without changing the Mersenne-Twister stream ---------------

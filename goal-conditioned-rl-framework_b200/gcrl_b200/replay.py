@@ -97,6 +97,30 @@ class _Ring:
         check(lib.gcrl_replay_get_rows(self._h, first, n, np_ptr(out), self._stream()))
         return out
 
+    # -- true resume: the live window in deque order (and the priorities), cf. HERBuffer.state_dict ----------
+    def state_dict(self):
+        self._flush()
+        sd = {"kind": type(self).__name__, "max_len": self.max_len, "alpha": self.alpha, "dims": self._dims,
+              "rows": self.rows() if self._h else None}
+        if self._PRIORITIZED:
+            sd["priorities"] = self.priorities if self._h else None
+        return sd
+
+    def load_state_dict(self, sd):
+        if sd["kind"] != type(self).__name__ or sd["max_len"] != self.max_len:
+            raise ValueError("buffer checkpoint was written by a different buffer type / max_len")
+        self._staged = []
+        if self._h:
+            check(lib.gcrl_replay_destroy(self._h))
+            self._h, self._dims = None, None
+        if sd["rows"] is None or len(sd["rows"]) == 0:
+            return
+        self._ensure(*sd["dims"])
+        rows = np.ascontiguousarray(sd["rows"], np.float32)
+        check(lib.gcrl_replay_push(self._h, rows.shape[0], np_ptr(rows), self._stream()))
+        if self._PRIORITIZED:
+            self.set_priorities(sd["priorities"])
+
 
 class ReplayBuffer(_Ring):
     """Reference src/buffer.py:8-35.  Positions come from ``random.sample(range(len), B)`` -- the same
@@ -105,15 +129,20 @@ class ReplayBuffer(_Ring):
     def __init__(self, max_len: int, *, device=0):
         super().__init__(max_len, device=device)
 
-    def sample(self, batch_size: int, indices=None):
+    def sample_into(self, batch_size, out, indices=None):
         assert len(self) >= batch_size, "Not enough in buffer to sample"
         self._flush()
         B = int(batch_size)
         if indices is None:
             indices = _lib.py_sample_range(len(self), B)
         indices = np.ascontiguousarray(indices, np.int64)
-        out = self._outputs(B)
         check(lib.gcrl_replay_sample(self._h, B, np_ptr(indices), *(vp(t.data_ptr()) for t in out), self._stream()))
+
+    def sample(self, batch_size: int, indices=None):                            # :16-32
+        assert len(self) >= batch_size, "Not enough in buffer to sample"
+        self._flush()
+        out = self._outputs(int(batch_size))
+        self.sample_into(batch_size, out, indices)
         return tuple(out)
 
 

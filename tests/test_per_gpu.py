@@ -329,3 +329,50 @@ def test_agent_update_with_uniform_replay_equals_the_explicit_batch_update():
         assert [float(x) for x in i1] == [float(x) for x in i2]
     for (w, b), (w2, b2) in zip(a1.actor.layers() + a1.critic.layers(), a2.actor.layers() + a2.critic.layers()):
         assert np.array_equal(w, w2) and np.array_equal(b, b2)
+
+
+@pytest.mark.parametrize("btype", ["PER", "REPLAY"])
+def test_true_resume_with_replay_buffers_is_bit_identical(tmp_path, btype):
+    """save_checkpoint / load_checkpoint carry the ring (deque order), the priorities and both host generators
+    (random for ReplayBuffer, numpy.random for PERBuffer): the resumed run draws the same positions and makes
+    bit-identical updates."""
+    import torch
+    import gcrl_b200
+    from tests.test_ddpg_gpu import make_config
+    D, A, H, L, B = 13, 3, 64, 3, 96
+    rng = np.random.default_rng(12)
+    rows = rand_rows(rng, 900, D, A)
+    cfg = make_config(hidden_dim=H, layer_count=L, batch_size=B, buffer_type=btype, max_len=500, alpha=0.6, beta=0.4,
+                      beta_end=50)
+    torch.manual_seed(5)
+    a1 = gcrl_b200.DDPG(D, A, cfg, None, 1, 40)
+    for i in range(700):
+        a1.push(*(x[i] for x in rows))
+    random.seed(3)
+    np.random.seed(3)
+    for i in range(4):
+        a1.update(37 + i)
+    a1.save_checkpoint(str(tmp_path / "ck"))
+    def cont(ag):
+        out = []
+        for i in range(4):
+            for j in range(700 + 50 * i, 750 + 50 * i):
+                ag.push(*(x[j] for x in rows))
+            out.append(ag.update(41 + i))
+        return out
+    ref = cont(a1)
+    random.seed(77)
+    np.random.seed(77)
+    torch.manual_seed(99)
+    a2 = gcrl_b200.DDPG(D, A, cfg, None, 1, 40)
+    a2.load_checkpoint(str(tmp_path / "ck"))
+    assert len(a2.buffer) == 500
+    got = cont(a2)
+    for r, g_ in zip(ref, got):
+        assert len(r) == len(g_)
+        for x, y in zip(r, g_):
+            assert np.array_equal(np.asarray(x), np.asarray(y))
+    assert np.array_equal(bits(a1.buffer.rows()), bits(a2.buffer.rows()))
+    if btype == "PER":
+        assert np.array_equal(bits(a1.buffer.priorities), bits(a2.buffer.priorities))
+        assert a1.beta == a2.beta
