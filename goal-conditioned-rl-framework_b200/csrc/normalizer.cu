@@ -138,6 +138,16 @@ __global__ void norm_merge_kernel(const Moments *__restrict__ partials, int nblo
   update_from_moments(st, c, count, b.mean, b.m2, b.n);
 }
 
+// batch moments only (no state update): what a rank contributes to a data-parallel update
+__global__ void norm_collect_kernel(const Moments *__restrict__ partials, int nblocks, int dim,
+                                    Moments *__restrict__ out) {
+  const int c = threadIdx.x;
+  if (c >= dim) return;
+  Moments b{0.0, 0.0, 0.0};
+  for (int i = 0; i < nblocks; ++i) b = chan_merge(b, partials[size_t(i) * dim + c]);
+  out[c] = b;
+}
+
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
 norm_apply_kernel(const TI *__restrict__ x, int64_t n, int dim, NormState st, double clip,
@@ -282,6 +292,53 @@ int gcrl_norm_update(gcrl_norm *h, const void *x_host, int64_t n, int is_f64, vo
   cudaStream_t st = as_stream(stream);
   const void *xd = norm_stage_in(h, x_host, n, is_f64, st);
   norm_update_device(h, xd, n, is_f64, st);
+  GCRL_API_END
+}
+
+int gcrl_norm_batch_moments(gcrl_norm *h, const void *x_host, int64_t n, int is_f64, double *moments_host,
+                            void *stream) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(h != nullptr && moments_host != nullptr && (x_host != nullptr || n == 0) && n >= 0, "bad arguments");
+  GCRL_REQUIRE(h->dim <= 128, "normaliser dim > 128 not supported");
+  GCRL_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = as_stream(stream);
+  if (n == 0) {
+    std::memset(moments_host, 0, size_t(h->dim) * sizeof(Moments));
+    return GCRL_OK;
+  }
+  const void *xd = norm_stage_in(h, x_host, n, is_f64, st);
+  const int64_t rows_per_block = std::max<int64_t>(256, (n + h->max_blocks - 2) / (h->max_blocks - 1));
+  const int nblocks = int((n + rows_per_block - 1) / rows_per_block);
+  if (is_f64)
+    norm_partial_kernel<double><<<nblocks, kNormWarps * 32, 0, st>>>(static_cast<const double *>(xd), n, h->dim,
+                                                                     rows_per_block, h->d_partials);
+  else
+    norm_partial_kernel<float><<<nblocks, kNormWarps * 32, 0, st>>>(static_cast<const float *>(xd), n, h->dim,
+                                                                    rows_per_block, h->d_partials);
+  GCRL_LAUNCHED();
+  Moments *out = h->d_partials + size_t(h->max_blocks - 1) * h->dim;      // last slab of the scratch
+  norm_collect_kernel<<<1, 128, 0, st>>>(h->d_partials, nblocks, h->dim, out);
+  GCRL_LAUNCHED();
+  GCRL_CUDA(cudaMemcpyAsync(moments_host, out, size_t(h->dim) * sizeof(Moments), cudaMemcpyDeviceToHost, st));
+  GCRL_CUDA(cudaStreamSynchronize(st));
+  GCRL_API_END
+}
+
+int gcrl_norm_update_moments(gcrl_norm *h, const double *moments_host, int parts, void *stream) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(h != nullptr && moments_host != nullptr && parts >= 1, "bad arguments");
+  GCRL_REQUIRE(parts <= h->max_blocks, "too many parts");
+  GCRL_REQUIRE(h->dim <= 128, "normaliser dim > 128 not supported");
+  GCRL_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = as_stream(stream);
+  const size_t bytes = size_t(parts) * h->dim * sizeof(Moments);
+  int slot;
+  char *p = h->stage.acquire(bytes, &slot);
+  std::memcpy(p, moments_host, bytes);
+  GCRL_CUDA(cudaMemcpyAsync(h->d_partials, p, bytes, cudaMemcpyHostToDevice, st));
+  h->stage.release(slot, st);
+  norm_merge_kernel<<<1, 128, 0, st>>>(h->d_partials, parts, h->dim, h->st);
+  GCRL_LAUNCHED();
   GCRL_API_END
 }
 

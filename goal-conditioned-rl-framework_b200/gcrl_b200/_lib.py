@@ -67,6 +67,8 @@ SIGNATURES = {
     "gcrl_norm_destroy": (C.c_int, [vp]),
     "gcrl_norm_update": (C.c_int, [vp, vp, c_i64, C.c_int, vp]),
     "gcrl_norm_update_dev": (C.c_int, [vp, vp, c_i64, C.c_int, vp]),
+    "gcrl_norm_batch_moments": (C.c_int, [vp, vp, c_i64, C.c_int, vp, vp]),
+    "gcrl_norm_update_moments": (C.c_int, [vp, vp, C.c_int, vp]),
     "gcrl_norm_apply": (C.c_int, [vp, vp, c_i64, C.c_int, vp, vp]),
     "gcrl_norm_apply_dev_f32": (C.c_int, [vp, vp, c_i64, C.c_int, vp, c_i64, c_i64, vp]),
     "gcrl_norm_get_state": (C.c_int, [vp, vp, vp, C.POINTER(c_f64), C.POINTER(c_f64), vp]),

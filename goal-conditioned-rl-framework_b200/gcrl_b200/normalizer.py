@@ -72,8 +72,45 @@ class RunningNormalizer:
 
     def update(self, x):                                   # src/utils.py:75-80
         x, _ = self._as_rows(x, self.size)
+        if self._gather is not None:
+            return self.update_moments(self._gather(self.batch_moments(x)))
         check(lib.gcrl_norm_update(self._h, np_ptr(x), x.shape[0], int(x.dtype == np.float64),
                                    self._stream()))
+
+    # -- data parallel: every rank folds all ranks' batch moments, in rank order --------
+    _gather = None
+
+    def enable_data_parallel(self, process_group=None, gather=None):
+        """From now on ``update(x)`` is collective: the ranks' batch moments (2 * dim + 1 float64 numbers each)
+        are all-gathered and merged in rank order, so every replica of the running statistics stays
+        bit-identical and equals a single-process update on the concatenated batch to float64 rounding.
+        ``gather(moments [dim, 3]) -> [world, dim, 3]`` overrides the collective (tests)."""
+        if gather is None:
+            import torch
+            import torch.distributed as dist
+
+            def gather(m):
+                nccl = dist.get_backend(process_group) == "nccl"
+                t = torch.from_numpy(m)
+                if nccl:
+                    t = t.cuda(self.device_index)
+                out = [torch.empty_like(t) for _ in range(dist.get_world_size(process_group))]
+                dist.all_gather(out, t, group=process_group)
+                return np.stack([o.cpu().numpy() for o in out])
+        self._gather = gather
+
+    def batch_moments(self, x):
+        """(n, mean, M2) per column of a batch, float64 [dim, 3]; the running state is not touched."""
+        x, _ = self._as_rows(x, self.size)
+        out = np.empty((self.size, 3), np.float64)
+        check(lib.gcrl_norm_batch_moments(self._h, np_ptr(x), x.shape[0], int(x.dtype == np.float64), np_ptr(out),
+                                          self._stream()))
+        return out
+
+    def update_moments(self, moments):
+        """Fold batch moments [parts, dim, 3] (in the given order) into the running state."""
+        m = np.ascontiguousarray(moments, np.float64).reshape(-1, self.size, 3)
+        check(lib.gcrl_norm_update_moments(self._h, np_ptr(m), m.shape[0], self._stream()))
 
     def normalize(self, x):                                # src/utils.py:96-98
         x, shape = self._as_rows(x, self.size)

@@ -121,6 +121,15 @@ int gcrl_norm_create(gcrl_norm **out, int device, int dim, double clip_range, do
 int gcrl_norm_destroy(gcrl_norm *h);
 /* update(x), src/utils.py:75-94.  x: host [n, dim], float64 (is_f64 != 0) or float32. */
 int gcrl_norm_update(gcrl_norm *h, const void *x_host, int64_t n, int is_f64, void *stream);
+/* Data-parallel update (one process per GPU, every rank sees its own envs' observations): the local batch's
+ * moments per column, moments_host [dim][3] = (n, mean, M2 = sum (x - mean)^2), no state change; the caller
+ * all-gathers them and every rank folds ALL ranks' moments, in rank order, into its running state with
+ * gcrl_norm_update_moments (moments_host [parts][dim][3]) -- Chan's merge, then _update_from_moments
+ * (src/utils.py:82-94) once.  N ranks on per-rank batches == one rank on the concatenated batch to float64
+ * rounding, and the replicas stay bit-identical. */
+int gcrl_norm_batch_moments(gcrl_norm *h, const void *x_host, int64_t n, int is_f64, double *moments_host,
+                            void *stream);
+int gcrl_norm_update_moments(gcrl_norm *h, const double *moments_host, int parts, void *stream);
 /* Same with x already on the device. */
 int gcrl_norm_update_dev(gcrl_norm *h, const void *x_dev, int64_t n, int is_f64, void *stream);
 /* normalize(x), src/utils.py:96-98: clip((x-mean)/(sqrt(var)+1e-8), +-clip) in float64.

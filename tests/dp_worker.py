@@ -43,10 +43,34 @@ def main():
             assert weights_close(w, ws, 1e-3, 4) and weights_close(b, bs, 1e-3, 4)
     tqc_section(rank, world, local)
     p2p_section(rank, world, local)
+    normaliser_section(rank, world, local)
     if rank == 0:
         print("DP_OK", flush=True)
     dist.barrier()
     dist.destroy_process_group()
+
+
+def normaliser_section(rank, world, local):
+    """RunningNormalizer.update as a collective over NCCL: per-rank observation batches, identical replicas, and
+    equal to the oracle on the concatenated batch to float64 rounding."""
+    from gcrl_b200 import RunningNormalizer
+    from oracle import her as OH
+    dim = 19
+    nz = RunningNormalizer(dim, device=local)
+    nz.enable_data_parallel()
+    single = OH.RunningNormalizerOracle(dim)
+    rng = np.random.default_rng(17)
+    for step in range(4):
+        parts = [rng.standard_normal((2 + r, dim)) * (1 + step) + 0.5 * r for r in range(world)]   # same stream everywhere
+        nz.update(parts[rank])
+        single.update(np.concatenate(parts, 0))
+    np.testing.assert_allclose(nz.mean, single.mean, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(nz.var, single.var, rtol=1e-12, atol=1e-12)
+    flat = torch.from_numpy(np.concatenate([nz.mean, nz.var])).cuda(local)
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    for g in gathered[1:]:
+        assert torch.equal(g, gathered[0]), "normaliser replicas diverged"
 
 
 def p2p_section(rank, world, local):

@@ -107,3 +107,30 @@ def test_agent_glue_concat_matches_oracle():
     got = np.concatenate([no.normalize(obs), ng.normalize(dg)], -1)
     want = np.concatenate([oo.normalize(obs), og.normalize(dg)], -1)
     np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("world,dtype,tol", [(2, np.float64, 1e-12), (4, np.float64, 1e-12), (8, np.float32, 2e-6)])
+def test_data_parallel_update_equals_single_process_on_the_concatenated_batch(world, dtype, tol):
+    """every rank contributes the moments of its own envs' observations; all ranks fold all moments
+    in rank order.  N ranks on per-rank batches == one process on the concatenated batch (the oracle, i.e. the
+    reference's update) to float64 rounding -- float32 batches to float32 rounding, because NumPy forms
+    batch_var * n in the batch dtype (src/utils.py:88) -- and the replicas are bit-identical."""
+    from gcrl_b200 import RunningNormalizer
+    rng = np.random.default_rng(world)
+    dim = 19
+    ranks = [RunningNormalizer(dim) for _ in range(world)]
+    single = OH.RunningNormalizerOracle(dim)
+    for step in range(5):
+        parts = [(rng.standard_normal((3 + r, dim)) * (1 + step) + 0.3 * r).astype(dtype) for r in range(world)]
+        gathered = np.stack([nz.batch_moments(x) for nz, x in zip(ranks, parts)])      # the all-gather
+        for nz, x in zip(ranks, parts):
+            nz.enable_data_parallel(gather=lambda m, _g=gathered: _g)
+            nz.update(x)
+        single.update(np.concatenate(parts, 0))
+        np.testing.assert_allclose(ranks[0].mean, single.mean, rtol=tol, atol=tol)
+        np.testing.assert_allclose(ranks[0].var, single.var, rtol=tol, atol=tol)
+        assert ranks[0].count == pytest.approx(single.count, rel=1e-15)
+        for nz in ranks[1:]:
+            assert np.array_equal(nz.mean, ranks[0].mean) and np.array_equal(nz.var, ranks[0].var)
+    q = rng.standard_normal((7, dim))
+    np.testing.assert_allclose(ranks[-1].normalize(q), single.normalize(q), rtol=100 * tol, atol=100 * tol)
