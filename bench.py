@@ -60,6 +60,8 @@ def parse():
                     help="N > 1: average gradients over NVLink peer memory inside the captured graph (p2p) or with "
                          "NCCL all-reduce between the update phases (nccl)")
     ap.add_argument("--no-big-buffer", action="store_true", help="skip the 10M-transition sampler point")
+    ap.add_argument("--huge-buffer", action="store_true",
+                    help="also time the sampler on 100x the transitions (100M stored transitions, 23 GB; +1 min)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--spinup", type=int, default=80, help="extra untimed steps before the W warm-up steps")
     return ap.parse_args()
@@ -442,18 +444,20 @@ def gpu_main(args):
                 "transitions_per_s": batch / (ms_k * 1e-3)}
     # BASELINE configs[4]: the sampler on a 10x larger buffer (10M stored transitions = 49.2M deque entries,
     # 2.2 GB of packed rows, far beyond the 126 MB L2): the same 20 000 synthetic episodes committed 10 times
-    if rank == 0 and sweep_batches and not args.no_big_buffer:
+    for mult in ([10] if not args.no_big_buffer else []) + ([100] if args.huge_buffer else []):
+        if not (rank == 0 and sweep_batches):
+            break
         try:
             from gcrl_b200 import HERBuffer
-            big = HERBuffer(10 * max_len, 50, 1, k_future=k, index_source="device", seed=7, device=local)
+            big = HERBuffer(mult * max_len, 50, 1, k_future=k, index_source="device", seed=7, device=local)
             t0 = time.time()
-            for rep in range(10):
+            for rep in range(mult):
                 for e in range(E):
                     big.push_episode(data["s"][e], data["a"][e], data["ns"][e], data["r"][e], data["d"][e],
                                      data["ag"][e], data["fut"][e])
             torch.cuda.synchronize()
             log(f"[big buffer] {len(big)} entries committed in {time.time() - t0:.1f}s")
-            for batch in (256, 65536):
+            for batch in (256, 65536) + ((1 << 20,) if mult >= 100 else ()):
                 outs = [torch.empty((batch, w), dtype=torch.float32, device=dev) for w in (D, A, 1, D, 1)]
                 ptrs = [vp(o.data_ptr()) for o in outs]
                 for _ in range(5):
@@ -467,10 +471,10 @@ def gpu_main(args):
                 torch.cuda.synchronize()
                 ms_k = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
                 ach = batch * alg_bytes / (ms_k * 1e-3) / 1e9
-                rooflines[f"her_sample_kernel_B{batch}_buffer10M"] = {
+                rooflines[f"her_sample_kernel_B{batch}_buffer{mult * args.transitions // 1000000}M"] = {
                     "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                     "traffic": None, "ms_per_launch": ms_k, "algorithmic_bytes_per_transition": alg_bytes,
-                    "transitions_per_s": batch / (ms_k * 1e-3), "buffer_transitions": 10 * args.transitions}
+                    "transitions_per_s": batch / (ms_k * 1e-3), "buffer_transitions": mult * args.transitions}
             del big, outs
             torch.cuda.empty_cache()
         except Exception as e:   # noqa: BLE001
