@@ -16,6 +16,8 @@
 // The kernels leave the per-layer activations and pre-activation gradients in global memory; the
 // weight-gradient GEMMs of all layers then run as ONE multi-problem launch (mlp.cu).
 // Launches per update: 57 -> 9.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cstdlib>
 
@@ -183,8 +185,13 @@ size_t fused_smem_bytes(int R, int D, int A, int H, int L, bool two_keeps) {
 // ---------------------------------------------------------------------------------------------
 // critic phase
 // ---------------------------------------------------------------------------------------------
-// TD3 = false compiles the smoothing noise / second target critic / given-target / smooth-L1 branches out
-template <int R, bool TD3>
+// TD3 = false compiles the smoothing noise / second target critic / given-target / smooth-L1 branches out.
+// SPLIT: the slab is carried by a 2-CTA cluster.  The target path (a' = pi_t(s'), q' = Q_t(s', a'): 2L + 2 layer
+// steps) and the critic forward (L + 1 steps) do not depend on each other, so CTA 0 runs the former while CTA 1
+// runs the latter; CTA 0 drops q' into CTA 1's shared memory (DSMEM), one cluster barrier, and CTA 1 goes on
+// with the loss and the backward pass.  Critical path 3L + 3 -> 2L + 2 + (L - 1) layer steps; used when both
+// CTAs of every slab fit in one wave.
+template <int R, bool TD3, bool SPLIT>
 __global__ void __launch_bounds__(kFusedThreads, 1) fused_critic_kernel(FusedCriticArgs a) {
   extern __shared__ float4 fsm4[];
   const int D = a.D, A = a.A, H = a.H, L = a.L, B = a.B;
@@ -193,7 +200,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_critic_kernel(FusedCri
   float *x_ns = sp.xa, *x_sa = sp.xb;
   float *qn = sp.small, *q = qn + R, *yv = q + R, *dzh = yv + R, *rr = dzh + R, *dd = rr + R;
   float *anext = dd + R;                          // [A][R], A <= 4
-  const int row0 = blockIdx.x * R, tid = threadIdx.x;
+  const int slab = SPLIT ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  const int role = SPLIT ? int(blockIdx.x & 1) : 2;      // 0: target path, 1: critic path, 2: both
+  const int row0 = slab * R, tid = threadIdx.x;
 
   // ---- 0. stage the slab's rows: x_ns = [s' | (a')], x_sa = [s | a]; also emit [s | a | 0] rows ----
   for (int e = tid; e < KinP * R; e += kFusedThreads) {
@@ -212,7 +221,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_critic_kernel(FusedCri
     dd[tid] = row < B ? a.d[row] : 0.f;
   }
   __syncthreads();
-  if (a.sa_out != nullptr) {
+  if (a.sa_out != nullptr && role != 0) {
     for (int e = tid; e < a.ldc * R; e += kFusedThreads) {
       const int r = e / a.ldc, k = e - r * a.ldc;
       if (row0 + r < B) a.sa_out[size_t(row0 + r) * a.ldc + k] = k < KinP ? x_sa[k * R + r] : 0.f;
@@ -220,7 +229,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_critic_kernel(FusedCri
   }
 
   const float *h;
-  if (!TD3 || a.y_in == nullptr) {
+  if ((!TD3 || a.y_in == nullptr) && role != 1) {
     // ---- 1. a' = target_actor(s') (:1312); TD3: + clamp(noise * sigma, +-c), clamped to [-1, 1] (:174-179) ----
     h = slab_forward<R>(a.ta, L, H, x_ns, D, nullptr, sp.t0, sp.t1, sp.red, nullptr, 0, row0, B);
     slab_head<R>(h, H, a.ta.Wh, a.ta.ldwh, a.ta.bh, A, true, anext);
@@ -246,9 +255,20 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_critic_kernel(FusedCri
       __syncthreads();
     }
   }
+  if (SPLIT) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    if (role == 0) {                     // hand q' to the critic CTA and leave
+      float *peer_qn = cluster.map_shared_rank(qn, 1);
+      if (tid < R) peer_qn[tid] = qn[tid];
+      cluster.sync();
+      return;
+    }
+  }
   // ---- 3. q = critic([s, a]) (:1319), activations kept for the backward pass ----
   h = slab_forward<R>(a.c, L, H, x_sa, D + A, sp.keep1, nullptr, nullptr, sp.red, a.h_out, a.ldh, row0, B);
   slab_head<R>(h, H, a.c.Wh, a.c.ldwh, a.c.bh, 1, false, q);
+  if (SPLIT) cooperative_groups::this_cluster().sync();      // q' has arrived
   // ---- 4. Bellman target, loss, dL/dq (:1316-1326) ----
   if (tid == 0) {
     float ls = 0.f, ts = 0.f, qs = 0.f;
@@ -291,7 +311,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_critic_kernel(FusedCri
       }
       dzh[r] = g;
     }
-    float *mp = a.metric_partials + size_t(blockIdx.x) * 4;
+    float *mp = a.metric_partials + size_t(slab) * 4;
     mp[0] = ls; mp[1] = ts; mp[2] = qs; mp[3] = 0.f;
   }
   __syncthreads();
@@ -399,7 +419,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_actor_kernel(FusedActo
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
-static int g_fused_smem_set[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+static int g_fused_smem_set[6][2] = {};
 
 template <typename K>
 static void ensure_smem(K kernel, size_t bytes, int *flag) {
@@ -421,21 +441,52 @@ bool fused_supported(int B, int D, int A, int H, int L) {
   return fused_smem_bytes(R, D, A, H, L, true) <= size_t(200) * 1024;
 }
 
+static bool fused_split_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("GCRL_FUSED_SPLIT");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int launch_fused_critic(const FusedCriticArgs &a, cudaStream_t st) {
   const int R = fused_rows_per_cta(a.B);
   const int grid = (a.B + R - 1) / R;
   const size_t smem = fused_smem_bytes(R, a.D, a.A, a.H, a.L, false);
   const bool td3 = a.has_tc2 || a.noise != nullptr || a.y_in != nullptr || a.loss_kind != 0 || a.q_other != nullptr;
-  auto go = [&](auto kernel, int *flag) {
+  // two CTAs per slab (target path | critic path) when there is a target path and everything fits in one wave
+  const bool split = fused_split_enabled() && a.y_in == nullptr && 2 * grid <= sm_count();
+  auto go = [&](auto kernel, int *flag, bool clustered) {
     ensure_smem(kernel, smem, flag);
-    kernel<<<grid, kFusedThreads, smem, st>>>(a);
+    if (!clustered) {
+      kernel<<<grid, kFusedThreads, smem, st>>>(a);
+      return;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * grid);
+    cfg.blockDim = dim3(kFusedThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GCRL_CUDA(cudaLaunchKernelEx(&cfg, kernel, a));
   };
   if (R == 4) {
-    if (td3) go(fused_critic_kernel<4, true>, &g_fused_smem_set[2][0]);
-    else go(fused_critic_kernel<4, false>, &g_fused_smem_set[0][0]);
+    if (td3 && split) go(fused_critic_kernel<4, true, true>, &g_fused_smem_set[5][0], true);
+    else if (td3) go(fused_critic_kernel<4, true, false>, &g_fused_smem_set[2][0], false);
+    else if (split) go(fused_critic_kernel<4, false, true>, &g_fused_smem_set[4][0], true);
+    else go(fused_critic_kernel<4, false, false>, &g_fused_smem_set[0][0], false);
   } else {
-    if (td3) go(fused_critic_kernel<8, true>, &g_fused_smem_set[2][1]);
-    else go(fused_critic_kernel<8, false>, &g_fused_smem_set[0][1]);
+    if (td3 && split) go(fused_critic_kernel<8, true, true>, &g_fused_smem_set[5][1], true);
+    else if (td3) go(fused_critic_kernel<8, true, false>, &g_fused_smem_set[2][1], false);
+    else if (split) go(fused_critic_kernel<8, false, true>, &g_fused_smem_set[4][1], true);
+    else go(fused_critic_kernel<8, false, false>, &g_fused_smem_set[0][1], false);
   }
   GCRL_LAUNCHED();
   return grid;
