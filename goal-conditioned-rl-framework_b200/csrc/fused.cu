@@ -37,11 +37,16 @@ struct RowVec {
 
 template <int R>
 __device__ __forceinline__ void load_rows(const float *p, float (&x)[R]) {
-  const float4 *q = reinterpret_cast<const float4 *>(p);
+  if constexpr (R == 2) {
+    const float2 t = *reinterpret_cast<const float2 *>(p);
+    x[0] = t.x; x[1] = t.y;
+  } else {
+    const float4 *q = reinterpret_cast<const float4 *>(p);
 #pragma unroll
-  for (int i = 0; i < R / 4; ++i) {
-    const float4 t = q[i];
-    x[4 * i] = t.x; x[4 * i + 1] = t.y; x[4 * i + 2] = t.z; x[4 * i + 3] = t.w;
+    for (int i = 0; i < R / 4; ++i) {
+      const float4 t = q[i];
+      x[4 * i] = t.x; x[4 * i + 1] = t.y; x[4 * i + 2] = t.z; x[4 * i + 3] = t.w;
+    }
   }
 }
 
@@ -87,10 +92,14 @@ __device__ __forceinline__ void slab_matmul(const float *xT, int K, const float 
     }
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      float4 *dst = reinterpret_cast<float4 *>(red + (size_t(ks) * Np + j0 + c) * R);
+      if constexpr (R == 2) {
+        *reinterpret_cast<float2 *>(red + (size_t(ks) * Np + j0 + c) * R) = make_float2(acc[c][0], acc[c][1]);
+      } else {
+        float4 *dst = reinterpret_cast<float4 *>(red + (size_t(ks) * Np + j0 + c) * R);
 #pragma unroll
-      for (int q = 0; q < R / 4; ++q)
-        dst[q] = make_float4(acc[c][4 * q], acc[c][4 * q + 1], acc[c][4 * q + 2], acc[c][4 * q + 3]);
+        for (int q = 0; q < R / 4; ++q)
+          dst[q] = make_float4(acc[c][4 * q], acc[c][4 * q + 1], acc[c][4 * q + 2], acc[c][4 * q + 3]);
+      }
     }
   }
   __syncthreads();
@@ -419,7 +428,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_actor_kernel(FusedActo
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
-static int g_fused_smem_set[6][2] = {};
+static int g_fused_smem_set[6][3] = {};
 
 template <typename K>
 static void ensure_smem(K kernel, size_t bytes, int *flag) {
@@ -429,8 +438,13 @@ static void ensure_smem(K kernel, size_t bytes, int *flag) {
   }
 }
 
+// Rows per CTA.  The kernels are chains of dependent layer steps whose cost grows with R (16 FMAs per weight
+// load at R = 4, 8 at R = 2), so the smallest R whose slabs still fit in ONE wave of CTAs wins: at B = 256,
+// R = 2 (128 CTAs) runs the critic phase in 36.9 us and the actor phase in ~37 us, R = 4 (64 CTAs) in 48.9 / 45 us
+// (36.9 for the critic phase as 2-CTA clusters, see SPLIT).
 int fused_rows_per_cta(int B) {
   if (const char *e = getenv("GCRL_FUSED_R")) return atoi(e);
+  if (B <= 2 * sm_count()) return 2;
   return B <= 512 ? 4 : 8;
 }
 
@@ -456,7 +470,7 @@ int launch_fused_critic(const FusedCriticArgs &a, cudaStream_t st) {
   const size_t smem = fused_smem_bytes(R, a.D, a.A, a.H, a.L, false);
   const bool td3 = a.has_tc2 || a.noise != nullptr || a.y_in != nullptr || a.loss_kind != 0 || a.q_other != nullptr;
   // two CTAs per slab (target path | critic path) when there is a target path and everything fits in one wave
-  const bool split = fused_split_enabled() && a.y_in == nullptr && 2 * grid <= sm_count();
+  const bool split = fused_split_enabled() && R != 2 && a.y_in == nullptr && 2 * grid <= sm_count();
   auto go = [&](auto kernel, int *flag, bool clustered) {
     ensure_smem(kernel, smem, flag);
     if (!clustered) {
@@ -477,7 +491,10 @@ int launch_fused_critic(const FusedCriticArgs &a, cudaStream_t st) {
     cfg.numAttrs = 1;
     GCRL_CUDA(cudaLaunchKernelEx(&cfg, kernel, a));
   };
-  if (R == 4) {
+  if (R == 2) {
+    if (td3) go(fused_critic_kernel<2, true, false>, &g_fused_smem_set[2][2], false);
+    else go(fused_critic_kernel<2, false, false>, &g_fused_smem_set[0][2], false);
+  } else if (R == 4) {
     if (td3 && split) go(fused_critic_kernel<4, true, true>, &g_fused_smem_set[5][0], true);
     else if (td3) go(fused_critic_kernel<4, true, false>, &g_fused_smem_set[2][0], false);
     else if (split) go(fused_critic_kernel<4, false, true>, &g_fused_smem_set[4][0], true);
@@ -496,7 +513,10 @@ int launch_fused_actor(const FusedActorArgs &a, cudaStream_t st) {
   const int R = fused_rows_per_cta(a.B);
   const int grid = (a.B + R - 1) / R;
   const size_t smem = fused_smem_bytes(R, a.D, a.A, a.H, a.L, true);
-  if (R == 4) {
+  if (R == 2) {
+    ensure_smem(fused_actor_kernel<2>, smem, &g_fused_smem_set[1][2]);
+    fused_actor_kernel<2><<<grid, kFusedThreads, smem, st>>>(a);
+  } else if (R == 4) {
     ensure_smem(fused_actor_kernel<4>, smem, &g_fused_smem_set[1][0]);
     fused_actor_kernel<4><<<grid, kFusedThreads, smem, st>>>(a);
   } else {
