@@ -234,6 +234,58 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_kernel(GemmParams 
   gemm_body<BM, BN, TM, TN, OP>(p, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
+// Same-shape problems in one launch (the n critics of an ensemble): blockIdx.z enumerates the problems.
+struct BatchedGemm {
+  GemmParams p[kMaxBatchedLinear];
+};
+
+template <int BM, int BN, int TM, int TN, int OP>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) batched_gemm_kernel(BatchedGemm bg) {
+  gemm_body<BM, BN, TM, TN, OP>(bg.p[blockIdx.z], blockIdx.x, blockIdx.y, 0);
+}
+
+template <int OP>
+static void launch_batched_gemm(const BatchedGemm &bg, int n, cudaStream_t st) {
+  const GemmParams &p = bg.p[0];
+  const int sms = sm_count();
+  auto tiles = [&](int bm, int bn) { return ((p.M + bm - 1) / bm) * ((p.N + bn - 1) / bn) * n; };
+  if (tiles(128, 128) >= sms) {
+    dim3 grid((p.N + 127) / 128, (p.M + 127) / 128, n);
+    batched_gemm_kernel<128, 128, 8, 8, OP><<<grid, 256, 0, st>>>(bg);
+  } else if (tiles(64, 64) >= sms / 2) {
+    dim3 grid((p.N + 63) / 64, (p.M + 63) / 64, n);
+    batched_gemm_kernel<64, 64, 4, 4, OP><<<grid, 256, 0, st>>>(bg);
+  } else {
+    dim3 grid((p.N + 31) / 32, (p.M + 31) / 32, n);
+    batched_gemm_kernel<32, 32, 4, 4, OP><<<grid, 64, 0, st>>>(bg);
+  }
+  GCRL_LAUNCHED();
+}
+
+void launch_linear_fwd_batched(const LinearFwdProblem *pr, int n, int M, int N, int K, int act, cudaStream_t st) {
+  GCRL_REQUIRE(n >= 1 && n <= kMaxBatchedLinear, "too many batched problems");
+  BatchedGemm bg{};
+  for (int i = 0; i < n; ++i) {
+    GemmParams &p = bg.p[i];
+    p.A = pr[i].X; p.lda = pr[i].ldx; p.B = pr[i].W; p.ldb = pr[i].ldw; p.C = pr[i].Y; p.ldc = pr[i].ldy;
+    p.bias = pr[i].bias;
+    p.M = M; p.N = N; p.K = K; p.act_mode = act;
+  }
+  launch_batched_gemm<OP_FWD>(bg, n, st);
+}
+
+void launch_linear_dgrad_batched(const LinearDgradProblem *pr, int n, int M, int N, int K, cudaStream_t st) {
+  GCRL_REQUIRE(n >= 1 && n <= kMaxBatchedLinear, "too many batched problems");
+  BatchedGemm bg{};
+  for (int i = 0; i < n; ++i) {
+    GemmParams &p = bg.p[i];
+    p.A = pr[i].dZ; p.lda = pr[i].lddz; p.B = pr[i].W; p.ldb = pr[i].ldw; p.C = pr[i].dX; p.ldc = pr[i].lddx;
+    p.act = pr[i].Xact; p.ldact = pr[i].ldxa;
+    p.M = M; p.N = K; p.K = N;  // output [M, K_layer], reduction over the layer's N outputs
+  }
+  launch_batched_gemm<OP_DGRAD>(bg, n, st);
+}
+
 // Multi-problem weight-gradient launch: blockIdx.x enumerates the output tiles of all problems,
 // blockIdx.z the batch slabs.
 struct MultiGemm {
@@ -378,6 +430,44 @@ head_fwd_kernel(const float *__restrict__ H, int ldh, const float *__restrict__ 
       }
     }
   }
+}
+
+// scalar heads of several same-shape networks in one launch: blockIdx.y enumerates the networks
+struct HeadFwdBatch {
+  HeadFwdProblem p[kMaxBatchedLinear];
+};
+
+__global__ void __launch_bounds__(256) head_fwd_batched_kernel(HeadFwdBatch hb, int ldh, int ldw, int M, int K) {
+  const HeadFwdProblem &pr = hb.p[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int K4 = K >> 2;
+  for (int m = warp; m < M; m += nwarps) {          // same arithmetic order as head_fwd_kernel<1>
+    const float *h = pr.Hact + size_t(m) * ldh;
+    float acc = 0.f;
+    for (int k4 = lane; k4 < K4; k4 += 32) {
+      const float4 hv = *reinterpret_cast<const float4 *>(h + k4 * 4);
+      const float4 wv = *reinterpret_cast<const float4 *>(pr.W + k4 * 4);
+      acc = fmaf(hv.x, wv.x, acc);
+      acc = fmaf(hv.y, wv.y, acc);
+      acc = fmaf(hv.z, wv.z, acc);
+      acc = fmaf(hv.w, wv.w, acc);
+    }
+    for (int k = K4 * 4 + lane; k < K; k += 32) acc = fmaf(h[k], pr.W[k], acc);
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) pr.out[m] = acc + pr.bias[0];
+  }
+}
+
+void launch_head_fwd_batched(const HeadFwdProblem *pr, int n, int ldh, int ldw, int M, int K, cudaStream_t st) {
+  GCRL_REQUIRE(n >= 1 && n <= kMaxBatchedLinear, "too many batched problems");
+  HeadFwdBatch hb{};
+  for (int i = 0; i < n; ++i) hb.p[i] = pr[i];
+  const int blocks = std::max(1, std::min((M + 7) / 8, sm_count() * 8));
+  head_fwd_batched_kernel<<<dim3(blocks, n), 256, 0, st>>>(hb, ldh, ldw, M, K);
+  GCRL_LAUNCHED();
 }
 
 void launch_head_fwd(const float *Hact, int ldh, const float *W, int ldw, const float *bias, float *out,

@@ -26,6 +26,15 @@ int launch_linear_wgrad(const float *dZ, int lddz, const float *X, int ldx, floa
                         int max_splits, cudaStream_t st);
 
 // Skinny output layer, NOUT <= 4:  out[m, col0 + n] = f(H[m,:] . W[n,:] + bias[n]),  f = tanh | id
+// ---- same-shape problems of an ensemble (the n critics) in one launch per layer ----
+constexpr int kMaxBatchedLinear = 8;
+struct LinearFwdProblem { const float *X; int ldx; const float *W; int ldw; const float *bias; float *Y; int ldy; };
+struct LinearDgradProblem { const float *dZ; int lddz; const float *W; int ldw; const float *Xact; int ldxa; float *dX; int lddx; };
+struct HeadFwdProblem { const float *Hact; const float *W; const float *bias; float *out; };   // out[m] = h[m] . W + bias
+void launch_linear_fwd_batched(const LinearFwdProblem *pr, int n, int M, int N, int K, int act, cudaStream_t st);
+void launch_linear_dgrad_batched(const LinearDgradProblem *pr, int n, int M, int N, int K, cudaStream_t st);
+void launch_head_fwd_batched(const HeadFwdProblem *pr, int n, int ldh, int ldw, int M, int K, cudaStream_t st);
+
 void launch_head_fwd(const float *Hact, int ldh, const float *W, int ldw, const float *bias, float *out,
                      int ldo, int col0, int M, int K, int nout, int tanh_out, cudaStream_t st);
 

@@ -608,6 +608,23 @@ void critic_fwd(gcrl_sac *ag, const CriticNet &c, const float *X, const std::vec
   launch_head_fwd(acts[ag->L - 1], ag->ldh, c.W(ag->L), c.ldw[ag->L], c.b(ag->L), q_out, 1, 0, B, ag->H, 1, 0, st);
 }
 
+// The whole ensemble on the same input rows: one launch per layer (blockIdx.z = critic) instead of n.
+// Activations land in ag->ch[i][l] (the caches of the backward pass, or plain scratch for the targets).
+void critics_fwd(gcrl_sac *ag, const CriticNet *nets, const float *X, float *q_out, int B, cudaStream_t st) {
+  const int n = ag->n, L = ag->L;
+  LinearFwdProblem pr[kMaxBatchedLinear];
+  for (int l = 0; l < L; ++l) {
+    for (int i = 0; i < n; ++i)
+      pr[i] = LinearFwdProblem{l == 0 ? X : ag->ch[i][l - 1], l == 0 ? ag->ldc : ag->ldh, nets[i].W(l), nets[i].ldw[l],
+                               nets[i].b(l), ag->ch[i][l], ag->ldh};
+    launch_linear_fwd_batched(pr, n, B, ag->H, l == 0 ? ag->D + ag->A : ag->H, ACT_LEAKY, st);
+  }
+  HeadFwdProblem hp[kMaxBatchedLinear];
+  for (int i = 0; i < n; ++i)
+    hp[i] = HeadFwdProblem{ag->ch[i][L - 1], nets[i].W(L), nets[i].b(L), q_out + int64_t(i) * ag->maxB};
+  launch_head_fwd_batched(hp, n, ag->ldh, nets[0].ldw[L], B, ag->H, st);
+}
+
 // actor forward on rows[:, :D]; action -> rows[:, D:D+A]
 void actor_fwd(gcrl_sac *ag, float *rows, const float *eps, int B, bool train, bool cache, float *act_out,
                cudaStream_t st) {
@@ -687,12 +704,12 @@ void critic_update(gcrl_sac *ag, int B, int flags, int mask, cudaStream_t st) {
   if (mask & PH_CGRAD) {
   // next action and log-probability = actor.sample(next_state) in train mode (batch statistics; running statistics move)
   actor_fwd(ag, ag->nsa, ag->eps_next, B, true, false, nullptr, st);
-  for (int i = 0; i < n; ++i) critic_fwd(ag, ag->target[i], ag->nsa, ag->th, ag->qt + int64_t(i) * ag->maxB, B, st);
+  critics_fwd(ag, ag->target, ag->nsa, ag->qt, B, st);         // ch[i] as scratch: overwritten by the critic forward
   sac_target_kernel<<<blocks_for(B, 256), 256, 0, st>>>(ag->qt, ag->maxB, n, ag->keep, ag->logp, ag->br, ag->bd,
                                                        ag->cfg.gamma, ag->cfg.entropy_coef, ag->alpha_state + 1,
                                                        ag->y, B);
   GCRL_LAUNCHED();
-  for (int i = 0; i < n; ++i) critic_fwd(ag, ag->critic[i], ag->sa, ag->ch[i], ag->q + int64_t(i) * ag->maxB, B, st);
+  critics_fwd(ag, ag->critic, ag->sa, ag->q, B, st);
   critic_metrics_kernel<<<1, 1024, 0, st>>>(ag->q, ag->maxB, n, ag->y, B, ag->mdev + M_CLOSS, 0,
                                             ag->per_on ? ag->per_w : nullptr, ag->per_on ? ag->per_td : nullptr);
   GCRL_LAUNCHED();
@@ -736,7 +753,7 @@ void critic_update(gcrl_sac *ag, int B, int flags, int mask, cudaStream_t st) {
     }
   }
   if (tqc && (mask & PH_CSTEP)) {   // logged Q = mean over the STEPPED critics (:1016-1019)
-    for (int i = 0; i < n; ++i) critic_fwd(ag, ag->critic[i], ag->sa, ag->th, ag->qt + int64_t(i) * ag->maxB, B, st);
+    critics_fwd(ag, ag->critic, ag->sa, ag->qt, B, st);        // the backward pass is done with ch[i]
     critic_metrics_kernel<<<1, 1024, 0, st>>>(ag->qt, ag->maxB, n, nullptr, B, ag->mdev + M_CLOSS, 1, nullptr, nullptr);
     GCRL_LAUNCHED();
   }
@@ -749,7 +766,7 @@ void actor_update(gcrl_sac *ag, int B, int flags, int mask, cudaStream_t st) {
   const bool dp = mask != PH_ALL;
   if (mask & PH_AGRAD) {
   actor_fwd(ag, ag->spi, ag->eps_cur, B, true, true, nullptr, st);
-  for (int i = 0; i < n; ++i) critic_fwd(ag, ag->critic[i], ag->spi, ag->ch[i], ag->q + int64_t(i) * ag->maxB, B, st);
+  critics_fwd(ag, ag->critic, ag->spi, ag->q, B, st);
   actor_trunc_kernel<<<1, 1024, 0, st>>>(ag->q, ag->maxB, n, ag->keep, ag->logp, ag->cfg.entropy_coef,
                                         ag->alpha_state + 1, ag->dq, ag->mdev + M_ALOSS, B);
   GCRL_LAUNCHED();
