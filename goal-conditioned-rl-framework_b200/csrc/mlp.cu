@@ -488,7 +488,7 @@ constexpr int kHeadSlabMax = 512;
 constexpr int kHeadColBlock = 64;
 
 template <int NOUT>
-__global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs a, int rows_per_slab) {
+__device__ __forceinline__ void head_bwd_body(const HeadBwdArgs &a, int rows_per_slab) {
   __shared__ float dz_s[kHeadSlabMax][NOUT];
   __shared__ float met_s[kHeadSlabMax][3];
   const int tid = threadIdx.x;
@@ -612,6 +612,36 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs a, int rows_p
       }
     }
   }
+}
+
+template <int NOUT>
+__global__ void __launch_bounds__(256) head_bwd_kernel(HeadBwdArgs a, int rows_per_slab) {
+  head_bwd_body<NOUT>(a, rows_per_slab);
+}
+
+// the same for several same-shape networks (scalar heads of a critic ensemble): blockIdx.z = network
+struct HeadBwdBatch {
+  HeadBwdArgs a[kMaxBatchedLinear];
+};
+__global__ void __launch_bounds__(256) head_bwd_batched_kernel(HeadBwdBatch hb, int rows_per_slab) {
+  head_bwd_body<1>(hb.a[blockIdx.z], rows_per_slab);
+}
+
+int launch_head_bwd_batched(const HeadBwdArgs *a, int n, int max_splits, cudaStream_t st) {
+  GCRL_REQUIRE(n >= 1 && n <= kMaxBatchedLinear, "too many batched problems");
+  HeadBwdBatch hb{};
+  for (int i = 0; i < n; ++i) {
+    GCRL_REQUIRE(a[i].nout == 1 && a[i].M == a[0].M && a[i].K == a[0].K, "batched heads must share their shape");
+    hb.a[i] = a[i];
+  }
+  int rows = (a[0].M + max_splits - 1) / max_splits;
+  rows = std::min(kHeadSlabMax, std::max(rows, 16));
+  const int slabs = (a[0].M + rows - 1) / rows;
+  if (slabs > max_splits) throw Error(GCRL_ERR_INVALID, "batch too large for head_bwd partial buffers");
+  const dim3 grid(slabs, (a[0].K + kHeadColBlock - 1) / kHeadColBlock, n);
+  head_bwd_batched_kernel<<<grid, 256, 0, st>>>(hb, rows);
+  GCRL_LAUNCHED();
+  return slabs;
 }
 
 int launch_head_bwd(const HeadBwdArgs &a, int max_splits, cudaStream_t st) {

@@ -62,6 +62,7 @@ struct HeadBwdArgs {
 };
 // Returns the number of row slabs S.
 int launch_head_bwd(const HeadBwdArgs &a, int max_splits, cudaStream_t st);
+int launch_head_bwd_batched(const HeadBwdArgs *a, int n, int max_splits, cudaStream_t st);   // nout == 1, same M / K
 
 // Critic layer-1 input gradient restricted to the action columns, fused with tanh':
 //   dz_out[m*4 + j] = (sum_n dZ1[m,n] W1[n, col0 + j]) * (1 - act[m, col0 + j]^2)
@@ -81,7 +82,7 @@ struct WgradProblem {
   float *pB;
   int N, K;          // layer output / input widths
 };
-constexpr int kMaxWgradProblems = 8;
+constexpr int kMaxWgradProblems = 8;   // == kMaxBatchedLinear: one problem per critic of an ensemble
 // Returns the number of batch slabs S (same for every problem).
 int launch_multi_wgrad(const WgradProblem *probs, int nprob, int M, int64_t split_stride, int max_splits,
                        cudaStream_t st);

@@ -36,6 +36,7 @@ namespace {
 inline int pad4(int x) { return (x + 3) & ~3; }
 constexpr int kMaxCritics = 8;
 constexpr int kSplits = 128;
+constexpr int kEnsembleBatchMax = 4096;   // up to this batch the ensemble's backward passes share their launches
 constexpr float kBnEps = 1e-5f;        // nn.BatchNorm1d default
 constexpr float kBnMomentum = 0.1f;
 constexpr float kLogSqrt2Pi = 0.91893853320467274178f;
@@ -566,6 +567,8 @@ struct gcrl_sac {
   std::vector<std::vector<float *>> ch;          // critics: [n][L] x [maxB, ldh]
   std::vector<float *> th;                       // target critic scratch [L]
   float *dz[2] = {nullptr, nullptr};
+  std::vector<float *> dzc;                      // [2 n] x [min(maxB, kEnsembleBatchMax), ldh]: per-critic gradient ping-pong
+  int64_t pset = 0;                              // floats per partial-gradient set (one set per critic)
   float *sa = nullptr, *nsa = nullptr, *spi = nullptr, *br = nullptr, *bd = nullptr;
   float *bs = nullptr, *ba = nullptr, *bns = nullptr, *br0 = nullptr, *bd0 = nullptr;
   float *q = nullptr, *qt = nullptr, *y = nullptr, *dq = nullptr;     // [n][maxB], [n][maxB], [maxB], [n][maxB*4]
@@ -654,12 +657,14 @@ void actor_fwd(gcrl_sac *ag, float *rows, const float *eps, int B, bool train, b
   GCRL_LAUNCHED();
 }
 
-void reduce_critic(gcrl_sac *ag, CriticNet &c, const int *splits, int head_splits, cudaStream_t st) {
+void reduce_critic(gcrl_sac *ag, CriticNet &c, const int *splits, int head_splits, cudaStream_t st,
+                   const float *partials = nullptr) {
+  if (partials == nullptr) partials = ag->partials;
   ReduceArgs r{};
   for (int l = 0; l < c.layers; ++l) {
     const int sp = l == c.layers - 1 ? head_splits : splits[l];
-    r.seg[r.nseg++] = SegDesc{c.w_off[l], c.out_d[l] * c.ldw[l], ag->partials, sp, ag->slab, c.w_off[l]};
-    r.seg[r.nseg++] = SegDesc{c.b_off[l], c.out_d[l], ag->partials, sp, ag->slab, c.b_off[l]};
+    r.seg[r.nseg++] = SegDesc{c.w_off[l], c.out_d[l] * c.ldw[l], partials, sp, ag->slab, c.w_off[l]};
+    r.seg[r.nseg++] = SegDesc{c.b_off[l], c.out_d[l], partials, sp, ag->slab, c.b_off[l]};
   }
   r.total = c.total; r.grad = c.g; r.sumsq_partials = ag->sumsq;
   r.metric_partials = nullptr; r.metric_splits = 0; r.metric_scale = 0.f; r.metrics = ag->mdev;
@@ -713,6 +718,55 @@ void critic_update(gcrl_sac *ag, int B, int flags, int mask, cudaStream_t st) {
   critic_metrics_kernel<<<1, 1024, 0, st>>>(ag->q, ag->maxB, n, ag->y, B, ag->mdev + M_CLOSS, 0,
                                             ag->per_on ? ag->per_w : nullptr, ag->per_on ? ag->per_td : nullptr);
   GCRL_LAUNCHED();
+  if (B <= kEnsembleBatchMax) {
+    // the ensemble's backward passes share their launches: one head launch, one weight-gradient and one
+    // input-gradient launch per layer (per-critic gradient buffers and partial sets), then reduce + AdamW per critic
+    HeadBwdArgs hs[kMaxBatchedLinear];
+    for (int i = 0; i < n; ++i) {
+      const CriticNet &c = ag->critic[i];
+      float *part = ag->partials + int64_t(i) * ag->pset;
+      HeadBwdArgs h{};
+      h.mode = 0; h.loss_kind = 0; h.clamp_y = 0; h.nout = 1;
+      h.q = ag->q + int64_t(i) * ag->maxB; h.y_in = ag->y;
+      if (ag->per_on) h.is_w = ag->per_w;
+      h.Hact = ag->ch[i][L - 1]; h.ldh = ag->ldh;
+      h.W = c.W(L); h.ldw = c.ldw[L];
+      h.dZprev = ag->dzc[2 * i]; h.lddz = ag->ldh;
+      h.pW = part + c.w_off[L]; h.w_split_stride = ag->slab;
+      h.pB = part + c.b_off[L]; h.b_split_stride = ag->slab;
+      h.metric_partials = part + ag->slab * kSplits;            // scratch tail, unused
+      h.M = B; h.K = ag->H;
+      hs[i] = h;
+    }
+    const int head_splits = launch_head_bwd_batched(hs, n, kSplits, st);
+    int splits[8] = {};
+    int cur = 0;
+    for (int l = L - 1; l >= 0; --l) {
+      WgradProblem wp[kMaxWgradProblems];
+      for (int i = 0; i < n; ++i) {
+        const CriticNet &c = ag->critic[i];
+        float *part = ag->partials + int64_t(i) * ag->pset;
+        wp[i] = WgradProblem{ag->dzc[2 * i + cur], ag->ldh, l == 0 ? ag->sa : ag->ch[i][l - 1], l == 0 ? ag->ldc : ag->ldh,
+                             part + c.w_off[l], c.ldw[l], part + c.b_off[l], ag->H, l == 0 ? K0 : ag->H};
+      }
+      splits[l] = launch_multi_wgrad(wp, n, B, ag->slab, kSplits, st);
+      if (l > 0) {
+        LinearDgradProblem dg[kMaxBatchedLinear];
+        for (int i = 0; i < n; ++i) {
+          const CriticNet &c = ag->critic[i];
+          dg[i] = LinearDgradProblem{ag->dzc[2 * i + cur], ag->ldh, c.W(l), c.ldw[l], ag->ch[i][l - 1], ag->ldh,
+                                     ag->dzc[2 * i + (cur ^ 1)], ag->ldh};
+        }
+        launch_linear_dgrad_batched(dg, n, B, ag->H, ag->H, st);
+        cur ^= 1;
+      }
+    }
+    for (int i = 0; i < n; ++i) {
+      CriticNet &c = ag->critic[i];
+      reduce_critic(ag, c, splits, head_splits, st, ag->partials + int64_t(i) * ag->pset);
+      if (!dp) adam(ag, c.p, c.m, c.v, c.g, c.total, 0, ag->target[i].p, (flags & 2) != 0, M_CGN + i, st);
+    }
+  } else
   for (int i = 0; i < n; ++i) {
     CriticNet &c = ag->critic[i];
     HeadBwdArgs h{};
@@ -770,6 +824,38 @@ void actor_update(gcrl_sac *ag, int B, int flags, int mask, cudaStream_t st) {
   actor_trunc_kernel<<<1, 1024, 0, st>>>(ag->q, ag->maxB, n, ag->keep, ag->logp, ag->cfg.entropy_coef,
                                         ag->alpha_state + 1, ag->dq, ag->mdev + M_ALOSS, B);
   GCRL_LAUNCHED();
+  if (B <= kEnsembleBatchMax) {        // the ensemble's input-gradient chains share their launches
+    HeadBwdArgs hs[kMaxBatchedLinear];
+    for (int i = 0; i < n; ++i) {
+      const CriticNet &c = ag->critic[i];
+      HeadBwdArgs h{};
+      h.mode = 2; h.nout = 1; h.dz_in = ag->dq + int64_t(i) * ag->maxB * 4;
+      h.Hact = ag->ch[i][L - 1]; h.ldh = ag->ldh;
+      h.W = c.W(L); h.ldw = c.ldw[L];
+      h.dZprev = ag->dzc[2 * i]; h.lddz = ag->ldh;
+      h.pW = nullptr; h.pB = nullptr;            // critic weight gradients are discarded
+      h.M = B; h.K = ag->H;
+      hs[i] = h;
+    }
+    launch_head_bwd_batched(hs, n, kSplits, st);
+    int cur = 0;
+    for (int l = L - 1; l >= 1; --l) {
+      LinearDgradProblem dg[kMaxBatchedLinear];
+      for (int i = 0; i < n; ++i) {
+        const CriticNet &c = ag->critic[i];
+        dg[i] = LinearDgradProblem{ag->dzc[2 * i + cur], ag->ldh, c.W(l), c.ldw[l], ag->ch[i][l - 1], ag->ldh,
+                                   ag->dzc[2 * i + (cur ^ 1)], ag->ldh};
+      }
+      launch_linear_dgrad_batched(dg, n, B, ag->H, ag->H, st);
+      cur ^= 1;
+    }
+    for (int i = 0; i < n; ++i) {                // summed over the critics in index order
+      const CriticNet &c = ag->critic[i];
+      action_grad_acc_kernel<<<blocks_for(B, 8), 256, 0, st>>>(ag->dzc[2 * i + cur], ag->ldh, c.W(0), c.ldw[0], D,
+                                                              ag->dact, B, ag->H, A, i > 0 ? 1 : 0);
+      GCRL_LAUNCHED();
+    }
+  } else
   for (int i = 0; i < n; ++i) {
     const CriticNet &c = ag->critic[i];
     HeadBwdArgs h{};
@@ -1042,6 +1128,7 @@ int gcrl_sac_create(gcrl_sac **out, int device, const gcrl_sac_config *cfg) {
       for (int l = 0; l < L; ++l) ag->ch[i].push_back(dev_alloc<float>(act));
     for (int l = 0; l < L; ++l) ag->th.push_back(dev_alloc<float>(act));
     for (auto &p : ag->dz) p = dev_alloc<float>(act);
+    for (int i = 0; i < 2 * n; ++i) ag->dzc.push_back(dev_alloc<float>(size_t(std::min<int64_t>(mb, kEnsembleBatchMax)) * ag->ldh));
     for (float **p : {&ag->sa, &ag->nsa, &ag->spi}) *p = dev_alloc<float>(mb * ag->ldc);
     for (float **p : {&ag->br, &ag->bd, &ag->br0, &ag->bd0, &ag->y, &ag->logp, &ag->per_w, &ag->per_td}) *p = dev_alloc<float>(mb);
     ag->bs = dev_alloc<float>(mb * D); ag->bns = dev_alloc<float>(mb * D); ag->ba = dev_alloc<float>(mb * A);
@@ -1049,7 +1136,8 @@ int gcrl_sac_create(gcrl_sac **out, int device, const gcrl_sac_config *cfg) {
     for (float **p : {&ag->act4, &ag->std4, &ag->gate4, &ag->dact, &ag->eps_next, &ag->eps_cur}) *p = dev_alloc<float>(mb * 4);
     ag->dzh = dev_alloc<float>(mb * 8);
     ag->slab = std::max(ag->actor.total, ag->critic[0].total);
-    ag->partials = dev_alloc<float>(size_t(kSplits) * ag->slab + size_t(kSplits) * 4);
+    ag->pset = int64_t(kSplits) * ag->slab + int64_t(kSplits) * 4;
+    ag->partials = dev_alloc<float>(size_t(ag->pset) * n);
     ag->sumsq = dev_alloc<float>(size_t(reduce_grid(int(ag->slab))) + 8);
     ag->mdev = dev_alloc<float>(32);
     GCRL_CUDA(cudaMemset(ag->mdev, 0, 32 * 4));
@@ -1079,6 +1167,7 @@ int gcrl_sac_destroy(gcrl_sac *ag) {
   for (int i = 0; i < ag->n; ++i) { ag->critic[i].destroy(); ag->target[i].destroy(); }
   for (auto &v : {ag->xhat, ag->ah, ag->th}) for (float *p : v) cudaFree(p);
   for (auto &v : ag->ch) for (float *p : v) cudaFree(p);
+  for (float *p : ag->dzc) cudaFree(p);
   for (float *p : {ag->invstd, ag->dz[0], ag->dz[1], ag->sa, ag->nsa, ag->spi, ag->br, ag->bd, ag->bs, ag->ba, ag->bns,
                    ag->br0, ag->bd0, ag->q, ag->qt, ag->y, ag->dq, ag->logp, ag->act4, ag->std4, ag->gate4, ag->dact,
                    ag->dzh, ag->eps_next, ag->eps_cur, ag->partials, ag->sumsq, ag->mdev, ag->alpha_state, ag->d_io,
