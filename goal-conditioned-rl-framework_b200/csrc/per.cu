@@ -45,6 +45,14 @@ constexpr int kScanTile = kScanThreads * kScanItems;
 constexpr double kTwo52 = 4503599627370496.0;          // 2^52
 constexpr double kTwo53 = 9007199254740992.0;
 
+// Per-call scalars of a prioritised draw, read from device memory so that the captured graph of the draw can be
+// replayed while the ring keeps turning (start moves with every push) and beta anneals.
+struct PerCall {
+  int64_t start;
+  float neg_beta;
+  int pad;
+};
+
 struct ReplayGeom {
   float *rows;
   float *prio;
@@ -69,9 +77,10 @@ __global__ void fill_i32_kernel(int *p, int64_t n, int v) {
 // ---- P.sum() ---------------------------------------------------------------------------------
 // One 8-lane group per leaf [leaf_off[l], leaf_off[l+1]) of NumPy's pairwise tree.
 __global__ void __launch_bounds__(256)
-leaf_sum_kernel(const float *__restrict__ prio, int64_t start, int64_t cap, const int *__restrict__ leaf_off,
-                int n_leaves, float *__restrict__ vals, int *__restrict__ flags) {
+leaf_sum_kernel(const float *__restrict__ prio, const PerCall *__restrict__ call, int64_t cap,
+                const int *__restrict__ leaf_off, int n_leaves, float *__restrict__ vals, int *__restrict__ flags) {
   if (blockIdx.x == 0 && threadIdx.x == 0) *flags = 0;       // the inexact-cumsum flag of this sample() call
+  const int64_t start = call->start;
   const int lane8 = threadIdx.x & 7;
   const int leaf = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
   const bool live = leaf < n_leaves;
@@ -96,18 +105,27 @@ leaf_sum_kernel(const float *__restrict__ prio, int64_t start, int64_t cap, cons
 }
 
 // Folds the tree: nodes are grouped by height, children precede parents; one CTA, one barrier per level.
+// SMEM: the node values live in shared memory (a level costs a barrier instead of an L2 round trip);
+// used whenever leaves + internal nodes fit (up to ~3M priorities), else the values stay in global memory.
+template <bool SMEM>
 __global__ void __launch_bounds__(1024)
 tree_fold_kernel(float *__restrict__ vals, const int *__restrict__ node_l, const int *__restrict__ node_r,
                  const int *__restrict__ group_off, int n_groups, int n_leaves, float *__restrict__ psum) {
+  extern __shared__ float sv[];
+  float *v = SMEM ? sv : vals;
+  if (SMEM) {
+    for (int j = threadIdx.x; j < n_leaves; j += blockDim.x) sv[j] = vals[j];
+    __syncthreads();
+  }
   for (int g = 0; g < n_groups; ++g) {
     for (int j = group_off[g] + threadIdx.x; j < group_off[g + 1]; j += blockDim.x)
-      vals[n_leaves + j] = __fadd_rn(vals[node_l[j]], vals[node_r[j]]);
+      v[n_leaves + j] = __fadd_rn(v[node_l[j]], v[node_r[j]]);
     __syncthreads();
   }
   if (threadIdx.x == 0) {
     const int n_internal = group_off[n_groups];
     // np.add.reduce seeds with the identity: 0.0f + tree
-    *psum = __fadd_rn(0.0f, vals[n_internal > 0 ? n_leaves + n_internal - 1 : 0]);
+    *psum = __fadd_rn(0.0f, v[n_internal > 0 ? n_leaves + n_internal - 1 : 0]);
   }
 }
 
@@ -120,9 +138,10 @@ __device__ __forceinline__ int64_t shfl_up_i64(int64_t v, int d) {
 }
 
 __global__ void __launch_bounds__(kScanThreads)
-normalise_scan_kernel(const float *__restrict__ prio, int64_t start, int64_t cap, int64_t n,
+normalise_scan_kernel(const float *__restrict__ prio, const PerCall *__restrict__ call, int64_t cap, int64_t n,
                       const float *__restrict__ psum, float *__restrict__ pnorm, int64_t *__restrict__ fixed,
                       int64_t *__restrict__ tile_sum, int *__restrict__ flags) {
+  const int64_t start = call->start;
   __shared__ float sp[kScanTile];
   __shared__ int64_t warp_tot[kScanThreads / 32];
   const int64_t base = int64_t(blockIdx.x) * kScanTile;
@@ -497,9 +516,12 @@ __device__ __forceinline__ void scatter_row(const ReplayGeom &g, int64_t slot, i
 }
 
 __global__ void __launch_bounds__(256)
-per_draw_kernel(ReplayGeom g, int64_t start, int64_t n, const double *__restrict__ cdf, const float *__restrict__ pnorm,
-                const double *__restrict__ u, int B, float neg_beta, float *s, float *a, float *r, float *ns, float *d,
-                float *__restrict__ w_raw, int64_t *__restrict__ pos_out, int64_t *__restrict__ slot_out) {
+per_draw_kernel(ReplayGeom g, const PerCall *__restrict__ call, int64_t n, const double *__restrict__ cdf,
+                const float *__restrict__ pnorm, const double *__restrict__ u, int B, float *s, float *a, float *r,
+                float *ns, float *d, float *__restrict__ w_raw, int64_t *__restrict__ pos_out,
+                int64_t *__restrict__ slot_out) {
+  const int64_t start = call->start;
+  const float neg_beta = call->neg_beta;
   const int lane = threadIdx.x & 31;
   const int64_t b = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
   if (b >= B) return;
@@ -584,6 +606,20 @@ struct gcrl_replay {
   int *d_flags = nullptr, *winner = nullptr;
   // pairwise-sum tree of the current N
   int64_t tree_n = -1;
+  bool fold_smem_set = false;
+  // the draw as a captured graph: (n, B, output pointers) -> exec; recaptured when the key repeats
+  PerCall *d_call = nullptr;
+  struct DrawKey {
+    int64_t n = -1, B = -1;
+    const void *ptr[6] = {};
+    bool operator==(const DrawKey &o) const {
+      return n == o.n && B == o.B && std::memcmp(ptr, o.ptr, sizeof(ptr)) == 0;
+    }
+  } graph_key, last_key;
+  cudaGraphExec_t graph_exec = nullptr;
+  uint64_t graph_kernels = 0;
+  cudaStream_t cap_stream = nullptr;
+  bool use_graphs = true;
   int n_leaves = 0, n_groups = 0;
   size_t tree_cap = 0;
   int *d_leaf_off = nullptr, *d_node_l = nullptr, *d_node_r = nullptr, *d_group_off = nullptr;
@@ -602,6 +638,7 @@ namespace {
 void ensure_batch(gcrl_replay *h, int64_t B, cudaStream_t st) {
   if (B <= h->batch_cap) return;
   GCRL_CUDA(cudaStreamSynchronize(st));
+  if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
   for (void *p : {(void *)h->d_u, (void *)h->d_wraw, (void *)h->d_pos, (void *)h->d_slot})
     if (p) GCRL_CUDA(cudaFree(p));
   h->batch_cap = std::max<int64_t>(B, 1024);
@@ -647,6 +684,7 @@ void build_tree(gcrl_replay *h, int64_t n, cudaStream_t st) {
   const size_t need = size_t(L) + 2;
   if (need > h->tree_cap) {
     GCRL_CUDA(cudaStreamSynchronize(st));
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }   // it holds the old tables
     for (void *p : {(void *)h->d_leaf_off, (void *)h->d_node_l, (void *)h->d_node_r, (void *)h->d_vals})
       if (p) GCRL_CUDA(cudaFree(p));
     h->tree_cap = need * 2;
@@ -711,6 +749,12 @@ int gcrl_replay_create(gcrl_replay **out, int device, int64_t capacity, int stat
       }
       h->d_psum = dev_alloc<float>(1);
       h->d_flags = dev_alloc<int>(1);
+      h->d_call = dev_alloc<PerCall>(1);
+      GCRL_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+      {
+        const char *ng = getenv("GCRL_B200_NO_GRAPH");
+        h->use_graphs = !(ng && ng[0] == '1');
+      }
       h->winner = dev_alloc<int>(size_t(capacity));
       fill_i32_kernel<<<blocks_for(capacity, 256 * 8), 256>>>(h->winner, capacity, -1);
       GCRL_LAUNCHED();
@@ -736,6 +780,9 @@ int gcrl_replay_destroy(gcrl_replay *h) {
                   (void *)h->d_leaf_off, (void *)h->d_node_l, (void *)h->d_node_r, (void *)h->d_group_off,
                   (void *)h->d_vals, (void *)h->d_u, (void *)h->d_wraw, (void *)h->d_pos, (void *)h->d_slot})
     if (p) cudaFree(p);
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  if (h->d_call) cudaFree(h->d_call);
   h->stage.destroy();
   delete h;
   GCRL_API_END
@@ -807,20 +854,37 @@ int gcrl_replay_sample_prioritized(gcrl_replay *h, int64_t B, const double *u_ho
   ensure_batch(h, B, st);
   const int64_t n = h->len, start = h->start(), cap = h->g.cap;
   build_tree(h, n, st);
-  int sl;
-  char *p = h->stage.acquire(size_t(B) * 8, &sl);
-  std::memcpy(p, u_host, size_t(B) * 8);
-  GCRL_CUDA(cudaMemcpyAsync(h->d_u, p, size_t(B) * 8, cudaMemcpyHostToDevice, st));
-  h->stage.release(sl, st);
-
-  leaf_sum_kernel<<<blocks_for(int64_t(h->n_leaves) * 8, 256), 256, 0, st>>>(h->g.prio, start, cap, h->d_leaf_off,
+  {   // per-call scalars + the B uniforms: one pinned slot, two small copies
+    int sl;
+    char *p = h->stage.acquire(size_t(B) * 8 + sizeof(PerCall), &sl);
+    PerCall hc{start, float(-beta), 0};
+    std::memcpy(p, &hc, sizeof(PerCall));
+    std::memcpy(p + sizeof(PerCall), u_host, size_t(B) * 8);
+    GCRL_CUDA(cudaMemcpyAsync(h->d_call, p, sizeof(PerCall), cudaMemcpyHostToDevice, st));
+    GCRL_CUDA(cudaMemcpyAsync(h->d_u, p + sizeof(PerCall), size_t(B) * 8, cudaMemcpyHostToDevice, st));
+    h->stage.release(sl, st);
+  }
+  auto launch_all = [&](cudaStream_t st) {
+  leaf_sum_kernel<<<blocks_for(int64_t(h->n_leaves) * 8, 256), 256, 0, st>>>(h->g.prio, h->d_call, cap, h->d_leaf_off,
                                                                            h->n_leaves, h->d_vals, h->d_flags);
   GCRL_LAUNCHED();
-  tree_fold_kernel<<<1, 1024, 0, st>>>(h->d_vals, h->d_node_l, h->d_node_r, h->d_group_off, h->n_groups, h->n_leaves,
-                                       h->d_psum);
-  GCRL_LAUNCHED();
+  {
+    const size_t fold_smem = size_t(2 * h->n_leaves) * sizeof(float);
+    if (fold_smem <= size_t(200) * 1024) {
+      if (!h->fold_smem_set) {
+        GCRL_CUDA(cudaFuncSetAttribute(tree_fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        h->fold_smem_set = true;
+      }
+      tree_fold_kernel<true><<<1, 1024, fold_smem, st>>>(h->d_vals, h->d_node_l, h->d_node_r, h->d_group_off,
+                                                         h->n_groups, h->n_leaves, h->d_psum);
+    } else {
+      tree_fold_kernel<false><<<1, 1024, 0, st>>>(h->d_vals, h->d_node_l, h->d_node_r, h->d_group_off, h->n_groups,
+                                                  h->n_leaves, h->d_psum);
+    }
+    GCRL_LAUNCHED();
+  }
   const int tiles = blocks_for(n, kScanTile);
-  normalise_scan_kernel<<<tiles, kScanThreads, 0, st>>>(h->g.prio, start, cap, n, h->d_psum, h->pnorm, h->fixed,
+  normalise_scan_kernel<<<tiles, kScanThreads, 0, st>>>(h->g.prio, h->d_call, cap, n, h->d_psum, h->pnorm, h->fixed,
                                                         h->tile_sum, h->d_flags);
   GCRL_LAUNCHED();
   tile_scan_kernel<<<1, 1024, 0, st>>>(h->tile_sum, tiles, h->d_total, h->d_flags);
@@ -843,11 +907,45 @@ int gcrl_replay_sample_prioritized(gcrl_replay *h, int64_t B, const double *u_ho
   }
   cdf_divide_kernel<<<std::min(tiles, sm_count() * 8), 256, 0, st>>>(cdf, n, h->d_last, h->d_flags);
   GCRL_LAUNCHED();
-  per_draw_kernel<<<blocks_for(B * 32, 256), 256, 0, st>>>(h->g, start, n, cdf, h->pnorm, h->d_u, int(B), float(-beta),
-                                                          s, a, r, ns, d, h->d_wraw, h->d_pos, h->d_slot);
+  per_draw_kernel<<<blocks_for(B * 32, 256), 256, 0, st>>>(h->g, h->d_call, n, cdf, h->pnorm, h->d_u, int(B), s, a, r, ns, d,
+                                                          h->d_wraw, h->d_pos, h->d_slot);
   GCRL_LAUNCHED();
   weight_norm_kernel<<<1, 1024, 0, st>>>(h->d_wraw, weights_dev, int(B));
   GCRL_LAUNCHED();
+  };
+  // The draw is 11 small launches: replayed as one graph once the same (length, batch, outputs) repeats -- i.e.
+  // as soon as the ring is full; while it is still filling every call has a new length and launches directly.
+  gcrl_replay::DrawKey key;
+  key.n = n; key.B = B;
+  const void *ptrs[6] = {s, a, r, ns, d, weights_dev};
+  std::memcpy(key.ptr, ptrs, sizeof(ptrs));
+  if (h->use_graphs && h->graph_exec != nullptr && key == h->graph_key) {
+    GCRL_CUDA(cudaGraphLaunch(h->graph_exec, st));
+    count_launch(h->graph_kernels);
+  } else if (h->use_graphs && key == h->last_key) {
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    const uint64_t before = launch_counter();
+    GCRL_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      launch_all(h->cap_stream);
+    } catch (...) {
+      cudaStreamEndCapture(h->cap_stream, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    GCRL_CUDA(cudaStreamEndCapture(h->cap_stream, &graph));
+    h->graph_kernels = launch_counter() - before;          // recorded, not executed, by the capture
+    count_launch(uint64_t(0) - h->graph_kernels);
+    GCRL_CUDA(cudaGraphInstantiate(&h->graph_exec, graph, 0));
+    GCRL_CUDA(cudaGraphDestroy(graph));
+    h->graph_key = key;
+    GCRL_CUDA(cudaGraphLaunch(h->graph_exec, st));
+    count_launch(h->graph_kernels);
+  } else {
+    launch_all(st);
+  }
+  h->last_key = key;
   h->last_B = B;
   if (idx_host_out != nullptr) {
     GCRL_CUDA(cudaMemcpyAsync(idx_host_out, h->d_pos, size_t(B) * 8, cudaMemcpyDeviceToHost, st));
