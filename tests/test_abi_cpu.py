@@ -45,6 +45,38 @@ def test_agent_config_struct_matches_header():
     assert ctypes.sizeof(AgentConfig) == 4 * len(fields)
 
 
+def test_sac_config_struct_matches_header():
+    from gcrl_b200._lib import SacConfig
+    src = open(HEADER).read()
+    body = re.search(r"typedef struct gcrl_sac_config \{(.*?)\} gcrl_sac_config;", src, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in re.findall(r"(?:int32_t|float)\s+([a-z_0-9, ]+);", body):
+        fields += [f.strip() for f in decl.split(",")]
+    assert fields == [f[0] for f in SacConfig._fields_]
+    assert ctypes.sizeof(SacConfig) == 4 * len(fields)
+
+
+def test_header_compiles_as_plain_c_and_struct_sizes_agree(tmp_path):
+    """The boundary is a C ABI: the header must be consumable by a C compiler (no C++ in the signatures), and the
+    structs the Python binding mirrors must have the sizes the C compiler gives them."""
+    import shutil
+    import subprocess
+    from gcrl_b200._lib import AgentConfig, SacConfig
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "gcrl_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %d\\n", sizeof(gcrl_agent_config), sizeof(gcrl_sac_config), '
+                   'GCRL_ABI_VERSION); return 0; }\n')
+    exe = tmp_path / "abi"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.dirname(HEADER), str(src), "-o", str(exe)],
+                   check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert [int(x) for x in out] == [ctypes.sizeof(AgentConfig), ctypes.sizeof(SacConfig), 3]
+
+
 def test_no_cpu_fallback_without_device():
     """Without a GPU the product must fail loudly, never compute on the host."""
     from gcrl_b200 import _lib

@@ -322,3 +322,38 @@ def test_true_resume_is_bit_identical(tmp_path, algo):
     for n1, n2 in zip((a1.actor, a1.target_actor), (a2.actor, a2.target_actor)):
         for (w, b), (w2, b2) in zip(n1.layers(), n2.layers()):
             assert np.array_equal(w, w2) and np.array_equal(b, b2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("algo", ["ddpg", "td3"])
+def test_exploration_select_action_consumes_the_reference_generators(algo):
+    """select_action(eval_action=False), src/agent.py:1345-1360 (DDPG) / :253-263 (TD3): DDPG first draws
+    random.random() and, below 0.2, returns clip(np.random.randn(n, A)); otherwise both add
+    np.random.normal(0, noise_std) to the (DDPG: twice-tanh'd) actor output and clip.  Seeded alike, the product
+    must consume both global generators exactly like that and return those values."""
+    import random
+    from gcrl_b200 import DDPG, TD3Agent
+    cls = DDPG if algo == "ddpg" else TD3Agent
+    D, A, n = 10, 3, 5
+    ag = cls(D, A, make_config(hidden_dim=64, layer_count=3, batch_size=64, noise_std=0.3), None, 1, 40)
+    rng = np.random.default_rng(2)
+    xs = [rng.standard_normal((n, D)).astype(np.float32) for _ in range(40)]
+    det = [np.asarray(ag.select_action(x, eval_action=True)) for x in xs]       # consumes no generator
+    random.seed(11)
+    np.random.seed(11)
+    got = [np.asarray(ag.select_action(x)) for x in xs]
+    end_state = (random.random(), np.random.random_sample())
+    random.seed(11)
+    np.random.seed(11)
+    branches = 0
+    for x, d_, g_ in zip(xs, det, got):
+        if algo == "ddpg" and random.random() < 0.2:
+            want = np.clip(np.random.randn(n, A), a_min=-1, a_max=1)
+            branches += 1
+        else:
+            # DDPG's eval output carries the reference's second tanh; TD3's is the raw actor output, tanh'd here
+            base = d_ if algo == "ddpg" else np.tanh(d_)
+            want = np.clip(base + np.random.normal(0, 0.3, size=base.shape), -1, 1)
+        np.testing.assert_allclose(g_, want, rtol=1e-6, atol=1e-6)
+    assert (random.random(), np.random.random_sample()) == end_state
+    assert algo == "td3" or 0 < branches < 40
