@@ -94,12 +94,25 @@ int gcrl_pyrandom_sample_range(uint32_t *mt624, int *pos, int64_t n, int64_t k, 
       pool[j] = pool[size_t(n - i - 1)];
     }
   } else {
-    std::unordered_set<int64_t> selected;
-    selected.reserve(size_t(k) * 2);
+    // membership set of the positions drawn so far (CPython uses a set; only membership matters): open
+    // addressing over a power-of-two table, no allocation per element
+    size_t cap = 16;
+    while (cap < size_t(k) * 4) cap <<= 1;
+    std::vector<int64_t> table(cap, -1);
+    const size_t mask = cap - 1;
+    auto slot_of = [&](int64_t j) {
+      size_t h = size_t(uint64_t(j) * 0x9E3779B97F4A7C15ull >> 32) & mask;
+      while (table[h] != -1 && table[h] != j) h = (h + 1) & mask;
+      return h;
+    };
     for (int64_t i = 0; i < k; ++i) {
       int64_t j = int64_t(g.randbelow(uint64_t(n)));
-      while (selected.count(j)) j = int64_t(g.randbelow(uint64_t(n)));
-      selected.insert(j);
+      size_t h = slot_of(j);
+      while (table[h] == j) {
+        j = int64_t(g.randbelow(uint64_t(n)));
+        h = slot_of(j);
+      }
+      table[h] = j;
       out[i] = j;
     }
   }

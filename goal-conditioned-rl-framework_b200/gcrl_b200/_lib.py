@@ -183,7 +183,7 @@ def require_cuda():
 
 
 def np_ptr(arr):
-    return arr.ctypes.data_as(vp)
+    return vp(arr.ctypes.data)      # the caller keeps `arr` alive for the duration of the call
 
 
 def current_stream(device_index):
@@ -219,17 +219,31 @@ def py_randint_seq(lo, hi):
     return out
 
 
+_mt_cache = None      # (state tuple we returned last, its 624 words as uint32 array, pos)
+
+
 def py_sample_range_from(state, n, k):
     """(positions, state_after) of random.sample(range(n), k) started from ``state`` (a random.getstate()
-    tuple); the interpreter's global generator is not touched."""
+    tuple); the interpreter's global generator is not touched.  Passing back the very tuple object this function
+    returned last skips the tuple -> array conversion (the dominant host cost of a draw)."""
     import numpy as np
-    version, internal, gauss = state
-    if version != 3 or len(internal) != 625:
-        raise RuntimeError("unexpected random.getstate() layout")
-    mt, pos = np.array(internal[:-1], dtype=np.uint32), C.c_int(internal[-1])
+    global _mt_cache
+    cached = _mt_cache
+    if cached is not None and cached[0] is state:
+        mt, pos, gauss = cached[1], C.c_int(cached[2]), state[2]
+    else:
+        version, internal, gauss = state
+        if version != 3 or len(internal) != 625:
+            raise RuntimeError("unexpected random.getstate() layout")
+        mt, pos = np.array(internal[:-1], dtype=np.uint32), C.c_int(internal[-1])
     out = np.empty(int(k), np.int64)
+    _mt_cache = None                     # mt is advanced in place
     check(lib.gcrl_pyrandom_sample_range(np_ptr(mt), C.byref(pos), int(n), int(k), np_ptr(out)))
-    return out, (3, tuple(mt.tolist()) + (pos.value,), gauss)
+    words = mt.tolist()
+    words.append(pos.value)
+    after = (3, tuple(words), gauss)
+    _mt_cache = (after, mt, pos.value)
+    return out, after
 
 
 def py_sample_range(n, k):

@@ -499,9 +499,15 @@ class _AgentBase:
     # the reference's interleaving.
     _pre = None
 
+    _known_state = None     # the tuple the global generator was just set to (by _take_predrawn), if still current
+
     def _predraw(self, B):
         n = len(self.buffer)
-        before = random.getstate()
+        # right after a successful _take_predrawn the global state IS the tuple it installed: no getstate(),
+        # and the C mirror recognises its own tuple and skips the 624-word conversion
+        before, self._known_state = self._known_state, None
+        if before is None:
+            before = random.getstate()
         idx, after = _lib.py_sample_range_from(before, n, B)     # C mirror of random.sample; global state untouched
         self._pre = (before, after, idx, n, B)
 
@@ -510,7 +516,9 @@ class _AgentBase:
         n = len(self.buffer)
         if pre is not None and pre[3] == n and pre[4] == B and random.getstate() == pre[0]:
             random.setstate(pre[1])
+            self._known_state = pre[1]
             return pre[2]
+        self._known_state = None
         return _lib.py_sample_range(n, B)
 
     def read_metrics(self):
