@@ -410,6 +410,22 @@ def gpu_main(args):
     e2e_value = world * B * n_e2e / (ms_e2e * 1e-3)
     assert all(np.isfinite(float(x)) for x in info), info
 
+    # the same public call with index_source="device" (positions and future offsets drawn on the GPU instead of
+    # mirroring the interpreter's Mersenne-Twister stream): what the host-side stream emulation costs
+    agent.index_source = "device"
+    agent.buffer.index_source = "device"
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    w0 = time.perf_counter()
+    for i in range(n_e2e):
+        info = e2e_step(i)
+    torch.cuda.synchronize()
+    ms_e2e_dev = (time.perf_counter() - w0) * 1e3
+    step += n_e2e
+    agent.index_source = "host"
+    agent.buffer.index_source = "host"
+
     # ---- kernel rooflines (rank 0, N=1): the HER sampler alone, CUDA events on its stream ----
     agent.index_source = "device"
     agent.buffer.index_source = "device"
@@ -576,7 +592,10 @@ def gpu_main(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / n_e2e, "steps": n_e2e,
                     "api": "DDPG.update(step) with host random.sample index stream + metric read-back; "
-                           "16 episodes ingested every 40 updates"},
+                           "16 episodes ingested every 40 updates",
+                    "device_index_stream": {"ms_per_step": ms_e2e_dev / n_e2e,
+                                            "value": world * B * n_e2e / (ms_e2e_dev * 1e-3),
+                                            "note": "same call, index_source='device' (rank-local wall clock)"}},
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "rooflines": rooflines, "sweep": sweep,
             "variants": variants,
             "cpu_baseline": None if cpu is None else {k_: cpu[k_] for k_ in ("value", "unit", "cores", "kind", "sample")},

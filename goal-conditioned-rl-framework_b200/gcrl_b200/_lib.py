@@ -192,58 +192,58 @@ def current_stream(device_index):
 
 
 # -- CPython `random` mirror (csrc/pyrandom.cu): exact draws from the interpreter's global stream ------------
-def _mt_load():
-    import random
+# The generator words of the last state tuple this module produced, kept as a uint32 array: converting a
+# random.getstate() tuple (625 Python ints) costs ~55 us, recognising one we made ourselves ~10 us (by value)
+# or nothing (same object).  The array is advanced in place by the C mirror, so the cache is dropped before
+# every call and re-armed with the tuple of the new state afterwards.
+_mt_cache = None      # (state tuple, its 624 words as uint32 array, pos)
 
+
+def _words_of(state):
+    """(uint32[624] array -- owned by the caller from here on, pos, gauss) for a random.getstate() tuple."""
     import numpy as np
-    version, internal, gauss = random.getstate()
+    global _mt_cache
+    cached, _mt_cache = _mt_cache, None
+    if cached is not None and (cached[0] is state or cached[0] == state):
+        return cached[1], C.c_int(cached[2]), state[2]
+    version, internal, gauss = state
     if version != 3 or len(internal) != 625:
         raise RuntimeError("unexpected random.getstate() layout")
     return np.array(internal[:-1], dtype=np.uint32), C.c_int(internal[-1]), gauss
 
 
-def _mt_store(mt, pos, gauss):
-    import random
-    random.setstate((3, tuple(mt.tolist()) + (pos.value,), gauss))
+def _state_of(mt, pos, gauss):
+    """The random.setstate() tuple of advanced words; remembers the pair."""
+    global _mt_cache
+    words = mt.tolist()
+    words.append(pos.value)
+    state = (3, tuple(words), gauss)
+    _mt_cache = (state, mt, pos.value)
+    return state
 
 
 def py_randint_seq(lo, hi):
     """[random.randint(lo[i], hi[i]) for i in range(len(lo))], consuming the global stream identically."""
+    import random
+
     import numpy as np
     lo = np.ascontiguousarray(lo, np.int32)
     hi = np.ascontiguousarray(hi, np.int32)
     out = np.empty(lo.shape, np.int32)
-    mt, pos, gauss = _mt_load()
+    mt, pos, gauss = _words_of(random.getstate())
     check(lib.gcrl_pyrandom_randint(np_ptr(mt), C.byref(pos), lo.size, np_ptr(lo), np_ptr(hi), np_ptr(out)))
-    _mt_store(mt, pos, gauss)
+    random.setstate(_state_of(mt, pos, gauss))
     return out
-
-
-_mt_cache = None      # (state tuple we returned last, its 624 words as uint32 array, pos)
 
 
 def py_sample_range_from(state, n, k):
     """(positions, state_after) of random.sample(range(n), k) started from ``state`` (a random.getstate()
-    tuple); the interpreter's global generator is not touched.  Passing back the very tuple object this function
-    returned last skips the tuple -> array conversion (the dominant host cost of a draw)."""
+    tuple); the interpreter's global generator is not touched."""
     import numpy as np
-    global _mt_cache
-    cached = _mt_cache
-    if cached is not None and cached[0] is state:
-        mt, pos, gauss = cached[1], C.c_int(cached[2]), state[2]
-    else:
-        version, internal, gauss = state
-        if version != 3 or len(internal) != 625:
-            raise RuntimeError("unexpected random.getstate() layout")
-        mt, pos = np.array(internal[:-1], dtype=np.uint32), C.c_int(internal[-1])
+    mt, pos, gauss = _words_of(state)
     out = np.empty(int(k), np.int64)
-    _mt_cache = None                     # mt is advanced in place
     check(lib.gcrl_pyrandom_sample_range(np_ptr(mt), C.byref(pos), int(n), int(k), np_ptr(out)))
-    words = mt.tolist()
-    words.append(pos.value)
-    after = (3, tuple(words), gauss)
-    _mt_cache = (after, mt, pos.value)
-    return out, after
+    return out, _state_of(mt, pos, gauss)
 
 
 def py_sample_range(n, k):
