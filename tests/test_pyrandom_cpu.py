@@ -52,3 +52,56 @@ def test_future_draws_of_the_buffer_use_the_same_stream():
         random.seed(T)
         got = buf._draw_future(T)
         assert np.array_equal(got, want) and random.getstate() == after
+
+
+def test_word_cache_survives_foreign_consumers_and_state_restores():
+    """The mirror keeps the generator words of the last state it produced (gcrl_b200/_lib.py::_words_of).  The
+    cache is keyed by that exact state, so draws by anybody else, reseeds and setstate() calls in between must
+    leave the stream identical to the interpreter's own."""
+    import random
+
+    import numpy as np
+    from gcrl_b200 import _lib
+    lo = np.repeat(np.arange(1, 9, dtype=np.int32), 3)
+    hi = np.full(lo.shape, 8, np.int32)
+
+    def run(sample, randint):
+        random.seed(21)
+        out = []
+        saved = None
+        for i in range(60):
+            out.append(list(sample(1000 + i, 7)))
+            if i % 3 == 0:
+                out.append(random.random())                  # a foreign consumer between two mirrored draws
+            out.append(list(randint(lo, hi)))
+            if i == 20:
+                saved = random.getstate()
+            if i == 40:
+                random.setstate(saved)                       # jump back: the cached words are stale now
+            if i == 50:
+                random.seed(5)
+        out.append(random.getstate())
+        return out
+
+    got = run(_lib.py_sample_range, _lib.py_randint_seq)
+    want = run(lambda n, k: random.sample(range(n), k), lambda l, h: [random.randint(int(a), int(b)) for a, b in zip(l, h)])
+    assert got == want
+
+
+def test_predraw_from_a_state_does_not_touch_the_global_generator():
+    import random
+
+    from gcrl_b200 import _lib
+    random.seed(8)
+    before = random.getstate()
+    idx, after = _lib.py_sample_range_from(before, 5000, 64)
+    assert random.getstate() == before
+    idx2, after2 = _lib.py_sample_range_from(after, 5000, 64)      # chained on its own tuple (cache hit)
+    assert random.getstate() == before
+    want = random.sample(range(5000), 64)
+    assert list(idx) == want and random.getstate() == after
+    want2 = random.sample(range(5000), 64)
+    assert list(idx2) == want2 and random.getstate() == after2
+    # a stale tuple (neither the cached object nor equal to it) still converts correctly
+    idx3, _ = _lib.py_sample_range_from(before, 5000, 64)
+    assert list(idx3) == want
