@@ -465,10 +465,6 @@ __global__ void alpha_step_kernel(const float *__restrict__ mean_in, const float
   st[3] = v;
 }
 
-__global__ void polyak_plain_kernel(float *__restrict__ t, const float *__restrict__ s, int n, float tau, float omt) {
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
-    t[e] = tau * s[e] + omt * t[e];
-}
 
 // ---- parameter containers ----------------------------------------------------------------------
 struct CriticNet {
@@ -593,22 +589,6 @@ enum : int { M_CLOSS = 0 /*[8]*/, M_TD = 8, M_Q = 9, M_CGN = 10 /*[8]*/, M_ALOSS
 
 int blocks_for(int64_t work, int per_block) {
   return int(std::max<int64_t>(1, std::min<int64_t>((work + per_block - 1) / per_block, int64_t(sm_count()) * 8)));
-}
-
-void critic_hidden_fwd(gcrl_sac *ag, const CriticNet &c, const float *X, const std::vector<float *> &acts, int B,
-                       cudaStream_t st) {
-  const float *in = X;
-  int ldin = ag->ldc, K = ag->D + ag->A;
-  for (int l = 0; l < ag->L; ++l) {
-    launch_linear_fwd(in, ldin, c.W(l), c.ldw[l], c.b(l), acts[l], ag->ldh, B, ag->H, K, ACT_LEAKY, st);
-    in = acts[l]; ldin = ag->ldh; K = ag->H;
-  }
-}
-
-void critic_fwd(gcrl_sac *ag, const CriticNet &c, const float *X, const std::vector<float *> &acts, float *q_out,
-                int B, cudaStream_t st) {
-  critic_hidden_fwd(ag, c, X, acts, B, st);
-  launch_head_fwd(acts[ag->L - 1], ag->ldh, c.W(ag->L), c.ldw[ag->L], c.b(ag->L), q_out, 1, 0, B, ag->H, 1, 0, st);
 }
 
 // The whole ensemble on the same input rows: one launch per layer (blockIdx.z = critic) instead of n.
