@@ -140,6 +140,11 @@ struct gcrl_agent {
   float *dzh = nullptr;                    // fused path: critic head dL/dq [maxB]
   float *per_w = nullptr, *per_td = nullptr;   // prioritised replay: importance weights in, TD errors out [maxB]
   bool per_on = false;                     // flags bit3 of the update being issued
+  // single-GPU update: the reduction of a network's partial gradients is deferred to its optimiser step and both
+  // run as one cooperative launch (optim.cu: reduce_adam_kernel)
+  bool fuse_opt = false, defer_now = false;
+  bool pending[NUM_NETS] = {};
+  ReduceArgs pending_r[NUM_NETS];
   bool use_fused = true, use_cluster = false;
   int dp_B = -1, dp_flags = -1;            // the update the data-parallel phases belong to
   // data-parallel averaging over NVLink peer memory (gcrl_agent_dp_connect)
@@ -245,6 +250,12 @@ void reduce_grads(gcrl_agent *ag, Net &n, const int *splits, int head_splits, bo
   r.metric_scale = 1.0f / float(B);
   r.metrics = ag->metrics;
   r.slot_loss = slot_loss; r.slot_td = slot_td; r.slot_q = slot_q;
+  if (ag->defer_now && !rereduce) {          // runs fused with this network's optimiser step
+    const int id = int(&n - ag->net);
+    ag->pending_r[id] = r;
+    ag->pending[id] = true;
+    return;
+  }
   launch_reduce_grads(r, st);
 }
 
@@ -261,6 +272,13 @@ void adam_step(gcrl_agent *ag, Net &n, int which, float max_norm, int slot_norm,
   a.polyak = (polyak && target) ? 1 : 0;
   a.metrics = ag->metrics; a.slot_norm = slot_norm;
   a.tmap = n.tmap; a.pT = n.pT; a.targetT = target ? target->pT : nullptr;
+  const int id = int(&n - ag->net);
+  if (ag->pending[id]) {
+    ag->pending[id] = false;
+    GCRL_REQUIRE(grad == nullptr, "a deferred reduction cannot be combined with an external gradient");
+    launch_reduce_adam(ag->pending_r[id], a, st);
+    return;
+  }
   launch_adam(a, st);
 }
 
@@ -552,6 +570,11 @@ enum : int { PH_CGRAD = 1, PH_CSTEP = 2, PH_AGRAD = 4, PH_ASTEP = 8, PH_ALL = 15
 
 void run_update_body(gcrl_agent *ag, int B, const float *noise, int flags, int mask, cudaStream_t st) {
   const bool dp = mask != PH_ALL;
+  ag->defer_now = ag->fuse_opt && !dp && !ag->p2p.on;
+  struct Reset {
+    gcrl_agent *a;
+    ~Reset() { a->defer_now = false; for (bool &p : a->pending) p = false; }
+  } reset{ag};
   if (mask & PH_CGRAD) {
     critic_phase_grads(ag, B, noise, st);
     if (ag->td3 && dp) critic2_phase_grads(ag, B, st);
@@ -744,6 +767,7 @@ int gcrl_agent_create(gcrl_agent **out, int device, const gcrl_agent_config *cfg
     ag->d_scalars = dev_alloc<StepScalars>(1);
     ag->scal_stage.init(256);
     GCRL_CUDA(cudaStreamCreateWithFlags(&ag->cap_stream, cudaStreamNonBlocking));
+    ag->fuse_opt = reduce_adam_available(ag->net[CRITIC1].total, ag->cap_stream);
     const char *ng = getenv("GCRL_B200_NO_GRAPH");
     ag->use_graphs = !(ng && ng[0] == '1');
     ag->io_stage.init(size_t(1) << 16);

@@ -184,6 +184,9 @@ struct AdamArgs {
   float *pT, *targetT;
 };
 void launch_adam(const AdamArgs &a, cudaStream_t st);
+// reduce + clip + Adam in one cooperative launch (optim.cu); availability is probed once per process
+bool reduce_adam_available(int total, cudaStream_t st);
+void launch_reduce_adam(const ReduceArgs &r, const AdamArgs &a, cudaStream_t st);
 // data-parallel averaging over NVLink peer memory (optim.cu)
 void launch_p2p_barrier(unsigned int *const *peer_flags, unsigned int *epoch, int rank, int world, int *err,
                         cudaStream_t st);
