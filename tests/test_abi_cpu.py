@@ -82,11 +82,15 @@ def test_no_cpu_fallback_without_device():
     from gcrl_b200 import _lib
     if _lib.device_count() > 0:
         pytest.skip("GPU present")
-    from gcrl_b200 import HERBuffer, RunningNormalizer
+    from gcrl_b200 import HERBuffer, PERBuffer, ReplayBuffer, RunningNormalizer
     with pytest.raises(_lib.GcrlError):
         HERBuffer(1000, 50, 1)
     with pytest.raises(_lib.GcrlError):
         RunningNormalizer(3)
+    with pytest.raises(_lib.GcrlError):
+        PERBuffer(1000, 0.6)
+    with pytest.raises(_lib.GcrlError):
+        ReplayBuffer(1000)
 
 
 def test_product_never_imports_oracle():
