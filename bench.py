@@ -511,12 +511,13 @@ def gpu_main(args):
             fl = 2.0 * B * (amac + 2 * cmac + (Ll - 1) * Hh * Hh + Hh)
             ach = fl / (msk.value * 1e-3) / 1e12
             # DRAM bytes per launch from the one `ncu --set full` capture of this kernel at the bench shape
-            # (profiles/r01b_ncu_full_fused_B256_raw.csv: dram__bytes_read.sum 3.89 MB + write 0.51 MB)
-            traffic = 4.40e6 if (B, Hh, Ll, D, A) == (256, 256, 3, 21, 3) else None
+            # (profiles/r01i_ncu_full_fused_B256_raw.csv, fused_critic_kernel<2,0,0>: dram__bytes_read.sum 5.46 MB +
+            # write 0.014 MB; the three networks are 1.65 MB -- 128 CTAs stream them through a cold L2 under ncu)
+            traffic = 5.47e6 if (B, Hh, Ll, D, A) == (256, 256, 3, 21, 3) else None
             rooflines[f"fused_critic_kernel_B{B}"] = {
                 "bound": "tensor", "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
                 "traffic": traffic, "ms_per_launch": msk.value, "algorithmic_flops_per_launch": fl,
-                "note": "fp32 FFMA row-slab kernel (weights streamed from L2 once per 4-row slab); latency-bound "
+                "note": "fp32 FFMA row-slab kernel (weights streamed from L2 once per 2-row slab); latency-bound "
                         "at this batch -- the tensor-core path serves batches >= 2048"}
         except Exception as e:   # noqa: BLE001
             log(f"[roofline] critic kernel timing skipped: {e}")
