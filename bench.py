@@ -454,9 +454,14 @@ def gpu_main(args):
         for batch in [B] + sweep_batches + ([1 << 20] if sweep_batches else []):
             ms_k = time_sampler(batch, 50 if batch <= 65536 else 20)
             ach = batch * alg_bytes / (ms_k * 1e-3) / 1e9
+            # DRAM bytes per launch from `ncu --set full` at the bench shape (profiles/r01j_ncu_full_sampler_*_raw.csv:
+            # dram__bytes_read.sum + dram__bytes_write.sum; 208-byte rows and 16-byte goal rows against 64-byte DRAM
+            # bursts, the writes of the small batches are absorbed by L2)
+            ncu_traffic = {65536: 25.94e6 + 0.04e6, 1 << 20: 305.4e6 + 140.6e6}
             rooflines[f"her_sample_kernel_B{batch}"] = {
                 "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": None, "ms_per_launch": ms_k, "algorithmic_bytes_per_transition": alg_bytes,
+                "traffic": ncu_traffic.get(batch) if (O, G, A, k) == (19, 3, 3, 4) else None,
+                "ms_per_launch": ms_k, "algorithmic_bytes_per_transition": alg_bytes,
                 "transitions_per_s": batch / (ms_k * 1e-3)}
     # BASELINE configs[4]: the sampler on a 10x larger buffer (10M stored transitions = 49.2M deque entries,
     # 2.2 GB of packed rows, far beyond the 126 MB L2): the same 20 000 synthetic episodes committed 10 times
