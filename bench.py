@@ -460,7 +460,7 @@ def gpu_main(args):
             ncu_traffic = {65536: 25.94e6 + 0.04e6, 1 << 20: 305.4e6 + 140.6e6}
             rooflines[f"her_sample_kernel_B{batch}"] = {
                 "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": ncu_traffic.get(batch) if (O, G, A, k) == (19, 3, 3, 4) else None,
+                "traffic": ncu_traffic.get(batch) if (O, G, A, k) == (18, 3, 3, 4) else None,
                 "ms_per_launch": ms_k, "algorithmic_bytes_per_transition": alg_bytes,
                 "transitions_per_s": batch / (ms_k * 1e-3)}
     # BASELINE configs[4]: the sampler on a 10x larger buffer (10M stored transitions = 49.2M deque entries,
