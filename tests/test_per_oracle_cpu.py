@@ -137,3 +137,29 @@ def test_weighted_update_oracles_match_reference_fixture(algo, case):
             tag = f"critic_{i + 1}" if algo == "sac" else f"critic_{i}"
             for (w, b_), (rw, rb) in zip(orc.critics[i], sac_params_from_golden(g, si, tag)):
                 assert weights_close(w, rw, lr, n) and weights_close(b_, rb, lr, n), tag
+
+
+def test_restatements_hold_on_random_shapes():
+    """Property check (hypothesis): any length, any float32 priorities -- the restated pairwise sum equals
+    ndarray.sum() bit for bit and the restated draw equals RandomState.choice."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(n=st.integers(1, 700), seed=st.integers(0, 2 ** 31 - 1), spread=st.integers(0, 12))
+    def check(n, seed, spread):
+        rng = np.random.default_rng(seed)
+        prio = (10.0 ** rng.uniform(-spread, 1, n)).astype(np.float32)
+        assert bits(OP.pairwise_sum_f32(prio)) == bits(prio.sum())
+        P = OP.normalised_priorities(prio)
+        ref = prio.copy()
+        ref /= ref.sum()
+        assert np.array_equal(bits(P), bits(ref))
+        B = int(rng.integers(1, 33))
+        np.random.seed(seed % (2 ** 32))
+        state = np.random.get_state()
+        want = np.random.choice(n, B, p=ref)
+        np.random.set_state(state)
+        assert np.array_equal(OP.choice_indices(P, np.random.random_sample(B)), want)
+
+    check()
