@@ -53,6 +53,7 @@ class HERBuffer:
         self.cap_transitions = int(cap_transitions)
         self._h = None
         self._dims = None
+        self._bounds = {}                 # T -> (lo, hi) of apply_her's randint calls
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -110,8 +111,11 @@ class HERBuffer:
         k = self.k_future
         fut = np.zeros((T, max(k, 1)), np.uint8)
         if T > 1 and k > 0:   # the same (T - 1) * k draws, in the same order, through the C mirror of CPython's MT
-            lo = np.repeat(np.arange(1, T, dtype=np.int32), k)
-            fut[:T - 1, :k] = _lib.py_randint_seq(lo, np.full(lo.shape, T - 1, np.int32)).reshape(T - 1, k)
+            bounds = self._bounds.get(T)
+            if bounds is None:
+                lo = np.repeat(np.arange(1, T, dtype=np.int32), k)
+                bounds = self._bounds[T] = (lo, np.full(lo.shape, T - 1, np.int32))
+            fut[:T - 1, :k] = _lib.py_randint_seq(*bounds).reshape(T - 1, k)
         return fut
 
     def _commit(self, ep):
