@@ -11,6 +11,7 @@ from . import _lib
 from ._lib import check, lib, np_ptr, vp
 
 _FLUSH_LEN = 50  # the reference flushes on `done or len >= 50` (literal, src/buffer.py:117)
+_RANDINT_BOUNDS = {}  # (T, k) -> (lo, hi) arrays of apply_her's randint calls, in its draw order
 
 
 def _to_np(x, dtype=np.float32):
@@ -53,7 +54,6 @@ class HERBuffer:
         self.cap_transitions = int(cap_transitions)
         self._h = None
         self._dims = None
-        self._bounds = {}                 # T -> (lo, hi) of apply_her's randint calls
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -111,10 +111,10 @@ class HERBuffer:
         k = self.k_future
         fut = np.zeros((T, max(k, 1)), np.uint8)
         if T > 1 and k > 0:   # the same (T - 1) * k draws, in the same order, through the C mirror of CPython's MT
-            bounds = self._bounds.get(T)
+            bounds = _RANDINT_BOUNDS.get((T, k))
             if bounds is None:
                 lo = np.repeat(np.arange(1, T, dtype=np.int32), k)
-                bounds = self._bounds[T] = (lo, np.full(lo.shape, T - 1, np.int32))
+                bounds = _RANDINT_BOUNDS[(T, k)] = (lo, np.full(lo.shape, T - 1, np.int32))
             fut[:T - 1, :k] = _lib.py_randint_seq(*bounds).reshape(T - 1, k)
         return fut
 
