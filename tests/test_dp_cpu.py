@@ -47,8 +47,15 @@ def _worker(rank, world, port, out):
         avg.average((1,))          # critic phase
         avg.average((0,))          # actor phase
         avg.average_metrics()
+        # the normaliser's moments all-gather: rank order, every rank sees every rank's moments
+        from gcrl_b200.normalizer import RunningNormalizer
+        nz = RunningNormalizer.__new__(RunningNormalizer)      # host plumbing only: no CUDA object behind it
+        nz.device_index, nz.size = 0, 3
+        nz.enable_data_parallel()
+        mine = np.full((3, 3), float(rank + 1)) * np.array([1.0, 10.0, 100.0])
+        gathered = nz._gather(mine)
         out.put((rank, t.tolist(), ag.grads[0][:3].tolist(), ag.grads[1][:3].tolist(), ag.metrics[:2].tolist(),
-                 avg.calls))
+                 avg.calls, gathered.tolist()))
     finally:
         dist.destroy_process_group()
 
@@ -67,7 +74,9 @@ def test_gloo_world2_mean_allreduce_and_averager():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, t, g0, g1, m, calls in res:
+    for rank, t, g0, g1, m, calls, gathered in res:
+        want = [(np.full((3, 3), float(r + 1)) * np.array([1.0, 10.0, 100.0])).tolist() for r in range(2)]
+        assert gathered == want                      # [world, dim, 3], rank order, identical on every rank
         assert t == [0.5, 15.0]                      # mean over ranks
         assert g0 == [1.5, 1.5, 1.5]                 # (1 + 2) / 2
         assert g1 == [0.0, 1.5, 3.0]
