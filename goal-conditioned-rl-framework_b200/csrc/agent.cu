@@ -140,12 +140,7 @@ struct gcrl_agent {
   float *dzh = nullptr;                    // fused path: critic head dL/dq [maxB]
   float *per_w = nullptr, *per_td = nullptr;   // prioritised replay: importance weights in, TD errors out [maxB]
   bool per_on = false;                     // flags bit3 of the update being issued
-  // single-GPU update: the reduction of a network's partial gradients is deferred to its optimiser step and both
-  // run as one cooperative launch (optim.cu: reduce_adam_kernel)
-  bool fuse_opt = false, defer_now = false;
-  bool pending[NUM_NETS] = {};
-  ReduceArgs pending_r[NUM_NETS];
-  bool use_fused = true, use_cluster = false;
+  bool use_fused = true;
   int dp_B = -1, dp_flags = -1;            // the update the data-parallel phases belong to
   // data-parallel averaging over NVLink peer memory (gcrl_agent_dp_connect)
   struct P2P {
@@ -250,12 +245,6 @@ void reduce_grads(gcrl_agent *ag, Net &n, const int *splits, int head_splits, bo
   r.metric_scale = 1.0f / float(B);
   r.metrics = ag->metrics;
   r.slot_loss = slot_loss; r.slot_td = slot_td; r.slot_q = slot_q;
-  if (ag->defer_now && !rereduce) {          // runs fused with this network's optimiser step
-    const int id = int(&n - ag->net);
-    ag->pending_r[id] = r;
-    ag->pending[id] = true;
-    return;
-  }
   launch_reduce_grads(r, st);
 }
 
@@ -272,13 +261,6 @@ void adam_step(gcrl_agent *ag, Net &n, int which, float max_norm, int slot_norm,
   a.polyak = (polyak && target) ? 1 : 0;
   a.metrics = ag->metrics; a.slot_norm = slot_norm;
   a.tmap = n.tmap; a.pT = n.pT; a.targetT = target ? target->pT : nullptr;
-  const int id = int(&n - ag->net);
-  if (ag->pending[id]) {
-    ag->pending[id] = false;
-    GCRL_REQUIRE(grad == nullptr, "a deferred reduction cannot be combined with an external gradient");
-    launch_reduce_adam(ag->pending_r[id], a, st);
-    return;
-  }
   launch_adam(a, st);
 }
 
@@ -352,13 +334,8 @@ struct PhaseState {
 };
 
 // ---- row-slab fused path (fused.cu): DDPG, B <= 1024 ---------------------------------------------
-constexpr int kClusterMaxBatch = 2048;
-bool cluster_ok(const gcrl_agent *ag, int B) {
-  return ag->use_fused && ag->use_cluster && !ag->td3 && !ag->per_on && B <= kClusterMaxBatch &&  // (cluster.cu: DDPG only)
-         cluster_supported(B, ag->D, ag->A, ag->H, ag->L);
-}
 bool fused_ok(const gcrl_agent *ag, int B) {
-  return cluster_ok(ag, B) || (ag->use_fused && fused_supported(B, ag->D, ag->A, ag->H, ag->L));
+  return ag->use_fused && fused_supported(B, ag->D, ag->A, ag->H, ag->L);
 }
 
 FusedNet fused_net(const gcrl_agent *ag, const Net &n) {
@@ -417,7 +394,7 @@ FusedCriticArgs fused_critic_args(gcrl_agent *ag, int B, int which = 0) {
 
 void fused_critic_phase_grads(gcrl_agent *ag, int B, int which, cudaStream_t st) {
   const FusedCriticArgs a = fused_critic_args(ag, B, which);
-  const int slabs = cluster_ok(ag, B) ? launch_cluster_critic(a, st) : launch_fused_critic(a, st);
+  const int slabs = launch_fused_critic(a, st);
   Net &c = ag->net[which == 0 ? CRITIC1 : CRITIC2];
   const int S = fused_wgrads(ag, c, which == 0 ? ag->acts_c1 : ag->acts_c2, ag->D + ag->A, ag->dzh, 1, B, st);
   int splits[8];
@@ -437,7 +414,7 @@ void fused_actor_phase_grads(gcrl_agent *ag, int B, cudaStream_t st) {
   for (int l = 0; l < ag->L; ++l) { a.h_out[l] = ag->acts_actor.h[l]; a.dz_out[l] = ag->dzl[l]; }
   a.da_out = ag->dz_act;
   a.metric_partials = ag->metric_partials;
-  const int slabs = cluster_ok(ag, B) ? launch_cluster_actor(a, st) : launch_fused_actor(a, st);
+  const int slabs = launch_fused_actor(a, st);
   const int S = fused_wgrads(ag, ag->net[ACTOR], ag->acts_actor, ag->D, ag->dz_act, 4, B, st);
   int splits[8];
   for (int l = 0; l < 8; ++l) splits[l] = S;
@@ -570,11 +547,6 @@ enum : int { PH_CGRAD = 1, PH_CSTEP = 2, PH_AGRAD = 4, PH_ASTEP = 8, PH_ALL = 15
 
 void run_update_body(gcrl_agent *ag, int B, const float *noise, int flags, int mask, cudaStream_t st) {
   const bool dp = mask != PH_ALL;
-  ag->defer_now = ag->fuse_opt && !dp && !ag->p2p.on;
-  struct Reset {
-    gcrl_agent *a;
-    ~Reset() { a->defer_now = false; for (bool &p : a->pending) p = false; }
-  } reset{ag};
   if (mask & PH_CGRAD) {
     critic_phase_grads(ag, B, noise, st);
     if (ag->td3 && dp) critic2_phase_grads(ag, B, st);
@@ -750,11 +722,6 @@ int gcrl_agent_create(gcrl_agent **out, int device, const gcrl_agent_config *cfg
     ag->per_td = dev_alloc<float>(size_t(mb));
     const char *nf = getenv("GCRL_B200_NO_FUSED");
     ag->use_fused = !(nf && nf[0] == '1');
-    // cluster.cu (layers split over an 8-CTA cluster through DSMEM) is parity-green but measured slower
-    // than the row-slab kernels at B = 256 (0.275 vs 0.160 ms per update, profiles/README.md): opt-in
-    const char *nc = getenv("GCRL_B200_CLUSTER");
-    ag->use_cluster = nc && nc[0] == '1';
-    if (ag->use_fused && ag->use_cluster && cluster_supported(1, D, A, H, L)) cluster_init(D, A, H, L);
     ag->bs = dev_alloc<float>(size_t(mb) * D);
     ag->bns = dev_alloc<float>(size_t(mb) * D);
     ag->ba = dev_alloc<float>(size_t(mb) * A);
@@ -767,7 +734,6 @@ int gcrl_agent_create(gcrl_agent **out, int device, const gcrl_agent_config *cfg
     ag->d_scalars = dev_alloc<StepScalars>(1);
     ag->scal_stage.init(256);
     GCRL_CUDA(cudaStreamCreateWithFlags(&ag->cap_stream, cudaStreamNonBlocking));
-    ag->fuse_opt = reduce_adam_available(ag->net[CRITIC1].total, ag->cap_stream);
     const char *ng = getenv("GCRL_B200_NO_GRAPH");
     ag->use_graphs = !(ng && ng[0] == '1');
     ag->io_stage.init(size_t(1) << 16);
@@ -1071,10 +1037,9 @@ int gcrl_agent_time_critic_kernel(gcrl_agent *ag, int64_t B, int iters, float *m
   cudaEvent_t e0, e1;
   GCRL_CUDA(cudaEventCreate(&e0));
   GCRL_CUDA(cudaEventCreate(&e1));
-  const bool cl = cluster_ok(ag, int(B));
-  for (int i = 0; i < 3; ++i) cl ? launch_cluster_critic(a, st) : launch_fused_critic(a, st);
+  for (int i = 0; i < 3; ++i) launch_fused_critic(a, st);
   GCRL_CUDA(cudaEventRecord(e0, st));
-  for (int i = 0; i < iters; ++i) cl ? launch_cluster_critic(a, st) : launch_fused_critic(a, st);
+  for (int i = 0; i < iters; ++i) launch_fused_critic(a, st);
   GCRL_CUDA(cudaEventRecord(e1, st));
   GCRL_CUDA(cudaEventSynchronize(e1));
   float ms = 0.f;

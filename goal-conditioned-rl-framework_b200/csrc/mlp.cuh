@@ -128,11 +128,6 @@ struct FusedActorArgs {
 bool fused_supported(int B, int D, int A, int H, int L);
 int launch_fused_critic(const FusedCriticArgs &a, cudaStream_t st);   // returns the grid (metric slabs)
 int launch_fused_actor(const FusedActorArgs &a, cudaStream_t st);
-// cluster-fused variants (cluster.cu): 8-CTA clusters, layers split by output column over DSMEM
-bool cluster_supported(int B, int D, int A, int H, int L);
-void cluster_init(int D, int A, int H, int L);
-int launch_cluster_critic(const FusedCriticArgs &a, cudaStream_t st);   // returns the number of clusters
-int launch_cluster_actor(const FusedActorArgs &a, cudaStream_t st);
 
 // ---- tensor-core dense layers (tc_gemm.cu): tcgen05 / TMEM / TMA, 3xTF32 split for fp32 accuracy ----
 bool tc_dense_supported(int M, int N, int K);
@@ -184,9 +179,6 @@ struct AdamArgs {
   float *pT, *targetT;
 };
 void launch_adam(const AdamArgs &a, cudaStream_t st);
-// reduce + clip + Adam in one cooperative launch (optim.cu); availability is probed once per process
-bool reduce_adam_available(int total, cudaStream_t st);
-void launch_reduce_adam(const ReduceArgs &r, const AdamArgs &a, cudaStream_t st);
 // data-parallel averaging over NVLink peer memory (optim.cu)
 void launch_p2p_barrier(unsigned int *const *peer_flags, unsigned int *epoch, int rank, int world, int *err,
                         cudaStream_t st);

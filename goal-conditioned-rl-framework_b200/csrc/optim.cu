@@ -6,8 +6,6 @@
 // is one flat fp32 buffer, so an optimiser step is two launches: a fixed-order reduction of
 // the split-batch partial gradients (+ sum of squares) and one fused clip + Adam (+ Polyak)
 // pass.  Bound: HBM traffic of 7 fp32 words per parameter (g, m, v, p read; m, v, p write).
-#include <cooperative_groups.h>
-
 #include <algorithm>
 
 #include "mlp.cuh"
@@ -228,83 +226,6 @@ __global__ void __launch_bounds__(kOptThreads) adam_kernel(AdamArgs a) { adam_bo
 
 void launch_adam(const AdamArgs &a, cudaStream_t st) {
   adam_kernel<<<reduce_grid(a.n), kOptThreads, 0, st>>>(a);
-  GCRL_LAUNCHED();
-}
-
-// Both halves of an optimiser step in one cooperative launch: fixed-order reduction of the split partials
-// (+ per-CTA sums of squares), grid barrier, global-norm clip + Adam (+ Polyak).  Same grid, same element
-// mapping and same arithmetic as the two kernels above -- bit-identical results, one launch and one pass over
-// the flat gradient less.  Opt-in (GCRL_FUSED_OPT=1) for the single-GPU update -- it measured slower, see
-// reduce_adam_available; the data-parallel paths average the gradient across ranks between the two halves.
-struct ReduceAdamArgs {
-  ReduceArgs r;
-  AdamArgs a;
-};
-__global__ void __launch_bounds__(kOptThreads) reduce_adam_kernel(const __grid_constant__ ReduceAdamArgs ra) {
-  reduce_grads_body(ra.r);
-  __threadfence();
-  cooperative_groups::this_grid().sync();
-  adam_body(ra.a);
-}
-
-__global__ void coop_probe_kernel(int *out) {
-  cooperative_groups::this_grid().sync();
-  if (blockIdx.x == 0 && threadIdx.x == 0) *out = 1;
-}
-
-// Can reduce_grid(total) CTAs of the fused kernel be co-resident, and does a cooperative launch survive stream
-// capture + graph replay on this driver?  Probed once per process (on `st`, a capture-capable stream).
-bool reduce_adam_available(int total, cudaStream_t st) {
-  static int cached = -1;
-  if (cached >= 0) return cached == 1;
-  cached = 0;
-  // opt-in: measured SLOWER than the two plain launches at the BASELINE shape (0.150 vs 0.143 ms per update:
-  // the cooperative launch and the grid barrier cost more than the launch they save), see profiles/README.md
-  const char *e = getenv("GCRL_FUSED_OPT");
-  if (!(e && e[0] == '1')) return false;
-  int dev = 0, coop = 0, per_sm = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return false;
-  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-  if (!coop) return false;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reduce_adam_kernel, kOptThreads, 0) != cudaSuccess ||
-      per_sm < 4) {
-    cudaGetLastError();
-    return false;
-  }
-  (void)total;
-  int *flag = nullptr;
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t exec = nullptr;
-  bool ok = false;
-  do {
-    if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) break;
-    cudaMemset(flag, 0, sizeof(int));
-    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) break;
-    void *args[] = {&flag};
-    const cudaError_t le = cudaLaunchCooperativeKernel((void *)coop_probe_kernel, dim3(sm_count() * 4), dim3(kOptThreads),
-                                                       args, 0, st);
-    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
-    if (le != cudaSuccess || ce != cudaSuccess || graph == nullptr) break;
-    if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) break;
-    if (cudaGraphLaunch(exec, st) != cudaSuccess) break;
-    if (cudaStreamSynchronize(st) != cudaSuccess) break;
-    int h = 0;
-    if (cudaMemcpy(&h, flag, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) break;
-    ok = h == 1;
-  } while (false);
-  cudaGetLastError();
-  if (exec) cudaGraphExecDestroy(exec);
-  if (graph) cudaGraphDestroy(graph);
-  if (flag) cudaFree(flag);
-  cached = ok ? 1 : 0;
-  return ok;
-}
-
-void launch_reduce_adam(const ReduceArgs &r, const AdamArgs &a, cudaStream_t st) {
-  ReduceAdamArgs ra{r, a};
-  void *args[] = {&ra};
-  GCRL_CUDA(cudaLaunchCooperativeKernel((void *)reduce_adam_kernel, dim3(reduce_grid(r.total)), dim3(kOptThreads), args,
-                                        0, st));
   GCRL_LAUNCHED();
 }
 
