@@ -128,7 +128,8 @@ struct gcrl_agent {
   float *partials = nullptr;               // [kMaxSplits][max net total]
   int64_t slab = 0;
   float *metric_partials = nullptr;        // [kMaxSplits][4]
-  float *sumsq = nullptr;                  // [reduce grid]
+  float *sumsq = nullptr;                  // [max(reduce grid, wgrad tiles)]
+  int nsumsq = 0;                          // how many sums of squares the pending optimiser step reads
   float *metrics = nullptr;                // [8]
   StepScalars *d_scalars = nullptr;
   PinnedRing scal_stage;
@@ -245,6 +246,7 @@ void reduce_grads(gcrl_agent *ag, Net &n, const int *splits, int head_splits, bo
   r.metric_scale = 1.0f / float(B);
   r.metrics = ag->metrics;
   r.slot_loss = slot_loss; r.slot_td = slot_td; r.slot_q = slot_q;
+  ag->nsumsq = reduce_grid(n.total);
   launch_reduce_grads(r, st);
 }
 
@@ -253,7 +255,7 @@ void adam_step(gcrl_agent *ag, Net &n, int which, float max_norm, int slot_norm,
                cudaStream_t st, const float *grad = nullptr) {
   AdamArgs a{};
   a.p = n.p; a.m = n.m; a.v = n.v; a.g = grad ? grad : n.g; a.n = n.total;
-  a.sumsq_partials = ag->sumsq; a.nsumsq = reduce_grid(n.total);
+  a.sumsq_partials = ag->sumsq; a.nsumsq = ag->nsumsq;
   a.max_norm = max_norm;
   a.weight_decay = ag->cfg.weight_decay;
   a.sc = ag->d_scalars; a.which = which;
@@ -346,23 +348,44 @@ FusedNet fused_net(const gcrl_agent *ag, const Net &n) {
     f.b[l] = n.p + n.b_off[l];
   }
   f.Wh = n.p + n.w_off[ag->L]; f.ldwh = n.ldw[ag->L]; f.bh = n.p + n.b_off[ag->L];
+  f.flat = n.p; f.nflat = n.total; f.flatT = n.pT; f.nflatT = n.total_t;
   return f;
 }
 
-// weight gradients of all layers of `n` in one launch; hidden-layer operands: dzl[l] and
-// (l == 0 ? sa : acts.h[l-1]); head operand: dz_head [B][ld_head] and acts.h[L-1]
-int fused_wgrads(gcrl_agent *ag, const Net &n, const Acts &acts, int K0, const float *dz_head, int ld_head,
-                 int B, cudaStream_t st) {
+// weight gradients of all layers of `n` in ONE launch that also completes the split-batch sums into the flat
+// gradient n.g, the per-tile sums of squares and the batch-mean metrics (mlp.cu: multi_wgrad_kernel);
+// hidden-layer operands: dzl[l] and (l == 0 ? sa : acts.h[l-1]); head operand: dz_head [B][ld_head] and acts.h[L-1]
+void fused_wgrads(gcrl_agent *ag, Net &n, const Acts &acts, int K0, const float *dz_head, int ld_head, int B,
+                  int slot_loss, int slot_td, int slot_q, int metric_splits, cudaStream_t st) {
   WgradProblem pr[kMaxWgradProblems];
   const int L = ag->L;
   for (int l = 0; l < L; ++l) {
     pr[l] = WgradProblem{ag->dzl[l], ag->ldh, l == 0 ? ag->sa : acts.h[l - 1], l == 0 ? ag->ldc : ag->ldh,
                          ag->partials + n.w_off[l], n.ldw[l], ag->partials + n.b_off[l], ag->H,
-                         l == 0 ? K0 : ag->H};
+                         l == 0 ? K0 : ag->H, n.g + n.w_off[l], n.g + n.b_off[l]};
   }
   pr[L] = WgradProblem{dz_head, ld_head, acts.h[L - 1], ag->ldh, ag->partials + n.w_off[L], n.ldw[L],
-                       ag->partials + n.b_off[L], n.out_d[L], ag->H};
-  return launch_multi_wgrad(pr, L + 1, B, ag->slab, kMaxSplits, st);
+                       ag->partials + n.b_off[L], n.out_d[L], ag->H, n.g + n.w_off[L], n.g + n.b_off[L]};
+  WgradFinal fin{};
+  fin.sumsq_partials = ag->sumsq;
+  fin.metric_partials = metric_splits > 0 ? ag->metric_partials : nullptr;
+  fin.metric_splits = metric_splits;
+  fin.metric_scale = 1.0f / float(B);
+  fin.metrics = ag->metrics;
+  fin.slot_loss = slot_loss; fin.slot_td = slot_td; fin.slot_q = slot_q;
+  ag->nsumsq = launch_wgrad_complete(pr, L + 1, B, fin, st);
+}
+
+// the same per-tile sums of squares for a gradient that is already complete in n.g (data-parallel phases: the
+// cross-rank average replaced it) -- bit-identical to what fused_wgrads leaves for the same values
+void fused_grad_sumsq(gcrl_agent *ag, Net &n, cudaStream_t st) {
+  WgradProblem pr[kMaxWgradProblems];
+  for (int l = 0; l < n.layers; ++l) {
+    pr[l] = WgradProblem{};
+    pr[l].ldw = n.ldw[l]; pr[l].N = n.out_d[l]; pr[l].K = n.in_d[l];
+    pr[l].gW = n.g + n.w_off[l]; pr[l].gB = n.g + n.b_off[l];
+  }
+  ag->nsumsq = launch_wgrad_sumsq(pr, n.layers, ag->sumsq, st);
 }
 
 FusedCriticArgs fused_critic_args(gcrl_agent *ag, int B, int which = 0) {
@@ -396,13 +419,10 @@ void fused_critic_phase_grads(gcrl_agent *ag, int B, int which, cudaStream_t st)
   const FusedCriticArgs a = fused_critic_args(ag, B, which);
   const int slabs = launch_fused_critic(a, st);
   Net &c = ag->net[which == 0 ? CRITIC1 : CRITIC2];
-  const int S = fused_wgrads(ag, c, which == 0 ? ag->acts_c1 : ag->acts_c2, ag->D + ag->A, ag->dzh, 1, B, st);
-  int splits[8];
-  for (int l = 0; l < 8; ++l) splits[l] = S;
   // TD3: td error / Q metrics come from the critic-2 launch (they need both critics' Q)
   const bool metrics_here = !ag->td3 || which == 1;
-  reduce_grads(ag, c, splits, S, false, which == 0 ? S_CLOSS : S_C2LOSS, metrics_here ? S_TD : -1,
-               metrics_here ? S_Q : -1, slabs, B, st);
+  fused_wgrads(ag, c, which == 0 ? ag->acts_c1 : ag->acts_c2, ag->D + ag->A, ag->dzh, 1, B,
+               which == 0 ? S_CLOSS : S_C2LOSS, metrics_here ? S_TD : -1, metrics_here ? S_Q : -1, slabs, st);
 }
 
 void fused_actor_phase_grads(gcrl_agent *ag, int B, cudaStream_t st) {
@@ -415,10 +435,7 @@ void fused_actor_phase_grads(gcrl_agent *ag, int B, cudaStream_t st) {
   a.da_out = ag->dz_act;
   a.metric_partials = ag->metric_partials;
   const int slabs = launch_fused_actor(a, st);
-  const int S = fused_wgrads(ag, ag->net[ACTOR], ag->acts_actor, ag->D, ag->dz_act, 4, B, st);
-  int splits[8];
-  for (int l = 0; l < 8; ++l) splits[l] = S;
-  reduce_grads(ag, ag->net[ACTOR], splits, S, false, S_ALOSS, -1, -1, slabs, B, st);
+  fused_wgrads(ag, ag->net[ACTOR], ag->acts_actor, ag->D, ag->dz_act, 4, B, S_ALOSS, -1, -1, slabs, st);
 }
 
 // critic(s): forward, loss, backward, partials -> flat local-mean gradient(s) + metrics
@@ -447,6 +464,7 @@ const float *p2p_average(gcrl_agent *ag, int net, cudaStream_t st) {
   auto &pp = ag->p2p;
   launch_p2p_barrier(pp.d_peer_flags, pp.epoch, pp.rank, pp.world, pp.err, st);
   launch_p2p_reduce(pp.d_peer_g[net], pp.world, pp.gavg[net], ag->net[net].total, ag->sumsq, st);
+  ag->nsumsq = reduce_grid(ag->net[net].total);
   return pp.gavg[net];
 }
 
@@ -456,6 +474,7 @@ void critic_phase_step(gcrl_agent *ag, int which, int flags, bool rereduce, cuda
   Net &c = ag->net[id];
   const float *grad = nullptr;
   if (ag->p2p.on) grad = p2p_average(ag, id, st);
+  else if (rereduce && fused_ok(ag, ag->dp_B)) fused_grad_sumsq(ag, c, st);
   else if (rereduce) reduce_grads(ag, c, nullptr, 0, true, -1, -1, -1, 0, 1, st);
   // TD3 critic 1 is NOT clipped (:201 is commented out), critic 2 is
   const float clip = (ag->td3 && which == 0) ? -1.0f : ag->cfg.grad_clip;
@@ -516,6 +535,7 @@ void actor_phase_step(gcrl_agent *ag, bool rereduce, cudaStream_t st) {
   Net &a = ag->net[ACTOR];
   const float *grad = nullptr;
   if (ag->p2p.on) grad = p2p_average(ag, ACTOR, st);
+  else if (rereduce && fused_ok(ag, ag->dp_B)) fused_grad_sumsq(ag, a, st);
   else if (rereduce) reduce_grads(ag, a, nullptr, 0, true, -1, -1, -1, 0, 1, st);
   adam_step(ag, a, 1, ag->cfg.grad_clip, S_AGRAD, &ag->net[T_ACTOR], ag->td3, st, grad);
 }
@@ -728,7 +748,9 @@ int gcrl_agent_create(gcrl_agent **out, int device, const gcrl_agent_config *cfg
     ag->slab = std::max(ag->net[ACTOR].total, ag->net[CRITIC1].total);
     ag->partials = dev_alloc<float>(size_t(kMaxSplits) * ag->slab);
     ag->metric_partials = dev_alloc<float>(size_t(256) * 4);
-    ag->sumsq = dev_alloc<float>(size_t(reduce_grid(int(ag->slab))) + 8);
+    const int ht = (H + 31) / 32;              // 32 x 32 output tiles of the largest net (multi_wgrad_kernel)
+    const int wtiles = ht * ((D + A + 31) / 32) + (L - 1) * ht * ht + ht + 8;
+    ag->sumsq = dev_alloc<float>(size_t(std::max(reduce_grid(int(ag->slab)), wtiles)) + 8);
     ag->metrics = dev_alloc<float>(8);
     GCRL_CUDA(cudaMemset(ag->metrics, 0, 8 * sizeof(float)));
     ag->d_scalars = dev_alloc<StepScalars>(1);

@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 namespace gcrl {
@@ -19,6 +20,16 @@ int sm_count() {
     cached = n > 0 ? n : 148;
   }
   return cached;
+}
+
+bool pdl_enabled(int cls) {
+  static int mask = -1;
+  if (mask < 0) {
+    const char *e = getenv("GCRL_NO_PDL");
+    const char *m = getenv("GCRL_PDL_MASK");
+    mask = (e && e[0] == '1') ? 0 : (m ? atoi(m) : (PDL_FUSED | PDL_OPTIM));
+  }
+  return (mask & cls) != 0;
 }
 
 static std::atomic<uint64_t> g_launches{0};

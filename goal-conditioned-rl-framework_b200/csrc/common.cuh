@@ -81,7 +81,35 @@ struct PinnedRing {
   void release(int slot, cudaStream_t st);
 };
 
+// ---- programmatic dependent launch -------------------------------------------------------
+// Kernels of one update run back to back on one stream (one captured graph).  Launched through launch_pdl, a
+// kernel may be scheduled while its predecessor drains; it calls pdl_wait() before touching global memory (the
+// predecessor has then completed and flushed) and pdl_launch_dependents() once its own CTAs are running, so the
+// launch latency and prologue of kernel N+1 hide under kernel N.  GCRL_NO_PDL=1 turns the attribute off (the two
+// device calls are then no-ops).  Measured (profiles/README.md, round 2): worth ~1.5 us per update on the row-slab
+// and optimiser kernels; HARMFUL for the weight-gradient launch, whose 576 small CTAs, let in early, all land on
+// the 20 SMs the 128-CTA row-slab kernel leaves free (+10 us) -- hence the default class mask.
+enum : int { PDL_FUSED = 1, PDL_WGRAD = 2, PDL_OPTIM = 4, PDL_OTHER = 8 };   // GCRL_PDL_MASK selects kernel classes
+bool pdl_enabled(int cls = PDL_OTHER);
+template <int CLS = PDL_OTHER, typename... KArgs, typename... Args>
+void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled(CLS) ? 1 : 0;
+  GCRL_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
+
 // ---- device helpers -------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Exact unsigned division by a runtime constant (Granlund-Montgomery, 32-bit n < 2^31).
 struct FastDiv {
   uint32_t d, mul, shr;

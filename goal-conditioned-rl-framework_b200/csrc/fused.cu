@@ -165,6 +165,18 @@ __device__ __forceinline__ const float *slab_forward(const FusedNet &n, int L, i
   return x;
 }
 
+// Pull a network's parameters into L2 before the layer chain starts.  After an L2 flush (or any other traffic
+// that evicted them) every layer step would otherwise begin with a DRAM round trip that all CTAs wait on, since
+// they walk the weights in the same order; one 128-byte line per thread, spread over the grid.
+__device__ __forceinline__ void prefetch_l2(const float *p, int n, int gtid, int gthreads) {
+  for (int e = gtid * 32; e < n; e += gthreads * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + e));
+}
+__device__ __forceinline__ void prefetch_net(const FusedNet &n, bool forward, bool backward, int gtid, int gthreads) {
+  prefetch_l2(n.flat, n.nflat, gtid, gthreads);              // biases, head, W[out][in] (input gradient)
+  if (forward) prefetch_l2(n.flatT, n.nflatT, gtid, gthreads);
+  (void)backward;
+}
+
 struct SmemPlan {
   float *xa, *xb, *t0, *t1, *red, *small;
   float *keep1[kFusedMaxL], *keep2[kFusedMaxL];
@@ -206,6 +218,17 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_critic_kernel(FusedCri
   const int D = a.D, A = a.A, H = a.H, L = a.L, B = a.B;
   const int KinP = (D + A + 3) & ~3;
   SmemPlan sp = carve<R>(reinterpret_cast<float *>(fsm4), KinP, H, L, false);
+  pdl_wait();
+  pdl_launch_dependents();
+  {
+    const int gtid = blockIdx.x * kFusedThreads + threadIdx.x, gth = gridDim.x * kFusedThreads;
+    if (!TD3 || a.y_in == nullptr) {
+      prefetch_net(a.ta, true, false, gtid, gth);
+      prefetch_net(a.tc, true, false, gtid, gth);
+      if (TD3 && a.has_tc2) prefetch_net(a.tc2, true, false, gtid, gth);
+    }
+    prefetch_net(a.c, true, true, gtid, gth);
+  }
   float *x_ns = sp.xa, *x_sa = sp.xb;
   float *qn = sp.small, *q = qn + R, *yv = q + R, *dzh = yv + R, *rr = dzh + R, *dd = rr + R;
   float *anext = dd + R;                          // [A][R], A <= 4
@@ -349,6 +372,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_actor_kernel(FusedActo
   const int D = a.D, A = a.A, H = a.H, L = a.L, B = a.B;
   const int KinP = (D + A + 3) & ~3;
   SmemPlan sp = carve<R>(reinterpret_cast<float *>(fsm4), KinP, H, L, true);
+  pdl_wait();
+  pdl_launch_dependents();
+  {
+    const int gtid = blockIdx.x * kFusedThreads + threadIdx.x, gth = gridDim.x * kFusedThreads;
+    prefetch_net(a.actor, true, true, gtid, gth);
+    prefetch_net(a.c, true, true, gtid, gth);
+  }
   float *x_sa = sp.xa;
   float *q = sp.small, *act = q + R, *da = act + 4 * R;   // act, da: [A][R]
   const int row0 = blockIdx.x * R, tid = threadIdx.x;
@@ -474,7 +504,7 @@ int launch_fused_critic(const FusedCriticArgs &a, cudaStream_t st) {
   auto go = [&](auto kernel, int *flag, bool clustered) {
     ensure_smem(kernel, smem, flag);
     if (!clustered) {
-      kernel<<<grid, kFusedThreads, smem, st>>>(a);
+      launch_pdl<PDL_FUSED>(kernel, dim3(grid), dim3(kFusedThreads), smem, st, a);
       return;
     }
     cudaLaunchConfig_t cfg{};
@@ -482,13 +512,15 @@ int launch_fused_critic(const FusedCriticArgs &a, cudaStream_t st) {
     cfg.blockDim = dim3(kFusedThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled(PDL_FUSED) ? 2 : 1;
     GCRL_CUDA(cudaLaunchKernelEx(&cfg, kernel, a));
   };
   if (R == 2) {
@@ -515,13 +547,13 @@ int launch_fused_actor(const FusedActorArgs &a, cudaStream_t st) {
   const size_t smem = fused_smem_bytes(R, a.D, a.A, a.H, a.L, true);
   if (R == 2) {
     ensure_smem(fused_actor_kernel<2>, smem, &g_fused_smem_set[1][2]);
-    fused_actor_kernel<2><<<grid, kFusedThreads, smem, st>>>(a);
+    launch_pdl<PDL_FUSED>(fused_actor_kernel<2>, dim3(grid), dim3(kFusedThreads), smem, st, a);
   } else if (R == 4) {
     ensure_smem(fused_actor_kernel<4>, smem, &g_fused_smem_set[1][0]);
-    fused_actor_kernel<4><<<grid, kFusedThreads, smem, st>>>(a);
+    launch_pdl<PDL_FUSED>(fused_actor_kernel<4>, dim3(grid), dim3(kFusedThreads), smem, st, a);
   } else {
     ensure_smem(fused_actor_kernel<8>, smem, &g_fused_smem_set[1][1]);
-    fused_actor_kernel<8><<<grid, kFusedThreads, smem, st>>>(a);
+    launch_pdl<PDL_FUSED>(fused_actor_kernel<8>, dim3(grid), dim3(kFusedThreads), smem, st, a);
   }
   GCRL_LAUNCHED();
   return grid;

@@ -286,32 +286,187 @@ void launch_linear_dgrad_batched(const LinearDgradProblem *pr, int n, int M, int
   launch_batched_gemm<OP_DGRAD>(bg, n, st);
 }
 
-// Multi-problem weight-gradient launch: blockIdx.x enumerates the output tiles of all problems,
-// blockIdx.z the batch slabs.
+// Multi-problem weight-gradient launches: blockIdx.x enumerates the 32 x 32 output tiles of all problems.
 struct MultiGemm {
   GemmParams p[kMaxWgradProblems];
+  float *gW[kMaxWgradProblems], *gB[kMaxWgradProblems];   // complete-gradient destinations (wgrad_tile_kernel)
   int tile_begin[kMaxWgradProblems + 1];
   int tiles_x[kMaxWgradProblems];
   int nprob;
+  WgradFinal fin;
 };
 
-template <int BM, int BN, int TM, int TN>
-__global__ void __launch_bounds__((BM / TM) * (BN / TN)) multi_wgrad_kernel(MultiGemm mg) {
-  int i = 0;
+__device__ __forceinline__ void locate_tile(const MultiGemm &mg, int &i, int &bx, int &by) {
+  i = 0;
   while (i + 1 < mg.nprob && int(blockIdx.x) >= mg.tile_begin[i + 1]) ++i;
   const int local = blockIdx.x - mg.tile_begin[i];
-  const int bx = local % mg.tiles_x[i], by = local / mg.tiles_x[i];
+  bx = local % mg.tiles_x[i];
+  by = local / mg.tiles_x[i];
+}
+
+// split-batch partial slabs (blockIdx.z), summed later by reduce_grads_kernel: the ensemble path of sac.cu
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) multi_wgrad_kernel(const __grid_constant__ MultiGemm mg) {
+  int i, bx, by;
+  locate_tile(mg, i, bx, by);
   gemm_body<BM, BN, TM, TN, OP_WGRAD>(mg.p[i], bx, by, blockIdx.z);
 }
 
-int launch_multi_wgrad(const WgradProblem *probs, int nprob, int M, int64_t split_stride, int max_splits,
-                       cudaStream_t st) {
+// ---- complete weight gradients in one launch (row-slab path, batch <= 1024) -------------------------------
+// One CTA per 32 x 32 output tile, GROUPS groups of 64 threads; group g reduces batch rows [g chunk, (g+1) chunk)
+// with the 4 x 4 register tiles of gemm_body (own shared-memory stage, own named barrier), then the groups'
+// tiles are summed through shared memory in group order -- a fixed order -- straight into the flat gradient,
+// together with the tile's sum of squares for the global-norm clip.  No partial slabs in HBM, no reduction
+// launch, no atomics.  Tile 0 also finalises the batch-mean metrics of the phase.
+constexpr int kWgThreads = 64, kWgTile = 32, kWgFinish = 256;
+constexpr int kWgStageFloats = 2 * 2 * BK * (kWgTile + SPAD);      // As[2][BK][36] + Bs[2][BK][36] per group
+
+__device__ __forceinline__ void bar_group(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kWgThreads) : "memory"); }
+
+// sum of squares of one finished tile: thread t < 256 owns the 16-byte group t of the tile (+ bias row t for
+// t < 32 in the first tile column); 8 warp trees, then the 8 warp sums in order.  Shared by both kernels below.
+__device__ __forceinline__ void tile_sumsq_store(float sq, float *s_sq, float *dst) {
+  const int tid = threadIdx.x;
+  if (tid < kWgFinish) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, s);
+    if ((tid & 31) == 0) s_sq[tid >> 5] = sq;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWgFinish / 32; ++w) t += s_sq[w];
+    *dst = t;
+  }
+}
+
+template <int GROUPS>
+__global__ void __launch_bounds__(kWgThreads * GROUPS) wgrad_tile_kernel(const __grid_constant__ MultiGemm mg) {
+  constexpr int BM = kWgTile, BN = kWgTile, NT = kWgThreads, TXN = BN / 4;
+  static_assert(GROUPS * kWgThreads >= kWgFinish && GROUPS <= 8, "finish mapping / named barriers");
+  extern __shared__ float4 wg_sm4[];
+  __shared__ float s_sq[kWgFinish / 32];
+  float *sm = reinterpret_cast<float *>(wg_sm4);
+  pdl_wait();
+  pdl_launch_dependents();
+  int pi, bx, by;
+  locate_tile(mg, pi, bx, by);
+  const GemmParams &p = mg.p[pi];
+  const int grp = threadIdx.x / NT, tid = threadIdx.x % NT;
+  const int tx = tid % TXN, ty = tid / TXN;
+  const int m0 = by * BM, n0 = bx * BN;
+  float(*As)[BK][BM + SPAD] = reinterpret_cast<float(*)[BK][BM + SPAD]>(sm + size_t(grp) * kWgStageFloats);
+  float(*Bs)[BK][BN + SPAD] = reinterpret_cast<float(*)[BK][BN + SPAD]>(sm + size_t(grp) * kWgStageFloats + 2 * BK * (BM + SPAD));
+  const int rbeg = min(p.K, grp * p.k_chunk), rend = min(p.K, rbeg + p.k_chunk);
+  const int nk = (rend - rbeg + BK - 1) / BK;
+  float4 ra[BM * 4 / NT], rb[BN * 4 / NT];
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bsum = 0.f;
+  auto gload = [&](int t) {
+    const int r0 = rbeg + t * BK;
+    load_ic<BM, NT>(p.A, p.lda, m0, p.M, r0, rend, ra, tid);
+    load_ic<BN, NT>(p.B, p.ldb, n0, p.N, r0, rend, rb, tid);
+  };
+  auto sstore = [&](int buf) {
+    store_ic<BM, NT>(As[buf], ra, tid);
+    store_ic<BN, NT>(Bs[buf], rb, tid);
+  };
+  if (nk > 0) {
+    gload(0);
+    sstore(0);
+  }
+  bar_group(grp);
+  for (int t = 0; t < nk; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < nk) gload(t + 1);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 av = *reinterpret_cast<const float4 *>(&As[buf][k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4 *>(&Bs[buf][k][tx * 4]);
+      const float a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (bx == 0 && tid < BM) {
+#pragma unroll
+      for (int k = 0; k < BK; ++k) bsum += As[buf][k][tid];
+    }
+    if (t + 1 < nk) sstore(buf ^ 1);
+    bar_group(grp);
+  }
+  // ---- the groups' tiles -> shared memory (each group reuses its own stage), then the ordered sum ----
+  float *red = sm + size_t(grp) * kWgStageFloats;          // [32][32] tile, then [32] bias sums
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4 *>(red + (ty * 4 + i) * BN + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  if (tid < BM) red[BM * BN + tid] = bsum;
+  __syncthreads();
+  float sq = 0.f;
+  const int t = threadIdx.x;
+  if (t < kWgFinish) {
+    const int r = t / (BN / 4), c = (t % (BN / 4)) * 4;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int z = 0; z < GROUPS; ++z) {
+      const float4 v = *reinterpret_cast<const float4 *>(sm + size_t(z) * kWgStageFloats + r * BN + c);
+      g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+    }
+    // rows are written over the full padded width (zeros beyond the layer's input width)
+    if (m0 + r < p.M && n0 + c < p.ldc) {
+      *reinterpret_cast<float4 *>(mg.gW[pi] + size_t(m0 + r) * p.ldc + n0 + c) = g;
+      sq = fmaf(g.x, g.x, sq); sq = fmaf(g.y, g.y, sq); sq = fmaf(g.z, g.z, sq); sq = fmaf(g.w, g.w, sq);
+    }
+    if (bx == 0 && t < BM && m0 + t < p.M) {
+      float gb = 0.f;
+#pragma unroll
+      for (int z = 0; z < GROUPS; ++z) gb += sm[size_t(z) * kWgStageFloats + BM * BN + t];
+      mg.gB[pi][m0 + t] = gb;
+      sq = fmaf(gb, gb, sq);
+    }
+  }
+  tile_sumsq_store(sq, s_sq, mg.fin.sumsq_partials + blockIdx.x);
+  if (blockIdx.x == 0 && mg.fin.metric_partials != nullptr && t < 3) {
+    float s = 0.f;
+    for (int k = 0; k < mg.fin.metric_splits; ++k) s += mg.fin.metric_partials[size_t(k) * 4 + t];
+    const int slot = t == 0 ? mg.fin.slot_loss : (t == 1 ? mg.fin.slot_td : mg.fin.slot_q);
+    if (slot >= 0) mg.fin.metrics[slot] = s * mg.fin.metric_scale;
+  }
+}
+
+// sums of squares of a complete flat gradient, tile by tile, bit-identical to what wgrad_tile_kernel leaves
+// for the same values (the data-parallel phases, after the cross-rank average replaced the gradient)
+__global__ void __launch_bounds__(kWgFinish) wgrad_sumsq_kernel(const __grid_constant__ MultiGemm mg) {
+  constexpr int BM = kWgTile, BN = kWgTile;
+  __shared__ float s_sq[kWgFinish / 32];
+  pdl_wait();
+  pdl_launch_dependents();
+  int pi, bx, by;
+  locate_tile(mg, pi, bx, by);
+  const GemmParams &p = mg.p[pi];
+  const int m0 = by * BM, n0 = bx * BN, t = threadIdx.x;
+  const int r = t / (BN / 4), c = (t % (BN / 4)) * 4;
+  float sq = 0.f;
+  if (m0 + r < p.M && n0 + c < p.ldc) {
+    const float4 g = __ldcg(reinterpret_cast<const float4 *>(mg.gW[pi] + size_t(m0 + r) * p.ldc + n0 + c));
+    sq = fmaf(g.x, g.x, sq); sq = fmaf(g.y, g.y, sq); sq = fmaf(g.z, g.z, sq); sq = fmaf(g.w, g.w, sq);
+  }
+  if (bx == 0 && t < BM && m0 + t < p.M) {
+    const float gb = __ldcg(mg.gB[pi] + m0 + t);
+    sq = fmaf(gb, gb, sq);
+  }
+  tile_sumsq_store(sq, s_sq, mg.fin.sumsq_partials + blockIdx.x);
+}
+
+static int fill_multi(MultiGemm &mg, const WgradProblem *probs, int nprob, int M, int64_t split_stride, int chunk,
+                      bool need_dest) {
   GCRL_REQUIRE(nprob >= 1 && nprob <= kMaxWgradProblems, "too many wgrad problems");
-  int splits = std::max(1, std::min(max_splits, M / 64));
-  int chunk = (M + splits - 1) / splits;
-  chunk = (chunk + BK - 1) / BK * BK;
-  splits = (M + chunk - 1) / chunk;
-  MultiGemm mg{};
   mg.nprob = nprob;
   int tiles = 0;
   for (int i = 0; i < nprob; ++i) {
@@ -322,15 +477,62 @@ int launch_multi_wgrad(const WgradProblem *probs, int nprob, int M, int64_t spli
     p.k_chunk = chunk;
     p.c_split_stride = split_stride;
     p.cb_split_stride = split_stride;
+    mg.gW[i] = probs[i].gW; mg.gB[i] = probs[i].gB;
+    GCRL_REQUIRE(!need_dest || (probs[i].gW != nullptr && probs[i].gB != nullptr), "fused wgrad needs gradient destinations");
     mg.tile_begin[i] = tiles;
     mg.tiles_x[i] = (p.N + 31) / 32;
     tiles += mg.tiles_x[i] * ((p.M + 31) / 32);
   }
   mg.tile_begin[nprob] = tiles;
-  dim3 grid(tiles, 1, splits);
-  multi_wgrad_kernel<32, 32, 4, 4><<<grid, 64, 0, st>>>(mg);
+  return tiles;
+}
+
+int launch_multi_wgrad(const WgradProblem *probs, int nprob, int M, int64_t split_stride, int max_splits,
+                       cudaStream_t st) {
+  int splits = std::max(1, std::min(max_splits, M / 64));
+  int chunk = (M + splits - 1) / splits;
+  chunk = (chunk + BK - 1) / BK * BK;
+  splits = (M + chunk - 1) / chunk;
+  MultiGemm mg{};
+  const int tiles = fill_multi(mg, probs, nprob, M, split_stride, chunk, false);
+  multi_wgrad_kernel<32, 32, 4, 4><<<dim3(tiles, 1, splits), 64, 0, st>>>(mg);
   GCRL_LAUNCHED();
   return splits;
+}
+
+template <int GROUPS>
+static void launch_wgrad_tiles(const MultiGemm &mg, int tiles, cudaStream_t st) {
+  static bool attr_set = false;
+  const size_t smem = size_t(GROUPS) * kWgStageFloats * sizeof(float);
+  if (!attr_set && smem > 48 * 1024) {
+    GCRL_CUDA(cudaFuncSetAttribute(wgrad_tile_kernel<GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    attr_set = true;
+  }
+  // no early launch: the small CTAs would pile onto the SMs the preceding row-slab kernel leaves free
+  launch_pdl<PDL_WGRAD>(wgrad_tile_kernel<GROUPS>, dim3(tiles), dim3(kWgThreads * GROUPS), smem, st, mg);
+}
+
+int launch_wgrad_complete(const WgradProblem *probs, int nprob, int M, const WgradFinal &fin, cudaStream_t st) {
+  // 4 or 8 groups per CTA (the ordered sum needs >= 256 threads; named barriers 1..8 + the CTA barrier)
+  const int groups = M > 256 ? 8 : 4;
+  int chunk = (M + groups - 1) / groups;
+  chunk = (chunk + BK - 1) / BK * BK;
+  MultiGemm mg{};
+  mg.fin = fin;
+  const int tiles = fill_multi(mg, probs, nprob, M, 0, chunk, true);
+  if (groups == 8) launch_wgrad_tiles<8>(mg, tiles, st);
+  else launch_wgrad_tiles<4>(mg, tiles, st);
+  GCRL_LAUNCHED();
+  return tiles;
+}
+
+int launch_wgrad_sumsq(const WgradProblem *probs, int nprob, float *sumsq_partials, cudaStream_t st) {
+  MultiGemm mg{};
+  mg.fin.sumsq_partials = sumsq_partials;
+  const int tiles = fill_multi(mg, probs, nprob, 0, 0, 0, true);
+  launch_pdl<PDL_WGRAD>(wgrad_sumsq_kernel, dim3(tiles), dim3(kWgFinish), 0, st, mg);
+  GCRL_LAUNCHED();
+  return tiles;
 }
 
 template <int OP>

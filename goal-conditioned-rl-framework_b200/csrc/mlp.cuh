@@ -81,11 +81,25 @@ struct WgradProblem {
   float *pW; int ldw;
   float *pB;
   int N, K;          // layer output / input widths
+  float *gW, *gB;    // WgradFinal: where this layer's weight / bias gradient lives in the flat gradient buffer
 };
 constexpr int kMaxWgradProblems = 8;   // == kMaxBatchedLinear: one problem per critic of an ensemble
-// Returns the number of batch slabs S (same for every problem).
+// What wgrad_tile_kernel finalises next to the gradient: per-tile sums of squares for the clip and the
+// batch-mean metrics of the phase.
+struct WgradFinal {
+  float *sumsq_partials;    // [tiles]
+  const float *metric_partials; int metric_splits; float metric_scale;
+  float *metrics; int slot_loss, slot_td, slot_q;
+};
+// Split-batch partial slabs (summed later by reduce_grads); returns the number of batch slabs S.
 int launch_multi_wgrad(const WgradProblem *probs, int nprob, int M, int64_t split_stride, int max_splits,
                        cudaStream_t st);
+// Complete gradients straight into probs[i].gW / gB + sums of squares + metrics in ONE launch (M <= 1024);
+// returns the number of output tiles (= sums of squares written).
+int launch_wgrad_complete(const WgradProblem *probs, int nprob, int M, const WgradFinal &fin, cudaStream_t st);
+// Per-tile sums of squares of a complete gradient (probs[i].gW / gB, N, K, ldw), bit-identical to the ones
+// launch_wgrad_complete leaves; returns the number of tiles.
+int launch_wgrad_sumsq(const WgradProblem *probs, int nprob, float *sumsq_partials, cudaStream_t st);
 
 // ---- row-slab fused update kernels (fused.cu) -----------------------------------------------
 constexpr int kFusedMaxL = 6;
@@ -96,6 +110,8 @@ struct FusedNet {               // hidden layers 0..L-1 and the output head of o
   int ldt[kFusedMaxL], ldw[kFusedMaxL];
   const float *Wh, *bh;         // head [nout][ldwh]
   int ldwh;
+  const float *flat, *flatT;    // the whole parameter buffer and its transposed copy (L2 prefetch at kernel start)
+  int nflat, nflatT;
 };
 struct FusedCriticArgs {
   FusedNet ta, tc, c;           // target actor, target critic, critic

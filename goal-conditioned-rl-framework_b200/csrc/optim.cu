@@ -66,10 +66,14 @@ __device__ __forceinline__ void reduce_grads_body(const ReduceArgs &a) {
   }
 }
 
-__global__ void __launch_bounds__(kOptThreads) reduce_grads_kernel(ReduceArgs a) { reduce_grads_body(a); }
+__global__ void __launch_bounds__(kOptThreads) reduce_grads_kernel(ReduceArgs a) {
+  pdl_wait();
+  pdl_launch_dependents();
+  reduce_grads_body(a);
+}
 
 void launch_reduce_grads(const ReduceArgs &a, cudaStream_t st) {
-  reduce_grads_kernel<<<reduce_grid(a.total), kOptThreads, 0, st>>>(a);
+  launch_pdl<PDL_OPTIM>(reduce_grads_kernel, dim3(reduce_grid(a.total)), dim3(kOptThreads), 0, st, a);
   GCRL_LAUNCHED();
 }
 
@@ -177,6 +181,8 @@ void launch_p2p_metrics(unsigned int *const *peer_flags, unsigned int *epoch, in
 // preceded by clip_grad_norm_: g *= min(1, max_norm / (||g|| + 1e-6)).
 __device__ __forceinline__ void adam_body(const AdamArgs &a) {
   __shared__ float s_coef, s_norm;
+  pdl_wait();
+  pdl_launch_dependents();
   if (threadIdx.x < 32) {
     float s = 0.f;
     for (int i = threadIdx.x; i < a.nsumsq; i += 32) s += a.sumsq_partials[i];
@@ -225,13 +231,15 @@ __device__ __forceinline__ void adam_body(const AdamArgs &a) {
 __global__ void __launch_bounds__(kOptThreads) adam_kernel(AdamArgs a) { adam_body(a); }
 
 void launch_adam(const AdamArgs &a, cudaStream_t st) {
-  adam_kernel<<<reduce_grid(a.n), kOptThreads, 0, st>>>(a);
+  launch_pdl<PDL_OPTIM>(adam_kernel, dim3(reduce_grid(a.n)), dim3(kOptThreads), 0, st, a);
   GCRL_LAUNCHED();
 }
 
 __global__ void __launch_bounds__(kOptThreads)
 polyak_kernel(float *__restrict__ target, const float *__restrict__ src, int n, float tau, float omt,
               const int *__restrict__ tmap, float *__restrict__ targetT) {
+  pdl_wait();
+  pdl_launch_dependents();
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
     const float t = tau * src[e] + omt * target[e];
     target[e] = t;
@@ -244,7 +252,7 @@ polyak_kernel(float *__restrict__ target, const float *__restrict__ src, int n, 
 
 void launch_polyak(float *target, const float *src, int n, float tau, float one_minus_tau,
                    const int *tmap, float *targetT, cudaStream_t st) {
-  polyak_kernel<<<reduce_grid(n), kOptThreads, 0, st>>>(target, src, n, tau, one_minus_tau, tmap, targetT);
+  launch_pdl<PDL_OPTIM>(polyak_kernel, dim3(reduce_grid(n)), dim3(kOptThreads), 0, st, target, src, n, tau, one_minus_tau, tmap, targetT);
   GCRL_LAUNCHED();
 }
 
