@@ -200,8 +200,9 @@ class ClockSampler(threading.Thread):
     def __init__(self, index, period=0.02):
         super().__init__(daemon=True)
         self.index, self.period = index, period
-        self.samples, self.reasons, self.stop_flag = [], set(), False
+        self.samples, self.times, self.reasons, self.stop_flag = [], [], set(), False
         self.max_mhz, self.ok = None, False
+        self.armed, self.window = False, [None, None]   # throttle reasons / clocks are reported for the armed window
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -215,13 +216,15 @@ class ClockSampler(threading.Thread):
     def sample(self):
         nv = self.nv
         self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        self.times.append(time.perf_counter())
         try:
             mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
         except Exception:   # noqa: BLE001
             mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-        for name, bit in {**self.BAD, **self.NOTE}.items():
-            if mask & bit:
-                self.reasons.add(name)
+        if self.armed:
+            for name, bit in {**self.BAD, **self.NOTE}.items():
+                if mask & bit:
+                    self.reasons.add(name)
 
     def run(self):
         while self.ok and not self.stop_flag:
@@ -231,14 +234,291 @@ class ClockSampler(threading.Thread):
                 break
             time.sleep(self.period)
 
+    def arm(self):
+        """Start of the window the clocks line describes (the thread itself was started long before, so that its
+        start-up cannot disturb the timed steps)."""
+        self.armed, self.window[0] = True, time.perf_counter()
+
+    def disarm(self):
+        self.armed, self.window[1] = False, time.perf_counter()
+
     def result(self):
         self.stop_flag = True
         if not self.ok:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml_unavailable"]}
         if not self.samples:
             self.sample()
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": float(self.max_mhz),
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        t0, t1 = self.window
+        inwin = [m for m, t in zip(self.samples, self.times) if t0 is not None and t0 <= t <= (t1 or t)]
+        use = inwin if len(inwin) >= 3 else self.samples
+        return {"sm_mhz": float(np.median(use)), "sm_max_mhz": float(self.max_mhz),
+                "reasons": sorted(self.reasons), "samples": len(use),
+                "window": "timed steps + 0.3 s of the same load" if use is inwin else "whole run (window too short)"}
+
+
+
+# ------------------------------------------------------------------------------------------
+# data-parallel evidence (N > 1): replicas identical, and N ranks == 1 rank on the concatenated batch
+# ------------------------------------------------------------------------------------------
+def dp_parity(args, local, rank, world, dp_mode, updates=4):
+    """Outside every timed region: `updates` DDPG updates on fixed per-rank batches through the data-parallel
+    path that is being benchmarked; every rank hashes all four networks (replicas must be bit-identical); rank 0
+    repeats the run with ONE agent (fp32 FFMA engine) on the concatenated batches and reports the largest
+    deviation, relative to the largest weight of the tensor (SURVEY 8e parity rule)."""
+    import hashlib
+
+    import torch
+    import torch.distributed as dist
+    from gcrl_b200 import DDPG
+    O, G, A, B = args.obs, args.goal, args.act, args.batch
+    D = O + G
+
+    def batch_of(r, i):
+        g = np.random.default_rng(5000 + 97 * i + r)
+        s = g.standard_normal((B, D)).astype(np.float32)
+        ns = (s + 0.1 * g.standard_normal((B, D))).astype(np.float32)
+        a = g.uniform(-1, 1, (B, A)).astype(np.float32)
+        rew = -(g.random((B, 1)) > 0.3).astype(np.float32)
+        d = (g.random((B, 1)) < 0.1).astype(np.float32)
+        return s, a, rew, ns, d
+
+    def nets(ag):
+        return [w for net in (ag.actor, ag.critic, ag.target_actor, ag.target_critic) for pair in net.layers() for w in pair]
+
+    def fresh(max_batch, precision=1):
+        torch.manual_seed(777)
+        return DDPG(D, A, agent_config(args, 1000), None, 1, 40, device=local, max_batch=max_batch, precision=precision)
+
+    steps = list(range(38, 38 + updates))            # crosses the step-40 Polyak update
+    ag = fresh(B)
+    if dp_mode == "p2p":
+        ag.enable_peer_data_parallel()
+    else:
+        ag.enable_data_parallel()
+    for i, st in enumerate(steps):
+        info = ag.update(st, batch=tuple(torch.from_numpy(x).cuda(local) for x in batch_of(rank, i)))
+    mine = nets(ag)
+    digest = hashlib.sha1(b"".join(np.ascontiguousarray(w).tobytes() for w in mine)).hexdigest()
+    digests = [None] * world
+    dist.all_gather_object(digests, digest)
+    metrics = [None] * world
+    dist.all_gather_object(metrics, [float(x) for x in info])
+    out = {"replicas_identical": len(set(digests)) == 1, "updates": updates, "batch_per_rank": B, "path": dp_mode,
+           "metrics_identical": all(m == metrics[0] for m in metrics)}
+    if rank == 0:
+        one = fresh(world * B, precision=0)
+        for i, st in enumerate(steps):
+            cat = [np.concatenate([batch_of(r, i)[j] for r in range(world)]) for j in range(5)]
+            one.update(st, batch=tuple(torch.from_numpy(x).cuda(local) for x in cat))
+        rel = max(float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-30)) for a, b in zip(mine, nets(one)))
+        out["max_rel_vs_concat"] = rel
+        out["tolerance"] = 1e-4
+        out["ok"] = bool(out["replicas_identical"] and rel < 1e-4)
+        del one
+    del ag
+    torch.cuda.synchronize()
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# the other BASELINE configs, short runs (also at N > 1, so that the scaling record carries them)
+# ------------------------------------------------------------------------------------------
+def extra_configs(args, local, rank, world, dp_mode, flush, stream, peaks):
+    import types as _t
+
+    import torch
+    import torch.distributed as dist
+    from gcrl_b200 import DDPG, HERBuffer, TQCAgent
+    from gcrl_b200._lib import check, lib, vp
+    dev = torch.device("cuda", local)
+    sp = vp(stream.cuda_stream)
+    out = {}
+    T = 50
+
+    def maxr(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def fill(buf, data, E):
+        for e in range(E):
+            buf.push_episode(data["s"][e], data["a"][e], data["ns"][e], data["r"][e], data["d"][e], data["ag"][e], data["fut"][e])
+
+    def timed(fn, n, align=None):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for i, (e0, e1) in enumerate(evs):
+            flush.fill_(i & 0xFF)
+            if align is not None:
+                align()
+            e0.record(stream)
+            fn(i)
+            e1.record(stream)
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs) / n
+
+    # ---- configs[2]: DDPG, PickAndPlace shape (obs 19 + goal 3, act 4, H 256 x 3, k_future 8), GLOBAL batch 65536
+    try:
+        O, G, A, k, H, L = 19, 3, 4, 8, 256, 3
+        gb = 65536
+        Bl = gb // world
+        E = 2000
+        rng = np.random.default_rng(3000 + rank)
+        data = synth(rng, E, T, O, G, A, k)
+        a2 = _t.SimpleNamespace(**vars(args))
+        a2.obs, a2.goal, a2.act, a2.k_future, a2.hidden, a2.layers, a2.batch = O, G, A, k, H, L, Bl
+        torch.manual_seed(1898)
+        ag = DDPG(O + G, A, agent_config(a2, E * ((T - 1) * (k + 1) + 1)), None, 1, 40, index_source="device",
+                  device=local, max_batch=Bl, seed=4000 + rank)
+        fill(ag.buffer, data, E)
+        align = None
+        if world > 1:
+            if dp_mode == "p2p":
+                ag.enable_peer_data_parallel()
+                align = ag.peer_barrier
+            else:
+                ag.enable_data_parallel()
+        st = [1]
+
+        def one(_i):
+            ag._run_update(st[0], sync=False)
+            st[0] += 1
+        for _ in range(12):
+            one(0)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms_k = maxr(timed(one, 10, align))
+        amac = (O + G) * H + (L - 1) * H * H + H * A
+        cmac = (O + G + A) * H + (L - 1) * H * H + H
+        flops = 2.0 * (4 * amac + 6 * cmac) * gb
+        info = ag.read_metrics()
+        out["ddpg_pickplace_global_B65536"] = {
+            "workload": f"DDPG sample+update, PickAndPlace shape (obs {O}, goal {G}, act {A}), k_future {k}, hidden {H} x {L}, "
+                        f"global batch {gb} = {Bl} per GPU x {world}, {E * T} stored transitions per GPU",
+            "ms_per_step": ms_k, "transitions_per_s": gb / (ms_k * 1e-3), "updates_per_s": 1e3 / ms_k,
+            "update_tflops": flops / (ms_k * 1e-3) / 1e12, "scaling": "strong", "path": dp_mode if world > 1 else "single GPU",
+            "engine": "tcgen05 3xTF32" if Bl >= 2048 else "row-slab fp32", "finite": bool(all(np.isfinite(float(x)) for x in info))}
+        del ag, data
+        torch.cuda.empty_cache()
+    except Exception as e:   # noqa: BLE001
+        out["ddpg_pickplace_global_B65536"] = {"error": repr(e)}
+
+    # ---- configs[3]: TQC, Slide shape (= Push: obs 18 + goal 3, act 3), 5 critics / drop 2, batch 512 per GPU
+    try:
+        O, G, A, k, H, L, Bl = 18, 3, 3, 4, 512, 3, 512
+        E = 2000
+        rng = np.random.default_rng(6000 + rank)
+        data = synth(rng, E, T, O, G, A, k)
+        a3 = _t.SimpleNamespace(**vars(args))
+        a3.obs, a3.goal, a3.act, a3.k_future, a3.hidden, a3.layers, a3.batch = O, G, A, k, H, L, Bl
+        cfg = agent_config(a3, E * ((T - 1) * (k + 1) + 1))
+        cfg.alpha_lr, cfg.alpha_min, cfg.alpha_min_steps, cfg.grad_clip, cfg.gamma = 3e-4, 3e-4, 1, 5.0, 0.95
+        torch.manual_seed(1898)
+        tq = TQCAgent(O + G, A, cfg, None, 1, 40, index_source="device", device=local)
+        fill(tq.buffer, data, E)
+        if world > 1:
+            tq.enable_data_parallel()
+        for i in range(6):
+            tq.update(i + 1)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        n = 30
+        t0 = time.perf_counter()
+        for i in range(n):
+            info = tq.update(7 + i)
+        torch.cuda.synchronize()
+        ms_k = maxr((time.perf_counter() - t0) * 1e3 / n)
+        out["tqc_slide_B512_per_gpu"] = {
+            "workload": f"TQCAgent.update (5 scalar critics, drop top 2, learned alpha), Slide shape (obs {O}, goal {G}, act {A}), "
+                        f"hidden {H} x {L} (config_tqc_push.yaml), batch {Bl} per GPU, metric read-back every update",
+            "ms_per_update": ms_k, "updates_per_s": 1e3 / ms_k, "transitions_per_s": world * Bl / (ms_k * 1e-3),
+            "scaling": "weak", "path": "NCCL all-reduce between the update phases" if world > 1 else "single GPU",
+            "finite": bool(all(np.isfinite(float(np.mean(x))) for x in info))}
+        del tq, data
+        torch.cuda.empty_cache()
+    except Exception as e:   # noqa: BLE001
+        out["tqc_slide_B512_per_gpu"] = {"error": repr(e)}
+
+    # ---- configs[4]: the sampler on a 10M-transition shard per GPU (no collective: shards are independent);
+    # at N = 1 the `rooflines` section already carries these points (her_sample_kernel_B*_buffer10M)
+    try:
+        if world == 1:
+            raise StopIteration
+        O, G, A, k = args.obs, args.goal, args.act, args.k_future
+        D = O + G
+        E = 20000
+        rng = np.random.default_rng(8000 + rank)
+        data = synth(rng, E, T, O, G, A, k)
+        per_ep = (T - 1) * (k + 1) + 1
+        big = HERBuffer(10 * E * per_ep, 50, 1, k_future=k, index_source="device", seed=7 + rank, device=local)
+        for _rep in range(10):
+            fill(big, data, E)
+        torch.cuda.synchronize()
+        alg_bytes = 4 * (2 * O + A + 2 * G) + 5 + 4 * (2 * D + A + 2)
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        rec = {}
+        for batch in (256, 65536):
+            outs = [torch.empty((batch, w), dtype=torch.float32, device=dev) for w in (D, A, 1, D, 1)]
+            ptrs = [vp(o.data_ptr()) for o in outs]
+
+            def one(_i):
+                check(lib.gcrl_her_sample(big.handle, batch, None, *ptrs, None, sp))
+            for _ in range(5):
+                one(0)
+            if world > 1:
+                dist.barrier()
+            ms_k = maxr(timed(one, 30))
+            ach = batch * alg_bytes / (ms_k * 1e-3) / 1e9
+            rec[f"B{batch}"] = {"ms_per_launch": ms_k, "transitions_per_s": world * batch / (ms_k * 1e-3),
+                                "hbm_gbs_per_gpu": ach, "hbm_frac_per_gpu": ach / hbm_peak}
+        out["sampler_10M_per_gpu"] = {
+            "workload": f"HER sample + relabel + reward on {len(big)} deque entries (10M stored transitions) per GPU, "
+                        f"Push shape, every GPU samples its own shard", "scaling": "weak", **rec}
+        del big, data
+        torch.cuda.empty_cache()
+    except StopIteration:
+        pass
+    except Exception as e:   # noqa: BLE001
+        out["sampler_10M_per_gpu"] = {"error": repr(e)}
+    return out
+
+
+def normaliser_rooflines(local, flush, stream, hbm_peak, dim=19):
+    """RunningNormalizer.update / normalize (src/utils.py:75-98) on device-resident float32 batches [n, dim]:
+    update reads the batch once (4 n dim bytes), normalize reads it and writes float32 (8 n dim bytes)."""
+    import ctypes as C
+
+    import torch
+    from gcrl_b200 import RunningNormalizer
+    from gcrl_b200._lib import check, lib, vp
+    dev = torch.device("cuda", local)
+    sp = vp(stream.cuda_stream)
+    out = {}
+    nz = RunningNormalizer(dim, device=local)
+    for n in (64, 100_000, 1_000_000):
+        x = torch.randn(n, dim, device=dev)
+        y = torch.empty(n, dim, device=dev)
+        for name, fn, nbytes in (
+                ("norm_update", lambda: check(lib.gcrl_norm_update_dev(nz._h, vp(x.data_ptr()), n, 0, sp)), 4 * n * dim),
+                ("norm_apply", lambda: check(lib.gcrl_norm_apply_dev_f32(nz._h, vp(x.data_ptr()), n, 0, vp(y.data_ptr()), dim, 0, sp)),
+                 8 * n * dim)):
+            for _ in range(3):
+                fn()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+            for i, (a0, a1) in enumerate(evs):
+                flush.fill_(i & 0xFF)
+                a0.record(stream)
+                fn()
+                a1.record(stream)
+            torch.cuda.synchronize()
+            ms_k = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+            ach = nbytes / (ms_k * 1e-3) / 1e9
+            out[f"{name}_n{n}_dim{dim}"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                                            "frac": ach / hbm_peak, "traffic": None, "ms_per_launch": ms_k,
+                                            "algorithmic_bytes_per_launch": nbytes, "rows_per_s": n / (ms_k * 1e-3)}
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -305,41 +585,79 @@ def gpu_main(args):
                 agent.enable_data_parallel()
         else:
             agent.enable_data_parallel()
+    parity = None
+    if world > 1:
+        try:
+            parity = dp_parity(args, local, rank, world, args.dp)
+            log(f"[rank {rank}] dp_parity: {parity}")
+        except Exception as e:   # noqa: BLE001
+            parity = {"error": repr(e)}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
     sp = vp(stream.cuda_stream)
+    clocks = ClockSampler(local)     # started here, long before the timed window (arm() marks the window)
+    clocks.start()
 
-    def device_step(step, batch=B):
+    def device_step(step, batch=B, ag=None):
         """Async step on the device index stream, no host read-back (what `value` times)."""
-        agent.batch_size = batch
-        agent._run_update(step, sync=False)
+        ag = ag or agent
+        ag.batch_size = batch
+        ag._run_update(step, sync=False)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_steps(n, first_step, batch=B, do_flush=True):
+    def timed_steps(n, first_step, batch=B, do_flush=True, ag=None):
+        """n steps, each bracketed by CUDA events on the launching stream; returns the per-step ms.  With the
+        peer-memory path the ranks are re-aligned by one flag barrier AFTER the L2 flush and BEFORE the start
+        event: the (untimed) 256 MiB flush finishes at slightly different times on every rank, and without the
+        alignment that skew would be charged to the step through its first gradient barrier."""
+        ag = ag or agent
+        align = world > 1 and getattr(ag, "_peer_dp", None) is not None
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
         for i, (e0, e1) in enumerate(evs):
             if do_flush:
                 flush.fill_(i & 0xFF)
+            if align:
+                ag.peer_barrier()
             e0.record(stream)
-            device_step(first_step + i, batch)
+            device_step(first_step + i, batch, ag)
             e1.record(stream)
         torch.cuda.synchronize()
-        return sum(a.elapsed_time(b) for a, b in evs)    # ms
+        return [a.elapsed_time(b) for a, b in evs]    # ms
+
+    def over_ranks(per_step):
+        """max over ranks of the summed time (the contract's number) + where the time went per rank and step."""
+        t = torch.tensor(per_step, dtype=torch.float64, device=dev)
+        if world > 1:
+            allt = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            allt = torch.stack(allt).cpu().numpy()
+        else:
+            allt = t.cpu().numpy()[None]
+        sums = allt.sum(1)
+        r, i = np.unravel_index(int(np.argmax(allt)), allt.shape)
+        detail = {"rank0": [round(float(x), 4) for x in allt[0]],
+                  "max_over_ranks": [round(float(x), 4) for x in allt.max(0)],
+                  "sum_ms_per_rank": [round(float(x), 4) for x in sums],
+                  "slowest": {"rank": int(r), "step": int(i), "ms": round(float(allt[r, i]), 4)},
+                  "median_ms": round(float(np.median(allt)), 4)}
+        return float(sums.max()), detail
 
     # ---- warm-up (graph capture for both flag sets, clocks ramp), then the timed region ----
     step = 1
     for _ in range(max(args.warmup, 3) + args.spinup):
         device_step(step)
         step += 1
+    for _ in timed_steps(3, step):        # the timed loop's own code path (events, flush, alignment), untimed
+        pass
+    step += 3
     barrier()
-    clocks = ClockSampler(local)
-    clocks.start()
+    clocks.arm()
     l0 = int(lib.gcrl_kernel_launches())
-    ms = timed_steps(args.steps, step)
+    per_step = timed_steps(args.steps, step)
     step += args.steps
     launches = int(lib.gcrl_kernel_launches()) - l0
     barrier()
@@ -349,11 +667,9 @@ def gpu_main(args):
         device_step(step)
         step += 1
     torch.cuda.synchronize()
+    clocks.disarm()
     clk = clocks.result()
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms, per_step_detail = over_ranks(per_step)
     value = world * B * args.steps / (ms * 1e-3)
 
     # back-to-back (no flush, graph replays pipelined): the production regime, reported beside `value`
@@ -569,13 +885,21 @@ def gpu_main(args):
             device_step(step, batch)
             step += 1
         n = max(20, min(200, args.steps))
-        ms_s = timed_steps(n, step, batch)
+        ms_s = sum(timed_steps(n, step, batch))
         step += n
         flops = 2.0 * (4 * (D * args.hidden + (args.layers - 1) * args.hidden ** 2 + args.hidden * A)
                        + 6 * ((D + A) * args.hidden + (args.layers - 1) * args.hidden ** 2 + args.hidden)) * batch
         sweep[f"B{batch}"] = {"ms_per_step": ms_s / n, "transitions_per_s": batch * n / (ms_s * 1e-3),
                               "updates_per_s": n / (ms_s * 1e-3), "update_tflops": flops / (ms_s / n * 1e-3) / 1e12}
 
+    extra = {}
+    if not args.no_sweep:
+        extra = extra_configs(args, local, rank, world, args.dp, flush, stream, peaks)
+    if rank == 0 and not args.no_sweep:
+        try:
+            rooflines.update(normaliser_rooflines(local, flush, stream, hbm_peak))
+        except Exception as e:   # noqa: BLE001
+            log(f"[roofline] normaliser timing skipped: {e}")
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_arm(args, 10 ** 9, 2, seconds=args.cpu_seconds)
@@ -593,6 +917,7 @@ def gpu_main(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
             "updates_per_s": world * args.steps / (ms * 1e-3) / world,
+            "per_step_ms": per_step_detail,
             "back_to_back": {"ms_per_step": ms_b2b / args.steps, "value": world * B * args.steps / (ms_b2b * 1e-3),
                              "note": "same steps without the L2 flush, graph replays pipelined"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -603,7 +928,7 @@ def gpu_main(args):
                                             "value": world * B * n_e2e / (ms_e2e_dev * 1e-3),
                                             "note": "same call, index_source='device' (rank-local wall clock)"}},
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "rooflines": rooflines, "sweep": sweep,
-            "variants": variants,
+            "variants": variants, "configs": extra, "dp_parity": parity,
             "cpu_baseline": None if cpu is None else {k_: cpu[k_] for k_ in ("value", "unit", "cores", "kind", "sample")},
             "library": os.path.relpath(gcrl_b200.library_path(), ROOT),
             "kernel_launches_total": int(lib.gcrl_kernel_launches()) - launches0,

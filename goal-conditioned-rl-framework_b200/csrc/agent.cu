@@ -148,8 +148,10 @@ struct gcrl_agent {
     bool on = false;
     int rank = 0, world = 1;
     unsigned int *flags = nullptr, *epoch = nullptr;     // [8] arrival counters written by the peers; my barrier count
+    unsigned int *ticket = nullptr, *wticket = nullptr;  // CTA tickets of the barrier + average launch / the weight-gradient launch
+    bool signalled = false;                              // capture-time: the gradient's producer raises the flag itself
     int *err = nullptr;
-    float *outbox = nullptr, *metrics_avg = nullptr;     // [8] metrics published to / averaged over the ranks
+    float *outbox = nullptr, *metrics_avg = nullptr;     // [2][8] metrics published to / [8] averaged over the ranks
     float *gavg[NUM_NETS] = {};                          // averaged gradient of every trainable network
     unsigned int **d_peer_flags = nullptr;               // device arrays of `world` peer pointers
     float **d_peer_outbox = nullptr;
@@ -261,7 +263,8 @@ void adam_step(gcrl_agent *ag, Net &n, int which, float max_norm, int slot_norm,
   a.sc = ag->d_scalars; a.which = which;
   a.target = target ? target->p : nullptr; a.tau = ag->cfg.tau; a.one_minus_tau = float(1.0 - double(ag->cfg.tau));
   a.polyak = (polyak && target) ? 1 : 0;
-  a.metrics = ag->metrics; a.slot_norm = slot_norm;
+  a.metrics = ag->p2p.on ? ag->p2p.metrics_avg : ag->metrics;   // the norm of the averaged gradient is global already
+  a.slot_norm = slot_norm;
   a.tmap = n.tmap; a.pT = n.pT; a.targetT = target ? target->pT : nullptr;
   launch_adam(a, st);
 }
@@ -373,6 +376,12 @@ void fused_wgrads(gcrl_agent *ag, Net &n, const Acts &acts, int K0, const float 
   fin.metric_scale = 1.0f / float(B);
   fin.metrics = ag->metrics;
   fin.slot_loss = slot_loss; fin.slot_td = slot_td; fin.slot_q = slot_q;
+  if (ag->p2p.on) {       // the last CTA raises this rank's flag at every peer (p2p_average then only waits)
+    auto &pp = ag->p2p;
+    fin.peer_flags = pp.d_peer_flags; fin.epoch = pp.epoch; fin.ticket = pp.wticket; fin.outbox = pp.outbox;
+    fin.rank = pp.rank; fin.world = pp.world;
+    pp.signalled = true;
+  }
   ag->nsumsq = launch_wgrad_complete(pr, L + 1, B, fin, st);
 }
 
@@ -457,14 +466,21 @@ void critic2_phase_grads(gcrl_agent *ag, int B, cudaStream_t st) {   // TD3 only
 
 // clip + Adam (+ Polyak) of critic `which`; rereduce: gradients were replaced by the cross-rank
 // average, so the sums of squares are recomputed first.
-// p2p mode: barrier (every rank's local gradient of `net` is complete), then average the peers' buffers
-// into p2p.gavg[net] (+ the sums of squares the clip needs).  The next barrier in stream order also
-// guarantees that every rank finished reading before anybody overwrites its local gradient again.
-const float *p2p_average(gcrl_agent *ag, int net, cudaStream_t st) {
+// p2p mode: ONE launch per network -- flag barrier (every rank's local gradient of `net` is complete), average of
+// the peers' buffers into p2p.gavg[net] (+ the sums of squares the clip needs), and the batch-mean metrics that
+// are final at this point (`metric_mask`, slot bits) averaged over the ranks on the same barrier.
+const float *p2p_average(gcrl_agent *ag, int net, unsigned int metric_mask, cudaStream_t st) {
   auto &pp = ag->p2p;
-  launch_p2p_barrier(pp.d_peer_flags, pp.epoch, pp.rank, pp.world, pp.err, st);
-  launch_p2p_reduce(pp.d_peer_g[net], pp.world, pp.gavg[net], ag->net[net].total, ag->sumsq, st);
-  ag->nsumsq = reduce_grid(ag->net[net].total);
+  P2PReduceHost h{};
+  h.peers = pp.d_peer_g[net]; h.peer_flags = pp.d_peer_flags; h.peer_outbox = pp.d_peer_outbox;
+  h.epoch = pp.epoch; h.ticket = pp.ticket; h.err = pp.err;
+  h.rank = pp.rank; h.world = pp.world; h.n = ag->net[net].total;
+  h.out = pp.gavg[net]; h.sumsq_partials = ag->sumsq;
+  h.local_metrics = ag->metrics; h.outbox = pp.outbox; h.metrics_avg = pp.metrics_avg; h.metric_mask = metric_mask;
+  h.signalled = pp.signalled ? 1 : 0;
+  pp.signalled = false;
+  launch_p2p_reduce(h, st);
+  ag->nsumsq = p2p_reduce_grid(ag->net[net].total);
   return pp.gavg[net];
 }
 
@@ -473,7 +489,10 @@ void critic_phase_step(gcrl_agent *ag, int which, int flags, bool rereduce, cuda
   const int id = which == 0 ? CRITIC1 : CRITIC2;
   Net &c = ag->net[id];
   const float *grad = nullptr;
-  if (ag->p2p.on) grad = p2p_average(ag, id, st);
+  // metrics final before this barrier: DDPG critic loss / td / q; TD3 critic 1: its loss; critic 2: loss, td, q
+  const unsigned int mm = !ag->td3 ? ((1u << S_CLOSS) | (1u << S_TD) | (1u << S_Q))
+                                   : (which == 0 ? (1u << S_CLOSS) : ((1u << S_C2LOSS) | (1u << S_TD) | (1u << S_Q)));
+  if (ag->p2p.on) grad = p2p_average(ag, id, mm, st);
   else if (rereduce && fused_ok(ag, ag->dp_B)) fused_grad_sumsq(ag, c, st);
   else if (rereduce) reduce_grads(ag, c, nullptr, 0, true, -1, -1, -1, 0, 1, st);
   // TD3 critic 1 is NOT clipped (:201 is commented out), critic 2 is
@@ -534,7 +553,7 @@ void actor_phase_grads(gcrl_agent *ag, int B, cudaStream_t st) {
 void actor_phase_step(gcrl_agent *ag, bool rereduce, cudaStream_t st) {
   Net &a = ag->net[ACTOR];
   const float *grad = nullptr;
-  if (ag->p2p.on) grad = p2p_average(ag, ACTOR, st);
+  if (ag->p2p.on) grad = p2p_average(ag, ACTOR, 1u << S_ALOSS, st);
   else if (rereduce && fused_ok(ag, ag->dp_B)) fused_grad_sumsq(ag, a, st);
   else if (rereduce) reduce_grads(ag, a, nullptr, 0, true, -1, -1, -1, 0, 1, st);
   adam_step(ag, a, 1, ag->cfg.grad_clip, S_AGRAD, &ag->net[T_ACTOR], ag->td3, st, grad);
@@ -581,11 +600,6 @@ void run_update_body(gcrl_agent *ag, int B, const float *noise, int flags, int m
   }
   if ((mask & PH_AGRAD) && (flags & 1)) actor_phase_grads(ag, B, st);
   if ((mask & PH_ASTEP) && (flags & 1)) actor_phase_step(ag, dp, st);
-  if (ag->p2p.on && mask == PH_ALL) {          // batch-mean metrics averaged over the ranks (losses, td, q)
-    auto &pp = ag->p2p;
-    launch_p2p_metrics(pp.d_peer_flags, pp.epoch, pp.rank, pp.world, pp.err, ag->metrics, pp.outbox, pp.d_peer_outbox,
-                       pp.metrics_avg, st);
-  }
 }
 
 // Replay (or capture on first use) the graph of (B, flags, phase mask).  TD3 noise pointers vary
@@ -775,7 +789,7 @@ int gcrl_agent_destroy(gcrl_agent *ag) {
   cudaDeviceSynchronize();
   for (auto &kv : ag->graphs) cudaGraphExecDestroy(kv.second.exec);
   for (void *p : ag->p2p.opened) cudaIpcCloseMemHandle(p);
-  for (void *p : {(void *)ag->p2p.flags, (void *)ag->p2p.epoch, (void *)ag->p2p.err, (void *)ag->p2p.outbox,
+  for (void *p : {(void *)ag->p2p.flags, (void *)ag->p2p.epoch, (void *)ag->p2p.ticket, (void *)ag->p2p.wticket, (void *)ag->p2p.err, (void *)ag->p2p.outbox,
                   (void *)ag->p2p.metrics_avg, (void *)ag->p2p.d_peer_flags, (void *)ag->p2p.d_peer_outbox})
     if (p) cudaFree(p);
   for (int i = 0; i < NUM_NETS; ++i) {
@@ -1093,13 +1107,17 @@ int gcrl_agent_dp_export(gcrl_agent *ag, unsigned char *handles /*[n_items][64]*
   if (pp.flags == nullptr) {
     pp.flags = dev_alloc<unsigned int>(8);
     pp.epoch = dev_alloc<unsigned int>(1);
+    pp.ticket = dev_alloc<unsigned int>(1);
+    pp.wticket = dev_alloc<unsigned int>(1);
+    GCRL_CUDA(cudaMemset(pp.wticket, 0, sizeof(unsigned int)));
     pp.err = dev_alloc<int>(1);
-    pp.outbox = dev_alloc<float>(8);
+    pp.outbox = dev_alloc<float>(16);
     pp.metrics_avg = dev_alloc<float>(8);
     GCRL_CUDA(cudaMemset(pp.flags, 0, 8 * sizeof(unsigned int)));
     GCRL_CUDA(cudaMemset(pp.epoch, 0, sizeof(unsigned int)));
+    GCRL_CUDA(cudaMemset(pp.ticket, 0, sizeof(unsigned int)));
     GCRL_CUDA(cudaMemset(pp.err, 0, sizeof(int)));
-    GCRL_CUDA(cudaMemset(pp.outbox, 0, 8 * sizeof(float)));
+    GCRL_CUDA(cudaMemset(pp.outbox, 0, 16 * sizeof(float)));
     GCRL_CUDA(cudaMemset(pp.metrics_avg, 0, 8 * sizeof(float)));
     GCRL_CUDA(cudaDeviceSynchronize());
   }
@@ -1152,6 +1170,15 @@ int gcrl_agent_dp_connect(gcrl_agent *ag, int rank, int world, const unsigned ch
   for (auto &kv : ag->graphs) cudaGraphExecDestroy(kv.second.exec);      // graphs captured without the averaging
   ag->graphs.clear();
   GCRL_CUDA(cudaDeviceSynchronize());
+  GCRL_API_END
+}
+
+int gcrl_agent_dp_barrier(gcrl_agent *ag, void *stream) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(ag != nullptr && ag->p2p.on, "peer-memory data parallelism is not connected");
+  GCRL_CUDA(cudaSetDevice(ag->device));
+  auto &pp = ag->p2p;
+  launch_p2p_barrier(pp.d_peer_flags, pp.epoch, pp.rank, pp.world, pp.err, as_stream(stream));
   GCRL_API_END
 }
 

@@ -89,7 +89,7 @@ struct PinnedRing {
 // device calls are then no-ops).  Measured (profiles/README.md, round 2): worth ~1.5 us per update on the row-slab
 // and optimiser kernels; HARMFUL for the weight-gradient launch, whose 576 small CTAs, let in early, all land on
 // the 20 SMs the 128-CTA row-slab kernel leaves free (+10 us) -- hence the default class mask.
-enum : int { PDL_FUSED = 1, PDL_WGRAD = 2, PDL_OPTIM = 4, PDL_OTHER = 8 };   // GCRL_PDL_MASK selects kernel classes
+enum : int { PDL_FUSED = 1, PDL_WGRAD = 2, PDL_OPTIM = 4, PDL_OTHER = 8, PDL_P2P = 16 };   // GCRL_PDL_MASK selects kernel classes
 bool pdl_enabled(int cls = PDL_OTHER);
 template <int CLS = PDL_OTHER, typename... KArgs, typename... Args>
 void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {

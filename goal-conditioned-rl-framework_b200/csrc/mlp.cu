@@ -438,6 +438,28 @@ __global__ void __launch_bounds__(kWgThreads * GROUPS) wgrad_tile_kernel(const _
     const int slot = t == 0 ? mg.fin.slot_loss : (t == 1 ? mg.fin.slot_td : mg.fin.slot_q);
     if (slot >= 0) mg.fin.metrics[slot] = s * mg.fin.metric_scale;
   }
+  if (mg.fin.peer_flags != nullptr) {
+    // every CTA: gradient tile (and tile 0's metrics) ordered before its ticket; the last one raises the flags
+    __shared__ int s_last;
+    __syncthreads();
+    if (t == 0) {
+      __threadfence();
+      const unsigned int k = atomicAdd(mg.fin.ticket, 1u);
+      s_last = k == gridDim.x - 1;
+      if (s_last) *mg.fin.ticket = 0;
+    }
+    __syncthreads();
+    if (s_last) {
+      const unsigned int e = *mg.fin.epoch + 1u;
+      if (t < 8) mg.fin.outbox[(e & 1u) * 8 + t] = __ldcg(mg.fin.metrics + t);
+      __syncthreads();
+      if (t < mg.fin.world) {
+        __threadfence_system();
+        volatile unsigned int *dst = mg.fin.peer_flags[t] + mg.fin.rank;
+        *dst = e;
+      }
+    }
+  }
 }
 
 // sums of squares of a complete flat gradient, tile by tile, bit-identical to what wgrad_tile_kernel leaves

@@ -90,6 +90,10 @@ struct WgradFinal {
   float *sumsq_partials;    // [tiles]
   const float *metric_partials; int metric_splits; float metric_scale;
   float *metrics; int slot_loss, slot_td, slot_q;
+  // peer-memory data parallelism: the LAST CTA to finish tells every peer "this rank's gradient is complete"
+  // (and publishes the metrics) -- the flag travels over NVLink while the averaging kernel is being launched
+  unsigned int *const *peer_flags; const unsigned int *epoch; unsigned int *ticket;
+  float *outbox; int rank, world;
 };
 // Split-batch partial slabs (summed later by reduce_grads); returns the number of batch slabs S.
 int launch_multi_wgrad(const WgradProblem *probs, int nprob, int M, int64_t split_stride, int max_splits,
@@ -198,11 +202,17 @@ void launch_adam(const AdamArgs &a, cudaStream_t st);
 // data-parallel averaging over NVLink peer memory (optim.cu)
 void launch_p2p_barrier(unsigned int *const *peer_flags, unsigned int *epoch, int rank, int world, int *err,
                         cudaStream_t st);
-void launch_p2p_reduce(const float *const *peers, int world, float *out, int n, float *sumsq_partials,
-                       cudaStream_t st);
-void launch_p2p_metrics(unsigned int *const *peer_flags, unsigned int *epoch, int rank, int world, int *err,
-                        const float *local, float *outbox, const float *const *peer_outbox, float *avg,
-                        cudaStream_t st);
+// flag barrier + rank-order average of one network's gradient + metric exchange, ONE launch (optim.cu)
+struct P2PReduceHost {
+  const float *const *peers; unsigned int *const *peer_flags; const float *const *peer_outbox;
+  unsigned int *epoch, *ticket; int *err;
+  int rank, world, n;
+  float *out, *sumsq_partials;
+  const float *local_metrics; float *outbox, *metrics_avg; unsigned int metric_mask;
+  int signalled;      // the producer of the gradient has already raised this rank's flag (WgradFinal::peer_flags)
+};
+int p2p_reduce_grid(int n);              // CTAs (= sums of squares) of the launch below
+void launch_p2p_reduce(const P2PReduceHost &h, cudaStream_t st);
 void launch_polyak(float *target, const float *src, int n, float tau, float one_minus_tau,
                    const int *tmap, float *targetT, cudaStream_t st);
 // pT[tmap[e]] = p[e] for every weight element

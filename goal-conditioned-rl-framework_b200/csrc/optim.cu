@@ -7,6 +7,7 @@
 // the split-batch partial gradients (+ sum of squares) and one fused clip + Adam (+ Polyak)
 // pass.  Bound: HBM traffic of 7 fp32 words per parameter (g, m, v, p read; m, v, p write).
 #include <algorithm>
+#include <cstdlib>
 
 #include "mlp.cuh"
 
@@ -112,66 +113,112 @@ void launch_p2p_barrier(unsigned int *const *peer_flags, unsigned int *epoch, in
   GCRL_LAUNCHED();
 }
 
-// out[e] = (sum_r peers[r][e]) / world  (+ per-CTA sums of squares for the global-norm clip)
-__global__ void __launch_bounds__(kOptThreads)
-p2p_reduce_kernel(const float *const *peers, int world, float inv_world, float *__restrict__ out, int n,
-                  float *__restrict__ sumsq_partials) {
+// ---- barrier + average in ONE launch ---------------------------------------------------------------------
+// CTA 0 publishes this rank's batch-mean metrics and tells every peer "my gradient of this network is complete"
+// (stream order: the weight-gradient kernel has finished); EVERY CTA then polls the rank's own flag words, which the
+// peers write over NVLink, and reads all ranks' buffers for its elements -- all loads of a thread in flight
+// together (an NVLink round trip is ~2 us; a load-add-load-add chain over 8 ranks would be 8 of them) -- summing
+// in rank order 0..N-1 on every rank: bit-identical replicas by construction.  The batch-mean metrics ride on
+// the same barrier (double-buffered outbox, rank-order mean).  The last CTA to finish advances the epoch word
+// the next barrier starts from.  Reuse of a gradient buffer is safe without a second barrier: a rank overwrites
+// it two barriers later, which its peers can only have reached after finishing these reads.
+struct P2PReduceArgs {
+  const float *const *peers;            // [world] flat gradient of this network on every rank
+  unsigned int *const *peer_flags;      // [world] flag arrays (8 words each)
+  const float *const *peer_outbox;      // [world] metric outboxes (2 x 8 floats each)
+  unsigned int *epoch, *ticket;
+  int *err;
+  int rank, world, n;
+  float inv_world;
+  float *out, *sumsq_partials;
+  const float *local_metrics;
+  float *outbox, *metrics_avg;
+  unsigned int metric_mask;             // slots averaged over the ranks at this barrier
+  int debug;                            // timing experiments only (GCRL_P2P_DEBUG): 1 no flag wait, 2 local reads only
+  int signalled;                        // this rank's flag was raised by the kernel that produced the gradient
+};
+
+template <int WORLD>
+__global__ void __launch_bounds__(kOptThreads) p2p_reduce_kernel(const __grid_constant__ P2PReduceArgs a) {
   __shared__ float scratch[32];
-  float sq = 0.f;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int r = 0; r < world; ++r) s += __ldcv(peers[r] + e);        // never from a stale L1 line
-    const float g = s * inv_world;
-    out[e] = g;
-    sq = fmaf(g, g, sq);
-  }
-  const float tot = block_sum_fixed(sq, scratch);
-  if (threadIdx.x == 0) sumsq_partials[blockIdx.x] = tot;
-}
-
-void launch_p2p_reduce(const float *const *peers, int world, float *out, int n, float *sumsq_partials,
-                       cudaStream_t st) {
-  p2p_reduce_kernel<<<reduce_grid(n), kOptThreads, 0, st>>>(peers, world, 1.0f / float(world), out, n, sumsq_partials);
-  GCRL_LAUNCHED();
-}
-
-// metrics in ONE single-block launch: publish the local 8 floats, flag barrier, average the ranks' copies
-// (losses, td error and q are batch means; the gradient norms are already global)
-__global__ void __launch_bounds__(32)
-p2p_metrics_kernel(unsigned int *const *peer_flags, unsigned int *epoch, int rank, int world, int *err,
-                   const float *__restrict__ local, float *__restrict__ outbox, const float *const *peer_outbox,
-                   float *__restrict__ avg) {
   __shared__ unsigned int e_s;
-  if (threadIdx.x < 8) outbox[threadIdx.x] = local[threadIdx.x];
-  if (threadIdx.x == 0) e_s = *epoch + 1u;
-  __syncwarp();
+  pdl_wait();      // (no early launch of the dependent optimiser kernel: its CTAs would sit on the SMs while this one polls)
+  const int tid = threadIdx.x;
+  if (tid == 0) e_s = *a.epoch + 1u;
+  __syncthreads();
   const unsigned int e = e_s;
-  if (int(threadIdx.x) < world) {
-    __threadfence_system();
-    volatile unsigned int *dst = peer_flags[threadIdx.x] + rank;
-    *dst = e;
-    volatile unsigned int *src = peer_flags[rank] + threadIdx.x;
+  if (blockIdx.x == 0 && !a.signalled) {
+    if (tid < 8) a.outbox[(e & 1u) * 8 + tid] = a.local_metrics[tid];
+    __syncthreads();
+    if (tid < a.world) {
+      __threadfence_system();                                  // gradient + outbox visible before the flag is
+      volatile unsigned int *dst = a.peer_flags[tid] + a.rank;
+      *dst = e;
+    }
+  }
+  if (tid < a.world && !(a.debug & 1)) {
+    // acquire loads at system scope: what the peer wrote before raising its flag is visible to the loads below
+    const unsigned int *src = a.peer_flags[a.rank] + tid;
     const long long t0 = clock64();
-    while (*src < e) {
-      if (clock64() - t0 > 120000000000ll) {
-        *err = 1;
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(src) : "memory");
+      if (seen < e && clock64() - t0 > 120000000000ll) {       // ~60 s: a peer died; fail loudly instead of hanging
+        *a.err = 1;
         break;
       }
-    }
-    __threadfence_system();
+    } while (seen < e);
   }
-  __syncwarp();
-  if (threadIdx.x < 8) {
+  __syncthreads();
+  float sq = 0.f;
+  const int n4 = a.n >> 2;                                     // flat buffers are 16-byte granular
+  for (int q = blockIdx.x * blockDim.x + tid; q < n4; q += gridDim.x * blockDim.x) {
+    float4 v[WORLD];
+#pragma unroll
+    for (int r = 0; r < WORLD; ++r)
+      if (r < a.world) v[r] = __ldcv(reinterpret_cast<const float4 *>(a.peers[(a.debug & 2) ? a.rank : r]) + q);   // never a stale L1 line
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < WORLD; ++r)
+      if (r < a.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+    s.x *= a.inv_world; s.y *= a.inv_world; s.z *= a.inv_world; s.w *= a.inv_world;
+    reinterpret_cast<float4 *>(a.out)[q] = s;
+    sq = fmaf(s.x, s.x, sq); sq = fmaf(s.y, s.y, sq); sq = fmaf(s.z, s.z, sq); sq = fmaf(s.w, s.w, sq);
+  }
+  const float tot = block_sum_fixed(sq, scratch);
+  if (tid == 0) a.sumsq_partials[blockIdx.x] = tot;
+  if (blockIdx.x == 0 && tid < 8 && ((a.metric_mask >> tid) & 1u)) {
     float s = 0.f;
-    for (int r = 0; r < world; ++r) s += __ldcv(peer_outbox[r] + threadIdx.x);
-    avg[threadIdx.x] = s / float(world);
+    for (int r = 0; r < a.world; ++r) s += __ldcv(a.peer_outbox[r] + (e & 1u) * 8 + tid);
+    a.metrics_avg[tid] = s * a.inv_world;
   }
-  if (threadIdx.x == 0) *epoch = e;
+  if (tid == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(a.ticket, 1u);
+    if (t == gridDim.x - 1) {
+      *a.ticket = 0;
+      *a.epoch = e;
+    }
+  }
 }
-void launch_p2p_metrics(unsigned int *const *peer_flags, unsigned int *epoch, int rank, int world, int *err,
-                        const float *local, float *outbox, const float *const *peer_outbox, float *avg,
-                        cudaStream_t st) {
-  p2p_metrics_kernel<<<1, 32, 0, st>>>(peer_flags, epoch, rank, world, err, local, outbox, peer_outbox, avg);
+
+int p2p_reduce_grid(int n) { return std::max(1, std::min(((n >> 2) + kOptThreads - 1) / kOptThreads, sm_count())); }
+
+void launch_p2p_reduce(const P2PReduceHost &h, cudaStream_t st) {
+  P2PReduceArgs a{};
+  a.peers = h.peers; a.peer_flags = h.peer_flags; a.peer_outbox = h.peer_outbox;
+  a.epoch = h.epoch; a.ticket = h.ticket; a.err = h.err;
+  a.rank = h.rank; a.world = h.world; a.n = h.n; a.inv_world = 1.0f / float(h.world);
+  a.out = h.out; a.sumsq_partials = h.sumsq_partials;
+  a.local_metrics = h.local_metrics; a.outbox = h.outbox; a.metrics_avg = h.metrics_avg; a.metric_mask = h.metric_mask;
+  GCRL_REQUIRE(h.world >= 1 && h.world <= 8 && (h.n & 3) == 0, "p2p reduce: 1 <= world <= 8, 16-byte granular buffers");
+  static const int debug = getenv("GCRL_P2P_DEBUG") ? atoi(getenv("GCRL_P2P_DEBUG")) : 0;
+  a.debug = debug;
+  a.signalled = h.signalled;
+  const dim3 grid(p2p_reduce_grid(h.n)), block(kOptThreads);
+  if (h.world <= 2) launch_pdl<PDL_P2P>(p2p_reduce_kernel<2>, grid, block, 0, st, a);
+  else if (h.world <= 4) launch_pdl<PDL_P2P>(p2p_reduce_kernel<4>, grid, block, 0, st, a);
+  else launch_pdl<PDL_P2P>(p2p_reduce_kernel<8>, grid, block, 0, st, a);
   GCRL_LAUNCHED();
 }
 

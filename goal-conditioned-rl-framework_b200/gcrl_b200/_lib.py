@@ -95,6 +95,7 @@ SIGNATURES = {
                                          C.c_int, vp]),
     "gcrl_agent_dp_export": (C.c_int, [vp, vp, C.POINTER(C.c_int)]),
     "gcrl_agent_dp_connect": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+    "gcrl_agent_dp_barrier": (C.c_int, [vp, vp]),
     "gcrl_agent_grad_buffer": (C.c_int, [vp, C.c_int, pp, C.POINTER(c_i64)]),
     "gcrl_agent_metrics_buffer": (C.c_int, [vp, pp]),
     # SAC / TQC

@@ -295,6 +295,10 @@ class _AgentBase:
         self._dp = None
         self._peer_dp = (rank, world)
 
+    def peer_barrier(self):
+        """One flag barrier over the peer-connected ranks on the current stream (no host synchronisation)."""
+        check(lib.gcrl_agent_dp_barrier(self._h, self._stream()))
+
     def enable_data_parallel(self, process_group=None, allreduce_mean=None):
         """Average gradients over the ranks of ``process_group`` (torch.distributed, NCCL over
         NVLink) between the backward and the optimiser phases of every update.  Each rank keeps

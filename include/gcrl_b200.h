@@ -257,6 +257,9 @@ int gcrl_agent_update_phase(gcrl_agent *h, int phase, gcrl_her *buf, int64_t B,
  * (same batch size and flags).  world <= 8 (one NVSwitch domain). */
 int gcrl_agent_dp_export(gcrl_agent *h, unsigned char *handles, int *n_items);
 int gcrl_agent_dp_connect(gcrl_agent *h, int rank, int world, const unsigned char *all_handles);
+/* One flag barrier over the connected ranks on `stream` (a single-warp kernel), outside any update: aligns
+ * the ranks, e.g. before a timed region.  Every rank must call it the same number of times. */
+int gcrl_agent_dp_barrier(gcrl_agent *h, void *stream);
 /* flat fp32 gradient of a trainable network: device pointer + element count (for NCCL) */
 int gcrl_agent_grad_buffer(gcrl_agent *h, int net, float **grad_dev, int64_t *count);
 /* device float[8] holding the metrics of the most recent update (averaged across ranks by the
