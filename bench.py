@@ -671,6 +671,8 @@ def gpu_main(args):
     clk = clocks.result()
     ms, per_step_detail = over_ranks(per_step)
     value = world * B * args.steps / (ms * 1e-3)
+    agent.read_metrics()           # (outside the timed region) surfaces a data-parallel watchdog error right here
+    log(f"[rank {rank}] timed steps done: {ms / args.steps:.4f} ms per step")
 
     # back-to-back (no flush, graph replays pipelined): the production regime, reported beside `value`
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -685,6 +687,8 @@ def gpu_main(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_b2b = float(t.item())
+    agent.read_metrics()
+    log(f"[rank {rank}] back-to-back steps done: {ms_b2b / args.steps:.4f} ms per step")
 
     # ---- e2e: the public API call a user makes -- agent.update(step) with the reference's host
     # Mersenne-Twister index stream (H2D of the positions from pinned memory), the 8-float metric

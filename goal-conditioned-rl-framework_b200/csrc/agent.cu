@@ -148,6 +148,7 @@ struct gcrl_agent {
     bool on = false;
     int rank = 0, world = 1;
     unsigned int *flags = nullptr, *epoch = nullptr;     // [8] arrival counters written by the peers; my barrier count
+    unsigned int *go = nullptr;                          // local release word: CTA 0 saw every peer's flag
     unsigned int *ticket = nullptr, *wticket = nullptr;  // CTA tickets of the barrier + average launch / the weight-gradient launch
     bool signalled = false;                              // capture-time: the gradient's producer raises the flag itself
     int *err = nullptr;
@@ -473,7 +474,7 @@ const float *p2p_average(gcrl_agent *ag, int net, unsigned int metric_mask, cuda
   auto &pp = ag->p2p;
   P2PReduceHost h{};
   h.peers = pp.d_peer_g[net]; h.peer_flags = pp.d_peer_flags; h.peer_outbox = pp.d_peer_outbox;
-  h.epoch = pp.epoch; h.ticket = pp.ticket; h.err = pp.err;
+  h.epoch = pp.epoch; h.ticket = pp.ticket; h.go = pp.go; h.err = pp.err;
   h.rank = pp.rank; h.world = pp.world; h.n = ag->net[net].total;
   h.out = pp.gavg[net]; h.sumsq_partials = ag->sumsq;
   h.local_metrics = ag->metrics; h.outbox = pp.outbox; h.metrics_avg = pp.metrics_avg; h.metric_mask = metric_mask;
@@ -699,7 +700,9 @@ void finish_metrics(gcrl_agent *ag, float *metrics_host, cudaStream_t st) {
   if (ag->p2p.on) {
     int err = 0;
     GCRL_CUDA(cudaMemcpy(&err, ag->p2p.err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (err) throw Error(GCRL_ERR_CUDA, "data-parallel barrier timed out: a peer rank stopped responding");
+    if (err)
+      throw Error(GCRL_ERR_CUDA, "data-parallel barrier timed out: rank " + std::to_string((err - 1) / 16) +
+                                     " never saw the flag of rank " + std::to_string((err - 1) % 16));
   }
 }
 
@@ -789,7 +792,7 @@ int gcrl_agent_destroy(gcrl_agent *ag) {
   cudaDeviceSynchronize();
   for (auto &kv : ag->graphs) cudaGraphExecDestroy(kv.second.exec);
   for (void *p : ag->p2p.opened) cudaIpcCloseMemHandle(p);
-  for (void *p : {(void *)ag->p2p.flags, (void *)ag->p2p.epoch, (void *)ag->p2p.ticket, (void *)ag->p2p.wticket, (void *)ag->p2p.err, (void *)ag->p2p.outbox,
+  for (void *p : {(void *)ag->p2p.flags, (void *)ag->p2p.epoch, (void *)ag->p2p.ticket, (void *)ag->p2p.wticket, (void *)ag->p2p.go, (void *)ag->p2p.err, (void *)ag->p2p.outbox,
                   (void *)ag->p2p.metrics_avg, (void *)ag->p2p.d_peer_flags, (void *)ag->p2p.d_peer_outbox})
     if (p) cudaFree(p);
   for (int i = 0; i < NUM_NETS; ++i) {
@@ -1110,6 +1113,8 @@ int gcrl_agent_dp_export(gcrl_agent *ag, unsigned char *handles /*[n_items][64]*
     pp.ticket = dev_alloc<unsigned int>(1);
     pp.wticket = dev_alloc<unsigned int>(1);
     GCRL_CUDA(cudaMemset(pp.wticket, 0, sizeof(unsigned int)));
+    pp.go = dev_alloc<unsigned int>(1);
+    GCRL_CUDA(cudaMemset(pp.go, 0, sizeof(unsigned int)));
     pp.err = dev_alloc<int>(1);
     pp.outbox = dev_alloc<float>(16);
     pp.metrics_avg = dev_alloc<float>(8);

@@ -205,7 +205,7 @@ void launch_p2p_barrier(unsigned int *const *peer_flags, unsigned int *epoch, in
 // flag barrier + rank-order average of one network's gradient + metric exchange, ONE launch (optim.cu)
 struct P2PReduceHost {
   const float *const *peers; unsigned int *const *peer_flags; const float *const *peer_outbox;
-  unsigned int *epoch, *ticket; int *err;
+  unsigned int *epoch, *ticket, *go; int *err;
   int rank, world, n;
   float *out, *sumsq_partials;
   const float *local_metrics; float *outbox, *metrics_avg; unsigned int metric_mask;

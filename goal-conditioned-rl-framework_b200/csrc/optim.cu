@@ -13,6 +13,7 @@
 
 namespace gcrl {
 
+long long p2p_timeout_cycles();
 constexpr int kOptThreads = 256;
 
 int reduce_grid(int total) {
@@ -84,7 +85,8 @@ void launch_reduce_grads(const ReduceArgs &a, cudaStream_t st) {
 // all-reduce is pure latency: 32 us through NCCL at 8 GPUs, measured).  Cross-GPU ordering is a flag barrier:
 // rank r bumps slot r of every peer's flag array, then spins on its own array.
 __global__ void __launch_bounds__(32)
-p2p_barrier_kernel(unsigned int *const *peer_flags, unsigned int *epoch, int rank, int world, int *err) {
+p2p_barrier_kernel(unsigned int *const *peer_flags, unsigned int *epoch, int rank, int world, int *err,
+                   long long timeout_cycles) {
   __shared__ unsigned int e_s;
   if (threadIdx.x == 0) e_s = *epoch + 1u;
   __syncwarp();
@@ -96,10 +98,11 @@ p2p_barrier_kernel(unsigned int *const *peer_flags, unsigned int *epoch, int ran
     volatile unsigned int *src = peer_flags[rank] + threadIdx.x;
     const long long t0 = clock64();
     while (*src < e) {
-      if (clock64() - t0 > 120000000000ll) {                  // ~60 s: a peer died; fail loudly instead of hanging
-        *err = 1;
+      if (clock64() - t0 > timeout_cycles) {                  // a peer died; fail loudly instead of hanging
+        *err = 1 + int(threadIdx.x) + 16 * rank;
         break;
       }
+      __nanosleep(40);
     }
     __threadfence_system();
   }
@@ -107,9 +110,20 @@ p2p_barrier_kernel(unsigned int *const *peer_flags, unsigned int *epoch, int ran
   if (threadIdx.x == 0) *epoch = e;
 }
 
+// watchdog of every cross-GPU wait: 60 s by default, GCRL_P2P_TIMEOUT_MS overrides (tests, debugging)
+long long p2p_timeout_cycles() {
+  static long long cyc = 0;
+  if (cyc == 0) {
+    const char *e = getenv("GCRL_P2P_TIMEOUT_MS");
+    const double ms = e ? atof(e) : 60000.0;
+    cyc = (long long)(ms * 2.0e6);        // ~2 GHz SM clock
+  }
+  return cyc;
+}
+
 void launch_p2p_barrier(unsigned int *const *peer_flags, unsigned int *epoch, int rank, int world, int *err,
                         cudaStream_t st) {
-  p2p_barrier_kernel<<<1, 32, 0, st>>>(peer_flags, epoch, rank, world, err);
+  p2p_barrier_kernel<<<1, 32, 0, st>>>(peer_flags, epoch, rank, world, err, p2p_timeout_cycles());
   GCRL_LAUNCHED();
 }
 
@@ -126,8 +140,9 @@ struct P2PReduceArgs {
   const float *const *peers;            // [world] flat gradient of this network on every rank
   unsigned int *const *peer_flags;      // [world] flag arrays (8 words each)
   const float *const *peer_outbox;      // [world] metric outboxes (2 x 8 floats each)
-  unsigned int *epoch, *ticket;
+  unsigned int *epoch, *ticket, *go;
   int *err;
+  long long timeout_cycles;
   int rank, world, n;
   float inv_world;
   float *out, *sumsq_partials;
@@ -156,20 +171,41 @@ __global__ void __launch_bounds__(kOptThreads) p2p_reduce_kernel(const __grid_co
       *dst = e;
     }
   }
-  if (tid < a.world && !(a.debug & 1)) {
-    // acquire loads at system scope: what the peer wrote before raising its flag is visible to the loads below
-    const unsigned int *src = a.peer_flags[a.rank] + tid;
-    const long long t0 = clock64();
-    unsigned int seen;
-    do {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(src) : "memory");
-      if (seen < e && clock64() - t0 > 120000000000ll) {       // ~60 s: a peer died; fail loudly instead of hanging
-        *a.err = 1;
-        break;
+  // Only ONE warp of the grid polls the flag words the peers write over NVLink (system-scope acquire loads, with
+  // back-off); the other CTAs wait on a local "go" word that CTA 0 releases at GPU scope.  (Every CTA polling
+  // the NVLink-written line itself -- 8 x 135 spinning threads at 8 ranks -- starved the incoming writes: the
+  // 8-GPU run of this round hung in exactly that variant, 2 and 4 GPUs did not.)
+  if (!(a.debug & 1)) {
+    if (blockIdx.x == 0) {
+      if (tid < a.world) {
+        const unsigned int *src = a.peer_flags[a.rank] + tid;
+        const long long t0 = clock64();
+        unsigned int seen;
+        for (;;) {
+          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(src) : "memory");
+          if (seen >= e) break;
+          if (clock64() - t0 > a.timeout_cycles) {             // a peer died: fail loudly instead of hanging
+            atomicExch(a.err, 1 + tid + 16 * a.rank);
+            break;
+          }
+          __nanosleep(40);
+        }
       }
-    } while (seen < e);
+      __syncthreads();
+      if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.go), "r"(e) : "memory");
+    } else {
+      if (tid == 0) {
+        const long long t0 = clock64();
+        unsigned int seen;
+        for (;;) {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.go) : "memory");
+          if (seen >= e || clock64() - t0 > 2 * a.timeout_cycles) break;
+          __nanosleep(20);
+        }
+      }
+      __syncthreads();
+    }
   }
-  __syncthreads();
   float sq = 0.f;
   const int n4 = a.n >> 2;                                     // flat buffers are 16-byte granular
   for (int q = blockIdx.x * blockDim.x + tid; q < n4; q += gridDim.x * blockDim.x) {
@@ -207,7 +243,8 @@ int p2p_reduce_grid(int n) { return std::max(1, std::min(((n >> 2) + kOptThreads
 void launch_p2p_reduce(const P2PReduceHost &h, cudaStream_t st) {
   P2PReduceArgs a{};
   a.peers = h.peers; a.peer_flags = h.peer_flags; a.peer_outbox = h.peer_outbox;
-  a.epoch = h.epoch; a.ticket = h.ticket; a.err = h.err;
+  a.epoch = h.epoch; a.ticket = h.ticket; a.go = h.go; a.err = h.err;
+  a.timeout_cycles = p2p_timeout_cycles();
   a.rank = h.rank; a.world = h.world; a.n = h.n; a.inv_world = 1.0f / float(h.world);
   a.out = h.out; a.sumsq_partials = h.sumsq_partials;
   a.local_metrics = h.local_metrics; a.outbox = h.outbox; a.metrics_avg = h.metrics_avg; a.metric_mask = h.metric_mask;
