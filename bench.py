@@ -159,11 +159,87 @@ def cpu_arm(args, steps, warmup, seconds=None):
                 updates_per_s=n / dt, ms_per_step=dt / n * 1e3, steps=n)
 
 
+def reference_arm(args, steps, warmup, seconds=None):
+    """The UNMODIFIED reference (oracle/_ref/src/{buffer,agent,model,utils}.py, vendored by oracle/make_ref.py in
+    the build container): its own HERBuffer -- filled through its own push() / apply_her() up to its own cap of
+    max_len = 1M entries -- and its own DDPG.update(step) = HERBuffer.sample(B) + critic_update + actor_update
+    (src/agent.py:1378-1404), on the host's cores with torch's default thread count.  Returns None when
+    oracle/_ref is absent (a checkout that never ran build() next to the reference)."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isfile(os.path.join(ref_dir, "src", "agent.py")):
+        return None
+    sys.path.insert(0, ref_dir)
+    import torch
+    import src.agent as ref_agent      # noqa: E402  (the vendored reference)
+    import src.utils as ref_utils      # noqa: E402
+    torch.manual_seed(1898)
+    random.seed(1898)
+    T, k, O, G, A, B = 50, args.k_future, args.obs, args.goal, args.act, args.batch
+    D = O + G
+    max_len = 1_000_000
+    cfg = ref_utils.BaseAgentConfig(
+        hidden_dim=args.hidden, layer_count=args.layers, actor_lr=1e-3, actor_lr_min=1e-3, ac_scheduler_steps=1,
+        critic_lr=1e-3, critic_lr_min=1e-3, cr_scheduler_steps=1, buffer_type="HER", max_len=max_len, alpha=1.0,
+        batch_size=B, gamma=0.98, ac_update_freq=1, noise_std=0.2, noise_clamp=0.5, policy_noise=0.0, grad_clip=10.0,
+        beta=1.0, beta_end=1, k_future=k, max_eps_len=50, tau=0.05)
+    ag = ref_agent.DDPG(obs_dim=D, ac_dim=A, config=cfg, weights=None, nenvs=1, gradient_step=40)
+    # panda-gym's sparse reward (un-vendored dependency; the published rule, as in tests/golden/make_golden.py)
+    ag.buffer.compute_reward = lambda a, b, info: -np.array(np.linalg.norm(a - b, axis=-1) > 0.05, dtype=np.float32)
+    rng = np.random.default_rng(0)
+    per_ep = (T - 1) * (k + 1) + 1
+    E = max_len // per_ep + 1
+    data = synth(rng, E, T, O, G, A, k)
+    t0 = time.time()
+    for e in range(E):                      # the reference's own ingest path, transition by transition
+        s_t, ns_t = torch.from_numpy(data["s"][e]), torch.from_numpy(data["ns"][e])
+        for t in range(T):
+            ag.buffer.push(0, s_t[t], data["a"][e][t], ns_t[t], np.float64(data["r"][e][t]), bool(t == T - 1 and False),
+                           data["s"][e][t][-G:], data["ag"][e][t])
+    fill_s = time.time() - t0
+    # torch's intra-op thread count: its default (all cores) is often SLOWER than a few threads on these small
+    # GEMMs, so the baseline gets the best of {default, 8, 4, 1} -- measured here, two updates each
+    best, cores = None, torch.get_num_threads()
+    for nt in sorted({torch.get_num_threads(), 8, 4, 1}, reverse=True):
+        if nt > (os.cpu_count() or 1):
+            continue
+        torch.set_num_threads(nt)
+        ag.update(1)
+        t0 = time.perf_counter()
+        ag.update(2)
+        ag.update(3)
+        dt = (time.perf_counter() - t0) / 2
+        if best is None or dt < best:
+            best, cores = dt, nt
+    torch.set_num_threads(cores)
+    log(f"[reference] HERBuffer of {len(ag.buffer)} entries filled through push()/apply_her() in {fill_s:.1f}s "
+        f"({len(ag.buffer) / fill_s:.0f} entries/s); torch threads {cores} (fastest of the candidates)")
+    for i in range(warmup):
+        ag.update(i + 1)
+    n, t0 = 0, time.perf_counter()
+    while n < steps:
+        ag.update(warmup + n + 1)
+        n += 1
+        if seconds is not None and time.perf_counter() - t0 > seconds:
+            break
+    dt = time.perf_counter() - t0
+    return dict(value=n * B / dt, unit=UNIT, cores=cores, kind="reference",
+                sample=f"{n} calls of the unmodified reference DDPG.update(step) (src/agent.py:1378-1404: "
+                       f"HERBuffer.sample({B}) over a {len(ag.buffer)}-entry deque + critic and actor updates, H={args.hidden}, "
+                       f"L={args.layers}), {dt:.1f}s; the buffer was filled by the reference's own push()/apply_her() at "
+                       f"{len(ag.buffer) / fill_s:.0f} entries/s",
+                updates_per_s=n / dt, ms_per_step=dt / n * 1e3, steps=n, ingest_entries_per_s=len(ag.buffer) / fill_s)
+
+
 def reference_main(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res = cpu_arm(args, args.steps, args.warmup, seconds=120.0)
+    res = reference_arm(args, args.steps, min(args.warmup, 3), seconds=90.0)
+    port = None
+    if res is None:                      # no vendored reference in this checkout: the NumPy port stands in
+        res = cpu_arm(args, args.steps, args.warmup, seconds=120.0)
+    elif not args.no_cpu:
+        port = cpu_arm(args, 10 ** 9, 2, seconds=10.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": res["steps"], "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
@@ -173,6 +249,8 @@ def reference_main(args):
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if port is not None:
+        line["cpu_port"] = {k: port[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
 
 
@@ -906,7 +984,13 @@ def gpu_main(args):
             log(f"[roofline] normaliser timing skipped: {e}")
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_arm(args, 10 ** 9, 2, seconds=args.cpu_seconds)
+        try:
+            cpu = reference_arm(args, 10 ** 9, 2, seconds=args.cpu_seconds)
+        except Exception as e:   # noqa: BLE001
+            log(f"[cpu] the vendored reference failed ({e!r}); timing the NumPy port instead")
+            cpu = None
+        if cpu is None:
+            cpu = cpu_arm(args, 10 ** 9, 2, seconds=args.cpu_seconds)
     variants = {}
     if rank == 0 and world == 1 and not args.no_sweep:
         variants = time_variants(args, data, E, max_len, dev, local)

@@ -54,6 +54,7 @@ struct HerGeom {
   int off_ns, off_a, off_r, off_d, off_ag, off_fut;
   FastDiv div_k1, div_D, div_A, div_rf4;
   uint64_t seed;
+  float threshold;          // sparse reward: -(||ag - g|| > threshold), 0.05 for the Panda tasks
 };
 
 struct __align__(16) CommitHdr {
@@ -263,7 +264,7 @@ her_sample_kernel(HerGeom g, int64_t B, const int64_t *__restrict__ idx, float *
       // -(d > 0.05) as float32: -1.0f, or -0.0f with the SIGN BIT SET on success
       // (-np.array(False, float32)).  Written as an INTEGER word: with a float-typed select
       // nvcc 12.9 rewrites {-1.0f, -0.0f} into int->float(-(int)pred), which yields +0.0f.
-      reinterpret_cast<uint32_t *>(row)[g.off_r] = 0x80000000u | ((dist > 0.05f) ? 0x3F800000u : 0u);
+      reinterpret_cast<uint32_t *>(row)[g.off_r] = 0x80000000u | ((dist > g.threshold) ? 0x3F800000u : 0u);
       row[g.off_d] = 0.0f;                                      // new_done = False
     }
   }
@@ -413,6 +414,7 @@ int gcrl_her_create(gcrl_her **out, int device, int64_t max_entries, int64_t cap
     g.div_A = FastDiv(uint32_t(act_dim));
     g.div_rf4 = FastDiv(uint32_t(g.row_f / 4));
     g.seed = seed;
+    g.threshold = 0.05f;
     h->smem_bytes = size_t(kSamplesPerBlock) * g.row_f * 4 + 3 * kSamplesPerBlock * 4;
     GCRL_REQUIRE(h->smem_bytes <= 227 * 1024, "transition row too wide for the sampler tile");
     g.rows = dev_alloc<float>(size_t(h->cap_tr) * g.row_f);
@@ -542,6 +544,14 @@ int gcrl_her_push_episode(gcrl_her *h, int T, const float *s, const float *a, co
   h->total_entries = new_total;
   h->total_tr += T;
   h->next_eid += 1;
+  GCRL_API_END
+}
+
+int gcrl_her_set_threshold(gcrl_her *h, float threshold) {
+  GCRL_API_BEGIN
+  GCRL_REQUIRE(h != nullptr, "handle is NULL");
+  GCRL_REQUIRE(threshold >= 0.f, "the distance threshold must be >= 0");
+  h->g.threshold = threshold;
   GCRL_API_END
 }
 

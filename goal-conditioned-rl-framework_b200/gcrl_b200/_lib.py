@@ -51,6 +51,7 @@ SIGNATURES = {
     "gcrl_her_create": (C.c_int, [pp, C.c_int, c_i64, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, c_u64]),
     "gcrl_her_destroy": (C.c_int, [vp]),
     "gcrl_her_push_episode": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "gcrl_her_set_threshold": (C.c_int, [vp, C.c_float]),
     "gcrl_her_len": (c_i64, [vp]),
     "gcrl_her_total_entries": (c_i64, [vp]),
     "gcrl_her_live_transitions": (c_i64, [vp]),
@@ -154,7 +155,7 @@ def _load():
         fn = getattr(dll, name)          # AttributeError if the library lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if dll.gcrl_abi_version() != 3:
+    if dll.gcrl_abi_version() != 4:
         raise ImportError("libgcrl_b200.so ABI version mismatch")
     return dll
 

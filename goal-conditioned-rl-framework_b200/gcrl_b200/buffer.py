@@ -31,8 +31,11 @@ class HERBuffer:
                   ``random.sample(range(len), B)``: the reference's exact Mersenne-Twister
                   stream (src/buffer.py:124,153), bit-identical batches.
       "device" -- both are drawn on the GPU (no per-call host work).
-    ``compute_reward`` is accepted for interface compatibility (src/env.py:105 assigns
-    it); relabelled rewards always use the sparse Panda rule -(||ag - g|| > 0.05).
+    ``compute_reward`` (src/env.py:105 assigns the env's function): relabelled rewards are computed on the
+    GPU with the sparse Panda rule -(||ag - g||_2 > threshold) as float32.  An assigned callable is therefore
+    PROBED on known-answer points around the threshold (as soon as the goal width is known) and must agree
+    with that rule exactly; any other reward function raises ``ValueError`` instead of silently training on
+    different rewards.  ``threshold`` (default 0.05, src/buffer.py:93) is passed to the kernel.
     """
 
     def __init__(self, max_mem_len, max_eps_len, nenvs, threshold=0.05, k_future=4, *,
@@ -40,13 +43,18 @@ class HERBuffer:
         _lib.require_cuda()
         if index_source not in ("host", "device"):
             raise ValueError(f"index_source must be 'host' or 'device', got {index_source!r}")
+        if not 1 <= int(max_eps_len) <= 255:
+            raise ValueError(f"max_eps_len must be in [1, 255] (future offsets are stored as uint8), got {max_eps_len}")
+        if float(threshold) < 0:
+            raise ValueError(f"threshold must be >= 0, got {threshold}")
         self.max_mem_len = int(max_mem_len)
         self.episodes = [deque(maxlen=max_eps_len) for _ in range(nenvs)]
         self.device_index = int(device)
         self.device = f"cuda:{self.device_index}"
         self.threshold = threshold
         self.k_future = int(k_future)
-        self.compute_reward = None
+        self._compute_reward = None
+        self._reward_checked = True
         self.obs_normalizer = None
         self.dg_normalizer = None
         self.index_source = index_source
@@ -60,6 +68,41 @@ class HERBuffer:
             lib.gcrl_her_destroy(self._h)
             self._h = None
 
+    # -- the injected reward function (src/env.py:105, called at src/buffer.py:166) --------------
+    @property
+    def compute_reward(self):
+        return self._compute_reward
+
+    @compute_reward.setter
+    def compute_reward(self, fn):
+        self._compute_reward = fn
+        self._reward_checked = fn is None
+        if fn is not None and self._dims is not None:
+            self._check_reward(self._dims[2])
+
+    def _check_reward(self, G):
+        """The kernel relabels with -(||a - b||_2 > threshold) as float32 (csrc/her.cu, phase 3).  Probe the
+        assigned callable on points whose distance is 0, well inside, exactly at and one float32 step either side
+        of the threshold, and well outside; it must return that rule's values (0 / -1)."""
+        thr = np.float32(self.threshold)
+        dists = np.array([0.0, 0.5 * thr, np.nextafter(thr, np.float32(0)), thr, np.nextafter(thr, np.float32(1)),
+                          2.0 * thr + 0.1], np.float32)
+        a = np.zeros((len(dists), G), np.float32)
+        b = np.zeros((len(dists), G), np.float32)
+        b[:, 0] = dists                      # ||a - b|| is exactly dists[i] (one non-zero coordinate)
+        want = -(dists > thr).astype(np.float32)
+        try:
+            got = np.stack([np.asarray(self._compute_reward(a[i], b[i], {}), np.float32).reshape(()) for i in range(len(dists))])
+        except Exception as e:   # noqa: BLE001
+            raise ValueError(f"compute_reward could not be evaluated on [{G}]-vectors: {e!r}") from e
+        if not np.array_equal(got, want):
+            raise ValueError(
+                "HERBuffer.compute_reward is not the sparse rule -(||achieved - goal||_2 > threshold) "
+                f"(threshold {float(thr)}): on distances {dists.tolist()} it returned {got.tolist()}, the GPU "
+                f"relabel computes {want.tolist()}.  Only that reward is relabelled on the device; pass the matching "
+                "`threshold` to HERBuffer, or use a sparse-reward task.")
+        self._reward_checked = True
+
     # -- handle ---------------------------------------------------------------------------
     def _ensure(self, D, A, G):
         if self._h is None:
@@ -67,8 +110,11 @@ class HERBuffer:
             check(lib.gcrl_her_create(C.byref(h), self.device_index, self.max_mem_len,
                                       self.cap_transitions, D, G, A, self.k_future, self.seed))
             self._h, self._dims = h, (D, A, G)
+            check(lib.gcrl_her_set_threshold(h, float(self.threshold)))
         elif self._dims != (D, A, G):
             raise ValueError(f"transition shape changed: {self._dims} -> {(D, A, G)}")
+        if not self._reward_checked:
+            self._check_reward(G)
 
     @property
     def handle(self):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GCRL_ABI_VERSION 3
+#define GCRL_ABI_VERSION 4
 
 #define GCRL_OK 0
 #define GCRL_ERR_INVALID 1      /* bad argument / shape                                  */
@@ -71,6 +71,10 @@ int gcrl_her_push_episode(gcrl_her *h, int T, const float *s, const float *a, co
                           const float *r, const float *d, const float *ag, const uint8_t *fut,
                           void *stream);
 
+/* Distance threshold of the sparse relabel reward -(||achieved - goal||_2 > threshold) (HERBuffer's `threshold`
+ * constructor argument, src/buffer.py:93; panda-gym's tasks use 0.05, the default).  Takes effect for the
+ * following samples. */
+int gcrl_her_set_threshold(gcrl_her *h, float threshold);
 int64_t gcrl_her_len(const gcrl_her *h);            /* __len__, src/buffer.py:137-138   */
 int64_t gcrl_her_total_entries(const gcrl_her *h);  /* entries ever appended            */
 int64_t gcrl_her_live_transitions(const gcrl_her *h);

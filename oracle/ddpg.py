@@ -203,6 +203,12 @@ class DDPGOracle:
         self.ac_update_freq = ac_update_freq
         self.flip_delta = 0.0            # > 0: actor_update also evaluates _actor_flip_slack
         self.last_actor_flip_slack = 0.0
+        # per-ELEMENT allowance for the actor's weights that the near-zero pre-activations seen so far can
+        # explain (test tolerance, not reference behaviour; see _flip_track): [[W, b], ...] like the actor
+        self.flip_allowance = zeros_like_params([[np.asarray(w, np.float64), np.asarray(b, np.float64)] for w, b in actor])
+        self._flip_dm = zeros_like_params(self.flip_allowance)
+        self._flip_dv = zeros_like_params(self.flip_allowance)
+        self._last_flip_abs = None
 
     # src/agent.py:1302-1343
     def critic_update(self, s, a, r, ns, d, weights=None):
@@ -247,8 +253,12 @@ class DDPGOracle:
         grads, _ = mlp_backward(self.actor, a_acts, d_a, final_tanh=True)
         if self.flip_delta:
             self.last_actor_flip_slack = self._actor_flip_slack(s, a_acts, c_acts, dq, grads)
+        pre_norm = grad_norm_python(grads)
         if self.grad_clip is not None:
             clip_grad_norm_(grads, self.grad_clip)
+        if self.flip_delta:
+            coef = 1.0 if self.grad_clip is None else min(1.0, self.grad_clip / (pre_norm + 1e-6))
+            self._flip_track(grads, coef, self.actor_sched.lr)
         self.actor_opt.step(self.actor, grads, self.actor_sched.lr)
         self.actor_sched.step()
         self.last_actor_grads = grads
@@ -267,6 +277,8 @@ class DDPGOracle:
         base = grad_norm_python(grads)
         slack = 0.0
         D = s.shape[1]
+        flip_abs = zeros_like_params([[np.asarray(w, np.float64), np.asarray(b, np.float64)] for w, b in grads])
+        self._last_flip_abs = flip_abs
 
         def row_grads(a_row, c_row, r_):
             _, d_in = mlp_backward(self.critic, c_row, dq[r_:r_ + 1], final_tanh=False, need_input_grad=True)
@@ -288,7 +300,44 @@ class DDPGOracle:
                     g2 = [[w + (nw - ow), b + (nb - ob)]
                           for (w, b), (nw, nb), (ow, ob) in zip(grads, g_new, g_old)]
                     slack += abs(grad_norm_python(g2) - base)
+                    for fa, gn, go in zip(flip_abs, g_new, g_old):
+                        fa[0] += np.abs(np.asarray(gn[0], np.float64) - go[0])
+                        fa[1] += np.abs(np.asarray(gn[1], np.float64) - go[1])
         return slack / max(base, 1e-30)
+
+    def _flip_track(self, grads, coef, lr):
+        """Per-element bound on how far the actor's weights may legitimately differ from this oracle's because of
+        the near-zero hidden pre-activations seen so far (test tolerance, not reference behaviour).
+
+        A pre-activation that is zero to fp32 rounding takes LeakyReLU slope 1 or 0.01 depending on the summation
+        order, which changes ONE batch row's contribution to the gradient: element e of the (clipped) gradient
+        moves by at most d_e = coef (sum over such units of |g_row_new - g_row_old|_e) + |g_e| slack, where slack
+        bounds the change of the clip coefficient.  Adam carries the perturbation in both moments,
+            dm <- b1 dm + (1 - b1) d,      dv <- b2 dv + (1 - b2) (2 |g| d + d^2),
+        and the step lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps) is monotone in m and in v separately, so its extreme
+        values over the box [m +- dm] x [v +- dv] are at the corners.  The allowance accumulates the largest corner
+        deviation of every step, capped at Adam's hard bound 2 lr.  Elements that no flipped row touches get 0."""
+        opt = self.actor_opt
+        t = opt.t + 1
+        bc1, bc2s = 1.0 - opt.b1 ** t, (1.0 - opt.b2 ** t) ** 0.5
+        for i in range(len(grads)):
+            for j in range(2):
+                g = np.abs(np.asarray(grads[i][j], np.float64))
+                d = coef * self._last_flip_abs[i][j] + g * self.last_actor_flip_slack
+                dm, dv = self._flip_dm[i][j], self._flip_dv[i][j]
+                dm *= opt.b1
+                dm += (1.0 - opt.b1) * d
+                dv *= opt.b2
+                dv += (1.0 - opt.b2) * (2.0 * g * d + d * d)
+                # the moments this step will use
+                m = np.asarray(opt.m[i][j], np.float64) * opt.b1 + (1.0 - opt.b1) * np.asarray(grads[i][j], np.float64)
+                v = np.asarray(opt.v[i][j], np.float64) * opt.b2 + (1.0 - opt.b2) * g * g
+                nom = m / (np.sqrt(v) / bc2s + opt.eps)
+                dev = np.zeros_like(nom)
+                for mm in (m - dm, m + dm):
+                    for vv in (np.maximum(v - dv, 0.0), v + dv):
+                        dev = np.maximum(dev, np.abs(mm / (np.sqrt(vv) / bc2s + opt.eps) - nom))
+                self.flip_allowance[i][j] += np.minimum(2.0 * lr, (lr / bc1) * dev)
 
     # src/agent.py:1255-1271
     def soft_update(self, tau):

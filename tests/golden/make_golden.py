@@ -208,7 +208,9 @@ def flat_params(module):
 
 def ddpg_case(agent_mod, utils_mod, name, *, D, A, H, L, B, steps, seed, gamma=0.98,
               tau=0.05, grad_clip=10.0, actor_lr=1e-3, critic_lr=1e-3, actor_lr_min=None,
-              critic_lr_min=None, ac_T=1, cr_T=1, ac_update_freq=1, store_weights=True):
+              critic_lr_min=None, ac_T=1, cr_T=1, ac_update_freq=1, store_weights=True, store_batches=True):
+    """store_batches=False (the large-batch cases): the batches are NOT written to the fixture; the test
+    regenerates them from `seed` with the same NumPy generator calls, in the same order, as below."""
     import torch
     sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
     from oracle import ddpg as O  # only for the seeded weight initialiser
@@ -248,8 +250,11 @@ def ddpg_case(agent_mod, utils_mod, name, *, D, A, H, L, B, steps, seed, gamma=0
         batch = tuple(torch.from_numpy(x) for x in (s, a, r, ns, d))
         ag.buffer.sample = lambda bs, _b=batch: _b                   # feed explicit batch
         info = ag.update(step)
-        out[f"s{si}_batch_s"], out[f"s{si}_batch_a"], out[f"s{si}_batch_r"] = s, a, r
-        out[f"s{si}_batch_ns"], out[f"s{si}_batch_d"] = ns, d
+        if store_batches:
+            out[f"s{si}_batch_s"], out[f"s{si}_batch_a"], out[f"s{si}_batch_r"] = s, a, r
+            out[f"s{si}_batch_ns"], out[f"s{si}_batch_d"] = ns, d
+        else:                                   # a checksum pins the regenerated stream
+            out[f"s{si}_batch_sum"] = np.array([x.astype(np.float64).sum() for x in (s, a, r, ns, d)])
         out[f"s{si}_info"] = np.array([float(x) for x in info], np.float64)
         out[f"s{si}_lr"] = np.array([ag.critic_opt.param_groups[0]["lr"],
                                      ag.actor_opt.param_groups[0]["lr"]], np.float64)
@@ -263,7 +268,7 @@ def ddpg_case(agent_mod, utils_mod, name, *, D, A, H, L, B, steps, seed, gamma=0
 
 
 def td3_case(agent_mod, utils_mod, name, *, D, A, H, L, B, steps, seed, gamma=0.98, tau=0.05,
-             grad_clip=1.0, lr=1e-3, policy_noise=0.2, noise_clamp=0.5, ac_update_freq=2):
+             grad_clip=1.0, lr=1e-3, policy_noise=0.2, noise_clamp=0.5, ac_update_freq=2, store_batches=True):
     """Unmodified reference TD3Agent.update on explicit batches; every torch.randn_like draw of
     the target-policy smoothing (src/agent.py:175) is recorded."""
     import torch
@@ -314,8 +319,11 @@ def td3_case(agent_mod, utils_mod, name, *, D, A, H, L, B, steps, seed, gamma=0.
         finally:
             agent_mod.torch.randn_like = real_randn_like
         assert len(drawn) == 1
-        for key, val in zip(("s", "a", "r", "ns", "d"), (s, a, r, ns, d)):
-            out[f"s{si}_batch_{key}"] = val
+        if store_batches:
+            for key, val in zip(("s", "a", "r", "ns", "d"), (s, a, r, ns, d)):
+                out[f"s{si}_batch_{key}"] = val
+        else:
+            out[f"s{si}_batch_sum"] = np.array([x.astype(np.float64).sum() for x in (s, a, r, ns, d)])
         out[f"s{si}_noise"] = drawn[0]
         out[f"s{si}_info"] = np.array([float(x) for x in info], np.float64)
         if si == len(steps) - 1:
@@ -633,12 +641,26 @@ def sac_cases(agent_mod, utils_mod):
              seed=34, grad_clip=0.5, tau=0.005, alpha_min_steps=0, alpha_lr=1e-2)
 
 
+def large_batch_cases(agent_mod, utils_mod):
+    """Large-batch updates on the PickAndPlace shape (time-feature obs 20 + goal 3 = 23, act 4, H 256 x 3, k 8:
+    src/config/DDPG/config_ddpg_pickplace.yaml:14-45) -- the batch sizes the tensor-core engine serves
+    (>= 2048).  Batches are regenerated from the seed by the tests; weights are stored for the last step."""
+    ddpg_case(agent_mod, utils_mod, "pickplace_B2048", D=23, A=4, H=256, L=3, B=2048,
+              steps=[39, 40, 41], seed=31, store_weights=False, store_batches=False)
+    ddpg_case(agent_mod, utils_mod, "pickplace_B8192", D=23, A=4, H=256, L=3, B=8192,
+              steps=[40, 41, 42], seed=32, store_weights=False, store_batches=False)
+    td3_case(agent_mod, utils_mod, "pickplace_B4096", D=23, A=4, H=256, L=3, B=4096, steps=[1, 2, 3], seed=33,
+             ac_update_freq=2, store_batches=False)
+
+
 def main():
     agent_mod, buffer_mod, model_mod, utils_mod = import_reference()
     if len(sys.argv) > 1 and sys.argv[1] == "sac":
         return sac_cases(agent_mod, utils_mod)
     if len(sys.argv) > 1 and sys.argv[1] == "per":
         return per_cases(agent_mod, utils_mod)
+    if len(sys.argv) > 1 and sys.argv[1] == "large":
+        return large_batch_cases(agent_mod, utils_mod)
     td3_case(agent_mod, utils_mod, "push_h64", D=22, A=3, H=64, L=3, B=128, steps=[1, 2, 3, 4, 5], seed=21)
     td3_case(agent_mod, utils_mod, "pickplace_h256", D=23, A=4, H=256, L=2, B=200, steps=[7, 8, 9], seed=22,
              grad_clip=0.1, ac_update_freq=1, tau=0.005, policy_noise=0.3, noise_clamp=0.25)
@@ -668,6 +690,7 @@ def main():
     checkpoint_case(model_mod)
     sac_cases(agent_mod, utils_mod)
     per_cases(agent_mod, utils_mod)
+    large_batch_cases(agent_mod, utils_mod)
 
 
 if __name__ == "__main__":

@@ -283,3 +283,45 @@ def test_buffer_and_agent_resume_from_checkpoint_sample_the_same_batches(tmp_pat
     assert ref[0] == got[0] and ref[1] == got[1]
     for x, y in zip(ref[2], got[2]):
         assert_bits(x, y, "resumed buffer dump")
+
+
+@pytest.mark.parametrize("threshold", [0.05, 0.02, 0.11])
+def test_threshold_and_injected_reward_are_honoured(threshold):
+    """HERBuffer(threshold=...) reaches the kernel (relabelled rewards follow -(d > threshold), bit for bit), a
+    compute_reward that IS that rule is accepted, anything else is rejected at the first commit."""
+    from gcrl_b200 import HERBuffer
+    rng = np.random.default_rng(11)
+    O, G, A, k, T, E = 7, 3, 3, 4, 50, 6
+    s, a, ns, r, d, ag = synth(rng, E, T, O, G, A)
+    fut = np.zeros((E, T, k), np.uint8)
+    for t in range(T - 1):
+        fut[:, t] = rng.integers(t + 1, T, (E, k))
+    thr32 = np.float32(threshold)
+
+    def rule(x, y, info=None):                           # the oracle's arithmetic with this threshold
+        diff = np.asarray(x, np.float32) - np.asarray(y, np.float32)
+        sq = diff * diff
+        acc = sq[..., 0]
+        for c in range(1, sq.shape[-1]):
+            acc = acc + sq[..., c]
+        return -(np.sqrt(acc) > thr32).astype(np.float32)
+
+    buf = HERBuffer(100_000, 50, 1, threshold=threshold, k_future=k)
+    buf.compute_reward = rule                            # assigned before the first transition, like src/env.py:105
+    for e in range(E):
+        buf.push_episode(s[e], a[e], ns[e], r[e], d[e], ag[e], fut[e])
+    per = (T - 1) * (k + 1) + 1
+    idx = np.arange(E * per)
+    S, Aa, R, NS, Dn = buf.sample_host(len(idx), indices=idx)
+    ep, o = idx // per, idx % per
+    t = np.minimum(o // (k + 1), T - 1)
+    j = np.where(o < (T - 1) * (k + 1), o % (k + 1), 0)
+    rel = j > 0
+    f = fut[ep[rel], t[rel], j[rel] - 1].astype(np.int64)
+    want = rule(ag[ep[rel], t[rel]], ag[ep[rel], f])
+    assert_bits(R[rel, 0], want, "relabel reward at this threshold")
+    assert 0 < np.count_nonzero(want) < want.size        # both outcomes occur, so the threshold matters
+    bad = HERBuffer(100_000, 50, 1, threshold=threshold, k_future=k)
+    bad.compute_reward = lambda x, y, info: -np.float32(np.linalg.norm(x - y))      # dense reward
+    with pytest.raises(ValueError, match="compute_reward"):
+        bad.push_episode(s[0], a[0], ns[0], r[0], d[0], ag[0], fut[0])

@@ -6,7 +6,8 @@ import pytest
 
 from oracle import ddpg as OD
 from oracle import her as OH
-from tests.helpers import (DDPG_CASES, HER_CASES, bits, ddpg_params_from_golden, her_episodes,
+from tests.helpers import (DDPG_LARGE_CASES, TD3_LARGE_CASES, golden_update_inputs, weight_error_report,
+                           DDPG_CASES, HER_CASES, bits, ddpg_params_from_golden, her_episodes,
                            load, weights_close)
 
 RTOL = 1e-5
@@ -134,6 +135,27 @@ def test_ddpg_oracle_matches_reference(case):
                     assert weights_close(b, rb, lr, si + 1), (si, tag)
 
 
+@pytest.mark.parametrize("case", DDPG_LARGE_CASES)
+def test_ddpg_oracle_matches_reference_large_batch(case):
+    """Batches of 2048 / 8192 on the PickAndPlace shape (regenerated from the seed): the oracle against the
+    unmodified reference's metrics (every step) and weights (last step).  fp32 batch means over B terms: BLAS
+    and NumPy sum in different orders, the metric tolerance grows like sqrt(B / 256)."""
+    g = load("ddpg_" + case)
+    orc, _ = make_ddpg_oracle(g)
+    _, batches = golden_update_inputs(g)
+    B = int(g["meta"][4])
+    rtol = 2e-5 * max(1.0, (B / 256.0) ** 0.5)
+    n = len(g["steps"])
+    for si, step in enumerate(g["steps"]):
+        info = orc.update_on_batch(int(step), *batches[si])
+        np.testing.assert_allclose(np.array(info), g[f"s{si}_info"], rtol=rtol, atol=1e-6)
+    lr = max(float(g["hp"][3]), float(g["hp"][4]))
+    for tag, params in (("actor", orc.actor), ("critic", orc.critic), ("target_actor", orc.target_actor),
+                        ("target_critic", orc.target_critic)):
+        for (w, b), (rw, rb) in zip(params, ddpg_params_from_golden(g, n - 1, tag)):
+            assert weights_close(w, rw, lr, n) and weights_close(b, rb, lr, n), (tag, weight_error_report(w, rw, lr, n))
+
+
 def test_checkpoint_forward_matches_reference():
     g = load("checkpoint_reach")
     actor = OD.state_dict_to_params({k[6:]: g[k] for k in g.files if k.startswith("actor.")},
@@ -160,17 +182,19 @@ def make_td3_oracle(g):
                         policy_noise=pn, noise_clamp=nc, ac_update_freq=freq), nets
 
 
-@pytest.mark.parametrize("case", TD3_CASES)
+@pytest.mark.parametrize("case", TD3_CASES + TD3_LARGE_CASES)
 def test_td3_oracle_matches_reference(case):
     g = load("td3_" + case)
     orc, _ = make_td3_oracle(g)
     lr = float(g["hp"][3])
     n = len(g["steps"])
+    _, batches = golden_update_inputs(g, n_critics=2)
+    rtol = 2e-5 * max(1.0, (int(g["meta"][4]) / 256.0) ** 0.5)
     for si, step in enumerate(g["steps"]):
-        info = orc.update_on_batch(int(step), *ddpg_batch(g, si), g[f"s{si}_noise"])
+        info = orc.update_on_batch(int(step), *batches[si], g[f"s{si}_noise"])
         ref = g[f"s{si}_info"]
         assert len(info) == len(ref)
-        np.testing.assert_allclose(np.array(info), ref, rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(np.array(info), ref, rtol=rtol, atol=1e-6)
     for tag in ("actor", "critic_1", "critic_2", "target_actor", "target_critic_1", "target_critic_2"):
         for (w, b), (rw, rb) in zip(getattr(orc, tag), ddpg_params_from_golden(g, n - 1, tag)):
             assert weights_close(w, rw, lr, n) and weights_close(b, rb, lr, n), tag

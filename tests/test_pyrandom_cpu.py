@@ -105,3 +105,39 @@ def test_predraw_from_a_state_does_not_touch_the_global_generator():
     # a stale tuple (neither the cached object nor equal to it) still converts correctly
     idx3, _ = _lib.py_sample_range_from(before, 5000, 64)
     assert list(idx3) == want
+
+
+def test_injected_compute_reward_is_probed_against_the_sparse_rule():
+    """HERBuffer.compute_reward (assigned by src/env.py:105) must BE the rule the GPU relabels with; anything
+    else is rejected instead of silently ignored (host logic only: no CUDA object behind the buffer)."""
+    import pytest
+    from gcrl_b200.buffer import HERBuffer
+    from oracle import her as OH
+
+    def panda(a, b, info, thr=0.05):                      # panda-gym's own NumPy calls
+        return -np.array(np.linalg.norm(a - b, axis=-1) > thr, dtype=np.float32)
+
+    buf = HERBuffer.__new__(HERBuffer)
+    buf._dims, buf.threshold = (21, 3, 3), 0.05
+    buf.compute_reward = panda                            # probed at assignment (the goal width is known)
+    assert buf._reward_checked
+    buf.compute_reward = OH.compute_reward
+    assert buf._reward_checked
+    buf.compute_reward = None
+    for bad in (lambda a, b, info: -np.float32(np.linalg.norm(a - b)),               # dense reward
+                lambda a, b, info: panda(a, b, info, thr=0.08),                      # other threshold
+                lambda a, b, info: -np.array(np.linalg.norm(a - b) >= np.float32(0.05), np.float32)):   # >= instead of >
+        with pytest.raises(ValueError, match="compute_reward"):
+            buf.compute_reward = bad
+    # the threshold the buffer was built with is the one the probe (and the kernel) uses
+    buf.compute_reward = None
+    buf.threshold = 0.08
+    buf.compute_reward = lambda a, b, info: panda(a, b, info, thr=0.08)
+    assert buf._reward_checked
+    # assigned before the first transition: checked lazily, as soon as the goal width is known
+    late = HERBuffer.__new__(HERBuffer)
+    late._dims, late.threshold = None, 0.05
+    late.compute_reward = lambda a, b, info: np.float32(0.0)
+    assert not late._reward_checked
+    with pytest.raises(ValueError, match="compute_reward"):
+        late._check_reward(3)
