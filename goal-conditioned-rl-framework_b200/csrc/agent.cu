@@ -112,6 +112,7 @@ constexpr int kMaxSplits = 128;
 }  // namespace
 
 struct gcrl_agent {
+  uint32_t magic = 0x544E4741u;   // handle type tag: the two agent families share the Python base class
   int device = 0;
   gcrl_agent_config cfg{};
   int D = 0, A = 0, H = 0, L = 0, ldh = 0, ldc = 0;
@@ -580,6 +581,25 @@ void write_scalars(gcrl_agent *ag, double lr_c, double lr_a, bool actor_steps, c
   ag->scal_stage.release(slot, st);
 }
 
+// The Adam step counters advance in write_scalars, before the update is enqueued.  If anything after that throws
+// (argument checks, a CUDA error, graph capture), the Python schedulers do not step either, so the counters are
+// restored -- otherwise every later bias correction would be off by one step.
+struct AdamStepGuard {
+  gcrl_agent *ag;
+  int t[NUM_NETS];
+  bool per_on; int dp_B, dp_flags;
+  bool done = false;
+  explicit AdamStepGuard(gcrl_agent *a) : ag(a), per_on(a->per_on), dp_B(a->dp_B), dp_flags(a->dp_flags) {
+    for (int i = 0; i < NUM_NETS; ++i) t[i] = a->net[i].adam_t;
+  }
+  void commit() { done = true; }
+  ~AdamStepGuard() {
+    if (done) return;
+    for (int i = 0; i < NUM_NETS; ++i) ag->net[i].adam_t = t[i];
+    ag->per_on = per_on; ag->dp_B = dp_B; ag->dp_flags = dp_flags;
+  }
+};
+
 // phase masks: bit0 critic grads, bit1 critic step, bit2 actor grads, bit3 actor step.
 // A single-GPU update runs all four back to back (mask 15); the data-parallel path runs them one
 // at a time with the caller's gradient all-reduce in between (steps then re-reduce).
@@ -708,6 +728,13 @@ void finish_metrics(gcrl_agent *ag, float *metrics_host, cudaStream_t st) {
 
 }  // namespace
 
+// Every entry point checks the handle's type tag: a gcrl_agent handle passed to the other family's functions would be
+// reinterpreted as a different struct (garbage shapes and pointers).
+static inline void require_handle(const gcrl_agent *h) {
+  if (h == nullptr) throw ::gcrl::Error(GCRL_ERR_INVALID, "handle is NULL");
+  if (h->magic != 0x544E4741u) throw ::gcrl::Error(GCRL_ERR_INVALID, "handle is not a DDPG / TD3 agent (gcrl_agent_create)");
+}
+
 extern "C" {
 
 int gcrl_agent_create(gcrl_agent **out, int device, const gcrl_agent_config *cfg) {
@@ -816,12 +843,13 @@ int gcrl_agent_destroy(gcrl_agent *ag) {
 }
 
 int gcrl_agent_num_layers(const gcrl_agent *ag, int net) {
-  if (ag == nullptr || net < 0 || net >= NUM_NETS || !ag->has[net]) return -1;
+  if (ag == nullptr || ag->magic != 0x544E4741u || net < 0 || net >= NUM_NETS || !ag->has[net]) return -1;
   return ag->net[net].layers;
 }
 
 int gcrl_agent_layer_shape(const gcrl_agent *ag, int net, int layer, int *out_dim, int *in_dim) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag && net >= 0 && net < NUM_NETS && ag->has[net], "bad network id");
   GCRL_REQUIRE(layer >= 0 && layer < ag->net[net].layers, "bad layer index");
   if (out_dim) *out_dim = ag->net[net].out_d[layer];
@@ -832,6 +860,7 @@ int gcrl_agent_layer_shape(const gcrl_agent *ag, int net, int layer, int *out_di
 int gcrl_agent_set_layer(gcrl_agent *ag, int net, int layer, const float *weight_host,
                          const float *bias_host, void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag && net >= 0 && net < NUM_NETS && ag->has[net], "bad network id");
   Net &n = ag->net[net];
   GCRL_REQUIRE(layer >= 0 && layer < n.layers && weight_host && bias_host, "bad layer / NULL data");
@@ -850,6 +879,7 @@ int gcrl_agent_set_layer(gcrl_agent *ag, int net, int layer, const float *weight
 int gcrl_agent_get_layer(gcrl_agent *ag, int net, int layer, float *weight_host, float *bias_host,
                          void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag && net >= 0 && net < NUM_NETS && ag->has[net], "bad network id");
   Net &n = ag->net[net];
   GCRL_REQUIRE(layer >= 0 && layer < n.layers, "bad layer index");
@@ -870,6 +900,7 @@ int gcrl_agent_get_layer(gcrl_agent *ag, int net, int layer, float *weight_host,
 static int adam_layer_io(gcrl_agent *ag, int net, int layer, float *m_w, float *m_b, float *v_w, float *v_b, int set,
                          void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag && net >= 0 && net < NUM_NETS && ag->has[net] && ag->net[net].m, "bad (or non-trainable) network id");
   Net &n = ag->net[net];
   GCRL_REQUIRE(layer >= 0 && layer < n.layers && m_w && m_b && v_w && v_b, "bad layer / NULL data");
@@ -907,12 +938,14 @@ int gcrl_agent_set_adam_layer(gcrl_agent *ag, int net, int layer, const float *m
 }
 int gcrl_agent_get_adam_step(gcrl_agent *ag, int net, int *step) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag && step && net >= 0 && net < NUM_NETS && ag->has[net] && ag->net[net].m, "bad network id");
   *step = ag->net[net].adam_t;
   GCRL_API_END
 }
 int gcrl_agent_set_adam_step(gcrl_agent *ag, int net, int step) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag && step >= 0 && net >= 0 && net < NUM_NETS && ag->has[net] && ag->net[net].m, "bad network id");
   ag->net[net].adam_t = step;
   GCRL_API_END
@@ -920,6 +953,7 @@ int gcrl_agent_set_adam_step(gcrl_agent *ag, int net, int step) {
 
 int gcrl_agent_hard_update(gcrl_agent *ag, void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag != nullptr, "agent handle is NULL");
   GCRL_CUDA(cudaSetDevice(ag->device));
   cudaStream_t st = as_stream(stream);
@@ -936,6 +970,7 @@ int gcrl_agent_hard_update(gcrl_agent *ag, void *stream) {
 
 int gcrl_agent_reset_optim(gcrl_agent *ag, void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag != nullptr, "agent handle is NULL");
   GCRL_CUDA(cudaSetDevice(ag->device));
   cudaStream_t st = as_stream(stream);
@@ -953,14 +988,17 @@ int gcrl_agent_update_batch(gcrl_agent *ag, int64_t B, const float *s_dev, const
                             const float *noise_dev, double lr_critic, double lr_actor, int flags,
                             float *metrics_host, void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   check_batch(ag, B);
   GCRL_CUDA(cudaSetDevice(ag->device));
   cudaStream_t st = as_stream(stream);
   const float *noise = nullptr;
+  AdamStepGuard guard(ag);
   ag->per_on = (flags & 8) != 0;
   ingest(ag, nullptr, B, nullptr, s_dev, a_dev, r_dev, ns_dev, d_dev, noise_dev, &noise, st);
   write_scalars(ag, lr_critic, lr_actor, (flags & 1) != 0, st);
   run_update(ag, int(B), noise, flags, PH_ALL, st);
+  guard.commit();
   finish_metrics(ag, metrics_host, st);
   GCRL_API_END
 }
@@ -969,21 +1007,25 @@ int gcrl_agent_update_from_buffer(gcrl_agent *ag, gcrl_her *buf, int64_t B, cons
                                   const float *noise_dev, double lr_critic, double lr_actor, int flags,
                                   float *metrics_host, void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   check_batch(ag, B);
   GCRL_REQUIRE(buf != nullptr, "buffer handle is NULL");
   GCRL_CUDA(cudaSetDevice(ag->device));
   cudaStream_t st = as_stream(stream);
   const float *noise = nullptr;
+  AdamStepGuard guard(ag);
   ag->per_on = (flags & 8) != 0;
   ingest(ag, buf, B, idx_host, nullptr, nullptr, nullptr, nullptr, nullptr, noise_dev, &noise, st);
   write_scalars(ag, lr_critic, lr_actor, (flags & 1) != 0, st);
   run_update(ag, int(B), noise, flags, PH_ALL, st);
+  guard.commit();
   finish_metrics(ag, metrics_host, st);
   GCRL_API_END
 }
 
 int gcrl_agent_read_metrics(gcrl_agent *ag, float *metrics_host, void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag != nullptr && metrics_host != nullptr, "NULL argument");
   GCRL_CUDA(cudaSetDevice(ag->device));
   finish_metrics(ag, metrics_host, as_stream(stream));
@@ -992,6 +1034,7 @@ int gcrl_agent_read_metrics(gcrl_agent *ag, float *metrics_host, void *stream) {
 
 int gcrl_agent_act(gcrl_agent *ag, int64_t n, const float *obs_host, float *act_host, void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   check_batch(ag, n);
   GCRL_REQUIRE(obs_host && act_host, "NULL argument");
   GCRL_CUDA(cudaSetDevice(ag->device));
@@ -1014,6 +1057,7 @@ int gcrl_agent_act(gcrl_agent *ag, int64_t n, const float *obs_host, float *act_
 int gcrl_agent_q(gcrl_agent *ag, int64_t n, const float *obs_host, const float *act_host, float *q_host,
                  void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   check_batch(ag, n);
   GCRL_REQUIRE(obs_host && act_host && q_host, "NULL argument");
   GCRL_CUDA(cudaSetDevice(ag->device));
@@ -1034,6 +1078,7 @@ int gcrl_agent_q(gcrl_agent *ag, int64_t n, const float *obs_host, const float *
 
 int gcrl_agent_per_buffers(gcrl_agent *ag, float **weights_dev, float **td_dev) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag != nullptr && weights_dev != nullptr && td_dev != nullptr, "NULL argument");
   *weights_dev = ag->per_w;
   *td_dev = ag->per_td;
@@ -1046,18 +1091,21 @@ int gcrl_agent_update_phase(gcrl_agent *ag, int phase, gcrl_her *buf, int64_t B,
                             const float *d_dev, const float *noise_dev, double lr_critic, double lr_actor,
                             int flags, void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   check_batch(ag, B);
   GCRL_REQUIRE(phase >= 0 && phase <= 3, "phase must be 0..3");
   GCRL_CUDA(cudaSetDevice(ag->device));
   cudaStream_t st = as_stream(stream);
-  ag->per_on = (flags & 8) != 0;
   if (phase == 0) {
     const float *noise = nullptr;
+    AdamStepGuard guard(ag);
+    ag->per_on = (flags & 8) != 0;
     ingest(ag, buf, B, idx_host, s_dev, a_dev, r_dev, ns_dev, d_dev, noise_dev, &noise, st);
     write_scalars(ag, lr_critic, lr_actor, (flags & 1) != 0, st);
     ag->dp_B = int(B);
     ag->dp_flags = flags;
     run_update(ag, int(B), noise, flags, PH_CGRAD, st);
+    guard.commit();
   } else {
     GCRL_REQUIRE(ag->dp_B == int(B) && ag->dp_flags == flags, "phase 1..3 must follow phase 0 of the same update");
     run_update(ag, int(B), ag->td3 ? ag->noise : nullptr, flags, phase == 1 ? PH_CSTEP : (phase == 2 ? PH_AGRAD : PH_ASTEP), st);
@@ -1067,6 +1115,7 @@ int gcrl_agent_update_phase(gcrl_agent *ag, int phase, gcrl_her *buf, int64_t B,
 
 int gcrl_agent_time_critic_kernel(gcrl_agent *ag, int64_t B, int iters, float *ms_per_launch, void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   check_batch(ag, B);
   GCRL_REQUIRE(iters >= 1 && ms_per_launch != nullptr, "bad argument");
   GCRL_REQUIRE(fused_ok(ag, int(B)), "the fused critic-phase kernel does not serve this batch / shape");
@@ -1103,6 +1152,7 @@ static int dp_items(gcrl_agent *ag, void **ptrs) {
 
 int gcrl_agent_dp_export(gcrl_agent *ag, unsigned char *handles /*[n_items][64]*/, int *n_items) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag != nullptr && n_items != nullptr, "NULL argument");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   GCRL_CUDA(cudaSetDevice(ag->device));
@@ -1137,6 +1187,7 @@ int gcrl_agent_dp_export(gcrl_agent *ag, unsigned char *handles /*[n_items][64]*
 
 int gcrl_agent_dp_connect(gcrl_agent *ag, int rank, int world, const unsigned char *all_handles /*[world][n_items][64]*/) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag != nullptr && all_handles != nullptr, "NULL argument");
   GCRL_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "need 1 <= world <= 8 and 0 <= rank < world");
   GCRL_REQUIRE(ag->p2p.flags != nullptr, "call gcrl_agent_dp_export first");
@@ -1180,6 +1231,7 @@ int gcrl_agent_dp_connect(gcrl_agent *ag, int rank, int world, const unsigned ch
 
 int gcrl_agent_dp_barrier(gcrl_agent *ag, void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag != nullptr && ag->p2p.on, "peer-memory data parallelism is not connected");
   GCRL_CUDA(cudaSetDevice(ag->device));
   auto &pp = ag->p2p;
@@ -1189,6 +1241,7 @@ int gcrl_agent_dp_barrier(gcrl_agent *ag, void *stream) {
 
 int gcrl_agent_grad_buffer(gcrl_agent *ag, int net, float **grad_dev, int64_t *count) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag && net >= 0 && net < NUM_NETS && ag->has[net] && ag->net[net].g, "bad network id");
   if (grad_dev) *grad_dev = ag->net[net].g;
   if (count) *count = ag->net[net].total;
@@ -1197,6 +1250,7 @@ int gcrl_agent_grad_buffer(gcrl_agent *ag, int net, float **grad_dev, int64_t *c
 
 int gcrl_agent_metrics_buffer(gcrl_agent *ag, float **metrics_dev) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag != nullptr && metrics_dev != nullptr, "NULL argument");
   *metrics_dev = ag->metrics;
   GCRL_API_END

@@ -543,6 +543,7 @@ struct ActorNet {
 }  // namespace
 
 struct gcrl_sac {
+  uint32_t magic = 0x54434153u;   // handle type tag: the two agent families share the Python base class
   int device = 0;
   gcrl_sac_config cfg{};
   int D = 0, A = 0, H = 0, L = 0, n = 0, keep = 0, ldh = 0, ldc = 0;
@@ -1071,6 +1072,13 @@ void actor_linear_geom(const gcrl_sac *ag, int layer, int *rows, int *cols, int 
 
 }  // namespace
 
+// Every entry point checks the handle's type tag: a gcrl_sac handle passed to the other family's functions would be
+// reinterpreted as a different struct (garbage shapes and pointers).
+static inline void require_handle(const gcrl_sac *h) {
+  if (h == nullptr) throw ::gcrl::Error(GCRL_ERR_INVALID, "handle is NULL");
+  if (h->magic != 0x54434153u) throw ::gcrl::Error(GCRL_ERR_INVALID, "handle is not a SAC / TQC agent (gcrl_sac_create)");
+}
+
 extern "C" {
 
 int gcrl_sac_create(gcrl_sac **out, int device, const gcrl_sac_config *cfg) {
@@ -1164,6 +1172,7 @@ int gcrl_sac_destroy(gcrl_sac *ag) {
 
 int gcrl_sac_set_actor_linear(gcrl_sac *ag, int layer, const float *w, const float *b, void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag && w && b, "NULL argument");
   GCRL_CUDA(cudaSetDevice(ag->device));
   int rows, cols, ld, woff, boff;
@@ -1175,6 +1184,7 @@ int gcrl_sac_set_actor_linear(gcrl_sac *ag, int layer, const float *w, const flo
 
 int gcrl_sac_get_actor_linear(gcrl_sac *ag, int layer, float *w, float *b, void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag != nullptr, "NULL argument");
   GCRL_CUDA(cudaSetDevice(ag->device));
   int rows, cols, ld, woff, boff;
@@ -1187,6 +1197,7 @@ int gcrl_sac_get_actor_linear(gcrl_sac *ag, int layer, float *w, float *b, void 
 int gcrl_sac_set_actor_bn(gcrl_sac *ag, int layer, const float *weight, const float *bias, const float *rm,
                           const float *rv, void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag && layer >= 0 && layer < ag->L, "bad BatchNorm layer index");
   GCRL_CUDA(cudaSetDevice(ag->device));
   cudaStream_t st = as_stream(stream);
@@ -1200,6 +1211,7 @@ int gcrl_sac_set_actor_bn(gcrl_sac *ag, int layer, const float *weight, const fl
 
 int gcrl_sac_get_actor_bn(gcrl_sac *ag, int layer, float *weight, float *bias, float *rm, float *rv, void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag && layer >= 0 && layer < ag->L, "bad BatchNorm layer index");
   GCRL_CUDA(cudaSetDevice(ag->device));
   cudaStream_t st = as_stream(stream);
@@ -1214,6 +1226,7 @@ int gcrl_sac_get_actor_bn(gcrl_sac *ag, int layer, float *weight, float *bias, f
 int gcrl_sac_set_critic_layer(gcrl_sac *ag, int critic, int target, int layer, const float *w, const float *b,
                               void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag && w && b && critic >= 0 && critic < ag->n, "bad critic index / NULL data");
   CriticNet &c = target ? ag->target[critic] : ag->critic[critic];
   GCRL_REQUIRE(layer >= 0 && layer < c.layers, "bad layer index");
@@ -1225,6 +1238,7 @@ int gcrl_sac_set_critic_layer(gcrl_sac *ag, int critic, int target, int layer, c
 
 int gcrl_sac_get_critic_layer(gcrl_sac *ag, int critic, int target, int layer, float *w, float *b, void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag && critic >= 0 && critic < ag->n, "bad critic index");
   CriticNet &c = target ? ag->target[critic] : ag->critic[critic];
   GCRL_REQUIRE(layer >= 0 && layer < c.layers, "bad layer index");
@@ -1236,6 +1250,7 @@ int gcrl_sac_get_critic_layer(gcrl_sac *ag, int critic, int target, int layer, f
 
 int gcrl_sac_hard_update(gcrl_sac *ag, void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag != nullptr, "agent handle is NULL");
   GCRL_CUDA(cudaSetDevice(ag->device));
   for (int i = 0; i < ag->n; ++i)
@@ -1246,6 +1261,7 @@ int gcrl_sac_hard_update(gcrl_sac *ag, void *stream) {
 
 int gcrl_sac_set_log_alpha(gcrl_sac *ag, float log_alpha, void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag != nullptr, "agent handle is NULL");
   GCRL_CUDA(cudaSetDevice(ag->device));
   const float v[4] = {log_alpha, std::exp(log_alpha), 0.f, 0.f};   // fresh AdamW state (reset(), :763-765)
@@ -1257,6 +1273,7 @@ int gcrl_sac_set_log_alpha(gcrl_sac *ag, float log_alpha, void *stream) {
 
 int gcrl_sac_get_log_alpha(gcrl_sac *ag, float *log_alpha, void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag != nullptr && log_alpha != nullptr, "NULL argument");
   GCRL_CUDA(cudaSetDevice(ag->device));
   GCRL_CUDA(cudaMemcpyAsync(log_alpha, ag->alpha_state, 4, cudaMemcpyDeviceToHost, as_stream(stream)));
@@ -1268,6 +1285,7 @@ int gcrl_sac_update_batch(gcrl_sac *ag, int64_t B, const float *s, const float *
                           const float *d, const float *eps_next, const float *eps_cur, double lr_c, double lr_a,
                           int flags, float *metrics_host, void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag != nullptr, "agent handle is NULL");
   GCRL_CUDA(cudaSetDevice(ag->device));
   sac_update(ag, -1, nullptr, B, nullptr, s, a, r, ns, d, eps_next, eps_cur, lr_c, lr_a, flags, metrics_host,
@@ -1279,6 +1297,7 @@ int gcrl_sac_update_from_buffer(gcrl_sac *ag, gcrl_her *buf, int64_t B, const in
                                 const float *eps_next, const float *eps_cur, double lr_c, double lr_a, int flags,
                                 float *metrics_host, void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag != nullptr && buf != nullptr, "NULL handle");
   GCRL_CUDA(cudaSetDevice(ag->device));
   sac_update(ag, -1, buf, B, idx_host, nullptr, nullptr, nullptr, nullptr, nullptr, eps_next, eps_cur, lr_c, lr_a,
@@ -1290,6 +1309,7 @@ int gcrl_sac_update_phase(gcrl_sac *ag, int phase, gcrl_her *buf, int64_t B, con
                           const float *a, const float *r, const float *ns, const float *d, const float *eps_next,
                           const float *eps_cur, double lr_c, double lr_a, int flags, void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag != nullptr && phase >= 0 && phase <= 3, "NULL handle / phase outside 0..3");
   GCRL_CUDA(cudaSetDevice(ag->device));
   sac_update(ag, phase, buf, B, idx_host, s, a, r, ns, d, eps_next, eps_cur, lr_c, lr_a, flags, nullptr,
@@ -1299,6 +1319,7 @@ int gcrl_sac_update_phase(gcrl_sac *ag, int phase, gcrl_her *buf, int64_t B, con
 
 int gcrl_sac_per_buffers(gcrl_sac *ag, float **weights_dev, float **td_dev) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag != nullptr && weights_dev != nullptr && td_dev != nullptr, "NULL argument");
   *weights_dev = ag->per_w;
   *td_dev = ag->per_td;
@@ -1307,6 +1328,7 @@ int gcrl_sac_per_buffers(gcrl_sac *ag, float **weights_dev, float **td_dev) {
 
 int gcrl_sac_dp_buffer(gcrl_sac *ag, int which, float **dev, int64_t *count) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag != nullptr && dev != nullptr && count != nullptr, "NULL argument");
   switch (which) {
     case 0: *dev = ag->actor.g; *count = ag->actor.total + 4; break;                       // + alpha's batch mean
@@ -1320,6 +1342,7 @@ int gcrl_sac_dp_buffer(gcrl_sac *ag, int which, float **dev, int64_t *count) {
 
 int gcrl_sac_read_metrics(gcrl_sac *ag, int flags, float *metrics_host, void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag != nullptr && metrics_host != nullptr, "NULL argument");
   GCRL_CUDA(cudaSetDevice(ag->device));
   read_metrics(ag, flags, metrics_host, as_stream(stream));
@@ -1329,6 +1352,7 @@ int gcrl_sac_read_metrics(gcrl_sac *ag, int flags, float *metrics_host, void *st
 int gcrl_sac_act(gcrl_sac *ag, int64_t n, const float *obs_host, const float *eps_host, float *act_host,
                  void *stream) {
   GCRL_API_BEGIN
+  require_handle(ag);
   GCRL_REQUIRE(ag && obs_host && act_host, "NULL argument");
   GCRL_REQUIRE(n >= 1 && n <= ag->maxB, "row count outside [1, max_batch]");
   GCRL_CUDA(cudaSetDevice(ag->device));

@@ -131,6 +131,7 @@ class _AgentBase:
         h = vp()
         check(lib.gcrl_agent_create(C.byref(h), self.device_index, C.byref(cfg)))
         self._h = h
+        self._max_batch = int(max_batch or config.batch_size)
         self._metrics = (C.c_float * 8)()
 
     def _init_common(self, obs_dim, ac_dim, config, nenvs, gradient_step, index_source, device, seed):
@@ -247,7 +248,12 @@ class _AgentBase:
     def _actor_forward(self, obs):
         obs = np.ascontiguousarray(obs, np.float32).reshape(-1, self.obs_dim)
         out = np.empty((obs.shape[0], self.ac_dim), np.float32)
-        check(lib.gcrl_agent_act(self._h, obs.shape[0], np_ptr(obs), np_ptr(out), self._stream()))
+        cap = int(self._max_batch)
+        for lo in range(0, obs.shape[0], cap):       # any number of envs: the act scratch holds max_batch rows
+            hi = min(obs.shape[0], lo + cap)
+            o_, out_ = np.ascontiguousarray(obs[lo:hi]), np.empty((hi - lo, self.ac_dim), np.float32)
+            check(lib.gcrl_agent_act(self._h, hi - lo, np_ptr(o_), np_ptr(out_), self._stream()))
+            out[lo:hi] = out_
         return out
 
     def q_values(self, obs, act):

@@ -198,6 +198,7 @@ class _SacBase(_AgentBase):
         h = vp()
         check(lib.gcrl_sac_create(C.byref(h), self.device_index, C.byref(cfg)))
         self._h = h
+        self._max_batch = int(max_batch or config.batch_size)
         self._metrics = (C.c_float * 12)()
         self._bn_batches = 0
         self.actor = _SacActorView(self)
@@ -254,9 +255,20 @@ class _SacBase(_AgentBase):
     def select_action(self, obs_tensor, eval_action: bool = False):           # :641-647 / :1044-1050
         obs = np.ascontiguousarray(obs_tensor, np.float32).reshape(-1, self.obs_dim)
         out = np.empty((obs.shape[0], self.ac_dim), np.float32)
-        eps = None if eval_action else np.random.standard_normal((obs.shape[0], self.ac_dim)).astype(np.float32)
-        check(lib.gcrl_sac_act(self._h, obs.shape[0], np_ptr(obs), None if eps is None else np_ptr(eps),
-                               np_ptr(out), self._stream()))
+        # Normal.rsample draws from torch's generator in the reference (src/model.py:135-137), never from NumPy's
+        # global stream (which PERBuffer.sample consumes): same generator here, on the agent's device
+        eps = None
+        if not eval_action:
+            import torch
+            eps = torch.randn((obs.shape[0], self.ac_dim), dtype=torch.float32, device=self.device).cpu().numpy()
+        cap = int(self._max_batch)
+        for lo in range(0, obs.shape[0], cap):       # any number of envs: the act scratch holds max_batch rows
+            hi = min(obs.shape[0], lo + cap)
+            o_, out_ = np.ascontiguousarray(obs[lo:hi]), np.empty((hi - lo, self.ac_dim), np.float32)
+            e_ = None if eps is None else np.ascontiguousarray(eps[lo:hi])
+            check(lib.gcrl_sac_act(self._h, hi - lo, np_ptr(o_), None if e_ is None else np_ptr(e_), np_ptr(out_),
+                                   self._stream()))
+            out[lo:hi] = out_
         return out
 
     def _polyak_now(self, step):
@@ -344,10 +356,72 @@ class _SacBase(_AgentBase):
         torch.save(self.log_alpha, os.path.join(path, "log_alpha.pth"))
 
     def reset(self):
-        self._init_parameters()
-        for c, t in zip(self._critic_views, self._target_views):   # reference re-inits the targets independently
-            t.set_layers(c.layers())
-        self.set_log_alpha(0.0)
+        """SACAgent.reset / TQCAgent.reset (src/agent.py:755-769, :1161-1170): ``module.apply(_init_weights)`` on the
+        actor, every critic and every TARGET critic re-draws xavier weights / bias 0.01 for the nn.Linear layers
+        only -- BatchNorm affine parameters and running statistics survive, the targets get their OWN draws (they
+        are not copies of the online critics afterwards) -- then log_alpha = 0 with a fresh AdamW.  Draw order as
+        the reference: actor (hidden Linears, mean head, log-std head), critics, target critics."""
+        import torch
+        H, L, D, A = self.config.hidden_dim, self.config.layer_count, self.obs_dim, self.ac_dim
+
+        def xavier(o, i):
+            w = torch.empty(o, i)
+            torch.nn.init.xavier_uniform_(w)
+            return w.numpy(), np.full((o,), 0.01, np.float32)
+
+        for l in range(L):
+            self.actor.set_linear(l, *xavier(H, D if l == 0 else H))
+        self.actor.set_linear(L, *xavier(A, H))
+        self.actor.set_linear(L + 1, *xavier(A, H))
+        for view in list(self._critic_views) + list(self._target_views):
+            view.set_layers([xavier(1 if l == L else H, D + A if l == 0 else H) for l in range(L + 1)])
+        self.set_log_alpha(0.0)          # also re-creates alpha's AdamW state (gcrl_sac_set_log_alpha)
+
+    # -- what the DDPG / TD3 base offers through gcrl_agent_* does not exist for this handle type ---------------
+    def _not_for_sac(self, what):
+        raise NotImplementedError(
+            f"{type(self).__name__}.{what} is not available: SAC / TQC agents checkpoint through save_weights() "
+            "(the reference's own format: actor.pth, critic_*.pth, log_alpha.pth -- src/agent.py:701-705, :1102-1106) "
+            "and the normalisers' YAML; optimiser moments are not exported for these agents")
+
+    def state_dict(self):
+        self._not_for_sac("state_dict")
+
+    def load_state_dict(self, sd):
+        self._not_for_sac("load_state_dict")
+
+    def save_checkpoint(self, path):
+        self._not_for_sac("save_checkpoint")
+
+    def load_checkpoint(self, path):
+        self._not_for_sac("load_checkpoint")
+
+    def hard_update(self):
+        self.update_target_network()
+
+    def q_values(self, *a, **k):
+        self._not_for_sac("q_values")
+
+    def _actor_forward(self, *a, **k):
+        self._not_for_sac("_actor_forward")
+
+    def read_metrics(self):
+        self._not_for_sac("read_metrics")
+
+    def enable_peer_data_parallel(self, process_group=None):
+        self._not_for_sac("enable_peer_data_parallel (use enable_data_parallel: NCCL between the update phases)")
+
+    def peer_barrier(self):
+        self._not_for_sac("peer_barrier")
+
+    def _num_layers(self, net):
+        self._not_for_sac("_num_layers")
+
+    def _get_layers(self, net):
+        self._not_for_sac("_get_layers")
+
+    def _set_layers(self, net, layers):
+        self._not_for_sac("_set_layers")
 
 
 class SACAgent(_SacBase):

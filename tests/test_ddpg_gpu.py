@@ -419,3 +419,38 @@ def test_exploration_select_action_consumes_the_reference_generators(algo):
         np.testing.assert_allclose(g_, want, rtol=1e-6, atol=1e-6)
     assert (random.random(), np.random.random_sample()) == end_state
     assert algo == "td3" or 0 < branches < 40
+
+
+def test_failed_update_leaves_step_counters_untouched():
+    """An update that fails (under-filled buffer; TD3 without its noise tensor) must not advance Adam's step
+    counters: the Python schedulers do not step on an exception either, and every later bias correction would
+    be off by one (csrc/agent.cu::AdamStepGuard)."""
+    import ctypes as C
+    from gcrl_b200 import DDPG
+    from gcrl_b200._lib import GcrlError, check, lib
+    from gcrl_b200.agent import NET_ACTOR, NET_CRITIC
+    from tests.helpers import her_episodes
+    ag = DDPG(10, 3, make_config(batch_size=64, max_len=100000), None, 2, 40, index_source="device")
+    ep = her_episodes(load("her_reach_small"))[2]                  # a 7-step episode: 31 entries < 64
+    ag.buffer.push_episode(ep["s"], ep["a"], ep["ns"], ep["r"], ep["d"], ep["ag"], ep["fut"])
+
+    def steps():
+        out = []
+        for net in (NET_ACTOR, NET_CRITIC):
+            t = C.c_int()
+            check(lib.gcrl_agent_get_adam_step(ag._h, net, C.byref(t)))
+            out.append(t.value)
+        return out
+
+    before, lr_before = steps(), (ag.critic_scheduler.last_epoch, ag.actor_scheduler.last_epoch)
+    with pytest.raises((AssertionError, GcrlError)):
+        ag.update(1)
+    with pytest.raises(GcrlError):
+        check(lib.gcrl_agent_update_from_buffer(ag._h, ag.buffer.handle, 64, None, None, 1e-3, 1e-3, 3, None, None))
+    assert steps() == before
+    assert (ag.critic_scheduler.last_epoch, ag.actor_scheduler.last_epoch) == lr_before
+    # ... and a valid update afterwards advances both by exactly one
+    for e in her_episodes(load("her_reach_small")):
+        ag.buffer.push_episode(e["s"], e["a"], e["ns"], e["r"], e["d"], e["ag"], e["fut"])
+    ag.update(1)
+    assert steps() == [before[0] + 1, before[1] + 1]

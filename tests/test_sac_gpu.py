@@ -248,3 +248,58 @@ def test_tqc_two_emulated_ranks_stay_replicated_and_track_the_averaged_gradient(
             assert np.array_equal(w, w2) and np.array_equal(b, b2)
     for (w, _), (ws, _) in zip(ranks[0]._critic_views[0].layers(), single._critic_views[0].layers()):
         assert np.max(np.abs(w - ws)) <= 2.0 * 1e-3 * 3                              # Adam's hard bound
+
+
+@pytest.mark.parametrize("algo", ["sac", "tqc"])
+def test_reset_redraws_linears_only_and_handle_types_do_not_mix(algo):
+    """reset() as SACAgent.reset / TQCAgent.reset (src/agent.py:755-769, :1161-1170): xavier re-draw of the nn.Linear
+    layers of the actor, the critics AND (independently) the target critics; BatchNorm parameters and running
+    statistics survive; log_alpha back to 0.  The DDPG-only services of the shared base class refuse loudly, and
+    the C side rejects a handle of the other agent family instead of reinterpreting it."""
+    import torch
+    from gcrl_b200 import SACAgent, TQCAgent
+    from gcrl_b200._lib import GcrlError, check, lib
+    cls = SACAgent if algo == "sac" else TQCAgent
+    D, A, H, L, B = 22, 3, 64, 2, 32
+    torch.manual_seed(5)
+    ag = cls(D, A, sac_config(hidden_dim=H, layer_count=L, batch_size=B), None, 1, 40)
+    rng = np.random.default_rng(0)
+    gam, bet, rm, rv = (rng.standard_normal(H).astype(np.float32) for _ in range(4))
+    ag.actor.set_bn(0, gam, bet, rm, np.abs(rv) + 0.5)
+    ag.set_log_alpha(-0.7)
+    before_lin = ag.actor.linear(0)[0].copy()
+    before_c = ag._critic_views[0].layers()[0][0].copy()
+    ag.reset()
+    g2, b2, rm2, rv2 = ag.actor.bn(0)
+    assert np.array_equal(g2, gam) and np.array_equal(b2, bet) and np.array_equal(rm2, rm) and np.array_equal(rv2, np.abs(rv) + 0.5)
+    assert not np.array_equal(ag.actor.linear(0)[0], before_lin)
+    assert not np.array_equal(ag._critic_views[0].layers()[0][0], before_c)
+    for c, t in zip(ag._critic_views, ag._target_views):          # independent draws, not copies
+        assert not np.array_equal(c.layers()[0][0], t.layers()[0][0])
+        assert np.all(c.layers()[0][1] == np.float32(0.01)) and np.all(t.layers()[0][1] == np.float32(0.01))
+    bound = np.sqrt(6.0 / (H + D))
+    assert np.abs(ag.actor.linear(0)[0]).max() <= bound + 1e-6
+    assert float(ag.get_log_alpha()) == 0.0
+    for name, call in (("state_dict", lambda: ag.state_dict()), ("save_checkpoint", lambda: ag.save_checkpoint("/tmp/x")),
+                       ("load_checkpoint", lambda: ag.load_checkpoint("/tmp/x")), ("q_values", lambda: ag.q_values(None, None)),
+                       ("enable_peer_data_parallel", lambda: ag.enable_peer_data_parallel())):
+        with pytest.raises(NotImplementedError, match=name):
+            call()
+    # a SAC / TQC handle is not a gcrl_agent, and vice versa
+    with pytest.raises(GcrlError, match="handle is not"):
+        check(lib.gcrl_agent_hard_update(ag._h, None))
+    from gcrl_b200 import DDPG
+    dd = DDPG(D, A, make_config(hidden_dim=H, layer_count=L, batch_size=B), None, 1, 40)
+    with pytest.raises(GcrlError, match="handle is not"):
+        check(lib.gcrl_sac_hard_update(dd._h, None))
+    assert lib.gcrl_agent_num_layers(ag._h, 0) == -1
+    # select_action: any number of envs (more than max_batch), exploration noise from torch's generator only
+    np.random.seed(3)
+    state = np.random.get_state()[1].copy()
+    obs = rng.standard_normal((3 * B + 5, D)).astype(np.float32)
+    torch.manual_seed(9)
+    a1 = ag.select_action(obs)
+    torch.manual_seed(9)
+    a2 = ag.select_action(obs)
+    assert a1.shape == (3 * B + 5, A) and np.array_equal(a1, a2) and np.all(np.abs(a1) <= 1.0)
+    assert np.array_equal(np.random.get_state()[1], state), "NumPy's global stream must not be consumed"
