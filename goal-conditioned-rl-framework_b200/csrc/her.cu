@@ -11,9 +11,14 @@
 //   ag  [cap_tr][gpad]  : compact copy of ag so the future-goal gather touches a 12-16 B
 //                         row of a small (L2-resident at 1M transitions) array
 //   eps [cap_ep]        : {entry_start, tr_slot, T} per live episode (ring, pow2)
-//   buckets[nb]         : episode id holding entry (b << 6) (ring, pow2) -> O(1) lookup
-//   hdr                 : totals, maintained by the commit kernel so that graph-captured
-//                         sample kernels see fresh values without new kernel arguments
+//   buckets[nb]         : the RECORD {entry_start, tr_slot, T, id} of the episode holding entry (b << 6)
+//                         (ring, pow2, 32 B): position -> episode in ONE load for the common case (the position
+//                         falls into that episode), else a short forward walk over eps
+//   hdr                 : totals, maintained by the commit kernel (diagnostics; the sampler gets them by value)
+//
+// The sampler is a chain of dependent gathers, so its latency is the number of HBM round trips on that chain:
+// bucket record -> (packed row || future-offset word) -> future goal = 3 (round 1: header -> bucket -> episode
+// record -> binary search -> two rounds of row loads -> future goal = 6-7).
 #include <algorithm>
 #include <cstring>
 #include <deque>
@@ -33,6 +38,14 @@ struct __align__(16) EpRec {
   uint32_t T;
 };
 
+struct __align__(32) BucketRec {     // the episode that holds entry (bucket << kBucketShift)
+  int64_t entry_start;
+  uint32_t tr_slot;
+  uint32_t T;
+  int64_t eid;
+  int64_t pad;
+};
+
 struct HerHeader {
   int64_t total_entries;
   int64_t len;
@@ -47,7 +60,7 @@ struct HerGeom {
   float *rows;
   float *ag;
   EpRec *eps;
-  int64_t *buckets;
+  BucketRec *buckets;
   HerHeader *hdr;
   uint32_t cap_tr, ep_mask, bucket_mask;
   int D, G, A, K, row_f, gpad;
@@ -87,8 +100,11 @@ __global__ void __launch_bounds__(256) her_commit_kernel(HerGeom g, const char *
     if (slot >= g.cap_tr) slot -= g.cap_tr;
     ag4[size_t(slot) * g4 + q] = src_ag[e];
   }
-  for (int b = tid; b < int(h.n_buckets); b += nth)
-    g.buckets[(h.first_bucket + b) & g.bucket_mask] = h.eid;
+  for (int b = tid; b < int(h.n_buckets); b += nth) {
+    BucketRec br;
+    br.entry_start = h.entry_start; br.tr_slot = h.tr_slot; br.T = h.T; br.eid = h.eid; br.pad = 0;
+    g.buckets[(h.first_bucket + b) & g.bucket_mask] = br;
+  }
   if (tid == 0) {
     EpRec rec;
     rec.entry_start = h.entry_start;
@@ -168,65 +184,74 @@ __device__ __forceinline__ void write_field(float *__restrict__ out, const float
   }
 }
 
-template <bool VEC>
+// totals by value: the host mirrors the deque counters (and counts the device-stream draws), so no thread waits
+// on a header load before it can compute anything
+struct SampleScalars {
+  int64_t total_entries, len;
+  unsigned long long draw_epoch;
+};
+
+template <bool VEC, int SPB>
 __global__ void __launch_bounds__(kSampleThreads)
-her_sample_kernel(HerGeom g, int64_t B, const int64_t *__restrict__ idx, float *__restrict__ out_s,
-                  float *__restrict__ out_a, float *__restrict__ out_r, float *__restrict__ out_ns,
-                  float *__restrict__ out_d, int64_t *__restrict__ idx_out) {
+her_sample_kernel(const __grid_constant__ HerGeom g, const SampleScalars sc, int64_t B, const int64_t *__restrict__ idx,
+                  float *__restrict__ out_s, float *__restrict__ out_a, float *__restrict__ out_r,
+                  float *__restrict__ out_ns, float *__restrict__ out_d, int64_t *__restrict__ idx_out) {
   extern __shared__ float4 smem4[];
   float *tile = reinterpret_cast<float *>(smem4);
-  uint32_t *m_row = reinterpret_cast<uint32_t *>(tile + kSamplesPerBlock * g.row_f);
-  uint32_t *m_ep0 = m_row + kSamplesPerBlock;
-  uint32_t *m_j = m_ep0 + kSamplesPerBlock;
+  uint32_t *m_row = reinterpret_cast<uint32_t *>(tile + SPB * g.row_f);
 
   const int tid = threadIdx.x;
-  const int64_t base = int64_t(blockIdx.x) * kSamplesPerBlock;
-  const int n = int(min(int64_t(kSamplesPerBlock), B - base));
+  const int64_t base = int64_t(blockIdx.x) * SPB;
+  const int n = int(min(int64_t(SPB), B - base));
 
-  // ---- phase 1: deque position -> (episode, t, j) -> ring slot -------------------------
+  // ---- round trip 1: deque position -> bucket record -> (episode, t, j) -> ring slot ------------------
+  uint32_t j = 0, ep0 = 0;
+  uint32_t futw = 0;
   if (tid < n) {
-    const HerHeader *hdr = g.hdr;
-    const int64_t total = hdr->total_entries, len = hdr->len, ep_last = hdr->ep_last;
     int64_t p;
     if (idx != nullptr) {
       p = idx[base + tid];
-      p = p < 0 ? 0 : (p >= len ? len - 1 : p);
+      p = p < 0 ? 0 : (p >= sc.len ? sc.len - 1 : p);
     } else {
-      p = feistel_position(uint64_t(base + tid), uint64_t(len), g.seed, hdr->draw_epoch);
+      p = feistel_position(uint64_t(base + tid), uint64_t(sc.len), g.seed, sc.draw_epoch);
     }
     if (idx_out != nullptr) idx_out[base + tid] = p;
-    const int64_t ge = total - len + p;  // global entry id
-    const int64_t b = ge >> kBucketShift;
-    int64_t lo = g.buckets[b & g.bucket_mask];
-    lo = lo < hdr->ep_first ? hdr->ep_first : lo;  // never look at evicted episode records
-    int64_t hi = (((b + 1) << kBucketShift) < total) ? g.buckets[(b + 1) & g.bucket_mask] : ep_last;
-    EpRec rec = g.eps[lo & g.ep_mask];
-    while (lo < hi) {  // largest episode id in [lo, hi] whose first entry is <= ge
-      const int64_t mid = (lo + hi + 1) >> 1;
-      const EpRec r2 = g.eps[mid & g.ep_mask];
-      if (r2.entry_start <= ge) { lo = mid; rec = r2; } else { hi = mid - 1; }
+    const int64_t ge = sc.total_entries - sc.len + p;  // global entry id
+    const int4 *bp = reinterpret_cast<const int4 *>(g.buckets + ((ge >> kBucketShift) & g.bucket_mask));
+    const int4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
+    int64_t entry_start = (int64_t(uint32_t(b0.y)) << 32) | uint32_t(b0.x);
+    uint32_t tr_slot = uint32_t(b0.z), T = uint32_t(b0.w);
+    int64_t eid = (int64_t(uint32_t(b1.y)) << 32) | uint32_t(b1.x);
+    // the bucket's episode holds entry (bucket << 6); the position may belong to a later one (an episode of 50
+    // steps spans 246 entries = ~4 buckets, so usually it does not): walk forward over the episode records
+    while (ge >= entry_start + int64_t(T - 1) * (g.K + 1) + 1) {
+      ++eid;
+      const EpRec r2 = g.eps[eid & g.ep_mask];
+      entry_start = r2.entry_start; tr_slot = r2.tr_slot; T = r2.T;
     }
-    const uint32_t o = uint32_t(ge - rec.entry_start);
+    const uint32_t o = uint32_t(ge - entry_start);
     uint32_t t = g.div_k1.div(o);
-    uint32_t j = o - t * uint32_t(g.K + 1);
-    if (t >= rec.T - 1) { t = rec.T - 1; j = 0; }  // last step carries no relabels
-    uint32_t slot = rec.tr_slot + t;
+    j = o - t * uint32_t(g.K + 1);
+    if (t >= T - 1) { t = T - 1; j = 0; }  // last step carries no relabels
+    uint32_t slot = tr_slot + t;
     if (slot >= g.cap_tr) slot -= g.cap_tr;
     m_row[tid] = slot;
-    m_ep0[tid] = rec.tr_slot;
-    m_j[tid] = j;
+    ep0 = tr_slot;
+    // ---- round trip 2 (with the row gather below): the 4 future offsets that contain this relabel's
+    if (j > 0) futw = __ldg(reinterpret_cast<const uint32_t *>(g.rows + size_t(slot) * g.row_f + g.off_fut) + ((j - 1) >> 2));
   }
   __syncthreads();
 
-  // ---- phase 2: coalesced 16 B gathers of the packed rows into shared memory -----------
+  // ---- round trip 2: coalesced 16 B gathers of the packed rows into shared memory, all loads of a thread in flight
   {
     const int rf4 = g.row_f >> 2;
     const int nchunks = n * rf4;
     const float4 *rows4 = reinterpret_cast<const float4 *>(g.rows);
-    for (int c0 = tid; c0 < nchunks; c0 += kSampleThreads * 4) {
-      float4 v[4];
+    constexpr int U = 8;
+    for (int c0 = tid; c0 < nchunks; c0 += kSampleThreads * U) {
+      float4 v[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int c = c0 + u * kSampleThreads;
         if (c < nchunks) {
           const uint32_t i = g.div_rf4.div(c), q = c - i * rf4;
@@ -234,59 +259,54 @@ her_sample_kernel(HerGeom g, int64_t B, const int64_t *__restrict__ idx, float *
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int c = c0 + u * kSampleThreads;
         if (c < nchunks) smem4[c] = v[u];
       }
     }
   }
-  __syncthreads();
-
-  // ---- phase 3: future-goal relabel + sparse reward (bit-exact fp32, no FMA) -----------
-  if (tid < n) {
-    const uint32_t j = m_j[tid];
-    if (j > 0) {
-      float *row = tile + tid * g.row_f;
-      const uint8_t *fut = reinterpret_cast<const uint8_t *>(row + g.off_fut);
-      uint32_t fs = m_ep0[tid] + uint32_t(fut[j - 1]);
-      if (fs >= g.cap_tr) fs -= g.cap_tr;
-      const float *agf = g.ag + size_t(fs) * g.gpad;
-      float acc = 0.f;
-      for (int c = 0; c < g.G; ++c) {
-        const float gf = __ldg(agf + c);
-        const float diff = __fsub_rn(row[g.off_ag + c], gf);   // achieved(t) - future goal
-        const float sq = __fmul_rn(diff, diff);
-        acc = (c == 0) ? sq : __fadd_rn(acc, sq);              // left-to-right, no FMA
-        row[g.D - g.G + c] = gf;
-        row[g.off_ns + g.D - g.G + c] = gf;
-      }
-      const float dist = __fsqrt_rn(acc);
-      // -(d > 0.05) as float32: -1.0f, or -0.0f with the SIGN BIT SET on success
-      // (-np.array(False, float32)).  Written as an INTEGER word: with a float-typed select
-      // nvcc 12.9 rewrites {-1.0f, -0.0f} into int->float(-(int)pred), which yields +0.0f.
-      reinterpret_cast<uint32_t *>(row)[g.off_r] = 0x80000000u | ((dist > g.threshold) ? 0x3F800000u : 0u);
-      row[g.off_d] = 0.0f;                                      // new_done = False
+  // ---- round trip 3: the future achieved goal (issued before the barrier: it overlaps the tail of the gather)
+  float gf[4] = {0.f, 0.f, 0.f, 0.f};
+  const float *agf = nullptr;
+  if (tid < n && j > 0) {
+    uint32_t fs = ep0 + ((futw >> (8 * ((j - 1) & 3))) & 0xffu);
+    if (fs >= g.cap_tr) fs -= g.cap_tr;
+    agf = g.ag + size_t(fs) * g.gpad;
+    if (g.G <= 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(agf));
+      gf[0] = v.x; gf[1] = v.y; gf[2] = v.z; gf[3] = v.w;
     }
   }
   __syncthreads();
 
-  // ---- phase 4: coalesced write-out of the five output tensors --------------------------
+  // ---- relabel + sparse reward (bit-exact fp32, no FMA) --------------------------------------------------
+  if (tid < n && j > 0) {
+    float *row = tile + tid * g.row_f;
+    float acc = 0.f;
+    for (int c = 0; c < g.G; ++c) {
+      const float gfc = g.G <= 4 ? gf[c] : __ldg(agf + c);
+      const float diff = __fsub_rn(row[g.off_ag + c], gfc);    // achieved(t) - future goal
+      const float sq = __fmul_rn(diff, diff);
+      acc = (c == 0) ? sq : __fadd_rn(acc, sq);                // left-to-right, no FMA
+      row[g.D - g.G + c] = gfc;
+      row[g.off_ns + g.D - g.G + c] = gfc;
+    }
+    const float dist = __fsqrt_rn(acc);
+    // -(d > threshold) as float32: -1.0f, or -0.0f with the SIGN BIT SET on success
+    // (-np.array(False, float32)).  Written as an INTEGER word: with a float-typed select
+    // nvcc 12.9 rewrites {-1.0f, -0.0f} into int->float(-(int)pred), which yields +0.0f.
+    reinterpret_cast<uint32_t *>(row)[g.off_r] = 0x80000000u | ((dist > g.threshold) ? 0x3F800000u : 0u);
+    row[g.off_d] = 0.0f;                                        // new_done = False
+  }
+  __syncthreads();
+
+  // ---- coalesced write-out of the five output tensors ---------------------------------------------------
   const FastDiv one(1);
   write_field<VEC>(out_s + base * g.D, tile, n, g.D, 0, g.row_f, g.div_D, tid);
   write_field<VEC>(out_ns + base * g.D, tile, n, g.D, g.off_ns, g.row_f, g.div_D, tid);
   write_field<VEC>(out_a + base * g.A, tile, n, g.A, g.off_a, g.row_f, g.div_A, tid);
   write_field<VEC>(out_r + base, tile, n, 1, g.off_r, g.row_f, one, tid);
   write_field<VEC>(out_d + base, tile, n, 1, g.off_d, g.row_f, one, tid);
-
-  // device index stream: the last CTA to finish advances the draw epoch
-  if (idx == nullptr && tid == 0) {
-    __threadfence();
-    const unsigned int t = atomicAdd(&g.hdr->ticket, 1u);
-    if (t == gridDim.x - 1) {
-      g.hdr->ticket = 0;
-      atomicAdd(&g.hdr->draw_epoch, 1ull);
-    }
-  }
 }
 
 }  // namespace gcrl
@@ -304,6 +324,7 @@ struct gcrl_her {
   int64_t total_entries = 0, total_tr = 0, next_eid = 0, ep_first = 0, tr_live_first = 0;
   std::deque<std::pair<int64_t, int>> live;  // (entry_end, T) of live episodes, oldest first
   uint64_t seed = 0, host_ctr = 0;
+  unsigned long long draw_epoch = 0;         // device index stream: one epoch per launch that draws its own positions
   PinnedRing stage;
   char *d_stage[PinnedRing::kSlots] = {};
   size_t blob_max = 0;
@@ -319,17 +340,30 @@ struct gcrl_her {
   int64_t len() const { return std::min(total_entries, max_entries); }
 };
 
+static constexpr int kSmallTile = 32;      // samples per CTA while the batch is too small to fill the SMs with 128
+static size_t sample_smem(const gcrl_her *h, int spb) { return size_t(spb) * h->g.row_f * 4 + size_t(spb) * 4; }
+
 static void her_launch_sample(gcrl_her *h, int64_t B, const int64_t *idx_dev, float *s, float *a,
                               float *r, float *ns, float *d, int64_t *idx_out, cudaStream_t st) {
-  const unsigned blocks = unsigned((B + kSamplesPerBlock - 1) / kSamplesPerBlock);
   auto aligned = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   const bool vec = aligned(s) && aligned(a) && aligned(r) && aligned(ns) && aligned(d);
-  if (vec)
-    her_sample_kernel<true><<<blocks, kSampleThreads, h->smem_bytes, st>>>(h->g, B, idx_dev, s, a, r,
-                                                                         ns, d, idx_out);
-  else
-    her_sample_kernel<false><<<blocks, kSampleThreads, h->smem_bytes, st>>>(h->g, B, idx_dev, s, a,
-                                                                          r, ns, d, idx_out);
+  SampleScalars sc;
+  sc.total_entries = h->total_entries;
+  sc.len = h->len();
+  sc.draw_epoch = h->draw_epoch;
+  if (idx_dev == nullptr) h->draw_epoch += 1;
+  // small batches: 32 samples per CTA (4x the CTAs, each row gather a single round of loads)
+  const bool small = B <= int64_t(sm_count()) * 4 * kSmallTile;
+  const int spb = small ? kSmallTile : kSamplesPerBlock;
+  const unsigned blocks = unsigned((B + spb - 1) / spb);
+  const size_t smem = sample_smem(h, spb);
+  if (small) {
+    if (vec) her_sample_kernel<true, kSmallTile><<<blocks, kSampleThreads, smem, st>>>(h->g, sc, B, idx_dev, s, a, r, ns, d, idx_out);
+    else her_sample_kernel<false, kSmallTile><<<blocks, kSampleThreads, smem, st>>>(h->g, sc, B, idx_dev, s, a, r, ns, d, idx_out);
+  } else {
+    if (vec) her_sample_kernel<true, kSamplesPerBlock><<<blocks, kSampleThreads, smem, st>>>(h->g, sc, B, idx_dev, s, a, r, ns, d, idx_out);
+    else her_sample_kernel<false, kSamplesPerBlock><<<blocks, kSampleThreads, smem, st>>>(h->g, sc, B, idx_dev, s, a, r, ns, d, idx_out);
+  }
   GCRL_LAUNCHED();
 }
 
@@ -415,24 +449,28 @@ int gcrl_her_create(gcrl_her **out, int device, int64_t max_entries, int64_t cap
     g.div_rf4 = FastDiv(uint32_t(g.row_f / 4));
     g.seed = seed;
     g.threshold = 0.05f;
-    h->smem_bytes = size_t(kSamplesPerBlock) * g.row_f * 4 + 3 * kSamplesPerBlock * 4;
+    h->smem_bytes = sample_smem(h, kSamplesPerBlock);
     GCRL_REQUIRE(h->smem_bytes <= 227 * 1024, "transition row too wide for the sampler tile");
     g.rows = dev_alloc<float>(size_t(h->cap_tr) * g.row_f);
     g.ag = dev_alloc<float>(size_t(h->cap_tr) * g.gpad);
     g.eps = dev_alloc<EpRec>(size_t(h->cap_ep));
-    g.buckets = dev_alloc<int64_t>(size_t(h->nb));
+    g.buckets = dev_alloc<BucketRec>(size_t(h->nb));
     g.hdr = dev_alloc<HerHeader>(1);
     GCRL_CUDA(cudaMemset(g.hdr, 0, sizeof(HerHeader)));
-    GCRL_CUDA(cudaMemset(g.buckets, 0, size_t(h->nb) * sizeof(int64_t)));
+    GCRL_CUDA(cudaMemset(g.buckets, 0, size_t(h->nb) * sizeof(BucketRec)));
     GCRL_CUDA(cudaMemset(g.eps, 0, size_t(h->cap_ep) * sizeof(EpRec)));
     h->blob_max = sizeof(CommitHdr) + size_t(255) * (g.row_f + g.gpad) * 4;
     h->stage.init(h->blob_max);
     for (int i = 0; i < PinnedRing::kSlots; ++i) h->d_stage[i] = dev_alloc<char>(h->blob_max);
     h->idx_stage.init(size_t(1) << 16);
-    GCRL_CUDA(cudaFuncSetAttribute(her_sample_kernel<true>,
+    GCRL_CUDA(cudaFuncSetAttribute(her_sample_kernel<true, kSamplesPerBlock>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->smem_bytes)));
-    GCRL_CUDA(cudaFuncSetAttribute(her_sample_kernel<false>,
+    GCRL_CUDA(cudaFuncSetAttribute(her_sample_kernel<false, kSamplesPerBlock>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->smem_bytes)));
+    GCRL_CUDA(cudaFuncSetAttribute(her_sample_kernel<true, kSmallTile>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, int(sample_smem(h, kSmallTile))));
+    GCRL_CUDA(cudaFuncSetAttribute(her_sample_kernel<false, kSmallTile>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, int(sample_smem(h, kSmallTile))));
   } catch (...) {
     delete h;
     throw;
@@ -607,6 +645,7 @@ int gcrl_her_clear(gcrl_her *h) {
   GCRL_CUDA(cudaDeviceSynchronize());
   GCRL_CUDA(cudaMemset(h->g.hdr, 0, sizeof(HerHeader)));
   h->total_entries = h->total_tr = h->next_eid = h->ep_first = h->tr_live_first = 0;
+  h->draw_epoch = 0;
   h->live.clear();
   GCRL_API_END
 }

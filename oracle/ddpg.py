@@ -209,6 +209,11 @@ class DDPGOracle:
         self._flip_dm = zeros_like_params(self.flip_allowance)
         self._flip_dv = zeros_like_params(self.flip_allowance)
         self._last_flip_abs = None
+        # the same for the critic (its own forward pass in critic_update)
+        self.last_critic_flip_slack = 0.0
+        self.flip_allowance_critic = zeros_like_params([[np.asarray(w, np.float64), np.asarray(b, np.float64)] for w, b in critic])
+        self._flip_dm_c = zeros_like_params(self.flip_allowance_critic)
+        self._flip_dv_c = zeros_like_params(self.flip_allowance_critic)
 
     # src/agent.py:1302-1343
     def critic_update(self, s, a, r, ns, d, weights=None):
@@ -232,8 +237,15 @@ class DDPGOracle:
             td = np.abs(y - q).astype(F32)
             dq = (F32(2.0) * diff * w / F32(B)).astype(F32)
         grads, _ = mlp_backward(self.critic, acts, dq, final_tanh=False)
+        if self.flip_delta:
+            self.last_critic_flip_slack, flip_abs = self._critic_flip_slack(acts, dq, grads)
+        pre_norm = grad_norm_python(grads)
         if self.grad_clip is not None:
             clip_grad_norm_(grads, self.grad_clip)
+        if self.flip_delta:
+            coef = 1.0 if self.grad_clip is None else min(1.0, self.grad_clip / (pre_norm + 1e-6))
+            self._flip_track(self.critic_opt, grads, coef, self.critic_sched.lr, flip_abs, self.last_critic_flip_slack,
+                             self._flip_dm_c, self._flip_dv_c, self.flip_allowance_critic)
         gnorm = grad_norm_python(grads)
         self.critic_opt.step(self.critic, grads, self.critic_sched.lr)
         self.critic_sched.step()
@@ -258,7 +270,8 @@ class DDPGOracle:
             clip_grad_norm_(grads, self.grad_clip)
         if self.flip_delta:
             coef = 1.0 if self.grad_clip is None else min(1.0, self.grad_clip / (pre_norm + 1e-6))
-            self._flip_track(grads, coef, self.actor_sched.lr)
+            self._flip_track(self.actor_opt, grads, coef, self.actor_sched.lr, self._last_flip_abs,
+                             self.last_actor_flip_slack, self._flip_dm, self._flip_dv, self.flip_allowance)
         self.actor_opt.step(self.actor, grads, self.actor_sched.lr)
         self.actor_sched.step()
         self.last_actor_grads = grads
@@ -305,7 +318,29 @@ class DDPGOracle:
                         fa[1] += np.abs(np.asarray(gn[1], np.float64) - go[1])
         return slack / max(base, 1e-30)
 
-    def _flip_track(self, grads, coef, lr):
+    def _critic_flip_slack(self, acts, dq, grads):
+        """_actor_flip_slack for critic_update's own forward pass q = critic([s, a]): hidden units whose
+        pre-activation is within flip_delta of zero, each flipping ONE batch row's contribution to the critic's
+        gradient.  Returns (bound on the change of the gradient norm, relative; per-element |change| like grads)."""
+        base = grad_norm_python(grads)
+        slack = 0.0
+        flip_abs = zeros_like_params([[np.asarray(w, np.float64), np.asarray(b, np.float64)] for w, b in grads])
+        for li in range(1, len(acts) - 1):
+            h = acts[li]
+            rows, units = np.nonzero(np.abs(np.where(h > 0, h, h / LEAKY_SLOPE)) < self.flip_delta)
+            for r_, u_ in zip(rows, units):
+                row = [x[r_:r_ + 1].copy() for x in acts]
+                g_old, _ = mlp_backward(self.critic, row, dq[r_:r_ + 1], final_tanh=False)
+                row[li][0, u_] = F32(-1e-30) if row[li][0, u_] > 0 else F32(1e-30)
+                g_new, _ = mlp_backward(self.critic, row, dq[r_:r_ + 1], final_tanh=False)
+                g2 = [[w + (nw - ow), b + (nb - ob)] for (w, b), (nw, nb), (ow, ob) in zip(grads, g_new, g_old)]
+                slack += abs(grad_norm_python(g2) - base)
+                for fa, gn, go in zip(flip_abs, g_new, g_old):
+                    fa[0] += np.abs(np.asarray(gn[0], np.float64) - go[0])
+                    fa[1] += np.abs(np.asarray(gn[1], np.float64) - go[1])
+        return slack / max(base, 1e-30), flip_abs
+
+    def _flip_track(self, opt, grads, coef, lr, flip_abs, slack, flip_dm, flip_dv, allowance):
         """Per-element bound on how far the actor's weights may legitimately differ from this oracle's because of
         the near-zero hidden pre-activations seen so far (test tolerance, not reference behaviour).
 
@@ -317,14 +352,13 @@ class DDPGOracle:
         and the step lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps) is monotone in m and in v separately, so its extreme
         values over the box [m +- dm] x [v +- dv] are at the corners.  The allowance accumulates the largest corner
         deviation of every step, capped at Adam's hard bound 2 lr.  Elements that no flipped row touches get 0."""
-        opt = self.actor_opt
         t = opt.t + 1
         bc1, bc2s = 1.0 - opt.b1 ** t, (1.0 - opt.b2 ** t) ** 0.5
         for i in range(len(grads)):
             for j in range(2):
                 g = np.abs(np.asarray(grads[i][j], np.float64))
-                d = coef * self._last_flip_abs[i][j] + g * self.last_actor_flip_slack
-                dm, dv = self._flip_dm[i][j], self._flip_dv[i][j]
+                d = coef * flip_abs[i][j] + g * slack
+                dm, dv = flip_dm[i][j], flip_dv[i][j]
                 dm *= opt.b1
                 dm += (1.0 - opt.b1) * d
                 dv *= opt.b2
@@ -337,7 +371,7 @@ class DDPGOracle:
                 for mm in (m - dm, m + dm):
                     for vv in (np.maximum(v - dv, 0.0), v + dv):
                         dev = np.maximum(dev, np.abs(mm / (np.sqrt(vv) / bc2s + opt.eps) - nom))
-                self.flip_allowance[i][j] += np.minimum(2.0 * lr, (lr / bc1) * dev)
+                allowance[i][j] += np.minimum(2.0 * lr, (lr / bc1) * dev)
 
     # src/agent.py:1255-1271
     def soft_update(self, tau):

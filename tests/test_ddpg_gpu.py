@@ -93,26 +93,53 @@ def test_large_batch_update_matches_reference_fixture(case, precision, capsys):
     ag._set_layers(NET_ACTOR, actor0)
     ag._set_layers(NET_CRITIC, critic0)
     ag.update_target_network()
+    # The oracle runs alongside ONLY to bound the conditioning of this batch: LeakyReLU' jumps at 0, so hidden
+    # units whose pre-activation is zero to the engine's rounding (fp32 tiles ~5e-7, 3xTF32 ~2e-6 per layer; the
+    # deltas below are ~10x that) may take either slope, which moves the gradient norms (slack) and, through
+    # Adam, individual weights (per-element allowance) -- oracle/ddpg.py::_flip_track.  Everything else is held
+    # to the reference's own numbers.
+    cfg = make_config(g)
+    orc = OD.DDPGOracle([[w.copy(), b.copy()] for w, b in actor0], [[w.copy(), b.copy()] for w, b in critic0],
+                        gamma=cfg.gamma, tau=cfg.tau, grad_clip=cfg.grad_clip, actor_lr=cfg.actor_lr, critic_lr=cfg.critic_lr)
+    orc.flip_delta = 2e-5 if precision else 5e-6
     rtol = 2e-5 * max(1.0, (B / 256.0) ** 0.5)
     n = len(g["steps"])
     worst = 0.0
+    lines = []
+    failures = []
+    critic_flips = False
     for si, step in enumerate(g["steps"]):
         info = ag.update(int(step), batch=tuple(torch.from_numpy(x).cuda() for x in batches[si]))
+        orc.update_on_batch(int(step), *batches[si])
         got, ref = np.array([float(x) for x in info]), g[f"s{si}_info"]
         assert len(got) == len(ref)
-        worst = max(worst, float(np.max(np.abs(got - ref) / (np.abs(ref) + 1e-6))))
-        np.testing.assert_allclose(got, ref, rtol=rtol, atol=1e-6)
+        rel = np.abs(got - ref) / (np.abs(ref) + 1e-6)
+        tol = np.full(len(ref), rtol)
+        tol[4] += orc.last_critic_flip_slack           # critic gradient norm
+        tol[5] += orc.last_actor_flip_slack            # actor gradient norm
+        critic_flips = critic_flips or orc.last_critic_flip_slack > 0
+        lines.append(f"  step {int(step)}: metric rel errors " + " ".join(f"{x:.1e}" for x in rel) +
+                     f"   (flip slack: critic norm {orc.last_critic_flip_slack:.1e}, actor norm {orc.last_actor_flip_slack:.1e})")
+        worst = max(worst, float(rel[:4].max()))
+        if not np.all(np.abs(got - ref) <= tol * np.abs(ref) + 1e-6):
+            failures.append((int(step), got.tolist(), ref.tolist(), tol.tolist()))
     lr = max(float(g["hp"][3]), float(g["hp"][4]))
-    lines = [f"{case} precision={precision}: worst metric rel err {worst:.2e} (allowed {rtol:.2e})"]
+    lines.insert(0, f"{case} precision={precision}: worst loss / td / q rel err {worst:.2e} (allowed {rtol:.2e})")
     for tag, net in (("actor", ag.actor), ("critic", ag.critic), ("target_actor", ag.target_actor),
                      ("target_critic", ag.target_critic)):
+        allow = orc.flip_allowance if "actor" in tag else orc.flip_allowance_critic
+        scale = cfg.tau * n if tag.startswith("target") else 1.0           # Polyak passes at most tau per step on
         for li, ((w, b), (rw, rb)) in enumerate(zip(net.layers(), ddpg_params_from_golden(g, n - 1, tag))):
             mx, p9999, tol, used = weight_error_report(w, rw, lr, n)
-            lines.append(f"  {tag}.{li}.weight: max {mx:.2e}, 99.99 % {p9999:.2e}, allowance {tol:.2e} ({100 * used:.1f} % used)")
-            assert weights_close(w, rw, lr, n), (case, tag, li, rel_err(w, rw))
-            assert weights_close(b, rb, lr, n), (case, tag, li, rel_err(b, rb))
+            lines.append(f"  {tag}.{li}.weight: max {mx:.2e}, 99.99 % {p9999:.2e}, base allowance {tol:.2e} ({100 * used:.1f} % used), "
+                         f"median flip allowance {float(np.median(allow[li][0])) * scale:.1e}")
+            frac = 5e-3 if ("actor" in tag and critic_flips) else 2e-4     # indirect effect of the stepped critic, see the odd-shape test
+            if not (weights_close(w, rw, lr, n, extra=allow[li][0] * scale, outlier_frac=frac) and
+                    weights_close(b, rb, lr, n, extra=allow[li][1] * scale, outlier_frac=frac)):
+                failures.append((tag, li, rel_err(w, rw), rel_err(b, rb)))
     with capsys.disabled():
         print("\n" + "\n".join(lines))
+    assert not failures, failures
 
 
 @pytest.mark.parametrize("B,H,L,D,A", [(1, 64, 3, 10, 3), (33, 100, 2, 22, 3), (1000, 256, 3, 23, 4),
@@ -133,6 +160,7 @@ def test_update_matches_oracle_odd_shapes(B, H, L, D, A):
     orc = OD.DDPGOracle(actor0, critic0, gamma=cfg.gamma, tau=cfg.tau, grad_clip=cfg.grad_clip,
                         actor_lr=cfg.actor_lr, critic_lr=cfg.critic_lr)
     orc.flip_delta = 5e-6
+    critic_flips = False
     for si, step in enumerate((39, 40, 41, 42)):
         s = rng.standard_normal((B, D)).astype(np.float32)
         ns = (s + 0.1 * rng.standard_normal((B, D))).astype(np.float32)
@@ -147,6 +175,8 @@ def test_update_matches_oracle_odd_shapes(B, H, L, D, A):
         # actor gradient norm: plus the oracle's own bound for hidden units whose pre-activation
         # is zero to fp32 rounding (LeakyReLU' jumps there; oracle/ddpg.py::_actor_flip_slack)
         rtol[5] += orc.last_actor_flip_slack
+        rtol[4] += orc.last_critic_flip_slack
+        critic_flips = critic_flips or orc.last_critic_flip_slack > 0
         got, want = np.array([float(x) for x in got]), np.array(want)
         assert np.all(np.abs(got - want) <= rtol * np.abs(want) + 2e-6), (step, got, want, rtol)
     # A LeakyReLU sign flip of a pre-activation that is zero to fp32 rounding changes one batch row's whole
@@ -157,13 +187,16 @@ def test_update_matches_oracle_odd_shapes(B, H, L, D, A):
     for name, net, ref in (("actor", ag.actor, orc.actor), ("critic", ag.critic, orc.critic),
                            ("target_actor", ag.target_actor, orc.target_actor),
                            ("target_critic", ag.target_critic, orc.target_critic)):
+        allow = orc.flip_allowance if "actor" in name else orc.flip_allowance_critic
+        scale = cfg.tau * n if name.startswith("target") else 1.0          # Polyak passes at most tau per step on
+        # The actor's gradient also depends on the STEPPED critic: where the critic's own weights moved inside their
+        # flip allowance, the actor's small-gradient elements can change Adam direction -- an indirect effect the
+        # per-element bound does not carry; those few elements (<= 0.5 %) are held to Adam's hard bound only.
+        frac = 5e-3 if ("actor" in name and critic_flips) else 2e-4
         for li, ((w, b), (rw, rb)) in enumerate(zip(net.layers(), ref)):
-            ew = eb = None
-            if "actor" in name:
-                scale = cfg.tau * n if name == "target_actor" else 1.0     # Polyak passes at most tau per step on
-                ew, eb = orc.flip_allowance[li][0] * scale, orc.flip_allowance[li][1] * scale
-            assert weights_close(w, rw, 1e-3, n, extra=ew), (name, li, rel_err(w, rw))
-            assert weights_close(b, rb, 1e-3, n, extra=eb), (name, li, rel_err(b, rb))
+            ew, eb = allow[li][0] * scale, allow[li][1] * scale
+            assert weights_close(w, rw, 1e-3, n, extra=ew, outlier_frac=frac), (name, li, rel_err(w, rw))
+            assert weights_close(b, rb, 1e-3, n, extra=eb, outlier_frac=frac), (name, li, rel_err(b, rb))
 
 
 @pytest.mark.parametrize("B,H,L,D,A", [(2048, 256, 3, 21, 3), (5000, 64, 2, 23, 4), (1100, 512, 3, 22, 3)])
@@ -190,7 +223,7 @@ def test_tensor_core_update_matches_fp32_update(B, H, L, D, A):
     orc.flip_delta = 2e-5
     rtol = np.full(6, 5e-5 * max(1.0, (B / 256.0) ** 0.5))
     steps = (39, 40, 41)     # the step-40 Polyak update in the middle
-    slack_total = 0.0
+    critic_flips = False
     for si, step in enumerate(steps):
         s = rng.standard_normal((B, D)).astype(np.float32)
         ns = (s + 0.1 * rng.standard_normal((B, D))).astype(np.float32)
@@ -200,7 +233,8 @@ def test_tensor_core_update_matches_fp32_update(B, H, L, D, A):
         want = np.array(orc.update_on_batch(step, s, a, r, ns, d))
         tol = rtol.copy() * (si + 1)          # the three implementations drift apart step by step
         tol[5] += orc.last_actor_flip_slack
-        slack_total += orc.last_actor_flip_slack
+        tol[4] += orc.last_critic_flip_slack
+        critic_flips = critic_flips or orc.last_critic_flip_slack > 0
         batch = tuple(torch.from_numpy(x).cuda() for x in (s, a, r, ns, d))
         got = [np.array([float(x) for x in ag.update(step, batch=batch)]) for ag in agents]
         for g in got:
@@ -212,16 +246,15 @@ def test_tensor_core_update_matches_fp32_update(B, H, L, D, A):
     for name, a0, a1, ref in (("actor", fp32.actor, tc.actor, orc.actor), ("critic", fp32.critic, tc.critic, orc.critic),
                               ("target_actor", fp32.target_actor, tc.target_actor, orc.target_actor),
                               ("target_critic", fp32.target_critic, tc.target_critic, orc.target_critic)):
-        extra = orc.flip_allowance if "actor" in name else None
+        extra = orc.flip_allowance if "actor" in name else orc.flip_allowance_critic
+        scale = cfg.tau * n if name.startswith("target") else 1.0      # Polyak passes at most tau per step on
+        frac = 5e-3 if ("actor" in name and critic_flips) else 2e-4     # indirect effect of the stepped critic, see the odd-shape test
         for li, ((w0, b0), (w1, b1), (rw, rb)) in enumerate(zip(a0.layers(), a1.layers(), ref)):
-            ew = extra[li][0] if extra is not None else None
-            eb = extra[li][1] if extra is not None else None
-            if name == "target_actor" and ew is not None:
-                ew, eb = ew * cfg.tau * n, eb * cfg.tau * n        # Polyak passes at most tau per step on
-            assert weights_close(w1, rw, 1e-3, n, extra=ew), (name, li, "tc vs oracle")
-            assert weights_close(b1, rb, 1e-3, n, extra=eb), (name, li, "tc vs oracle")
-            assert weights_close(w1, w0, 1e-3, n, extra=ew), (name, li, "tc vs fp32")
-            assert weights_close(b1, b0, 1e-3, n, extra=eb), (name, li, "tc vs fp32")
+            ew, eb = extra[li][0] * scale, extra[li][1] * scale
+            assert weights_close(w1, rw, 1e-3, n, extra=ew, outlier_frac=frac), (name, li, "tc vs oracle")
+            assert weights_close(b1, rb, 1e-3, n, extra=eb, outlier_frac=frac), (name, li, "tc vs oracle")
+            assert weights_close(w1, w0, 1e-3, n, extra=ew, outlier_frac=frac), (name, li, "tc vs fp32")
+            assert weights_close(b1, b0, 1e-3, n, extra=eb, outlier_frac=frac), (name, li, "tc vs fp32")
     assert lib_launch_names_include_tc()
 
 
@@ -445,7 +478,7 @@ def test_failed_update_leaves_step_counters_untouched():
     before, lr_before = steps(), (ag.critic_scheduler.last_epoch, ag.actor_scheduler.last_epoch)
     with pytest.raises((AssertionError, GcrlError)):
         ag.update(1)
-    with pytest.raises(GcrlError):
+    with pytest.raises((AssertionError, GcrlError)):          # GCRL_ERR_UNDERFILLED surfaces as the reference's assert
         check(lib.gcrl_agent_update_from_buffer(ag._h, ag.buffer.handle, 64, None, None, 1e-3, 1e-3, 3, None, None))
     assert steps() == before
     assert (ag.critic_scheduler.last_epoch, ag.actor_scheduler.last_epoch) == lr_before

@@ -286,11 +286,11 @@ def test_reset_redraws_linears_only_and_handle_types_do_not_mix(algo):
         with pytest.raises(NotImplementedError, match=name):
             call()
     # a SAC / TQC handle is not a gcrl_agent, and vice versa
-    with pytest.raises(GcrlError, match="handle is not"):
+    with pytest.raises(ValueError, match="handle is not"):
         check(lib.gcrl_agent_hard_update(ag._h, None))
     from gcrl_b200 import DDPG
     dd = DDPG(D, A, make_config(hidden_dim=H, layer_count=L, batch_size=B), None, 1, 40)
-    with pytest.raises(GcrlError, match="handle is not"):
+    with pytest.raises(ValueError, match="handle is not"):
         check(lib.gcrl_sac_hard_update(dd._h, None))
     assert lib.gcrl_agent_num_layers(ag._h, 0) == -1
     # select_action: any number of envs (more than max_batch), exploration noise from torch's generator only
