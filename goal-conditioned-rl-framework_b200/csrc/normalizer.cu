@@ -45,31 +45,57 @@ __device__ __forceinline__ double shfl_xor_d(double v, int m) {
   return __shfl_xor_sync(0xffffffffu, v, m);
 }
 
-constexpr int kNormWarps = 8;  // columns handled concurrently per CTA
+constexpr int kNormWarps = 8;
+constexpr int kNormThreads = kNormWarps * 32;
 
+// Batch moments of one row block, HBM-bound: the block's elements are read ONCE, in flat (row-major) order, by
+// T = dim * floor(256 / dim) threads -- a multiple of the row width, so thread t sees column t % dim only and
+// consecutive threads read consecutive addresses.  Every thread keeps float64 sums of (x - p) and (x - p)^2 about
+// a per-column pivot p (the block's first row: shifted sums do not cancel), four independent loads in flight;
+// the threads of a column are then merged in thread order with Chan's formula (fixed order: deterministic).
 template <typename T>
-__global__ void __launch_bounds__(kNormWarps * 32)
+__global__ void __launch_bounds__(kNormThreads)
 norm_partial_kernel(const T *__restrict__ x, int64_t n, int dim, int64_t rows_per_block,
                     Moments *__restrict__ partials /* [gridDim.x][dim] */) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ Moments sm[kNormThreads];
+  const int tid = threadIdx.x;
+  const int per_col = kNormThreads / dim;            // threads per column
+  const int T_ = per_col * dim;                      // active threads
   const int64_t r0 = int64_t(blockIdx.x) * rows_per_block;
   const int64_t r1 = min(n, r0 + rows_per_block);
-  for (int c = warp; c < dim; c += kNormWarps) {
-    Moments acc{0.0, 0.0, 0.0};
-    for (int64_t r = r0 + lane; r < r1; r += 32) {
-      const double v = double(x[r * dim + c]);
-      acc.n += 1.0;
-      const double d = v - acc.mean;
-      acc.mean += d / acc.n;
-      acc.m2 += d * (v - acc.mean);
+  Moments acc{0.0, 0.0, 0.0};
+  if (tid < T_ && r0 < r1) {
+    const int c = tid % dim;
+    const double p = double(x[r0 * dim + c]);
+    const T *base = x + r0 * dim;
+    const int64_t cnt = (r1 - r0) * dim;
+    double s1 = 0.0, s2 = 0.0, k = 0.0;
+    int64_t e = tid;
+    for (; e + 3 * int64_t(T_) < cnt; e += 4 * int64_t(T_)) {
+      const double v0 = double(base[e]) - p, v1 = double(base[e + T_]) - p, v2 = double(base[e + 2 * int64_t(T_)]) - p,
+                   v3 = double(base[e + 3 * int64_t(T_)]) - p;
+      s1 += (v0 + v1) + (v2 + v3);
+      s2 += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
+      k += 4.0;
     }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-      Moments o{shfl_xor_d(acc.n, m), shfl_xor_d(acc.mean, m), shfl_xor_d(acc.m2, m)};
-      // merge in a lane-order-independent way: lower lane first
-      acc = (lane & m) ? chan_merge(o, acc) : chan_merge(acc, o);
+    for (; e < cnt; e += T_) {
+      const double v = double(base[e]) - p;
+      s1 += v;
+      s2 += v * v;
+      k += 1.0;
     }
-    if (lane == 0) partials[size_t(blockIdx.x) * dim + c] = acc;
+    if (k > 0.0) {
+      acc.n = k;
+      acc.mean = p + s1 / k;
+      acc.m2 = fmax(s2 - s1 * s1 / k, 0.0);
+    }
+  }
+  sm[tid] = acc;
+  __syncthreads();
+  if (tid < dim) {                                   // column tid: its threads tid, tid + dim, ... in order
+    Moments m = sm[tid];
+    for (int j = 1; j < per_col; ++j) m = chan_merge(m, sm[tid + j * dim]);
+    partials[size_t(blockIdx.x) * dim + tid] = m;
   }
 }
 
@@ -127,40 +153,83 @@ norm_update_seq_kernel(const T *__restrict__ x, int n, int dim, NormState st) {
   update_from_moments(st, c, count, double(mean), double(mul_rn(var, T(n))), double(n));
 }
 
-__global__ void norm_merge_kernel(const Moments *__restrict__ partials, int nblocks, int dim,
-                                  NormState st) {
-  const int c = threadIdx.x;  // single CTA, one thread per column
+// All row-block partials of column c folded by ONE WARP: lane l takes blocks l, l + 32, ... (their loads are
+// independent and issued together -- a single thread walking 592 partials paid one memory round trip each,
+// 200 us), then a shuffle tree with the lower lane first.  The tree's shape depends on nblocks only, so every
+// rank of a data-parallel run folds identically.
+__device__ __forceinline__ Moments merge_partials_warp(const Moments *__restrict__ partials, int nblocks, int dim, int c,
+                                                       int lane) {
+  Moments acc{0.0, 0.0, 0.0};
+  for (int i0 = lane; i0 < nblocks; i0 += 128) {
+    Moments v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + 32 * u;
+      v[u] = i < nblocks ? partials[size_t(i) * dim + c] : Moments{0.0, 0.0, 0.0};
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc = chan_merge(acc, v[u]);
+  }
+#pragma unroll
+  for (int m = 1; m <= 16; m <<= 1) {
+    Moments o{shfl_xor_d(acc.n, m), shfl_xor_d(acc.mean, m), shfl_xor_d(acc.m2, m)};
+    acc = (lane & m) ? chan_merge(o, acc) : chan_merge(acc, o);
+  }
+  return acc;
+}
+
+constexpr int kMergeThreads = 1024;
+
+__global__ void __launch_bounds__(kMergeThreads)
+norm_merge_kernel(const Moments *__restrict__ partials, int nblocks, int dim, NormState st) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const double count = *st.count;
-  __syncthreads();            // every column reads the old count before thread 0 replaces it
-  if (c >= dim) return;
-  Moments b{0.0, 0.0, 0.0};
-  for (int i = 0; i < nblocks; ++i) b = chan_merge(b, partials[size_t(i) * dim + c]);
-  update_from_moments(st, c, count, b.mean, b.m2, b.n);
+  __syncthreads();            // every column reads the old count before column 0 replaces it
+  for (int c = warp; c < dim; c += kMergeThreads / 32) {
+    const Moments b = merge_partials_warp(partials, nblocks, dim, c, lane);
+    if (lane == 0) update_from_moments(st, c, count, b.mean, b.m2, b.n);
+  }
 }
 
 // batch moments only (no state update): what a rank contributes to a data-parallel update
-__global__ void norm_collect_kernel(const Moments *__restrict__ partials, int nblocks, int dim,
-                                    Moments *__restrict__ out) {
-  const int c = threadIdx.x;
-  if (c >= dim) return;
-  Moments b{0.0, 0.0, 0.0};
-  for (int i = 0; i < nblocks; ++i) b = chan_merge(b, partials[size_t(i) * dim + c]);
-  out[c] = b;
+__global__ void __launch_bounds__(kMergeThreads)
+norm_collect_kernel(const Moments *__restrict__ partials, int nblocks, int dim, Moments *__restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = warp; c < dim; c += kMergeThreads / 32) {
+    const Moments b = merge_partials_warp(partials, nblocks, dim, c, lane);
+    if (lane == 0) out[c] = b;
+  }
 }
 
+// normalize(x) = clip((x - mean) / (sqrt(var) + 1e-8), +-clip) in float64, operation for operation as NumPy does it
+// (src/utils.py:96-98).  The per-column mean and denominator sit in shared memory; four independent loads per
+// thread and iteration keep enough bytes in flight for HBM (one load per thread ran at 23 % of it).
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
 norm_apply_kernel(const TI *__restrict__ x, int64_t n, int dim, NormState st, double clip,
                   TO *__restrict__ out, int64_t out_stride, int64_t out_col0, FastDiv ddiv) {
+  __shared__ double s_mean[128], s_den[128];
+  if (int(threadIdx.x) < dim) {
+    s_mean[threadIdx.x] = st.mean[threadIdx.x];
+    s_den[threadIdx.x] = sqrt(st.var[threadIdx.x]) + 1e-8;
+  }
+  __syncthreads();
   const int64_t total = n * dim;
-  for (int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
-       e += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t r = (total < (int64_t(1) << 31)) ? int64_t(ddiv.div(uint32_t(e))) : e / dim;
+  const bool small = total < (int64_t(1) << 31);
+  const int64_t step = int64_t(gridDim.x) * blockDim.x;
+  auto emit = [&](int64_t e, TI xv) {
+    const int64_t r = small ? int64_t(ddiv.div(uint32_t(e))) : e / dim;
     const int c = int(e - r * dim);
-    double z = (double(x[e]) - st.mean[c]) / (sqrt(st.var[c]) + 1e-8);
+    double z = (double(xv) - s_mean[c]) / s_den[c];
     z = fmin(fmax(z, -clip), clip);
     out[r * out_stride + out_col0 + c] = TO(z);
+  };
+  int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; e + 3 * step < total; e += 4 * step) {
+    const TI v0 = x[e], v1 = x[e + step], v2 = x[e + 2 * step], v3 = x[e + 3 * step];
+    emit(e, v0); emit(e + step, v1); emit(e + 2 * step, v2); emit(e + 3 * step, v3);
   }
+  for (; e < total; e += step) emit(e, x[e]);
 }
 
 }  // namespace gcrl
@@ -202,9 +271,7 @@ static void norm_update_device(gcrl_norm *h, const void *x_dev, int64_t n, int i
     norm_partial_kernel<float><<<nblocks, kNormWarps * 32, 0, st>>>(
         static_cast<const float *>(x_dev), n, h->dim, rows_per_block, h->d_partials);
   GCRL_LAUNCHED();
-  const int threads = 128;
-  GCRL_REQUIRE(h->dim <= threads, "normaliser dim > 128 not supported");
-  norm_merge_kernel<<<1, threads, 0, st>>>(h->d_partials, nblocks, h->dim, h->st);
+  norm_merge_kernel<<<1, kMergeThreads, 0, st>>>(h->d_partials, nblocks, h->dim, h->st);
   GCRL_LAUNCHED();
 }
 
@@ -317,7 +384,7 @@ int gcrl_norm_batch_moments(gcrl_norm *h, const void *x_host, int64_t n, int is_
                                                                     rows_per_block, h->d_partials);
   GCRL_LAUNCHED();
   Moments *out = h->d_partials + size_t(h->max_blocks - 1) * h->dim;      // last slab of the scratch
-  norm_collect_kernel<<<1, 128, 0, st>>>(h->d_partials, nblocks, h->dim, out);
+  norm_collect_kernel<<<1, kMergeThreads, 0, st>>>(h->d_partials, nblocks, h->dim, out);
   GCRL_LAUNCHED();
   GCRL_CUDA(cudaMemcpyAsync(moments_host, out, size_t(h->dim) * sizeof(Moments), cudaMemcpyDeviceToHost, st));
   GCRL_CUDA(cudaStreamSynchronize(st));
@@ -337,7 +404,7 @@ int gcrl_norm_update_moments(gcrl_norm *h, const double *moments_host, int parts
   std::memcpy(p, moments_host, bytes);
   GCRL_CUDA(cudaMemcpyAsync(h->d_partials, p, bytes, cudaMemcpyHostToDevice, st));
   h->stage.release(slot, st);
-  norm_merge_kernel<<<1, 128, 0, st>>>(h->d_partials, parts, h->dim, h->st);
+  norm_merge_kernel<<<1, kMergeThreads, 0, st>>>(h->d_partials, parts, h->dim, h->st);
   GCRL_LAUNCHED();
   GCRL_API_END
 }

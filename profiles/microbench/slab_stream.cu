@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <vector>
 namespace cg = cooperative_groups;
+template <typename F> float time_it(F f, int iters = 20);
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
 
@@ -189,7 +190,115 @@ __global__ void __launch_bounds__(kConsumers + 32, 1) ring_kernel(const float *W
   if (CL > 1) cg::this_cluster().sync();
 }
 
-template <typename F> float time_it(F f, int iters = 20) {
+// mode 3: N-split over a 2-CTA cluster: the pair carries R rows, each CTA streams HALF of every layer's columns
+// (per-thread __ldg), the half results are exchanged through distributed shared memory, one cluster barrier per layer
+template <int R>
+__global__ void __launch_bounds__(kConsumers, 1) nsplit_kernel(const float *W, int nlayers, int steps, float *out) {
+  __shared__ __align__(16) float xT[2][H * R];
+  extern __shared__ float4 dyn[];
+  float *red = reinterpret_cast<float *>(dyn);       // [16][128][R]
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();
+  float *peer_x0 = cluster.map_shared_rank(&xT[0][0], rank ^ 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int e = tid; e < H * R; e += kConsumers) xT[0][e] = 0.001f * (e % 7);
+  __syncthreads();
+  cluster.sync();
+  const int ks = warp, j0 = rank * 128 + lane * 4;          // 16 K-groups of 16 rows, 128 columns per CTA
+  for (int s = 0; s < steps; ++s) {
+    const float *M = W + size_t(s % nlayers) * H * H + size_t(ks * 16) * H + j0;
+    const float *x = xT[s & 1] + ks * 16 * R;
+    float acc[4][R] = {};
+#pragma unroll 16
+    for (int i = 0; i < 16; ++i) {
+      const float4 w = __ldg(reinterpret_cast<const float4 *>(M + size_t(i) * H));
+      float xv[R];
+      load_rows<R>(x + i * R, xv);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        acc[0][r] = fmaf(w.x, xv[r], acc[0][r]); acc[1][r] = fmaf(w.y, xv[r], acc[1][r]);
+        acc[2][r] = fmaf(w.z, xv[r], acc[2][r]); acc[3][r] = fmaf(w.w, xv[r], acc[3][r]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int r = 0; r < R; ++r) red[(ks * 128 + lane * 4 + c) * R + r] = acc[c][r];
+    __syncthreads();
+    float *ynext = xT[(s + 1) & 1];
+    float *ypeer = peer_x0 + ((s + 1) & 1) * H * R;
+    for (int e = tid; e < 128 * R; e += kConsumers) {
+      float v = 0.f;
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) v += red[k2 * 128 * R + e];
+      v = v > 0.f ? v : 0.01f * v;
+      ynext[rank * 128 * R + e] = v;
+      ypeer[rank * 128 * R + e] = v;
+    }
+    cluster.sync();
+  }
+  if (tid < R) out[blockIdx.x * R + tid] = xT[steps & 1][tid];
+}
+template <int R> void run_nsplit(const float *W, int nl, int steps, float *out, int grid) {
+  const size_t smem = size_t(16) * 128 * R * 4;
+  auto k = nsplit_kernel<R>;
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kConsumers); cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1]; attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  const float us = time_it([&] { CK(cudaLaunchKernelEx(&cfg, k, W, nl, steps, out)); });
+  printf("nsplit R=%d (rows per 2-CTA pair) grid=%3d steps=%d: %7.2f us  (%.2f us/step)\n", R, grid, steps, us, us / steps);
+}
+
+// mode 4: as mode 0, but software-pipelined: the 8 weight loads of K-batch b+1 are issued BEFORE the 64 FMAs of
+// batch b (register double buffer), so a warp's load latency overlaps its own arithmetic
+template <int R, int DEPTH>
+__global__ void __launch_bounds__(kConsumers, 1) ldg_pipe_kernel(const float *W, int nlayers, int steps, float *out) {
+  __shared__ float xT[2][H * R];
+  extern __shared__ float4 dyn[];
+  float *red = reinterpret_cast<float *>(dyn);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int e = tid; e < H * R; e += kConsumers) xT[0][e] = 0.001f * (e % 7);
+  __syncthreads();
+  const int cw = warp & 1, ks = warp >> 1, j0 = (cw * 32 + lane) * 4;
+  constexpr int NB = 32 / DEPTH;     // batches of DEPTH rows per K-group
+  for (int s = 0; s < steps; ++s) {
+    const float *M = W + size_t(s % nlayers) * H * H + size_t(ks * 32) * H + j0;
+    const float *x = xT[s & 1] + ks * 32 * R;
+    float acc[4][R] = {};
+    float4 wb[2][DEPTH];
+#pragma unroll
+    for (int i = 0; i < DEPTH; ++i) wb[0][i] = __ldg(reinterpret_cast<const float4 *>(M + size_t(i) * H));
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      if (b + 1 < NB) {
+#pragma unroll
+        for (int i = 0; i < DEPTH; ++i) wb[(b + 1) & 1][i] = __ldg(reinterpret_cast<const float4 *>(M + size_t((b + 1) * DEPTH + i) * H));
+      }
+#pragma unroll
+      for (int i = 0; i < DEPTH; ++i) {
+        const float4 w = wb[b & 1][i];
+        float xv[R];
+        load_rows<R>(x + (b * DEPTH + i) * R, xv);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          acc[0][r] = fmaf(w.x, xv[r], acc[0][r]); acc[1][r] = fmaf(w.y, xv[r], acc[1][r]);
+          acc[2][r] = fmaf(w.z, xv[r], acc[2][r]); acc[3][r] = fmaf(w.w, xv[r], acc[3][r]);
+        }
+      }
+    }
+    combine<R>(acc, red, xT[(s + 1) & 1], warp, lane, tid);
+  }
+  if (tid < R) out[blockIdx.x * R + tid] = xT[steps & 1][tid];
+}
+template <int R, int DEPTH> void run_ldg_pipe(const float *W, int nl, int steps, float *out, int grid) {
+  const size_t smem = size_t(8) * H * R * 4;
+  const float us = time_it([&] { ldg_pipe_kernel<R, DEPTH><<<grid, kConsumers, smem>>>(W, nl, steps, out); });
+  printf("ldg-pipelined R=%d depth=%2d grid=%3d steps=%d: %7.2f us  (%.2f us/step)\n", R, DEPTH, grid, steps, us, us / steps);
+}
+
+template <typename F> float time_it(F f, int iters) {
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   for (int i = 0; i < 3; ++i) f();
   CK(cudaDeviceSynchronize());
@@ -242,6 +351,16 @@ int main() {
     run_ring<2, 32, 6, 2>(W, nl, steps, out, grid);
     run_ring<4, 32, 4, 2>(W, nl, steps, out, grid);
     run_ring<2, 32, 4, 4>(W, nl, steps, out, grid == 148 ? 144 : grid);
+  }
+  for (int grid : {1, 128}) {
+    run_ldg_pipe<2, 4>(W, nl, steps, out, grid);
+    run_ldg_pipe<2, 8>(W, nl, steps, out, grid);
+    run_ldg_pipe<2, 16>(W, nl, steps, out, grid);
+    run_ldg_pipe<4, 8>(W, nl, steps, out, grid);
+  }
+  for (int grid : {2, 64, 128, 148}) {
+    run_nsplit<4>(W, nl, steps, out, grid);
+    run_nsplit<8>(W, nl, steps, out, grid);
   }
   printf("done\n");
   return 0;
