@@ -22,6 +22,9 @@
 
 struct gcrl_her;
 namespace gcrl {
+SampleScalars her_next_scalars(gcrl_her *h, bool positions_given);
+const HerGeom &her_geom(const gcrl_her *h);
+int64_t her_len(const gcrl_her *h);
 void her_sample_into(gcrl_her *h, int64_t B, const int64_t *idx_host, float *s, float *a, float *r,
                      float *ns, float *d, int64_t *idx_out, cudaStream_t st);
 int her_state_dim(const gcrl_her *h);
@@ -132,7 +135,11 @@ struct gcrl_agent {
   float *sumsq = nullptr;                  // [max(reduce grid, wgrad tiles)]
   int nsumsq = 0;                          // how many sums of squares the pending optimiser step reads
   float *metrics = nullptr;                // [8]
-  StepScalars *d_scalars = nullptr;
+  StepScalars *d_scalars = nullptr;        // StepScalars, then the SampleScalars of the update (one H2D copy)
+  SampleScalars *d_sample_sc = nullptr;
+  int64_t *d_idx = nullptr;                // positions of the in-kernel sampler (host index stream) [maxB]
+  gcrl_her *sample_buf = nullptr;          // the update being issued draws its batch inside the critic kernel
+  SampleScalars sample_sc{};
   PinnedRing scal_stage;
   PinnedRing io_stage;
   float *d_io = nullptr;
@@ -142,7 +149,7 @@ struct gcrl_agent {
   float *dzh = nullptr;                    // fused path: critic head dL/dq [maxB]
   float *per_w = nullptr, *per_td = nullptr;   // prioritised replay: importance weights in, TD errors out [maxB]
   bool per_on = false;                     // flags bit3 of the update being issued
-  bool use_fused = true;
+  bool use_fused = true, fuse_sampler = true;
   int dp_B = -1, dp_flags = -1;            // the update the data-parallel phases belong to
   // data-parallel averaging over NVLink peer memory (gcrl_agent_dp_connect)
   struct P2P {
@@ -163,7 +170,7 @@ struct gcrl_agent {
   bool use_graphs = true;
   cudaStream_t cap_stream = nullptr;       // capture-only stream (the caller's may be the legacy one)
   struct GraphRec { cudaGraphExec_t exec; uint64_t kernels; };
-  std::map<std::tuple<int64_t, int, int>, GraphRec> graphs;   // (B, flags, phase mask)
+  std::map<std::tuple<int64_t, int, int, uintptr_t>, GraphRec> graphs;   // (B, flags, phase mask, sampled buffer)
 };
 
 namespace {
@@ -414,6 +421,13 @@ FusedCriticArgs fused_critic_args(gcrl_agent *ag, int B, int which = 0) {
   }
   if (ag->per_on) { a.is_w = ag->per_w; a.td_out = ag->per_td; }
   a.s = ag->bs; a.a = ag->ba; a.r = ag->br0; a.ns = ag->bns; a.d = ag->bd0;
+  if (ag->sample_buf != nullptr && which == 0) {        // the kernel draws the batch itself (TD3 critic 2 reuses it)
+    a.sample = 1;
+    a.geom = her_geom(ag->sample_buf);
+    a.sample_sc = ag->d_sample_sc;
+    a.sample_idx = ag->d_idx;
+    a.bs = ag->bs; a.ba = ag->ba; a.br = ag->br0; a.bns = ag->bns; a.bd = ag->bd0;
+  }
   a.B = B; a.D = ag->D; a.A = ag->A; a.H = ag->H; a.L = ag->L; a.ldh = ag->ldh; a.ldc = ag->ldc;
   a.gamma = ag->cfg.gamma;
   a.y_lo = float(-1.0 / (1.0 - double(ag->cfg.gamma)));
@@ -571,13 +585,15 @@ void write_scalars(gcrl_agent *ag, double lr_c, double lr_a, bool actor_steps, c
     out[3] = 0.f;
   };
   int slot;
-  auto *sc = reinterpret_cast<StepScalars *>(ag->scal_stage.acquire(sizeof(StepScalars), &slot));
+  constexpr size_t kScalBytes = sizeof(StepScalars) + sizeof(SampleScalars);
+  auto *sc = reinterpret_cast<StepScalars *>(ag->scal_stage.acquire(kScalBytes, &slot));
+  std::memcpy(sc + 1, &ag->sample_sc, sizeof(SampleScalars));
   ag->net[CRITIC1].adam_t += 1;
   if (ag->td3) ag->net[CRITIC2].adam_t += 1;
   fill(ag->net[CRITIC1].adam_t, lr_c, &sc->step_size_c);
   if (actor_steps) ag->net[ACTOR].adam_t += 1;
   fill(std::max(1, ag->net[ACTOR].adam_t), lr_a, &sc->step_size_a);
-  GCRL_CUDA(cudaMemcpyAsync(ag->d_scalars, sc, sizeof(StepScalars), cudaMemcpyHostToDevice, st));
+  GCRL_CUDA(cudaMemcpyAsync(ag->d_scalars, sc, kScalBytes, cudaMemcpyHostToDevice, st));
   ag->scal_stage.release(slot, st);
 }
 
@@ -630,7 +646,7 @@ void run_update(gcrl_agent *ag, int B, const float *noise, int flags, int mask, 
     run_update_body(ag, B, noise, flags, mask, st);
     return;
   }
-  const auto key = std::make_tuple(int64_t(B), flags, mask);
+  const auto key = std::make_tuple(int64_t(B), flags, mask, reinterpret_cast<uintptr_t>(ag->sample_buf));
   auto it = ag->graphs.find(key);
   if (it == ag->graphs.end()) {
     cudaGraph_t graph = nullptr;
@@ -659,10 +675,29 @@ void run_update(gcrl_agent *ag, int B, const float *noise, int flags, int mask, 
 void ingest(gcrl_agent *ag, gcrl_her *buf, int64_t B, const int64_t *idx_host, const float *s, const float *a,
             const float *r, const float *ns, const float *d, const float *noise_dev, const float **noise_out,
             cudaStream_t st) {
+  ag->sample_buf = nullptr;
   if (buf != nullptr) {
     GCRL_REQUIRE(her_state_dim(buf) == ag->D && her_act_dim(buf) == ag->A, "buffer / agent shape mismatch");
     GCRL_REQUIRE(her_device(buf) == ag->device, "buffer and agent live on different devices");
-    her_sample_into(buf, B, idx_host, ag->bs, ag->ba, ag->br0, ag->bns, ag->bd0, nullptr, st);
+    if (fused_ok(ag, int(B)) && ag->fuse_sampler && fused_sample_supported(her_geom(buf))) {
+      // row-slab path: the critic-phase kernel draws its own rows; here only the positions (host index stream)
+      // and the buffer's totals travel to the device
+      if (her_len(buf) < B) throw Error(GCRL_ERR_UNDERFILLED, "[ERROR] Not enough in buffer to sample");
+      if (idx_host != nullptr) {
+        const int64_t len = her_len(buf);
+        for (int64_t i = 0; i < B; ++i)
+          if (idx_host[i] < 0 || idx_host[i] >= len) throw Error(GCRL_ERR_INVALID, "sample index out of range [0, len)");
+        int slot;
+        char *p = ag->io_stage.acquire(size_t(B) * sizeof(int64_t), &slot);
+        std::memcpy(p, idx_host, size_t(B) * sizeof(int64_t));
+        GCRL_CUDA(cudaMemcpyAsync(ag->d_idx, p, size_t(B) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        ag->io_stage.release(slot, st);
+      }
+      ag->sample_sc = her_next_scalars(buf, idx_host != nullptr);
+      ag->sample_buf = buf;
+    } else {
+      her_sample_into(buf, B, idx_host, ag->bs, ag->ba, ag->br0, ag->bns, ag->bd0, nullptr, st);
+    }
     s = ag->bs; a = ag->ba; r = ag->br0; ns = ag->bns; d = ag->bd0;
   } else {
     GCRL_REQUIRE(s && a && r && ns && d, "NULL batch pointer");
@@ -797,7 +832,11 @@ int gcrl_agent_create(gcrl_agent **out, int device, const gcrl_agent_config *cfg
     ag->sumsq = dev_alloc<float>(size_t(std::max(reduce_grid(int(ag->slab)), wtiles)) + 8);
     ag->metrics = dev_alloc<float>(8);
     GCRL_CUDA(cudaMemset(ag->metrics, 0, 8 * sizeof(float)));
-    ag->d_scalars = dev_alloc<StepScalars>(1);
+    ag->d_scalars = reinterpret_cast<StepScalars *>(dev_alloc<char>(sizeof(StepScalars) + sizeof(SampleScalars)));
+    ag->d_sample_sc = reinterpret_cast<SampleScalars *>(ag->d_scalars + 1);
+    ag->d_idx = dev_alloc<int64_t>(size_t(mb));
+    const char *nfs = getenv("GCRL_B200_NO_FUSED_SAMPLER");
+    ag->fuse_sampler = !(nfs && nfs[0] == '1');
     ag->scal_stage.init(256);
     GCRL_CUDA(cudaStreamCreateWithFlags(&ag->cap_stream, cudaStreamNonBlocking));
     const char *ng = getenv("GCRL_B200_NO_GRAPH");
@@ -835,6 +874,7 @@ int gcrl_agent_destroy(gcrl_agent *ag) {
     if (p) cudaFree(p);
   for (float *p : ag->dzl) cudaFree(p);
   cudaFree(ag->d_scalars);
+  cudaFree(ag->d_idx);
   if (ag->cap_stream) cudaStreamDestroy(ag->cap_stream);
   ag->scal_stage.destroy();
   ag->io_stage.destroy();
@@ -1121,7 +1161,10 @@ int gcrl_agent_time_critic_kernel(gcrl_agent *ag, int64_t B, int iters, float *m
   GCRL_REQUIRE(fused_ok(ag, int(B)), "the fused critic-phase kernel does not serve this batch / shape");
   GCRL_CUDA(cudaSetDevice(ag->device));
   cudaStream_t st = as_stream(stream);
+  gcrl_her *const sampled = ag->sample_buf;        // time the kernel on the resident dense batch
+  ag->sample_buf = nullptr;
   const FusedCriticArgs a = fused_critic_args(ag, int(B));
+  ag->sample_buf = sampled;
   cudaEvent_t e0, e1;
   GCRL_CUDA(cudaEventCreate(&e0));
   GCRL_CUDA(cudaEventCreate(&e1));

@@ -199,7 +199,7 @@ __device__ __forceinline__ SmemPlan carve(float *base, int KinP, int H, int L, b
 size_t fused_smem_bytes(int R, int D, int A, int H, int L, bool two_keeps) {
   const int KinP = (D + A + 3) & ~3;
   size_t f = size_t(2) * KinP * R + size_t(2) * H * R + size_t(L) * H * R * (two_keeps ? 2 : 1) +
-             size_t(2048) * R + 16 * R;
+             size_t(2048) * R + 24 * R;
   return f * sizeof(float);
 }
 
@@ -236,21 +236,78 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_critic_kernel(FusedCri
   const int role = SPLIT ? int(blockIdx.x & 1) : 2;      // 0: target path, 1: critic path, 2: both
   const int row0 = slab * R, tid = threadIdx.x;
 
+  // ---- 0a. (sample) draw this slab's rows from the HER episode store: 3 dependent gathers (bucket record ->
+  //          packed row || future offsets -> future goal), relabel + reward in shared memory ----
+  const float *tile = nullptr;
+  if (a.sample) {
+    const HerGeom &g = a.geom;
+    float *tl = sp.red;                              // R packed rows (row_f <= 2048 floats each)
+    __shared__ uint32_t s_slot[8];
+    const SampleScalars sc = *a.sample_sc;
+    const int nrows = min(R, B - row0);
+    SampleRef ref{0u, 0u, 0u, 0u};
+    if (tid < nrows) {
+      ref = her_resolve(g, sc, row0 + tid, sc.use_idx ? a.sample_idx : nullptr, nullptr);
+      s_slot[tid] = ref.slot;
+    }
+    __syncthreads();
+    const int rf4 = g.row_f >> 2;
+    const float4 *rows4 = reinterpret_cast<const float4 *>(g.rows);
+    for (int c = tid; c < nrows * rf4; c += kFusedThreads) {
+      const int i = c / rf4, q = c - i * rf4;
+      reinterpret_cast<float4 *>(tl)[c] = ldg_stream4(rows4 + size_t(s_slot[i]) * rf4 + q);
+    }
+    float *gfs = sp.small + 16 * R;                  // behind the per-row scalars: [R][8] future goals (G <= 8)
+    if (tid < nrows && ref.j > 0) {
+      const float *agf = g.ag + size_t(her_future_slot(g, ref)) * g.gpad;
+      for (int c = 0; c < g.G; ++c) gfs[tid * 8 + c] = __ldg(agf + c);
+    }
+    __syncthreads();
+    if (tid < nrows && ref.j > 0) her_relabel_row(g, tl + tid * g.row_f, gfs + tid * 8);
+    __syncthreads();
+    if (role != 0) {                                 // the dense batch, for the actor phase and the second critic
+      for (int e = tid; e < nrows * D; e += kFusedThreads) {
+        const int i = e / D, k = e - i * D;
+        a.bs[size_t(row0 + i) * D + k] = tl[i * g.row_f + k];
+        a.bns[size_t(row0 + i) * D + k] = tl[i * g.row_f + g.off_ns + k];
+      }
+      for (int e = tid; e < nrows * A; e += kFusedThreads) {
+        const int i = e / A, k = e - i * A;
+        a.ba[size_t(row0 + i) * A + k] = tl[i * g.row_f + g.off_a + k];
+      }
+      if (tid < nrows) {
+        a.br[row0 + tid] = tl[tid * g.row_f + g.off_r];
+        a.bd[row0 + tid] = tl[tid * g.row_f + g.off_d];
+      }
+    }
+    tile = tl;
+  }
   // ---- 0. stage the slab's rows: x_ns = [s' | (a')], x_sa = [s | a]; also emit [s | a | 0] rows ----
   for (int e = tid; e < KinP * R; e += kFusedThreads) {
     const int k = e / R, r = e - k * R, row = row0 + r;
     float vns = 0.f, vsa = 0.f;
     if (row < B) {
-      if (k < D) { vns = a.ns[size_t(row) * D + k]; vsa = a.s[size_t(row) * D + k]; }
-      else if (k < D + A) vsa = a.a[size_t(row) * A + (k - D)];
+      if (tile != nullptr) {
+        const float *t = tile + r * a.geom.row_f;
+        if (k < D) { vns = t[a.geom.off_ns + k]; vsa = t[k]; }
+        else if (k < D + A) vsa = t[a.geom.off_a + (k - D)];
+      } else {
+        if (k < D) { vns = a.ns[size_t(row) * D + k]; vsa = a.s[size_t(row) * D + k]; }
+        else if (k < D + A) vsa = a.a[size_t(row) * A + (k - D)];
+      }
     }
     x_ns[e] = vns;
     x_sa[e] = vsa;
   }
   if (tid < R) {
     const int row = row0 + tid;
-    rr[tid] = row < B ? a.r[row] : 0.f;
-    dd[tid] = row < B ? a.d[row] : 0.f;
+    if (tile != nullptr) {
+      rr[tid] = row < B ? tile[tid * a.geom.row_f + a.geom.off_r] : 0.f;
+      dd[tid] = row < B ? tile[tid * a.geom.row_f + a.geom.off_d] : 0.f;
+    } else {
+      rr[tid] = row < B ? a.r[row] : 0.f;
+      dd[tid] = row < B ? a.d[row] : 0.f;
+    }
   }
   __syncthreads();
   if (a.sa_out != nullptr && role != 0) {
@@ -477,6 +534,9 @@ int fused_rows_per_cta(int B) {
   if (B <= 2 * sm_count()) return 2;
   return B <= 512 ? 4 : 8;
 }
+
+// can the critic-phase kernel draw its own rows from this episode store?
+bool fused_sample_supported(const HerGeom &g) { return g.G <= 8 && g.row_f <= 2048; }
 
 bool fused_supported(int B, int D, int A, int H, int L) {
   if (B < 1 || B > 1024 || L < 1 || L > kFusedMaxL || A > 4 || H < 4 || H > 2048) return false;

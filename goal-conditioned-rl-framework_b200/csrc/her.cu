@@ -24,51 +24,9 @@
 #include <deque>
 #include <vector>
 
-#include "common.cuh"
+#include "her_device.cuh"
 
 namespace gcrl {
-
-constexpr int kBucketShift = 6;
-constexpr int kSamplesPerBlock = 128;
-constexpr int kSampleThreads = 256;
-
-struct __align__(16) EpRec {
-  int64_t entry_start;
-  uint32_t tr_slot;
-  uint32_t T;
-};
-
-struct __align__(32) BucketRec {     // the episode that holds entry (bucket << kBucketShift)
-  int64_t entry_start;
-  uint32_t tr_slot;
-  uint32_t T;
-  int64_t eid;
-  int64_t pad;
-};
-
-struct HerHeader {
-  int64_t total_entries;
-  int64_t len;
-  int64_t ep_first;
-  int64_t ep_last;
-  unsigned long long draw_epoch;
-  unsigned int ticket;
-  unsigned int pad;
-};
-
-struct HerGeom {
-  float *rows;
-  float *ag;
-  EpRec *eps;
-  BucketRec *buckets;
-  HerHeader *hdr;
-  uint32_t cap_tr, ep_mask, bucket_mask;
-  int D, G, A, K, row_f, gpad;
-  int off_ns, off_a, off_r, off_d, off_ag, off_fut;
-  FastDiv div_k1, div_D, div_A, div_rf4;
-  uint64_t seed;
-  float threshold;          // sparse reward: -(||ag - g|| > threshold), 0.05 for the Panda tasks
-};
 
 struct __align__(16) CommitHdr {
   int64_t entry_start, eid, total_entries, len, ep_first, first_bucket;
@@ -119,36 +77,6 @@ __global__ void __launch_bounds__(256) her_commit_kernel(HerGeom g, const char *
 }
 
 // ---------------------------------------------------------------------------------------
-// on-device index stream: keyed 4-round Feistel permutation of [0, n) with cycle walking.
-// Position i of call `epoch` is perm_epoch(i): B distinct, uniformly spread positions,
-// i.e. sampling WITHOUT replacement like random.sample (reference src/buffer.py:124).
-// ---------------------------------------------------------------------------------------
-__host__ __device__ inline int64_t feistel_position(uint64_t x, uint64_t n, uint64_t seed,
-                                                    uint64_t epoch) {
-  if (n <= 1) return 0;
-  int b = 0;
-  while (b < 63 && (1ull << b) < n) ++b;
-  if (b < 2) b = 2;
-  b += (b & 1);
-  const int half = b >> 1;
-  const uint32_t mask = half >= 32 ? 0xffffffffu : ((1u << half) - 1u);
-  const uint64_t k0 = splitmix64(seed ^ (epoch * 0xD1B54A32D192ED03ull));
-  const uint64_t k1 = splitmix64(k0);
-  const uint32_t keys[4] = {uint32_t(k0), uint32_t(k0 >> 32), uint32_t(k1), uint32_t(k1 >> 32)};
-  do {
-    uint32_t L = uint32_t(x >> half) & mask, R = uint32_t(x) & mask;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      uint32_t nl = R;
-      R = L ^ (mix32(R ^ keys[r]) & mask);
-      L = nl;
-    }
-    x = (uint64_t(L) << half) | R;
-  } while (x >= n);
-  return int64_t(x);
-}
-
-// ---------------------------------------------------------------------------------------
 // sample: gather + relabel + reward, 128 samples per CTA staged through shared memory so
 // both the row gathers (16 B vectors, 13 per Push row) and the five output streams are
 // coalesced.
@@ -184,13 +112,6 @@ __device__ __forceinline__ void write_field(float *__restrict__ out, const float
   }
 }
 
-// totals by value: the host mirrors the deque counters (and counts the device-stream draws), so no thread waits
-// on a header load before it can compute anything
-struct SampleScalars {
-  int64_t total_entries, len;
-  unsigned long long draw_epoch;
-};
-
 template <bool VEC, int SPB>
 __global__ void __launch_bounds__(kSampleThreads)
 her_sample_kernel(const __grid_constant__ HerGeom g, const SampleScalars sc, int64_t B, const int64_t *__restrict__ idx,
@@ -204,41 +125,11 @@ her_sample_kernel(const __grid_constant__ HerGeom g, const SampleScalars sc, int
   const int64_t base = int64_t(blockIdx.x) * SPB;
   const int n = int(min(int64_t(SPB), B - base));
 
-  // ---- round trip 1: deque position -> bucket record -> (episode, t, j) -> ring slot ------------------
-  uint32_t j = 0, ep0 = 0;
-  uint32_t futw = 0;
+  // ---- round trip 1: deque position -> bucket record -> (episode, t, j) -> ring slot (her_device.cuh) ----
+  SampleRef ref{0u, 0u, 0u, 0u};
   if (tid < n) {
-    int64_t p;
-    if (idx != nullptr) {
-      p = idx[base + tid];
-      p = p < 0 ? 0 : (p >= sc.len ? sc.len - 1 : p);
-    } else {
-      p = feistel_position(uint64_t(base + tid), uint64_t(sc.len), g.seed, sc.draw_epoch);
-    }
-    if (idx_out != nullptr) idx_out[base + tid] = p;
-    const int64_t ge = sc.total_entries - sc.len + p;  // global entry id
-    const int4 *bp = reinterpret_cast<const int4 *>(g.buckets + ((ge >> kBucketShift) & g.bucket_mask));
-    const int4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
-    int64_t entry_start = (int64_t(uint32_t(b0.y)) << 32) | uint32_t(b0.x);
-    uint32_t tr_slot = uint32_t(b0.z), T = uint32_t(b0.w);
-    int64_t eid = (int64_t(uint32_t(b1.y)) << 32) | uint32_t(b1.x);
-    // the bucket's episode holds entry (bucket << 6); the position may belong to a later one (an episode of 50
-    // steps spans 246 entries = ~4 buckets, so usually it does not): walk forward over the episode records
-    while (ge >= entry_start + int64_t(T - 1) * (g.K + 1) + 1) {
-      ++eid;
-      const EpRec r2 = g.eps[eid & g.ep_mask];
-      entry_start = r2.entry_start; tr_slot = r2.tr_slot; T = r2.T;
-    }
-    const uint32_t o = uint32_t(ge - entry_start);
-    uint32_t t = g.div_k1.div(o);
-    j = o - t * uint32_t(g.K + 1);
-    if (t >= T - 1) { t = T - 1; j = 0; }  // last step carries no relabels
-    uint32_t slot = tr_slot + t;
-    if (slot >= g.cap_tr) slot -= g.cap_tr;
-    m_row[tid] = slot;
-    ep0 = tr_slot;
-    // ---- round trip 2 (with the row gather below): the 4 future offsets that contain this relabel's
-    if (j > 0) futw = __ldg(reinterpret_cast<const uint32_t *>(g.rows + size_t(slot) * g.row_f + g.off_fut) + ((j - 1) >> 2));
+    ref = her_resolve(g, sc, base + tid, idx, idx_out);
+    m_row[tid] = ref.slot;
   }
   __syncthreads();
 
@@ -268,10 +159,8 @@ her_sample_kernel(const __grid_constant__ HerGeom g, const SampleScalars sc, int
   // ---- round trip 3: the future achieved goal (issued before the barrier: it overlaps the tail of the gather)
   float gf[4] = {0.f, 0.f, 0.f, 0.f};
   const float *agf = nullptr;
-  if (tid < n && j > 0) {
-    uint32_t fs = ep0 + ((futw >> (8 * ((j - 1) & 3))) & 0xffu);
-    if (fs >= g.cap_tr) fs -= g.cap_tr;
-    agf = g.ag + size_t(fs) * g.gpad;
+  if (tid < n && ref.j > 0) {
+    agf = g.ag + size_t(her_future_slot(g, ref)) * g.gpad;
     if (g.G <= 4) {
       const float4 v = __ldg(reinterpret_cast<const float4 *>(agf));
       gf[0] = v.x; gf[1] = v.y; gf[2] = v.z; gf[3] = v.w;
@@ -280,23 +169,26 @@ her_sample_kernel(const __grid_constant__ HerGeom g, const SampleScalars sc, int
   __syncthreads();
 
   // ---- relabel + sparse reward (bit-exact fp32, no FMA) --------------------------------------------------
-  if (tid < n && j > 0) {
+  if (tid < n && ref.j > 0) {
     float *row = tile + tid * g.row_f;
-    float acc = 0.f;
-    for (int c = 0; c < g.G; ++c) {
-      const float gfc = g.G <= 4 ? gf[c] : __ldg(agf + c);
-      const float diff = __fsub_rn(row[g.off_ag + c], gfc);    // achieved(t) - future goal
-      const float sq = __fmul_rn(diff, diff);
-      acc = (c == 0) ? sq : __fadd_rn(acc, sq);                // left-to-right, no FMA
-      row[g.D - g.G + c] = gfc;
-      row[g.off_ns + g.D - g.G + c] = gfc;
+    if (g.G <= 4) {
+      her_relabel_row(g, row, gf);
+    } else {                       // wide goals: the future goal is staged behind the (already consumed) future offsets
+      float *tmp = row + g.off_fut;
+      float acc = 0.f;
+      for (int c = 0; c < g.G; ++c) {
+        const float gfc = __ldg(agf + c);
+        const float diff = __fsub_rn(row[g.off_ag + c], gfc);
+        const float sq = __fmul_rn(diff, diff);
+        acc = (c == 0) ? sq : __fadd_rn(acc, sq);
+        row[g.D - g.G + c] = gfc;
+        row[g.off_ns + g.D - g.G + c] = gfc;
+      }
+      (void)tmp;
+      const float dist = __fsqrt_rn(acc);
+      reinterpret_cast<uint32_t *>(row)[g.off_r] = 0x80000000u | ((dist > g.threshold) ? 0x3F800000u : 0u);
+      row[g.off_d] = 0.0f;
     }
-    const float dist = __fsqrt_rn(acc);
-    // -(d > threshold) as float32: -1.0f, or -0.0f with the SIGN BIT SET on success
-    // (-np.array(False, float32)).  Written as an INTEGER word: with a float-typed select
-    // nvcc 12.9 rewrites {-1.0f, -0.0f} into int->float(-(int)pred), which yields +0.0f.
-    reinterpret_cast<uint32_t *>(row)[g.off_r] = 0x80000000u | ((dist > g.threshold) ? 0x3F800000u : 0u);
-    row[g.off_d] = 0.0f;                                        // new_done = False
   }
   __syncthreads();
 
@@ -340,6 +232,20 @@ struct gcrl_her {
   int64_t len() const { return std::min(total_entries, max_entries); }
 };
 
+namespace gcrl {
+SampleScalars her_next_scalars(gcrl_her *h, bool positions_given) {
+  SampleScalars sc;
+  sc.total_entries = h->total_entries;
+  sc.len = h->len();
+  sc.draw_epoch = h->draw_epoch;
+  sc.use_idx = positions_given ? 1 : 0;
+  if (!positions_given) h->draw_epoch += 1;     // device index stream: one epoch per draw
+  return sc;
+}
+const HerGeom &her_geom(const gcrl_her *h) { return h->g; }
+int64_t her_len(const gcrl_her *h) { return h->len(); }
+}  // namespace gcrl
+
 static constexpr int kSmallTile = 32;      // samples per CTA while the batch is too small to fill the SMs with 128
 static size_t sample_smem(const gcrl_her *h, int spb) { return size_t(spb) * h->g.row_f * 4 + size_t(spb) * 4; }
 
@@ -347,11 +253,7 @@ static void her_launch_sample(gcrl_her *h, int64_t B, const int64_t *idx_dev, fl
                               float *r, float *ns, float *d, int64_t *idx_out, cudaStream_t st) {
   auto aligned = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
   const bool vec = aligned(s) && aligned(a) && aligned(r) && aligned(ns) && aligned(d);
-  SampleScalars sc;
-  sc.total_entries = h->total_entries;
-  sc.len = h->len();
-  sc.draw_epoch = h->draw_epoch;
-  if (idx_dev == nullptr) h->draw_epoch += 1;
+  const SampleScalars sc = her_next_scalars(h, idx_dev != nullptr);
   // small batches: 32 samples per CTA (4x the CTAs, each row gather a single round of loads)
   const bool small = B <= int64_t(sm_count()) * 4 * kSmallTile;
   const int spb = small ? kSmallTile : kSamplesPerBlock;

@@ -3,6 +3,7 @@
 // of 4 floats and the base 16-byte aligned; logical sizes are arbitrary.
 #pragma once
 #include "common.cuh"
+#include "her_device.cuh"
 
 namespace gcrl {
 
@@ -128,6 +129,14 @@ struct FusedCriticArgs {
   const float *is_w;            // prioritised replay: per-sample importance weight of the loss (nullptr: 1)
   float *td_out;                // prioritised replay: per-sample TD error [B] (max with q_other's), or nullptr
   const float *s, *a, *r, *ns, *d;   // dense batch
+  // sample != 0: the kernel draws the batch itself from the HER episode store (her_device.cuh: position ->
+  // episode -> packed row + future goal -> relabel + reward, per slab) and leaves the dense batch in bs .. bd
+  // for the actor phase; one launch and one pass over the batch less than a separate sampler
+  int sample;
+  HerGeom geom;
+  const SampleScalars *sample_sc;    // totals / draw epoch of this update (device struct, written by the host)
+  const int64_t *sample_idx;         // positions (host index stream), used when sample_sc->use_idx
+  float *bs, *ba, *br, *bns, *bd;    // dense batch out
   int B, D, A, H, L, ldh, ldc;
   float gamma, y_lo; int clamp_y;
   float *sa_out;                // [B][ldc]  = [s | a | 0] rows (layer-1 wgrad operand)
@@ -146,6 +155,7 @@ struct FusedActorArgs {
   float *metric_partials;
 };
 bool fused_supported(int B, int D, int A, int H, int L);
+bool fused_sample_supported(const HerGeom &g);
 int launch_fused_critic(const FusedCriticArgs &a, cudaStream_t st);   // returns the grid (metric slabs)
 int launch_fused_actor(const FusedActorArgs &a, cudaStream_t st);
 
