@@ -852,10 +852,10 @@ def gpu_main(args):
         for batch in [B] + sweep_batches + ([1 << 20] if sweep_batches else []):
             ms_k = time_sampler(batch, 50 if batch <= 65536 else 20)
             ach = batch * alg_bytes / (ms_k * 1e-3) / 1e9
-            # DRAM bytes per launch from `ncu --set full` at the bench shape (profiles/r01j_ncu_full_sampler_*_raw.csv:
-            # dram__bytes_read.sum + dram__bytes_write.sum; 208-byte rows and 16-byte goal rows against 64-byte DRAM
-            # bursts, the writes of the small batches are absorbed by L2)
-            ncu_traffic = {65536: 25.94e6 + 0.04e6, 1 << 20: 305.4e6 + 140.6e6}
+            # DRAM bytes per launch from `ncu --set full` at the bench shape (profiles/r02_sampler_*_ncu_full_raw.csv:
+            # dram__bytes_read.sum + dram__bytes_write.sum; 208-byte rows, 16-byte goal rows and 32-byte bucket
+            # records against 64-byte DRAM bursts, the writes of the small batches are absorbed by L2)
+            ncu_traffic = {65536: 27.69e6 + 0.06e6, 1 << 20: 304.31e6 + 145.9e6}   # profiles/r02_sampler_*_ncu_full_raw.csv
             rooflines[f"her_sample_kernel_B{batch}"] = {
                 "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                 "traffic": ncu_traffic.get(batch) if (O, G, A, k) == (18, 3, 3, 4) else None,
@@ -913,15 +913,28 @@ def gpu_main(args):
             # gradients through the (L - 1) hidden layers
             fl = 2.0 * B * (amac + 2 * cmac + (Ll - 1) * Hh * Hh + Hh)
             ach = fl / (msk.value * 1e-3) / 1e12
-            # DRAM bytes per launch from the one `ncu --set full` capture of this kernel at the bench shape
-            # (profiles/r01i_ncu_full_fused_B256_raw.csv, fused_critic_kernel<2,0,0>: dram__bytes_read.sum 5.46 MB +
-            # write 0.014 MB; the three networks are 1.65 MB -- 128 CTAs stream them through a cold L2 under ncu)
-            traffic = 5.47e6 if (B, Hh, Ll, D, A) == (256, 256, 3, 21, 3) else None
+            # DRAM bytes per launch from the `ncu --set full` capture of this kernel at the bench shape
+            # (profiles/r02_update_B256_ncu_full_raw.csv, fused_critic_kernel<2,0,0>: dram__bytes_read.sum 6.71 MB +
+            # write 0.01 MB: the three networks (1.65 MB) through a cold L2 under ncu, plus the in-kernel row gather)
+            traffic = 6.72e6 if (B, Hh, Ll, D, A) == (256, 256, 3, 21, 3) else None
+            sm_hz = float(clk.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)) * 1e6
+            fp32_peak = 148 * 128 * 2 * sm_hz / 1e12
+            # what actually bounds the row-slab kernels (profiles/README.md, round 2): every CTA streams ALL the
+            # weights of the phase through its SM's unified L1 / shared-memory array, which moves 128 B per clock and
+            # sees every byte twice (fill + read): a 256 x 256 fp32 layer cannot take less than 2.1 us per SM,
+            # whatever the load path (per-thread LDG, cp.async.bulk ring, software pipelining all measure 2.1-2.2 us)
+            wbytes = 4.0 * (amac + 2 * cmac + (Ll - 1) * Hh * Hh)
+            port_ms = 2.0 * wbytes / (128.0 * sm_hz) * 1e3
             rooflines[f"fused_critic_kernel_B{B}"] = {
                 "bound": "tensor", "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
                 "traffic": traffic, "ms_per_launch": msk.value, "algorithmic_flops_per_launch": fl,
-                "note": "fp32 FFMA row-slab kernel (weights streamed from L2 once per 2-row slab); latency-bound "
-                        "at this batch -- the tensor-core path serves batches >= 2048"}
+                "pipe": "fp32 FFMA (no MMA is issued below 2048 rows; `bound`/`peak` follow the contract's bf16 "
+                        "tensor denominator, the fractions below are the honest ones)",
+                "frac_fp32_pipe": ach / fp32_peak, "fp32_peak_tflops": fp32_peak,
+                "sram_port_bound_ms": port_ms, "frac_sram_port": port_ms / msk.value,
+                "note": "row-slab kernel: each of the 128 CTAs carries 2 batch rows through every layer of the phase; "
+                        "bound by the per-SM L1/shared-memory port (every weight byte crosses it twice), not by "
+                        "FMA issue or HBM -- the tensor-core path serves batches >= 2048"}
         except Exception as e:   # noqa: BLE001
             log(f"[roofline] critic kernel timing skipped: {e}")
         if sweep_batches:

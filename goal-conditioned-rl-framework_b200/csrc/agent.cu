@@ -10,6 +10,8 @@
 // rows (sa, nsa, spi) fold torch.cat: the actor heads write their tanh output straight into
 // the action columns.  An update is captured once per (batch, flags) into a CUDA graph and
 // replayed; per-step scalars (lr / bias corrections) travel through a small device struct.
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -138,6 +140,10 @@ struct gcrl_agent {
   StepScalars *d_scalars = nullptr;        // StepScalars, then the SampleScalars of the update (one H2D copy)
   SampleScalars *d_sample_sc = nullptr;
   int64_t *d_idx = nullptr;                // positions of the in-kernel sampler (host index stream) [maxB]
+  float *h_pub = nullptr, *d_pub = nullptr; // mapped host memory the last optimiser kernel publishes the metrics to
+  unsigned int pub_seq = 0;                // sequence number of the most recent update
+  bool pub_valid = false;                  // ... and whether that update publishes (whole-update launches only)
+  bool publish_now = false;                // capture-time: the optimiser step being recorded is the update's last
   gcrl_her *sample_buf = nullptr;          // the update being issued draws its batch inside the critic kernel
   SampleScalars sample_sc{};
   PinnedRing scal_stage;
@@ -275,6 +281,11 @@ void adam_step(gcrl_agent *ag, Net &n, int which, float max_norm, int slot_norm,
   a.metrics = ag->p2p.on ? ag->p2p.metrics_avg : ag->metrics;   // the norm of the averaged gradient is global already
   a.slot_norm = slot_norm;
   a.tmap = n.tmap; a.pT = n.pT; a.targetT = target ? target->pT : nullptr;
+  if (ag->publish_now) {
+    a.publish = ag->d_pub;
+    a.publish_src = a.metrics;
+    a.publish_err = ag->p2p.on ? ag->p2p.err : nullptr;
+  }
   launch_adam(a, st);
 }
 
@@ -582,7 +593,6 @@ void write_scalars(gcrl_agent *ag, double lr_c, double lr_a, bool actor_steps, c
     out[0] = float(lr / bc1);
     out[1] = float(std::sqrt(bc2));
     out[2] = float(1.0 - lr * double(ag->cfg.weight_decay));
-    out[3] = 0.f;
   };
   int slot;
   constexpr size_t kScalBytes = sizeof(StepScalars) + sizeof(SampleScalars);
@@ -593,6 +603,8 @@ void write_scalars(gcrl_agent *ag, double lr_c, double lr_a, bool actor_steps, c
   fill(ag->net[CRITIC1].adam_t, lr_c, &sc->step_size_c);
   if (actor_steps) ag->net[ACTOR].adam_t += 1;
   fill(std::max(1, ag->net[ACTOR].adam_t), lr_a, &sc->step_size_a);
+  sc->pad1 = 0.f;
+  sc->seq = ++ag->pub_seq;
   GCRL_CUDA(cudaMemcpyAsync(ag->d_scalars, sc, kScalBytes, cudaMemcpyHostToDevice, st));
   ag->scal_stage.release(slot, st);
 }
@@ -624,19 +636,33 @@ enum : int { PH_CGRAD = 1, PH_CSTEP = 2, PH_AGRAD = 4, PH_ASTEP = 8, PH_ALL = 15
 void run_update_body(gcrl_agent *ag, int B, const float *noise, int flags, int mask, cudaStream_t st) {
   const bool dp = mask != PH_ALL;
   if (mask & PH_CGRAD) {
+    GCRL_NVTX("gcrl: critic phase (targets, loss, backward, weight gradients)");
     critic_phase_grads(ag, B, noise, st);
     if (ag->td3 && dp) critic2_phase_grads(ag, B, st);
   }
+  const bool actor_steps = (flags & 1) != 0;
   if (mask & PH_CSTEP) {
+    GCRL_NVTX("gcrl: critic step (average, clip, Adam, Polyak)");
     ddpg_actor_target_polyak(ag, flags, st);
+    ag->publish_now = !dp && !actor_steps && !ag->td3;
     critic_phase_step(ag, 0, flags, dp, st);
     if (ag->td3) {
       if (!dp) critic2_phase_grads(ag, B, st);
+      ag->publish_now = !dp && !actor_steps;
       critic_phase_step(ag, 1, flags, dp, st);
     }
+    ag->publish_now = false;
   }
-  if ((mask & PH_AGRAD) && (flags & 1)) actor_phase_grads(ag, B, st);
-  if ((mask & PH_ASTEP) && (flags & 1)) actor_phase_step(ag, dp, st);
+  if ((mask & PH_AGRAD) && (flags & 1)) {
+    GCRL_NVTX("gcrl: actor phase (policy, Q, backward, weight gradients)");
+    actor_phase_grads(ag, B, st);
+  }
+  if ((mask & PH_ASTEP) && (flags & 1)) {
+    GCRL_NVTX("gcrl: actor step (average, clip, Adam, Polyak)");
+    ag->publish_now = !dp;
+    actor_phase_step(ag, dp, st);
+    ag->publish_now = false;
+  }
 }
 
 // Replay (or capture on first use) the graph of (B, flags, phase mask).  TD3 noise pointers vary
@@ -749,15 +775,40 @@ void ensure_io(gcrl_agent *ag, size_t floats, cudaStream_t st) {
 
 void finish_metrics(gcrl_agent *ag, float *metrics_host, cudaStream_t st) {
   if (metrics_host == nullptr) return;
+  auto dp_error = [](int err) {
+    return Error(GCRL_ERR_CUDA, "data-parallel barrier timed out: rank " + std::to_string((err - 1) / 16) +
+                                    " never saw the flag of rank " + std::to_string((err - 1) % 16));
+  };
+  if (ag->pub_valid) {
+    // the update's last optimiser kernel wrote the metrics and then its sequence number into mapped host memory:
+    // poll that word (no D2H copy, no stream synchronisation, no driver call on the critical path)
+    volatile unsigned int *seq = reinterpret_cast<volatile unsigned int *>(ag->h_pub) + 8;
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned long spins = 0;
+    while (*seq != ag->pub_seq) {
+      if ((++spins & 0xFFFF) == 0) {
+        if (cudaStreamQuery(st) != cudaErrorNotReady) {       // finished (or failed) without publishing this number
+          GCRL_CUDA(cudaStreamSynchronize(st));
+          if (*seq == ag->pub_seq) break;
+          throw Error(GCRL_ERR_CUDA, "the update finished without publishing its metrics");
+        }
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120))
+          throw Error(GCRL_ERR_CUDA, "timed out waiting for the update's metrics");
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    std::memcpy(metrics_host, ag->h_pub, 8 * sizeof(float));
+    const int err = reinterpret_cast<const int *>(ag->h_pub)[9];
+    if (err) throw dp_error(err);
+    return;
+  }
   GCRL_CUDA(cudaMemcpyAsync(metrics_host, ag->p2p.on ? ag->p2p.metrics_avg : ag->metrics, 8 * sizeof(float),
                             cudaMemcpyDeviceToHost, st));
   GCRL_CUDA(cudaStreamSynchronize(st));
   if (ag->p2p.on) {
     int err = 0;
     GCRL_CUDA(cudaMemcpy(&err, ag->p2p.err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (err)
-      throw Error(GCRL_ERR_CUDA, "data-parallel barrier timed out: rank " + std::to_string((err - 1) / 16) +
-                                     " never saw the flag of rank " + std::to_string((err - 1) % 16));
+    if (err) throw dp_error(err);
   }
 }
 
@@ -835,6 +886,9 @@ int gcrl_agent_create(gcrl_agent **out, int device, const gcrl_agent_config *cfg
     ag->d_scalars = reinterpret_cast<StepScalars *>(dev_alloc<char>(sizeof(StepScalars) + sizeof(SampleScalars)));
     ag->d_sample_sc = reinterpret_cast<SampleScalars *>(ag->d_scalars + 1);
     ag->d_idx = dev_alloc<int64_t>(size_t(mb));
+    GCRL_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ag->h_pub), 64, cudaHostAllocMapped));
+    std::memset(ag->h_pub, 0, 64);
+    GCRL_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&ag->d_pub), ag->h_pub, 0));
     const char *nfs = getenv("GCRL_B200_NO_FUSED_SAMPLER");
     ag->fuse_sampler = !(nfs && nfs[0] == '1');
     ag->scal_stage.init(256);
@@ -875,6 +929,7 @@ int gcrl_agent_destroy(gcrl_agent *ag) {
   for (float *p : ag->dzl) cudaFree(p);
   cudaFree(ag->d_scalars);
   cudaFree(ag->d_idx);
+  if (ag->h_pub) cudaFreeHost(ag->h_pub);
   if (ag->cap_stream) cudaStreamDestroy(ag->cap_stream);
   ag->scal_stage.destroy();
   ag->io_stage.destroy();
@@ -1028,6 +1083,7 @@ int gcrl_agent_update_batch(gcrl_agent *ag, int64_t B, const float *s_dev, const
                             const float *noise_dev, double lr_critic, double lr_actor, int flags,
                             float *metrics_host, void *stream) {
   GCRL_API_BEGIN
+  GCRL_NVTX("gcrl_agent_update_batch");
   require_handle(ag);
   check_batch(ag, B);
   GCRL_CUDA(cudaSetDevice(ag->device));
@@ -1038,6 +1094,7 @@ int gcrl_agent_update_batch(gcrl_agent *ag, int64_t B, const float *s_dev, const
   ingest(ag, nullptr, B, nullptr, s_dev, a_dev, r_dev, ns_dev, d_dev, noise_dev, &noise, st);
   write_scalars(ag, lr_critic, lr_actor, (flags & 1) != 0, st);
   run_update(ag, int(B), noise, flags, PH_ALL, st);
+  ag->pub_valid = true;
   guard.commit();
   finish_metrics(ag, metrics_host, st);
   GCRL_API_END
@@ -1047,6 +1104,7 @@ int gcrl_agent_update_from_buffer(gcrl_agent *ag, gcrl_her *buf, int64_t B, cons
                                   const float *noise_dev, double lr_critic, double lr_actor, int flags,
                                   float *metrics_host, void *stream) {
   GCRL_API_BEGIN
+  GCRL_NVTX("gcrl_agent_update_from_buffer");
   require_handle(ag);
   check_batch(ag, B);
   GCRL_REQUIRE(buf != nullptr, "buffer handle is NULL");
@@ -1058,6 +1116,7 @@ int gcrl_agent_update_from_buffer(gcrl_agent *ag, gcrl_her *buf, int64_t B, cons
   ingest(ag, buf, B, idx_host, nullptr, nullptr, nullptr, nullptr, nullptr, noise_dev, &noise, st);
   write_scalars(ag, lr_critic, lr_actor, (flags & 1) != 0, st);
   run_update(ag, int(B), noise, flags, PH_ALL, st);
+  ag->pub_valid = true;
   guard.commit();
   finish_metrics(ag, metrics_host, st);
   GCRL_API_END
@@ -1074,6 +1133,7 @@ int gcrl_agent_read_metrics(gcrl_agent *ag, float *metrics_host, void *stream) {
 
 int gcrl_agent_act(gcrl_agent *ag, int64_t n, const float *obs_host, float *act_host, void *stream) {
   GCRL_API_BEGIN
+  GCRL_NVTX("gcrl_agent_act");
   require_handle(ag);
   check_batch(ag, n);
   GCRL_REQUIRE(obs_host && act_host, "NULL argument");
@@ -1131,6 +1191,7 @@ int gcrl_agent_update_phase(gcrl_agent *ag, int phase, gcrl_her *buf, int64_t B,
                             const float *d_dev, const float *noise_dev, double lr_critic, double lr_actor,
                             int flags, void *stream) {
   GCRL_API_BEGIN
+  GCRL_NVTX("gcrl_agent_update_phase");
   require_handle(ag);
   check_batch(ag, B);
   GCRL_REQUIRE(phase >= 0 && phase <= 3, "phase must be 0..3");
@@ -1145,6 +1206,7 @@ int gcrl_agent_update_phase(gcrl_agent *ag, int phase, gcrl_her *buf, int64_t B,
     ag->dp_B = int(B);
     ag->dp_flags = flags;
     run_update(ag, int(B), noise, flags, PH_CGRAD, st);
+    ag->pub_valid = false;                 // phase-cut update: metrics through the D2H copy
     guard.commit();
   } else {
     GCRL_REQUIRE(ag->dp_B == int(B) && ag->dp_flags == flags, "phase 1..3 must follow phase 0 of the same update");

@@ -1,6 +1,7 @@
 // Shared helpers for the gcrl_b200 CUDA library (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 
 #include <stdexcept>
@@ -50,6 +51,17 @@ void set_last_error(const std::string &m);
   return GCRL_OK;
 
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// NVTX range over a host-side phase of the hot path (header-only NVTX3: a no-op unless a profiler is attached).
+// The ranges sit on the C-ABI entry points and on the phases inside an update while it is being captured; graph
+// replays show up as the enclosing entry-point range.
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange &) = delete;
+  NvtxRange &operator=(const NvtxRange &) = delete;
+};
+#define GCRL_NVTX(name) ::gcrl::NvtxRange _gcrl_nvtx_range_(name)
 
 // number of SMs of the current device (148 on B200), cached per process
 int sm_count();

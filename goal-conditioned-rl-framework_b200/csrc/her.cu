@@ -402,6 +402,7 @@ int gcrl_her_push_episode(gcrl_her *h, int T, const float *s, const float *a, co
                           const float *r, const float *d, const float *ag, const uint8_t *fut,
                           void *stream) {
   GCRL_API_BEGIN
+  GCRL_NVTX("gcrl_her_push_episode");
   GCRL_REQUIRE(h != nullptr, "handle is NULL");
   GCRL_REQUIRE(T >= 1 && T <= 255, "episode length must be in [1, 255]");
   GCRL_REQUIRE(s && a && ns && r && d && ag, "NULL episode array");
@@ -556,6 +557,7 @@ int gcrl_her_sample(gcrl_her *h, int64_t B, const int64_t *idx_host, float *stat
                     float *actions_dev, float *rewards_dev, float *next_states_dev,
                     float *dones_dev, int64_t *idx_out_dev, void *stream) {
   GCRL_API_BEGIN
+  GCRL_NVTX("gcrl_her_sample");
   GCRL_REQUIRE(h != nullptr, "handle is NULL");
   GCRL_REQUIRE(B == 0 || (states_dev && actions_dev && rewards_dev && next_states_dev && dones_dev),
                "NULL output");
@@ -582,6 +584,7 @@ int gcrl_her_sample_host(gcrl_her *h, int64_t B, const int64_t *idx_host, float 
                          float *actions, float *rewards, float *next_states, float *dones,
                          int64_t *idx_out, void *stream) {
   GCRL_API_BEGIN
+  GCRL_NVTX("gcrl_her_sample_host");
   GCRL_REQUIRE(h != nullptr, "handle is NULL");
   GCRL_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = as_stream(stream);

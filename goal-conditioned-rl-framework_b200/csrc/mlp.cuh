@@ -193,7 +193,8 @@ void launch_reduce_grads(const ReduceArgs &a, cudaStream_t st);
 
 struct StepScalars {       // written by the host before every update (device copy)
   // per optimiser: lr / (1 - b1^t), sqrt(1 - b2^t), 1 - lr * weight_decay, unused
-  float step_size_c, bc2_sqrt_c, decay_c, pad0;
+  float step_size_c, bc2_sqrt_c, decay_c;
+  unsigned int seq;        // update counter: the last optimiser kernel publishes it with the metrics (AdamArgs::publish)
   float step_size_a, bc2_sqrt_a, decay_a, pad1;
 };
 struct AdamArgs {
@@ -207,6 +208,12 @@ struct AdamArgs {
   // transposed weight copies kept in step with p / target (fused.cu's forward operand)
   const int *tmap;         // [n] index into pT, or -1 (bias / padding)
   float *pT, *targetT;
+  // last optimiser kernel of an update: copy the 8 metrics (+ the data-parallel watchdog word) into MAPPED host
+  // memory and then the update's sequence number -- the host polls that word instead of paying a D2H copy and a
+  // stream synchronisation per update()
+  float *publish;          // mapped host: float[8] metrics, uint32 seq, int32 err  (nullptr: do not publish)
+  const float *publish_src;
+  const int *publish_err;
 };
 void launch_adam(const AdamArgs &a, cudaStream_t st);
 // data-parallel averaging over NVLink peer memory (optim.cu)

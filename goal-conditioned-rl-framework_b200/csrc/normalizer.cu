@@ -353,6 +353,7 @@ int gcrl_norm_destroy(gcrl_norm *h) {
 
 int gcrl_norm_update(gcrl_norm *h, const void *x_host, int64_t n, int is_f64, void *stream) {
   GCRL_API_BEGIN
+  GCRL_NVTX("gcrl_norm_update");
   GCRL_REQUIRE(h != nullptr && (x_host != nullptr || n == 0) && n >= 0, "bad arguments");
   GCRL_CUDA(cudaSetDevice(h->device));
   if (n == 0) return GCRL_OK;
@@ -411,6 +412,7 @@ int gcrl_norm_update_moments(gcrl_norm *h, const double *moments_host, int parts
 
 int gcrl_norm_update_dev(gcrl_norm *h, const void *x_dev, int64_t n, int is_f64, void *stream) {
   GCRL_API_BEGIN
+  GCRL_NVTX("gcrl_norm_update_dev");
   GCRL_REQUIRE(h != nullptr && (x_dev != nullptr || n == 0) && n >= 0, "bad arguments");
   GCRL_CUDA(cudaSetDevice(h->device));
   norm_update_device(h, x_dev, n, is_f64, as_stream(stream));
@@ -420,6 +422,7 @@ int gcrl_norm_update_dev(gcrl_norm *h, const void *x_dev, int64_t n, int is_f64,
 int gcrl_norm_apply(gcrl_norm *h, const void *x_host, int64_t n, int is_f64, double *out_host,
                     void *stream) {
   GCRL_API_BEGIN
+  GCRL_NVTX("gcrl_norm_apply");
   GCRL_REQUIRE(h != nullptr && n >= 0 && (n == 0 || (x_host && out_host)), "bad arguments");
   GCRL_CUDA(cudaSetDevice(h->device));
   if (n == 0) return GCRL_OK;
@@ -441,6 +444,7 @@ int gcrl_norm_apply(gcrl_norm *h, const void *x_host, int64_t n, int is_f64, dou
 int gcrl_norm_apply_dev_f32(gcrl_norm *h, const void *x_dev, int64_t n, int is_f64,
                             float *out_dev, int64_t out_stride, int64_t out_col0, void *stream) {
   GCRL_API_BEGIN
+  GCRL_NVTX("gcrl_norm_apply_dev_f32");
   GCRL_REQUIRE(h != nullptr && n >= 0 && (n == 0 || (x_dev && out_dev)), "bad arguments");
   GCRL_REQUIRE(out_stride >= h->dim + out_col0 && out_col0 >= 0, "bad output stride / column");
   GCRL_CUDA(cudaSetDevice(h->device));

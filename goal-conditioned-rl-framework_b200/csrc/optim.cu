@@ -308,8 +308,17 @@ __device__ __forceinline__ void adam_body(const AdamArgs &a) {
       if (tm >= 0) a.targetT[tm] = t;
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && a.metrics != nullptr && a.slot_norm >= 0)
-    a.metrics[a.slot_norm] = s_norm * coef;  // norm after clipping (src/agent.py:1332,:1300)
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const float post = s_norm * coef;         // norm after clipping (src/agent.py:1332,:1300)
+    if (a.metrics != nullptr && a.slot_norm >= 0) a.metrics[a.slot_norm] = post;
+    if (a.publish != nullptr) {
+      // every other slot was written by earlier kernels of this update; the norm slot just above by this thread
+      for (int i = 0; i < 8; ++i) a.publish[i] = (a.publish_src == a.metrics && i == a.slot_norm) ? post : __ldcg(a.publish_src + i);
+      reinterpret_cast<int *>(a.publish)[9] = a.publish_err != nullptr ? __ldcg(a.publish_err) : 0;
+      __threadfence_system();
+      reinterpret_cast<volatile unsigned int *>(a.publish)[8] = a.sc->seq;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kOptThreads) adam_kernel(AdamArgs a) { adam_body(a); }

@@ -1285,6 +1285,7 @@ int gcrl_sac_update_batch(gcrl_sac *ag, int64_t B, const float *s, const float *
                           const float *d, const float *eps_next, const float *eps_cur, double lr_c, double lr_a,
                           int flags, float *metrics_host, void *stream) {
   GCRL_API_BEGIN
+  GCRL_NVTX("gcrl_sac_update_batch");
   require_handle(ag);
   GCRL_REQUIRE(ag != nullptr, "agent handle is NULL");
   GCRL_CUDA(cudaSetDevice(ag->device));
@@ -1297,6 +1298,7 @@ int gcrl_sac_update_from_buffer(gcrl_sac *ag, gcrl_her *buf, int64_t B, const in
                                 const float *eps_next, const float *eps_cur, double lr_c, double lr_a, int flags,
                                 float *metrics_host, void *stream) {
   GCRL_API_BEGIN
+  GCRL_NVTX("gcrl_sac_update_from_buffer");
   require_handle(ag);
   GCRL_REQUIRE(ag != nullptr && buf != nullptr, "NULL handle");
   GCRL_CUDA(cudaSetDevice(ag->device));
@@ -1309,6 +1311,7 @@ int gcrl_sac_update_phase(gcrl_sac *ag, int phase, gcrl_her *buf, int64_t B, con
                           const float *a, const float *r, const float *ns, const float *d, const float *eps_next,
                           const float *eps_cur, double lr_c, double lr_a, int flags, void *stream) {
   GCRL_API_BEGIN
+  GCRL_NVTX("gcrl_sac_update_phase");
   require_handle(ag);
   GCRL_REQUIRE(ag != nullptr && phase >= 0 && phase <= 3, "NULL handle / phase outside 0..3");
   GCRL_CUDA(cudaSetDevice(ag->device));
