@@ -944,10 +944,18 @@ def gpu_main(args):
             bt = torch.zeros(Hh, device=dev)
             yt = torch.empty(Mt, Hh, device=dev)
 
+            whi, wlo = torch.empty_like(wt), torch.empty_like(wt)
+            check(lib.gcrl_split_tf32(local, vp(wt.data_ptr()), vp(whi.data_ptr()), vp(wlo.data_ptr()), wt.numel(), sp))
+
             def dense(engine):
-                check(lib.gcrl_dense_layer(local, engine, 0, Mt, Hh, Hh, vp(xt.data_ptr()), Hh, vp(wt.data_ptr()), Hh,
-                                           vp(bt.data_ptr()), None, 0, vp(yt.data_ptr()), Hh, sp))
-            for engine, name in ((1, "tc_dense_kernel"), (0, "gemm_kernel_fp32")):
+                if engine == 2:      # what the agents call: the weight operand pre-split once per optimiser step
+                    check(lib.gcrl_dense_layer_presplit(local, 0, Mt, Hh, Hh, vp(xt.data_ptr()), Hh, vp(whi.data_ptr()),
+                                                        vp(wlo.data_ptr()), Hh, vp(bt.data_ptr()), None, 0,
+                                                        vp(yt.data_ptr()), Hh, sp))
+                else:
+                    check(lib.gcrl_dense_layer(local, engine, 0, Mt, Hh, Hh, vp(xt.data_ptr()), Hh, vp(wt.data_ptr()), Hh,
+                                               vp(bt.data_ptr()), None, 0, vp(yt.data_ptr()), Hh, sp))
+            for engine, name in ((2, "tc_dense_kernel"), (1, "tc_dense_kernel_split_in_kernel"), (0, "gemm_kernel_fp32")):
                 try:
                     for _ in range(3):
                         dense(engine)
@@ -963,16 +971,18 @@ def gpu_main(args):
                     ach = fl / (ms_k * 1e-3) / 1e12
                     rooflines[f"{name}_M{Mt}_H{Hh}"] = {
                         "bound": "tensor", "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
-                        "traffic": (83.8e6 if (engine == 1 and Hh == 256) else None),   # ncu: 67.4 MB read + 16.4 MB written
+                        "traffic": (83.8e6 if (engine >= 1 and Hh == 256) else None),   # ncu (round 1): 67.4 MB read + 16.4 MB written
                         "ms_per_launch": ms_k, "algorithmic_flops_per_launch": fl,
-                        "tensor_pipe_tflops": (3.0 * ach if engine == 1 else None),
-                        "tensor_pipe_frac_of_tf32_rate": (3.0 * ach / (0.5 * bf16_peak) if engine == 1 else None),
+                        "tensor_pipe_tflops": (3.0 * ach if engine >= 1 else None),
+                        "tensor_pipe_frac_of_tf32_rate": (3.0 * ach / (0.5 * bf16_peak) if engine >= 1 else None),
                         "note": ("tcgen05 kind::tf32, 3 MMAs per product (hi/lo split) for fp32 accuracy: tensor-pipe "
-                                 "work is 3x the algorithmic flops; the TF32 rate is half the measured bf16 peak" if engine == 1 else
+                                 "work is 3x the algorithmic flops; the TF32 rate is half the measured bf16 peak; " +
+                                 ("weights pre-split once per optimiser step (the agents' path)" if engine == 2 else
+                                  "both operands split in shared memory (round-1 scheme, for comparison)") if engine >= 1 else
                                  "fp32 FFMA tiles (the precision-0 path), for comparison")}
                 except Exception as e:   # noqa: BLE001
                     log(f"[roofline] dense layer engine {engine} skipped: {e}")
-            del xt, wt, bt, yt
+            del xt, wt, bt, yt, whi, wlo
 
     sweep = {}
     for batch in sweep_batches:

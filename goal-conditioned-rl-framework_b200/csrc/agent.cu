@@ -49,6 +49,10 @@ struct Net {
   float *p = nullptr, *g = nullptr, *m = nullptr, *v = nullptr;
   float *pT = nullptr;
   int *tmap = nullptr;           // [total] -> index into pT, -1 for bias / padding
+  // TF32 hi / lo halves of p and pT (tensor-core engine: the weight operand arrives pre-split, tc_gemm.cu);
+  // refreshed after every optimiser / Polyak step of an update that uses that engine, lazily otherwise
+  float *p_hi = nullptr, *p_lo = nullptr, *pT_hi = nullptr, *pT_lo = nullptr;
+  bool split_stale = true;
   int adam_t = 0;
 
   void init(int in, int hid, int out, int layer_count, bool trainable) {
@@ -91,10 +95,21 @@ struct Net {
       GCRL_CUDA(cudaMemset(v, 0, size_t(total) * 4));
     }
   }
+  void alloc_split() {
+    if (p_hi != nullptr) return;
+    p_hi = dev_alloc<float>(total); p_lo = dev_alloc<float>(total);
+    pT_hi = dev_alloc<float>(total_t); pT_lo = dev_alloc<float>(total_t);
+  }
+  void split(cudaStream_t st) {
+    launch_split_tf32(p, p_hi, p_lo, total, st);
+    launch_split_tf32(pT, pT_hi, pT_lo, total_t, st);
+  }
   void destroy() {
     cudaFree(p);
     cudaFree(pT);
     cudaFree(tmap);
+    for (float *q : {p_hi, p_lo, pT_hi, pT_lo})
+      if (q) cudaFree(q);
     if (g) { cudaFree(g); cudaFree(m); cudaFree(v); }
   }
   const float *W(int l) const { return p + w_off[l]; }
@@ -156,6 +171,7 @@ struct gcrl_agent {
   float *per_w = nullptr, *per_td = nullptr;   // prioritised replay: importance weights in, TD errors out [maxB]
   bool per_on = false;                     // flags bit3 of the update being issued
   bool use_fused = true, fuse_sampler = true;
+  bool tc_update = false;                  // the update being recorded / issued runs on the tensor-core engine
   int dp_B = -1, dp_flags = -1;            // the update the data-parallel phases belong to
   // data-parallel averaging over NVLink peer memory (gcrl_agent_dp_connect)
   struct P2P {
@@ -189,6 +205,21 @@ bool use_tc(const gcrl_agent *ag, int B, int N, int K) {
   return ag->cfg.precision == 2 ? B >= 128 : (ag->cfg.precision == 1 && B >= kTcMinBatch);
 }
 
+// does an update / forward at this batch run its hidden layers on the tensor cores (pre-split weights needed)?
+bool engine_tc(const gcrl_agent *ag, int B) { return use_tc(ag, B, ag->H, (ag->H + 3) & ~3); }
+
+// the TF32 hi / lo copies of every network whose parameters changed since they were last split (eager, outside capture)
+void ensure_split(gcrl_agent *ag, cudaStream_t st) {
+  for (int i = 0; i < NUM_NETS; ++i)
+    if (ag->has[i] && ag->net[i].p_hi != nullptr && ag->net[i].split_stale) {
+      ag->net[i].split(st);
+      ag->net[i].split_stale = false;
+    }
+}
+void mark_split_stale(gcrl_agent *ag) {
+  for (int i = 0; i < NUM_NETS; ++i) ag->net[i].split_stale = true;
+}
+
 // ---- forward / backward building blocks ----------------------------------------------------
 // hidden stack: X[B, K0] -> acts.h[0..L-1]
 void forward_hidden(const gcrl_agent *ag, const Net &n, const float *X, int ldx, int K0, const Acts &acts,
@@ -199,7 +230,8 @@ void forward_hidden(const gcrl_agent *ag, const Net &n, const float *X, int ldx,
     // layer 0: the operand rows and the weight rows are zero-padded to ld, so the padded K is exact
     const int Kp = (K + 3) & ~3;
     if (use_tc(ag, B, ag->H, Kp))
-      launch_tc_dense(in, ldin, n.W(l), n.ldw[l], n.b(l), nullptr, 0, acts.h[l], ag->ldh, B, ag->H, Kp, 0, st);
+      launch_tc_dense(in, ldin, n.p_hi + n.w_off[l], n.ldw[l], n.b(l), nullptr, 0, acts.h[l], ag->ldh, B, ag->H, Kp, 0, st,
+                      n.p_lo + n.w_off[l]);
     else
       launch_linear_fwd(in, ldin, n.W(l), n.ldw[l], n.b(l), acts.h[l], ag->ldh, B, ag->H, K, ACT_LEAKY, st);
     in = acts.h[l];
@@ -229,8 +261,8 @@ void backward_hidden(gcrl_agent *ag, const Net &n, const float *X, int ldx, int 
     }
     if (l > 0) {
       if (use_tc(ag, B, ag->H, ag->H))   // dX = dZ Wt^T with the transposed weight copy as the K-major operand
-        launch_tc_dense(ag->dz[cur], ag->ldh, n.pT + n.t_off[l], n.ldt[l], nullptr, acts.h[l - 1], ag->ldh,
-                        ag->dz[cur ^ 1], ag->ldh, B, ag->H, ag->H, 1, st);
+        launch_tc_dense(ag->dz[cur], ag->ldh, n.pT_hi + n.t_off[l], n.ldt[l], nullptr, acts.h[l - 1], ag->ldh,
+                        ag->dz[cur ^ 1], ag->ldh, B, ag->H, ag->H, 1, st, n.pT_lo + n.t_off[l]);
       else
         launch_linear_dgrad(ag->dz[cur], ag->ldh, n.W(l), n.ldw[l], acts.h[l - 1], ag->ldh, ag->dz[cur ^ 1],
                             ag->ldh, B, ag->H, ag->H, st);
@@ -287,6 +319,10 @@ void adam_step(gcrl_agent *ag, Net &n, int which, float max_norm, int slot_norm,
     a.publish_err = ag->p2p.on ? ag->p2p.err : nullptr;
   }
   launch_adam(a, st);
+  if (ag->tc_update) {          // this update's later layers read the stepped weights through the tensor cores
+    n.split(st);
+    if (a.polyak) target->split(st);
+  }
 }
 
 // ---- phases ------------------------------------------------------------------------------------
@@ -530,9 +566,11 @@ void critic_phase_step(gcrl_agent *ag, int which, int flags, bool rereduce, cuda
 
 // DDPG: the actor target blends the PRE-step actor, before the actor step (:1397-1401)
 void ddpg_actor_target_polyak(gcrl_agent *ag, int flags, cudaStream_t st) {
-  if (!ag->td3 && (flags & 2))
+  if (!ag->td3 && (flags & 2)) {
     launch_polyak(ag->net[T_ACTOR].p, ag->net[ACTOR].p, ag->net[ACTOR].total, ag->cfg.tau,
                   float(1.0 - double(ag->cfg.tau)), ag->net[ACTOR].tmap, ag->net[T_ACTOR].pT, st);
+    if (ag->tc_update) ag->net[T_ACTOR].split(st);
+  }
 }
 
 void actor_phase_grads(gcrl_agent *ag, int B, cudaStream_t st) {
@@ -668,6 +706,9 @@ void run_update_body(gcrl_agent *ag, int B, const float *noise, int flags, int m
 // Replay (or capture on first use) the graph of (B, flags, phase mask).  TD3 noise pointers vary
 // per call, so the noise is first copied into an internal buffer by the caller.
 void run_update(gcrl_agent *ag, int B, const float *noise, int flags, int mask, cudaStream_t st) {
+  ag->tc_update = !fused_ok(ag, B) && engine_tc(ag, B);
+  if (ag->tc_update) ensure_split(ag, st);          // (the update itself re-splits what it steps)
+  else mark_split_stale(ag);                        // weights move without their split copies following
   if (!ag->use_graphs) {
     run_update_body(ag, B, noise, flags, mask, st);
     return;
@@ -896,7 +937,11 @@ int gcrl_agent_create(gcrl_agent **out, int device, const gcrl_agent_config *cfg
     const char *ng = getenv("GCRL_B200_NO_GRAPH");
     ag->use_graphs = !(ng && ng[0] == '1');
     ag->io_stage.init(size_t(1) << 16);
-    if (ag->cfg.precision >= 1) tc_dense_init();
+    if (ag->cfg.precision >= 1) {
+      tc_dense_init();
+      for (int i = 0; i < NUM_NETS; ++i)
+        if (ag->has[i]) ag->net[i].alloc_split();
+    }
   } catch (...) {
     delete ag;
     throw;
@@ -967,6 +1012,7 @@ int gcrl_agent_set_layer(gcrl_agent *ag, int net, int layer, const float *weight
   std::memcpy(&padded[size_t(o) * ld], bias_host, size_t(o) * 4);
   GCRL_CUDA(cudaMemcpyAsync(n.p + n.w_off[layer], padded.data(), padded.size() * 4, cudaMemcpyHostToDevice, st));
   launch_sync_transposed(n.p, n.pT, n.tmap, n.total, st);
+  n.split_stale = true;
   GCRL_CUDA(cudaStreamSynchronize(st));
   GCRL_API_END
 }
@@ -1059,6 +1105,7 @@ int gcrl_agent_hard_update(gcrl_agent *ag, void *stream) {
                                 cudaMemcpyDeviceToDevice, st));
       GCRL_CUDA(cudaMemcpyAsync(ag->net[pr[0]].pT, ag->net[pr[1]].pT, size_t(ag->net[pr[1]].total_t) * 4,
                                 cudaMemcpyDeviceToDevice, st));
+      ag->net[pr[0]].split_stale = true;
     }
   GCRL_API_END
 }
@@ -1144,6 +1191,7 @@ int gcrl_agent_act(gcrl_agent *ag, int64_t n, const float *obs_host, float *act_
   float *obs = stage_to_device(ag, obs_host, size_t(n) * D, 0, st);
   // uses the actor-phase scratch (spi / acts_actor): select_action never overlaps an update
   launch_pack_rows(obs, D, nullptr, A, ag->spi, ag->ldc, int(n), st);
+  if (engine_tc(ag, int(n))) ensure_split(ag, st);
   const Net &actor = ag->net[ACTOR];
   forward_hidden(ag, actor, ag->spi, ag->ldc, D, ag->acts_actor, int(n), st);
   float *out = ag->d_io + size_t(n) * D;
@@ -1167,6 +1215,7 @@ int gcrl_agent_q(gcrl_agent *ag, int64_t n, const float *obs_host, const float *
   float *obs = stage_to_device(ag, obs_host, size_t(n) * D, 0, st);
   float *act = stage_to_device(ag, act_host, size_t(n) * A, size_t(n) * D, st);
   launch_pack_rows(obs, D, act, A, ag->spi, ag->ldc, int(n), st);
+  if (engine_tc(ag, int(n))) ensure_split(ag, st);
   const Net &c = ag->net[CRITIC1];
   forward_hidden(ag, c, ag->spi, ag->ldc, D + A, ag->acts_c1, int(n), st);
   float *out = ag->d_io + size_t(n) * (D + A);

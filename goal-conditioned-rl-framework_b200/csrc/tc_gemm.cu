@@ -140,9 +140,14 @@ struct TcSmem {
   static constexpr int kBytes = STAGES * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/ + 4 * 32 * kStgLd * 4;
 };
 
-template <int BN>
+// PRESPLIT: the B operand (the layer's weights) arrives already split into TF32 hi / lo halves (two tensors, kept
+// next to the parameters and refreshed after every optimiser step): the producer loads both, the splitter warps only
+// handle the activation tile -- a third of the shared-memory passes they made over a stage, off the TMA -> MMA
+// critical path for 2/3 of the bytes.
+template <int BN, bool PRESPLIT>
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs a) {
+tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmB2, TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   using S = TcSmem<BN>;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -209,11 +214,12 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb = 0; kb < ti.nk; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(empty(s), ((it / STAGES) & 1) ^ 1);
-          mbar_expect_tx(full(s), S::kA + S::kB);
+          mbar_expect_tx(full(s), S::kA + (PRESPLIT ? 2 : 1) * S::kB);
           const uint32_t st = base + s * S::kStage;
           if (!wg) {
             tma_load_2d(st, &tmA, full(s), kb * BKF, ti.m0);
             tma_load_2d(st + 2 * S::kA, &tmB, full(s), kb * BKF, ti.n0);
+            if (PRESPLIT) tma_load_2d(st + 2 * S::kA + S::kB, &tmB2, full(s), kb * BKF, ti.n0);
           } else {
             // boxes of 16 batch rows x 32 features (128-byte swizzle, 32-byte atoms), one per 32-feature MN block
             const int r = ti.slab * a.rows_per_slab + kb * 16;
@@ -344,7 +350,7 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t st = base + s * S::kStage;
         // chunk c (16 bytes) of the stage: A chunks first (hi at st, lo at st + kA), then B chunks
         // (hi at st + 2 kA, lo at + kB).  All loads of a thread are issued before the first store.
-        constexpr int kChunksA = S::kA / 16, kChunks = (S::kA + S::kB) / 16;
+        constexpr int kChunksA = S::kA / 16, kChunks = PRESPLIT ? kChunksA : (S::kA + S::kB) / 16;
         constexpr int kPer = (kChunks + kSplitThreads - 1) / kSplitThreads;
         if (!(a.dbg & 1)) {
           float x[kPer][4];
@@ -452,18 +458,24 @@ template <int BN>
 void set_attr() {
   static bool attr_set = false;
   if (!attr_set) {
-    GCRL_CUDA(cudaFuncSetAttribute(tc_dense_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    GCRL_CUDA(cudaFuncSetAttribute(tc_dense_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   TcSmem<BN>::kBytes));
+    GCRL_CUDA(cudaFuncSetAttribute(tc_dense_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    TcSmem<BN>::kBytes));
     attr_set = true;
   }
 }
 
 template <int BN>
-void launch_bn(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcArgs &a, cudaStream_t st) {
+void launch_bn(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap *tmB2, const TcArgs &a,
+               cudaStream_t st) {
   set_attr<BN>();
   const int tiles = a.kind == 1 ? a.nslabs * a.n_tiles * a.k_tiles : a.m_tiles * a.n_tiles;
   const int grid = std::min(tiles, sm_count());
-  tc_dense_kernel<BN><<<grid, kTcThreads, TcSmem<BN>::kBytes, st>>>(tmA, tmB, a);
+  if (tmB2 != nullptr)
+    tc_dense_kernel<BN, true><<<grid, kTcThreads, TcSmem<BN>::kBytes, st>>>(tmA, tmB, *tmB2, a);
+  else
+    tc_dense_kernel<BN, false><<<grid, kTcThreads, TcSmem<BN>::kBytes, st>>>(tmA, tmB, tmB, a);
   GCRL_LAUNCHED();
 }
 
@@ -484,7 +496,8 @@ bool tc_dense_supported(int M, int N, int K) {
 // out[M, N] = epilogue( X[M, K] * W[N, K]^T )
 //   mode 0: leaky(. + bias)   mode 1: . * leaky'(act)   mode 2: . + bias
 void launch_tc_dense(const float *X, int ldx, const float *W, int ldw, const float *bias, const float *act,
-                     int ldact, float *out, int ldo, int M, int N, int K, int mode, cudaStream_t st) {
+                     int ldact, float *out, int ldo, int M, int N, int K, int mode, cudaStream_t st,
+                     const float *W_lo) {
   GCRL_REQUIRE(tc_dense_supported(M, N, K), "shape not supported by the tensor-core dense kernel");
   GCRL_REQUIRE((ldx % 4) == 0 && (ldw % 4) == 0 && (ldo % 4) == 0, "leading dimensions must be multiples of 4");
   // column tile: as wide as the layer when the row tiles alone fill the SMs (the activation tile is then
@@ -500,10 +513,30 @@ void launch_tc_dense(const float *X, int ldx, const float *W, int ldw, const flo
   a.n_tiles = (N + BN - 1) / BN;
   if (const char *e = getenv("GCRL_TC_DBG")) a.dbg = atoi(e);
   const CUtensorMap tmA = make_map(X, M, K, ldx, BM);
-  const CUtensorMap tmB = make_map(W, N, K, ldw, BN);
-  if (BN == 64) launch_bn<64>(tmA, tmB, a, st);
-  else if (BN == 128) launch_bn<128>(tmA, tmB, a, st);
-  else launch_bn<256>(tmA, tmB, a, st);
+  const CUtensorMap tmB = make_map(W, N, K, ldw, BN);          // W_lo given: W holds the TF32 hi halves
+  CUtensorMap tmB2;
+  if (W_lo != nullptr) tmB2 = make_map(W_lo, N, K, ldw, BN);
+  const CUtensorMap *p2 = W_lo != nullptr ? &tmB2 : nullptr;
+  if (BN == 64) launch_bn<64>(tmA, tmB, p2, a, st);
+  else if (BN == 128) launch_bn<128>(tmA, tmB, p2, a, st);
+  else launch_bn<256>(tmA, tmB, p2, a, st);
+}
+
+// hi = rna_tf32(x), lo = rna_tf32(x - hi): the halves the 3xTF32 product is built from
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict__ src, float *__restrict__ hi,
+                                                         float *__restrict__ lo, int n) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const float x = src[e];
+    const uint32_t h = rna_tf32(x);
+    hi[e] = __uint_as_float(h);
+    lo[e] = __uint_as_float(rna_tf32(x - __uint_as_float(h)));
+  }
+}
+
+void launch_split_tf32(const float *src, float *hi, float *lo, int n, cudaStream_t st) {
+  const int grid = std::max(1, std::min((n + 255) / 256, sm_count() * 4));
+  split_tf32_kernel<<<grid, 256, 0, st>>>(src, hi, lo, n);
+  GCRL_LAUNCHED();
 }
 
 bool tc_wgrad_supported(int M, int N, int K) {
@@ -535,9 +568,9 @@ int launch_tc_wgrad(const float *dZ, int lddz, const float *X, int ldx, float *p
   if (const char *e = getenv("GCRL_TC_DBG")) a.dbg = atoi(e);
   const CUtensorMap tmA = make_map(dZ, M, N, lddz, 16, 32, true);
   const CUtensorMap tmB = make_map(X, M, K, ldx, 16, 32, true);
-  if (BN == 64) launch_bn<64>(tmA, tmB, a, st);
-  else if (BN == 128) launch_bn<128>(tmA, tmB, a, st);
-  else launch_bn<256>(tmA, tmB, a, st);
+  if (BN == 64) launch_bn<64>(tmA, tmB, nullptr, a, st);
+  else if (BN == 128) launch_bn<128>(tmA, tmB, nullptr, a, st);
+  else launch_bn<256>(tmA, tmB, nullptr, a, st);
   if (pB != nullptr) {
     colsum_partials_kernel<<<dim3(slabs, (N + 127) / 128), 128, 0, st>>>(dZ, lddz, M, N, rows, pB, b_split_stride);
     GCRL_LAUNCHED();
@@ -562,6 +595,28 @@ extern "C" int gcrl_dense_layer(int device, int engine, int mode, int64_t M, int
     GCRL_REQUIRE(engine == 0 && mode != 1, "engine 0 (fp32 FFMA) implements modes 0 and 2");
     launch_linear_fwd(x_dev, ldx, w_dev, ldw, bias_dev, y_dev, ldy, int(M), N, K, mode == 0 ? ACT_LEAKY : ACT_NONE, st);
   }
+  GCRL_API_END
+}
+
+extern "C" int gcrl_split_tf32(int device, const float *src_dev, float *hi_dev, float *lo_dev, int64_t n, void *stream) {
+  GCRL_API_BEGIN
+  using namespace gcrl;
+  GCRL_REQUIRE(src_dev && hi_dev && lo_dev && n >= 0 && n < (int64_t(1) << 31), "bad argument");
+  GCRL_CUDA(cudaSetDevice(device));
+  if (n > 0) launch_split_tf32(src_dev, hi_dev, lo_dev, int(n), as_stream(stream));
+  GCRL_API_END
+}
+
+extern "C" int gcrl_dense_layer_presplit(int device, int mode, int64_t M, int N, int K, const float *x_dev, int ldx,
+                                         const float *w_hi_dev, const float *w_lo_dev, int ldw, const float *bias_dev,
+                                         const float *act_dev, int ldact, float *y_dev, int ldy, void *stream) {
+  GCRL_API_BEGIN
+  using namespace gcrl;
+  GCRL_REQUIRE(x_dev && w_hi_dev && w_lo_dev && y_dev && M >= 1 && M < (int64_t(1) << 31), "bad argument");
+  GCRL_REQUIRE(mode >= 0 && mode <= 2 && (mode == 1 ? act_dev != nullptr : bias_dev != nullptr), "bad mode / operands");
+  GCRL_CUDA(cudaSetDevice(device));
+  launch_tc_dense(x_dev, ldx, w_hi_dev, ldw, bias_dev, act_dev, ldact, y_dev, ldy, int(M), N, K, mode, as_stream(stream),
+                  w_lo_dev);
   GCRL_API_END
 }
 

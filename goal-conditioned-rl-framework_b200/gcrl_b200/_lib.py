@@ -137,6 +137,9 @@ SIGNATURES = {
     "gcrl_sac_per_buffers": (C.c_int, [vp, pp, pp]),
     # diagnostics
     "gcrl_agent_time_critic_kernel": (C.c_int, [vp, c_i64, C.c_int, C.POINTER(c_f32), vp]),
+    "gcrl_split_tf32": (C.c_int, [C.c_int, vp, vp, vp, c_i64, vp]),
+    "gcrl_dense_layer_presplit": (C.c_int, [C.c_int, C.c_int, c_i64, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_int, vp, vp,
+                                            C.c_int, vp, C.c_int, vp]),
     "gcrl_dense_wgrad": (C.c_int, [C.c_int, C.c_int, c_i64, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, c_i64,
                                    vp, c_i64, C.c_int, C.POINTER(C.c_int), vp]),
     "gcrl_dense_layer": (C.c_int, [C.c_int, C.c_int, C.c_int, c_i64, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp,

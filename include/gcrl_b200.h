@@ -449,6 +449,14 @@ int gcrl_dense_layer(int device, int engine, int mode, int64_t M, int N, int K, 
  *   pw[s][n][k] = sum_{m in slab s} dz[m, n] x[m, k],  pb[s][n] = sum_{m in slab s} dz[m, n]
  * for s < *splits_out <= max_splits slabs of batch rows (the caller sums the slabs in order).
  * engine 0: fp32 FFMA tiles; engine 1: tcgen05, MN-major operands, 3xTF32 split. */
+/* The tensor-core dense layer as the agents call it: the weight operand pre-split into its TF32 hi / lo halves
+ * (gcrl_split_tf32: hi = rna_tf32(w), lo = rna_tf32(w - hi); same layout as w), so that the kernel only splits the
+ * activation tile.  Same modes as gcrl_dense_layer. */
+int gcrl_split_tf32(int device, const float *src_dev, float *hi_dev, float *lo_dev, int64_t n, void *stream);
+int gcrl_dense_layer_presplit(int device, int mode, int64_t M, int N, int K, const float *x_dev, int ldx,
+                              const float *w_hi_dev, const float *w_lo_dev, int ldw, const float *bias_dev,
+                              const float *act_dev, int ldact, float *y_dev, int ldy, void *stream);
+
 int gcrl_dense_wgrad(int device, int engine, int64_t M, int N, int K, const float *dz_dev, int lddz,
                      const float *x_dev, int ldx, float *pw_dev, int ldw, int64_t w_split_stride,
                      float *pb_dev, int64_t b_split_stride, int max_splits, int *splits_out, void *stream);
