@@ -435,23 +435,38 @@ CUtensorMap make_map(const float *ptr, int64_t rows, int cols, int ld, int box_r
   return m;
 }
 
-// pB[slab][n] = sum over the slab's rows of dZ[m][n]   (bias gradient partials; fixed order)
-__global__ void __launch_bounds__(128)
+// pB[slab][n] = sum over the slab's rows of dZ[m][n]   (bias gradient partials; fixed order).
+// One CTA per (slab, 32-column block): 8 row lanes x 32 columns, every warp reads whole 128-byte row segments,
+// 8 loads per thread in flight; the row lanes are summed through shared memory in lane order.  (The first version
+// -- 128 threads per 128 columns, 4 loads in flight, 256 CTAs -- kept 0.5 MB in flight and ran at 1.2 TB/s:
+// 11 % of the B = 65536 update.)
+__global__ void __launch_bounds__(256)
 colsum_partials_kernel(const float *__restrict__ dZ, int lddz, int M, int N, int rows_per_slab, float *__restrict__ pB,
                        long long split_stride) {
-  const int n = blockIdx.y * 128 + threadIdx.x;
-  if (n >= N) return;
+  __shared__ float sm[8][33];
+  const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int n = blockIdx.y * 32 + lane;
   const int r0 = blockIdx.x * rows_per_slab, r1 = min(M, r0 + rows_per_slab);
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int m = r0;
-  for (; m + 3 < r1; m += 4) {
-    s0 += dZ[size_t(m) * lddz + n];
-    s1 += dZ[size_t(m + 1) * lddz + n];
-    s2 += dZ[size_t(m + 2) * lddz + n];
-    s3 += dZ[size_t(m + 3) * lddz + n];
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (n < N) {
+    int m = r0 + rl;
+    for (; m + 56 < r1; m += 64) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = dZ[size_t(m + 8 * u) * lddz + n];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s[u] += v[u];
+    }
+    for (; m < r1; m += 8) s[0] += dZ[size_t(m) * lddz + n];
   }
-  for (; m < r1; ++m) s0 += dZ[size_t(m) * lddz + n];
-  pB[(long long)blockIdx.x * split_stride + n] = (s0 + s1) + (s2 + s3);
+  sm[rl][lane] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+  __syncthreads();
+  if (rl == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][lane];
+    pB[(long long)blockIdx.x * split_stride + n] = t;
+  }
 }
 
 template <int BN>
@@ -572,7 +587,7 @@ int launch_tc_wgrad(const float *dZ, int lddz, const float *X, int ldx, float *p
   else if (BN == 128) launch_bn<128>(tmA, tmB, nullptr, a, st);
   else launch_bn<256>(tmA, tmB, nullptr, a, st);
   if (pB != nullptr) {
-    colsum_partials_kernel<<<dim3(slabs, (N + 127) / 128), 128, 0, st>>>(dZ, lddz, M, N, rows, pB, b_split_stride);
+    colsum_partials_kernel<<<dim3(slabs, (N + 31) / 32), 256, 0, st>>>(dZ, lddz, M, N, rows, pB, b_split_stride);
     GCRL_LAUNCHED();
   }
   return slabs;
