@@ -227,6 +227,58 @@ def _state_of(mt, pos, gauss):
     return state
 
 
+# Direct view of the interpreter's global generator.  random._inst is a _random.Random (CPython: PyObject_HEAD, then
+# `int index; uint32_t state[624];`, Modules/_randommodule.c), so the C mirror can advance the very words the
+# interpreter draws from, in place: no getstate() (625 Python ints, ~18 us), no tuple of the advanced state (~20 us),
+# no setstate() (~5 us) per call.  The layout is VERIFIED against getstate() on a scratch generator and on the global
+# one before it is trusted (and re-checked whenever random._inst is replaced); any mismatch falls back to the
+# state-tuple path below.  The two entry points run through a PyDLL handle: the GIL stays held while the words move.
+_direct = None        # None: not probed yet; False: layout check failed; else (instance, address)
+_pydll = None
+
+
+def _probe_direct():
+    import random
+    global _direct, _pydll
+    try:
+        def view(inst):
+            addr = id(inst)
+            index = C.c_int.from_address(addr + 16).value
+            words = (C.c_uint32 * 624).from_address(addr + 20)
+            return index, tuple(words)
+
+        scratch = random.Random(0x5EED1234)
+        for inst, draws in ((scratch, 700), (random._inst, 0)):      # the global generator is only LOOKED at
+            for step in range(3):
+                for _ in range(draws if step else 0):
+                    inst.random()                                     # across a 624-word refill on the scratch one
+                version, internal, _g = inst.getstate()
+                index, words = view(inst)
+                if version != 3 or len(internal) != 625 or internal[-1] != index or internal[:-1] != words:
+                    raise RuntimeError("layout mismatch")
+        if _pydll is None:
+            _pydll = C.PyDLL(library_path())
+            for name in ("gcrl_pyrandom_randint", "gcrl_pyrandom_sample_range"):
+                fn = getattr(_pydll, name)
+                fn.restype, fn.argtypes = SIGNATURES[name]
+        _direct = (random._inst, id(random._inst))
+    except Exception:   # noqa: BLE001  (another interpreter / layout: the portable path is always correct)
+        _direct = False
+
+
+def _direct_ptrs():
+    """(words pointer, index pointer) into the interpreter's global generator, or None."""
+    import random
+    if os.environ.get("GCRL_PYRANDOM_PORTABLE") == "1":
+        return None
+    if _direct is None or (_direct and _direct[0] is not random._inst):
+        _probe_direct()
+    if not _direct:
+        return None
+    addr = _direct[1]
+    return vp(addr + 20), C.cast(addr + 16, C.POINTER(C.c_int))
+
+
 def py_randint_seq(lo, hi):
     """[random.randint(lo[i], hi[i]) for i in range(len(lo))], consuming the global stream identically."""
     import random
@@ -235,6 +287,10 @@ def py_randint_seq(lo, hi):
     lo = np.ascontiguousarray(lo, np.int32)
     hi = np.ascontiguousarray(hi, np.int32)
     out = np.empty(lo.shape, np.int32)
+    ptrs = _direct_ptrs()
+    if ptrs is not None:
+        check(_pydll.gcrl_pyrandom_randint(ptrs[0], ptrs[1], lo.size, np_ptr(lo), np_ptr(hi), np_ptr(out)))
+        return out
     mt, pos, gauss = _words_of(random.getstate())
     check(lib.gcrl_pyrandom_randint(np_ptr(mt), C.byref(pos), lo.size, np_ptr(lo), np_ptr(hi), np_ptr(out)))
     random.setstate(_state_of(mt, pos, gauss))
@@ -254,6 +310,17 @@ def py_sample_range_from(state, n, k):
 def py_sample_range(n, k):
     """np.array(random.sample(range(n), k), int64), consuming the global stream identically."""
     import random
+
+    import numpy as np
+    ptrs = _direct_ptrs()
+    if ptrs is not None:
+        out = np.empty(int(k), np.int64)
+        check(_pydll.gcrl_pyrandom_sample_range(ptrs[0], ptrs[1], int(n), int(k), np_ptr(out)))
+        return out
     out, after = py_sample_range_from(random.getstate(), n, k)
     random.setstate(after)
     return out
+
+
+def direct_stream_available():
+    return _direct_ptrs() is not None

@@ -512,6 +512,8 @@ class _AgentBase:
     _known_state = None     # the tuple the global generator was just set to (by _take_predrawn), if still current
 
     def _predraw(self, B):
+        if _lib.direct_stream_available():
+            return          # drawing in place from the interpreter's generator costs ~6 us: nothing worth hiding
         n = len(self.buffer)
         # right after a successful _take_predrawn the global state IS the tuple it installed: no getstate(),
         # and the C mirror recognises its own tuple and skips the 624-word conversion
@@ -524,6 +526,8 @@ class _AgentBase:
     def _take_predrawn(self, B):
         pre, self._pre = self._pre, None
         n = len(self.buffer)
+        if pre is None and _lib.direct_stream_available():
+            return _lib.py_sample_range(n, B)
         if pre is not None and pre[3] == n and pre[4] == B and random.getstate() == pre[0]:
             random.setstate(pre[1])
             self._known_state = pre[1]

@@ -141,3 +141,35 @@ def test_injected_compute_reward_is_probed_against_the_sparse_rule():
     assert not late._reward_checked
     with pytest.raises(ValueError, match="compute_reward"):
         late._check_reward(3)
+
+
+def test_direct_view_of_the_interpreter_generator_equals_the_portable_path(monkeypatch):
+    """_lib advances the words of random._inst in place when CPython's _random.Random layout checks out (probed
+    against getstate() without consuming a draw); GCRL_PYRANDOM_PORTABLE=1 forces the getstate()/setstate() path.
+    Same values, same generator state afterwards, interleaved with the interpreter's own draws."""
+    from gcrl_b200 import _lib
+    lo = np.arange(1, 50, dtype=np.int32).repeat(4)
+    hi = np.full(lo.shape, 49, np.int32)
+    runs = []
+    for portable in ("0", "1"):
+        monkeypatch.setenv("GCRL_PYRANDOM_PORTABLE", portable)
+        _lib._direct = None                                # probe again under this setting
+        random.seed(4242)
+        before = random.getstate()
+        assert (_lib.direct_stream_available()) == (portable == "0") or portable == "0"
+        assert random.getstate() == before, "probing must not consume from the global stream"
+        out = [random.random()]
+        out += _lib.py_randint_seq(lo, hi).tolist()
+        out.append(random.randint(0, 10 ** 9))
+        out += _lib.py_sample_range(4_920_000, 256).tolist()
+        out.append(random.random())
+        out += _lib.py_sample_range(700, 699).tolist()     # crosses several 624-word refills
+        runs.append((out, random.getstate()))
+    assert runs[0] == runs[1]
+    # and both equal the interpreter itself
+    random.seed(4242)
+    want = [random.random()] + [random.randint(int(a), int(b)) for a, b in zip(lo, hi)] + [random.randint(0, 10 ** 9)]
+    want += random.sample(range(4_920_000), 256) + [random.random()] + random.sample(range(700), 699)
+    assert runs[0][0] == want and runs[0][1] == random.getstate()
+    monkeypatch.delenv("GCRL_PYRANDOM_PORTABLE")
+    _lib._direct = None
