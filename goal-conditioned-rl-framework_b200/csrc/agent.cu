@@ -1110,6 +1110,26 @@ int gcrl_agent_hard_update(gcrl_agent *ag, void *stream) {
   GCRL_API_END
 }
 
+// Polyak step theta_t <- tau theta + (1 - tau) theta_t of selected target networks, outside update()
+// (DDPG.update_target_network(hard_update=False, tau), src/agent.py:1259-1271; TD3 update_actor / update_critic
+// :117-132).  which: bit0 actor, bit1 critic(s).
+int gcrl_agent_soft_update(gcrl_agent *ag, int which, double tau, void *stream) {
+  GCRL_API_BEGIN
+  require_handle(ag);
+  GCRL_REQUIRE(which >= 1 && which <= 3 && tau >= 0.0 && tau <= 1.0, "which in 1..3, tau in [0, 1]");
+  GCRL_CUDA(cudaSetDevice(ag->device));
+  cudaStream_t st = as_stream(stream);
+  const int pairs[3][3] = {{T_ACTOR, ACTOR, 1}, {T_CRITIC1, CRITIC1, 2}, {T_CRITIC2, CRITIC2, 2}};
+  for (auto &pr : pairs)
+    if ((which & pr[2]) && ag->has[pr[0]]) {
+      Net &t = ag->net[pr[0]];
+      const Net &srcn = ag->net[pr[1]];
+      launch_polyak(t.p, srcn.p, srcn.total, float(tau), float(1.0 - tau), srcn.tmap, t.pT, st);
+      t.split_stale = true;
+    }
+  GCRL_API_END
+}
+
 int gcrl_agent_reset_optim(gcrl_agent *ag, void *stream) {
   GCRL_API_BEGIN
   require_handle(ag);

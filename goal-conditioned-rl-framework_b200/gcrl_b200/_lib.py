@@ -86,6 +86,7 @@ SIGNATURES = {
     "gcrl_agent_get_adam_step": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int)]),
     "gcrl_agent_set_adam_step": (C.c_int, [vp, C.c_int, C.c_int]),
     "gcrl_agent_hard_update": (C.c_int, [vp, vp]),
+    "gcrl_agent_soft_update": (C.c_int, [vp, C.c_int, c_f64, vp]),
     "gcrl_agent_reset_optim": (C.c_int, [vp, vp]),
     "gcrl_agent_update_batch": (C.c_int, [vp, c_i64, vp, vp, vp, vp, vp, vp, c_f64, c_f64, C.c_int, vp, vp]),
     "gcrl_agent_update_from_buffer": (C.c_int, [vp, vp, c_i64, vp, vp, c_f64, c_f64, C.c_int, vp, vp]),

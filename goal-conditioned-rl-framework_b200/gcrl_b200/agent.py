@@ -567,10 +567,11 @@ class DDPG(_AgentBase):
             self.critic.load(critic_path)
         self.update_target_network()
 
-    def update_target_network(self, hard_update: bool = True, tau: float = 0.005):
-        if not hard_update:
-            raise NotImplementedError("soft updates run inside update() on the device")
-        self.hard_update()
+    def update_target_network(self, hard_update: bool = True, tau: float = 0.005):      # :1255-1271
+        if hard_update:
+            self.hard_update()
+        else:
+            check(lib.gcrl_agent_soft_update(self._h, 3, float(tau), self._stream()))
 
     def _flags(self, step):
         return (1 if step % self.ac_update_freq == 0 else 0) | (2 if step % self.POLYAK_EVERY == 0 else 0)
@@ -637,6 +638,12 @@ class TD3Agent(_AgentBase):
 
     def update_target_network(self):
         self.hard_update()
+
+    def update_actor(self, tau: float = 0.005):                                          # :117-121
+        check(lib.gcrl_agent_soft_update(self._h, 1, float(tau), self._stream()))
+
+    def update_critic(self, tau: float = 0.005):                                         # :123-132
+        check(lib.gcrl_agent_soft_update(self._h, 2, float(tau), self._stream()))
 
     def _trainable_critics(self):
         return (NET_CRITIC, NET_CRITIC2)

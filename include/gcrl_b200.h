@@ -201,6 +201,10 @@ int gcrl_agent_get_adam_step(gcrl_agent *h, int net, int *step);
 int gcrl_agent_set_adam_step(gcrl_agent *h, int net, int step);
 /* update_target_network(hard_update=True), src/agent.py:1255-1258 */
 int gcrl_agent_hard_update(gcrl_agent *h, void *stream);
+/* Polyak step theta_t <- tau theta + (1 - tau) theta_t of the target actor (which bit0) and / or the target critic(s)
+ * (bit1), outside update(): DDPG.update_target_network(hard_update=False, tau) src/agent.py:1259-1271, TD3Agent.update_actor
+ * / update_critic :117-132.  (Inside update() the Polyak steps are fused into the optimiser kernels.) */
+int gcrl_agent_soft_update(gcrl_agent *h, int which, double tau, void *stream);
 /* Optimiser state is zeroed (Adam step counters too): a fresh torch.optim.Adam. */
 int gcrl_agent_reset_optim(gcrl_agent *h, void *stream);
 

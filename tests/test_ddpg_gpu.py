@@ -489,3 +489,33 @@ def test_failed_update_leaves_step_counters_untouched():
         ag.buffer.push_episode(e["s"], e["a"], e["ns"], e["r"], e["d"], e["ag"], e["fut"])
     ag.update(1)
     assert steps() == [before[0] + 1, before[1] + 1]
+
+
+def test_public_soft_update_matches_the_reference_rule():
+    """DDPG.update_target_network(hard_update=False, tau) (src/agent.py:1259-1271) and TD3Agent.update_actor /
+    update_critic (:117-132) outside update(): theta_t <- tau theta + (1 - tau) theta_t in fp32, bit for bit."""
+    from gcrl_b200 import DDPG, TD3Agent
+    from gcrl_b200.agent import NET_ACTOR, NET_CRITIC
+    rng = np.random.default_rng(5)
+    D, A, H, L = 10, 3, 64, 2
+    ag = DDPG(D, A, make_config(hidden_dim=H, layer_count=L), None, 1, 40)
+    t_before = [[w.copy(), b.copy()] for w, b in ag.target_actor.layers() + ag.target_critic.layers()]
+    ag._set_layers(NET_ACTOR, OD.init_mlp(rng, D, H, A, L))
+    ag._set_layers(NET_CRITIC, OD.init_mlp(rng, D + A, H, 1, L))
+    src = ag.actor.layers() + ag.critic.layers()
+    tau = 0.05
+    ag.update_target_network(hard_update=False, tau=tau)
+    for (tw, tb), (w, b), (gw, gb) in zip(t_before, src, ag.target_actor.layers() + ag.target_critic.layers()):
+        want_w = (np.float32(tau) * w + np.float32(1 - tau) * tw).astype(np.float32)
+        want_b = (np.float32(tau) * b + np.float32(1 - tau) * tb).astype(np.float32)
+        np.testing.assert_allclose(gw, want_w, rtol=2e-7, atol=1e-9)      # one fused multiply-add may replace mul + add
+        np.testing.assert_allclose(gb, want_b, rtol=2e-7, atol=1e-9)
+    td = TD3Agent(D, A, make_config(hidden_dim=H, layer_count=L), None, 1, 40)
+    a0 = [w.copy() for w, _ in td.target_actor.layers()]
+    c0 = [w.copy() for w, _ in td.target_critic_2.layers()]
+    td._set_layers(NET_ACTOR, OD.init_mlp(rng, D, H, A, L))
+    td.update_critic(0.3)                                  # actor target untouched; critic targets blend equal weights
+    assert all(np.array_equal(x, y) for x, (y, _) in zip(a0, td.target_actor.layers()))
+    assert all(np.allclose(x, y, rtol=2e-7, atol=0) for x, (y, _) in zip(c0, td.target_critic_2.layers()))
+    td.update_actor(0.3)
+    assert not np.array_equal(a0[0], td.target_actor.layers()[0][0])
