@@ -717,11 +717,16 @@ def gpu_main(args):
             allt = t.cpu().numpy()[None]
         sums = allt.sum(1)
         r, i = np.unravel_index(int(np.argmax(allt)), allt.shape)
-        detail = {"rank0": [round(float(x), 4) for x in allt[0]],
-                  "max_over_ranks": [round(float(x), 4) for x in allt.max(0)],
+        mx = allt.max(0)
+        keep = 200                                     # long runs: the first steps + the distribution, not 3 x K numbers
+        detail = {"rank0": [round(float(x), 4) for x in allt[0][:keep]],
+                  "max_over_ranks": [round(float(x), 4) for x in mx[:keep]],
                   "sum_ms_per_rank": [round(float(x), 4) for x in sums],
                   "slowest": {"rank": int(r), "step": int(i), "ms": round(float(allt[r, i]), 4)},
-                  "median_ms": round(float(np.median(allt)), 4)}
+                  "median_ms": round(float(np.median(allt)), 4),
+                  "max_over_ranks_p50_p99_max": [round(float(np.median(mx)), 4), round(float(np.quantile(mx, 0.99)), 4),
+                                                 round(float(mx.max()), 4)],
+                  "steps_listed": int(min(keep, allt.shape[1]))}
         return float(sums.max()), detail
 
     # ---- warm-up (graph capture for both flag sets, clocks ramp), then the timed region ----
