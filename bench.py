@@ -493,28 +493,43 @@ def extra_configs(args, local, rank, world, dp_mode, flush, stream, peaks):
         cfg = agent_config(a3, E * ((T - 1) * (k + 1) + 1))
         cfg.alpha_lr, cfg.alpha_min, cfg.alpha_min_steps, cfg.grad_clip, cfg.gamma = 3e-4, 3e-4, 1, 5.0, 0.95
         torch.manual_seed(1898)
-        tq = TQCAgent(O + G, A, cfg, None, 1, 40, index_source="device", device=local)
-        fill(tq.buffer, data, E)
-        if world > 1:
-            tq.enable_data_parallel()
-        for i in range(6):
-            tq.update(i + 1)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        n = 30
-        t0 = time.perf_counter()
-        for i in range(n):
-            info = tq.update(7 + i)
-        torch.cuda.synchronize()
-        ms_k = maxr((time.perf_counter() - t0) * 1e3 / n)
+        def time_tqc(sync_bn):
+            torch.manual_seed(1898)
+            tq = TQCAgent(O + G, A, cfg, None, 1, 40, index_source="device", device=local)
+            fill(tq.buffer, data, E)
+            if world > 1:
+                tq.enable_data_parallel(sync_bn=sync_bn)
+            for i in range(6):
+                tq.update(i + 1)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            n = 30
+            t0 = time.perf_counter()
+            for i in range(n):
+                info = tq.update(7 + i)
+            torch.cuda.synchronize()
+            ms = maxr((time.perf_counter() - t0) * 1e3 / n)
+            fin = bool(all(np.isfinite(float(np.mean(x))) for x in info))
+            del tq
+            return ms, fin
+        ms_k, fin = time_tqc(True)
         out["tqc_slide_B512_per_gpu"] = {
             "workload": f"TQCAgent.update (5 scalar critics, drop top 2, learned alpha), Slide shape (obs {O}, goal {G}, act {A}), "
                         f"hidden {H} x {L} (config_tqc_push.yaml), batch {Bl} per GPU, metric read-back every update",
             "ms_per_update": ms_k, "updates_per_s": 1e3 / ms_k, "transitions_per_s": world * Bl / (ms_k * 1e-3),
-            "scaling": "weak", "path": "NCCL all-reduce between the update phases" if world > 1 else "single GPU",
-            "finite": bool(all(np.isfinite(float(np.mean(x))) for x in info))}
-        del tq, data
+            "scaling": "weak",
+            "path": ("NCCL between graph segments: BatchNorm statistics over the global batch (sync-BN, "
+                     f"{3 * L} all-gathers) + 2 gradient averages per update = one rank on the concatenated batch"
+                     if world > 1 else "single GPU"),
+            "finite": fin}
+        if world > 1:
+            ms_l, fin_l = time_tqc(False)
+            out["tqc_slide_B512_per_gpu"]["local_batchnorm_statistics"] = {
+                "ms_per_update": ms_l, "transitions_per_s": world * Bl / (ms_l * 1e-3), "finite": fin_l,
+                "path": "enable_data_parallel(sync_bn=False): 4 phases, 3 NCCL all-reduces per update, running "
+                        "statistics averaged; close to, not equal to, the single-rank result"}
+        del data
         torch.cuda.empty_cache()
     except Exception as e:   # noqa: BLE001
         out["tqc_slide_B512_per_gpu"] = {"error": repr(e)}

@@ -134,6 +134,117 @@ bn_bwd_kernel(float *__restrict__ dh, const float *__restrict__ h, const float *
   }
 }
 
+// ---- BatchNorm1d with batch statistics over all data-parallel ranks ("sync-BN") --------------------
+// The 1-GPU semantics of nn.BatchNorm1d on the concatenated batch (reference src/model.py:103-111):
+// every rank writes its local per-column (mean, M2 = sum (z - mean)^2) -- or, in the backward pass, (sum dy,
+// sum dy xhat) -- into its slot of a [world][2 ldh] buffer, the caller all-gathers the buffer between two graph
+// segments, and every rank merges the slots in rank order (Chan's parallel variance; equal local batch sizes), so
+// all ranks normalise with bit-identical statistics.  With world = 1 the result equals bn_fwd_kernel / bn_bwd_kernel
+// bit for bit.
+__global__ void __launch_bounds__(1024)
+bn_stats_kernel(const float *__restrict__ z, int ld, int B, int H, float *__restrict__ slot, int ldh) {
+  __shared__ float red[33][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool ok = c < H;
+  float s = 0.f;
+  if (ok)
+    for (int m = threadIdx.y; m < B; m += 32) s += z[size_t(m) * ld + c];
+  const float mu = col_reduce(s, red) / float(B);
+  s = 0.f;
+  if (ok)
+    for (int m = threadIdx.y; m < B; m += 32) {
+      const float d = z[size_t(m) * ld + c] - mu;
+      s = fmaf(d, d, s);
+    }
+  const float m2 = col_reduce(s, red);
+  if (ok && threadIdx.y == 0) {
+    slot[c] = mu;
+    slot[ldh + c] = m2;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+bn_fwd_sync_kernel(float *__restrict__ z, int ld, int B, int H, const float *__restrict__ gamma,
+                   const float *__restrict__ beta, float *__restrict__ rmean, float *__restrict__ rvar,
+                   float *__restrict__ invstd_out, float *__restrict__ h, const float *__restrict__ gather, int world,
+                   int ldh) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  if (c >= H) return;
+  float msum = gather[c];
+  for (int r = 1; r < world; ++r) msum += gather[size_t(r) * 2 * ldh + c];
+  const float mu = msum / float(world);
+  float m2 = 0.f;
+  for (int r = 0; r < world; ++r) {
+    const float d = gather[size_t(r) * 2 * ldh + c] - mu;
+    m2 += gather[size_t(r) * 2 * ldh + ldh + c] + float(B) * d * d;
+  }
+  const float n = float(world) * float(B);
+  const float var = m2 / n;
+  if (threadIdx.y == 0) {
+    rmean[c] = (1.0f - kBnMomentum) * rmean[c] + kBnMomentum * mu;
+    rvar[c] = (1.0f - kBnMomentum) * rvar[c] + kBnMomentum * (var * (n / (n - 1.0f)));
+  }
+  const float invstd = 1.0f / sqrtf(var + kBnEps);
+  const float g = gamma[c], b = beta[c];
+  for (int m = threadIdx.y; m < B; m += 32) {
+    const size_t e = size_t(m) * ld + c;
+    const float xh = (z[e] - mu) * invstd;
+    z[e] = xh;
+    h[e] = fmaxf(xh * g + b, 0.f);
+  }
+  if (threadIdx.y == 0) invstd_out[c] = invstd;
+}
+
+__global__ void __launch_bounds__(1024)
+bn_bwd_stats_kernel(const float *__restrict__ dh, const float *__restrict__ h, const float *__restrict__ xhat, int ld,
+                    int B, int H, float *__restrict__ slot, int ldh) {
+  __shared__ float red[33][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool ok = c < H;
+  float s1 = 0.f, s2 = 0.f;
+  if (ok)
+    for (int m = threadIdx.y; m < B; m += 32) {
+      const size_t e = size_t(m) * ld + c;
+      const float dy = h[e] > 0.f ? dh[e] : 0.f;
+      s1 += dy;
+      s2 = fmaf(dy, xhat[e], s2);
+    }
+  s1 = col_reduce(s1, red);
+  s2 = col_reduce(s2, red);
+  if (ok && threadIdx.y == 0) {
+    slot[c] = s1;
+    slot[ldh + c] = s2;
+  }
+}
+
+// dgamma / dbeta stay the LOCAL sums (the flat gradient is averaged over the ranks afterwards, like every other
+// parameter gradient); the input gradient uses the sums over all ranks and n = world * B rows.
+__global__ void __launch_bounds__(1024)
+bn_bwd_sync_kernel(float *__restrict__ dh, const float *__restrict__ h, const float *__restrict__ xhat, int ld, int B,
+                   int H, const float *__restrict__ gamma, const float *__restrict__ invstd,
+                   float *__restrict__ dgamma, float *__restrict__ dbeta, const float *__restrict__ gather, int world,
+                   int rank, int ldh) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  if (c >= H) return;
+  float s1 = gather[c], s2 = gather[ldh + c];
+  for (int r = 1; r < world; ++r) {
+    s1 += gather[size_t(r) * 2 * ldh + c];
+    s2 += gather[size_t(r) * 2 * ldh + ldh + c];
+  }
+  const float g = gamma[c], is = invstd[c], n = float(world) * float(B);
+  const float sum_dxhat = s1 * g, sum_dxhat_xhat = s2 * g;
+  for (int m = threadIdx.y; m < B; m += 32) {
+    const size_t e = size_t(m) * ld + c;
+    const float dy = h[e] > 0.f ? dh[e] : 0.f;
+    const float dxhat = dy * g;
+    dh[e] = is / n * (n * dxhat - sum_dxhat - xhat[e] * sum_dxhat_xhat);
+  }
+  if (threadIdx.y == 0) {
+    dgamma[c] = gather[size_t(rank) * 2 * ldh + ldh + c];
+    dbeta[c] = gather[size_t(rank) * 2 * ldh + c];
+  }
+}
+
 // ---- tanh-Gaussian policy head -------------------------------------------------------------------
 struct PolicyFwdArgs {
   const float *feat; int ldh;            // last hidden activation [M, K]
@@ -556,6 +667,14 @@ struct gcrl_sac {
   cudaStream_t cap_stream = nullptr;             // capture-only stream (the caller's may be the legacy one)
   struct GraphRec { cudaGraphExec_t exec; uint64_t kernels; };
   std::map<std::tuple<int, int, int>, GraphRec> graphs;   // (B, flags, phase mask)
+  // sync-BN (gcrl_sac_set_sync_bn): the update is cut into graph segments, each ending in the collective the caller
+  // runs before the next one (gcrl_sac_update_segment)
+  int sync_world = 0, sync_rank = 0;
+  float *bn_gather = nullptr;                    // [world][2 ldh]: per-rank BatchNorm partial statistics
+  struct SegRec { cudaGraphExec_t exec; uint64_t kernels; int collective; };
+  std::map<std::tuple<int, int>, std::vector<SegRec>> seg_graphs;     // (B, flags)
+  std::vector<SegRec> *seg_build = nullptr;      // the segment list being captured
+  uint64_t seg_mark = 0;
   float *critic_grads = nullptr;                 // [n][critic_stride]: the ensemble's flat gradients, contiguous
   int critic_stride = 0;
   // activations
@@ -592,6 +711,23 @@ int blocks_for(int64_t work, int per_block) {
   return int(std::max<int64_t>(1, std::min<int64_t>((work + per_block - 1) / per_block, int64_t(sm_count()) * 8)));
 }
 
+// Collectives a graph segment ends in (gcrl_sac_update_segment): what the caller runs before the next segment.
+enum : int { COLL_DONE = 0, COLL_GATHER_BN = 1, COLL_AVG_CRITIC = 2, COLL_AVG_ACTOR = 3 };
+
+// Close the graph segment being captured and open the next one.  Only the segmented capture reaches this.
+void seg_cut(gcrl_sac *ag, int collective, bool last = false) {
+  cudaGraph_t graph = nullptr;
+  GCRL_CUDA(cudaStreamEndCapture(ag->cap_stream, &graph));
+  const uint64_t now = launch_counter();
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  GCRL_CUDA(e);
+  ag->seg_build->push_back(gcrl_sac::SegRec{exec, now - ag->seg_mark, collective});
+  ag->seg_mark = now;
+  if (!last) GCRL_CUDA(cudaStreamBeginCapture(ag->cap_stream, cudaStreamCaptureModeThreadLocal));
+}
+
 // The whole ensemble on the same input rows: one launch per layer (blockIdx.z = critic) instead of n.
 // Activations land in ag->ch[i][l] (the caches of the backward pass, or plain scratch for the targets).
 void critics_fwd(gcrl_sac *ag, const CriticNet *nets, const float *X, float *q_out, int B, cudaStream_t st) {
@@ -618,11 +754,24 @@ void actor_fwd(gcrl_sac *ag, float *rows, const float *eps, int B, bool train, b
   for (int l = 0; l < ag->L; ++l) {
     launch_linear_fwd(in, ldin, a.p + a.w_off[l], a.ldw[l], a.p + a.b_off[l], ag->xhat[l], ag->ldh, B, ag->H, K,
                       ACT_NONE, st);
-    bn_fwd_kernel<<<(ag->H + 31) / 32, dim3(32, 32), 0, st>>>(ag->xhat[l], ag->ldh, B, ag->H, a.p + a.gam_off[l],
-                                                              a.p + a.bet_off[l], a.rmean + size_t(l) * ag->ldh,
-                                                              a.rvar + size_t(l) * ag->ldh,
-                                                              ag->invstd + size_t(l) * ag->ldh, ag->ah[l], train ? 1 : 0);
-    GCRL_LAUNCHED();
+    if (train && ag->sync_world > 0) {
+      GCRL_REQUIRE(ag->seg_build != nullptr, "a sync-BN agent trains through gcrl_sac_update_segment only");
+      bn_stats_kernel<<<(ag->H + 31) / 32, dim3(32, 32), 0, st>>>(
+          ag->xhat[l], ag->ldh, B, ag->H, ag->bn_gather + size_t(ag->sync_rank) * 2 * ag->ldh, ag->ldh);
+      GCRL_LAUNCHED();
+      seg_cut(ag, COLL_GATHER_BN);
+      bn_fwd_sync_kernel<<<(ag->H + 31) / 32, dim3(32, 32), 0, st>>>(
+          ag->xhat[l], ag->ldh, B, ag->H, a.p + a.gam_off[l], a.p + a.bet_off[l], a.rmean + size_t(l) * ag->ldh,
+          a.rvar + size_t(l) * ag->ldh, ag->invstd + size_t(l) * ag->ldh, ag->ah[l], ag->bn_gather, ag->sync_world,
+          ag->ldh);
+      GCRL_LAUNCHED();
+    } else {
+      bn_fwd_kernel<<<(ag->H + 31) / 32, dim3(32, 32), 0, st>>>(ag->xhat[l], ag->ldh, B, ag->H, a.p + a.gam_off[l],
+                                                                a.p + a.bet_off[l], a.rmean + size_t(l) * ag->ldh,
+                                                                a.rvar + size_t(l) * ag->ldh,
+                                                                ag->invstd + size_t(l) * ag->ldh, ag->ah[l], train ? 1 : 0);
+      GCRL_LAUNCHED();
+    }
     in = ag->ah[l]; ldin = ag->ldh; K = ag->H;
   }
   PolicyFwdArgs p{};
@@ -780,6 +929,7 @@ void critic_update(gcrl_sac *ag, int B, int flags, int mask, cudaStream_t st) {
     if (!dp) adam(ag, c.p, c.m, c.v, c.g, c.total, 0, ag->target[i].p, (flags & 2) != 0, M_CGN + i, st);
   }
   }
+  if (ag->seg_build != nullptr) seg_cut(ag, COLL_AVG_CRITIC);
   if (dp && (mask & PH_CSTEP)) {
     for (int i = 0; i < n; ++i) {
       CriticNet &c = ag->critic[i];
@@ -873,10 +1023,23 @@ void actor_update(gcrl_sac *ag, int B, int flags, int mask, cudaStream_t st) {
   int splits[8] = {};
   int cur = 0;
   for (int l = L - 1; l >= 0; --l) {
-    bn_bwd_kernel<<<(ag->H + 31) / 32, dim3(32, 32), 0, st>>>(ag->dz[cur], ag->ah[l], ag->xhat[l], ag->ldh, B, ag->H,
-                                                              a.p + a.gam_off[l], ag->invstd + size_t(l) * ag->ldh,
-                                                              a.g + a.gam_off[l], a.g + a.bet_off[l]);
-    GCRL_LAUNCHED();
+    if (ag->sync_world > 0) {
+      GCRL_REQUIRE(ag->seg_build != nullptr, "a sync-BN agent trains through gcrl_sac_update_segment only");
+      bn_bwd_stats_kernel<<<(ag->H + 31) / 32, dim3(32, 32), 0, st>>>(
+          ag->dz[cur], ag->ah[l], ag->xhat[l], ag->ldh, B, ag->H, ag->bn_gather + size_t(ag->sync_rank) * 2 * ag->ldh,
+          ag->ldh);
+      GCRL_LAUNCHED();
+      seg_cut(ag, COLL_GATHER_BN);
+      bn_bwd_sync_kernel<<<(ag->H + 31) / 32, dim3(32, 32), 0, st>>>(
+          ag->dz[cur], ag->ah[l], ag->xhat[l], ag->ldh, B, ag->H, a.p + a.gam_off[l], ag->invstd + size_t(l) * ag->ldh,
+          a.g + a.gam_off[l], a.g + a.bet_off[l], ag->bn_gather, ag->sync_world, ag->sync_rank, ag->ldh);
+      GCRL_LAUNCHED();
+    } else {
+      bn_bwd_kernel<<<(ag->H + 31) / 32, dim3(32, 32), 0, st>>>(ag->dz[cur], ag->ah[l], ag->xhat[l], ag->ldh, B, ag->H,
+                                                                a.p + a.gam_off[l], ag->invstd + size_t(l) * ag->ldh,
+                                                                a.g + a.gam_off[l], a.g + a.bet_off[l]);
+      GCRL_LAUNCHED();
+    }
     const float *xin = l == 0 ? ag->spi : ag->ah[l - 1];
     const int ldin = l == 0 ? ag->ldc : ag->ldh;
     const int K = l == 0 ? D : ag->H;
@@ -907,6 +1070,7 @@ void actor_update(gcrl_sac *ag, int B, int flags, int mask, cudaStream_t st) {
     GCRL_LAUNCHED();
   }
   }
+  if (ag->seg_build != nullptr) seg_cut(ag, COLL_AVG_ACTOR);
   if (mask & PH_ASTEP) {
     if (dp) rereduce(ag, a.g, a.total, st);
     adam(ag, a.p, a.m, a.v, a.g, a.total, 1, nullptr, false, M_AGN, st);
@@ -961,14 +1125,63 @@ void run_phases(gcrl_sac *ag, int B, int flags, int mask, cudaStream_t st) {
   count_launch(it->second.kernels);
 }
 
+// Segmented update (sync-BN): the body is captured ONCE per (B, flags) as a chain of graphs, cut wherever a
+// collective has to run (BatchNorm statistics, the two gradient averages); segment `seg` replays graph `seg` and
+// reports the collective the caller owes before the next one.
+constexpr int PH_SEGMENTED = PH_ALL | 16;          // all four phases, data-parallel form (mask != PH_ALL)
+
+int run_segment(gcrl_sac *ag, int B, int flags, int seg, cudaStream_t st) {
+  GCRL_REQUIRE(ag->use_graphs, "sync-BN needs CUDA graphs (unset GCRL_B200_NO_GRAPH)");
+  ag->per_on = (flags & 8) != 0;
+  const auto key = std::make_tuple(B, flags);
+  auto it = ag->seg_graphs.find(key);
+  if (it == ag->seg_graphs.end()) {
+    std::vector<gcrl_sac::SegRec> segs;
+    const uint64_t before = launch_counter();
+    ag->seg_build = &segs;
+    ag->seg_mark = before;
+    GCRL_CUDA(cudaStreamBeginCapture(ag->cap_stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      run_body(ag, B, flags, PH_SEGMENTED, ag->cap_stream);
+      seg_cut(ag, COLL_DONE, true);
+    } catch (...) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(ag->cap_stream, &cs);
+      if (cs != cudaStreamCaptureStatusNone) {
+        cudaGraph_t g = nullptr;
+        cudaStreamEndCapture(ag->cap_stream, &g);
+        if (g) cudaGraphDestroy(g);
+      }
+      for (auto &r : segs) cudaGraphExecDestroy(r.exec);
+      ag->seg_build = nullptr;
+      count_launch(before - launch_counter());
+      throw;
+    }
+    ag->seg_build = nullptr;
+    count_launch(before - launch_counter());              // recorded, not executed, by the capture
+    it = ag->seg_graphs.emplace(key, std::move(segs)).first;
+  }
+  GCRL_REQUIRE(seg >= 0 && seg < int(it->second.size()), "segment index past the end of the update");
+  const auto &r = it->second[size_t(seg)];
+  GCRL_CUDA(cudaGraphLaunch(r.exec, st));
+  count_launch(r.kernels);
+  return r.collective;
+}
+
 // phase < 0: the whole update.  phase 0..3: the data-parallel cut (critic grads | critic steps | actor grads |
 // actor step), the caller averaging critic_grads / the actor gradient across ranks in between.
 void sac_update(gcrl_sac *ag, int phase, gcrl_her *buf, int64_t B64, const int64_t *idx_host, const float *s,
                 const float *a, const float *r, const float *ns, const float *d, const float *eps_next,
-                const float *eps_cur, double lr_c, double lr_a, int flags, float *metrics_host, cudaStream_t st) {
+                const float *eps_cur, double lr_c, double lr_a, int flags, float *metrics_host, cudaStream_t st,
+                int seg = -1, int *collective = nullptr) {
   GCRL_REQUIRE(ag != nullptr, "agent handle is NULL");
   GCRL_REQUIRE(B64 >= 2 && B64 <= ag->maxB, "batch size outside [2, max_batch] (BatchNorm needs > 1 row)");
   const int B = int(B64);
+  if (seg > 0) {
+    GCRL_REQUIRE(ag->dp_B == B && ag->dp_flags == flags, "segment > 0 must follow segment 0 of the same update");
+    *collective = run_segment(ag, B, flags, seg, st);
+    return;
+  }
   if (phase > 0) {
     GCRL_REQUIRE(ag->dp_B == B && ag->dp_flags == flags, "phase 1..3 must follow phase 0 of the same update");
     run_phases(ag, B, flags, phase == 1 ? PH_CSTEP : (phase == 2 ? PH_AGRAD : PH_ASTEP), st);
@@ -994,6 +1207,10 @@ void sac_update(gcrl_sac *ag, int phase, gcrl_her *buf, int64_t B64, const int64
     out[2] = float(1.0 - lr * double(ag->cfg.weight_decay));
     out[3] = 0.f;
   };
+  // the step counters move only if the update is issued: a throw below (capture, CUDA error, a misuse check)
+  // must not leave the bias corrections one step ahead of the Python schedulers
+  const int t_c0 = ag->adam_t_c, t_a0 = ag->adam_t_a, t_al0 = ag->adam_t_alpha;
+  try {
   int slot;   // d_scalars[0] = critic / actor AdamW scalars, d_scalars[1] (first 3 floats) = alpha's
   auto *sc = reinterpret_cast<StepScalars *>(ag->scal_stage.acquire(2 * sizeof(StepScalars), &slot));
   ag->adam_t_c += 1;
@@ -1008,6 +1225,11 @@ void sac_update(gcrl_sac *ag, int phase, gcrl_her *buf, int64_t B64, const int64
   }
   GCRL_CUDA(cudaMemcpyAsync(ag->d_scalars, sc, sizeof(StepScalars) + 16, cudaMemcpyHostToDevice, st));
   ag->scal_stage.release(slot, st);
+  if (seg == 0) {
+    ag->dp_B = B; ag->dp_flags = flags;
+    *collective = run_segment(ag, B, flags, 0, st);
+    return;
+  }
   if (phase == 0) {
     ag->dp_B = B; ag->dp_flags = flags;
     run_phases(ag, B, flags, PH_CGRAD, st);
@@ -1015,6 +1237,10 @@ void sac_update(gcrl_sac *ag, int phase, gcrl_her *buf, int64_t B64, const int64
   }
   run_phases(ag, B, flags, PH_ALL, st);
   read_metrics(ag, flags, metrics_host, st);
+  } catch (...) {
+    ag->adam_t_c = t_c0; ag->adam_t_a = t_a0; ag->adam_t_alpha = t_al0;
+    throw;
+  }
 }
 
 void read_metrics(gcrl_sac *ag, int flags, float *metrics_host, cudaStream_t st) {
@@ -1162,6 +1388,8 @@ int gcrl_sac_destroy(gcrl_sac *ag) {
                    ag->critic_grads, ag->per_w, ag->per_td})
     if (p) cudaFree(p);
   for (auto &kv : ag->graphs) cudaGraphExecDestroy(kv.second.exec);
+  for (auto &kv : ag->seg_graphs) for (auto &r : kv.second) cudaGraphExecDestroy(r.exec);
+  if (ag->bn_gather) cudaFree(ag->bn_gather);
   if (ag->cap_stream) cudaStreamDestroy(ag->cap_stream);
   cudaFree(ag->d_scalars);
   ag->scal_stage.destroy();
@@ -1320,6 +1548,39 @@ int gcrl_sac_update_phase(gcrl_sac *ag, int phase, gcrl_her *buf, int64_t B, con
   GCRL_API_END
 }
 
+int gcrl_sac_set_sync_bn(gcrl_sac *ag, int world, int rank) {
+  GCRL_API_BEGIN
+  require_handle(ag);
+  GCRL_REQUIRE(world >= 0 && world <= 1024 && (world == 0 || (rank >= 0 && rank < world)),
+               "need 0 <= world <= 1024 and 0 <= rank < world (world 0 switches sync-BN off)");
+  GCRL_CUDA(cudaSetDevice(ag->device));
+  GCRL_CUDA(cudaDeviceSynchronize());
+  for (auto &kv : ag->seg_graphs) for (auto &r : kv.second) cudaGraphExecDestroy(r.exec);
+  ag->seg_graphs.clear();
+  if (ag->bn_gather) { cudaFree(ag->bn_gather); ag->bn_gather = nullptr; }
+  ag->sync_world = world; ag->sync_rank = world > 0 ? rank : 0;
+  if (world > 0) {
+    ag->bn_gather = dev_alloc<float>(size_t(world) * 2 * ag->ldh);
+    GCRL_CUDA(cudaMemset(ag->bn_gather, 0, size_t(world) * 2 * ag->ldh * 4));
+  }
+  GCRL_API_END
+}
+
+int gcrl_sac_update_segment(gcrl_sac *ag, int segment, gcrl_her *buf, int64_t B, const int64_t *idx_host,
+                            const float *s, const float *a, const float *r, const float *ns, const float *d,
+                            const float *eps_next, const float *eps_cur, double lr_c, double lr_a, int flags,
+                            int *collective, void *stream) {
+  GCRL_API_BEGIN
+  GCRL_NVTX("gcrl_sac_update_segment");
+  require_handle(ag);
+  GCRL_REQUIRE(segment >= 0 && collective != nullptr, "segment < 0 / NULL collective");
+  GCRL_REQUIRE(ag->sync_world > 0, "gcrl_sac_set_sync_bn first");
+  GCRL_CUDA(cudaSetDevice(ag->device));
+  sac_update(ag, -1, buf, B, idx_host, s, a, r, ns, d, eps_next, eps_cur, lr_c, lr_a, flags, nullptr,
+             as_stream(stream), segment, collective);
+  GCRL_API_END
+}
+
 int gcrl_sac_per_buffers(gcrl_sac *ag, float **weights_dev, float **td_dev) {
   GCRL_API_BEGIN
   require_handle(ag);
@@ -1338,7 +1599,12 @@ int gcrl_sac_dp_buffer(gcrl_sac *ag, int which, float **dev, int64_t *count) {
     case 1: *dev = ag->critic_grads; *count = int64_t(ag->n) * ag->critic_stride; break;
     case 2: *dev = ag->actor.rmean; *count = int64_t(2) * ag->L * ag->ldh; break;          // BatchNorm running stats
     case 3: *dev = ag->mdev; *count = 32; break;
-    default: throw Error(GCRL_ERR_INVALID, "which must be 0 (actor grad), 1 (critic grads), 2 (BN stats), 3 (metrics)");
+    case 4:
+      GCRL_REQUIRE(ag->bn_gather != nullptr, "gcrl_sac_set_sync_bn first");
+      *dev = ag->bn_gather; *count = int64_t(ag->sync_world) * 2 * ag->ldh; break;          // [world][2 ldh]
+    default:
+      throw Error(GCRL_ERR_INVALID,
+                  "which must be 0 (actor grad), 1 (critic grads), 2 (BN running stats), 3 (metrics), 4 (sync-BN slots)");
   }
   GCRL_API_END
 }

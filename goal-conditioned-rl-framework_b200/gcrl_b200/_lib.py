@@ -117,6 +117,9 @@ SIGNATURES = {
     "gcrl_sac_act": (C.c_int, [vp, c_i64, vp, vp, vp, vp]),
     "gcrl_sac_update_phase": (C.c_int, [vp, C.c_int, vp, c_i64, vp, vp, vp, vp, vp, vp, vp, vp, c_f64, c_f64, C.c_int,
                                         vp]),
+    "gcrl_sac_set_sync_bn": (C.c_int, [vp, C.c_int, C.c_int]),
+    "gcrl_sac_update_segment": (C.c_int, [vp, C.c_int, vp, c_i64, vp, vp, vp, vp, vp, vp, vp, vp, c_f64, c_f64, C.c_int,
+                                          C.POINTER(C.c_int), vp]),
     "gcrl_sac_dp_buffer": (C.c_int, [vp, C.c_int, pp, C.POINTER(c_i64)]),
     "gcrl_sac_read_metrics": (C.c_int, [vp, C.c_int, vp, vp]),
     # uniform / prioritised replay
@@ -159,7 +162,7 @@ def _load():
         fn = getattr(dll, name)          # AttributeError if the library lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if dll.gcrl_abi_version() != 4:
+    if dll.gcrl_abi_version() != 5:
         raise ImportError("libgcrl_b200.so ABI version mismatch")
     return dll
 

@@ -181,6 +181,7 @@ class _SacBase(_AgentBase):
     ALGO = ALGO_SAC
     N_CRITICS, DROP_TOP = 2, 1
     ENTROPY_COEF = 0.2
+    _sync_bn = None          # set by enable_data_parallel(sync_bn=True): the BatchNorm statistics all-gather
 
     def __init__(self, obs_dim, ac_dim, config, weights, nenvs, gradient_step, *,
                  index_source="host", device=0, max_batch=None, seed=1898):
@@ -282,6 +283,34 @@ class _SacBase(_AgentBase):
         return self._per
 
     # -- data parallel: same GradAverager as DDPG / TD3 over the buffers of gcrl_sac_dp_buffer -------
+    def enable_data_parallel(self, process_group=None, allreduce_mean=None, sync_bn=True, *, world=None, rank=None,
+                             allgather=None):
+        """Gradient averaging between the update phases as for DDPG / TD3, plus -- ``sync_bn=True``, the default --
+        BatchNorm batch statistics over the GLOBAL batch, so that N ranks on B rows each equal one rank on the
+        concatenated N * B rows (the reference is single-GPU, src/model.py:103-111 normalises over the
+        whole batch).  Every rank must use the same local batch size.  ``sync_bn=False`` keeps local statistics
+        (torch DDP's default without SyncBatchNorm: 4 phases, 3 collectives per update instead of 3 + 3 per
+        BatchNorm layer) and averages the running statistics after every update.
+        ``world`` / ``rank`` / ``allgather(slots_tensor)`` override torch.distributed (tests)."""
+        dp = super().enable_data_parallel(process_group, allreduce_mean)
+        self._sync_bn = None
+        if not sync_bn:
+            check(lib.gcrl_sac_set_sync_bn(self._h, 0, 0))
+            return dp
+        if world is None:
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+        check(lib.gcrl_sac_set_sync_bn(self._h, int(world), int(rank)))
+        slots = self.grad_tensor(4)
+        if allgather is None:
+            import torch.distributed as dist
+            mine = slots.view(int(world), -1)[int(rank)]
+
+            def allgather(t, _mine=mine, _group=process_group):
+                dist.all_gather_into_tensor(t, _mine, group=_group)      # in place: row `rank` is the input
+        self._sync_bn = lambda: allgather(slots)
+        return dp
+
     def grad_tensor(self, which):
         from .parallel import device_tensor
         ptr, n = vp(), C.c_int64()
@@ -321,7 +350,22 @@ class _SacBase(_AgentBase):
             bufh = self.buffer.handle
         else:
             ptrs = tuple(vp(t.data_ptr()) for t in batch)
-        if self._dp is not None:
+        if self._dp is not None and self._sync_bn is not None:
+            # sync-BN: graph segments, each ending in the collective the C side names (include/gcrl_b200.h)
+            st = self._stream()
+            coll = C.c_int(0)
+            for seg in range(1 << 16):
+                check(lib.gcrl_sac_update_segment(self._h, seg, bufh, B, iptr, *ptrs, en, ec, lr_c, lr_a, flags,
+                                                  C.byref(coll), st))
+                if coll.value == 0:
+                    break
+                if coll.value == 1:
+                    self._sync_bn()                        # all-gather of the BatchNorm partial statistics
+                else:
+                    self._dp.average((1,) if coll.value == 2 else (0,))
+            self._dp.average_metrics()
+            check(lib.gcrl_sac_read_metrics(self._h, flags, mptr, st))
+        elif self._dp is not None:
             st = self._stream()
             for phase in range(4):
                 check(lib.gcrl_sac_update_phase(self._h, phase, bufh, B, iptr, *ptrs, en, ec, lr_c, lr_a, flags, st))

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GCRL_ABI_VERSION 4
+#define GCRL_ABI_VERSION 5
 
 #define GCRL_OK 0
 #define GCRL_ERR_INVALID 1      /* bad argument / shape                                  */
@@ -365,8 +365,28 @@ int gcrl_sac_update_phase(gcrl_sac *h, int phase, gcrl_her *buf, int64_t B, cons
                           const float *d_dev, const float *eps_next_dev, const float *eps_cur_dev,
                           double lr_critic, double lr_actor, int flags, void *stream);
 /* which: 0 actor gradient (+ 4 trailing floats: alpha's batch mean), 1 all critic gradients (contiguous),
- * 2 BatchNorm running mean | var of every layer, 3 the 32-float device metrics block. */
+ * 2 BatchNorm running mean | var of every layer, 3 the 32-float device metrics block, 4 the sync-BN slots
+ * [world][2 * pad4(hidden)] (after gcrl_sac_set_sync_bn; this rank's slot is row `rank`). */
 int gcrl_sac_dp_buffer(gcrl_sac *h, int which, float **dev, int64_t *count);
+/* Sync-BN: BatchNorm1d of SACActorModel (src/model.py:103-111) normalises with the statistics of the WHOLE
+ * global batch, so that `world` ranks on B rows each equal one rank on the concatenated world * B rows (the 1-GPU
+ * semantics; all ranks must use the same B).  gcrl_sac_set_sync_bn(world, rank) switches it on (world = 0: off;
+ * world = 1 reproduces gcrl_sac_update_* bit for bit).  The update is then issued as a chain of graph segments:
+ *     for (seg = 0;; ++seg) {
+ *       gcrl_sac_update_segment(h, seg, ..., &collective, stream);
+ *       if (collective == 0) break;                       update complete
+ *       1: all-gather the sync-BN slots (which = 4: every rank contributes row `rank`, in place)
+ *       2: average the critic gradients (which = 1)      3: average the actor gradient + alpha mean (which = 0)
+ *     }
+ * on `stream`, every rank issuing the same sequence.  Segment 0 takes the batch (arguments as
+ * gcrl_sac_update_phase phase 0); later segments only need (B, flags) to match.  2 * layer_count gathers for the
+ * forward passes of a critic+actor update, layer_count for the backward pass; the running statistics come out
+ * identical on every rank (no average of which = 2 needed). */
+int gcrl_sac_set_sync_bn(gcrl_sac *h, int world, int rank);
+int gcrl_sac_update_segment(gcrl_sac *h, int segment, gcrl_her *buf, int64_t B, const int64_t *idx_host,
+                            const float *s_dev, const float *a_dev, const float *r_dev, const float *ns_dev,
+                            const float *d_dev, const float *eps_next_dev, const float *eps_cur_dev,
+                            double lr_critic, double lr_actor, int flags, int *collective, void *stream);
 /* The metrics tuple of the most recent update (float[12], same order as gcrl_sac_update_batch). */
 int gcrl_sac_read_metrics(gcrl_sac *h, int flags, float *metrics_host, void *stream);
 

@@ -131,38 +131,65 @@ def p2p_section(rank, world, local):
 
 def tqc_section(rank, world, local):
     """TQC over NCCL: every rank on its own batch and noise; replicas (weights, log_alpha, BatchNorm running
-    statistics) must stay bit-identical across ranks."""
+    statistics) must stay bit-identical across ranks.  With sync-BN (the default) the ranks must also equal ONE rank
+    on the concatenated batch at the weights_close tolerance."""
     from oracle import ddpg as OD
     from oracle import sac as OS
     from gcrl_b200 import TQCAgent
-    from tests.test_sac_gpu import load_initial, sac_config
+    from tests.helpers import assert_sac_actor_close, weights_close
+    from tests.test_sac_gpu import actor_params, assert_running_stats_close, load_initial, sac_config
     D, A, H, L, B = 22, 3, 64, 3, 128
-    rng = np.random.default_rng(7)
-    cfg = sac_config(hidden_dim=H, layer_count=L, batch_size=B, grad_clip=0.5, tau=0.05, alpha_min_steps=0, alpha_lr=1e-2)
-    actor0, stats0 = OS.init_sac_actor(rng, D, H, A, L, head_scale=0.1, log_std_bias=-1.0)
-    critics0 = [OD.init_mlp(rng, D + A, H, 1, L) for _ in range(5)]
-    ag = TQCAgent(D, A, cfg, None, 1, 2, device=local)
-    load_initial(ag, actor0, stats0, critics0)
-    ag.enable_data_parallel()
     dev = torch.device("cuda", local)
-    for step in (1, 2, 3):
-        per_rank = []
-        for _ in range(world):
-            b = rand_batch_on(rng, B, D, A, local)
-            e = [torch.from_numpy(rng.standard_normal((B, A)).astype(np.float32)).to(dev) for _ in range(2)]
-            per_rank.append((b, e))
-        b, e = per_rank[rank]
-        info = ag.update(step, batch=b, eps_next=e[0], eps_cur=e[1])
-        assert len(info) == 9 and all(np.isfinite(float(x)) for x in info)
-    parts = [torch.from_numpy(w).reshape(-1) for v in ag._critic_views + ag._target_views for w, _ in v.layers()]
-    parts += [torch.from_numpy(np.concatenate([x.reshape(-1) for x in ag.actor.bn(l)])) for l in range(L)]
-    parts += [torch.from_numpy(ag.actor.linear(l)[0]).reshape(-1) for l in range(L + 2)]
-    parts.append(torch.tensor([ag.get_log_alpha()]))
-    flat = torch.cat(parts).to(dev)
-    gathered = [torch.empty_like(flat) for _ in range(world)]
-    dist.all_gather(gathered, flat)
-    for g in gathered[1:]:
-        assert torch.equal(g, gathered[0]), "TQC replicas diverged"
+    for sync_bn in (True, False):
+        rng = np.random.default_rng(7)
+        actor0, stats0 = OS.init_sac_actor(rng, D, H, A, L, head_scale=0.1, log_std_bias=-1.0)
+        critics0 = [OD.init_mlp(rng, D + A, H, 1, L) for _ in range(5)]
+
+        def make(batch):
+            cfg = sac_config(hidden_dim=H, layer_count=L, batch_size=batch, grad_clip=0.5, tau=0.05, alpha_min_steps=0,
+                             alpha_lr=1e-2)
+            a = TQCAgent(D, A, cfg, None, 1, 2, device=local)
+            load_initial(a, actor0, stats0, critics0)
+            return a
+        ag = make(B)
+        ag.enable_data_parallel(sync_bn=sync_bn)
+        single = make(world * B) if (sync_bn and rank == 0) else None
+        nsteps = 4
+        for step in range(1, nsteps + 1):
+            per_rank = []
+            for _ in range(world):
+                b = rand_batch_on(rng, B, D, A, local)
+                e = [torch.from_numpy(rng.standard_normal((B, A)).astype(np.float32)).to(dev) for _ in range(2)]
+                per_rank.append((b, e))
+            b, e = per_rank[rank]
+            info = ag.update(step, batch=b, eps_next=e[0], eps_cur=e[1])
+            assert len(info) in (6, 9) and all(np.isfinite(float(x)) for x in info)
+            if single is not None:
+                cat = tuple(torch.cat([pr[0][k] for pr in per_rank]) for k in range(5))
+                e0 = torch.cat([pr[1][0] for pr in per_rank])
+                e1 = torch.cat([pr[1][1] for pr in per_rank])
+                want = single.update(step, batch=cat, eps_next=e0, eps_cur=e1)
+                np.testing.assert_allclose([float(x) for x in info[:2]], [float(x) for x in want[:2]], rtol=2e-5,
+                                           atol=1e-6, err_msg="sync-BN critic losses (averaged over ranks) vs one rank")
+        parts = [torch.from_numpy(w).reshape(-1) for v in ag._critic_views + ag._target_views for w, _ in v.layers()]
+        parts += [torch.from_numpy(np.concatenate([x.reshape(-1) for x in ag.actor.bn(l)])) for l in range(L)]
+        parts += [torch.from_numpy(ag.actor.linear(l)[0]).reshape(-1) for l in range(L + 2)]
+        parts.append(torch.tensor([ag.get_log_alpha()]))
+        flat = torch.cat(parts).to(dev)
+        gathered = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        for g in gathered[1:]:
+            assert torch.equal(g, gathered[0]), f"TQC replicas diverged (sync_bn={sync_bn})"
+        if single is not None:
+            (p0, s0), (ps, ss) = actor_params(ag), actor_params(single)
+            assert_sac_actor_close(p0, ps, 1e-3, nsteps)
+            assert_running_stats_close(p0, s0, ps, ss)
+            for v0, vs in zip(ag._critic_views + ag._target_views, single._critic_views + single._target_views):
+                for (w, b_), (ws, bs) in zip(v0.layers(), vs.layers()):
+                    assert weights_close(w, ws, 1e-3, nsteps) and weights_close(b_, bs, 1e-3, nsteps), "sync-BN critic"
+            assert abs(ag.get_log_alpha() - single.get_log_alpha()) <= 1e-6
+        dist.barrier()
+        del ag, single
 
 
 def make_agent_on(dev, D, A, H, L, B):

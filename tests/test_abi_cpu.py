@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_error_string():
     from gcrl_b200 import _lib
-    assert _lib.lib.gcrl_abi_version() == 4
+    assert _lib.lib.gcrl_abi_version() == 5
     assert isinstance(_lib.lib.gcrl_last_error(), bytes)
 
 
@@ -74,7 +74,7 @@ def test_header_compiles_as_plain_c_and_struct_sizes_agree(tmp_path):
     subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.dirname(HEADER), str(src), "-o", str(exe)],
                    check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
-    assert [int(x) for x in out] == [ctypes.sizeof(AgentConfig), ctypes.sizeof(SacConfig), 4]
+    assert [int(x) for x in out] == [ctypes.sizeof(AgentConfig), ctypes.sizeof(SacConfig), 5]
 
 
 def test_no_cpu_fallback_without_device():

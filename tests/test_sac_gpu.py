@@ -176,11 +176,15 @@ def _make(algo, D, A, H, L, B, seed=5):
     return ag
 
 
+@pytest.mark.parametrize("sync_bn", [False, True])
 @pytest.mark.parametrize("algo", ["sac", "tqc"])
-def test_world1_phases_equal_whole_update_bitwise(algo):
+def test_world1_phases_equal_whole_update_bitwise(algo, sync_bn):
+    """World of one: the four data-parallel phases (local BatchNorm statistics) and the sync-BN segment chain
+    (statistics merged over the ranks' slots) both reproduce the whole update bit for bit."""
     D, A, H, L, B = 22, 3, 64, 3, 128
     whole, phased = _make(algo, D, A, H, L, B), _make(algo, D, A, H, L, B)
-    phased.enable_data_parallel(allreduce_mean=lambda t: t)            # world of one: identity
+    phased.enable_data_parallel(allreduce_mean=lambda t: t, sync_bn=sync_bn, world=1, rank=0,
+                                allgather=lambda t: t)                 # world of one: identity
     rng = np.random.default_rng(0)
     for step in (1, 2, 3):
         *batch, e1, e2 = _rand_batch(rng, B, D, A)
@@ -248,6 +252,109 @@ def test_tqc_two_emulated_ranks_stay_replicated_and_track_the_averaged_gradient(
             assert np.array_equal(w, w2) and np.array_equal(b, b2)
     for (w, _), (ws, _) in zip(ranks[0]._critic_views[0].layers(), single._critic_views[0].layers()):
         assert np.max(np.abs(w - ws)) <= 2.0 * 1e-3 * 3                              # Adam's hard bound
+
+
+@pytest.mark.parametrize("algo,world", [("sac", 2), ("tqc", 2), ("tqc", 4)])
+def test_sync_bn_ranks_equal_one_rank_on_the_concatenated_batch(algo, world):
+    """with BatchNorm statistics taken over the global batch, `world` ranks on B rows each must equal ONE
+    rank on the concatenated world * B rows -- metrics and weights at the DDPG tolerance (tests/helpers.py), not the
+    2e-2 of the local-statistics mode.  The ranks are agents on one GPU driven in lock step through
+    gcrl_sac_update_segment; the collectives (slot all-gather, gradient averages) are done by hand exactly as NCCL does
+    them.  Replicas must stay bit-identical, running statistics included, without averaging them."""
+    import torch
+    from gcrl_b200._lib import check, lib, vp
+    D, A, H, L, B = 22, 3, 64, 3, 128
+    ranks = [_make(algo, D, A, H, L, B) for _ in range(world)]
+    single = _make(algo, D, A, H, L, world * B)
+    for r, ag in enumerate(ranks):
+        check(lib.gcrl_sac_set_sync_bn(ag._h, world, r))
+    slots = [ag.grad_tensor(4).view(world, -1) for ag in ranks]
+    rng = np.random.default_rng(2)
+    st = vp(torch.cuda.current_stream().cuda_stream)
+    nsteps, lr = 4, 1e-3
+    counts = {1: 0, 2: 0, 3: 0}
+    for step in range(1, nsteps + 1):
+        data = [_rand_batch(rng, B, D, A) for _ in ranks]
+        flags = (1 if step % 2 == 0 else 0) | 2 | (4 if step % 2 == 0 else 0)
+        seg = 0
+        while True:
+            colls = []
+            for ag, b in zip(ranks, data):
+                coll = C.c_int(-1)
+                check(lib.gcrl_sac_update_segment(ag._h, seg, None, B, None, *(vp(t.data_ptr()) for t in b[:5]),
+                                                  vp(b[5].data_ptr()), vp(b[6].data_ptr()), lr, lr, flags,
+                                                  C.byref(coll), st))
+                colls.append(coll.value)
+            assert len(set(colls)) == 1
+            if colls[0] == 0:
+                break
+            counts[colls[0]] += 1
+            if colls[0] == 1:                                   # all-gather: rank r contributes row r
+                for r in range(world):
+                    for q in range(world):
+                        if q != r:
+                            slots[q][r].copy_(slots[r][r])
+            else:
+                g = [ag.grad_tensor(1 if colls[0] == 2 else 0) for ag in ranks]
+                mean = sum(g[1:], g[0].clone()) / world
+                for t in g:
+                    t.copy_(mean)
+            seg += 1
+        cat = [torch.cat(x) for x in zip(*data)]
+        info = _update_with_flags(single, step, cat, flags, lr)
+        m = []
+        for ag in ranks:
+            buf = (C.c_float * 12)()
+            check(lib.gcrl_sac_read_metrics(ag._h, flags, C.cast(buf, vp), st))
+            m.append(np.array(list(buf)))
+        got = sum(m) / world
+        np.testing.assert_allclose(got[:5], info[:5], rtol=2e-5, atol=1e-6)          # losses / td / q
+        assert all(np.array_equal(m[0][9:11], x[9:11]) for x in m[1:])              # alpha, log_alpha replicated
+    # per update: L gathers for the target-policy forward (+ 2 L on actor steps), one critic average, one actor average
+    assert counts == {1: L * nsteps + 2 * L * (nsteps // 2), 2: nsteps, 3: nsteps // 2}
+    p0, s0 = actor_params(ranks[0])
+    for ag in ranks[1:]:
+        p1, s1 = actor_params(ag)
+        for (w, b), (w2, b2) in zip(p0 + s0, p1 + s1):
+            assert np.array_equal(w, w2) and np.array_equal(b, b2)
+        for v0, v1 in zip(ranks[0]._critic_views + ranks[0]._target_views, ag._critic_views + ag._target_views):
+            for (w, b), (w2, b2) in zip(v0.layers(), v1.layers()):
+                assert np.array_equal(w, w2) and np.array_equal(b, b2)
+    ps, ss = actor_params(single)
+    assert_sac_actor_close(p0, ps, lr, nsteps)      # pre-BatchNorm biases (zero true gradient): Adam's hard bound
+    assert_running_stats_close(p0, s0, ps, ss)
+    for i, (v0, vs) in enumerate(zip(ranks[0]._critic_views + ranks[0]._target_views,
+                                     single._critic_views + single._target_views)):
+        for k, ((w, b), (ws, bs)) in enumerate(zip(v0.layers(), vs.layers())):
+            assert weights_close(w, ws, lr, nsteps) and weights_close(b, bs, lr, nsteps), f"critic {i} layer {k}"
+    assert abs(ranks[0].get_log_alpha() - single.get_log_alpha()) <= 1e-6
+    # a sync-BN agent refuses the whole-update entry points instead of silently using local statistics
+    with pytest.raises(ValueError):
+        _update_with_flags(ranks[0], 9, [x[:B] for x in cat], flags, lr)
+
+
+def assert_running_stats_close(params, stats, ref_params, ref_stats):
+    """BatchNorm running statistics of two runs that should agree.  The running mean of layer l is an average of
+    batch means of z = W x + b, so it inherits the drift of the pre-BatchNorm bias b one to one -- and that bias has
+    an exactly-zero true gradient, i.e. AdamW moves it by rounding noise (assert_sac_actor_close holds it to Adam's
+    hard bound only; it cannot change the train-mode output).  Allowance: 3 x the observed bias difference + 2e-6;
+    the running variance does not see the bias and is held to rel 2e-5."""
+    for k, ((rm, rv), (rms, rvs)) in enumerate(zip(stats, ref_stats)):
+        db = float(np.max(np.abs(np.asarray(params[2 * k][1], np.float64) - ref_params[2 * k][1])))
+        np.testing.assert_allclose(rm, rms, rtol=1e-5, atol=3.0 * db + 2e-6, err_msg=f"running_mean {k}")
+        np.testing.assert_allclose(rv, rvs, rtol=2e-5, atol=1e-7, err_msg=f"running_var {k}")
+
+
+def _update_with_flags(ag, step, cat, flags, lr):
+    """One whole update through the C ABI with explicit flags / learning rates (the Python update() derives them from
+    the step number and the schedulers)."""
+    import torch
+    from gcrl_b200._lib import check, lib, vp
+    buf = (C.c_float * 12)()
+    st = vp(torch.cuda.current_stream().cuda_stream)
+    check(lib.gcrl_sac_update_batch(ag._h, cat[0].shape[0], *(vp(t.data_ptr()) for t in cat[:5]),
+                                    vp(cat[5].data_ptr()), vp(cat[6].data_ptr()), lr, lr, flags, C.cast(buf, vp), st))
+    return np.array(list(buf))
 
 
 @pytest.mark.parametrize("algo", ["sac", "tqc"])
