@@ -19,9 +19,11 @@
 // tile i overlaps the MMAs of tile i+1).
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <tuple>
+#include <vector>
 
 #include "mlp.cuh"
 
@@ -113,10 +115,80 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
          (uint64_t(1) << 46) | (uint64_t(1) << 61);
 }
 
+// One lane of a converged warp.  The producer and MMA warps run their loops with ALL lanes (uniform control flow) and
+// elect the issuing lane only around the asynchronous instructions: the operands (descriptors, coordinates, barrier
+// addresses) are then provably warp-uniform and live in uniform registers.  Inside an `if (lane == 0)` region the
+// compiler wraps every UTCHMMA / UTMALDG in a broadcast loop (ELECT, 5 x R2UR.BROADCAST, BRA.U.ANY: ~200 clk per MMA
+// for 128 clk of tensor work) -- that loop, not shared memory or L2, bounded the first versions of these kernels.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ uint32_t rna_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return r;
+}
+
+// Epilogue of one 32-row x 32-column accumulator chunk that a warp has staged in shared memory (row stride kStgLd):
+// lane = 4 columns of one of 4 rows, 8 row groups, so that every global access is a full 128-byte row segment.
+// All 8 shared loads (and, for the input gradient, all 8 loads of the saved activation) are issued before the first
+// store: with the loads, the arithmetic and the store of one row group chained through the same four registers the
+// eight groups ran back to back at ~300 clk each, and the epilogue (10 us per 128 x 256 tile), not the MMAs (8 us),
+// set the pace of the whole kernel (profiles/README.md, timeline of the CTA-pair kernel).
+//   mode 0: leaky(acc + bias)   1: acc * leaky'(act)   2: acc + bias   3: acc
+__device__ __forceinline__ void epilogue_store32(uint32_t stg, int lane, int row0, int col0, int rows_valid,
+                                                 int cols_valid, int mode, const float *__restrict__ bias,
+                                                 const float *__restrict__ act, int ldact, float *__restrict__ out,
+                                                 int ldo) {
+  const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+  const int col = col0 + sub_c;
+  if (col >= cols_valid) return;                       // widths are multiples of 4 (padded leading dimensions)
+  float4 x[8];
+#pragma unroll
+  for (int r8 = 0; r8 < 8; ++r8)
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(x[r8].x), "=f"(x[r8].y), "=f"(x[r8].z), "=f"(x[r8].w)
+                 : "r"(stg + uint32_t((r8 * 4 + sub_r) * kStgLd + sub_c) * 4));
+  if (mode == 1) {
+    float4 h[8];
+#pragma unroll
+    for (int r8 = 0; r8 < 8; ++r8) {
+      const int row = row0 + r8 * 4 + sub_r;
+      h[r8] = row < rows_valid ? *reinterpret_cast<const float4 *>(act + size_t(row) * ldact + col)
+                               : make_float4(1.f, 1.f, 1.f, 1.f);
+    }
+#pragma unroll
+    for (int r8 = 0; r8 < 8; ++r8) {
+      x[r8].x = h[r8].x > 0.f ? x[r8].x : x[r8].x * kLeakySlope;
+      x[r8].y = h[r8].y > 0.f ? x[r8].y : x[r8].y * kLeakySlope;
+      x[r8].z = h[r8].z > 0.f ? x[r8].z : x[r8].z * kLeakySlope;
+      x[r8].w = h[r8].w > 0.f ? x[r8].w : x[r8].w * kLeakySlope;
+    }
+  } else if (mode != 3) {
+    const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + col));
+#pragma unroll
+    for (int r8 = 0; r8 < 8; ++r8) {
+      x[r8].x += bv.x; x[r8].y += bv.y; x[r8].z += bv.z; x[r8].w += bv.w;
+      if (mode == 0) {
+        x[r8].x = x[r8].x > 0.f ? x[r8].x : x[r8].x * kLeakySlope;
+        x[r8].y = x[r8].y > 0.f ? x[r8].y : x[r8].y * kLeakySlope;
+        x[r8].z = x[r8].z > 0.f ? x[r8].z : x[r8].z * kLeakySlope;
+        x[r8].w = x[r8].w > 0.f ? x[r8].w : x[r8].w * kLeakySlope;
+      }
+    }
+  }
+#pragma unroll
+  for (int r8 = 0; r8 < 8; ++r8) {
+    const int row = row0 + r8 * 4 + sub_r;
+    if (row < rows_valid) *reinterpret_cast<float4 *>(out + size_t(row) * ldo + col) = x[r8];
+  }
 }
 
 struct TcArgs {
@@ -130,6 +202,7 @@ struct TcArgs {
   // the batch is the reduction; n_tiles = ceil(N / 128), k_tiles = ceil(K / BN); M rows in nslabs slabs
   int kind, rows_per_slab, nslabs, k_tiles;
   long long split_stride;
+  long long *trace;              // GCRL_TC_TRACE: per-stage timestamps of the first CTA pair (pair kernel only)
   int dbg;                       // timing experiments only (GCRL_TC_DBG): 1 skip split, 2 skip stores, 4 one MMA per k step
 };
 
@@ -206,16 +279,16 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   };
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const Tile ti = decode(t);
-        for (int kb = 0; kb < ti.nk; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(empty(s), ((it / STAGES) & 1) ^ 1);
+    // ===== TMA producer (whole warp in the loop, one elected lane issues) =====
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const Tile ti = decode(t);
+      for (int kb = 0; kb < ti.nk; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(empty(s), ((it / STAGES) & 1) ^ 1);
+        const uint32_t st = base + s * S::kStage;
+        if (elect_one()) {
           mbar_expect_tx(full(s), S::kA + (PRESPLIT ? 2 : 1) * S::kB);
-          const uint32_t st = base + s * S::kStage;
           if (!wg) {
             tma_load_2d(st, &tmA, full(s), kb * BKF, ti.m0);
             tma_load_2d(st + 2 * S::kA, &tmB, full(s), kb * BKF, ti.n0);
@@ -229,11 +302,12 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int b = 0; b < BN / 32; ++b) tma_load_2d(st + 2 * S::kA + b * 2048, &tmB, full(s), ti.n0 + 32 * b, r);
           }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer (whole warp in the loop, one elected lane issues) =====
+    {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6) = 1, A/B = TF32 [7,10),[10,13) = 2,
       // K-major both, N >> 3 at [17,23), M >> 4 at [24,29)
       // kind 1: A and B MN-major (bits 15, 16)
@@ -255,20 +329,24 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint64_t a_lo = wg ? umma_desc_mn(st + S::kA) : umma_desc_sw(st + S::kA);
           const uint64_t b_hi = wg ? umma_desc_mn(st + 2 * S::kA) : umma_desc_sw(st + 2 * S::kA);
           const uint64_t b_lo = wg ? umma_desc_mn(st + 2 * S::kA + S::kB) : umma_desc_sw(st + 2 * S::kA + S::kB);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BKF / 8; ++k) {
-            // UMMA K = 8 for tf32.  K-major: 32 bytes along the swizzled row (+2 in the >>4 address);
-            // MN-major: the next 8-row group of every box (+1024 bytes)
-            const uint64_t ko = wg ? uint64_t(k * (1024 >> 4)) : uint64_t(k * 2);
-            umma_tf32(d, a_lo + ko, b_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
-            if (!(a.dbg & 4)) {
-              umma_tf32(d, a_hi + ko, b_lo + ko, idesc, 1u);
-              umma_tf32(d, a_hi + ko, b_hi + ko, idesc, 1u);
+            for (int k = 0; k < BKF / 8; ++k) {
+              // UMMA K = 8 for tf32.  K-major: 32 bytes along the swizzled row (+2 in the >>4 address);
+              // MN-major: the next 8-row group of every box (+1024 bytes)
+              const uint64_t ko = wg ? uint64_t(k * (1024 >> 4)) : uint64_t(k * 2);
+              umma_tf32(d, a_lo + ko, b_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (!(a.dbg & 4)) {
+                umma_tf32(d, a_hi + ko, b_lo + ko, idesc, 1u);
+                umma_tf32(d, a_hi + ko, b_hi + ko, idesc, 1u);
+              }
             }
+            umma_commit(empty(s));                      // smem stage reusable once these MMAs retire
           }
-          umma_commit(empty(s));                        // smem stage reusable once these MMAs retire
+          __syncwarp();
         }
-        umma_commit(tfull(as));                         // accumulator complete
+        if (elect_one()) umma_commit(tfull(as));        // accumulator complete
+        __syncwarp();
       }
     }
   } else if (warp < 6) {
@@ -287,11 +365,14 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // 32 accumulator columns at a time: TMEM -> registers (lane = row) -> padded smem tile ->
       // (lane = 4 columns of one of 4 rows) so that every global access is a full 128-byte row segment
       const uint32_t stg = stage_base + uint32_t(q) * (32 * kStgLd * 4);
-      const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = 0; c < ((a.dbg & 64) ? 0 : BN); c += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + uint32_t(c), v);
+        if (a.dbg & 128) {
+          asm volatile("" ::"r"(v[0]), "r"(v[31]));
+          continue;
+        }
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
@@ -299,40 +380,9 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                        "r"(v[j + 1]), "r"(v[j + 2]), "r"(v[j + 3])
                        : "memory");
         __syncwarp();
-        const int col = n0 + c + sub_c;
-        if (col < cols_valid && !(a.dbg & 2)) {         // widths are multiples of 4 (padded leading dims)
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (a.mode == 0 || a.mode == 2) bv = __ldg(reinterpret_cast<const float4 *>(a.bias + col));
-#pragma unroll
-          for (int r8 = 0; r8 < 8; ++r8) {
-            const int lr = r8 * 4 + sub_r;
-            const int row = m0 + q * 32 + lr;
-            float4 x;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
-                         : "r"(stg + uint32_t(lr * kStgLd + sub_c) * 4));
-            if (row < rows_valid) {
-              if (a.mode == 3) {
-                // plain store (weight-gradient partial slab)
-              } else if (a.mode == 1) {
-                const float4 h = *reinterpret_cast<const float4 *>(a.act + size_t(row) * a.ldact + col);
-                x.x = h.x > 0.f ? x.x : x.x * kLeakySlope;
-                x.y = h.y > 0.f ? x.y : x.y * kLeakySlope;
-                x.z = h.z > 0.f ? x.z : x.z * kLeakySlope;
-                x.w = h.w > 0.f ? x.w : x.w * kLeakySlope;
-              } else {
-                x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
-                if (a.mode == 0) {
-                  x.x = x.x > 0.f ? x.x : x.x * kLeakySlope;
-                  x.y = x.y > 0.f ? x.y : x.y * kLeakySlope;
-                  x.z = x.z > 0.f ? x.z : x.z * kLeakySlope;
-                  x.w = x.w > 0.f ? x.w : x.w * kLeakySlope;
-                }
-              }
-              *reinterpret_cast<float4 *>(obase + size_t(row) * a.ldo + col) = x;
-            }
-          }
-        }
+        if (!(a.dbg & 2))
+          epilogue_store32(stg, lane, m0 + q * 32, n0 + c, rows_valid, cols_valid, a.mode, a.bias, a.act, a.ldact, obase,
+                           a.ldo);
       }
       tc_fence_before();
       __syncwarp();
@@ -396,6 +446,276 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+  }
+}
+
+// ---- CTA-pair variant (cta_group::2): dense forward / input gradient with pre-split weights, N % 256 == 0 -------
+// Two CTAs on the two SMs of a TPC compute one 256-row x 256-column tile: each CTA stages ITS 128 activation rows
+// (TMA -> in-smem hi / lo split, as above) and only ITS HALF (128 of the 256 rows) of the pre-split weight tile; the
+// tensor cores of the pair read both halves.  Per 16-wide K tile and SM that is 24 KB of TMA writes instead of 40 and
+// 48 KB of operand reads instead of 72 -- the shared-memory port (128 B/clk) is what bounds the single-CTA kernel
+// (DESIGN.md 4).  The leader (cluster rank 0) issues every MMA; accumulators: rows 0-127 in the leader's TMEM,
+// 128-255 in the peer's, two stages of 256 columns each.
+//   full[s]        TMA -> splitter                (per CTA)
+//   split_done[s]  splitter -> MMA / relay        (per CTA, all splitter threads)
+//   peer_ready[s]  the peer's relay thread (its otherwise idle MMA warp) -> leader: "my stage s is split"
+//   empty[s]       MMA commit, multicast to both CTAs -> TMA
+//   tfull[a]       MMA commit, multicast -> epilogue of both CTAs;  tempty[a]  both epilogues -> leader MMA
+template <int STAGES2>
+struct TcSmem2 {
+  static constexpr int kA = BM * ROWB;                       // 128 activation rows
+  static constexpr int kBh = 128 * ROWB;                     // this CTA's half of the 256 weight rows
+  static constexpr int kStage = 2 * kA + 2 * kBh;            // A_hi | A_lo | B_hi | B_lo
+  static constexpr int kBytes = STAGES2 * kStage + 1024 + 512 + 4 * 32 * kStgLd * 4;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default semantics (release at CTA scope), as CUTLASS's ClusterBarrier::arrive: the .release.cluster form compiles
+  // to MEMBAR + ERRBAR in front of the arrive, ~800 clk per call -- with one call per stage in the relay thread that
+  // alone bounded the pair kernel at 27 us (profiles/README.md)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {      // arrives on `bar` in BOTH CTAs of the pair
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask)
+               : "memory");
+}
+
+template <int STAGES2>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+tc_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                     const __grid_constant__ CUtensorMap tmBlo, TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  using S = TcSmem2<STAGES2>;
+  constexpr int BN = 256;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + STAGES2 * S::kStage;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto split_done = [&](int s) { return bars + 8u * (STAGES2 + s); };
+  auto peer_ready = [&](int s) { return bars + 8u * (2 * STAGES2 + s); };
+  auto empty = [&](int s) { return bars + 8u * (3 * STAGES2 + s); };
+  auto tfull = [&](int s) { return bars + 8u * (4 * STAGES2 + s); };
+  auto tempty = [&](int s) { return bars + 8u * (4 * STAGES2 + 2 + s); };
+  const uint32_t tmem_slot = bars + 8u * (4 * STAGES2 + 4);
+  const uint32_t stage_base = bars + 512;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  // timeline of the first pair (GCRL_TC_TRACE=file): globaltimer at the hand-over points of every stage use
+  auto mark = [&](int role, uint32_t it) {
+    if (a.trace != nullptr && blockIdx.x < 2 && it < 64) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      a.trace[(size_t(blockIdx.x) * 8 + role) * 64 + it] = t;
+    }
+  };
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(split_done(s), kSplitWarps);
+      mbar_init(peer_ready(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull(s), 1);
+      mbar_init(tempty(s), 8);                         // 4 epilogue warps in each CTA of the pair
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2 * BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();                                  // barriers of both CTAs initialised before any remote arrive
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int total_tiles = a.m_tiles * a.n_tiles;       // m_tiles: 256-row tiles
+  const int nk = (a.K + BKF - 1) / BKF;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs: own activation rows, own half of the weight rows) =====
+    uint32_t it = 0;
+    for (int t = pair; t < total_tiles; t += npairs) {
+      const int m0 = (t / a.n_tiles) * 256 + int(rank) * BM;
+      const int nb = (t % a.n_tiles) * BN + int(rank) * 128;
+      for (int kb = 0; kb < nk; ++kb, ++it) {
+        const int s = it % STAGES2;
+        mbar_wait(empty(s), ((it / STAGES2) & 1) ^ 1);
+        const uint32_t st = base + s * S::kStage;
+        if (elect_one()) {
+          mark(0, it);
+          mbar_expect_tx(full(s), S::kA + 2 * S::kBh);
+          tma_load_2d(st, &tmA, full(s), kb * BKF, m0);
+          tma_load_2d(st + 2 * S::kA, &tmBhi, full(s), kb * BKF, nb);
+          tma_load_2d(st + 2 * S::kA + S::kBh, &tmBlo, full(s), kb * BKF, nb);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ===== MMA issuer (leader only): M = 256 over the pair, N = 256 =====
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(256 >> 4) << 24);
+      uint32_t it = 0, tile_it = 0;
+      for (int t = pair; t < total_tiles; t += npairs, ++tile_it) {
+        const int as = tile_it & 1;
+        mbar_wait(tempty(as), ((tile_it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + uint32_t(as * BN);
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % STAGES2;
+          mbar_wait(split_done(s), (it / STAGES2) & 1);
+          mbar_wait(peer_ready(s), (it / STAGES2) & 1);
+          tc_fence_after();
+          const uint32_t st = base + s * S::kStage;
+          const uint64_t a_hi = umma_desc_sw(st), a_lo = umma_desc_sw(st + S::kA);
+          const uint64_t b_hi = umma_desc_sw(st + 2 * S::kA), b_lo = umma_desc_sw(st + 2 * S::kA + S::kBh);
+          if (elect_one()) {
+            mark(3, it);
+#pragma unroll
+            for (int k = 0; k < BKF / 8; ++k) {
+              const uint64_t ko = uint64_t(k * 2);
+              umma_tf32_pair(d, a_lo + ko, b_hi + ko, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (!(a.dbg & 4)) {
+                umma_tf32_pair(d, a_hi + ko, b_lo + ko, idesc, 1u);
+                umma_tf32_pair(d, a_hi + ko, b_hi + ko, idesc, 1u);
+              }
+            }
+            umma_commit_pair(empty(s));
+            mark(4, it);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit_pair(tfull(as));
+        __syncwarp();
+      }
+    } else {
+      // ===== relay (peer only): "my stage is split" -> the leader's peer_ready =====
+      uint32_t it = 0;
+      for (int t = pair; t < total_tiles; t += npairs)
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % STAGES2;
+          mbar_wait(split_done(s), (it / STAGES2) & 1);
+          if (elect_one()) {
+            mbar_arrive_cluster(map_to_cta(peer_ready(s), 0));
+            mark(5, it);
+          }
+          __syncwarp();
+        }
+    }
+  } else if (warp < 6) {
+    // ===== epilogue (both CTAs): own 128 rows, all 256 columns =====
+    const int q = warp & 3;
+    uint32_t tile_it = 0;
+    for (int t = pair; t < total_tiles; t += npairs, ++tile_it) {
+      const int m0 = (t / a.n_tiles) * 256 + int(rank) * BM, n0 = (t % a.n_tiles) * BN;
+      const int as = tile_it & 1;
+      if (lane == 0) mbar_wait(tfull(as), (tile_it >> 1) & 1);
+      __syncwarp();
+      tc_fence_after();
+      if (q == 0 && lane == 0) mark(6, tile_it);
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN);
+      const uint32_t stg = stage_base + uint32_t(q) * (32 * kStgLd * 4);
+#pragma unroll 1
+      for (int c = 0; c < ((a.dbg & 64) ? 0 : BN); c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + uint32_t(c), v);
+        if (a.dbg & 128) {
+          asm volatile("" ::"r"(v[0]), "r"(v[31]));
+          continue;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + uint32_t(lane * kStgLd + j) * 4), "r"(v[j]),
+                       "r"(v[j + 1]), "r"(v[j + 2]), "r"(v[j + 3])
+                       : "memory");
+        __syncwarp();
+        if (!(a.dbg & 2))
+          epilogue_store32(stg, lane, m0 + q * 32, n0 + c, a.M, a.N, a.mode, a.bias, a.act, a.ldact, a.out, a.ldo);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_cta(tempty(as), 0));
+      if (q == 0 && lane == 0) mark(7, tile_it);
+    }
+  } else {
+    // ===== hi / lo splitter (both CTAs): the activation tile only =====
+    const int tid = threadIdx.x - 6 * 32;
+    uint32_t it = 0;
+    for (int t = pair; t < total_tiles; t += npairs) {
+      for (int kb = 0; kb < nk; ++kb, ++it) {
+        const int s = it % STAGES2;
+        if (lane == 0) mbar_wait(full(s), (it / STAGES2) & 1);
+        __syncwarp();
+        if (tid == 0) mark(1, it);
+        const uint32_t st = base + s * S::kStage;
+        constexpr int kChunks = S::kA / 16, kPer = kChunks / kSplitThreads;
+        static_assert(kChunks % kSplitThreads == 0, "splitter threads must tile the activation stage");
+        float x[kPer][4];
+        if (!(a.dbg & 1)) {
+#pragma unroll
+        for (int u = 0; u < kPer; ++u)
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(x[u][0]), "=f"(x[u][1]), "=f"(x[u][2]), "=f"(x[u][3])
+                       : "r"(st + 16u * (tid + u * kSplitThreads)));
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+          const uint32_t hi_addr = st + 16u * (tid + u * kSplitThreads);
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            h[e] = rna_tf32(x[u][e]);
+            l[e] = rna_tf32(x[u][e] - __uint_as_float(h[e]));
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3])
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr + S::kA), "r"(l[0]), "r"(l[1]), "r"(l[2]),
+                       "r"(l[3])
+                       : "memory");
+        }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(split_done(s));
+        if (tid == 0) mark(2, it);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                                  // no CTA of the pair leaves while the other may still use it
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
   }
 }
 
@@ -494,6 +814,34 @@ void launch_bn(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap
   GCRL_LAUNCHED();
 }
 
+// CTA pairs that can be co-resident (one per TPC); 0 = the pair kernel is switched off (GCRL_TC_PAIR=0) or the
+// device cannot host it.  Queried once, outside stream capture (tc_dense_init).
+int pair_capacity() {
+  static int pairs = -1;
+  if (pairs < 0) {
+    pairs = 0;
+    const char *e = getenv("GCRL_TC_PAIR");
+    if (!(e && e[0] == '0')) {
+      GCRL_CUDA(cudaFuncSetAttribute(tc_dense_pair_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem2<6>::kBytes));
+      GCRL_CUDA(cudaFuncSetAttribute(tc_dense_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem2<3>::kBytes));
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(unsigned(sm_count() & ~1));
+      cfg.blockDim = dim3(kTcThreads);
+      cfg.dynamicSmemBytes = TcSmem2<6>::kBytes;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, tc_dense_pair_kernel<6>, &cfg) == cudaSuccess && n > 0)
+        pairs = std::min(n, sm_count() / 2);
+      else
+        cudaGetLastError();
+    }
+  }
+  return pairs;
+}
+
 }  // namespace
 
 // one-time host setup (driver entry point, shared-memory opt-in): call outside stream capture
@@ -502,6 +850,7 @@ void tc_dense_init() {
   set_attr<64>();
   set_attr<128>();
   set_attr<256>();
+  pair_capacity();
 }
 
 bool tc_dense_supported(int M, int N, int K) {
@@ -527,6 +876,40 @@ void launch_tc_dense(const float *X, int ldx, const float *W, int ldw, const flo
   a.m_tiles = (M + BM - 1) / BM;
   a.n_tiles = (N + BN - 1) / BN;
   if (const char *e = getenv("GCRL_TC_DBG")) a.dbg = atoi(e);
+  // CTA pairs (256 x 256 tiles, each SM stages half of the weight tile) once they alone fill 3/4 of the TPCs
+  int pairs = (W_lo != nullptr && N % 256 == 0) ? pair_capacity() : 0;
+  if (const char *e = getenv("GCRL_TC_PAIR_RT")) if (e[0] == '0') pairs = 0;      // microbenchmarks: per-launch switch
+  const int pair_tiles = ((M + 255) / 256) * (N / 256);
+  if (pairs > 0 && 4 * pair_tiles >= 3 * pairs) {
+    a.m_tiles = (M + 255) / 256;
+    a.n_tiles = N / 256;
+    const CUtensorMap tmA = make_map(X, M, K, ldx, BM);
+    const CUtensorMap tmBhi = make_map(W, N, K, ldw, 128);
+    const CUtensorMap tmBlo = make_map(W_lo, N, K, ldw, 128);
+    const int grid = 2 * std::min(pair_tiles, pairs);
+    if (getenv("GCRL_TC_VERBOSE")) fprintf(stderr, "[tc] pair kernel: %d pairs resident, %d tiles, grid %d\n", pairs, pair_tiles, grid);
+    const char *tr = getenv("GCRL_TC_TRACE");
+    constexpr size_t kTrace = 2 * 8 * 64;
+    if (tr != nullptr) {
+      GCRL_CUDA(cudaMalloc(&a.trace, kTrace * sizeof(long long)));
+      GCRL_CUDA(cudaMemsetAsync(a.trace, 0, kTrace * sizeof(long long), st));
+    }
+    const char *se = getenv("GCRL_TC_STAGES2");
+    if (se && se[0] == '3') tc_dense_pair_kernel<3><<<grid, kTcThreads, TcSmem2<3>::kBytes, st>>>(tmA, tmBhi, tmBlo, a);
+    else tc_dense_pair_kernel<6><<<grid, kTcThreads, TcSmem2<6>::kBytes, st>>>(tmA, tmBhi, tmBlo, a);
+    GCRL_LAUNCHED();
+    if (tr != nullptr) {          // debug only: synchronous dump, [cta 0..1][role 0..7][stage use 0..63] nanoseconds
+      std::vector<long long> h(kTrace);
+      GCRL_CUDA(cudaStreamSynchronize(st));
+      GCRL_CUDA(cudaMemcpy(h.data(), a.trace, kTrace * sizeof(long long), cudaMemcpyDeviceToHost));
+      cudaFree(a.trace);
+      if (FILE *f = fopen(tr, "wb")) {
+        fwrite(h.data(), sizeof(long long), kTrace, f);
+        fclose(f);
+      }
+    }
+    return;
+  }
   const CUtensorMap tmA = make_map(X, M, K, ldx, BM);
   const CUtensorMap tmB = make_map(W, N, K, ldw, BN);          // W_lo given: W holds the TF32 hi halves
   CUtensorMap tmB2;

@@ -87,3 +87,37 @@ def test_tc_wgrad_matches_float64(M, N, K):
     assert float(W[:, K:].abs().max()) == 0.0
     wb = dz.double().sum(0)
     assert ((pb[:S, :N].double().sum(0) - wb).abs().max() / wb.abs().max()).item() <= 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(65536, 256, 256), (16384, 256, 256), (20000, 256, 256), (16385, 256, 256),
+                                   (30000, 512, 512), (14500, 256, 24), (1000, 256, 256), (4096, 512, 512)])
+def test_tc_dense_presplit_weights_match_float64(M, N, K):
+    """The agent's large-batch path: weights pre-split into TF32 hi / lo halves (gcrl_split_tf32), activations split
+    in the kernel.  Large M with N % 256 == 0 runs on CTA pairs (cta_group::2: 256 x 256 tiles, every SM stages half
+    of the weight tile), the rest on the single-CTA kernel; same tolerance as the un-split entry point (1e-5 max-norm
+    relative), ragged row tails and both N tiles covered."""
+    import torch
+    from gcrl_b200._lib import check, lib, vp
+    torch.manual_seed(M + N + K)
+    x = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") / K ** 0.5
+    b = torch.randn(N, device="cuda")
+    act = torch.randn(M, N, device="cuda")
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    st = vp(torch.cuda.current_stream().cuda_stream)
+    check(lib.gcrl_split_tf32(0, vp(w.data_ptr()), vp(hi.data_ptr()), vp(lo.data_ptr()), w.numel(), st))
+    assert torch.equal((hi.double() + lo.double()).float(), w) or float((hi + lo - w).abs().max()) <= 2e-7 * float(w.abs().max())
+    ref = x.double() @ w.double().T
+    wants = {0: torch.nn.functional.leaky_relu(ref + b.double(), 0.01),
+             1: ref * torch.where(act > 0, 1.0, 0.01).double(),
+             2: ref + b.double()}
+    for mode, want in wants.items():
+        y = torch.full((M, N), float("nan"), device="cuda")
+        check(lib.gcrl_dense_layer_presplit(0, mode, M, N, K, vp(x.data_ptr()), K, vp(hi.data_ptr()), vp(lo.data_ptr()), K,
+                                            vp(b.data_ptr()) if mode != 1 else None,
+                                            vp(act.data_ptr()) if mode == 1 else None, N if mode == 1 else 0,
+                                            vp(y.data_ptr()), N, st))
+        torch.cuda.synchronize()
+        assert torch.isfinite(y).all(), mode
+        err = ((y.double() - want).abs().max() / want.abs().max()).item()
+        assert err <= 1e-5, (mode, err)
