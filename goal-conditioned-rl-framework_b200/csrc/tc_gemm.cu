@@ -202,8 +202,10 @@ struct TcArgs {
   // the batch is the reduction; n_tiles = ceil(N / 128), k_tiles = ceil(K / BN); M rows in nslabs slabs
   int kind, rows_per_slab, nslabs, k_tiles;
   long long split_stride;
+  int full_items;                // pair kernel: tiles taken whole; the rest are split into two 256 x 128 halves
   long long *trace;              // GCRL_TC_TRACE: per-stage timestamps of the first CTA pair (pair kernel only)
-  int dbg;                       // timing experiments only (GCRL_TC_DBG): 1 skip split, 2 skip stores, 4 one MMA per k step
+  int dbg;                       // timing experiments only (GCRL_TC_DBG): 1 skip split, 2 skip stores, 4 one MMA per k
+                                 // step, 64 no epilogue, 128 epilogue stops after the TMEM load (wrong results)
 };
 
 template <int BN>
@@ -557,25 +559,44 @@ tc_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int total_tiles = a.m_tiles * a.n_tiles;       // m_tiles: 256-row tiles
   const int nk = (a.K + BKF - 1) / BKF;
+  // Work items: 256 x 256 tiles (m_tiles counts 256-row tiles); when the last round would leave at least half of the
+  // pairs idle, its tiles are cut into two 256 x 128 halves taken by different pairs (MMA N = 128, 64 weight rows per
+  // CTA), so the round costs about half a tile time: 256 tiles on 74 pairs take 3.5 rounds instead of 4.
+  const int total_items = a.full_items + 2 * (a.m_tiles * a.n_tiles - a.full_items);
+  struct Item { int m0, n0, ncols; };
+  auto decode = [&](int w) {
+    int t = w, half = 0, nc = BN;
+    if (w >= a.full_items) {
+      const int h = w - a.full_items;
+      t = a.full_items + (h >> 1); half = h & 1; nc = BN / 2;
+    }
+    Item it;
+    it.m0 = (t / a.n_tiles) * 256 + int(rank) * BM;
+    it.n0 = (t % a.n_tiles) * BN + half * (BN / 2);
+    it.ncols = nc;
+    return it;
+  };
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs: own activation rows, own half of the weight rows) =====
     uint32_t it = 0;
-    for (int t = pair; t < total_tiles; t += npairs) {
-      const int m0 = (t / a.n_tiles) * 256 + int(rank) * BM;
-      const int nb = (t % a.n_tiles) * BN + int(rank) * 128;
+    for (int w = pair; w < total_items; w += npairs) {
+      const Item wi = decode(w);
+      const int rows_b = wi.ncols / 2;                       // this CTA's share of the weight rows: 128 or 64
+      const int nb = wi.n0 + int(rank) * rows_b;
       for (int kb = 0; kb < nk; ++kb, ++it) {
         const int s = it % STAGES2;
         mbar_wait(empty(s), ((it / STAGES2) & 1) ^ 1);
         const uint32_t st = base + s * S::kStage;
         if (elect_one()) {
           mark(0, it);
-          mbar_expect_tx(full(s), S::kA + 2 * S::kBh);
-          tma_load_2d(st, &tmA, full(s), kb * BKF, m0);
-          tma_load_2d(st + 2 * S::kA, &tmBhi, full(s), kb * BKF, nb);
-          tma_load_2d(st + 2 * S::kA + S::kBh, &tmBlo, full(s), kb * BKF, nb);
+          mbar_expect_tx(full(s), S::kA + 2 * rows_b * ROWB);
+          tma_load_2d(st, &tmA, full(s), kb * BKF, wi.m0);
+          for (int r = 0; r < rows_b; r += 64) {             // weight maps: boxes of 64 rows
+            tma_load_2d(st + 2 * S::kA + r * ROWB, &tmBhi, full(s), kb * BKF, nb + r);
+            tma_load_2d(st + 2 * S::kA + S::kBh + r * ROWB, &tmBlo, full(s), kb * BKF, nb + r);
+          }
         }
         __syncwarp();
       }
@@ -583,9 +604,10 @@ tc_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   } else if (warp == 1) {
     if (leader) {
       // ===== MMA issuer (leader only): M = 256 over the pair, N = 256 =====
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(256 >> 4) << 24);
+      const uint32_t idesc_m = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(256 >> 4) << 24);
       uint32_t it = 0, tile_it = 0;
-      for (int t = pair; t < total_tiles; t += npairs, ++tile_it) {
+      for (int w = pair; w < total_items; w += npairs, ++tile_it) {
+        const uint32_t idesc = idesc_m | (uint32_t(decode(w).ncols >> 3) << 17);
         const int as = tile_it & 1;
         mbar_wait(tempty(as), ((tile_it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -620,7 +642,7 @@ tc_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     } else {
       // ===== relay (peer only): "my stage is split" -> the leader's peer_ready =====
       uint32_t it = 0;
-      for (int t = pair; t < total_tiles; t += npairs)
+      for (int w = pair; w < total_items; w += npairs)
         for (int kb = 0; kb < nk; ++kb, ++it) {
           const int s = it % STAGES2;
           mbar_wait(split_done(s), (it / STAGES2) & 1);
@@ -635,8 +657,9 @@ tc_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ===== epilogue (both CTAs): own 128 rows, all 256 columns =====
     const int q = warp & 3;
     uint32_t tile_it = 0;
-    for (int t = pair; t < total_tiles; t += npairs, ++tile_it) {
-      const int m0 = (t / a.n_tiles) * 256 + int(rank) * BM, n0 = (t % a.n_tiles) * BN;
+    for (int w = pair; w < total_items; w += npairs, ++tile_it) {
+      const Item wi = decode(w);
+      const int m0 = wi.m0, n0 = wi.n0;
       const int as = tile_it & 1;
       if (lane == 0) mbar_wait(tfull(as), (tile_it >> 1) & 1);
       __syncwarp();
@@ -645,7 +668,7 @@ tc_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN);
       const uint32_t stg = stage_base + uint32_t(q) * (32 * kStgLd * 4);
 #pragma unroll 1
-      for (int c = 0; c < ((a.dbg & 64) ? 0 : BN); c += 32) {
+      for (int c = 0; c < ((a.dbg & 64) ? 0 : wi.ncols); c += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + uint32_t(c), v);
         if (a.dbg & 128) {
@@ -671,7 +694,7 @@ tc_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ===== hi / lo splitter (both CTAs): the activation tile only =====
     const int tid = threadIdx.x - 6 * 32;
     uint32_t it = 0;
-    for (int t = pair; t < total_tiles; t += npairs) {
+    for (int w = pair; w < total_items; w += npairs) {
       for (int kb = 0; kb < nk; ++kb, ++it) {
         const int s = it % STAGES2;
         if (lane == 0) mbar_wait(full(s), (it / STAGES2) & 1);
@@ -823,7 +846,6 @@ int pair_capacity() {
     const char *e = getenv("GCRL_TC_PAIR");
     if (!(e && e[0] == '0')) {
       GCRL_CUDA(cudaFuncSetAttribute(tc_dense_pair_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem2<6>::kBytes));
-      GCRL_CUDA(cudaFuncSetAttribute(tc_dense_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem2<3>::kBytes));
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(unsigned(sm_count() & ~1));
       cfg.blockDim = dim3(kTcThreads);
@@ -884,9 +906,12 @@ void launch_tc_dense(const float *X, int ldx, const float *W, int ldw, const flo
     a.m_tiles = (M + 255) / 256;
     a.n_tiles = N / 256;
     const CUtensorMap tmA = make_map(X, M, K, ldx, BM);
-    const CUtensorMap tmBhi = make_map(W, N, K, ldw, 128);
-    const CUtensorMap tmBlo = make_map(W_lo, N, K, ldw, 128);
-    const int grid = 2 * std::min(pair_tiles, pairs);
+    const CUtensorMap tmBhi = make_map(W, N, K, ldw, 64);
+    const CUtensorMap tmBlo = make_map(W_lo, N, K, ldw, 64);
+    const int used = std::min(pair_tiles, pairs);
+    const int grid = 2 * used;
+    const int rest = pair_tiles % used;                      // tiles of the last, partly filled round
+    a.full_items = (rest > 0 && 2 * rest <= used && !getenv("GCRL_TC_NO_HALVES")) ? pair_tiles - rest : pair_tiles;
     if (getenv("GCRL_TC_VERBOSE")) fprintf(stderr, "[tc] pair kernel: %d pairs resident, %d tiles, grid %d\n", pairs, pair_tiles, grid);
     const char *tr = getenv("GCRL_TC_TRACE");
     constexpr size_t kTrace = 2 * 8 * 64;
@@ -894,9 +919,7 @@ void launch_tc_dense(const float *X, int ldx, const float *W, int ldw, const flo
       GCRL_CUDA(cudaMalloc(&a.trace, kTrace * sizeof(long long)));
       GCRL_CUDA(cudaMemsetAsync(a.trace, 0, kTrace * sizeof(long long), st));
     }
-    const char *se = getenv("GCRL_TC_STAGES2");
-    if (se && se[0] == '3') tc_dense_pair_kernel<3><<<grid, kTcThreads, TcSmem2<3>::kBytes, st>>>(tmA, tmBhi, tmBlo, a);
-    else tc_dense_pair_kernel<6><<<grid, kTcThreads, TcSmem2<6>::kBytes, st>>>(tmA, tmBhi, tmBlo, a);
+    tc_dense_pair_kernel<6><<<grid, kTcThreads, TcSmem2<6>::kBytes, st>>>(tmA, tmBhi, tmBlo, a);
     GCRL_LAUNCHED();
     if (tr != nullptr) {          // debug only: synchronous dump, [cta 0..1][role 0..7][stage use 0..63] nanoseconds
       std::vector<long long> h(kTrace);
