@@ -37,6 +37,7 @@ constexpr int STAGES = 4;
 constexpr int kSplitWarps = 8;
 constexpr int kSplitThreads = kSplitWarps * 32;
 constexpr int kTcThreads = (6 + kSplitWarps) * 32;
+constexpr int kPairThreads = kTcThreads + 4 * 32;   // pair kernel: a second set of 4 epilogue warps (14-17)
 constexpr int kStgLd = 36;         // epilogue staging row stride in floats (16-byte aligned, conflict-free)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -468,7 +469,7 @@ struct TcSmem2 {
   static constexpr int kA = BM * ROWB;                       // 128 activation rows
   static constexpr int kBh = 128 * ROWB;                     // this CTA's half of the 256 weight rows
   static constexpr int kStage = 2 * kA + 2 * kBh;            // A_hi | A_lo | B_hi | B_lo
-  static constexpr int kBytes = STAGES2 * kStage + 1024 + 512 + 4 * 32 * kStgLd * 4;
+  static constexpr int kBytes = STAGES2 * kStage + 1024 + 512 + 8 * 32 * kStgLd * 4;       // 8 epilogue warps
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -507,7 +508,7 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {      // arrives
 }
 
 template <int STAGES2>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 tc_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                      const __grid_constant__ CUtensorMap tmBlo, TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -544,7 +545,7 @@ tc_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull(s), 1);
-      mbar_init(tempty(s), 8);                         // 4 epilogue warps in each CTA of the pair
+      mbar_init(tempty(s), 16);                        // 8 epilogue warps in each CTA of the pair
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
@@ -653,9 +654,11 @@ tc_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           __syncwarp();
         }
     }
-  } else if (warp < 6) {
-    // ===== epilogue (both CTAs): own 128 rows, all 256 columns =====
-    const int q = warp & 3;
+  } else if (warp < 6 || warp >= 14) {
+    // ===== epilogue (both CTAs): own 128 rows; warps 2-5 take the first half of the columns, warps 14-17 the second
+    // (a warp can only read the TMEM lane quarter warp % 4).  With 4 warps the epilogue of a tile (10 us with the
+    // mainloop running beside it) was slower than its MMAs (8 us) and set the pace =====
+    const int q = warp & 3, part = warp >= 14 ? 1 : 0;
     uint32_t tile_it = 0;
     for (int w = pair; w < total_items; w += npairs, ++tile_it) {
       const Item wi = decode(w);
@@ -664,11 +667,12 @@ tc_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (lane == 0) mbar_wait(tfull(as), (tile_it >> 1) & 1);
       __syncwarp();
       tc_fence_after();
-      if (q == 0 && lane == 0) mark(6, tile_it);
+      if (q == 0 && part == 0 && lane == 0) mark(6, tile_it);
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN);
-      const uint32_t stg = stage_base + uint32_t(q) * (32 * kStgLd * 4);
+      const uint32_t stg = stage_base + uint32_t(q + 4 * part) * (32 * kStgLd * 4);
+      const int c_lo = part * (wi.ncols / 2), c_hi = c_lo + wi.ncols / 2;
 #pragma unroll 1
-      for (int c = 0; c < ((a.dbg & 64) ? 0 : wi.ncols); c += 32) {
+      for (int c = c_lo; c < ((a.dbg & 64) ? 0 : c_hi); c += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + uint32_t(c), v);
         if (a.dbg & 128) {
@@ -688,7 +692,7 @@ tc_dense_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(map_to_cta(tempty(as), 0));
-      if (q == 0 && lane == 0) mark(7, tile_it);
+      if (q == 0 && part == 0 && lane == 0) mark(7, tile_it);
     }
   } else {
     // ===== hi / lo splitter (both CTAs): the activation tile only =====
@@ -845,17 +849,17 @@ int pair_capacity() {
     pairs = 0;
     const char *e = getenv("GCRL_TC_PAIR");
     if (!(e && e[0] == '0')) {
-      GCRL_CUDA(cudaFuncSetAttribute(tc_dense_pair_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem2<6>::kBytes));
+      GCRL_CUDA(cudaFuncSetAttribute(tc_dense_pair_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem2<5>::kBytes));
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(unsigned(sm_count() & ~1));
-      cfg.blockDim = dim3(kTcThreads);
-      cfg.dynamicSmemBytes = TcSmem2<6>::kBytes;
+      cfg.blockDim = dim3(kPairThreads);
+      cfg.dynamicSmemBytes = TcSmem2<5>::kBytes;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, tc_dense_pair_kernel<6>, &cfg) == cudaSuccess && n > 0)
+      if (cudaOccupancyMaxActiveClusters(&n, tc_dense_pair_kernel<5>, &cfg) == cudaSuccess && n > 0)
         pairs = std::min(n, sm_count() / 2);
       else
         cudaGetLastError();
@@ -919,7 +923,7 @@ void launch_tc_dense(const float *X, int ldx, const float *W, int ldw, const flo
       GCRL_CUDA(cudaMalloc(&a.trace, kTrace * sizeof(long long)));
       GCRL_CUDA(cudaMemsetAsync(a.trace, 0, kTrace * sizeof(long long), st));
     }
-    tc_dense_pair_kernel<6><<<grid, kTcThreads, TcSmem2<6>::kBytes, st>>>(tmA, tmBhi, tmBlo, a);
+    tc_dense_pair_kernel<5><<<grid, kPairThreads, TcSmem2<5>::kBytes, st>>>(tmA, tmBhi, tmBlo, a);
     GCRL_LAUNCHED();
     if (tr != nullptr) {          // debug only: synchronous dump, [cta 0..1][role 0..7][stage use 0..63] nanoseconds
       std::vector<long long> h(kTrace);

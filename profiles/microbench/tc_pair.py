@@ -8,7 +8,7 @@ import torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "goal-conditioned-rl-framework_b200"))
 from gcrl_b200._lib import check, lib, vp  # noqa: E402
 
-M, N, K = int(os.environ.get("TC_M", 65536)), 256, 256
+M, N, K = int(os.environ.get("TC_M", 65536)), 256, int(os.environ.get("TC_K", 256))
 torch.manual_seed(0)
 x = torch.randn(M, K, device="cuda")
 w = torch.randn(N, K, device="cuda") / 16
@@ -47,7 +47,7 @@ def timed(pair, dbg):
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
     ts.sort()
-    print(f"flush={FLUSH} pair={pair} dbg={dbg:3d} M={M}: median {ts[len(ts) // 2]:.1f} us, min {ts[0]:.1f} us", flush=True)
+    print(f"flush={FLUSH} pair={pair} dbg={dbg:3d} M={M} K={K}: median {ts[len(ts) // 2]:.1f} us, min {ts[0]:.1f} us", flush=True)
 
 
 for pair in [int(v) for v in os.environ.get("TC_PAIRS", "1,0").split(",")]:
