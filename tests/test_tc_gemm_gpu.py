@@ -90,11 +90,13 @@ def test_tc_wgrad_matches_float64(M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K", [(65536, 256, 256), (16384, 256, 256), (20000, 256, 256), (16385, 256, 256),
-                                   (30000, 512, 512), (14500, 256, 24), (1000, 256, 256), (4096, 512, 512)])
+                                   (30000, 512, 512), (14500, 256, 24), (1000, 256, 256), (4096, 512, 512),
+                                   (8192, 256, 256), (8000, 256, 32)])
 def test_tc_dense_presplit_weights_match_float64(M, N, K):
     """The agent's large-batch path: weights pre-split into TF32 hi / lo halves (gcrl_split_tf32), activations split
     in the kernel.  Large M with N % 256 == 0 runs on CTA pairs (cta_group::2: 256 x 256 tiles, every SM stages half
-    of the weight tile), the rest on the single-CTA kernel; same tolerance as the un-split entry point (1e-5 max-norm
+    of the weight tile; a partly filled last round as two 256 x 128 halves per tile),
+    the rest on the single-CTA kernel; same tolerance as the un-split entry point (1e-5 max-norm
     relative), ragged row tails and both N tiles covered."""
     import torch
     from gcrl_b200._lib import check, lib, vp
