@@ -991,13 +991,14 @@ def gpu_main(args):
                     ach = fl / (ms_k * 1e-3) / 1e12
                     rooflines[f"{name}_M{Mt}_H{Hh}"] = {
                         "bound": "tensor", "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
-                        "traffic": (83.8e6 if (engine >= 1 and Hh == 256) else None),   # ncu (round 1): 67.4 MB read + 16.4 MB written
+                        "traffic": (83.8e6 if (engine >= 1 and Hh == 256) else None),   # ncu: 67.4 MB read + 16.4 MB written (r01e; the pair kernel: 67.7 + 16.0, gpurun tc_pair_ncu)
                         "ms_per_launch": ms_k, "algorithmic_flops_per_launch": fl,
                         "tensor_pipe_tflops": (3.0 * ach if engine >= 1 else None),
                         "tensor_pipe_frac_of_tf32_rate": (3.0 * ach / (0.5 * bf16_peak) if engine >= 1 else None),
                         "note": ("tcgen05 kind::tf32, 3 MMAs per product (hi/lo split) for fp32 accuracy: tensor-pipe "
                                  "work is 3x the algorithmic flops; the TF32 rate is half the measured bf16 peak; " +
-                                 ("weights pre-split once per optimiser step (the agents' path)" if engine == 2 else
+                                 ("weights pre-split once per optimiser step (the agents' path): at this size the CTA-pair "
+                                  "kernel (cta_group::2, 256 x 256 tiles, half the weight tile per SM)" if engine == 2 else
                                   "both operands split in shared memory (round-1 scheme, for comparison)") if engine >= 1 else
                                  "fp32 FFMA tiles (the precision-0 path), for comparison")}
                 except Exception as e:   # noqa: BLE001
