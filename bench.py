@@ -342,7 +342,8 @@ def dp_parity(args, local, rank, world, dp_mode, updates=4):
     """Outside every timed region: `updates` DDPG updates on fixed per-rank batches through the data-parallel
     path that is being benchmarked; every rank hashes all four networks (replicas must be bit-identical); rank 0
     repeats the run with ONE agent (fp32 FFMA engine) on the concatenated batches and reports the largest
-    deviation, relative to the largest weight of the tensor (SURVEY 8e parity rule)."""
+    deviation, relative to the largest weight of the tensor, and whether every tensor is inside the tolerance the
+    parity tests use for post-update weights (SURVEY 8e parity rule)."""
     import hashlib
 
     import torch
@@ -388,10 +389,23 @@ def dp_parity(args, local, rank, world, dp_mode, updates=4):
         for i, st in enumerate(steps):
             cat = [np.concatenate([batch_of(r, i)[j] for r in range(world)]) for j in range(5)]
             one.update(st, batch=tuple(torch.from_numpy(x).cuda(local) for x in cat))
-        rel = max(float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-30)) for a, b in zip(mine, nets(one)))
+        ref = nets(one)
+        rel = max(float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-30)) for a, b in zip(mine, ref))
         out["max_rel_vs_concat"] = rel
-        out["tolerance"] = 1e-4
-        out["ok"] = bool(out["replicas_identical"] and rel < 1e-4)
+        # the parity tests' own rule (tests/helpers.py::weights_close): per tensor |w - ref| <= 1e-5 max|ref| + 5e-3 lr n
+        # for all but 2e-4 of the elements, those inside Adam's hard bound 2 lr n -- restated here so that the bench
+        # does not import the test tree; the old flat 1e-4 on max_rel is kept in the line for comparison
+        lr, worst_used, within = 1e-3, 0.0, True
+        for a, b in zip(mine, ref):
+            err = np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64))
+            tol = 1e-5 * float(np.max(np.abs(b))) + 5e-3 * lr * updates
+            worst_used = max(worst_used, float(np.max(err)) / tol)
+            within = within and float(np.max(err)) <= 2.0 * lr * updates + 1e-5 * float(np.max(np.abs(b))) \
+                and int(np.count_nonzero(err > tol)) <= 2e-4 * err.size
+        out["tolerance"] = "weights_close: 1e-5 max|w| + 5e-3 lr n per tensor (<= 2e-4 of the elements up to Adam's bound 2 lr n)"
+        out["worst_fraction_of_tolerance"] = worst_used
+        out["max_rel_below_1e-4"] = bool(rel < 1e-4)
+        out["ok"] = bool(out["replicas_identical"] and within)
         del one
     del ag
     torch.cuda.synchronize()
