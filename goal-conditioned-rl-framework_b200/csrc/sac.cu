@@ -1095,6 +1095,8 @@ void run_body(gcrl_sac *ag, int B, int flags, int mask, cudaStream_t st) {
 // Replay (or capture on first use) the CUDA graph of (B, flags, phase mask): ~170 launches per TQC update
 // become one graph launch; everything that varies per step travels through device scalars.
 void run_phases(gcrl_sac *ag, int B, int flags, int mask, cudaStream_t st) {
+  // (a graph captured before gcrl_sac_set_sync_bn would otherwise replay with local statistics)
+  GCRL_REQUIRE(ag->sync_world == 0, "a sync-BN agent trains through gcrl_sac_update_segment only");
   ag->per_on = (flags & 8) != 0;
   if (!ag->use_graphs) {
     run_body(ag, B, flags, mask, st);

@@ -456,11 +456,12 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // Two CTAs on the two SMs of a TPC compute one 256-row x 256-column tile: each CTA stages ITS 128 activation rows
 // (TMA -> in-smem hi / lo split, as above) and only ITS HALF (128 of the 256 rows) of the pre-split weight tile; the
 // tensor cores of the pair read both halves.  Per 16-wide K tile and SM that is 24 KB of TMA writes instead of 40 and
-// 48 KB of operand reads instead of 72 -- the shared-memory port (128 B/clk) is what bounds the single-CTA kernel
-// (DESIGN.md 4).  The leader (cluster rank 0) issues every MMA; accumulators: rows 0-127 in the leader's TMEM,
-// 128-255 in the peer's, two stages of 256 columns each.
+// 48 KB of operand reads instead of 72 through the shared-memory port (128 B/clk).  The leader (cluster
+// rank 0) issues every MMA; accumulators: rows 0-127 in the leader's TMEM, 128-255 in the peer's, two stages of 256
+// columns each.  18 warps: 0 TMA producer, 1 MMA issuer (leader) / relay (peer), 2-5 and 14-17 epilogue (two warps
+// per TMEM lane quarter, half of the columns each), 6-13 hi / lo splitter.
 //   full[s]        TMA -> splitter                (per CTA)
-//   split_done[s]  splitter -> MMA / relay        (per CTA, all splitter threads)
+//   split_done[s]  splitter -> MMA / relay        (per CTA, one arrival per splitter warp)
 //   peer_ready[s]  the peer's relay thread (its otherwise idle MMA warp) -> leader: "my stage s is split"
 //   empty[s]       MMA commit, multicast to both CTAs -> TMA
 //   tfull[a]       MMA commit, multicast -> epilogue of both CTAs;  tempty[a]  both epilogues -> leader MMA
