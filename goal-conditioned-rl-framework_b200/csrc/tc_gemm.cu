@@ -203,6 +203,8 @@ struct TcArgs {
   // the batch is the reduction; n_tiles = ceil(N / 128), k_tiles = ceil(K / BN); M rows in nslabs slabs
   int kind, rows_per_slab, nslabs, k_tiles;
   long long split_stride;
+  float *colsum;                 // kind 1: bias-gradient partials pB[slab][n] = column sums of the slab's dZ rows, taken
+  long long colsum_stride;       // by the splitter warps from the tiles they split anyway (nullptr: separate kernel)
   int full_items;                // pair kernel: tiles taken whole; the rest are split into two 256 x 128 halves
   long long *trace;              // GCRL_TC_TRACE: per-stage timestamps of the first CTA pair (pair kernel only)
   int dbg;                       // timing experiments only (GCRL_TC_DBG): 1 skip split, 2 skip stores, 4 one MMA per k
@@ -213,7 +215,8 @@ template <int BN>
 struct TcSmem {
   static constexpr int kA = BM * ROWB, kB = BN * ROWB;
   static constexpr int kStage = 2 * kA + 2 * kB;            // A_hi | A_lo | B_hi | B_lo
-  static constexpr int kBytes = STAGES * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/ + 4 * 32 * kStgLd * 4;
+  static constexpr int kColsum = 16 * BM * 4;               // kind 1: [16 row lanes][128 features] column-sum scratch
+  static constexpr int kBytes = STAGES * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/ + 4 * 32 * kStgLd * 4 + kColsum;
 };
 
 // PRESPLIT: the B operand (the layer's weights) arrives already split into TF32 hi / lo halves (two tensors, kept
@@ -395,8 +398,17 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===== hi / lo splitter =====
     const int tid = threadIdx.x - 6 * 32;
     uint32_t it = 0;
+    // kind 1: the dZ operand passes through these threads' registers, so the bias gradient (column sums of dZ over
+    // the slab's rows) is taken here instead of by a second pass over dZ (6 x 20 us per B = 65 536 update).  A thread's
+    // two dZ chunks sit at the same place of every stage: box = 32 features, 16 batch rows of 128 bytes, the 32-byte
+    // units of a row XOR-swizzled with (row & 3) (SWIZZLE_128B_ATOM_32B).  Only the tile of the first k block writes.
+    const bool colsum_on = wg && a.colsum != nullptr;
+    const uint32_t cs_scratch = stage_base + 4 * 32 * kStgLd * 4;
+    float cs[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int nk = decode(t).nk;
+      const Tile tile = decode(t);
+      const int nk = tile.nk;
+      const bool cs_tile = colsum_on && tile.n0 == 0;
       for (int kb = 0; kb < nk; ++kb, ++it) {
         const int s = it % STAGES;
         mbar_wait(full(s), (it / STAGES) & 1);
@@ -419,6 +431,12 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                            : "=f"(x[u][0]), "=f"(x[u][1]), "=f"(x[u][2]), "=f"(x[u][3])
                            : "r"(hi_addr[u]));
           }
+          if (cs_tile) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) cs[u][e] += x[u][e];
+          }
 #pragma unroll
           for (int u = 0; u < kPer; ++u) {
             const int c = tid + u * kSplitThreads;
@@ -440,6 +458,29 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
         mbar_arrive(ready(s));
+      }
+      if (cs_tile) {                                   // uniform over the splitter warps
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int c = tid + u * kSplitThreads, cc = c & 127, row = cc >> 3;
+          const int f = (c >> 7) * 32 + ((((cc >> 1) & 3) ^ (row & 3)) << 3) + (cc & 1) * 4;
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cs_scratch + uint32_t(row * BM + f) * 4),
+                       "f"(cs[u][0]), "f"(cs[u][1]), "f"(cs[u][2]), "f"(cs[u][3])
+                       : "memory");
+          cs[u][0] = cs[u][1] = cs[u][2] = cs[u][3] = 0.f;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kSplitThreads) : "memory");
+        if (tid < BM && tile.m0 + tid < a.N) {
+          float sum = 0.f;
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {
+            float v;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(cs_scratch + uint32_t(r * BM + tid) * 4));
+            sum += v;
+          }
+          a.colsum[(long long)tile.slab * a.colsum_stride + tile.m0 + tid] = sum;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kSplitThreads) : "memory");
       }
     }
   }
@@ -993,12 +1034,15 @@ int launch_tc_wgrad(const float *dZ, int lddz, const float *X, int ldx, float *p
   slabs = (M + rows - 1) / rows;
   a.rows_per_slab = rows; a.nslabs = slabs; a.split_stride = w_split_stride;
   if (const char *e = getenv("GCRL_TC_DBG")) a.dbg = atoi(e);
+  // the bias-gradient partials ride on the splitter warps (unless a timing switch removes the split work)
+  const bool fused_colsum = pB != nullptr && !(a.dbg & 1) && !getenv("GCRL_TC_NO_FUSED_COLSUM");
+  if (fused_colsum) { a.colsum = pB; a.colsum_stride = b_split_stride; }
   const CUtensorMap tmA = make_map(dZ, M, N, lddz, 16, 32, true);
   const CUtensorMap tmB = make_map(X, M, K, ldx, 16, 32, true);
   if (BN == 64) launch_bn<64>(tmA, tmB, nullptr, a, st);
   else if (BN == 128) launch_bn<128>(tmA, tmB, nullptr, a, st);
   else launch_bn<256>(tmA, tmB, nullptr, a, st);
-  if (pB != nullptr) {
+  if (pB != nullptr && !fused_colsum) {
     colsum_partials_kernel<<<dim3(slabs, (N + 31) / 32), 256, 0, st>>>(dZ, lddz, M, N, rows, pB, b_split_stride);
     GCRL_LAUNCHED();
   }
