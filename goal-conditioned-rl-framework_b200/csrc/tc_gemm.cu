@@ -143,7 +143,8 @@ __device__ __forceinline__ uint32_t rna_tf32(float x) {
 // store: with the loads, the arithmetic and the store of one row group chained through the same four registers the
 // eight groups ran back to back at ~300 clk each, and the epilogue (10 us per 128 x 256 tile), not the MMAs (8 us),
 // set the pace of the whole kernel (profiles/README.md, timeline of the CTA-pair kernel).
-//   mode 0: leaky(acc + bias)   1: acc * leaky'(act)   2: acc + bias   3: acc
+//   mode 0: leaky(acc + bias)   1: acc * leaky'(act)   2: acc + bias   3: acc   4: out + acc (the same lane of the
+//   same CTA stored `out` for an earlier slab of this weight-gradient tile)
 __device__ __forceinline__ void epilogue_store32(uint32_t stg, int lane, int row0, int col0, int rows_valid,
                                                  int cols_valid, int mode, const float *__restrict__ bias,
                                                  const float *__restrict__ act, int ldact, float *__restrict__ out,
@@ -171,6 +172,15 @@ __device__ __forceinline__ void epilogue_store32(uint32_t stg, int lane, int row
       x[r8].y = h[r8].y > 0.f ? x[r8].y : x[r8].y * kLeakySlope;
       x[r8].z = h[r8].z > 0.f ? x[r8].z : x[r8].z * kLeakySlope;
       x[r8].w = h[r8].w > 0.f ? x[r8].w : x[r8].w * kLeakySlope;
+    }
+  } else if (mode == 4) {
+#pragma unroll
+    for (int r8 = 0; r8 < 8; ++r8) {
+      const int row = row0 + r8 * 4 + sub_r;
+      if (row < rows_valid) {
+        const float4 o = *reinterpret_cast<const float4 *>(out + size_t(row) * ldo + col);
+        x[r8].x += o.x; x[r8].y += o.y; x[r8].z += o.z; x[r8].w += o.w;
+      }
     }
   } else if (mode != 3) {
     const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + col));
@@ -203,6 +213,7 @@ struct TcArgs {
   // the batch is the reduction; n_tiles = ceil(N / 128), k_tiles = ceil(K / BN); M rows in nslabs slabs
   int kind, rows_per_slab, nslabs, k_tiles;
   long long split_stride;
+  int acc_slabs;                 // kind 1: a CTA adds the later slabs of its (n, k) block onto the first one it wrote
   float *colsum;                 // kind 1: bias-gradient partials pB[slab][n] = column sums of the slab's dZ rows, taken
   long long colsum_stride;       // by the splitter warps from the tiles they split anyway (nullptr: separate kernel)
   int full_items;                // pair kernel: tiles taken whole; the rest are split into two 256 x 128 halves
@@ -267,14 +278,19 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int total_tiles = wg ? a.nslabs * a.n_tiles * a.k_tiles : a.m_tiles * a.n_tiles;
   // tile decode.  dense: (m block, n block), K tiles of BKF columns.  wgrad: (slab, n block, k block),
   // "K tiles" = 16 batch rows each.
-  struct Tile { int m0, n0, nk, slab; };
+  struct Tile { int m0, n0, nk, slab, out_slab, acc; };
   auto decode = [&](int t) {
     Tile ti;
     if (!wg) {
       ti.m0 = (t / a.n_tiles) * BM; ti.n0 = (t % a.n_tiles) * BN; ti.nk = (a.K + BKF - 1) / BKF; ti.slab = 0;
+      ti.out_slab = 0; ti.acc = 0;
     } else {
       const int per = a.n_tiles * a.k_tiles;
       ti.slab = t / per;
+      // the grid is a multiple of `per`: the tiles a CTA visits are the same (n, k) block of different slabs, and it
+      // adds the later ones onto the first (fewer partial slabs for reduce_grads to read)
+      ti.out_slab = a.acc_slabs ? int(t % gridDim.x) / per : ti.slab;
+      ti.acc = (a.acc_slabs && t >= int(gridDim.x)) ? 1 : 0;
       const int rem = t - ti.slab * per;
       ti.m0 = (rem / a.k_tiles) * BM;            // first output row (n index) of the tile
       ti.n0 = (rem % a.k_tiles) * BN;            // first output column (k index)
@@ -363,7 +379,8 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const Tile ti = decode(t);
       const int m0 = ti.m0, n0 = ti.n0;
       const int rows_valid = wg ? a.N : a.M, cols_valid = wg ? a.ldo : a.N;
-      float *const obase = a.out + (wg ? size_t(ti.slab) * size_t(a.split_stride) : size_t(0));
+      float *const obase = a.out + (wg ? size_t(ti.out_slab) * size_t(a.split_stride) : size_t(0));
+      const int emode = (wg && ti.acc) ? 4 : a.mode;
       const int as = tile_it & 1;
       mbar_wait(tfull(as), (tile_it >> 1) & 1);
       tc_fence_after();
@@ -387,7 +404,7 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                        : "memory");
         __syncwarp();
         if (!(a.dbg & 2))
-          epilogue_store32(stg, lane, m0 + q * 32, n0 + c, rows_valid, cols_valid, a.mode, a.bias, a.act, a.ldact, obase,
+          epilogue_store32(stg, lane, m0 + q * 32, n0 + c, rows_valid, cols_valid, emode, a.bias, a.act, a.ldact, obase,
                            a.ldo);
       }
       tc_fence_before();
@@ -478,7 +495,8 @@ tc_dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(cs_scratch + uint32_t(r * BM + tid) * 4));
             sum += v;
           }
-          a.colsum[(long long)tile.slab * a.colsum_stride + tile.m0 + tid] = sum;
+          float *const dst = a.colsum + (long long)tile.out_slab * a.colsum_stride + tile.m0 + tid;
+          *dst = tile.acc ? *dst + sum : sum;            // same thread wrote it for the earlier slab
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kSplitThreads) : "memory");
       }
@@ -872,10 +890,10 @@ void set_attr() {
 
 template <int BN>
 void launch_bn(const CUtensorMap &tmA, const CUtensorMap &tmB, const CUtensorMap *tmB2, const TcArgs &a,
-               cudaStream_t st) {
+               cudaStream_t st, int grid_wg = 0) {
   set_attr<BN>();
   const int tiles = a.kind == 1 ? a.nslabs * a.n_tiles * a.k_tiles : a.m_tiles * a.n_tiles;
-  const int grid = std::min(tiles, sm_count());
+  const int grid = grid_wg > 0 ? grid_wg : std::min(tiles, sm_count());
   if (tmB2 != nullptr)
     tc_dense_kernel<BN, true><<<grid, kTcThreads, TcSmem<BN>::kBytes, st>>>(tmA, tmB, *tmB2, a);
   else
@@ -1039,14 +1057,24 @@ int launch_tc_wgrad(const float *dZ, int lddz, const float *X, int ldx, float *p
   if (fused_colsum) { a.colsum = pB; a.colsum_stride = b_split_stride; }
   const CUtensorMap tmA = make_map(dZ, M, N, lddz, 16, 32, true);
   const CUtensorMap tmB = make_map(X, M, K, ldx, 16, 32, true);
-  if (BN == 64) launch_bn<64>(tmA, tmB, nullptr, a, st);
-  else if (BN == 128) launch_bn<128>(tmA, tmB, nullptr, a, st);
-  else launch_bn<256>(tmA, tmB, nullptr, a, st);
+  // more tiles than SMs: a grid that is a multiple of the tiles per slab makes every CTA revisit the SAME (n, k) block
+  // in later slabs, and it accumulates them in place -- grid / per partial slabs for reduce_grads instead of `slabs`
+  // (74 instead of 128 at M = 65 536: 102 -> 59 MB per network).  Needs the bias sums in the same kernel.
+  const int tiles = slabs * per;
+  int grid = std::min(tiles, sm_count()), written = slabs;
+  if (tiles > grid && per <= sm_count() && (fused_colsum || pB == nullptr) && !getenv("GCRL_TC_NO_SLAB_ACC")) {
+    grid = (sm_count() / per) * per;
+    a.acc_slabs = 1;
+    written = grid / per;
+  }
+  if (BN == 64) launch_bn<64>(tmA, tmB, nullptr, a, st, grid);
+  else if (BN == 128) launch_bn<128>(tmA, tmB, nullptr, a, st, grid);
+  else launch_bn<256>(tmA, tmB, nullptr, a, st, grid);
   if (pB != nullptr && !fused_colsum) {
     colsum_partials_kernel<<<dim3(slabs, (N + 31) / 32), 256, 0, st>>>(dZ, lddz, M, N, rows, pB, b_split_stride);
     GCRL_LAUNCHED();
   }
-  return slabs;
+  return written;
 }
 
 }  // namespace gcrl
