@@ -297,3 +297,38 @@ class SACOracle:
             alpha_loss = self.alpha_update(logp, step)
             return l1, l2, al, td, qv, g1, g2, ag, alpha_loss
         return l1, l2, td, qv, g1, g2
+
+
+# ---- sync-BN (data parallel): the exchange csrc/sac.cu performs between graph segments, restated ----------------
+# The reference is single-GPU: nn.BatchNorm1d (src/model.py:103-111) normalises over the whole batch, so N ranks on B
+# rows each must equal one rank on the concatenated N * B rows.  These two functions restate what every rank computes
+# from the all-gathered slots (bn_fwd_sync_kernel / bn_bwd_sync_kernel); tests/test_sac_oracle_cpu.py checks them
+# against the single-batch formulas of actor_sample / actor_backward above on the concatenated batch.
+def sync_bn_merge(means, m2s, rows_per_rank):
+    """Chan's parallel variance for equal local batches, ranks merged in order: local (mean_r, M2_r = sum (z - mean_r)^2)
+    -> (mean, biased variance) of the concatenated batch."""
+    means = [np.asarray(m, F32) for m in means]
+    world = len(means)
+    msum = means[0].copy()
+    for m in means[1:]:
+        msum = (msum + m).astype(F32)
+    mu = (msum / F32(world)).astype(F32)
+    m2 = np.zeros_like(mu)
+    for m, q in zip(means, m2s):
+        d = (m - mu).astype(F32)
+        m2 = (m2 + (np.asarray(q, F32) + F32(rows_per_rank) * d * d)).astype(F32)
+    return mu, (m2 / (F32(world) * F32(rows_per_rank))).astype(F32)
+
+
+def sync_bn_backward(dy, xhat, invstd, gamma, s1_all, s2_all, rows_total):
+    """Input gradient of one rank's rows: the column sums (sum dy, sum dy * xhat) are taken over ALL ranks (added in
+    rank order) and n is the global row count; dgamma / dbeta stay the rank's local sums (they are averaged with the
+    flat gradient afterwards)."""
+    s1 = np.asarray(s1_all[0], F32).copy()
+    s2 = np.asarray(s2_all[0], F32).copy()
+    for a, b in zip(s1_all[1:], s2_all[1:]):
+        s1 = (s1 + a).astype(F32)
+        s2 = (s2 + b).astype(F32)
+    n = F32(rows_total)
+    dxhat = (dy * gamma).astype(F32)
+    return (invstd / n * (n * dxhat - s1 * gamma - xhat * (s2 * gamma))).astype(F32)
